@@ -1,0 +1,38 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement of the tntblast v2.77 search hot path.
+ *
+ * Exports the same entry points as oracle/_ref/libtntref.so (see ref_harness.h) with the
+ * prefix orc_ instead of ref_, filling the same records, so tests can run the reference, the
+ * restatement and the CUDA engine on identical inputs.  Never imported by the product. */
+#ifndef TNT_ORACLE_H
+#define TNT_ORACLE_H
+
+#include "ref_harness.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *orc_last_error(void);
+int orc_dump_tables(float T, float na, ref_tables *out);
+long orc_seeds_raw(const uint8_t *codes, uint32_t len, int word_size, const char *oligo,
+	int complement, uint32_t *q_out, uint32_t *t_out, long cap);
+long orc_seeds_unique(const uint8_t *codes, uint32_t len, int word_size, const char *oligo,
+	int plus_strand, uint32_t *q_out, uint32_t *t_out, long cap);
+int orc_align(const char *query, const uint8_t *target, int target_len, float T, float na,
+	float strand_conc, int dangle5, int dangle3, ref_align_out *out);
+int orc_bind_window(const uint8_t *codes, uint32_t len, const char *oligo, int plus_strand,
+	uint32_t query_loc, uint32_t target_loc, float T, float na, float strand_conc,
+	int dangle5, int dangle3, ref_align_out *out);
+long orc_search(const uint8_t *codes, uint32_t len, const char *forward, const char *reverse,
+	const char *probe, int forward_degen, int reverse_degen, int probe_degen,
+	const ref_options *o);
+int orc_get_hits(ref_hit *out, long cap);
+
+/* number of NucCruc alignments (approximate_tm_heterodimer equivalents, cache misses only)
+ * executed by the last orc_search call -- the unit of the "alignments/s" metric */
+long orc_last_alignment_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
