@@ -1,0 +1,191 @@
+/* tntb200 -- B200-native engine for the tntblast search hot path (C ABI).
+ *
+ * Drop-in boundary for ONE path of jgans/thermonucleotideBLAST v2.77: what happens between
+ * "a target fragment has been read" and "a list of hybrid_sig hits comes back", i.e. the calls
+ *
+ *     dbase.hash(bio_seq.second, ...)                         tntblast_local.cpp:534
+ *     amplicon(...) / padlock(...) / hybrid(...)              tntblast_local.cpp:566,584,598,616
+ *                                                             (tntblast_worker.cpp:296,316,331,350)
+ *
+ * declared in tntblast.h:409-472.  The reference calls them once per (fragment, assay) from a
+ * per-thread loop; this ABI is the batched equivalent: register every fragment once, register
+ * every assay once, search, fetch flat hit records.  No torch / C++ types cross the boundary.
+ *
+ * All functions return 0 on success and a negative value on error; tnt_last_error() then holds
+ * the message (the reference throws `const char*`, throw.h:16-17 -- the C++ shim in
+ * INTEGRATION.md re-throws it).  The engine never falls back to a CPU path: if no CUDA device
+ * is usable, tnt_engine_create() fails.
+ */
+#ifndef TNTB200_H
+#define TNTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNTB200_ABI_VERSION 1
+
+/* hybrid_sig.h:19 */
+enum { TNT_ASSAY_PCR = 0, TNT_ASSAY_PROBE = 1, TNT_ASSAY_PADLOCK = 2, TNT_ASSAY_MIPS = 3 };
+/* seq.h:36-40 */
+enum { TNT_STRAND_PLUS = 1, TNT_STRAND_MINUS = 2, TNT_STRAND_BOTH = 3 };
+/* hybrid_sig.h:118 */
+enum { TNT_PLUS = 0, TNT_MINUS = 1 };
+/* which input oligo an output slot refers to */
+enum { TNT_OLIGO_F = 0, TNT_OLIGO_R = 1, TNT_OLIGO_P = 2, TNT_OLIGO_NONE = -1 };
+
+#define TNT_MAX_OLIGO_LEN 56  /* longest oligo the sm_100a kernels accept (reference: 1024) */
+
+typedef struct tnt_engine tnt_engine;
+
+/* NucCruc state that the reference sets once per thread (tntblast_local.cpp:363-367):
+ * NucCruc melt(param_set, opt.target_t); melt.Salt(opt.salt); melt.dangle(..); melt.dinkelbach(..)
+ * plus DNAHash dbase(opt.hash_word_size) (:345). */
+typedef struct {
+	float target_T;      /* K, default 310.15 (tntblast.h:64) */
+	float salt;          /* [Na+] M, default 0.05 (tntblast.h:61) */
+	int32_t dangle5;     /* default 0 (tntblast.h:72-73) */
+	int32_t dangle3;
+	int32_t dinkelbach;  /* must be 0: the iterative Tm mode is not implemented */
+	int32_t word_size;   /* hash word size W, 3..8, default 7 (tntblast.h:68) */
+	int32_t device;      /* CUDA device ordinal */
+	int32_t reserved;
+} tnt_engine_params;
+
+/* Scalars the reference passes to amplicon()/padlock()/hybrid() on every call
+ * (tntblast.h:409-472; values from Options, options.h:25-76). */
+typedef struct {
+	int32_t assay_format;            /* TNT_ASSAY_* (opt.assay_format) */
+	float forward_primer_strand;     /* opt.asymmetric_strand_ratio*opt.primer_strand */
+	float reverse_primer_strand;     /* opt.primer_strand */
+	float probe_strand;              /* opt.probe_strand */
+	float min_primer_tm, max_primer_tm, min_primer_dg, max_primer_dg;
+	float min_probe_tm, max_probe_tm, min_probe_dg, max_probe_dg;
+	uint32_t primer_clamp;
+	int32_t min_max_primer_clamp;    /* -1 disables */
+	uint32_t probe_clamp_5, probe_clamp_3;
+	uint32_t max_gap, max_mismatch, max_poly_degen;
+	uint32_t max_len;                /* opt.max_len (PCR amplicon / MIPS gap) */
+	int32_t single_primer_pcr;
+	int32_t target_strand;           /* TNT_STRAND_* (probe / padlock modes) */
+} tnt_search_options;
+
+/* One assay == one hybrid_sig after degenerate expansion (hybrid_sig.h:28-446): NUL-terminated
+ * ASCII oligos (NULL or "" when absent) and the *_degen multiplicities that divide the strand
+ * concentrations (amplicon_search.cpp:85-87). */
+typedef struct {
+	int32_t id;                      /* hybrid_sig::my_id(), echoed back in every hit */
+	const char *forward;
+	const char *reverse;
+	const char *probe;
+	int32_t forward_degen, reverse_degen, probe_degen;
+} tnt_assay;
+
+/* One bound oligo (oligo_info, tntblast.h:145-243). */
+typedef struct {
+	int32_t oligo;                   /* TNT_OLIGO_* : which input oligo sits in this slot */
+	int32_t loc_5, loc_3;            /* fragment-local target coordinates */
+	float tm, dH, dS;
+	int32_t num_mm, num_gap;
+	int32_t anchor_5, anchor_3;
+	uint32_t align_off;              /* offset of the NUL-terminated alignment text in the arena */
+} tnt_bound_oligo;
+
+/* One hit == the fields amplicon()/padlock()/hybrid() fill in a hybrid_sig
+ * (amplicon_search.cpp:447-555, padlock_search.cpp:155-222, probe_search.cpp:103-151).
+ * Coordinates are fragment-local, as in the reference (the caller adds the fragment offset,
+ * tntblast_local.cpp:654). */
+typedef struct {
+	int32_t assay_index;             /* index into the array given to tnt_engine_set_assays */
+	int32_t assay_id;
+	uint32_t target_id;              /* value returned by tnt_engine_add_target */
+	int32_t primer_strand;           /* TNT_PLUS / TNT_MINUS */
+	int32_t probe_strand;
+	int32_t amp_first, amp_last;     /* amplicon_range */
+	int32_t probe_first, probe_last; /* probe_range */
+	tnt_bound_oligo forward;         /* output "forward" slot (after the display swap) */
+	tnt_bound_oligo reverse;
+	tnt_bound_oligo probe;
+	int32_t forward_clamp;           /* forward_primer_clamp (anchor_3; anchor_3 of P1 for padlock) */
+	int32_t reverse_clamp;           /* reverse_primer_clamp (anchor_3; anchor_5 of P2 for padlock) */
+} tnt_hit;
+
+/* Counters of the last tnt_engine_search call. */
+typedef struct {
+	uint64_t db_bases;               /* bases searched (sum of fragment lengths) */
+	uint64_t seeds;                  /* unique (oligo, strand, diagonal) candidates emitted */
+	uint64_t alignments;             /* NucCruc heterodimer alignments executed */
+	uint64_t dp_cells;               /* sum of Lq*Lt over those alignments */
+	uint64_t bound_sites;            /* alignments that passed every per-oligo filter */
+	uint64_t hits;
+	uint64_t kernel_launches;        /* CUDA kernels launched by the call */
+	double scan_ms, align_ms, pair_ms, total_ms;   /* device time (CUDA events) */
+	uint64_t scan_bytes;             /* algorithmic bytes of the seed scan */
+} tnt_stats;
+
+const char *tnt_last_error(void);
+int tnt_abi_version(void);
+
+int tnt_engine_create(const tnt_engine_params *params, tnt_engine **out);
+void tnt_engine_destroy(tnt_engine *e);
+
+/* Replaces reading a fragment + DNAHash::hash (tntblast_local.cpp:510-534).  `codes` is the
+ * SEQPTR payload (seq.h:44-56): one byte per base, values 0..17 (seq.h:12-33).  The bytes are
+ * staged through pinned memory, packed on the device to 2 bit/base + a 1 bit/base non-ACGT
+ * mask + a sparse list of the non-ACGT codes, and stay resident in HBM until cleared. */
+int tnt_engine_add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *target_id);
+int tnt_engine_clear_targets(tnt_engine *e);
+
+int tnt_engine_set_assays(tnt_engine *e, const tnt_assay *assays, int32_t n);
+
+/* All registered assays against all registered fragments: seed scan -> NucCruc alignment of
+ * every candidate window -> per-oligo filters -> amplicon / padlock / probe assembly. */
+int tnt_engine_search(tnt_engine *e, const tnt_search_options *opt);
+
+/* Hits of the last search, ordered by (target_id, assay_index) and, inside one pair, in the
+ * order the reference's join loops emit them.  Pointers stay valid until the next search,
+ * clear or destroy.  `arena` holds the alignment strings. */
+int tnt_engine_get_hits(tnt_engine *e, const tnt_hit **hits, size_t *n, const char **arena, size_t *arena_size);
+int tnt_engine_get_stats(tnt_engine *e, tnt_stats *out);
+
+/* Amplicon / probe-site text of a hit as the reference builds it from the fragment
+ * (amplicon_search.cpp:508-537, padlock_search.cpp:203-218,338-352, probe_search.cpp:127-143):
+ * writes at most cap-1 characters + NUL, returns the full length. */
+long tnt_engine_hit_sequence(tnt_engine *e, const tnt_hit *hit, char *out, size_t cap);
+
+/* ---- Stage-level entry points (used by the parity tests and the roofline benchmark) ---- */
+
+/* Stage A: unique seeds of one oligo against one registered fragment, i.e. the list
+ * match_oligo_to_{minus,plus}_strand builds (bind_oligo.cpp:84-122): (query_loc, target_loc),
+ * sorted by diagonal.  Returns the number of seeds (which may exceed cap). */
+long tnt_engine_seeds(tnt_engine *e, uint32_t target_id, const char *oligo, int32_t plus_strand,
+	uint32_t *query_loc, uint32_t *target_loc, long cap);
+
+/* Stage B: one NucCruc evaluation per explicit candidate (what bind_oligo_to_*_strand does for
+ * one seed, bind_oligo.cpp:502-748 / :1205-1451, before the threshold filters). */
+typedef struct {
+	float tm, dH, dS, dG;
+	int32_t valid;
+	int32_t anchor5, anchor3;
+	int32_t num_mismatch, num_gap, max_poly_degen;
+	int32_t q_first, q_last, t_first, t_last;
+	int32_t target_start, target_stop;
+	int32_t loc_5, loc_3;
+	char alignment[512];
+} tnt_align_result;
+
+int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32_t plus_strand,
+	float strand_conc, const uint32_t *query_loc, const uint32_t *target_loc, long n,
+	tnt_align_result *out);
+
+/* Seed-scan-only pass over every registered fragment with the registered assays (timing aid for
+ * the HBM roofline): returns the number of unique candidates and the device time. */
+int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNTB200_H */

@@ -1,0 +1,137 @@
+"""Seeded synthetic inputs shared by the parity tests, bench.py and the golden-fixture script.
+
+Shapes follow SURVEY.md section 8(d): uniform random ACGT databases, assays sampled from the
+database with planted exact sites plus variants carrying mismatches and a 1-base indel, optional
+IUPAC codes / N runs in the target and inosine / IUPAC codes in the oligos.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = str.maketrans("ACGTMRSVWYHKDBNIacgt", "TGCAKYSBWRDMHVNItgca")
+
+
+def revcomp(s: str) -> str:
+    return s.translate(_COMP)[::-1]
+
+
+def random_codes(n: int, rng: np.random.Generator) -> np.ndarray:
+    """seq.h codes 0..3, uniform."""
+    return rng.integers(0, 4, size=n, dtype=np.uint8)
+
+
+def codes_to_str(codes: np.ndarray) -> str:
+    lut = np.frombuffer(b"ACGTIMRSVWYHKDBN-?", dtype=np.uint8)
+    return lut[codes].tobytes().decode()
+
+
+def str_to_codes(s: str) -> np.ndarray:
+    lut = np.full(256, 17, dtype=np.uint8)
+    for i, ch in enumerate("ACGTIMRSVWYHKDBN-"):
+        lut[ord(ch)] = i
+        lut[ord(ch.lower())] = i
+    return lut[np.frombuffer(s.encode(), dtype=np.uint8)]
+
+
+def rand_oligo(L: int, rng: np.random.Generator) -> str:
+    return ACGT[rng.integers(0, 4, size=L)].tobytes().decode()
+
+
+def mutate(s: str, nmut: int, rng: np.random.Generator, indel: bool = True) -> str:
+    s = list(s)
+    for _ in range(nmut):
+        p = int(rng.integers(0, len(s)))
+        k = int(rng.integers(0, 4 if indel else 2))
+        if k < 2:
+            s[p] = "ACGT"[int(rng.integers(0, 4))]
+        elif k == 2 and len(s) > 10:
+            del s[p]
+        else:
+            s.insert(p, "ACGT"[int(rng.integers(0, 4))])
+    return "".join(s)
+
+
+def plant(codes: np.ndarray, pos: int, text: str) -> None:
+    c = str_to_codes(text)
+    n = min(len(c), len(codes) - pos)
+    if n > 0:
+        codes[pos:pos + n] = c[:n]
+
+
+def sprinkle_degenerate(codes: np.ndarray, rng: np.random.Generator, frac: float = 1e-3,
+                        n_runs_per_50kb: float = 1.0) -> None:
+    """0.1 % two/three-fold IUPAC codes + N runs of length 1..10 (config 3 of SURVEY 8d)."""
+    n = len(codes)
+    k = int(n * frac)
+    if k:
+        idx = rng.integers(0, n, size=k)
+        codes[idx] = rng.integers(5, 15, size=k).astype(np.uint8)  # M..B
+    runs = int(n / 50000.0 * n_runs_per_50kb)
+    for _ in range(runs):
+        p = int(rng.integers(0, n))
+        L = int(rng.integers(1, 11))
+        codes[p:p + L] = 15
+
+
+def make_pcr_case(rng: np.random.Generator, n: int, n_sites: int = 3, probe: bool = False,
+                  lens: Tuple[int, int, int] = (20, 20, 25), amp: Tuple[int, int] = (80, 400)):
+    """One assay + a database of n bases with planted (mutated) amplicons on either strand."""
+    codes = random_codes(n, rng)
+    F = rand_oligo(lens[0], rng)
+    R = rand_oligo(lens[1], rng)
+    P = rand_oligo(lens[2], rng) if probe else None
+    for k in range(n_sites):
+        alen = int(rng.integers(amp[0], amp[1]))
+        inner = rand_oligo(alen, rng)
+        mid = ""
+        if probe:
+            pp = P if rng.integers(0, 2) else revcomp(P)
+            mid = rand_oligo(int(rng.integers(5, 30)), rng) + mutate(pp, int(rng.integers(0, 3)) if k else 0, rng)
+        text = mutate(F, int(rng.integers(0, 4)) if k else 0, rng) + mid + inner + \
+            mutate(revcomp(R), int(rng.integers(0, 4)) if k else 0, rng)
+        if rng.integers(0, 3) == 0:
+            text = revcomp(text)
+        pos = int(rng.integers(0, max(1, n - len(text) - 1)))
+        plant(codes, pos, text)
+    return codes, F, R, P
+
+
+def make_assays(rng: np.random.Generator, db: List[np.ndarray], n_assays: int, kind: str,
+                lens=(20, 21, 25), amp=(80, 400), variants: int = 2):
+    """Assays sampled from random oligos, each planted once exactly (+ `variants` mutated copies)
+    into random fragments of `db` (modified in place).  kind: pcr | taqman | probe | padlock."""
+    assays = []
+    for a in range(n_assays):
+        F = rand_oligo(int(rng.integers(lens[0] - 2, lens[0] + 3)), rng)
+        R = rand_oligo(int(rng.integers(lens[1] - 2, lens[1] + 3)), rng)
+        P = rand_oligo(int(rng.integers(lens[2] - 2, lens[2] + 3)), rng)
+        for v in range(1 + variants):
+            frag = db[int(rng.integers(0, len(db)))]
+            nm = 0 if v == 0 else int(rng.integers(1, 4))
+            if kind in ("pcr", "taqman"):
+                alen = int(rng.integers(amp[0], amp[1]))
+                mid = ""
+                if kind == "taqman":
+                    pp = P if rng.integers(0, 2) else revcomp(P)
+                    mid = rand_oligo(int(rng.integers(3, 20)), rng) + mutate(pp, nm if v else 0, rng)
+                text = mutate(F, nm, rng) + mid + rand_oligo(alen, rng) + mutate(revcomp(R), nm, rng)
+            elif kind == "probe":
+                text = mutate(revcomp(P), nm, rng)
+            else:  # padlock: 5'-F-3' 5'-R-3' adjacent on one strand
+                text = revcomp(mutate(F, nm, rng, indel=False) + mutate(R, nm, rng, indel=False))
+            if rng.integers(0, 2):
+                text = revcomp(text)
+            if len(frag) > len(text) + 2:
+                plant(frag, int(rng.integers(0, len(frag) - len(text) - 1)), text)
+        if kind == "pcr":
+            assays.append((F, R, None))
+        elif kind == "taqman":
+            assays.append((F, R, P))
+        elif kind == "probe":
+            assays.append((None, None, P))
+        else:
+            assays.append((F, R, None))
+    return assays

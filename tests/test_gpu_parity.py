@@ -1,0 +1,331 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle, stage by stage and end to end.
+
+Bar (BASELINE.json north_star): seeds, hit coordinates, strands, counts and alignment strings
+bit-exact; Tm within 0.01 C and dG within 0.001 kcal/mol.  The engine evaluates dH/dS/Tm with the
+reference's rounding, so the tests additionally demand bit-identical floats and only fall back to
+the stated tolerance in the assertion message.
+"""
+import numpy as np
+import pytest
+
+import gen
+import harness as H
+
+pytestmark = pytest.mark.gpu
+
+TM_TOL = 0.01
+DG_TOL = 0.001
+
+
+@pytest.fixture(scope="module")
+def eng(engine_lib):
+    from thermonucleotideblast_b200 import Engine
+    e = Engine()
+    yield e
+    e.close()
+
+
+def hit_key(engine, h, assay):
+    """Same tuple layout as harness.Hit.exact_key()."""
+    F, R, P = assay
+    names = {0: F, 1: R, 2: P, -1: ""}
+    seq = engine.hit_sequence(h)
+    fnv = 1469598103934665603
+    for ch in seq.encode():
+        fnv = ((fnv ^ ch) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return (h.primer_strand, h.probe_strand, h.amp_first, h.amp_last, h.probe_first, h.probe_last,
+            h.forward.num_mm, h.forward.num_gap, h.reverse.num_mm, h.reverse.num_gap,
+            h.probe.num_mm, h.probe.num_gap, h.forward_clamp, h.reverse_clamp,
+            len(seq), fnv,
+            (names[h.forward.oligo] or "").encode(), (names[h.reverse.oligo] or "").encode(),
+            h.forward_align.encode(), h.reverse_align.encode(), h.probe_align.encode(),
+            seq[:255].encode())
+
+
+def hit_floats(h):
+    return (h.forward.tm, h.forward.dH, h.forward.dS, h.reverse.tm, h.reverse.dH, h.reverse.dS,
+            h.probe.tm, h.probe.dH, h.probe.dS)
+
+
+def assert_hits_equal(engine, got, want, assay, T=310.15):
+    gk = [hit_key(engine, h, assay) for h in got]
+    wk = [h.exact_key() for h in want]
+    assert len(gk) == len(wk), f"hit count {len(gk)} != {len(wk)}"
+    # the reference emits hits of one (fragment, assay) in join order; compare as ordered lists
+    assert gk == wk
+    for g, w in zip(got, want):
+        gf, wf = hit_floats(g), w.floats()
+        for k in (0, 3, 6):
+            assert abs(gf[k] - wf[k]) <= TM_TOL, "Tm outside 0.01 C"
+            dg_g = gf[k + 1] - T * gf[k + 2]
+            dg_w = wf[k + 1] - T * wf[k + 2]
+            assert abs(dg_g - dg_w) <= DG_TOL, "dG outside 0.001 kcal/mol"
+        assert gf == wf, "floats are expected to be bit-identical"
+
+
+def to_opts(o):
+    """harness.Options -> engine SearchOptions (same field names)."""
+    from thermonucleotideblast_b200 import search_options
+    s = search_options()
+    for name, _ in s._fields_:
+        setattr(s, name, getattr(o, name))
+    return s
+
+
+# ---------------------------------------------------------------------------------------------
+def test_seeds_bit_exact(eng, oracle):
+    rng = np.random.default_rng(101)
+    eng.clear_targets()
+    frags = []
+    for k in range(4):
+        n = int(rng.integers(20000, 70000))
+        codes = gen.random_codes(n, rng)
+        if k % 2:
+            gen.sprinkle_degenerate(codes, rng, frac=5e-3, n_runs_per_50kb=20)
+            codes[rng.integers(0, n, size=20)] = 16
+            codes[rng.integers(0, n, size=20)] = 17
+        frags.append(codes)
+    oligos = [gen.rand_oligo(20, rng), gen.rand_oligo(30, rng), gen.rand_oligo(7, rng), gen.rand_oligo(56, rng)]
+    o = list(gen.rand_oligo(24, rng)); o[9] = "I"; oligos.append("".join(o))
+    o = list(gen.rand_oligo(26, rng)); o[3] = "N"; o[20] = "R"; oligos.append("".join(o))
+    oligos.append("ACGTAC")          # shorter than the word size: no seeds
+    oligos.append("AAAAAAAAAAAAAAAAAAAA")
+    # plant exact + shifted copies so several words share a diagonal
+    for ol in oligos[:2]:
+        gen.plant(frags[0], 1000, ol)
+        gen.plant(frags[0], 5000, gen.revcomp(ol))
+    eng.clear_targets()
+    ids = [eng.add_target(c) for c in frags]
+    total = 0
+    for tid, codes in zip(ids, frags):
+        for ol in oligos:
+            for plus in (False, True):
+                want = oracle.seeds(codes, ol, 7, plus, unique=True)
+                got = eng.seeds(tid, ol, plus)
+                assert got == want, (tid, ol, plus)
+                total += len(want)
+    assert total > 500
+
+
+def test_seeds_fragment_edges(eng, oracle):
+    """Tiny fragments, fragments shorter than a word, a seed on the very last position."""
+    rng = np.random.default_rng(7)
+    eng.clear_targets()
+    ol = gen.rand_oligo(20, rng)
+    frags = [gen.str_to_codes(ol[:5]), gen.str_to_codes(ol[:7]), gen.str_to_codes("ACGT" + ol),
+             gen.str_to_codes(gen.revcomp(ol)), gen.random_codes(8192, rng), gen.random_codes(8193, rng),
+             gen.random_codes(8191 + 7, rng)]
+    gen.plant(frags[4], 8192 - 20, ol)
+    gen.plant(frags[5], 8193 - 7, ol[:7])
+    ids = [eng.add_target(c) for c in frags]
+    for tid, codes in zip(ids, frags):
+        for plus in (False, True):
+            assert eng.seeds(tid, ol, plus) == oracle.seeds(codes, ol, 7, plus, unique=True)
+
+
+def _compare_align(eng, oracle, tid, codes, ol, plus, seeds, ct=9.0e-7, T=310.15, na=0.05, d5=0, d3=0):
+    got = eng.align(tid, ol, plus, seeds, ct=ct)
+    nvalid = 0
+    for (q, t), g in zip(seeds, got):
+        w = oracle.bind_window(codes, ol, plus, q, t, T=T, na=na, ct=ct, dangle5=d5, dangle3=d3)
+        assert g.valid == w.valid, (ol, plus, q, t)
+        assert (g.target_start, g.target_stop) == (w.target_start, w.target_stop)
+        if not w.valid:
+            continue
+        nvalid += 1
+        assert abs(g.tm - w.tm) <= TM_TOL and abs(g.dG - w.dG) <= DG_TOL, (ol, plus, q, t, g.tm, w.tm)
+        assert (g.tm, g.dH, g.dS, g.dG) == (w.tm, w.dH, w.dS, w.dG), "floats expected bit-identical"
+        assert (g.anchor5, g.anchor3, g.num_mismatch, g.num_gap, g.max_poly_degen) == \
+            (w.anchor5, w.anchor3, w.num_mismatch, w.num_gap, w.max_poly_degen), (ol, plus, q, t)
+        assert (g.q_first, g.q_last, g.t_first, g.t_last) == (w.q_first, w.q_last, w.t_first, w.t_last)
+        assert (g.loc_5, g.loc_3) == (w.loc_5, w.loc_3)
+        assert g.alignment == w.alignment, (ol, plus, q, t, g.alignment, w.alignment)
+    return nvalid
+
+
+def test_align_random_and_planted_windows(eng, oracle):
+    rng = np.random.default_rng(202)
+    n = 120000
+    codes = gen.random_codes(n, rng)
+    oligos = [gen.rand_oligo(L, rng) for L in (12, 18, 20, 22, 25, 30, 35, 56)]
+    # planted sites with 0..4 edits incl. indels, on both strands, some at the fragment edges
+    for i, ol in enumerate(oligos):
+        for k in range(12):
+            text = gen.mutate(gen.revcomp(ol) if k % 2 else ol, k % 5, rng)
+            gen.plant(codes, 2000 + (i * 12 + k) * 400, text)
+    gen.plant(codes, 0, gen.revcomp(oligos[2])[3:])
+    gen.plant(codes, n - 15, oligos[3][:15])
+    eng.clear_targets()
+    tid = eng.add_target(codes)
+    nvalid = 0
+    for ol in oligos:
+        for plus in (False, True):
+            seeds = oracle.seeds(codes, ol, 7, plus, unique=True)
+            nvalid += _compare_align(eng, oracle, tid, codes, ol, plus, seeds)
+    assert nvalid > 1000
+
+
+def test_align_degenerate_target_and_oligo(eng, oracle):
+    rng = np.random.default_rng(303)
+    n = 60000
+    codes = gen.random_codes(n, rng)
+    oligos = []
+    for L in (20, 24, 30):
+        o = list(gen.rand_oligo(L, rng))
+        o[int(rng.integers(7, L - 7))] = "I"
+        o[int(rng.integers(0, L))] = "RYMKSWN"[int(rng.integers(0, 7))]
+        oligos.append("".join(o))
+    for i, ol in enumerate(oligos):
+        plain = ol.replace("I", "A").replace("R", "A").replace("Y", "C").replace("M", "A").replace("K", "G") \
+            .replace("S", "C").replace("W", "A").replace("N", "T")
+        for k in range(10):
+            gen.plant(codes, 1000 + (i * 10 + k) * 500, gen.mutate(gen.revcomp(plain) if k % 2 else plain, k % 4, rng))
+    gen.sprinkle_degenerate(codes, rng, frac=2e-2, n_runs_per_50kb=40)
+    codes[rng.integers(0, n, size=200)] = 16   # DB_GAP: dropped from windows
+    codes[rng.integers(0, n, size=200)] = 17   # DB_UNKNOWN
+    codes[rng.integers(0, n, size=200)] = 4    # inosine in the target
+    eng.clear_targets()
+    tid = eng.add_target(codes)
+    nvalid = 0
+    for ol in oligos:
+        for plus in (False, True):
+            seeds = oracle.seeds(codes, ol, 7, plus, unique=True)
+            nvalid += _compare_align(eng, oracle, tid, codes, ol, plus, seeds, ct=2.5e-7)
+    assert nvalid > 200
+
+
+def test_readme_known_answer(eng):
+    """README.md:138,162-203 of the reference: gibb-marburg TaqMan assay."""
+    amp = ("TTCCCCTTTGGAGGCATCCAAGCGATGGGCTTTCAGGACAGGTGTACCTCCCAAGAATGTTGAGTATACAGAAGGGGAGGAAGCCAAAACATGCTACAATATAAG"
+           "TGTAACGGATCCCTCTGGAAAATCCTTGCTGTTGGATCCTCC")
+    rng = np.random.default_rng(1)
+    codes = gen.random_codes(6121 + len(amp) + 3000, rng)
+    gen.plant(codes, 6121, amp)
+    from thermonucleotideblast_b200 import Assay, search_options
+    eng.clear_targets()
+    eng.add_target(codes)
+    eng.set_assays([Assay(0, "TTCCCCTTTGGAGGCATC", "GGAGGATCCAACAGCAAGG", "CGATGGGCTTTCAGGACAGGTGT")])
+    hits = eng.search(search_options(min_primer_tm=40.0, min_probe_tm=45.0))
+    assert len(hits) == 1
+    h = hits[0]
+    assert (h.amp_first, h.amp_last, h.probe_first, h.probe_last) == (6121, 6267, 6143, 6165)
+    T = 310.15
+    assert abs((h.forward.dH - T * h.forward.dS) - (-16.8574)) < 1e-3 and abs(h.forward.dH + 135.5) < 1e-3
+    assert abs((h.reverse.dH - T * h.reverse.dS) - (-17.8955)) < 1e-3 and abs(h.reverse.dH + 146.5) < 1e-3
+    assert abs((h.probe.dH - T * h.probe.dS) - (-22.9778)) < 1e-3 and abs(h.probe.dH + 180.2) < 1e-3
+    assert (h.forward_clamp, h.reverse_clamp) == (18, 19)
+    assert h.forward_align == "5' TTCCCCTTTGGAGGCATC 3'\n   ||||||||||||||||||\n3' AAGGGGAAACCTCCGTAG 5'"
+    assert h.probe_align == "5' CGATGGGCTTTCAGGACAGGTGT 3'\n   |||||||||||||||||||||||\n3' GCTACCCGAAAGTCCTGTCCACA 5'"
+    # the probe text occurs verbatim in the plus strand, i.e. the oligo binds the minus strand
+    assert h.probe_strand == 1 and h.primer_strand == 0
+    assert eng.hit_sequence(h) == amp
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_search_pcr_and_taqman(eng, oracle, seed):
+    from thermonucleotideblast_b200 import Assay
+    rng = np.random.default_rng(1000 + seed)
+    total = 0
+    for it in range(8):
+        probe = bool(it % 2)
+        codes, F, R, P = gen.make_pcr_case(rng, int(rng.integers(20000, 90000)), n_sites=int(rng.integers(1, 6)), probe=probe)
+        if it % 4 == 3:
+            gen.sprinkle_degenerate(codes, rng, frac=2e-3, n_runs_per_50kb=5)
+        o = H.default_options(min_primer_tm=float(rng.choice([35.0, 40.0, 45.0])), min_probe_tm=40.0,
+                              max_len=int(rng.choice([500, 2000])), single_primer_pcr=int(rng.integers(0, 2)),
+                              primer_clamp=int(rng.integers(0, 3)),
+                              min_max_primer_clamp=int(rng.choice([-1, -1, 2])))
+        want = oracle.search(codes, F, R, P, o)
+        eng.clear_targets()
+        eng.add_target(codes)
+        eng.set_assays([Assay(7, F, R, P)])
+        got = eng.search(to_opts(o))
+        assert_hits_equal(eng, got, want, (F, R, P))
+        total += len(want)
+    assert total > 5
+
+
+def test_search_probe_and_padlock(eng, oracle):
+    from thermonucleotideblast_b200 import Assay
+    rng = np.random.default_rng(77)
+    total = 0
+    for it in range(10):
+        n = int(rng.integers(20000, 60000))
+        db = [gen.random_codes(n, rng)]
+        kind = "probe" if it % 2 else "padlock"
+        (F, R, P), = gen.make_assays(rng, db, 1, kind, variants=4)
+        codes = db[0]
+        if kind == "probe":
+            o = H.default_options(assay_format=H.ASSAY_PROBE, min_probe_tm=float(rng.choice([30.0, 45.0])),
+                                  target_strand=int(rng.choice([1, 2, 3])), probe_clamp_5=int(rng.integers(0, 2)))
+        else:
+            o = H.default_options(assay_format=int(rng.choice([H.ASSAY_PADLOCK, H.ASSAY_MIPS])), min_probe_tm=30.0,
+                                  max_len=int(rng.choice([0, 3, 50])), probe_clamp_3=int(rng.integers(0, 3)))
+        want = oracle.search(codes, F, R, P, o)
+        eng.clear_targets()
+        eng.add_target(codes)
+        eng.set_assays([Assay(3, F, R, P)])
+        got = eng.search(to_opts(o))
+        assert_hits_equal(eng, got, want, (F, R, P))
+        total += len(want)
+    assert total > 5
+
+
+def test_search_multi_fragment_multi_assay(eng, oracle):
+    """Batch semantics: many fragments x many assays in one call == the reference's nested loops."""
+    from thermonucleotideblast_b200 import Assay
+    rng = np.random.default_rng(4242)
+    db = [gen.random_codes(int(rng.integers(15000, 40000)), rng) for _ in range(6)]
+    assays = gen.make_assays(rng, db, 8, "taqman", variants=3)
+    o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+    eng.clear_targets()
+    for c in db:
+        eng.add_target(c)
+    eng.set_assays([Assay(100 + i, *a) for i, a in enumerate(assays)])
+    got = eng.search(to_opts(o))
+    st = eng.stats()
+    assert st.alignments > 0 and st.dp_cells > 0 and st.kernel_launches >= 2
+    k = 0
+    total = 0
+    for t, codes in enumerate(db):
+        for i, a in enumerate(assays):
+            want = oracle.search(codes, a[0], a[1], a[2], o)
+            mine = [h for h in got if h.target_id == t and h.assay_index == i]
+            assert all(h.assay_id == 100 + i for h in mine)
+            assert_hits_equal(eng, mine, want, a)
+            total += len(want)
+            k += len(mine)
+    assert k == len(got) and total >= 8
+
+
+def test_engine_matches_compiled_reference(eng, ref):
+    """Same comparison against the unmodified reference build (only where oracle/_ref travelled)."""
+    from thermonucleotideblast_b200 import Assay
+    rng = np.random.default_rng(99)
+    for it in range(4):
+        codes, F, R, P = gen.make_pcr_case(rng, 50000, n_sites=4, probe=bool(it % 2))
+        o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+        want = ref.search(codes, F, R, P, o)
+        eng.clear_targets()
+        eng.add_target(codes)
+        eng.set_assays([Assay(0, F, R, P)])
+        assert_hits_equal(eng, eng.search(to_opts(o)), want, (F, R, P))
+
+
+def test_refuses_unsupported(engine_lib):
+    from thermonucleotideblast_b200 import Assay, Engine, EngineError, search_options
+    with pytest.raises(EngineError):
+        Engine(word_size=12)
+    e = Engine()
+    try:
+        e.add_target(gen.random_codes(1000, np.random.default_rng(0)))
+        e.set_assays([Assay(0, "A" * 60, "ACGTACGTACGTACGTAC", None)])
+        with pytest.raises(EngineError):
+            e.search(search_options(min_primer_tm=40.0))
+        e.set_assays([Assay(0, "ACGTACGTACGTACGTAC", "ACGTACGTACGTACGTAC", None)])
+        with pytest.raises(EngineError):  # bounds that accept non-binding sites
+            e.search(search_options())
+        with pytest.raises(EngineError):
+            e.set_assays([Assay(0, "ACGTACGTACGTACGTAC", None, None)])
+    finally:
+        e.close()

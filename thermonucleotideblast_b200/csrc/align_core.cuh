@@ -1,0 +1,585 @@
+// NucCruc heterodimer evaluation of one (oligo, target window) pair, one CUDA thread per pair.
+//
+// What the reference does per candidate in NucCruc::approximate_tm_heterodimer
+// (nuc_cruc.cpp:2441-2454): the 3-state integer local alignment (align_dimer, :492-696), the
+// enumeration of co-optimal tracebacks (tm_dimer :2517-2540, enumerate_dimer_alignments
+// :973-1170, trace_back :1409-1618) and the nearest-neighbour dH/dS/Tm evaluation of every
+// enumerated alignment (evaluate_alignment :1620-2299), keeping the lowest dG.
+//
+// Layout choices (not the reference's):
+//  * the three DP rows live in shared memory, clamped at zero, indexed [column][thread] so a warp
+//    touches 32 consecutive banks;
+//  * the 15-byte NC_Elem of the reference shrinks to a 12-bit trace word per cell (trace masks +
+//    the sign facts the traceback tests), written [cell][thread] to a per-CTA scratch in global
+//    memory (coalesced 64 B per warp and cell);
+//  * maximal cells are not collected in a list: a "candidate" bit marks cells that tied or raised
+//    the running maximum, and everything from the last strict raise onwards is the row-major
+//    list the reference builds;
+//  * all floating point uses explicit round-to-nearest intrinsics in the reference's statement
+//    order (no FMA contraction), so dH/dS/Tm are bit-identical to the host computation.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "tnt_types.h"
+
+namespace tnt {
+
+// trace word layout
+constexpr unsigned TW_IQ_INS = 1u << 3;  // I_query came from M (insert)
+constexpr unsigned TW_IQ_EXT = 1u << 4;  // I_query came from I_query (extend)
+constexpr unsigned TW_IT_INS = 1u << 5;
+constexpr unsigned TW_IT_EXT = 1u << 6;
+constexpr unsigned TW_M_NEG = 1u << 7;
+constexpr unsigned TW_M_ZERO = 1u << 8;
+constexpr unsigned TW_IQ_NEG = 1u << 9;
+constexpr unsigned TW_IT_NEG = 1u << 10;
+constexpr unsigned TW_CAND = 1u << 11;   // M >= running maximum when the cell was computed
+// word of a never-written cell (row 0 / column 0 of the reference matrix, nuc_cruc.h:531-536)
+constexpr unsigned TW_BORDER = TW_M_NEG | TW_IQ_NEG | TW_IT_NEG;
+
+constexpr int P_AT = bA*7 + bT, P_TA = bT*7 + bA, P_GT = bG*7 + bT, P_TG = bT*7 + bG;
+constexpr int P_EE = bE*7 + bE, P_NONE = bGAP*7 + bGAP;
+
+// IUPAC membership sets, bit0=A bit1=C bit2=G bit3=T (nuc_cruc_anchor.cpp:8-139)
+__device__ __constant__ uint8_t c_base_set[NB] = {1, 2, 4, 8, 15, 0, 0, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15};
+
+__device__ __forceinline__ bool is_virtual(int b) { return b == bE || b == bGAP; }
+
+__device__ __forceinline__ bool dev_complementary(int q, int t)
+{
+	const unsigned ts = c_base_set[t];
+	const unsigned tc = ((ts & 1u) << 3) | ((ts & 8u) >> 3) | ((ts & 2u) << 1) | ((ts & 4u) >> 1);
+	return (c_base_set[q] & tc) != 0;
+}
+
+struct AlnState {
+	uint8_t q[MAX_COLS];
+	uint8_t t[MAX_COLS];
+	int b, e;            // live columns are [b, e)
+	int fm_q, fm_t, lm_q, lm_t;
+	float dH, dS, tm;
+};
+
+// Block-wide constants staged in shared memory.
+struct DpShared {
+	const int32_t *dg;   // [TABLE]
+	const uint8_t *bbp;  // [NB*NB]
+	const uint8_t *wc;   // [NPAIR]
+	const uint8_t *q;    // oligo, 5'->3'
+	int Lq;
+};
+
+struct DpResult {
+	int runmax;
+	int last_raise;  // linear cell index (i-1)*Lt + (j-1) of the last strict raise of the maximum
+	int nmax;        // cells equal to the maximum from there on
+};
+
+// ------------------------------------------------------------------------------------------
+// Stage 1: fill.  Rows follow the reversed oligo, columns the target 5'->3'
+// (align_dimer, nuc_cruc.cpp:508-693).  NT = threads per block (row/trace stride).
+// ------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *tgt, int Lt,
+	int32_t *rowM, int32_t *rowIq, int32_t *rowIt, uint16_t *trace)
+{
+	const int32_t *__restrict__ dg = sh.dg;
+	const uint8_t *__restrict__ bbp = sh.bbp;
+	const int Lq = sh.Lq;
+
+	for (int j = 0; j <= Lt; ++j) { rowM[j*NT] = 0; rowIq[j*NT] = 0; rowIt[j*NT] = 0; }
+
+	DpResult res;
+	res.runmax = -1;
+	res.last_raise = -1;
+	res.nmax = 0;
+
+	int cell = 0;
+	for (int i = 1; i <= Lq; ++i) {
+		const int qb = sh.q[Lq - i];
+		const int pq = (i == 1) ? (int)bGAP : (int)sh.q[Lq - i + 1];
+		const int gap_pq = bbp[bGAP*NB + pq]*NPAIR;   // previous pair (GAP, pq)
+		const int cur_it = bbp[bGAP*NB + qb];          // current pair of the I_target state
+		const int pen_ext_it = dg[gap_pq + cur_it];
+
+		int dM = 0, dIq = 0, dIt = 0;   // clamped states of (i-1, j-1)
+		int lM = 0, lIq = 0;            // clamped states of (i, j-1)
+		int pt_pq = bbp[bGAP*NB + pq];  // (prev target, prev query)
+		int pt_qb = bbp[bGAP*NB + qb];  // (prev target, query)
+		int pt_gap = bbp[bGAP*NB + bGAP];
+
+#pragma unroll 2
+		for (int j = 1; j <= Lt; ++j, ++cell) {
+			const int tb = tgt[j - 1];
+			const int cur = bbp[tb*NB + qb];
+			const int tb_pq = bbp[tb*NB + pq];
+			const int tb_gap = bbp[tb*NB + bGAP];
+
+			const int uM = rowM[j*NT], uIq = rowIq[j*NT], uIt = rowIt[j*NT];
+
+			// match / mismatch state
+			const int d1 = dM - dg[pt_pq*NPAIR + cur];
+			const int d2 = dIq - dg[pt_gap*NPAIR + cur];
+			const int d3 = dIt - dg[gap_pq + cur];
+			int M;
+			unsigned w;
+			if (d1 >= d2) {
+				if (d1 >= d3) { M = d1; w = T_DIAG | (d1 == d2 ? T_LEFT : 0u) | (d1 == d3 ? T_UP : 0u); }
+				else { M = d3; w = T_UP; }
+			}
+			else {
+				if (d2 >= d3) { M = d2; w = T_LEFT | (d2 == d3 ? T_UP : 0u); }
+				else { M = d3; w = T_UP; }
+			}
+
+			// gap in the query: extend along the row
+			const int qi = lM - dg[pt_qb*NPAIR + tb_gap];
+			const int qe = lIq - dg[pt_gap*NPAIR + tb_gap];
+			int Iq;
+			if (qi >= qe) { Iq = qi; w |= TW_IQ_INS | (qi == qe ? TW_IQ_EXT : 0u); }
+			else { Iq = qe; w |= TW_IQ_EXT; }
+
+			// gap in the target: extend down the column
+			const int ti = uM - dg[tb_pq*NPAIR + cur_it];
+			const int te = uIt - pen_ext_it;
+			int It;
+			if (ti >= te) { It = ti; w |= TW_IT_INS | (ti == te ? TW_IT_EXT : 0u); }
+			else { It = te; w |= TW_IT_EXT; }
+
+			if (M < 0) w |= TW_M_NEG;
+			if (M == 0) w |= TW_M_ZERO;
+			if (Iq < 0) w |= TW_IQ_NEG;
+			if (It < 0) w |= TW_IT_NEG;
+
+			if (M >= res.runmax) {
+				w |= TW_CAND;
+				if (M > res.runmax) { res.runmax = M; res.last_raise = cell; res.nmax = 1; }
+				else ++res.nmax;
+			}
+			trace[(size_t)cell*NT] = (uint16_t)w;
+
+			dM = uM; dIq = uIq; dIt = uIt;
+			lM = max(M, 0);
+			lIq = max(Iq, 0);
+			rowM[j*NT] = lM;
+			rowIq[j*NT] = lIq;
+			rowIt[j*NT] = max(It, 0);
+			pt_pq = tb_pq;
+			pt_qb = cur;
+			pt_gap = tb_gap;
+		}
+	}
+	return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 2: traceback of one path (trace_back, nuc_cruc.cpp:1409-1618)
+// ------------------------------------------------------------------------------------------
+struct Branch {
+	uint16_t id;     // (cell index + 1)*3 + state; identifies the trace byte the reference points at
+	uint8_t mask;
+	uint8_t cur;
+};
+constexpr int MAX_BRANCH = 3*(MAX_OLIGO + MAX_WINDOW);
+
+__device__ __forceinline__ bool path_split(unsigned m) { return __popc(m & 7u) > 1; }
+
+template <int NT>
+__device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, const uint16_t *trace,
+	int start_cell, Branch *stack, int &nstack, int &zero_count, AlnState &a, unsigned &flags)
+{
+	const int Lq = sh.Lq;
+	int last_i = start_cell/Lt + 1, last_j = start_cell%Lt + 1;
+	a.fm_q = Lq - last_i;
+	a.fm_t = last_j - 1;
+
+	int truncate_at_zero = 0;
+	bool count_zeros = false;
+	if (zero_count < 0) { zero_count = 0; count_zeros = true; }
+	else truncate_at_zero = zero_count--;
+
+	unsigned cur_id = 0;        // 0 == the static first_match byte of the reference
+	unsigned cur_mask = T_DIAG;
+
+	for (;;) {
+		bool valid = true;
+		unsigned local;
+		if (path_split(cur_mask)) {
+			int k = 0;
+			for (; k < nstack; ++k) if (stack[k].id == cur_id) break;
+			if (k == nstack) {
+				if (nstack == MAX_BRANCH) { flags |= F_STACK; return; }
+				stack[k].id = (uint16_t)cur_id;
+				stack[k].mask = (uint8_t)cur_mask;
+				stack[k].cur = (uint8_t)((cur_mask & T_DIAG) ? T_DIAG : ((cur_mask & T_UP) ? T_UP : T_LEFT));
+				++nstack;
+			}
+			local = stack[k].cur;
+		}
+		else local = cur_mask;
+
+		const bool inside = (last_i >= 1 && last_j >= 1);
+		const int cell = (last_i - 1)*Lt + (last_j - 1);
+		const unsigned w = inside ? (unsigned)trace[(size_t)cell*NT] : TW_BORDER;
+
+		if (local == T_DIAG) {
+			if (last_i > Lq || last_j < 1) valid = false;
+			else {
+				if (w & TW_M_NEG) valid = false;
+				else if (w & TW_M_ZERO) {
+					if (count_zeros) ++zero_count;
+					else if (--truncate_at_zero == 0) valid = false;
+				}
+				if (last_i < 1) { flags |= F_OOB; return; } // the reference reads query[len] here
+				if (a.e < MAX_COLS) { a.q[a.e] = sh.q[Lq - last_i]; a.t[a.e] = tgt[last_j - 1]; ++a.e; }
+				else flags |= F_TRUNC;
+				a.lm_q = Lq - last_i;
+				a.lm_t = last_j - 1;
+				cur_id = (unsigned)(cell + 1)*3u + 0u;
+				cur_mask = inside ? (w & 7u) : T_INVALID;
+				--last_i;
+				--last_j;
+			}
+		}
+		else if (local == T_LEFT) { // a gap goes into the query
+			if (last_j < 1) valid = false;
+			else {
+				if (w & TW_IQ_NEG) valid = false;
+				if (a.e < MAX_COLS) { a.q[a.e] = bGAP; a.t[a.e] = tgt[last_j - 1]; ++a.e; }
+				else flags |= F_TRUNC;
+				a.lm_q = Lq - last_i + 1;
+				a.lm_t = last_j - 1;
+				cur_id = (unsigned)(cell + 1)*3u + 1u;
+				cur_mask = inside ? (((w & TW_IQ_INS) ? T_DIAG : 0u) | ((w & TW_IQ_EXT) ? T_LEFT : 0u)) : T_INVALID;
+				--last_j;
+			}
+		}
+		else if (local == T_UP) { // a gap goes into the target
+			if (last_i > Lq) valid = false;
+			else {
+				if (w & TW_IT_NEG) valid = false;
+				if (last_i < 1) { flags |= F_OOB; return; }
+				if (a.e < MAX_COLS) { a.q[a.e] = sh.q[Lq - last_i]; a.t[a.e] = bGAP; ++a.e; }
+				else flags |= F_TRUNC;
+				a.lm_q = Lq - last_i;
+				a.lm_t = last_j;
+				cur_id = (unsigned)(cell + 1)*3u + 2u;
+				cur_mask = inside ? (((w & TW_IT_INS) ? T_DIAG : 0u) | ((w & TW_IT_EXT) ? T_UP : 0u)) : T_INVALID;
+				--last_i;
+			}
+		}
+		else { flags |= F_OOB; return; } // "invalid_match in trace back"
+
+		if (!valid) break;
+		if (last_i < 0 || last_j < 0) { flags |= F_OOB; return; }
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 3: nearest-neighbour evaluation (evaluate_alignment, nuc_cruc.cpp:1620-2299)
+// ------------------------------------------------------------------------------------------
+#define TNT_ADD(a, b) __fadd_rn((a), (b))
+#define TNT_SUB(a, b) __fsub_rn((a), (b))
+#define TNT_MUL(a, b) __fmul_rn((a), (b))
+
+__device__ __forceinline__ bool has_at_initiation(const DpShared &sh, const uint8_t *q, const uint8_t *t, int k)
+{
+	do { --k; } while (k != 0 && (q[k] == bGAP || t[k] == bGAP)); // nuc_cruc.cpp:2888-2905
+	const int bp = sh.bbp[q[k]*NB + t[k]];
+	return bp == P_AT || bp == P_TA;
+}
+
+__device__ bool nc_evaluate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct, AlnState &a)
+{
+	const uint8_t *q = a.q + a.b, *t = a.t + a.b;
+	const int n = a.e - a.b;
+	const uint8_t *bbp = sh.bbp;
+	const uint8_t *wc = sh.wc;
+	const float *__restrict__ H = th->H;
+	const float *__restrict__ S = th->S;
+
+#define ADD_HS(idx) do { const int _x = (idx); dH = TNT_ADD(dH, __ldg(H + _x)); dS = TNT_ADD(dS, __ldg(S + _x)); } while (0)
+#define SUB_HS(idx) do { const int _x = (idx); dH = TNT_SUB(dH, __ldg(H + _x)); dS = TNT_SUB(dS, __ldg(S + _x)); } while (0)
+#define NONVIRT_PAIR(p) (((p)%7 < bE) && ((p)/7 < bE))
+
+	int terminal = P_NONE, last_last = P_NONE, last = P_NONE;
+	float dH = th->init_H, dS = TNT_ADD(th->init_S, 0.0f);
+	unsigned nqgap = 0, ntgap = 0, nmm = 0, num_base = 0;
+	bool terminal_5 = false;
+
+	int cur = bbp[q[0]*NB + t[0]];
+	if (wc[cur]) {
+		terminal_5 = true;
+		if (cur == P_AT || cur == P_TA) { dH = TNT_ADD(dH, th->at_H); dS = TNT_ADD(dS, th->at_S); }
+	}
+	num_base += is_virtual(q[0]) ? 0u : 1u;
+	num_base += is_virtual(t[0]) ? 0u : 1u;
+
+	for (int k = 1; k < n; ++k) {
+		last_last = last;
+		last = cur;
+		cur = bbp[q[k]*NB + t[k]];
+		const bool in_loop = (q[k] == bGAP) || (t[k] == bGAP) || (!wc[last] && !wc[cur]);
+
+		if (!in_loop) {
+			if (k == 1 && !wc[last] && NONVIRT_PAIR(last)) {
+				ADD_HS((int)bbp[(last/7)*NB + bE]*NPAIR + cur);
+				ADD_HS((int)bbp[bE*NB + (last%7)]*NPAIR + cur);
+			}
+			else if (k == n - 1 && !wc[cur] && NONVIRT_PAIR(cur)) {
+				ADD_HS(last*NPAIR + (int)bbp[q[k]*NB + bE]);
+				ADD_HS(last*NPAIR + (int)bbp[bE*NB + t[k]]);
+			}
+			else ADD_HS(last*NPAIR + cur);
+			num_base += is_virtual(q[k]) ? 0u : 1u;
+			num_base += is_virtual(t[k]) ? 0u : 1u;
+		}
+
+		if (wc[cur] || cur == P_EE) {
+			terminal = cur;
+			if (!terminal_5) {
+				terminal_5 = true;
+				if (cur == P_AT || cur == P_TA) { dH = TNT_ADD(dH, th->at_H); dS = TNT_ADD(dS, th->at_S); }
+			}
+			const unsigned max_gap = max(nqgap, ntgap);
+
+			if (nmm > 1 || (max_gap > 0 && nmm == 1)) {
+				// an internal loop closes on this column
+				const unsigned gap_diff = nqgap > ntgap ? nqgap - ntgap : ntgap - nqgap;
+				const unsigned loop_size = nmm*2 + gap_diff;
+				if (loop_size == 2 && (last == P_GT || last == P_TG) && (last_last == P_GT || last_last == P_TG)) {
+					ADD_HS(last_last*NPAIR + last);
+					num_base += 2;
+				}
+				else {
+					dS = TNT_ADD(dS, __ldg(th->loop_S + loop_size));
+					dS = TNT_ADD(dS, TNT_MUL((float)gap_diff, th->asym_loop_dS));
+					int rhs_q = k - 1, rhs_t = k - 1;
+					SUB_HS(last*NPAIR + cur);
+					const bool last_has_gap = (last%7 == bGAP) || (last/7 >= bGAP);
+					if (!last_has_gap) ADD_HS(last*NPAIR + cur); // loop-terminal table == NN table
+					else {
+						int mm = P_NONE;
+						if (last/7 == bGAP) {
+							for (;;) {
+								if (!is_virtual(q[rhs_q])) { mm = bbp[q[rhs_q]*NB + (last%7)]; break; }
+								if (rhs_q == 0) break;
+								--rhs_q;
+							}
+						}
+						else {
+							for (;;) {
+								if (!is_virtual(t[rhs_t])) { mm = bbp[(last/7)*NB + t[rhs_t]]; break; }
+								if (rhs_t == 0) break;
+								--rhs_t;
+							}
+						}
+						ADD_HS(mm*NPAIR + cur);
+					}
+					int lhs_q = k - 1, lhs_t = k - 1;
+					for (;;) {
+						const int pm = bbp[q[lhs_q]*NB + t[lhs_t]];
+						if (wc[pm]) {
+							++lhs_q; ++lhs_t;
+							if (q[lhs_q] != bGAP && t[lhs_t] != bGAP) SUB_HS(pm*NPAIR + (int)bbp[q[lhs_q]*NB + t[lhs_t]]);
+							else {
+								num_base += 2;
+								while (q[lhs_q] == bGAP) ++lhs_q;
+								while (t[lhs_t] == bGAP) ++lhs_t;
+							}
+							ADD_HS(pm*NPAIR + (int)bbp[q[lhs_q]*NB + t[lhs_t]]);
+							break;
+						}
+						if (lhs_q == 0) break;
+						--lhs_q; --lhs_t;
+					}
+					if (rhs_q != lhs_q) ++num_base;
+					if (rhs_t != lhs_t) ++num_base;
+				}
+			}
+			else if (nqgap || ntgap) {
+				const unsigned bulge = max(nqgap, ntgap);
+				if (bulge == 1) ADD_HS(last_last*NPAIR + cur);
+				dS = TNT_ADD(dS, __ldg(th->bulge_S + bulge));
+				if (bulge != 1 && (q[k] == bA || q[k] == bT)) dS = TNT_ADD(dS, th->bulge_at_S);
+				if (bulge != 1 && has_at_initiation(sh, q, t, k)) dS = TNT_ADD(dS, th->bulge_at_S);
+			}
+			nqgap = ntgap = nmm = 0;
+		}
+		else nmm += (!is_virtual(q[k]) && !is_virtual(t[k])) ? 1u : 0u;
+
+		nqgap += (q[k] == bGAP) ? 1u : 0u;
+		ntgap += (t[k] == bGAP) ? 1u : 0u;
+	}
+
+	if (terminal == P_AT || terminal == P_TA) { dH = TNT_ADD(dH, th->at_H); dS = TNT_ADD(dS, th->at_S); }
+
+	a.dH = dH;
+	a.dS = dS;
+	if (dH >= 0.0f) return false;
+
+	// dS += SALT*(0.5f*num_base - 1)*log[Na+]
+	dS = TNT_ADD(dS, TNT_MUL(TNT_MUL(th->salt, TNT_SUB(TNT_MUL(0.5f, (float)num_base), 1.0f)), th->log_na));
+	a.dS = dS;
+	const float tm = TNT_SUB(__fdiv_rn(dH, TNT_ADD(r_log_ct, dS)), 273.15f);
+	a.tm = fmaxf(0.0f, tm);
+	return true;
+#undef ADD_HS
+#undef SUB_HS
+#undef NONVIRT_PAIR
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage 2+3 driver: every maximal cell, every enumerated path
+// (tm_dimer :2517-2540, enumerate_dimer_alignments :973-1170)
+// ------------------------------------------------------------------------------------------
+struct Best {
+	bool valid;
+	float dH, dS, tm;
+};
+
+template <int NT>
+__device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct,
+	const uint8_t *tgt, int Lt, const uint16_t *trace, const DpResult &dp,
+	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags)
+{
+	const int Lq = sh.Lq;
+	const float T = th->T;
+	best.valid = false;
+	best.dH = best.dS = best.tm = 0.0f;
+	if (dp.nmax == 0) return;
+
+	Branch stack[MAX_BRANCH];
+	const int ncell = Lq*Lt;
+	int seen = 0;
+
+	for (int cell = dp.last_raise; cell < ncell && seen < dp.nmax; ++cell) {
+		if (cell != dp.last_raise && !(trace[(size_t)cell*NT] & TW_CAND)) continue;
+		++seen;
+
+		bool first_time = true;
+		int nstack = 0, zero_count = -1;
+		unsigned trace_count = 0;
+		float best_dg = TNT_SUB(best.dH, TNT_MUL(T, best.dS));
+
+		for (;;) {
+			if (!first_time && nstack == 0 && zero_count <= 0) break;
+			if (16u < trace_count) break; // max_dp_path_enum = 16 (nuc_cruc.cpp:332, :1005)
+			++trace_count;
+			first_time = false;
+
+			AlnState &a = work;
+			a.b = a.e = 2; // room for a dangling-end column in front
+			a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
+			a.dH = a.dS = a.tm = 0.0f;
+			nc_trace_back<NT>(sh, tgt, Lt, trace, cell, stack, nstack, zero_count, a, flags);
+			if (flags & (F_OOB | F_STACK)) return;
+
+			// frayed ends: drop columns until both ends are Watson-Crick (:1022-1054)
+			while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.e - 1]*NB + a.t[a.e - 1]]]) {
+				if (!is_virtual(a.q[a.e - 1])) --a.lm_q;
+				if (!is_virtual(a.t[a.e - 1])) ++a.lm_t;
+				--a.e;
+			}
+			while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.b]*NB + a.t[a.b]]]) {
+				if (!is_virtual(a.q[a.b])) ++a.fm_q;
+				if (!is_virtual(a.t[a.b])) --a.fm_t;
+				++a.b;
+			}
+
+			if (zero_count == 0 && nstack > 0) {
+				while (nstack > 0) {
+					Branch &br = stack[nstack - 1];
+					bool more = false;
+					while ((br.cur = (uint8_t)(br.cur << 1)) < T_INVALID) if (br.cur & br.mask) { more = true; break; }
+					if (more) break;
+					--nstack;
+				}
+				zero_count = -1;
+			}
+
+			// optional dangling-end virtual bases (:1088-1137)
+			if (th->dangle5 && (a.fm_q != 0 || a.fm_t != Lt - 1)) {
+				int qb, tb;
+				if (a.fm_q == 0) qb = bE;
+				else { --a.fm_q; if (a.fm_q < 0 || a.fm_q >= Lq) { flags |= F_OOB; return; } qb = sh.q[a.fm_q]; }
+				if (a.fm_t == Lt - 1) tb = bE;
+				else { ++a.fm_t; if (a.fm_t < 0 || a.fm_t >= Lt) { flags |= F_OOB; return; } tb = tgt[a.fm_t]; }
+				--a.b;
+				a.q[a.b] = (uint8_t)qb;
+				a.t[a.b] = (uint8_t)tb;
+			}
+			if (th->dangle3 && (a.lm_q != Lq - 1 || a.lm_t != 0)) {
+				int qb, tb;
+				if (a.lm_q == Lq - 1) qb = bE;
+				else { ++a.lm_q; if (a.lm_q < 0 || a.lm_q >= Lq) { flags |= F_OOB; return; } qb = sh.q[a.lm_q]; }
+				if (a.lm_t == 0) tb = bE;
+				else { --a.lm_t; if (a.lm_t < 0 || a.lm_t >= Lt) { flags |= F_OOB; return; } tb = tgt[a.lm_t]; }
+				if (a.e < MAX_COLS) { a.q[a.e] = (uint8_t)qb; a.t[a.e] = (uint8_t)tb; ++a.e; }
+				else flags |= F_TRUNC;
+			}
+
+			if (a.e - a.b < 3) continue;
+
+			if (nc_evaluate(sh, th, r_log_ct, a)) {
+				const float local_dg = TNT_SUB(a.dH, TNT_MUL(T, a.dS));
+				if (!best.valid || local_dg < best_dg) {
+					best.valid = true;
+					best.dH = a.dH;
+					best.dS = a.dS;
+					best.tm = a.tm;
+					best_dg = local_dg;
+					// keep the winning columns
+					best_aln.b = a.b; best_aln.e = a.e;
+					best_aln.fm_q = a.fm_q; best_aln.fm_t = a.fm_t;
+					best_aln.lm_q = a.lm_q; best_aln.lm_t = a.lm_t;
+					for (int c = a.b; c < a.e; ++c) { best_aln.q[c] = a.q[c]; best_aln.t[c] = a.t[c]; }
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-oligo filters' inputs (nuc_cruc_anchor.cpp:143-192, :249-298; nuc_cruc.h:389-483)
+// ------------------------------------------------------------------------------------------
+__device__ inline unsigned nc_anchor5(const DpShared &sh, const uint8_t *tgt, int Lt, const AlnState &a)
+{
+	unsigned anchor = 0;
+	int qi = 0, ti = a.fm_q + a.fm_t;
+	if (a.e > a.b && a.t[a.b] == bE) return 0;
+	if (a.e > a.b && a.q[a.b] == bE) --ti;
+	if (ti >= Lt) return 0;
+	while (qi < sh.Lq && ti >= 0 && dev_complementary(sh.q[qi], tgt[ti])) { ++anchor; ++qi; --ti; }
+	return anchor;
+}
+
+__device__ inline unsigned nc_anchor3(const DpShared &sh, const uint8_t *tgt, int Lt, const AlnState &a)
+{
+	unsigned anchor = 0;
+	int qi = sh.Lq - 1, ti = (a.lm_q + a.lm_t + 1) - sh.Lq;
+	if (a.e > a.b && a.t[a.e - 1] == bE) return 0;
+	if (a.e > a.b && a.q[a.e - 1] == bE) ++ti;
+	if (ti >= Lt || ti < 0) return 0;
+	while (qi >= 0 && ti < Lt && dev_complementary(sh.q[qi], tgt[ti])) { ++anchor; --qi; ++ti; }
+	return anchor;
+}
+
+__device__ inline void nc_counts(const DpShared &sh, const AlnState &a, unsigned &mm, unsigned &gaps, unsigned &poly)
+{
+	unsigned aligned = 0, run = 0;
+	mm = gaps = poly = 0;
+	for (int c = a.b; c < a.e; ++c) {
+		const int q = a.q[c], t = a.t[c];
+		if (!is_virtual(q)) {
+			if (!is_virtual(t) && !dev_complementary(q, t)) ++mm;
+			++aligned;
+		}
+		gaps += (q == bGAP) + (t == bGAP);
+		if (t >= bM && t <= bN) { if (++run > poly) poly = run; }
+		else run = 0;
+	}
+	mm += (unsigned)sh.Lq - aligned;
+}
+
+} // namespace tnt

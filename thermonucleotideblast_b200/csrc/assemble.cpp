@@ -1,0 +1,352 @@
+// Stage C on the host: bound oligos -> hits.  O(#bound sites) work; the candidates themselves
+// never leave the GPU.
+
+#include "assemble.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+
+#include "thermo.h"
+
+namespace tnt {
+
+namespace {
+
+const char kBaseChar[] = "ACGTI$-MRSVWYHKDBN"; // nuc_cruc_output.cpp:11
+
+// Text form of an alignment, three lines, including the unaligned 5'/3' overhangs with ':' for
+// complementary-but-unaligned positions (nuc_cruc_output.cpp:87-204).
+std::string render_alignment(const BoundRec &r, const OligoStrand &os)
+{
+	const int Lq = os.len, Lt = r.Lt;
+	auto q = [&](int i) -> int { return (i >= 0 && i < Lq) ? os.seq[i] : (int)bGAP; };
+	auto t = [&](int i) -> int { return (i >= 0 && i < Lt) ? r.win[i] : (int)bGAP; };
+
+	const int prefix = std::max(0, std::min<int>(r.fm_q, Lt - 1 - r.fm_t));
+	const int suffix = std::max(0, std::min<int>(Lq - 1 - r.lm_q, r.lm_t));
+
+	std::string s;
+	s.reserve(3*(r.ncols + prefix + suffix + 8));
+	s += "5' ";
+	for (int i = 0; i < prefix; ++i) s += kBaseChar[q(r.fm_q - prefix + i)];
+	for (int c = 0; c < r.ncols; ++c) s += kBaseChar[r.cols_q[c]];
+	for (int i = 0; i < suffix; ++i) s += kBaseChar[q(r.lm_q + 1 + i)];
+	s += " 3'\n   ";
+	for (int i = 0; i < prefix; ++i) s += complementary(q(r.fm_q - prefix + i), t(r.fm_t + prefix - i)) ? ':' : ' ';
+	for (int c = 0; c < r.ncols; ++c) s += complementary(r.cols_t[c], r.cols_q[c]) ? '|' : ' ';
+	for (int i = 0; i < suffix; ++i) s += complementary(q(r.lm_q + 1 + i), t(r.lm_t - i - 1)) ? ':' : ' ';
+	s += "\n3' ";
+	for (int i = prefix; i > 0; --i) s += kBaseChar[t(r.fm_t + i)];
+	for (int c = 0; c < r.ncols; ++c) s += kBaseChar[r.cols_t[c]];
+	for (int i = 1; i <= suffix; ++i) s += kBaseChar[t(r.lm_t - i)];
+	s += " 5'";
+	return s;
+}
+
+uint32_t intern(std::string &arena, const std::string &s)
+{
+	const uint32_t off = (uint32_t)arena.size();
+	arena.append(s);
+	arena.push_back('\0');
+	return off;
+}
+
+tnt_bound_oligo empty_slot()
+{
+	// hybrid_sig::init() (hybrid_sig.h:52-107)
+	tnt_bound_oligo b{};
+	b.oligo = TNT_OLIGO_NONE;
+	b.tm = -1.0f;
+	b.dH = 100.0f;
+	b.dS = 0.0f;
+	b.num_mm = b.num_gap = -1;
+	return b;
+}
+
+tnt_bound_oligo slot_of(const BoundSite &s, int oligo, std::string &arena)
+{
+	tnt_bound_oligo b{};
+	b.oligo = oligo;
+	b.loc_5 = s.loc5;
+	b.loc_3 = s.loc3;
+	b.tm = s.tm;
+	b.dH = s.dH;
+	b.dS = s.dS;
+	b.num_mm = (int8_t)s.num_mm;   // hybrid_sig stores int8_t (hybrid_sig.h:165-176)
+	b.num_gap = (int8_t)s.num_gap;
+	b.anchor_5 = s.anchor5;
+	b.anchor_3 = s.anchor3;
+	b.align_off = intern(arena, s.alignment);
+	return b;
+}
+
+tnt_hit blank_hit(int assay_index, int assay_id, uint32_t target)
+{
+	tnt_hit h{};
+	h.assay_index = assay_index;
+	h.assay_id = assay_id;
+	h.target_id = target;
+	h.primer_strand = TNT_PLUS;
+	h.probe_strand = TNT_PLUS;
+	h.forward = h.reverse = h.probe = empty_slot();
+	h.forward_clamp = h.reverse_clamp = -1;
+	return h;
+}
+
+// Duplicate windows can report the same target range; one site survives per (loc_5, loc_3).
+// mask-variant order (bind_oligo.cpp:49-82): highest Tm, then most mismatches, then the longest
+// alignment text; hash-variant (oligo_info::operator<, tntblast.h:230-242): highest Tm.
+void unique_sites(std::vector<const BoundSite *> &v, bool mask_variant)
+{
+	if (mask_variant) {
+		// the reference collects with push_front over a list ordered by seed position
+		std::stable_sort(v.begin(), v.end(), [](const BoundSite *a, const BoundSite *b) { return a->target_loc > b->target_loc; });
+		std::stable_sort(v.begin(), v.end(), [](const BoundSite *a, const BoundSite *b) {
+			if (a->loc5 != b->loc5) return a->loc5 < b->loc5;
+			if (a->loc3 != b->loc3) return a->loc3 < b->loc3;
+			if (a->tm == b->tm) {
+				if (a->num_mm == b->num_mm) return a->alignment.size() > b->alignment.size();
+				return a->num_mm > b->num_mm;
+			}
+			return a->tm > b->tm;
+		});
+	}
+	else {
+		// seeds are visited in diagonal order (bind_oligo.cpp:157-161)
+		std::stable_sort(v.begin(), v.end(), [](const BoundSite *a, const BoundSite *b) {
+			return ((int)a->query_loc - (int)a->target_loc) < ((int)b->query_loc - (int)b->target_loc);
+		});
+		std::stable_sort(v.begin(), v.end(), [](const BoundSite *a, const BoundSite *b) {
+			if (a->loc5 != b->loc5) return a->loc5 < b->loc5;
+			if (a->loc3 != b->loc3) return a->loc3 < b->loc3;
+			return a->tm > b->tm;
+		});
+	}
+	size_t m = 0;
+	for (size_t i = 0; i < v.size(); ++i)
+		if (m == 0 || v[m - 1]->loc5 != v[i]->loc5 || v[m - 1]->loc3 != v[i]->loc3) v[m++] = v[i];
+	v.resize(m);
+}
+
+void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int assay_id, bool has_probe,
+	const AssembleOptions &opt, std::vector<tnt_hit> &hits, std::string &arena)
+{
+	// per (role, strand) uniqueness, then one list ordered by (loc_5, loc_3)
+	std::vector<const BoundSite *> all;
+	for (int plus = 0; plus < 2; ++plus)
+		for (int role = 0; role < 3; ++role) {
+			std::vector<const BoundSite *> cat;
+			for (const BoundSite *s : group) if (s->plus == plus && s->role == role) cat.push_back(s);
+			unique_sites(cat, true);
+			all.insert(all.end(), cat.begin(), cat.end());
+		}
+	std::stable_sort(all.begin(), all.end(), [](const BoundSite *a, const BoundSite *b) {
+		if (a->loc5 == b->loc5) return a->loc3 < b->loc3; // sort_by_oligo_loc, amplicon_search.cpp:12-26
+		return a->loc5 < b->loc5;
+	});
+
+	const bool apply_mmc = opt.min_max_primer_clamp >= 0;
+	const unsigned mmc = apply_mmc ? (unsigned)opt.min_max_primer_clamp : 0u;
+
+	for (size_t fi = 0; fi < all.size(); ++fi) {
+		const BoundSite &f = *all[fi];
+		if (f.plus || f.role == TNT_OLIGO_P) continue;
+		for (size_t ri = fi + 1; ri < all.size(); ++ri) {
+			const BoundSite &r = *all[ri];
+			if (!r.plus || r.role == TNT_OLIGO_P) continue;
+			if (!opt.single_primer_pcr && f.role == r.role) continue;
+			if (f.loc3 >= r.loc5) continue;
+			if ((r.loc3 - f.loc5 + 1) > (int)opt.max_len) continue;
+			if (apply_mmc && (unsigned)std::max(f.anchor3, r.anchor3) <= mmc) continue;
+
+			const bool swap_out = (f.role == TNT_OLIGO_R && r.role == TNT_OLIGO_F);
+			const BoundSite &fo = swap_out ? r : f, &ro = swap_out ? f : r;
+			const int f_oligo = (f.role == TNT_OLIGO_R && r.role == TNT_OLIGO_R) ? TNT_OLIGO_R : TNT_OLIGO_F;
+			const int r_oligo = (f.role == TNT_OLIGO_F && r.role == TNT_OLIGO_F) ? TNT_OLIGO_F : TNT_OLIGO_R;
+
+			auto emit = [&](const BoundSite *p) {
+				tnt_hit h = blank_hit(assay_index, assay_id, f.target);
+				h.primer_strand = (f.role == TNT_OLIGO_F) ? TNT_PLUS : TNT_MINUS;
+				h.amp_first = f.loc5;
+				h.amp_last = r.loc3;
+				h.forward = slot_of(fo, f_oligo, arena);
+				h.reverse = slot_of(ro, r_oligo, arena);
+				h.forward_clamp = (int8_t)fo.anchor3;
+				h.reverse_clamp = (int8_t)ro.anchor3;
+				if (p) {
+					h.probe = slot_of(*p, TNT_OLIGO_P, arena);
+					h.probe_first = p->loc5;
+					h.probe_last = p->loc3;
+					h.probe_strand = p->plus ? TNT_PLUS : TNT_MINUS;
+				}
+				hits.push_back(h);
+			};
+
+			if (!has_probe) { emit(nullptr); continue; }
+			for (size_t pi = fi + 1; pi < ri; ++pi) {
+				const BoundSite &p = *all[pi];
+				if (p.role != TNT_OLIGO_P) continue;
+				if (!(p.loc5 >= f.loc5 && p.loc3 <= r.loc3)) continue;
+				if (p.plus == f.plus) { if (p.loc5 <= f.loc3) continue; } // same strand as the forward primer
+				else if (p.loc3 >= r.loc5) continue;                      // same strand as the reverse primer
+				emit(&p);
+			}
+		}
+	}
+}
+
+void join_padlock(const std::vector<const BoundSite *> &group, int assay_index, int assay_id,
+	const AssembleOptions &opt, std::vector<tnt_hit> &hits, std::string &arena)
+{
+	const int max_len = opt.assay_format == TNT_ASSAY_MIPS ? (int)opt.max_len : 0;
+	for (int plus = 0; plus < 2; ++plus) {
+		std::vector<const BoundSite *> up, down;
+		for (const BoundSite *s : group) {
+			if (s->plus != plus) continue;
+			(s->role == TNT_OLIGO_R ? up : down).push_back(s);
+		}
+		unique_sites(up, false);
+		unique_sites(down, false);
+		for (const BoundSite *u : up)
+			for (const BoundSite *d : down) {
+				const int gap = plus ? d->loc5 - u->loc3 - 1 : u->loc5 - d->loc3 - 1;
+				if (gap < 0 || gap > max_len) continue;
+				tnt_hit h = blank_hit(assay_index, assay_id, u->target);
+				h.primer_strand = plus ? TNT_PLUS : TNT_MINUS;
+				h.amp_first = plus ? u->loc5 : d->loc5;
+				h.amp_last = plus ? d->loc3 : u->loc3;
+				if (h.amp_first > h.amp_last) throw std::runtime_error(":padlock: start > stop");
+				h.forward = slot_of(*d, TNT_OLIGO_F, arena);
+				h.reverse = slot_of(*u, TNT_OLIGO_R, arena);
+				h.forward_clamp = (int8_t)d->anchor3;
+				h.reverse_clamp = (int8_t)u->anchor5;
+				hits.push_back(h);
+			}
+	}
+}
+
+void join_probe(const std::vector<const BoundSite *> &group, int assay_index, int assay_id,
+	std::vector<tnt_hit> &hits, std::string &arena)
+{
+	for (int plus = 0; plus < 2; ++plus) { // minus strand first (probe_search.cpp:92-151)
+		std::vector<const BoundSite *> b;
+		for (const BoundSite *s : group) if (s->plus == plus) b.push_back(s);
+		unique_sites(b, false);
+		for (const BoundSite *s : b) {
+			if (s->loc5 > s->loc3) throw std::runtime_error(":hybrid: probe_start > probe_stop");
+			tnt_hit h = blank_hit(assay_index, assay_id, s->target);
+			h.probe = slot_of(*s, TNT_OLIGO_P, arena);
+			h.probe_first = s->loc5;
+			h.probe_last = s->loc3;
+			h.probe_strand = plus ? TNT_PLUS : TNT_MINUS;
+			hits.push_back(h);
+		}
+	}
+}
+
+} // namespace
+
+BoundSite make_site(const BoundRec &r, const OligoStrand &os)
+{
+	BoundSite s;
+	s.assay = os.assay;
+	s.role = os.role;
+	s.plus = os.plus;
+	s.target = r.target;
+	s.loc5 = r.loc5;
+	s.loc3 = r.loc3;
+	s.tm = r.tm; s.dH = r.dH; s.dS = r.dS; s.dG = r.dG;
+	s.anchor5 = r.anchor5; s.anchor3 = r.anchor3;
+	s.num_mm = r.num_mm; s.num_gap = r.num_gap; s.poly_degen = r.poly_degen;
+	s.valid = r.valid;
+	s.flags = r.flags;
+	s.query_loc = r.k;
+	s.target_loc = r.t;
+	s.win_start = r.win_start;
+	s.win_stop = r.win_stop;
+	s.q_first = r.fm_q;
+	s.q_last = r.lm_q;
+	s.t_first = r.lm_t; // alignment_range_target (nuc_cruc_anchor.cpp:386-389)
+	s.t_last = r.fm_t;
+	if (r.valid) s.alignment = render_alignment(r, os);
+	return s;
+}
+
+void assemble_hits(std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
+	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
+	std::vector<tnt_hit> &hits, std::string &arena)
+{
+	// (fragment, assay) pairs in ascending order, like the reference's nested loops
+	std::map<std::pair<uint32_t, int>, std::vector<const BoundSite *>> groups;
+	for (const BoundSite &s : sites) groups[{s.target, s.assay}].push_back(&s);
+	for (auto &kv : groups) {
+		const int ai = kv.first.second;
+		const int id = assay_ids[(size_t)ai];
+		if (assay_has_primers[(size_t)ai]) { // tntblast_local.cpp:559-611
+			if (opt.assay_format == TNT_ASSAY_PADLOCK || opt.assay_format == TNT_ASSAY_MIPS)
+				join_padlock(kv.second, ai, id, opt, hits, arena);
+			else join_pcr(kv.second, ai, id, assay_has_probe[(size_t)ai] != 0, opt, hits, arena);
+		}
+		else join_probe(kv.second, ai, id, hits, arena); // :612-625
+	}
+}
+
+void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop, SeqMode &mode)
+{
+	const bool primers = h.forward.oligo != TNT_OLIGO_NONE;
+	if (!primers) {
+		start = h.probe_first;
+		stop = h.probe_last;
+		mode = h.probe_strand == TNT_PLUS ? SeqMode::ProbePlus : SeqMode::ProbeMinus;
+		return;
+	}
+	start = h.amp_first;
+	stop = h.amp_last;
+	if (assay_format == TNT_ASSAY_PADLOCK || assay_format == TNT_ASSAY_MIPS)
+		mode = h.primer_strand == TNT_MINUS ? SeqMode::PadlockMinusStrand : SeqMode::PadlockPlusStrand;
+	else mode = h.primer_strand == TNT_PLUS ? SeqMode::PcrPlus : SeqMode::PcrMinus;
+}
+
+std::string render_hit_sequence(int start, int stop, SeqMode mode, int seq_len, int lo, const std::vector<uint8_t> &codes)
+{
+	static const char fwd[] = "ACGTIMRSVWYHKDBN-";   // hash_base_to_ascii (seq.h:58-101)
+	static const char cmp[] = "TGCAIKYSBWRDMHVN-";   // hash_base_to_ascii_complement (seq.h:103-146)
+	const int n = stop - start + 1;
+	std::string s((size_t)n, '-');
+	auto code_at = [&](long p) -> int {
+		const long k = p - lo;
+		if (k < 0 || k >= (long)codes.size()) throw std::runtime_error("internal: sequence fetch out of range");
+		const int c = codes[(size_t)k];
+		if (c > 16) throw std::runtime_error(":hash_base_to_ascii: Illegal base");
+		return c;
+	};
+	bool forward = true;
+	int first_i = 0;
+	switch (mode) {
+	case SeqMode::PcrPlus: forward = true; first_i = std::max(0, -start); break;                 // amplicon_search.cpp:512-523
+	case SeqMode::PcrMinus: forward = false; first_i = std::max(0, stop - seq_len + 1); break;  // :526-537
+	case SeqMode::ProbePlus: forward = true; first_i = 0; break;                                // probe_search.cpp:205-219
+	case SeqMode::ProbeMinus: forward = false; first_i = 0; break;                              // :129-142
+	case SeqMode::PadlockMinusStrand: forward = true; first_i = std::max(0, 1 - start); break;  // padlock_search.cpp:206-218
+	case SeqMode::PadlockPlusStrand: forward = false; first_i = std::max(0, stop - seq_len - 1); break; // :341-352
+	}
+	if (forward) {
+		long p = std::max(0, start);
+		for (int i = first_i; i < n; ++i, ++p) {
+			if (p >= seq_len) break;
+			s[(size_t)i] = fwd[code_at(p)];
+		}
+	}
+	else {
+		long p = std::min(stop, seq_len - 1);
+		for (int i = first_i; i < n; ++i, --p) {
+			if (p < 0) break;
+			s[(size_t)i] = cmp[code_at(p)];
+		}
+	}
+	return s;
+}
+
+} // namespace tnt

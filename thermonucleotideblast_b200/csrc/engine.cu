@@ -1,0 +1,949 @@
+// tntb200 engine: host orchestration + C ABI (include/tntb200.h).
+//
+// Host mirror of the reference call surface for the search hot path:
+//   tnt_engine_add_target   <- read_bio_seq + DNAHash::hash         tntblast_local.cpp:510-534
+//   tnt_engine_search       <- amplicon()/padlock()/hybrid() calls  tntblast_local.cpp:554-626
+// with the per-(fragment, assay) loop turned into three device stages:
+//   A  k_seed_scan / k_region_scan   seeds, one per (oligo strand, diagonal)
+//   B  k_align                       NucCruc Tm/dG of every candidate window + per-oligo filters
+//   C  assembly of amplicons / padlock sites / probe sites from the bound oligos (assemble.cpp)
+// There is no CPU fallback: every stage-A/B result comes from the kernels in kernels.cuh.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tntb200.h"
+#include "assemble.h"
+#include "kernels.cuh"
+#include "thermo.h"
+
+using namespace tnt;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct CudaError : std::runtime_error {
+	using std::runtime_error::runtime_error;
+};
+
+#define CUDA_OK(expr)                                                                      \
+	do {                                                                                   \
+		cudaError_t _e = (expr);                                                           \
+		if (_e != cudaSuccess) {                                                           \
+			char _b[512];                                                                  \
+			snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+			throw CudaError(_b);                                                           \
+		}                                                                                  \
+	} while (0)
+
+template <class T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t cap = 0;
+	~DevBuf() { if (p) cudaFree(p); }
+	// grow to at least n elements; `keep` elements of the old contents survive
+	void reserve(size_t n, size_t keep, cudaStream_t st)
+	{
+		if (n <= cap) return;
+		size_t ncap = std::max(n, cap + cap/2);
+		T *np = nullptr;
+		CUDA_OK(cudaMalloc(&np, ncap*sizeof(T)));
+		if (keep && p) CUDA_OK(cudaMemcpyAsync(np, p, keep*sizeof(T), cudaMemcpyDeviceToDevice, st));
+		if (p) { CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(p)); }
+		p = np;
+		cap = ncap;
+	}
+	void upload(const std::vector<T> &v, cudaStream_t st)
+	{
+		reserve(std::max<size_t>(v.size(), 1), 0, st);
+		if (!v.empty()) CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice, st));
+	}
+};
+
+constexpr size_t STAGE_BYTES = 32u << 20; // pinned staging buffers (x2)
+
+struct AssayHost {
+	int id;
+	std::string F, R, P;
+	int fdeg, rdeg, pdeg;
+};
+
+// A set of oligo strands searched together + its k-mer lookup table
+struct OsSet {
+	std::vector<OligoStrand> os;
+	std::vector<uint16_t> keys;     // [nos][MAX_OLIGO] little-endian keys
+	std::vector<uint32_t> present, offset, entry;
+	DevBuf<OligoStrand> d_os;
+	DevBuf<uint16_t> d_keys;
+	DevBuf<uint32_t> d_present, d_offset, d_entry;
+	uint32_t nkeys = 0;
+	uint64_t total_words = 0;
+	int max_len = 0, max_words = 0;
+};
+
+uint32_t le_key(uint16_t word, int W)
+{
+	// reference words carry the first base in the high digits; the packed database is read
+	// with the first base in the low bits
+	uint32_t k = 0;
+	for (int i = 0; i < W; ++i) k |= ((word >> (2*(W - 1 - i))) & 3u) << (2*i);
+	return k;
+}
+
+} // namespace
+
+struct tnt_engine {
+	tnt_engine_params prm{};
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8]{};
+
+	Thermo h_thermo{};
+	DevBuf<Thermo> d_thermo;
+
+	// resident database
+	DevBuf<uint64_t> db2;
+	DevBuf<uint32_t> nmask;
+	DevBuf<uint64_t> exc_pos;
+	DevBuf<uint8_t> exc_code;
+	uint64_t nwords = 0; // 32-base words in use
+	uint64_t nexc = 0;
+	uint64_t total_bases = 0;
+	std::vector<Target> targets;
+	DevBuf<Target> d_targets;
+	bool targets_dirty = true;
+	std::vector<ScanTile> tiles;
+	DevBuf<ScanTile> d_tiles;
+
+	uint8_t *h_stage[2] = {nullptr, nullptr};
+	uint8_t *d_stage[2] = {nullptr, nullptr};
+	cudaEvent_t stage_free[2]{};
+	DevBuf<uint32_t> block_count;
+	uint64_t *h_total = nullptr; // pinned
+	uint64_t *d_total = nullptr;
+
+	std::vector<AssayHost> assays;
+
+	// scratch of the search
+	DevBuf<Candidate> d_cand;
+	DevBuf<uint32_t> d_cand_count;
+	DevBuf<AlignUnit> d_units;
+	DevBuf<uint16_t> d_trace;
+	DevBuf<BoundRec> d_out;
+	DevBuf<uint32_t> d_out_count;
+	DevBuf<unsigned long long> d_cells;
+	DevBuf<Region> d_regions;
+	DevBuf<uint8_t> d_extract;
+
+	std::vector<tnt_hit> hits;
+	std::string arena;
+	tnt_stats stats{};
+	tnt_search_options last_opt{};
+
+	~tnt_engine()
+	{
+		for (int i = 0; i < 2; ++i) {
+			if (h_stage[i]) cudaFreeHost(h_stage[i]);
+			if (d_stage[i]) cudaFree(d_stage[i]);
+			if (stage_free[i]) cudaEventDestroy(stage_free[i]);
+		}
+		if (h_total) cudaFreeHost(h_total);
+		if (d_total) cudaFree(d_total);
+		for (auto &e : ev) if (e) cudaEventDestroy(e);
+		if (stream) cudaStreamDestroy(stream);
+	}
+
+	DbView view() const
+	{
+		DbView v;
+		v.db2 = db2.p; v.nmask = nmask.p; v.exc_pos = exc_pos.p; v.exc_code = exc_code.p; v.targets = d_targets.p;
+		return v;
+	}
+
+	void sync_targets()
+	{
+		if (!targets_dirty) return;
+		d_targets.upload(targets, stream);
+		tiles.clear();
+		for (uint32_t t = 0; t < targets.size(); ++t)
+			for (uint32_t s = 0; s < targets[t].len; s += SCAN_TILE) tiles.push_back(ScanTile{t, s});
+		d_tiles.upload(tiles, stream);
+		targets_dirty = false;
+	}
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Target upload: pinned double buffer -> H2D -> pack kernels
+// ------------------------------------------------------------------------------------------
+void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_out)
+{
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	if (e->targets.size() >= (1u << 24)) throw std::runtime_error("tnt_engine_add_target: too many fragments (limit 2^24)");
+
+	Target tg{};
+	tg.base = e->nwords*32u;
+	if (tg.base & 63u) tg.base += 32u; // fragments start on 64-base boundaries
+	tg.len = len;
+	tg.exc_begin = e->nexc;
+
+	const uint64_t first_word = tg.base/32u;
+	const uint64_t words = ((uint64_t)len + 31u)/32u;
+	const uint64_t need_words = first_word + words + 4; // +pad: the scan reads one word ahead
+	if (need_words > e->db2.cap) {
+		e->db2.reserve(need_words, e->nwords, e->stream);
+		e->nmask.reserve(e->db2.cap, e->nwords, e->stream);
+	}
+	// words skipped by the alignment and the read-ahead pad must be zero
+	CUDA_OK(cudaMemsetAsync(e->db2.p + e->nwords, 0, (need_words - e->nwords)*sizeof(uint64_t), e->stream));
+	CUDA_OK(cudaMemsetAsync(e->nmask.p + e->nwords, 0, (need_words - e->nwords)*sizeof(uint32_t), e->stream));
+
+	uint32_t done = 0;
+	int slot = 0;
+	while (done < len) {
+		const uint32_t n = (uint32_t)std::min<uint64_t>(STAGE_BYTES, len - done);
+		CUDA_OK(cudaEventSynchronize(e->stage_free[slot]));
+		std::memcpy(e->h_stage[slot], codes + done, n);
+		CUDA_OK(cudaMemcpyAsync(e->d_stage[slot], e->h_stage[slot], n, cudaMemcpyHostToDevice, e->stream));
+
+		const uint32_t nblocks = (n + PACK_BASES_PER_BLOCK - 1)/PACK_BASES_PER_BLOCK;
+		e->block_count.reserve(nblocks, 0, e->stream);
+		k_pack<<<nblocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], n, e->db2.p, e->nmask.p,
+			first_word + done/32u, e->block_count.p);
+		k_scan_counts<<<1, 1024, 0, e->stream>>>(e->block_count.p, nblocks, e->d_total);
+		CUDA_OK(cudaMemcpyAsync(e->h_total, e->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		const uint64_t nexc = *e->h_total;
+		if (nexc) {
+			e->exc_pos.reserve(e->nexc + nexc, e->nexc, e->stream);
+			e->exc_code.reserve(e->exc_pos.cap, e->nexc, e->stream);
+			k_emit_exceptions<<<nblocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], n, e->block_count.p,
+				e->nexc, tg.base + done, e->exc_pos.p, e->exc_code.p);
+			e->nexc += nexc;
+		}
+		CUDA_OK(cudaEventRecord(e->stage_free[slot], e->stream));
+		CUDA_OK(cudaGetLastError());
+		done += n;
+		slot ^= 1;
+	}
+	tg.exc_end = e->nexc;
+	e->nwords = first_word + words;
+	e->total_bases += len;
+	if (e->exc_pos.cap == 0) { e->exc_pos.reserve(16, 0, e->stream); e->exc_code.reserve(16, 0, e->stream); }
+	e->targets.push_back(tg);
+	e->targets_dirty = true;
+	if (id_out) *id_out = (uint32_t)e->targets.size() - 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Oligo strands
+// ------------------------------------------------------------------------------------------
+OligoStrand make_os(const tnt_engine *e, int assay_index, int role, bool plus, const std::string &oligo,
+	float ct, float min_tm, float max_tm, float min_dg, float max_dg, uint32_t clamp5, uint32_t clamp3,
+	const tnt_search_options &o)
+{
+	OligoStrand s{};
+	const int L = (int)oligo.size();
+	if (L > MAX_OLIGO) throw std::runtime_error("oligo longer than TNT_MAX_OLIGO_LEN (56) bases");
+	if (L == 0) throw std::runtime_error("empty oligo");
+	for (int i = 0; i < L; ++i) {
+		const int b = base_from_ascii(oligo[i]);
+		if (b < 0) throw std::runtime_error(":char_to_nucleic_acid: Illegal base");
+		s.seq[i] = (uint8_t)b;
+	}
+	s.len = L;
+	s.nwords = build_words(oligo.c_str(), e->prm.word_size, plus, s.words);
+	s.plus = plus ? 1 : 0;
+	s.assay = assay_index;
+	s.role = role;
+	if (!(ct > 0.0f)) throw std::runtime_error(":NucCruc::tm_dimer: Invalid strand_concentration");
+	s.r_log_ct = r_log_ct(ct);
+	s.min_tm = min_tm; s.max_tm = max_tm; s.min_dg = min_dg; s.max_dg = max_dg;
+	s.clamp5 = clamp5; s.clamp3 = clamp3;
+	s.max_gap = o.max_gap; s.max_mismatch = o.max_mismatch; s.max_poly_degen = o.max_poly_degen;
+	// A window without any alignment has Tm = 0 and dG = 0 in the reference and is then
+	// reported with stale coordinates.  Bounds that would let it through are refused.
+	if (min_tm <= 0.0f && max_tm >= 0.0f && min_dg <= 0.0f && max_dg >= 0.0f)
+		throw std::runtime_error("search bounds accept non-binding sites (Tm = 0, dG = 0): set a minimum Tm > 0 or a maximum dG < 0");
+	return s;
+}
+
+void finish_set(tnt_engine *e, OsSet &set)
+{
+	const int W = e->prm.word_size;
+	set.nkeys = 1u << (2*W);
+	const size_t nos = set.os.size();
+	if (nos >= (1u << 24)) throw std::runtime_error("too many oligo strands");
+	set.keys.assign(nos*MAX_OLIGO, 0);
+	set.offset.assign((size_t)set.nkeys + 1, 0);
+	set.present.assign((set.nkeys + 31)/32, 0);
+	set.total_words = 0;
+	set.max_len = 0;
+	set.max_words = 0;
+	for (size_t s = 0; s < nos; ++s) {
+		const OligoStrand &o = set.os[s];
+		set.max_len = std::max(set.max_len, o.len);
+		set.max_words = std::max(set.max_words, o.nwords);
+		for (int k = 0; k < o.nwords; ++k) {
+			const uint32_t key = le_key(o.words[k], W);
+			set.keys[s*MAX_OLIGO + k] = (uint16_t)key;
+			set.offset[key + 1]++;
+			set.present[key >> 5] |= 1u << (key & 31u);
+			set.total_words++;
+		}
+	}
+	for (uint32_t k = 0; k < set.nkeys; ++k) set.offset[k + 1] += set.offset[k];
+	set.entry.assign(std::max<size_t>(set.total_words, 1), 0);
+	std::vector<uint32_t> fill(set.offset.begin(), set.offset.end() - 1);
+	for (size_t s = 0; s < nos; ++s)
+		for (int k = 0; k < set.os[s].nwords; ++k)
+			set.entry[fill[set.keys[s*MAX_OLIGO + k]]++] = (uint32_t)(s << 8) | (uint32_t)k;
+	set.d_os.upload(set.os, e->stream);
+	set.d_keys.upload(set.keys, e->stream);
+	set.d_present.upload(set.present, e->stream);
+	set.d_offset.upload(set.offset, e->stream);
+	set.d_entry.upload(set.entry, e->stream);
+}
+
+ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
+{
+	ScanArgs a{};
+	a.db = e->view();
+	a.wt.present = set.d_present.p;
+	a.wt.offset = set.d_offset.p;
+	a.wt.entry = set.d_entry.p;
+	a.wt.nkeys = set.nkeys;
+	a.os = set.d_os.p;
+	a.os_keys = set.d_keys.p;
+	a.tiles = e->d_tiles.p;
+	a.W = e->prm.word_size;
+	a.cand = e->d_cand.p;
+	a.cand_count = e->d_cand_count.p;
+	a.cap = cap;
+	return a;
+}
+
+// Align every candidate currently in the buckets of `set`; append the survivors to `out`.
+// Returns false if a bucket overflowed (the caller shrinks the chunk and retries).
+bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec> &out, bool emit_all,
+	std::vector<uint32_t> *counts_out = nullptr)
+{
+	const size_t nos = set.os.size();
+	std::vector<uint32_t> counts(nos);
+	CUDA_OK(cudaMemcpyAsync(counts.data(), e->d_cand_count.p, nos*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	if (counts_out) *counts_out = counts;
+	std::vector<AlignUnit> units;
+	uint64_t total = 0;
+	for (size_t s = 0; s < nos; ++s) {
+		if (counts[s] > cap) return false;
+		for (uint32_t b = 0; b < counts[s]; b += ALIGN_THREADS)
+			units.push_back(AlignUnit{(uint32_t)s, b, std::min<uint32_t>(ALIGN_THREADS, counts[s] - b)});
+		total += counts[s];
+	}
+	e->stats.seeds += total;
+	if (units.empty()) return true;
+	if (emit_all && nos != 1) throw std::runtime_error("emit_all needs a single oligo strand");
+
+	e->d_units.upload(units, e->stream);
+
+	const int max_lt = set.max_len + 2*NUM_FLANK;
+	const size_t smem = ((TABLE*4 + NB*NB + 52 + MAX_OLIGO + 15) & ~15) + (size_t)3*(max_lt + 1)*ALIGN_THREADS*sizeof(int32_t);
+	CUDA_OK(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 1;
+	CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, ALIGN_THREADS, smem));
+	per_sm = std::max(per_sm, 1);
+	const uint32_t grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*per_sm);
+	const uint32_t trace_cells = (uint32_t)set.max_len*(uint32_t)max_lt;
+	e->d_trace.reserve((size_t)grid*trace_cells*ALIGN_THREADS, 0, e->stream);
+
+	size_t out_cap = emit_all ? (size_t)total : std::max<size_t>(e->d_out.cap, 1u << 16);
+	for (;;) {
+		e->d_out.reserve(out_cap, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_out_count.p, 0, sizeof(uint32_t), e->stream));
+		AlignArgs a{};
+		a.db = e->view();
+		a.thermo = e->d_thermo.p;
+		a.os = set.d_os.p;
+		a.cand = e->d_cand.p;
+		a.cap = cap;
+		a.units = e->d_units.p;
+		a.nunits = (uint32_t)units.size();
+		a.max_lt = max_lt;
+		a.trace = e->d_trace.p;
+		a.trace_cells = trace_cells;
+		a.out = e->d_out.p;
+		a.out_count = e->d_out_count.p;
+		a.out_cap = (uint32_t)out_cap;
+		a.emit_all = emit_all ? 1 : 0;
+		a.cells = e->d_cells.p;
+		CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
+		k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaEventRecord(e->ev[3], e->stream));
+		e->stats.kernel_launches++;
+		uint32_t n = 0;
+		CUDA_OK(cudaMemcpyAsync(&n, e->d_out_count.p, sizeof(n), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		float ms = 0;
+		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
+		e->stats.align_ms += ms;
+		if (emit_all) n = (uint32_t)total;
+		else if (n > out_cap) { // overflow: enlarge and redo this launch (cell counter is corrected below)
+			out_cap = (size_t)n + n/4;
+			continue;
+		}
+		e->stats.alignments += total;
+		const size_t old = out.size();
+		out.resize(old + n);
+		if (n) CUDA_OK(cudaMemcpyAsync(out.data() + old, e->d_out.p, (size_t)n*sizeof(BoundRec), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		return true;
+	}
+}
+
+// Stage A+B over all fragments for one oligo-strand set, chunked so the candidate buckets fit.
+void scan_and_align(tnt_engine *e, OsSet &set, std::vector<BoundRec> &out)
+{
+	if (set.os.empty() || e->tiles.empty()) return;
+	const size_t nos = set.os.size();
+	const double keys = (double)set.nkeys;
+	// expected candidates per base of database for the busiest oligo strand
+	const double per_base = (double)set.max_words/keys;
+	const size_t budget_bytes = (size_t)1 << 30;
+	const size_t cap_budget = std::max<size_t>(budget_bytes/sizeof(Candidate)/nos, 4096);
+	uint32_t tiles_per_chunk = (uint32_t)e->tiles.size();
+	{
+		// cap = 2 * expected + slack
+		const double exp_per_tile = per_base*SCAN_TILE;
+		const double max_tiles = ((double)cap_budget - 2048.0)/(2.0*std::max(exp_per_tile, 1e-9));
+		if (max_tiles < (double)tiles_per_chunk) tiles_per_chunk = (uint32_t)std::max(1.0, max_tiles);
+	}
+
+	e->d_cand_count.reserve(nos, 0, e->stream);
+	const size_t smem_scan = ((set.nkeys + 31)/32)*sizeof(uint32_t);
+	CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+
+	uint32_t t0 = 0;
+	while (t0 < e->tiles.size()) {
+		uint32_t t1 = (uint32_t)std::min<size_t>(e->tiles.size(), (size_t)t0 + tiles_per_chunk);
+		for (;;) {
+			const uint32_t ntiles = t1 - t0;
+			uint32_t cap = (uint32_t)std::min<double>(4.0e9, 2.0*per_base*SCAN_TILE*ntiles + 2048.0);
+			cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(cap_budget, 4096)*(ntiles == 1 ? 64 : 1));
+			e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
+			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*sizeof(uint32_t), e->stream));
+			ScanArgs a = scan_args(e, set, cap);
+			a.tile_begin = t0;
+			a.tile_end = t1;
+			const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)e->sm_count*8u);
+			CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
+			k_seed_scan<<<grid, SCAN_THREADS, smem_scan, e->stream>>>(a);
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
+			e->stats.kernel_launches++;
+			const uint64_t seeds_before = e->stats.seeds;
+			const bool ok = align_buckets(e, set, cap, out, false);
+			float ms = 0;
+			CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+			e->stats.scan_ms += ms;
+			if (ok) {
+				uint64_t bases = 0;
+				for (uint32_t t = t0; t < t1; ++t)
+					bases += std::min<uint32_t>(SCAN_TILE, e->targets[e->tiles[t].target].len - e->tiles[t].start);
+				e->stats.scan_bytes += bases/4 + bases/8 + (e->stats.seeds - seeds_before)*sizeof(Candidate);
+				break;
+			}
+			if (ntiles == 1) throw std::runtime_error("seed bucket overflow on a single tile (pathological repeat content)");
+			t1 = t0 + std::max<uint32_t>(1, ntiles/2); // shrink the chunk and retry
+		}
+		t0 = t1;
+	}
+}
+
+// Stage-2: scan regions with the given set
+void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> &regions, std::vector<BoundRec> &out)
+{
+	if (set.os.empty() || regions.empty()) return;
+	const size_t nos = set.os.size();
+	e->d_cand_count.reserve(nos, 0, e->stream);
+	e->d_regions.upload(regions, e->stream);
+	// every position of a region can seed at most (words of one assay) candidates; size the
+	// buckets for the worst bucket = all positions of all regions of that assay
+	std::map<int, uint64_t> per_assay;
+	for (const Region &r : regions) per_assay[r.assay] += r.stop - r.start;
+	uint64_t worst = 0;
+	for (auto &kv : per_assay) worst = std::max(worst, kv.second);
+	uint32_t cap = (uint32_t)std::min<uint64_t>(worst + 64, 1u << 26);
+	for (;;) {
+		e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*sizeof(uint32_t), e->stream));
+		RegionScanArgs ra{};
+		ra.s = scan_args(e, set, cap);
+		ra.regions = e->d_regions.p;
+		ra.nregions = (uint32_t)regions.size();
+		const uint32_t grid = std::min<uint32_t>((uint32_t)regions.size(), (uint32_t)e->sm_count*8u);
+		CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
+		k_region_scan<<<grid, SCAN_THREADS, 0, e->stream>>>(ra);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
+		e->stats.kernel_launches++;
+		const bool ok = align_buckets(e, set, cap, out, false);
+		float ms = 0;
+		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+		e->stats.scan_ms += ms;
+		if (ok) return;
+		cap *= 2;
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Search
+// ------------------------------------------------------------------------------------------
+void search(tnt_engine *e, const tnt_search_options &o)
+{
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->hits.clear();
+	e->arena.clear();
+	e->arena.push_back('\0'); // offset 0 == empty string
+	e->stats = tnt_stats{};
+	e->last_opt = o;
+	e->stats.db_bases = e->total_bases;
+	e->sync_targets();
+	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
+	cudaEvent_t t_begin = e->ev[4], t_end = e->ev[5];
+	CUDA_OK(cudaEventRecord(t_begin, e->stream));
+
+	if (o.assay_format != TNT_ASSAY_PCR && o.assay_format != TNT_ASSAY_PROBE &&
+		o.assay_format != TNT_ASSAY_PADLOCK && o.assay_format != TNT_ASSAY_MIPS)
+		throw std::runtime_error("unsupported assay format");
+
+	OsSet stage1, stage2;
+	const int W = e->prm.word_size;
+	(void)W;
+
+	for (size_t ai = 0; ai < e->assays.size(); ++ai) {
+		const AssayHost &as = e->assays[ai];
+		const bool has_primers = !as.F.empty() && !as.R.empty();
+		const bool has_probe = !as.P.empty();
+		const float fct = o.forward_primer_strand/as.fdeg;
+		const float rct = o.reverse_primer_strand/as.rdeg;
+		const float pct = o.probe_strand/as.pdeg;
+		if (has_primers) {
+			if (o.assay_format == TNT_ASSAY_PCR) {
+				for (int plus = 0; plus < 2; ++plus) {
+					OsSet &dst = plus ? stage2 : stage1;
+					dst.os.push_back(make_os(e, (int)ai, TNT_OLIGO_F, plus, as.F, fct, o.min_primer_tm, o.max_primer_tm,
+						o.min_primer_dg, o.max_primer_dg, 0, o.primer_clamp, o));
+					dst.os.push_back(make_os(e, (int)ai, TNT_OLIGO_R, plus, as.R, rct, o.min_primer_tm, o.max_primer_tm,
+						o.min_primer_dg, o.max_primer_dg, 0, o.primer_clamp, o));
+				}
+				if (has_probe)
+					for (int plus = 0; plus < 2; ++plus)
+						stage2.os.push_back(make_os(e, (int)ai, TNT_OLIGO_P, plus, as.P, pct, o.min_probe_tm, o.max_probe_tm,
+							o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, o.probe_clamp_3, o));
+			}
+			else if (o.assay_format == TNT_ASSAY_PADLOCK || o.assay_format == TNT_ASSAY_MIPS) {
+				for (int plus = 0; plus < 2; ++plus) {
+					if (!(o.target_strand & (plus ? TNT_STRAND_PLUS : TNT_STRAND_MINUS))) continue;
+					// upstream probe = "reverse" oligo with a 5' clamp, downstream = "forward" with a 3' clamp
+					stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_R, plus, as.R, rct, o.min_probe_tm, o.max_probe_tm,
+						o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, 0, o));
+					stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_F, plus, as.F, fct, o.min_probe_tm, o.max_probe_tm,
+						o.min_probe_dg, o.max_probe_dg, 0, o.probe_clamp_3, o));
+				}
+			}
+			else throw std::runtime_error("assay with primers in PROBE format");
+		}
+		else if (has_probe) {
+			for (int plus = 0; plus < 2; ++plus) {
+				if (!(o.target_strand & (plus ? TNT_STRAND_PLUS : TNT_STRAND_MINUS))) continue;
+				stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_P, plus, as.P, pct, o.min_probe_tm, o.max_probe_tm,
+					o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, o.probe_clamp_3, o));
+			}
+		}
+	}
+
+	std::vector<BoundRec> recs1, recs2;
+	finish_set(e, stage1);
+	scan_and_align(e, stage1, recs1);
+
+	if (!stage2.os.empty() && !recs1.empty()) {
+		finish_set(e, stage2);
+		// Partner primers / probes can only matter downstream of a bound minus-strand primer
+		// (amplicon_search.cpp:359-441: f on the minus strand, r and p after it, amplicon <= max_len;
+		// cull_oligo_match :679-765 uses max_len + 50 on seed positions).
+		std::vector<Region> regions;
+		const uint32_t slack = 64;
+		for (const BoundRec &b : recs1) {
+			if (b.flags & (F_OOB | F_STACK)) continue;
+			const Target &tg = e->targets[b.target];
+			Region r;
+			r.target = b.target;
+			r.assay = stage1.os[b.os].assay;
+			const int64_t lo = std::min<int64_t>((int64_t)b.t, (int64_t)b.loc5) - slack;
+			const int64_t hi = std::max<int64_t>((int64_t)b.t, (int64_t)b.loc5) + (int64_t)o.max_len + 50 + slack;
+			r.start = (uint32_t)std::max<int64_t>(0, lo);
+			r.stop = (uint32_t)std::min<int64_t>(tg.len, std::max<int64_t>(hi, 0));
+			if (r.stop > r.start) regions.push_back(r);
+		}
+		std::sort(regions.begin(), regions.end(), [](const Region &a, const Region &b) {
+			if (a.target != b.target) return a.target < b.target;
+			if (a.assay != b.assay) return a.assay < b.assay;
+			return a.start < b.start;
+		});
+		std::vector<Region> merged;
+		for (const Region &r : regions) {
+			if (!merged.empty() && merged.back().target == r.target && merged.back().assay == r.assay && r.start <= merged.back().stop)
+				merged.back().stop = std::max(merged.back().stop, r.stop);
+			else merged.push_back(r);
+		}
+		region_scan_and_align(e, stage2, merged, recs2);
+	}
+
+	CUDA_OK(cudaEventRecord(t_end, e->stream));
+	unsigned long long cells = 0;
+	CUDA_OK(cudaMemcpyAsync(&cells, e->d_cells.p, sizeof(cells), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->stats.dp_cells = cells;
+	float ms = 0;
+	CUDA_OK(cudaEventElapsedTime(&ms, t_begin, t_end));
+	e->stats.total_ms = ms;
+
+	// Stage C
+	std::vector<BoundSite> sites;
+	sites.reserve(recs1.size() + recs2.size());
+	for (const BoundRec &b : recs1) sites.push_back(make_site(b, stage1.os[b.os]));
+	for (const BoundRec &b : recs2) sites.push_back(make_site(b, stage2.os[b.os]));
+	for (const BoundSite &s : sites)
+		if (s.flags & (F_OOB | F_STACK))
+			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
+	e->stats.bound_sites = sites.size();
+
+	AssembleOptions ao;
+	ao.assay_format = o.assay_format;
+	ao.max_len = o.max_len;
+	ao.single_primer_pcr = o.single_primer_pcr != 0;
+	ao.min_max_primer_clamp = o.min_max_primer_clamp;
+	std::vector<int> assay_ids, assay_has_primers, assay_has_probe;
+	for (const AssayHost &a : e->assays) {
+		assay_ids.push_back(a.id);
+		assay_has_primers.push_back(!a.F.empty() && !a.R.empty());
+		assay_has_probe.push_back(!a.P.empty());
+	}
+	assemble_hits(sites, ao, assay_ids, assay_has_primers, assay_has_probe, e->hits, e->arena);
+	e->stats.hits = e->hits.size();
+}
+
+long hit_sequence(tnt_engine *e, const tnt_hit *h, char *out, size_t cap)
+{
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	if (h->target_id >= e->targets.size()) throw std::runtime_error("bad target id");
+	const Target &tg = e->targets[h->target_id];
+	e->sync_targets();
+	int start, stop;
+	SeqMode mode;
+	hit_sequence_plan(*h, e->last_opt.assay_format, start, stop, mode);
+	const int n = stop - start + 1;
+	if (n <= 0) throw std::runtime_error("hit with start > stop");
+	// fetch the overlapping part of the fragment
+	const int lo = std::max(start, 0), hi = std::min<int64_t>(stop, (int64_t)tg.len - 1);
+	std::vector<uint8_t> codes;
+	if (hi >= lo) {
+		const uint32_t m = (uint32_t)(hi - lo + 1);
+		e->d_extract.reserve(m, 0, e->stream);
+		k_extract_codes<<<std::min<uint32_t>((m + 255)/256, 1024u), 256, 0, e->stream>>>(e->view(), h->target_id, (uint32_t)lo, m, e->d_extract.p);
+		CUDA_OK(cudaGetLastError());
+		codes.resize(m);
+		CUDA_OK(cudaMemcpyAsync(codes.data(), e->d_extract.p, m, cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+	}
+	const std::string s = render_hit_sequence(start, stop, mode, (int)tg.len, lo, codes);
+	if (out && cap) {
+		const size_t m = std::min(cap - 1, s.size());
+		std::memcpy(out, s.data(), m);
+		out[m] = '\0';
+	}
+	return (long)s.size();
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+#define API_BEGIN try {
+#define API_END                                                        \
+	}                                                                  \
+	catch (const std::exception &ex) { g_error = ex.what(); return -1; } \
+	catch (const char *msg) { g_error = msg; return -1; }              \
+	catch (...) { g_error = "unknown error"; return -1; }              \
+	return 0;
+
+extern "C" {
+
+const char *tnt_last_error(void) { return g_error.c_str(); }
+int tnt_abi_version(void) { return TNTB200_ABI_VERSION; }
+
+int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
+{
+	API_BEGIN
+	if (!p || !out) throw std::runtime_error("null argument");
+	if (p->dinkelbach) throw std::runtime_error("the Dinkelbach Tm mode is not implemented in the B200 engine");
+	if (p->word_size < 3 || p->word_size > 8) throw std::runtime_error(":DNAHash: Unsupported word length");
+	int ndev = 0;
+	cudaError_t ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev == 0)
+		throw std::runtime_error(std::string("no usable CUDA device (the engine has no CPU fallback): ") + cudaGetErrorString(ce));
+	if (p->device < 0 || p->device >= ndev) throw std::runtime_error("bad device ordinal");
+	CUDA_OK(cudaSetDevice(p->device));
+	cudaDeviceProp prop;
+	CUDA_OK(cudaGetDeviceProperties(&prop, p->device));
+	if (prop.major < 10) throw std::runtime_error("the engine is built for sm_100a (B200) only");
+
+	std::unique_ptr<tnt_engine> e(new tnt_engine);
+	e->prm = *p;
+	e->sm_count = prop.multiProcessorCount;
+	CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	for (auto &ev : e->ev) CUDA_OK(cudaEventCreate(&ev));
+	for (int i = 0; i < 2; ++i) {
+		CUDA_OK(cudaMallocHost(&e->h_stage[i], STAGE_BYTES));
+		CUDA_OK(cudaMalloc(&e->d_stage[i], STAGE_BYTES));
+		CUDA_OK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
+	}
+	CUDA_OK(cudaMallocHost(&e->h_total, sizeof(uint64_t)));
+	CUDA_OK(cudaMalloc(&e->d_total, sizeof(uint64_t)));
+	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
+	e->d_thermo.reserve(1, 0, e->stream);
+	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
+	e->d_out_count.reserve(1, 0, e->stream);
+	e->d_cells.reserve(1, 0, e->stream);
+	e->exc_pos.reserve(16, 0, e->stream);
+	e->exc_code.reserve(16, 0, e->stream);
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	*out = e.release();
+	API_END
+}
+
+void tnt_engine_destroy(tnt_engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->prm.device);
+	cudaDeviceSynchronize();
+	delete e;
+}
+
+int tnt_engine_add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *target_id)
+{
+	API_BEGIN
+	if (!e || (!codes && len)) throw std::runtime_error("null argument");
+	add_target(e, codes, len, target_id);
+	API_END
+}
+
+int tnt_engine_clear_targets(tnt_engine *e)
+{
+	API_BEGIN
+	if (!e) throw std::runtime_error("null argument");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->targets.clear();
+	e->tiles.clear();
+	e->nwords = 0;
+	e->nexc = 0;
+	e->total_bases = 0;
+	e->targets_dirty = true;
+	e->hits.clear();
+	API_END
+}
+
+int tnt_engine_set_assays(tnt_engine *e, const tnt_assay *assays, int32_t n)
+{
+	API_BEGIN
+	if (!e || (n && !assays)) throw std::runtime_error("null argument");
+	std::vector<AssayHost> v;
+	for (int i = 0; i < n; ++i) {
+		AssayHost a;
+		a.id = assays[i].id;
+		a.F = assays[i].forward ? assays[i].forward : "";
+		a.R = assays[i].reverse ? assays[i].reverse : "";
+		a.P = assays[i].probe ? assays[i].probe : "";
+		a.fdeg = assays[i].forward_degen > 0 ? assays[i].forward_degen : 1;
+		a.rdeg = assays[i].reverse_degen > 0 ? assays[i].reverse_degen : 1;
+		a.pdeg = assays[i].probe_degen > 0 ? assays[i].probe_degen : 1;
+		if (a.F.empty() != a.R.empty()) throw std::runtime_error("an assay needs both primers or none");
+		if (a.F.empty() && a.P.empty()) throw std::runtime_error("assay without oligos");
+		v.push_back(a);
+	}
+	e->assays.swap(v);
+	API_END
+}
+
+int tnt_engine_search(tnt_engine *e, const tnt_search_options *opt)
+{
+	API_BEGIN
+	if (!e || !opt) throw std::runtime_error("null argument");
+	search(e, *opt);
+	API_END
+}
+
+int tnt_engine_get_hits(tnt_engine *e, const tnt_hit **hits, size_t *n, const char **arena, size_t *arena_size)
+{
+	API_BEGIN
+	if (!e) throw std::runtime_error("null argument");
+	if (hits) *hits = e->hits.data();
+	if (n) *n = e->hits.size();
+	if (arena) *arena = e->arena.data();
+	if (arena_size) *arena_size = e->arena.size();
+	API_END
+}
+
+int tnt_engine_get_stats(tnt_engine *e, tnt_stats *out)
+{
+	API_BEGIN
+	if (!e || !out) throw std::runtime_error("null argument");
+	*out = e->stats;
+	API_END
+}
+
+long tnt_engine_hit_sequence(tnt_engine *e, const tnt_hit *hit, char *out, size_t cap)
+{
+	try {
+		if (!e || !hit) throw std::runtime_error("null argument");
+		return hit_sequence(e, hit, out, cap);
+	}
+	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
+	catch (...) { g_error = "unknown error"; return -1; }
+}
+
+long tnt_engine_seeds(tnt_engine *e, uint32_t target_id, const char *oligo, int32_t plus_strand,
+	uint32_t *query_loc, uint32_t *target_loc, long cap_out)
+{
+	try {
+		if (!e || !oligo) throw std::runtime_error("null argument");
+		if (target_id >= e->targets.size()) throw std::runtime_error("bad target id");
+		CUDA_OK(cudaSetDevice(e->prm.device));
+		e->sync_targets();
+		e->stats = tnt_stats{};
+		OsSet set;
+		tnt_search_options o{};
+		o.max_gap = o.max_mismatch = o.max_poly_degen = 999;
+		set.os.push_back(make_os(e, 0, TNT_OLIGO_P, plus_strand != 0, oligo, 1.0e-6f, 1.0f, 9999.0f, -9999.0f, 0.0f, 0, 0, o));
+		finish_set(e, set);
+		// tiles of this fragment only
+		uint32_t t0 = 0, t1 = 0;
+		bool found = false;
+		for (uint32_t t = 0; t < e->tiles.size(); ++t) {
+			if (e->tiles[t].target != target_id) continue;
+			if (!found) { t0 = t; found = true; }
+			t1 = t + 1;
+		}
+		std::vector<Candidate> cands;
+		if (t1 > t0 && set.os[0].nwords > 0) {
+			uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)e->targets[target_id].len*2 + 64, 1u << 28);
+			e->d_cand_count.reserve(1, 0, e->stream);
+			e->d_cand.reserve(cap, 0, e->stream);
+			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, sizeof(uint32_t), e->stream));
+			ScanArgs a = scan_args(e, set, cap);
+			a.tile_begin = t0;
+			a.tile_end = t1;
+			const size_t smem_scan = ((set.nkeys + 31)/32)*sizeof(uint32_t);
+			CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+			k_seed_scan<<<std::min<uint32_t>(t1 - t0, (uint32_t)e->sm_count*8u), SCAN_THREADS, smem_scan, e->stream>>>(a);
+			CUDA_OK(cudaGetLastError());
+			uint32_t n = 0;
+			CUDA_OK(cudaMemcpyAsync(&n, e->d_cand_count.p, sizeof(n), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+			if (n > cap) throw std::runtime_error("seed buffer overflow");
+			cands.resize(n);
+			if (n) CUDA_OK(cudaMemcpyAsync(cands.data(), e->d_cand.p, n*sizeof(Candidate), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+		}
+		// the reference list is ordered by diagonal (stable sort by q - t, bind_oligo.cpp:98)
+		std::sort(cands.begin(), cands.end(), [](const Candidate &a, const Candidate &b) {
+			const int da = (int)(a.target_k >> 24) - (int)a.t, db = (int)(b.target_k >> 24) - (int)b.t;
+			return da < db;
+		});
+		for (long i = 0; i < (long)cands.size() && i < cap_out; ++i) {
+			query_loc[i] = cands[i].target_k >> 24;
+			target_loc[i] = cands[i].t;
+		}
+		return (long)cands.size();
+	}
+	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
+	catch (...) { g_error = "unknown error"; return -1; }
+}
+
+int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32_t plus_strand,
+	float strand_conc, const uint32_t *query_loc, const uint32_t *target_loc, long n, tnt_align_result *out)
+{
+	API_BEGIN
+	if (!e || !oligo || (n && (!query_loc || !target_loc || !out))) throw std::runtime_error("null argument");
+	if (target_id >= e->targets.size()) throw std::runtime_error("bad target id");
+	if (n > (1L << 26)) throw std::runtime_error("too many candidates in one call");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->sync_targets();
+	e->stats = tnt_stats{};
+	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
+	OsSet set;
+	tnt_search_options o{};
+	o.max_gap = o.max_mismatch = o.max_poly_degen = 999;
+	set.os.push_back(make_os(e, 0, TNT_OLIGO_P, plus_strand != 0, oligo, strand_conc, 1.0f, 9999.0f, -9999.0f, 0.0f, 0, 0, o));
+	finish_set(e, set);
+	std::vector<Candidate> cands((size_t)n);
+	for (long i = 0; i < n; ++i) {
+		if (query_loc[i] > 255) throw std::runtime_error("query_loc out of range");
+		cands[i].target_k = target_id | (query_loc[i] << 24);
+		cands[i].t = target_loc[i];
+	}
+	const uint32_t cap = (uint32_t)std::max<long>(n, 1);
+	e->d_cand.upload(cands, e->stream);
+	e->d_cand_count.reserve(1, 0, e->stream);
+	const uint32_t cnt = (uint32_t)n;
+	CUDA_OK(cudaMemcpyAsync(e->d_cand_count.p, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, e->stream));
+	std::vector<BoundRec> recs;
+	if (!align_buckets(e, set, cap, recs, true)) throw std::runtime_error("internal: bucket overflow");
+	for (long i = 0; i < n; ++i) {
+		const BoundSite s = make_site(recs[(size_t)i], set.os[0]);
+		tnt_align_result &r = out[i];
+		std::memset(&r, 0, sizeof(r));
+		r.tm = s.tm; r.dH = s.dH; r.dS = s.dS; r.dG = s.dG;
+		r.valid = s.valid;
+		r.target_start = s.win_start;
+		r.target_stop = s.win_stop;
+		if (s.flags & (F_OOB | F_STACK)) r.valid = -1;
+		if (s.valid) {
+			r.anchor5 = s.anchor5; r.anchor3 = s.anchor3;
+			r.num_mismatch = s.num_mm; r.num_gap = s.num_gap; r.max_poly_degen = s.poly_degen;
+			r.q_first = s.q_first; r.q_last = s.q_last; r.t_first = s.t_first; r.t_last = s.t_last;
+			r.loc_5 = s.loc5; r.loc_3 = s.loc3;
+			std::strncpy(r.alignment, s.alignment.c_str(), sizeof(r.alignment) - 1);
+		}
+	}
+	unsigned long long cells = 0;
+	CUDA_OK(cudaMemcpyAsync(&cells, e->d_cells.p, sizeof(cells), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->stats.dp_cells = cells;
+	API_END
+}
+
+int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms)
+{
+	API_BEGIN
+	(void)e; (void)opt; (void)candidates; (void)ms;
+	throw std::runtime_error("tnt_engine_scan_only: not implemented yet");
+	API_END
+}
+
+} // extern "C"

@@ -1,0 +1,481 @@
+// sm_100a kernels of the tntb200 engine: target packing, seed scan, NucCruc alignment.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "tnt_types.h"
+#include "align_core.cuh"
+
+namespace tnt {
+
+// ------------------------------------------------------------------------------------------
+// Resident database layout (HBM)
+//   db2  : 2 bit/base, 32 bases per uint64, base i of a word at bits [2i, 2i+1]  (code & 3 --
+//          exactly what DNAHash::hash<SEQPTR> indexes, seq_hash.h:571-573)
+//   nmask: 1 bit/base, 32 bases per uint32, set where the seq.h code is > 3
+//   exc  : sparse, sorted by global base index: the codes behind the set mask bits
+//          (seq.h values 4..17; DB_GAP/DB_UNKNOWN are dropped by the window loader)
+// Fragments start at multiples of 64 bases; the tail of the last word is zero.
+// ------------------------------------------------------------------------------------------
+struct DbView {
+	const uint64_t *db2;
+	const uint32_t *nmask;
+	const uint64_t *exc_pos;
+	const uint8_t *exc_code;
+	const Target *targets;
+};
+
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_BASES_PER_THREAD = 32;
+constexpr int PACK_BASES_PER_BLOCK = PACK_THREADS*PACK_BASES_PER_THREAD;
+
+// Pass 1: bytes -> 2-bit words + mask words, per-block count of non-ACGT bases.
+// `first_word` is the index of the first uint64 of this chunk in db2 (== first uint32 in nmask).
+__global__ void __launch_bounds__(PACK_THREADS) k_pack(const uint8_t *__restrict__ codes, uint32_t n,
+	uint64_t *__restrict__ db2, uint32_t *__restrict__ nmask, uint64_t first_word, uint32_t *__restrict__ block_count)
+{
+	const uint32_t word = blockIdx.x*PACK_THREADS + threadIdx.x;
+	const uint32_t base0 = word*PACK_BASES_PER_THREAD;
+	uint64_t bits = 0;
+	uint32_t mask = 0;
+	if (base0 < n) {
+		const uint32_t m = min(32u, n - base0);
+		if (m == 32) {
+			const uint4 *p = reinterpret_cast<const uint4 *>(codes + base0);
+			const uint4 a = __ldg(p), b = __ldg(p + 1);
+			const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+#pragma unroll
+				for (int s = 0; s < 4; ++s) {
+					const uint32_t c = (w[k] >> (8*s)) & 0xffu;
+					const int i = k*4 + s;
+					bits |= (uint64_t)(c & 3u) << (2*i);
+					mask |= (c > 3u ? 1u : 0u) << i;
+				}
+			}
+		}
+		else {
+			for (uint32_t i = 0; i < m; ++i) {
+				const uint32_t c = codes[base0 + i];
+				bits |= (uint64_t)(c & 3u) << (2*i);
+				mask |= (c > 3u ? 1u : 0u) << i;
+			}
+		}
+		db2[first_word + word] = bits;
+		nmask[first_word + word] = mask;
+	}
+	// block reduction of popc(mask)
+	unsigned cnt = __popc(mask);
+	for (int off = 16; off; off >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+	__shared__ unsigned s_cnt[PACK_THREADS/32];
+	if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned t = 0;
+		for (int k = 0; k < PACK_THREADS/32; ++k) t += s_cnt[k];
+		block_count[blockIdx.x] = t;
+	}
+}
+
+// Pass 2: exclusive scan of the per-block counts (one block; nblocks <= 64 Ki).
+__global__ void __launch_bounds__(1024) k_scan_counts(uint32_t *block_count, uint32_t nblocks, uint64_t *total)
+{
+	__shared__ uint32_t s_part[1024];
+	const uint32_t per = (nblocks + 1023)/1024;
+	const uint32_t b0 = threadIdx.x*per;
+	uint32_t sum = 0;
+	for (uint32_t k = 0; k < per && b0 + k < nblocks; ++k) sum += block_count[b0 + k];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
+		for (int k = 0; k < 1024; ++k) { const uint32_t v = s_part[k]; s_part[k] = run; run += v; }
+		*total = run;
+	}
+	__syncthreads();
+	uint32_t run = s_part[threadIdx.x];
+	for (uint32_t k = 0; k < per && b0 + k < nblocks; ++k) {
+		const uint32_t v = block_count[b0 + k];
+		block_count[b0 + k] = run;
+		run += v;
+	}
+}
+
+// Pass 3: ordered emission of the non-ACGT codes.  `exc_base` = number of entries already stored.
+__global__ void __launch_bounds__(PACK_THREADS) k_emit_exceptions(const uint8_t *__restrict__ codes, uint32_t n,
+	const uint32_t *__restrict__ block_offset, uint64_t exc_base, uint64_t global_base0,
+	uint64_t *__restrict__ exc_pos, uint8_t *__restrict__ exc_code)
+{
+	const uint32_t word = blockIdx.x*PACK_THREADS + threadIdx.x;
+	const uint32_t base0 = word*PACK_BASES_PER_THREAD;
+	unsigned cnt = 0;
+	if (base0 < n) {
+		const uint32_t m = min(32u, n - base0);
+		for (uint32_t i = 0; i < m; ++i) cnt += codes[base0 + i] > 3u;
+	}
+	// exclusive scan over the block
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned incl = cnt;
+	for (int off = 1; off < 32; off <<= 1) {
+		const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= (unsigned)off) incl += v;
+	}
+	__shared__ unsigned s_warp[PACK_THREADS/32];
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	unsigned warp_off = 0;
+	for (unsigned k = 0; k < warp; ++k) warp_off += s_warp[k];
+	uint64_t dst = exc_base + block_offset[blockIdx.x] + warp_off + (incl - cnt);
+	if (cnt) {
+		const uint32_t m = min(32u, n - base0);
+		for (uint32_t i = 0; i < m; ++i) {
+			const uint32_t c = codes[base0 + i];
+			if (c > 3u) {
+				exc_pos[dst] = global_base0 + base0 + i;
+				exc_code[dst] = (uint8_t)c;
+				++dst;
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Base access helpers
+// ------------------------------------------------------------------------------------------
+// W consecutive 2-bit bases starting at global base index g, first base in the low bits.
+__device__ __forceinline__ uint32_t kmer_at(const uint64_t *__restrict__ db2, uint64_t g, uint32_t kmask)
+{
+	const uint64_t wi = g >> 5;
+	const unsigned sh = (unsigned)(g & 31u)*2u;
+	uint64_t x = __ldg(db2 + wi) >> sh;
+	if (sh > 48u) x |= __ldg(db2 + wi + 1) << (64u - sh);
+	return (uint32_t)x & kmask;
+}
+
+__device__ inline int exception_code(const DbView &db, const Target &tg, uint64_t g)
+{
+	uint64_t lo = tg.exc_begin, hi = tg.exc_end;
+	while (lo < hi) {
+		const uint64_t mid = (lo + hi) >> 1;
+		const uint64_t v = __ldg(db.exc_pos + mid);
+		if (v < g) lo = mid + 1;
+		else hi = mid;
+	}
+	return (int)__ldg(db.exc_code + lo);
+}
+
+// Load the NucCruc target for the window [start, stop) of a fragment
+// (bind_oligo.cpp:521-592 minus strand: complement + push_front; :1224-1295 plus strand).
+__device__ inline int load_window(const DbView &db, const Target &tg, uint32_t start, uint32_t stop, bool plus, uint8_t *out)
+{
+	int n = 0;
+	for (uint32_t p = start; p < stop; ++p) {
+		const uint64_t g = tg.base + p;
+		int code = (int)((__ldg(db.db2 + (g >> 5)) >> ((g & 31u)*2u)) & 3u);
+		if ((__ldg(db.nmask + (g >> 5)) >> (g & 31u)) & 1u) {
+			code = exception_code(db, tg, g);
+			if (code > 15) continue; // DB_GAP / DB_UNKNOWN are skipped silently
+		}
+		int b;
+		if (plus) b = code <= 4 ? code : code + 2;
+		else {
+			// complement: A<->T C<->G I M<->K R<->Y S V<->B W H<->D N
+			const uint8_t COMP[16] = {bT, bG, bC, bA, bI, bK, bY, bS, bB, bW, bR, bD, bM, bH, bV, bN};
+			b = COMP[code];
+		}
+		out[n++] = (uint8_t)b;
+	}
+	if (!plus) for (int i = 0, j = n - 1; i < j; ++i, --j) { const uint8_t x = out[i]; out[i] = out[j]; out[j] = x; }
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Seed scan (replaces DNAHash::hash + find/find_complement + the sort/unique by diagonal of
+// match_oligo_to_*_strand, seq_hash.h:524-779, bind_oligo.cpp:84-122)
+// ------------------------------------------------------------------------------------------
+struct WordTable {
+	const uint32_t *present;   // bitmap over the 4^W little-endian k-mer keys
+	const uint32_t *offset;    // [4^W + 1]
+	const uint32_t *entry;     // os << 8 | word index
+	uint32_t nkeys;            // 4^W
+};
+
+struct ScanTile { uint32_t target; uint32_t start; };
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_TILE = SCAN_THREADS*32;
+
+struct ScanArgs {
+	DbView db;
+	WordTable wt;
+	const OligoStrand *os;
+	const uint16_t *os_keys;   // [nos][MAX_OLIGO] little-endian keys of the compacted word list
+	const ScanTile *tiles;
+	uint32_t tile_begin, tile_end;
+	int W;
+	Candidate *cand;           // [nos][cap]
+	uint32_t *cand_count;      // [nos]
+	uint32_t cap;
+};
+
+// One seed survives per (oligo strand, diagonal): the one with the smallest word index.  A hit
+// (k, t) is therefore dropped when an earlier word k' < k of the same list matches the target
+// at t - (k - k') (same q - t).  `lo` bounds how far back that test may look (0 for a whole
+// fragment, the region start in a region scan).
+__device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ db2, uint64_t tbase, uint32_t t,
+	uint32_t k, uint32_t lo, const uint16_t *__restrict__ keys, uint32_t kmask)
+{
+	for (uint32_t kk = 0; kk < k; ++kk) {
+		const uint32_t back = k - kk;
+		if (t < lo + back) continue;
+		if (kmer_at(db2, tbase + t - back, kmask) == keys[kk]) return false;
+	}
+	return true;
+}
+
+__device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t os, uint32_t target, uint32_t k, uint32_t t)
+{
+	const uint32_t slot = atomicAdd(a.cand_count + os, 1u);
+	if (slot < a.cap) {
+		Candidate c;
+		c.target_k = target | (k << 24);
+		c.t = t;
+		a.cand[(size_t)os*a.cap + slot] = c;
+	}
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
+{
+	extern __shared__ uint32_t s_present[];
+	for (uint32_t i = threadIdx.x; i < (a.wt.nkeys + 31)/32; i += SCAN_THREADS) s_present[i] = a.wt.present[i];
+	__syncthreads();
+
+	const uint32_t kmask = a.wt.nkeys - 1;
+	for (uint32_t tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
+		const ScanTile tl = a.tiles[tile];
+		const Target tg = a.db.targets[tl.target];
+		const uint32_t p0 = tl.start + threadIdx.x*32u;
+		if (p0 >= tg.len) continue;
+		const uint64_t wi = (tg.base + p0) >> 5;
+		const uint64_t lo = __ldg(a.db.db2 + wi);
+		const uint64_t hi = __ldg(a.db.db2 + wi + 1); // the allocation is padded by one word
+#pragma unroll 4
+		for (uint32_t b = 0; b < 32; ++b) {
+			const uint32_t p = p0 + b;
+			if (p + (uint32_t)a.W > tg.len) break;
+			const uint64_t x = b ? ((lo >> (2*b)) | (hi << (64 - 2*b))) : lo;
+			const uint32_t key = (uint32_t)x & kmask;
+			if (!((s_present[key >> 5] >> (key & 31u)) & 1u)) continue;
+			const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
+			for (uint32_t e = e0; e < e1; ++e) {
+				const uint32_t ent = __ldg(a.wt.entry + e);
+				const uint32_t os = ent >> 8, k = ent & 0xffu;
+				if (first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask))
+					emit_candidate(a, os, tl.target, k, p);
+			}
+		}
+	}
+}
+
+// Stage-2 scan: only the oligo strands of the region's assay, only inside the region
+// (the neighbourhood of a bound minus-strand primer site where a partner / probe may sit).
+struct RegionScanArgs {
+	ScanArgs s;
+	const Region *regions;
+	uint32_t nregions;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_region_scan(RegionScanArgs ra)
+{
+	const ScanArgs &a = ra.s;
+	const uint32_t kmask = a.wt.nkeys - 1;
+	for (uint32_t r = blockIdx.x; r < ra.nregions; r += gridDim.x) {
+		const Region rg = ra.regions[r];
+		const Target tg = a.db.targets[rg.target];
+		for (uint32_t p = rg.start + threadIdx.x; p < rg.stop; p += SCAN_THREADS) {
+			if (p + (uint32_t)a.W > tg.len) break;
+			const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
+			if (!((__ldg(a.wt.present + (key >> 5)) >> (key & 31u)) & 1u)) continue;
+			const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
+			for (uint32_t e = e0; e < e1; ++e) {
+				const uint32_t ent = __ldg(a.wt.entry + e);
+				const uint32_t os = ent >> 8, k = ent & 0xffu;
+				if (a.os[os].assay != rg.assay) continue;
+				if (first_on_diagonal(a.db.db2, tg.base, p, k, rg.start, a.os_keys + (size_t)os*MAX_OLIGO, kmask))
+					emit_candidate(a, os, rg.target, k, p);
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// NucCruc alignment of candidate windows + per-oligo filters
+// (bind_oligo_to_{minus,plus}_strand, bind_oligo.cpp:456-827 / :1159-1530, one seed per thread)
+// ------------------------------------------------------------------------------------------
+constexpr int ALIGN_THREADS = 128;
+
+struct AlignUnit { uint32_t os; uint32_t begin; uint32_t count; }; // `begin` indexes cand[os*cap + ...]
+
+struct AlignArgs {
+	DbView db;
+	const Thermo *thermo;
+	const OligoStrand *os;
+	const Candidate *cand;
+	uint32_t cap;
+	const AlignUnit *units;
+	uint32_t nunits;
+	int max_lt;                // row stride of the shared DP rows: columns 0..max_lt
+	uint16_t *trace;           // [gridDim.x][MAX cells][ALIGN_THREADS]
+	uint32_t trace_cells;      // cells reserved per CTA
+	BoundRec *out;             // filtered mode: appended; all mode: out[unit.begin' + tid]
+	uint32_t *out_count;
+	uint32_t out_cap;
+	int emit_all;              // 1: write every result at out[units[u].begin + tid] (cap ignored)
+	unsigned long long *cells; // sum of Lq*Lt
+};
+
+__global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
+{
+	extern __shared__ __align__(16) unsigned char s_raw[];
+	int32_t *s_dg = reinterpret_cast<int32_t *>(s_raw);
+	uint8_t *s_bbp = reinterpret_cast<uint8_t *>(s_dg + TABLE);
+	uint8_t *s_wc = s_bbp + NB*NB;
+	uint8_t *s_q = s_wc + 52;
+	int32_t *s_rows = reinterpret_cast<int32_t *>(s_raw + ((TABLE*4 + NB*NB + 52 + MAX_OLIGO + 15) & ~15));
+	const int row_stride = (a.max_lt + 1)*ALIGN_THREADS;
+
+	const int tid = threadIdx.x;
+	for (int i = tid; i < TABLE; i += ALIGN_THREADS) s_dg[i] = a.thermo->dg[i];
+	for (int i = tid; i < NB*NB; i += ALIGN_THREADS) s_bbp[i] = a.thermo->bbp[i];
+	for (int i = tid; i < NPAIR; i += ALIGN_THREADS) s_wc[i] = a.thermo->wc[i];
+
+	uint16_t *trace = a.trace + (size_t)blockIdx.x*a.trace_cells*ALIGN_THREADS + tid;
+	int32_t *rowM = s_rows + tid, *rowIq = rowM + row_stride, *rowIt = rowIq + row_stride;
+	unsigned long long my_cells = 0;
+
+	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+		const AlignUnit unit = a.units[u];
+		const OligoStrand &os = a.os[unit.os];
+		__syncthreads();
+		if (tid < os.len) s_q[tid] = os.seq[tid];
+		__syncthreads();
+
+		if ((uint32_t)tid >= unit.count) continue;
+
+		DpShared sh;
+		sh.dg = s_dg; sh.bbp = s_bbp; sh.wc = s_wc; sh.q = s_q; sh.Lq = os.len;
+
+		const Candidate c = a.cand[(size_t)unit.os*a.cap + unit.begin + tid];
+		const uint32_t target = c.target_k & 0xffffffu, k = c.target_k >> 24;
+		const Target tg = a.db.targets[target];
+
+		// window (bind_oligo.cpp:502-505)
+		const int s0 = (int)c.t - (int)(k + NUM_FLANK);
+		const uint32_t start = s0 > 0 ? (uint32_t)s0 : 0u;
+		const uint32_t stop = min(start + (uint32_t)os.len + 2u*NUM_FLANK, tg.len);
+
+		uint8_t tgt[MAX_WINDOW];
+		const int Lt = load_window(a.db, tg, start, stop, os.plus != 0, tgt);
+		my_cells += (unsigned long long)(os.len*Lt);
+
+		unsigned flags = 0;
+		AlnState work, best_aln;
+		Best best;
+		best.valid = false;
+		best.dH = best.dS = best.tm = 0.0f;
+		best_aln.b = best_aln.e = 2;
+		best_aln.fm_q = best_aln.fm_t = best_aln.lm_q = best_aln.lm_t = 0;
+
+		if (Lt > 0) {
+			const DpResult dp = nc_fill<ALIGN_THREADS>(sh, tgt, Lt, rowM, rowIq, rowIt, trace);
+			nc_enumerate<ALIGN_THREADS>(sh, a.thermo, os.r_log_ct, tgt, Lt, trace, dp, work, best_aln, best, flags);
+		}
+
+		// thresholds in the reference's order (bind_oligo.cpp:598-714)
+		const float tm = best.tm;
+		const float dG = __fsub_rn(best.dH, __fmul_rn(a.thermo->T, best.dS));
+		bool pass = !(tm < os.min_tm || tm > os.max_tm);
+		if (pass) pass = !(dG < os.min_dg || dG > os.max_dg);
+		unsigned anchor5 = 0, anchor3 = 0, mm = 0, gaps = 0, poly = 0;
+		const bool want = a.emit_all || pass;
+		if (want && best.valid) {
+			anchor5 = nc_anchor5(sh, tgt, Lt, best_aln);
+			anchor3 = nc_anchor3(sh, tgt, Lt, best_aln);
+			nc_counts(sh, best_aln, mm, gaps, poly);
+		}
+		else if (want) {
+			// No alignment at all: the reference evaluates the anchors on a cleared alignment
+			// (first/last match left over).  Tm is 0 there, so this only passes with min_tm <= 0.
+			mm = (unsigned)os.len;
+		}
+		if (pass) pass = anchor5 >= os.clamp5;
+		if (pass) pass = anchor3 >= os.clamp3;
+		if (pass) pass = mm <= os.max_mismatch;
+		if (pass) pass = gaps <= os.max_gap;
+		if (pass) pass = poly <= os.max_poly_degen;
+		if (flags & (F_OOB | F_STACK)) pass = true; // surface it to the host, which reports it
+
+		if (!(a.emit_all || pass)) continue;
+
+		uint32_t slot;
+		if (a.emit_all) slot = unit.begin + tid;
+		else {
+			slot = atomicAdd(a.out_count, 1u);
+			if (slot >= a.out_cap) continue;
+		}
+		BoundRec &r = a.out[slot];
+		r.os = unit.os;
+		r.target = target;
+		r.tm = tm; r.dH = best.dH; r.dS = best.dS; r.dG = dG;
+		r.anchor5 = (int16_t)anchor5; r.anchor3 = (int16_t)anchor3;
+		r.num_mm = (int16_t)mm; r.num_gap = (int16_t)gaps; r.poly_degen = (int16_t)poly;
+		r.valid = best.valid ? 1 : 0;
+		r.k = k; r.t = c.t;
+		r.win_start = (int32_t)start; r.win_stop = (int32_t)stop;
+		r.fm_q = (int16_t)best_aln.fm_q; r.fm_t = (int16_t)best_aln.fm_t;
+		r.lm_q = (int16_t)best_aln.lm_q; r.lm_t = (int16_t)best_aln.lm_t;
+		r.Lt = (uint8_t)Lt;
+		r.flags = (uint8_t)flags;
+		r.pad = 0;
+		const int ncols = best.valid ? best_aln.e - best_aln.b : 0;
+		r.ncols = (uint8_t)ncols;
+		for (int i = 0; i < ncols; ++i) { r.cols_q[i] = best_aln.q[best_aln.b + i]; r.cols_t[i] = best_aln.t[best_aln.b + i]; }
+		for (int i = 0; i < Lt; ++i) r.win[i] = tgt[i];
+
+		// target coordinates (bind_oligo.cpp:721-731 minus, :1424-1434 plus)
+		const int q_first = best_aln.fm_q, q_last = best_aln.lm_q, t_first = best_aln.lm_t, t_last = best_aln.fm_t;
+		int t5 = (int)start, t3 = (int)start;
+		if (os.plus) {
+			t5 += t_first;
+			t3 += t_last;
+			t3 += q_first;
+			t5 -= (os.len - 1) - q_last;
+		}
+		else {
+			t5 += (int)(stop - start) - 1 - t_last;
+			t3 += (int)(stop - start) - 1 - t_first;
+			t5 -= q_first;
+			t3 += (os.len - 1) - q_last;
+		}
+		r.loc5 = t5;
+		r.loc3 = t3;
+	}
+
+	// one atomic per warp for the cell counter
+	for (int off = 16; off; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
+	if ((tid & 31) == 0 && my_cells) atomicAdd(a.cells, my_cells);
+}
+
+// seq.h codes of [start, start+n) of one fragment (used to rebuild amplicon text for a hit)
+__global__ void k_extract_codes(DbView db, uint32_t target, uint32_t start, uint32_t n, uint8_t *out)
+{
+	const Target tg = db.targets[target];
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		const uint64_t g = tg.base + start + i;
+		int code = (int)((__ldg(db.db2 + (g >> 5)) >> ((g & 31u)*2u)) & 3u);
+		if ((__ldg(db.nmask + (g >> 5)) >> (g & 31u)) & 1u) code = exception_code(db, tg, g);
+		out[i] = (uint8_t)code;
+	}
+}
+
+} // namespace tnt

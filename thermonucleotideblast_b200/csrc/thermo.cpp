@@ -1,0 +1,207 @@
+// Host-side construction of the thermodynamic tables the kernels consume.
+//
+// Mirrors what the reference computes once per thread in NucCruc::NucCruc + Salt() +
+// update_dp_param() (nuc_cruc.cpp:226-487): the T/salt-dependent integer penalty table and the
+// pair-resolution table for IUPAC bases (nuc_cruc.cpp:14-213).  The parameter values themselves
+// are data (santalucia_tables.inc, exported from the reference by oracle/gen_tables.py).
+//
+// Everything here is IEEE binary32 evaluated in the same order as the reference so that the
+// integer truncation `int(x*10000.0f)` lands on the same value; the file is compiled without
+// FP contraction.
+
+#include "thermo.h"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "santalucia_tables.inc"
+
+namespace tnt {
+
+namespace {
+
+constexpr int pair_of(int x, int y) { return x*7 + y; }
+constexpr int sidx(int prev, int cur) { return prev*NPAIR + cur; }
+
+// A/C/G/T membership of each IUPAC code as a 4-bit set (A=1, C=2, G=4, T=8).
+// `B` shares N's set and default: the reference's switch falls through from B into N
+// (nuc_cruc.cpp:163-197).
+struct DegenRule { uint8_t set; uint8_t fallback; };
+const DegenRule kDegen[NB] = {
+	{0, bA}, {0, bC}, {0, bG}, {0, bT}, {0, bI}, {0, bE}, {0, bGAP},
+	{1 | 2, bA},      // M
+	{1 | 4, bA},      // R
+	{2 | 4, bG},      // S
+	{1 | 2 | 4, bA},  // V
+	{1 | 8, bA},      // W
+	{2 | 8, bT},      // Y
+	{1 | 2 | 8, bA},  // H
+	{4 | 8, bT},      // K
+	{1 | 4 | 8, bA},  // D
+	{15, bA},         // B (== N)
+	{15, bA},         // N
+};
+
+// The most optimistic concrete base for `x` when it faces `other`.
+int resolve(int x, int other)
+{
+	if (x < bM) return x;
+	if (other <= bT) {
+		const int wanted = 3 - other; // Watson-Crick partner in the 0..3 code
+		if (kDegen[x].set & (1u << wanted)) return wanted;
+	}
+	return kDegen[x].fallback;
+}
+
+inline int32_t scaled(float x) { return (int32_t)(x*10000.0f); } // NC_SCORE_SCALE, nuc_cruc.h:166
+inline int32_t unfavourable(float x) { const int32_t v = scaled(x); return v > 0 ? v : 0; }
+
+} // namespace
+
+uint8_t base_set(int b)
+{
+	static const uint8_t kSet[NB] = {1, 2, 4, 8, 15, 0, 0, 1 | 2, 1 | 4, 2 | 4, 1 | 2 | 4, 1 | 8, 2 | 8,
+		1 | 2 | 8, 4 | 8, 1 | 4 | 8, 2 | 4 | 8, 15};
+	return kSet[b];
+}
+
+bool complementary(int q, int t) // BASE::is_complemetary_base, nuc_cruc_anchor.cpp:8-139
+{
+	const unsigned ts = base_set(t);
+	const unsigned tc = ((ts & 1) << 3) | ((ts & 8) >> 3) | ((ts & 2) << 1) | ((ts & 4) >> 1);
+	return (base_set(q) & tc) != 0;
+}
+
+int base_from_ascii(char c) // BASE::char_to_nucleic_acid, nuc_cruc.h:190-231
+{
+	switch (c) {
+	case 'A': case 'a': return bA;
+	case 'C': case 'c': return bC;
+	case 'G': case 'g': return bG;
+	case 'T': case 't': return bT;
+	case 'I': case 'i': return bI;
+	case 'M': case 'm': return bM;
+	case 'R': case 'r': return bR;
+	case 'S': case 's': return bS;
+	case 'V': case 'v': return bV;
+	case 'W': case 'w': return bW;
+	case 'Y': case 'y': return bY;
+	case 'H': case 'h': return bH;
+	case 'K': case 'k': return bK;
+	case 'D': case 'd': return bD;
+	case 'B': case 'b': return bB;
+	case 'N': case 'n': return bN;
+	default: return -1;
+	}
+}
+
+void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3)
+{
+	if (T < 0.0f) throw std::runtime_error("update_dp_param: target_T < 0");
+	if (na < 1.0e-6f) throw std::runtime_error(":salt: [Na+] < 1.0e-6f");
+	if (na > 1.0f) throw std::runtime_error(":salt: [Na+] > 1.0f");
+
+	std::memset(&th, 0, sizeof(th));
+	th.T = T;
+	th.log_na = std::log(na); // float overload == logf, as in the reference translation unit
+	th.init_H = SL_INIT_H;
+	th.init_S = SL_INIT_S;
+	th.at_H = SL_AT_CLOSING_H;
+	th.at_S = SL_AT_CLOSING_S;
+	th.salt = SL_SALT;
+	th.asym_loop_dS = SL_ASYMMETRIC_LOOP_DS;
+	th.bulge_at_S = SL_BULGE_AT_CLOSING_S;
+	th.dangle5 = dangle5;
+	th.dangle3 = dangle3;
+	std::memcpy(th.H, SL_PARAM_H, sizeof(th.H));
+	std::memcpy(th.S, SL_PARAM_S, sizeof(th.S));
+	std::memcpy(th.loop_S, SL_LOOP_S, sizeof(th.loop_S));
+	std::memcpy(th.bulge_S, SL_BULGE_S, sizeof(th.bulge_S));
+
+	for (int x = 0; x < NB; ++x)
+		for (int y = 0; y < NB; ++y)
+			th.bbp[x*NB + y] = (uint8_t)pair_of(resolve(x, y), resolve(y, x));
+
+	// Watson-Crick pairs, inosine pairs with everything (nuc_cruc.cpp:229-238)
+	th.wc[pair_of(bA, bT)] = th.wc[pair_of(bT, bA)] = 1;
+	th.wc[pair_of(bC, bG)] = th.wc[pair_of(bG, bC)] = 1;
+	for (int b = bA; b <= bI; ++b) th.wc[pair_of(b, bI)] = th.wc[pair_of(bI, b)] = 1;
+
+	const float salt_correction = SL_SALT*th.log_na;
+	for (int i = 0; i < TABLE; ++i) th.dg[i] = scaled(SL_PARAM_H[i] - T*(SL_PARAM_S[i] + salt_correction));
+
+	// Supplementary terms (nuc_cruc.cpp:271-300, :379-486): pairs next to a gap, double
+	// mismatches and gap extension; never favourable.
+	const float loop_sc = salt_correction*SL_SUPP_SALT[0];
+	const float bulge_sc = salt_correction*SL_SUPP_SALT[1];
+	const float match_sc = salt_correction*SL_SUPP_SALT[2];
+	const float mismatch_sc = salt_correction*SL_SUPP_SALT[3];
+	const int32_t pen_loop = unfavourable(SL_SUPP[0] - T*(SL_SUPP[1] + loop_sc));
+	const int32_t pen_bulge = unfavourable(SL_SUPP[2] - T*(SL_SUPP[3] + bulge_sc));
+	const int32_t pen_at = unfavourable(SL_SUPP[4] - T*(SL_SUPP[5] + match_sc));
+	const int32_t pen_gc = unfavourable(SL_SUPP[6] - T*(SL_SUPP[7] + match_sc));
+	const int32_t pen_ino = unfavourable(SL_SUPP[8] - T*(SL_SUPP[9] + match_sc));
+	const int32_t pen_mm = unfavourable(SL_SUPP[10] - T*(SL_SUPP[11] + mismatch_sc));
+
+	for (int x = bA; x <= bI; ++x)
+		for (int y = bA; y <= bI; ++y) {
+			const int cur = pair_of(x, y);
+			int32_t next_to_gap = pen_mm;
+			if (th.wc[cur]) {
+				const bool at = (cur == pair_of(bA, bT)) || (cur == pair_of(bT, bA));
+				const bool gc = (cur == pair_of(bG, bC)) || (cur == pair_of(bC, bG));
+				next_to_gap = at ? pen_at : (gc ? pen_gc : pen_ino);
+			}
+			for (int k = bA; k <= bI; ++k) {
+				const int g1 = pair_of(k, bGAP), g2 = pair_of(bGAP, k);
+				th.dg[sidx(cur, g1)] = th.dg[sidx(g1, cur)] = next_to_gap;
+				th.dg[sidx(cur, g2)] = th.dg[sidx(g2, cur)] = next_to_gap;
+			}
+			if (!th.wc[cur])
+				for (int k = bA; k <= bI; ++k)
+					for (int l = bA; l <= bI; ++l)
+						if (!th.wc[pair_of(k, l)]) th.dg[sidx(cur, pair_of(k, l))] = pen_loop;
+		}
+	for (int x = bA; x <= bI; ++x)
+		for (int y = bA; y <= bI; ++y) {
+			th.dg[sidx(pair_of(x, bGAP), pair_of(y, bGAP))] = pen_bulge;
+			th.dg[sidx(pair_of(bGAP, x), pair_of(bGAP, y))] = pen_bulge;
+		}
+}
+
+float r_log_ct(float ct)
+{
+	return 1.9872e-3f*std::log(ct*1.0f); // NC_R*log(strand*alpha), nuc_cruc.cpp:2291
+}
+
+int build_words(const char *oligo, int W, bool complement, uint16_t *words)
+{
+	// DNAHash_iterator::build_word_list<std::string> (seq_hash.h:287-374): letters other than
+	// ACGT break the run without shifting the accumulator; valid words are appended densely.
+	const int L = (int)std::strlen(oligo);
+	if (W > L) return 0;
+	const unsigned mask = (1u << (2*W)) - 1u;
+	unsigned acc = 0;
+	int run = 0, n = 0;
+	for (int s = 0; s < L; ++s) {
+		const char c = complement ? oligo[L - 1 - s] : oligo[s];
+		int code;
+		switch (c) {
+		case 'A': case 'a': code = 0; break;
+		case 'C': case 'c': code = 1; break;
+		case 'G': case 'g': code = 2; break;
+		case 'T': case 't': code = 3; break;
+		default: code = -1; break;
+		}
+		if (code < 0) run = 0;
+		else {
+			++run;
+			acc = ((acc << 2) | (unsigned)(complement ? 3 - code : code)) & 0xffffu;
+		}
+		if (code >= 0 && run >= W) words[n++] = (uint16_t)(acc & mask);
+	}
+	return n;
+}
+
+} // namespace tnt

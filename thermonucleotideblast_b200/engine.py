@@ -1,0 +1,299 @@
+"""ctypes binding of the C ABI in include/tntb200.h (libtntb200.so, sm_100a).
+
+This is the host-side entry used by tests/ and bench.py; the reference-side binding a tntblast
+maintainer would add is the C++ shim in INTEGRATION.md.  There is no CPU path: creating an
+Engine without a usable CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtntb200.so")
+
+ASSAY_PCR, ASSAY_PROBE, ASSAY_PADLOCK, ASSAY_MIPS = 0, 1, 2, 3
+STRAND_PLUS, STRAND_MINUS, STRAND_BOTH = 1, 2, 3
+PLUS, MINUS = 0, 1
+OLIGO_F, OLIGO_R, OLIGO_P, OLIGO_NONE = 0, 1, 2, -1
+MAX_OLIGO_LEN = 56
+
+
+class EngineParams(C.Structure):
+    _fields_ = [("target_T", C.c_float), ("salt", C.c_float), ("dangle5", C.c_int32),
+                ("dangle3", C.c_int32), ("dinkelbach", C.c_int32), ("word_size", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SearchOptions(C.Structure):
+    _fields_ = [
+        ("assay_format", C.c_int32),
+        ("forward_primer_strand", C.c_float), ("reverse_primer_strand", C.c_float),
+        ("probe_strand", C.c_float),
+        ("min_primer_tm", C.c_float), ("max_primer_tm", C.c_float),
+        ("min_primer_dg", C.c_float), ("max_primer_dg", C.c_float),
+        ("min_probe_tm", C.c_float), ("max_probe_tm", C.c_float),
+        ("min_probe_dg", C.c_float), ("max_probe_dg", C.c_float),
+        ("primer_clamp", C.c_uint32), ("min_max_primer_clamp", C.c_int32),
+        ("probe_clamp_5", C.c_uint32), ("probe_clamp_3", C.c_uint32),
+        ("max_gap", C.c_uint32), ("max_mismatch", C.c_uint32), ("max_poly_degen", C.c_uint32),
+        ("max_len", C.c_uint32), ("single_primer_pcr", C.c_int32), ("target_strand", C.c_int32),
+    ]
+
+
+def search_options(**kw) -> SearchOptions:
+    """Reference CLI defaults (tntblast.h:19-76)."""
+    o = SearchOptions(
+        assay_format=ASSAY_PCR,
+        forward_primer_strand=9.0e-7, reverse_primer_strand=9.0e-7, probe_strand=2.5e-7,
+        min_primer_tm=0.0, max_primer_tm=9999.0, min_primer_dg=-9999.0, max_primer_dg=0.0,
+        min_probe_tm=0.0, max_probe_tm=9999.0, min_probe_dg=-9999.0, max_probe_dg=0.0,
+        primer_clamp=0, min_max_primer_clamp=-1, probe_clamp_5=0, probe_clamp_3=0,
+        max_gap=999, max_mismatch=999, max_poly_degen=3, max_len=2000,
+        single_primer_pcr=1, target_strand=STRAND_BOTH)
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+class CAssay(C.Structure):
+    _fields_ = [("id", C.c_int32), ("forward", C.c_char_p), ("reverse", C.c_char_p),
+                ("probe", C.c_char_p), ("forward_degen", C.c_int32), ("reverse_degen", C.c_int32),
+                ("probe_degen", C.c_int32)]
+
+
+class BoundOligo(C.Structure):
+    _fields_ = [("oligo", C.c_int32), ("loc_5", C.c_int32), ("loc_3", C.c_int32),
+                ("tm", C.c_float), ("dH", C.c_float), ("dS", C.c_float),
+                ("num_mm", C.c_int32), ("num_gap", C.c_int32),
+                ("anchor_5", C.c_int32), ("anchor_3", C.c_int32), ("align_off", C.c_uint32)]
+
+
+class CHit(C.Structure):
+    _fields_ = [("assay_index", C.c_int32), ("assay_id", C.c_int32), ("target_id", C.c_uint32),
+                ("primer_strand", C.c_int32), ("probe_strand", C.c_int32),
+                ("amp_first", C.c_int32), ("amp_last", C.c_int32),
+                ("probe_first", C.c_int32), ("probe_last", C.c_int32),
+                ("forward", BoundOligo), ("reverse", BoundOligo), ("probe", BoundOligo),
+                ("forward_clamp", C.c_int32), ("reverse_clamp", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("db_bases", C.c_uint64), ("seeds", C.c_uint64), ("alignments", C.c_uint64),
+                ("dp_cells", C.c_uint64), ("bound_sites", C.c_uint64), ("hits", C.c_uint64),
+                ("kernel_launches", C.c_uint64),
+                ("scan_ms", C.c_double), ("align_ms", C.c_double), ("pair_ms", C.c_double),
+                ("total_ms", C.c_double), ("scan_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class AlignResult(C.Structure):
+    _fields_ = [("tm", C.c_float), ("dH", C.c_float), ("dS", C.c_float), ("dG", C.c_float),
+                ("valid", C.c_int32), ("anchor5", C.c_int32), ("anchor3", C.c_int32),
+                ("num_mismatch", C.c_int32), ("num_gap", C.c_int32), ("max_poly_degen", C.c_int32),
+                ("q_first", C.c_int32), ("q_last", C.c_int32), ("t_first", C.c_int32), ("t_last", C.c_int32),
+                ("target_start", C.c_int32), ("target_stop", C.c_int32),
+                ("loc_5", C.c_int32), ("loc_3", C.c_int32),
+                ("alignment", C.c_char * 512)]
+
+
+@dataclass
+class Assay:
+    id: int
+    forward: Optional[str] = None
+    reverse: Optional[str] = None
+    probe: Optional[str] = None
+    forward_degen: int = 1
+    reverse_degen: int = 1
+    probe_degen: int = 1
+
+
+@dataclass
+class Hit:
+    """Python view of one tnt_hit with the alignment strings resolved."""
+    raw: CHit
+    forward_align: str
+    reverse_align: str
+    probe_align: str
+
+    def __getattr__(self, name):
+        return getattr(self.raw, name)
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libtntb200.so; raises if it has not been built (python -m thermonucleotideblast_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libtntb200.so is missing: run `python thermonucleotideblast_b200/build.py` "
+                           "(or __graft_entry__.build()); there is no fallback path")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    u8p = C.POINTER(C.c_uint8)
+    u32p = C.POINTER(C.c_uint32)
+    L.tnt_last_error.restype = C.c_char_p
+    L.tnt_abi_version.restype = C.c_int
+    L.tnt_engine_create.argtypes = [C.POINTER(EngineParams), C.POINTER(vp)]
+    L.tnt_engine_destroy.argtypes = [vp]
+    L.tnt_engine_destroy.restype = None
+    L.tnt_engine_add_target.argtypes = [vp, u8p, C.c_uint32, u32p]
+    L.tnt_engine_clear_targets.argtypes = [vp]
+    L.tnt_engine_set_assays.argtypes = [vp, C.POINTER(CAssay), C.c_int32]
+    L.tnt_engine_search.argtypes = [vp, C.POINTER(SearchOptions)]
+    L.tnt_engine_get_hits.argtypes = [vp, C.POINTER(C.POINTER(CHit)), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.tnt_engine_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.tnt_engine_hit_sequence.argtypes = [vp, C.POINTER(CHit), C.c_char_p, C.c_size_t]
+    L.tnt_engine_hit_sequence.restype = C.c_long
+    L.tnt_engine_seeds.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, u32p, u32p, C.c_long]
+    L.tnt_engine_seeds.restype = C.c_long
+    L.tnt_engine_align.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, C.c_float, u32p, u32p,
+                                   C.c_long, C.POINTER(AlignResult)]
+    L.tnt_engine_scan_only.argtypes = [vp, C.POINTER(SearchOptions), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine per GPU (and per host thread), like the per-thread DNAHash + NucCruc pair of the
+    reference (tntblast_local.cpp:345-372)."""
+
+    def __init__(self, target_T: float = 310.15, salt: float = 50.0e-3, dangle5: bool = False,
+                 dangle3: bool = False, word_size: int = 7, device: int = 0):
+        self.L = load_library()
+        prm = EngineParams(target_T=target_T, salt=salt, dangle5=int(dangle5), dangle3=int(dangle3),
+                           dinkelbach=0, word_size=word_size, device=device, reserved=0)
+        self.h = C.c_void_p()
+        self._check(self.L.tnt_engine_create(C.byref(prm), C.byref(self.h)))
+        self.target_T = target_T
+        self._keep = []
+
+    def _check(self, rc):
+        if rc < 0:
+            raise EngineError(self.L.tnt_last_error().decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tnt_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- targets ---------------------------------------------------------------------------
+    def add_target(self, codes: np.ndarray) -> int:
+        a = np.ascontiguousarray(codes, dtype=np.uint8)
+        tid = C.c_uint32()
+        self._check(self.L.tnt_engine_add_target(self.h, a.ctypes.data_as(C.POINTER(C.c_uint8)), a.size, C.byref(tid)))
+        return tid.value
+
+    def clear_targets(self):
+        self._check(self.L.tnt_engine_clear_targets(self.h))
+
+    # -- assays ----------------------------------------------------------------------------
+    def set_assays(self, assays: Sequence[Assay]):
+        arr = (CAssay * max(len(assays), 1))()
+        keep = []
+        for i, a in enumerate(assays):
+            f = a.forward.encode() if a.forward else None
+            r = a.reverse.encode() if a.reverse else None
+            p = a.probe.encode() if a.probe else None
+            keep.extend([f, r, p])
+            arr[i] = CAssay(a.id, f, r, p, a.forward_degen, a.reverse_degen, a.probe_degen)
+        self._check(self.L.tnt_engine_set_assays(self.h, arr, len(assays)))
+
+    # -- search ----------------------------------------------------------------------------
+    def search(self, opts: SearchOptions) -> List[Hit]:
+        self._check(self.L.tnt_engine_search(self.h, C.byref(opts)))
+        return self.hits()
+
+    def search_raw(self, opts: SearchOptions) -> int:
+        """Search without materialising Python hit objects; returns the hit count."""
+        self._check(self.L.tnt_engine_search(self.h, C.byref(opts)))
+        n = C.c_size_t()
+        self._check(self.L.tnt_engine_get_hits(self.h, None, C.byref(n), None, None))
+        return n.value
+
+    def hits(self) -> List[Hit]:
+        ph = C.POINTER(CHit)()
+        n = C.c_size_t()
+        arena = C.c_void_p()
+        asz = C.c_size_t()
+        self._check(self.L.tnt_engine_get_hits(self.h, C.byref(ph), C.byref(n), C.byref(arena), C.byref(asz)))
+        buf = C.string_at(arena.value, asz.value) if asz.value else b""
+
+        def s(off):
+            end = buf.index(b"\0", off)
+            return buf[off:end].decode()
+
+        out = []
+        for i in range(n.value):
+            h = CHit.from_buffer_copy(ph[i])
+            out.append(Hit(h, s(h.forward.align_off), s(h.reverse.align_off), s(h.probe.align_off)))
+        return out
+
+    def stats(self) -> Stats:
+        st = Stats()
+        self._check(self.L.tnt_engine_get_stats(self.h, C.byref(st)))
+        return st
+
+    def hit_sequence(self, hit: Hit) -> str:
+        raw = hit.raw if isinstance(hit, Hit) else hit
+        n = self.L.tnt_engine_hit_sequence(self.h, C.byref(raw), None, 0)
+        if n < 0:
+            raise EngineError(self.L.tnt_last_error().decode())
+        buf = C.create_string_buffer(n + 1)
+        self.L.tnt_engine_hit_sequence(self.h, C.byref(raw), buf, n + 1)
+        return buf.value.decode()
+
+    # -- stage-level entry points ------------------------------------------------------------
+    def seeds(self, target_id: int, oligo: str, plus: bool) -> List[Tuple[int, int]]:
+        cap = 1 << 16
+        while True:
+            q = np.zeros(cap, dtype=np.uint32)
+            t = np.zeros(cap, dtype=np.uint32)
+            n = self.L.tnt_engine_seeds(self.h, target_id, oligo.encode(), int(plus),
+                                        q.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                        t.ctypes.data_as(C.POINTER(C.c_uint32)), cap)
+            if n < 0:
+                raise EngineError(self.L.tnt_last_error().decode())
+            if n <= cap:
+                return list(zip(q[:n].tolist(), t[:n].tolist()))
+            cap = n
+
+    def align(self, target_id: int, oligo: str, plus: bool, seeds: Sequence[Tuple[int, int]],
+              ct: float = 9.0e-7):
+        n = len(seeds)
+        q = np.array([s[0] for s in seeds], dtype=np.uint32)
+        t = np.array([s[1] for s in seeds], dtype=np.uint32)
+        out = (AlignResult * max(n, 1))()
+        self._check(self.L.tnt_engine_align(self.h, target_id, oligo.encode(), int(plus), ct,
+                                            q.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                            t.ctypes.data_as(C.POINTER(C.c_uint32)), n, out))
+        return [out[i] for i in range(n)]
