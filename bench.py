@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark of the tntblast search hot path on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mbp M] [--assays A]
+
+One "step" is one pass of the hot path (seed scan -> NucCruc Tm/dG alignment -> amplicon
+assembly) over the whole workload.  Default workload = BASELINE.json configs[1]:
+100 TaqMan primer+probe triplets vs a synthetic 1 Gbp multi-record database (200 records x 5 Mbp,
+cut into <= 500 kbp fragments with the reference's overlap), flags -e 45 -E 50.
+
+Metric: DB Gbp*assay/s (database bases x input assays per second), whole job over all ranks.
+  value : inputs already resident in HBM when the timed region starts (search only)
+  e2e   : the same through the C ABI with host buffers: clear + upload of every fragment
+          (pinned staging, H2D, 2-bit pack) + search + hit read-back inside the timed region
+Extra keys: alignments_per_s (NucCruc heterodimer evaluations), roofline (NucCruc DP kernel,
+int32 issue roofline of SURVEY 8d), roofline_seed_scan (HBM), cpu_baseline (the unmodified
+reference OpenMP build on the host cores on a bounded slice of the same workload).
+
+Under torchrun (N > 1) every rank owns one GPU and a contiguous shard of the database of the same
+size (weak scaling; the path has no exchange step, so NCCL only carries the barrier and the
+max-over-ranks of the timings).  `--impl reference` times the reference's own CPU implementation
+(oracle/_ref/tntblast, built from /root/reference by oracle/Makefile) on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import gen  # noqa: E402
+
+METRIC = "DB Gbp*assay/s (tntblast search hot path: seed scan + NucCruc Tm/dG alignment + amplicon assembly)"
+UNIT = "Gbp*assay/s"
+RECORD_BP = 5_000_000
+FRAGMENT_BP = 500_000          # DEFAULT_FRAGMENT_TARGET_LENGTH, tntblast.h:81
+MAX_LEN = 2000                 # DEFAULT_MAX_LEN
+OVERLAP = MAX_LEN + 2          # opt.max_product_length() + 2, tntblast_local.cpp:174
+MIN_PRIMER_TM, MIN_PROBE_TM = 45.0, 50.0
+ALU_OPS_PER_CELL = 27          # 32-bit ALU ops per DP cell of align_dimer
+SM_COUNT, LANES_PER_SM = 148, 128
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def build_workload(rank: int, mbp: int, n_assays: int):
+    """Synthetic shard of `mbp` Mbp (records of 5 Mbp) + TaqMan assays planted into it."""
+    from thermonucleotideblast_b200.sharding import fragment_record
+    rng = np.random.default_rng(2 + 1000 * rank)
+    total = mbp * 1_000_000
+    records = []
+    left = total
+    while left > 0:
+        n = min(RECORD_BP, left)
+        records.append(gen.random_codes(n, rng))
+        left -= n
+    arng = np.random.default_rng(99)  # same assays on every rank
+    assays = gen.make_assays(arng, records, n_assays, "taqman", lens=(20, 21, 25), amp=(80, 400), variants=2)
+    fragments = []
+    for rec in records:
+        for (a, b) in fragment_record(len(rec), FRAGMENT_BP):
+            fragments.append(rec[a:min(len(rec), b + 1 + OVERLAP)])
+    return records, fragments, assays, total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        if shutil.which("nvidia-smi") is None:
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.f = open(self.path, "w")
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits", "-lms", "200"],
+                                     stdout=self.f, stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def write_reference_inputs(tmp: str, records, assays, sample_bp: int):
+    """FASTA (80 columns) of the leading `sample_bp` bases + tab-separated assay file."""
+    fa = os.path.join(tmp, "db.fa")
+    lut = np.frombuffer(b"ACGTIMRSVWYHKDBN-N", dtype=np.uint8)
+    left = sample_bp
+    with open(fa, "wb") as f:
+        for i, rec in enumerate(records):
+            if left <= 0:
+                break
+            n = min(len(rec), left)
+            f.write(b">rec%d synthetic\n" % i)
+            txt = lut[rec[:n]]
+            full = (n // 80) * 80
+            if full:
+                body = np.empty((full // 80, 81), dtype=np.uint8)
+                body[:, :80] = txt[:full].reshape(-1, 80)
+                body[:, 80] = ord("\n")
+                f.write(body.tobytes())
+            if n > full:
+                f.write(txt[full:].tobytes() + b"\n")
+            left -= n
+    q = os.path.join(tmp, "assays.txt")
+    with open(q, "w") as f:
+        for i, (F, R, P) in enumerate(assays):
+            f.write("assay%d\t%s\t%s\t%s\n" % (i, F, R, P))
+    return fa, q, sample_bp - max(left, 0)
+
+
+def run_reference_once(fa, q, cores: int, tmp: str) -> float:
+    exe = os.path.join(ROOT, "oracle", "_ref", "tntblast")
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    t0 = time.perf_counter()
+    subprocess.run([exe, "-i", q, "-d", fa, "-e", str(MIN_PRIMER_TM), "-E", str(MIN_PROBE_TM),
+                    "-o", os.path.join(tmp, "out.txt")], check=True, env=env,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(records, assays, seconds_target: float = 15.0):
+    exe = os.path.join(ROOT, "oracle", "_ref", "tntblast")
+    if not os.path.exists(exe):
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref/tntblast missing (build it with make -C oracle ref where /root/reference exists)"}
+    cores = host_cores()
+    # measured in the survey: ~0.016 Gbp*assay/s per core on 100 TaqMan assays
+    sample_bp = int(min(sum(len(r) for r in records), max(2_000_000, seconds_target * 0.016e9 * cores / max(len(assays), 1))))
+    tmp = tempfile.mkdtemp(prefix="tntref_")
+    try:
+        fa, q, used = write_reference_inputs(tmp, records, assays, sample_bp)
+        dt = run_reference_once(fa, q, cores, tmp)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": used * len(assays) / 1e9 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "first %.1f Mbp of the same database x %d assays, OMP_NUM_THREADS=%d, %.1f s wall (file read + search + output)"
+                      % (used / 1e6, len(assays), cores, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mbp", type=int, default=1000, help="database size per GPU in Mbp")
+    ap.add_argument("--assays", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    workload = ("%d TaqMan primer+probe triplets (20/21/25-mers, -e %g -E %g) vs synthetic %.3g Gbp multi-record "
+                "database per GPU (%d Mbp records, <=%d kbp fragments + %d bp overlap)"
+                % (args.assays, MIN_PRIMER_TM, MIN_PROBE_TM, args.mbp / 1000.0, RECORD_BP // 1_000_000,
+                   FRAGMENT_BP // 1000, OVERLAP))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded per-step sample so that warmup + steps end within a few minutes
+        cores = host_cores()
+        per_step_s = 6.0
+        sample_mbp = max(1, int(per_step_s * 0.016e9 * cores / max(args.assays, 1) / 1e6))
+        records, _, assays, _ = build_workload(0, min(args.mbp, max(sample_mbp, 5)), args.assays)
+        tmp = tempfile.mkdtemp(prefix="tntref_")
+        try:
+            fa, q, used = write_reference_inputs(tmp, records, assays, sample_mbp * 1_000_000)
+            for _ in range(args.warmup):
+                run_reference_once(fa, q, cores, tmp)
+            times = [run_reference_once(fa, q, cores, tmp) for _ in range(args.steps)]
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        dt = sum(times) / len(times)
+        v = used * len(assays) / 1e9 / dt
+        sample = "first %.1f Mbp of the same synthetic database x %d assays per step, OMP_NUM_THREADS=%d" % (used / 1e6, len(assays), cores)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from thermonucleotideblast_b200 import Assay, Engine, search_options
+
+    records, fragments, assays, db_bases = build_workload(rank, args.mbp, args.assays)
+    frag_bases = int(sum(len(f) for f in fragments))
+    opts = search_options(min_primer_tm=MIN_PRIMER_TM, min_probe_tm=MIN_PROBE_TM, max_len=MAX_LEN)
+    eng = Engine(device=local_rank)
+    eng.set_assays([Assay(i, F, R, P) for i, (F, R, P) in enumerate(assays)])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def upload():
+        eng.clear_targets()
+        for f in fragments:
+            eng.add_target(f)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident: search only -----------------------------------------------------------
+    upload()
+    for _ in range(args.warmup):
+        eng.search_raw(opts)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = scan_ms = align_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        nhits = eng.search_raw(opts)
+        st = eng.stats()
+        dev_ms += st.total_ms
+        scan_ms += st.scan_ms
+        align_ms += st.align_ms
+        launches += st.kernel_launches
+    barrier()
+    dt = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    dt = max_over_ranks(dt)
+    st = eng.stats()
+    units = sum_over_ranks(db_bases * len(assays) / 1e9)
+    aligns = sum_over_ranks(float(st.alignments))
+    value = units / dt
+
+    # ---- end to end: host buffers -> hits ------------------------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    upload()
+    eng.search_raw(opts)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        upload()
+        eng.search_raw(opts)
+        hits = eng.hits()
+        d2h = len(hits) * 172 + int(eng.stats().bound_sites) * 344
+    barrier()
+    e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    e2e_value = units / e2e_dt
+
+    # ---- rooflines ----------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    alu_peak = SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12  # int32 lane-ops/s, TOP/s
+    align_s = align_ms / args.steps / 1e3
+    scan_s = scan_ms / args.steps / 1e3
+    alu_achieved = ALU_OPS_PER_CELL * st.dp_cells / align_s / 1e12 if align_s > 0 else 0.0
+    scan_achieved = st.scan_bytes / scan_s / 1e9 if scan_s > 0 else 0.0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 (DP) + f32 (dH/dS/Tm)", "data": "synthetic",
+        "config": {"workload": workload, "db_bases_per_gpu": db_bases, "fragments_per_gpu": len(fragments),
+                   "fragment_bases_per_gpu": frag_bases, "assays": len(assays),
+                   "l2": "inputs larger than L2 (packed DB %.0f MB + candidate buffers)" % (frag_bases * 0.375 / 1e6)},
+        "alignments_per_s": aligns / dt,
+        "alignments_per_step": aligns,
+        "dp_cells_per_step": float(st.dp_cells),
+        "hits_per_step_rank0": int(nhits),
+        "device_ms_per_step": dev_ms / args.steps,
+        "kernel_ms_per_step": {"seed_scan": scan_ms / args.steps, "nuccruc_align": align_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frag_bases, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps},
+        "roofline": {"bound": "alu-int32", "achieved": alu_achieved, "peak": alu_peak, "unit": "TOP/s",
+                     "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": None,
+                     "kernel": "k_align (NucCruc DP + traceback + evaluation)",
+                     "note": "27 int32 ALU ops per DP cell (SURVEY 8d) x %d cells per step / CUDA-event time of the kernel; "
+                             "peak = 148 SM x 128 lanes x %.0f MHz (nominal issue peak, no measured figure exists)" % (st.dp_cells, sm_max)},
+        "roofline_seed_scan": {"bound": "hbm", "achieved": scan_achieved, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": scan_achieved / hbm_peak if hbm_peak else None, "traffic": None,
+                               "kernel": "k_seed_scan", "peak_source": hbm_src,
+                               "note": "0.375 B per base per pass + 8 B per emitted candidate (SURVEY 8d)"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(records, assays)
+    elif rank == 0:
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "only measured at N=1"}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

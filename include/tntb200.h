@@ -185,6 +185,16 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
  * the HBM roofline): returns the number of unique candidates and the device time. */
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms);
 
+/* ---- Host-only diagnostics (no GPU needed; used by the CPU test-suite) ---- */
+
+/* The integer penalty table of NucCruc::update_dp_param (nuc_cruc.cpp:340-487) and the
+ * best_base_pair table (nuc_cruc.cpp:14-213) as the engine uploads them: dg[49*49], bbp[18*18]. */
+int tnt_debug_thermo(float T, float na, int32_t *dg, uint8_t *bbp);
+
+/* Compacted seed word list of an oligo (DNAHash_iterator::build_word_list, seq_hash.h:287-374);
+ * returns the number of words written (at most TNT_MAX_OLIGO_LEN). */
+int tnt_debug_words(const char *oligo, int32_t word_size, int32_t complement, uint16_t *words);
+
 #ifdef __cplusplus
 }
 #endif

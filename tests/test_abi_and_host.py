@@ -1,0 +1,97 @@
+"""CPU-side checks: the C ABI library loads and exports every declared symbol, the host-side
+table construction matches the oracle, and the engine refuses to run without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gen
+import harness as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tntb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tnt_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(engine_lib):
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(engine_lib, s), s
+    assert engine_lib.tnt_abi_version() == 1
+
+
+def test_no_cpu_fallback(engine_lib):
+    """Without a usable CUDA device creation fails loudly; nothing routes around the kernels."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from thermonucleotideblast_b200 import Engine, EngineError
+    with pytest.raises(EngineError) as ei:
+        Engine()
+    assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "thermonucleotideblast_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "tnt_oracle" not in txt and "libtntoracle" not in txt and "harness" not in txt, f
+                assert "libtntref" not in txt, f
+
+
+def test_host_thermo_table_matches_oracle(engine_lib, oracle):
+    engine_lib.tnt_debug_thermo.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_int32), C.POINTER(C.c_uint8)]
+    for T, na in [(310.15, 0.05), (298.15, 0.2), (333.15, 0.01), (310.15, 1.0)]:
+        dg = (C.c_int32 * 2401)()
+        bbp = (C.c_uint8 * 324)()
+        assert engine_lib.tnt_debug_thermo(T, na, dg, bbp) == 0
+        assert list(dg) == list(oracle.dump_tables(T, na).delta_g)
+    # invalid salt is refused like NucCruc::salt does (nuc_cruc.h:852-867)
+    assert engine_lib.tnt_debug_thermo(310.15, 2.0, None, None) < 0
+
+
+def test_host_word_lists_match_oracle_seeds(engine_lib, oracle):
+    """The compacted word list (incl. the inosine offset quirk) reproduces the
+    oracle's raw seed enumeration on a fragment that contains every word once."""
+    engine_lib.tnt_debug_words.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint16)]
+    rng = np.random.default_rng(3)
+    for it in range(20):
+        L = int(rng.integers(7, 40))
+        ol = list(gen.rand_oligo(L, rng))
+        if it % 2:
+            ol[int(rng.integers(0, L))] = "I"
+        if it % 5 == 0:
+            ol[int(rng.integers(0, L))] = "N"
+        ol = "".join(ol)
+        W = int(rng.integers(3, 9))
+        for comp in (0, 1):
+            words = (C.c_uint16 * 64)()
+            n = engine_lib.tnt_debug_words(ol.encode(), W, comp, words)
+            assert n >= 0
+            # expected: distinct consecutive word indices 0..n-1 in the raw seed list of the oracle
+            plain = ol.replace("I", "A").replace("N", "A")
+            text = gen.revcomp(plain) if comp else plain
+            codes = gen.str_to_codes("ACGT" * 3 + text + "TGCA" * 3)
+            raw = oracle.seeds(codes, ol, W, bool(comp), unique=False)
+            assert (max(q for q, _ in raw) + 1 if raw else 0) <= n
+            # every word of the list must be the W-mer of the seed string at its true offset
+            s = gen.revcomp(ol) if comp else ol
+            k = 0
+            for off in range(len(s) - W + 1):
+                w = s[off:off + W]
+                if all(c in "ACGT" for c in w):
+                    val = 0
+                    for c in w:
+                        val = (val << 2) | "ACGT".index(c)
+                    assert words[k] == val
+                    k += 1
+            assert k == n

@@ -1,0 +1,124 @@
+"""The plain-C oracle against the committed golden vectors.
+
+tests/golden/*.json were produced by tests/golden/make_golden.py from the UNMODIFIED reference
+(oracle/_ref/libtntref.so).  This is what pins the oracle where /root/reference is absent.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gen
+import harness as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NB = {'A': 0, 'C': 1, 'G': 2, 'T': 3, 'I': 4, 'M': 7, 'R': 8, 'S': 9, 'V': 10, 'W': 11, 'Y': 12, 'H': 13,
+      'K': 14, 'D': 15, 'B': 16, 'N': 17}
+
+
+def load(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+def f32(x):
+    return float(np.float32(x)).hex()
+
+
+def align_rec(a):
+    return {"tm": f32(a.tm), "dH": f32(a.dH), "dS": f32(a.dS), "dG": f32(a.dG), "valid": a.valid,
+            "ints": [a.anchor5, a.anchor3, a.num_mismatch, a.num_gap, a.max_poly_degen,
+                     a.q_first, a.q_last, a.t_first, a.t_last, a.target_start, a.target_stop, a.loc_5, a.loc_3],
+            "alignment": a.alignment.decode()}
+
+
+def test_delta_g_tables(oracle):
+    for rec in load("tables.json"):
+        t = oracle.dump_tables(rec["T"], rec["na"])
+        assert list(t.delta_g) == rec["delta_g"]
+
+
+def test_alignments(oracle):
+    recs = load("alignments.json")
+    nvalid = 0
+    for r in recs:
+        tb = np.array([NB[c] for c in r["t"]], dtype=np.uint8)
+        a = oracle.align(r["q"], tb, T=r["T"], na=r["na"], ct=r["ct"], dangle5=r["d5"], dangle3=r["d3"])
+        got = align_rec(a)
+        want = r["out"]
+        if not want["valid"]:
+            assert not got["valid"]
+            continue
+        nvalid += 1
+        assert got == want, (r["q"], r["t"])
+    assert nvalid > 300
+
+
+def test_seeds_and_windows(oracle):
+    for rec in load("seeds.json"):
+        codes = gen.str_to_codes(rec["codes"])
+        for plus in (0, 1):
+            assert [list(x) for x in oracle.seeds(codes, rec["oligo"], rec["W"], bool(plus), unique=False)] == rec["raw%d" % plus]
+            uniq = oracle.seeds(codes, rec["oligo"], rec["W"], bool(plus), unique=True)
+            assert [list(x) for x in uniq] == rec["uniq%d" % plus]
+            for (q, t), want in zip(uniq, rec.get("bind%d" % plus, [])):
+                got = align_rec(oracle.bind_window(codes, rec["oligo"], bool(plus), q, t))
+                if want["valid"]:
+                    assert got == want
+                else:
+                    assert not got["valid"]
+
+
+def test_searches(oracle):
+    total = 0
+    for rec in load("searches.json"):
+        codes = gen.str_to_codes(rec["codes"])
+        o = H.default_options(**rec["opts"])
+        hits = oracle.search(codes, rec["F"], rec["R"], rec["P"], o)
+        got = [{"key": [x.decode() if isinstance(x, bytes) else x for x in h.exact_key()],
+                "floats": [f32(x) for x in h.floats()]} for h in hits]
+        assert got == rec["hits"], rec["kind"]
+        total += len(got)
+    assert total >= 50
+
+
+def test_readme_known_answer(oracle):
+    """Reference README.md:138,162-203 (gibb-marburg): dG/dH/dS, clamps, coordinates, strings."""
+    amp = ("TTCCCCTTTGGAGGCATCCAAGCGATGGGCTTTCAGGACAGGTGTACCTCCCAAGAATGTTGAGTATACAGAAGGGGAGGAAGCCAAAACATGCTACAATATAAG"
+           "TGTAACGGATCCCTCTGGAAAATCCTTGCTGTTGGATCCTCC")
+    rng = np.random.default_rng(1)
+    codes = gen.random_codes(6121 + len(amp) + 3000, rng)
+    gen.plant(codes, 6121, amp)
+    o = H.default_options(min_primer_tm=40.0, min_probe_tm=45.0)
+    hits = oracle.search(codes, "TTCCCCTTTGGAGGCATC", "GGAGGATCCAACAGCAAGG", "CGATGGGCTTTCAGGACAGGTGT", o)
+    assert len(hits) == 1
+    h = hits[0]
+    T = 310.15
+    assert (h.amp_first, h.amp_last, h.probe_first, h.probe_last) == (6121, 6267, 6143, 6165)
+    assert abs(h.forward_dH - T * h.forward_dS + 16.8574) < 1e-3 and abs(h.forward_dH + 135.5) < 1e-3
+    assert abs(h.forward_dS + 0.382533) < 1e-5
+    assert abs(h.reverse_dH - T * h.reverse_dS + 17.8955) < 1e-3 and abs(h.reverse_dH + 146.5) < 1e-3
+    assert abs(h.probe_dH - T * h.probe_dS + 22.9778) < 1e-3 and abs(h.probe_dH + 180.2) < 1e-3
+    assert min(h.forward_clamp, h.reverse_clamp) == 18
+    assert h.amplicon_len == 147
+    assert h.forward_align == b"5' TTCCCCTTTGGAGGCATC 3'\n   ||||||||||||||||||\n3' AAGGGGAAACCTCCGTAG 5'"
+    assert h.reverse_align == b"5' GGAGGATCCAACAGCAAGG 3'\n   |||||||||||||||||||\n3' CCTCCTAGGTTGTCGTTCC 5'"
+    assert h.probe_align == b"5' CGATGGGCTTTCAGGACAGGTGT 3'\n   |||||||||||||||||||||||\n3' GCTACCCGAAAGTCCTGTCCACA 5'"
+    assert h.amplicon_head.decode() == amp
+
+
+def test_oracle_vs_compiled_reference(oracle, ref):
+    """Differential run against the reference itself (skipped where oracle/_ref is absent)."""
+    rng = np.random.default_rng(5)
+    for it in range(300):
+        L = int(rng.integers(14, 34))
+        q = gen.rand_oligo(L, rng)
+        t = gen.rand_oligo(4, rng) + gen.mutate(gen.revcomp(q), int(rng.integers(0, 5)), rng) + gen.rand_oligo(4, rng)
+        tb = np.array([NB[c] for c in t], dtype=np.uint8)
+        a, b = ref.align(q, tb), oracle.align(q, tb)
+        assert a.key() == b.key() and (a.tm, a.dH, a.dS) == (b.tm, b.dH, b.dS)
+    for it in range(12):
+        codes, F, R, P = gen.make_pcr_case(rng, 30000, n_sites=3, probe=bool(it % 2))
+        o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+        a, b = ref.search(codes, F, R, P, o), oracle.search(codes, F, R, P, o)
+        assert [(h.exact_key(), h.floats()) for h in a] == [(h.exact_key(), h.floats()) for h in b]

@@ -479,13 +479,14 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 	const size_t nos = set.os.size();
 	e->d_cand_count.reserve(nos, 0, e->stream);
 	e->d_regions.upload(regions, e->stream);
-	// every position of a region can seed at most (words of one assay) candidates; size the
-	// buckets for the worst bucket = all positions of all regions of that assay
+	// Size the buckets for the busiest assay: expected seeds = positions x words / 4^W; start with
+	// generous slack and double on overflow (repeat-rich fragments can exceed any estimate).
 	std::map<int, uint64_t> per_assay;
 	for (const Region &r : regions) per_assay[r.assay] += r.stop - r.start;
 	uint64_t worst = 0;
 	for (auto &kv : per_assay) worst = std::max(worst, kv.second);
-	uint32_t cap = (uint32_t)std::min<uint64_t>(worst + 64, 1u << 26);
+	const double expect = (double)worst*(double)set.max_words/(double)set.nkeys;
+	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
 	for (;;) {
 		e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
 		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*sizeof(uint32_t), e->stream));
@@ -504,6 +505,7 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
 		e->stats.scan_ms += ms;
 		if (ok) return;
+		if (cap >= (1u << 30)) throw std::runtime_error("stage-2 seed buckets overflow");
 		cap *= 2;
 	}
 }
@@ -936,6 +938,23 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	e->stats.dp_cells = cells;
 	API_END
+}
+
+int tnt_debug_thermo(float T, float na, int32_t *dg, uint8_t *bbp)
+{
+	API_BEGIN
+	std::unique_ptr<Thermo> th(new Thermo);
+	build_thermo(*th, T, na, false, false);
+	if (dg) std::memcpy(dg, th->dg, sizeof(th->dg));
+	if (bbp) std::memcpy(bbp, th->bbp, sizeof(th->bbp));
+	API_END
+}
+
+int tnt_debug_words(const char *oligo, int32_t word_size, int32_t complement, uint16_t *words)
+{
+	if (!oligo || !words || word_size < 2 || word_size > 8) { g_error = "bad argument"; return -1; }
+	if (std::strlen(oligo) > (size_t)MAX_OLIGO) { g_error = "oligo longer than TNT_MAX_OLIGO_LEN"; return -1; }
+	return build_words(oligo, word_size, complement != 0, words);
 }
 
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms)
