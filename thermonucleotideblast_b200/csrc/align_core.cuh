@@ -172,6 +172,15 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 	return res;
 }
 
+// Read access to the stored trace of one alignment.  get(i, j) returns the trace word of DP cell
+// (i, j), 1 <= i <= Lq, 1 <= j <= Lt, in the layout of the TW_* constants above.
+template <int NT>
+struct RowMajorTrace {
+	const uint16_t *trace;
+	int Lt;
+	__device__ __forceinline__ unsigned get(int i, int j) const { return trace[(size_t)((i - 1)*Lt + (j - 1))*NT]; }
+};
+
 // ------------------------------------------------------------------------------------------
 // Stage 2: traceback of one path (trace_back, nuc_cruc.cpp:1409-1618)
 // ------------------------------------------------------------------------------------------
@@ -184,8 +193,8 @@ constexpr int MAX_BRANCH = 3*(MAX_OLIGO + MAX_WINDOW);
 
 __device__ __forceinline__ bool path_split(unsigned m) { return __popc(m & 7u) > 1; }
 
-template <int NT>
-__device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, const uint16_t *trace,
+template <class TV>
+__device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, const TV &tv,
 	int start_cell, Branch *stack, int &nstack, int &zero_count, AlnState &a, unsigned &flags)
 {
 	const int Lq = sh.Lq;
@@ -220,7 +229,7 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 
 		const bool inside = (last_i >= 1 && last_j >= 1);
 		const int cell = (last_i - 1)*Lt + (last_j - 1);
-		const unsigned w = inside ? (unsigned)trace[(size_t)cell*NT] : TW_BORDER;
+		const unsigned w = inside ? tv.get(last_i, last_j) : TW_BORDER;
 
 		if (local == T_DIAG) {
 			if (last_i > Lq || last_j < 1) valid = false;
@@ -438,24 +447,23 @@ struct Best {
 	float dH, dS, tm;
 };
 
-template <int NT>
+// `cells` lists the maximal DP cells as linear indices (i-1)*Lt + (j-1) in row-major order,
+// i.e. the order of the reference's max_ptr vector.
+template <class TV>
 __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct,
-	const uint8_t *tgt, int Lt, const uint16_t *trace, const DpResult &dp,
+	const uint8_t *tgt, int Lt, const TV &tv, const uint16_t *cells, int ncells,
 	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags)
 {
 	const int Lq = sh.Lq;
 	const float T = th->T;
 	best.valid = false;
 	best.dH = best.dS = best.tm = 0.0f;
-	if (dp.nmax == 0) return;
+	if (ncells == 0) return;
 
 	Branch stack[MAX_BRANCH];
-	const int ncell = Lq*Lt;
-	int seen = 0;
 
-	for (int cell = dp.last_raise; cell < ncell && seen < dp.nmax; ++cell) {
-		if (cell != dp.last_raise && !(trace[(size_t)cell*NT] & TW_CAND)) continue;
-		++seen;
+	for (int ci = 0; ci < ncells; ++ci) {
+		const int cell = cells[ci];
 
 		bool first_time = true;
 		int nstack = 0, zero_count = -1;
@@ -472,7 +480,7 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 			a.b = a.e = 2; // room for a dangling-end column in front
 			a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
 			a.dH = a.dS = a.tm = 0.0f;
-			nc_trace_back<NT>(sh, tgt, Lt, trace, cell, stack, nstack, zero_count, a, flags);
+			nc_trace_back(sh, tgt, Lt, tv, cell, stack, nstack, zero_count, a, flags);
 			if (flags & (F_OOB | F_STACK)) return;
 
 			// frayed ends: drop columns until both ends are Watson-Crick (:1022-1054)
@@ -580,6 +588,191 @@ __device__ inline void nc_counts(const DpShared &sh, const AlnState &a, unsigned
 		else run = 0;
 	}
 	mm += (unsigned)sh.Lq - aligned;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast fill (ACGT-only windows): column sweep with the oligo rows held in registers.
+//
+// The same recurrence as nc_fill, reorganised for the SM:
+//  * one column of the DP matrix (all LQ oligo rows, three states) lives in registers; the row
+//    loop is fully unrolled, so there is no indexed scratch and no shared-memory traffic for
+//    DP state at all;
+//  * every penalty the reference looks up through best_base_pair + delta_g depends only on
+//    (oligo row, target dinucleotide); the host tabulates them per oligo strand
+//    (build_row_tables, thermo.cpp) and the kernel reads them from shared memory as
+//    tab[row][kind][dinucleotide] -- the row is a compile-time offset, lanes differ only in the
+//    dinucleotide (<= 20 consecutive words), hence conflict-free;
+//  * a trace word is assembled with one funnel shift per fact (sign bits of differences) and two
+//    rows share one 32-bit store.
+// Rows >= Lq are padding: their penalties are huge, they never reach the running maximum and no
+// real row depends on them.
+// ------------------------------------------------------------------------------------------
+constexpr int ROW_WORDS = 72;      // P1[20] P2[20] P4[20] P3[4] P6[4] P7 pad[3]
+constexpr int ROW_P1 = 0, ROW_P2 = 20, ROW_P4 = 40, ROW_P3 = 60, ROW_P6 = 64, ROW_P7 = 68;
+constexpr int32_t ROW_PAD_PENALTY = 1 << 28;
+constexpr int MAX_MAXCELLS = 64;
+
+struct FastDp {
+	int runmax, last_i, last_j, nmax;
+};
+
+// packed trace bits of the fast fill, most significant first (order of insertion)
+//   11 d1!=M  10 d2!=M  9 d3!=M  8 qi!=Iq  7 qe!=Iq  6 ti!=It  5 te!=It  4 M<0  3 M>0  2 Iq<0  1 It<0  0 M<runmax
+__device__ __forceinline__ unsigned decode_fast_trace(unsigned raw)
+{
+	unsigned w = 0;
+	if (!(raw & (1u << 11))) w |= T_DIAG;
+	if (!(raw & (1u << 10))) w |= T_LEFT;
+	if (!(raw & (1u << 9))) w |= T_UP;
+	if (!(raw & (1u << 8))) w |= TW_IQ_INS;
+	if (!(raw & (1u << 7))) w |= TW_IQ_EXT;
+	if (!(raw & (1u << 6))) w |= TW_IT_INS;
+	if (!(raw & (1u << 5))) w |= TW_IT_EXT;
+	if (raw & (1u << 4)) w |= TW_M_NEG;
+	else if (!(raw & (1u << 3))) w |= TW_M_ZERO;
+	if (raw & (1u << 2)) w |= TW_IQ_NEG;
+	if (raw & (1u << 1)) w |= TW_IT_NEG;
+	if (!(raw & 1u)) w |= TW_CAND;
+	return w;
+}
+
+template <int LQ, int NT>
+struct ColMajorTrace {
+	const uint32_t *trace32;
+	__device__ __forceinline__ unsigned raw(int i, int j) const
+	{
+		const uint32_t w = trace32[(size_t)((j - 1)*(LQ/2) + ((i - 1) >> 1))*NT];
+		return ((i - 1) & 1) ? (w >> 16) : (w & 0xffffu);
+	}
+	__device__ __forceinline__ unsigned get(int i, int j) const { return decode_fast_trace(raw(i, j)); }
+};
+
+// target base j (0-based, NucCruc orientation) from the 2-bit packed window
+__device__ __forceinline__ int packed_base(uint64_t lo, uint64_t hi, int j)
+{
+	return (int)(((j < 32) ? (lo >> (2*j)) : (hi >> (2*(j - 32)))) & 3u);
+}
+
+template <int LQ, int NT>
+__device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
+	uint64_t tlo, uint64_t thi, int Lt, uint32_t *__restrict__ trace32)
+{
+	static_assert(LQ % 2 == 0, "two rows share a trace store");
+	int cM[LQ], cIq[LQ], cIt[LQ];
+#pragma unroll
+	for (int r = 0; r < LQ; ++r) { cM[r] = 0; cIq[r] = 0; cIt[r] = 0; }
+
+	FastDp res;
+	res.runmax = -1;
+	res.last_i = res.last_j = 0;
+	res.nmax = 0;
+
+	int pt = 4; // GAP in front of the first column
+	for (int j = 1; j <= Lt; ++j) {
+		const int tb = packed_base(tlo, thi, j - 1);
+		const int td = pt*4 + tb;
+		const int32_t *__restrict__ ptd = tab + td;
+		const int32_t *__restrict__ ptb = tab + tb;
+		const int p5 = p5tab[td];
+		uint32_t *__restrict__ col = trace32 + (size_t)(j - 1)*(LQ/2)*NT;
+
+		int dM = 0, dIq = 0, dIt = 0; // (i-1, j-1)
+		int uM = 0, uIt = 0;          // (i-1, j)
+		unsigned pair_word = 0;
+#pragma unroll
+		for (int r = 0; r < LQ; ++r) {
+			const int oM = cM[r], oIq = cIq[r], oIt = cIt[r]; // (i, j-1)
+
+			const int d1 = dM - ptd[r*ROW_WORDS + ROW_P1];
+			const int d2 = dIq - ptd[r*ROW_WORDS + ROW_P2];
+			const int d3 = dIt - ptb[r*ROW_WORDS + ROW_P3];
+			const int M = max(max(d1, d2), d3);
+
+			const int qi = oM - ptd[r*ROW_WORDS + ROW_P4];
+			const int qe = oIq - p5;
+			const int Iq = max(qi, qe);
+
+			const int ti = uM - ptb[r*ROW_WORDS + ROW_P6];
+			const int te = uIt - tab[r*ROW_WORDS + ROW_P7];
+			const int It = max(ti, te);
+
+			const int rr = M - res.runmax;
+			unsigned acc = 0;
+			acc = __funnelshift_l((unsigned)(d1 - M), acc, 1);
+			acc = __funnelshift_l((unsigned)(d2 - M), acc, 1);
+			acc = __funnelshift_l((unsigned)(d3 - M), acc, 1);
+			acc = __funnelshift_l((unsigned)(qi - Iq), acc, 1);
+			acc = __funnelshift_l((unsigned)(qe - Iq), acc, 1);
+			acc = __funnelshift_l((unsigned)(ti - It), acc, 1);
+			acc = __funnelshift_l((unsigned)(te - It), acc, 1);
+			acc = __funnelshift_l((unsigned)M, acc, 1);
+			acc = __funnelshift_l((unsigned)(-M), acc, 1);
+			acc = __funnelshift_l((unsigned)Iq, acc, 1);
+			acc = __funnelshift_l((unsigned)It, acc, 1);
+			acc = __funnelshift_l((unsigned)rr, acc, 1);
+
+			if (rr > 0) { res.nmax = 1; res.last_i = r + 1; res.last_j = j; }
+			else if (rr == 0) ++res.nmax;
+			res.runmax = max(res.runmax, M);
+
+			if (r & 1) col[(r >> 1)*NT] = pair_word | (acc << 16);
+			else pair_word = acc;
+
+			dM = oM; dIq = oIq; dIt = oIt;
+			cM[r] = max(M, 0);
+			cIq[r] = max(Iq, 0);
+			cIt[r] = max(It, 0);
+			uM = cM[r];
+			uIt = cIt[r];
+		}
+		pt = tb;
+	}
+	return res;
+}
+
+// Maximal cells in the reference's (row-major) order from a fast fill.  The sweep visits the
+// matrix column by column, so the cells tied with the maximum are gathered from the sweep
+// position of the last strict raise onwards and then ordered by (row, column).
+template <int LQ, int NT>
+__device__ inline int collect_max_cells_fast(const ColMajorTrace<LQ, NT> &tv, const FastDp &dp, int Lq, int Lt,
+	uint16_t *cells, unsigned &flags)
+{
+	if (dp.nmax == 0) return 0;
+	if (dp.nmax == 1 && dp.last_j > 0) {
+		cells[0] = (uint16_t)((dp.last_i - 1)*Lt + (dp.last_j - 1));
+		return 1;
+	}
+	int n = 0;
+	const int j0 = dp.last_j > 0 ? dp.last_j : 1;
+	for (int j = j0; j <= Lt && n < dp.nmax; ++j) {
+		const int i0 = (j == j0 && dp.last_j > 0) ? dp.last_i : 1;
+		for (int i = i0; i <= Lq && n < dp.nmax; ++i) {
+			if (tv.raw(i, j) & 1u) continue; // below the running maximum
+			if (n == MAX_MAXCELLS) { flags |= F_TRUNC; return n; }
+			// insertion sort by row-major index
+			const uint16_t key = (uint16_t)((i - 1)*Lt + (j - 1));
+			int k = n++;
+			while (k > 0 && cells[k - 1] > key) { cells[k] = cells[k - 1]; --k; }
+			cells[k] = key;
+		}
+	}
+	return n;
+}
+
+// The same list for the row-major (generic) fill.
+template <int NT>
+__device__ inline int collect_max_cells(const RowMajorTrace<NT> &tv, const DpResult &dp, int Lq, int Lt,
+	uint16_t *cells, unsigned &flags)
+{
+	if (dp.nmax == 0) return 0;
+	int n = 0;
+	const int ncell = Lq*Lt;
+	for (int cell = dp.last_raise < 0 ? 0 : dp.last_raise; cell < ncell && n < dp.nmax; ++cell) {
+		if (!(tv.trace[(size_t)cell*NT] & TW_CAND)) continue;
+		if (n == MAX_MAXCELLS) { flags |= F_TRUNC; return n; }
+		cells[n++] = (uint16_t)cell;
+	}
+	return n;
 }
 
 } // namespace tnt

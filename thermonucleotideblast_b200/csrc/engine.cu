@@ -86,6 +86,10 @@ struct OsSet {
 	DevBuf<OligoStrand> d_os;
 	DevBuf<uint16_t> d_keys;
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
+	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
+	std::vector<uint32_t> row_tab_off;
+	DevBuf<int32_t> d_row_tab;
+	DevBuf<uint32_t> d_row_tab_off;
 	uint32_t nkeys = 0;
 	uint64_t total_words = 0;
 	int max_len = 0, max_words = 0;
@@ -143,6 +147,10 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_out_count;
 	DevBuf<unsigned long long> d_cells;
 	DevBuf<Region> d_regions;
+	DevBuf<SlowItem> d_slow;
+	DevBuf<Candidate> d_slow_cand;
+	DevBuf<uint32_t> d_slot_map;
+	DevBuf<int32_t> d_p5;
 	DevBuf<uint8_t> d_extract;
 
 	std::vector<tnt_hit> hits;
@@ -309,6 +317,13 @@ void finish_set(tnt_engine *e, OsSet &set)
 	for (size_t s = 0; s < nos; ++s)
 		for (int k = 0; k < set.os[s].nwords; ++k)
 			set.entry[fill[set.keys[s*MAX_OLIGO + k]]++] = (uint32_t)(s << 8) | (uint32_t)k;
+	set.row_tab_off.assign(nos, 0);
+	size_t rows = 0;
+	for (size_t s = 0; s < nos; ++s) { set.row_tab_off[s] = (uint32_t)(rows*ROW_WORDS); rows += (size_t)set.os[s].len; }
+	set.row_tab.assign(std::max<size_t>(rows*ROW_WORDS, 1), 0);
+	for (size_t s = 0; s < nos; ++s) build_row_tables(e->h_thermo, set.os[s], set.row_tab.data() + set.row_tab_off[s]);
+	set.d_row_tab.upload(set.row_tab, e->stream);
+	set.d_row_tab_off.upload(set.row_tab_off, e->stream);
 	set.d_os.upload(set.os, e->stream);
 	set.d_keys.upload(set.keys, e->stream);
 	set.d_present.upload(set.present, e->stream);
@@ -334,6 +349,74 @@ ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
 	return a;
 }
 
+// Oligo length classes of the fast kernel (rows held in registers)
+const int kFastClasses[] = {20, 24, 28, 32, 40, 56};
+
+template <int LQ>
+void launch_fast(const AlignArgs &a, uint32_t grid, cudaStream_t st)
+{
+	k_align_fast<LQ><<<grid, ALIGN_THREADS, 0, st>>>(a);
+}
+
+int fast_blocks_per_sm(int lq)
+{
+	int n = 1;
+	switch (lq) {
+	case 20: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<20>, ALIGN_THREADS, 0); break;
+	case 24: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<24>, ALIGN_THREADS, 0); break;
+	case 28: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<28>, ALIGN_THREADS, 0); break;
+	case 32: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<32>, ALIGN_THREADS, 0); break;
+	case 40: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<40>, ALIGN_THREADS, 0); break;
+	default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<56>, ALIGN_THREADS, 0); break;
+	}
+	return std::max(n, 1);
+}
+
+// Run one alignment kernel (fast class `lq`, or the generic kernel when lq == 0) over `units`,
+// appending / writing results into e->d_out.  Returns the device time.
+float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector<AlignUnit> &units, int lq, int max_len)
+{
+	e->d_units.upload(units, e->stream);
+	a.units = e->d_units.p;
+	a.nunits = (uint32_t)units.size();
+	uint32_t grid;
+	size_t smem = 0;
+	if (lq == 0) {
+		const int max_lt = max_len + 2*NUM_FLANK;
+		smem = ((TABLE*4 + NB*NB + 52 + MAX_OLIGO + 15) & ~15) + (size_t)3*(max_lt + 1)*ALIGN_THREADS*sizeof(int32_t);
+		CUDA_OK(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		int per_sm = 1;
+		CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, ALIGN_THREADS, smem));
+		grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*std::max(per_sm, 1));
+		a.max_lt = max_lt;
+		a.trace_cells = (uint32_t)max_len*(uint32_t)max_lt;
+	}
+	else {
+		grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*fast_blocks_per_sm(lq));
+		a.trace_cells = (uint32_t)lq*(uint32_t)(lq + 2*NUM_FLANK);
+	}
+	e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS + 64, 0, e->stream);
+	a.trace = e->d_trace.p;
+	CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
+	switch (lq) {
+	case 0: k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a); break;
+	case 20: launch_fast<20>(a, grid, e->stream); break;
+	case 24: launch_fast<24>(a, grid, e->stream); break;
+	case 28: launch_fast<28>(a, grid, e->stream); break;
+	case 32: launch_fast<32>(a, grid, e->stream); break;
+	case 40: launch_fast<40>(a, grid, e->stream); break;
+	default: launch_fast<56>(a, grid, e->stream); break;
+	}
+	CUDA_OK(cudaGetLastError());
+	CUDA_OK(cudaEventRecord(e->ev[3], e->stream));
+	e->stats.kernel_launches++;
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	float ms = 0;
+	CUDA_OK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
+	(void)set;
+	return ms;
+}
+
 // Align every candidate currently in the buckets of `set`; append the survivors to `out`.
 // Returns false if a bucket overflowed (the caller shrinks the chunk and retries).
 bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec> &out, bool emit_all,
@@ -344,66 +427,97 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec
 	CUDA_OK(cudaMemcpyAsync(counts.data(), e->d_cand_count.p, nos*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	if (counts_out) *counts_out = counts;
-	std::vector<AlignUnit> units;
 	uint64_t total = 0;
 	for (size_t s = 0; s < nos; ++s) {
 		if (counts[s] > cap) return false;
-		for (uint32_t b = 0; b < counts[s]; b += ALIGN_THREADS)
-			units.push_back(AlignUnit{(uint32_t)s, b, std::min<uint32_t>(ALIGN_THREADS, counts[s] - b)});
 		total += counts[s];
 	}
 	e->stats.seeds += total;
-	if (units.empty()) return true;
+	if (total == 0) return true;
 	if (emit_all && nos != 1) throw std::runtime_error("emit_all needs a single oligo strand");
 
-	e->d_units.upload(units, e->stream);
-
-	const int max_lt = set.max_len + 2*NUM_FLANK;
-	const size_t smem = ((TABLE*4 + NB*NB + 52 + MAX_OLIGO + 15) & ~15) + (size_t)3*(max_lt + 1)*ALIGN_THREADS*sizeof(int32_t);
-	CUDA_OK(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 1;
-	CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, ALIGN_THREADS, smem));
-	per_sm = std::max(per_sm, 1);
-	const uint32_t grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*per_sm);
-	const uint32_t trace_cells = (uint32_t)set.max_len*(uint32_t)max_lt;
-	e->d_trace.reserve((size_t)grid*trace_cells*ALIGN_THREADS, 0, e->stream);
+	// units per fast class
+	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));
+	std::vector<std::vector<AlignUnit>> by_class(nclass);
+	for (size_t s = 0; s < nos; ++s) {
+		int c = 0;
+		while (c < nclass - 1 && kFastClasses[c] < set.os[s].len) ++c;
+		for (uint32_t b = 0; b < counts[s]; b += ALIGN_THREADS)
+			by_class[c].push_back(AlignUnit{(uint32_t)s, b, std::min<uint32_t>(ALIGN_THREADS, counts[s] - b)});
+	}
 
 	size_t out_cap = emit_all ? (size_t)total : std::max<size_t>(e->d_out.cap, 1u << 16);
+	size_t slow_cap = std::max<size_t>(e->d_slow.cap, 1u << 16);
+	// snapshot of the DP-cell counter so that a retried pass is not counted twice
+	unsigned long long cells_before = 0;
+	CUDA_OK(cudaMemcpyAsync(&cells_before, e->d_cells.p, sizeof(cells_before), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+
 	for (;;) {
 		e->d_out.reserve(out_cap, 0, e->stream);
-		CUDA_OK(cudaMemsetAsync(e->d_out_count.p, 0, sizeof(uint32_t), e->stream));
+		e->d_slow.reserve(slow_cap, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_out_count.p, 0, 2*sizeof(uint32_t), e->stream));
+		CUDA_OK(cudaMemcpyAsync(e->d_cells.p, &cells_before, sizeof(cells_before), cudaMemcpyHostToDevice, e->stream));
 		AlignArgs a{};
 		a.db = e->view();
 		a.thermo = e->d_thermo.p;
 		a.os = set.d_os.p;
 		a.cand = e->d_cand.p;
 		a.cap = cap;
-		a.units = e->d_units.p;
-		a.nunits = (uint32_t)units.size();
-		a.max_lt = max_lt;
-		a.trace = e->d_trace.p;
-		a.trace_cells = trace_cells;
 		a.out = e->d_out.p;
 		a.out_count = e->d_out_count.p;
 		a.out_cap = (uint32_t)out_cap;
 		a.emit_all = emit_all ? 1 : 0;
+		a.slot_map = nullptr;
 		a.cells = e->d_cells.p;
-		CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
-		k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a);
-		CUDA_OK(cudaGetLastError());
-		CUDA_OK(cudaEventRecord(e->ev[3], e->stream));
-		e->stats.kernel_launches++;
-		uint32_t n = 0;
-		CUDA_OK(cudaMemcpyAsync(&n, e->d_out_count.p, sizeof(n), cudaMemcpyDeviceToHost, e->stream));
-		CUDA_OK(cudaStreamSynchronize(e->stream));
+		a.row_tab = set.d_row_tab.p;
+		a.row_tab_off = set.d_row_tab_off.p;
+		a.p5_tab = e->d_p5.p;
+		a.slow = e->d_slow.p;
+		a.slow_count = e->d_out_count.p + 1;
+		a.slow_cap = (uint32_t)slow_cap;
+
 		float ms = 0;
-		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
-		e->stats.align_ms += ms;
-		if (emit_all) n = (uint32_t)total;
-		else if (n > out_cap) { // overflow: enlarge and redo this launch (cell counter is corrected below)
-			out_cap = (size_t)n + n/4;
-			continue;
+		for (int c = 0; c < nclass; ++c)
+			if (!by_class[c].empty()) ms += run_align_kernel(e, set, a, by_class[c], kFastClasses[c], set.max_len);
+
+		uint32_t cnt[2] = {0, 0};
+		CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1] + cnt[1]/4; continue; }
+
+		if (cnt[1]) {
+			// windows with IUPAC / inosine / N target bases: generic kernel
+			std::vector<SlowItem> items(cnt[1]);
+			CUDA_OK(cudaMemcpyAsync(items.data(), e->d_slow.p, items.size()*sizeof(SlowItem), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+			std::stable_sort(items.begin(), items.end(), [](const SlowItem &x, const SlowItem &y) { return x.os < y.os; });
+			std::vector<Candidate> sc(items.size());
+			std::vector<uint32_t> slots(items.size());
+			std::vector<AlignUnit> units;
+			for (size_t i = 0; i < items.size();) {
+				size_t j = i;
+				while (j < items.size() && items[j].os == items[i].os) ++j;
+				for (size_t b = i; b < j; b += ALIGN_THREADS)
+					units.push_back(AlignUnit{items[i].os, (uint32_t)b, (uint32_t)std::min<size_t>(ALIGN_THREADS, j - b)});
+				i = j;
+			}
+			for (size_t i = 0; i < items.size(); ++i) { sc[i] = items[i].c; slots[i] = items[i].slot; }
+			e->d_slow_cand.upload(sc, e->stream);
+			e->d_slot_map.upload(slots, e->stream);
+			AlignArgs g = a;
+			g.cand = e->d_slow_cand.p;
+			g.cap = 0; // units index the compacted array directly
+			g.slot_map = emit_all ? e->d_slot_map.p : nullptr;
+			ms += run_align_kernel(e, set, g, units, 0, set.max_len);
+			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
 		}
+		e->stats.align_ms += ms;
+
+		uint32_t n = cnt[0];
+		if (emit_all) n = (uint32_t)total;
+		else if (n > out_cap) { out_cap = (size_t)n + n/4; continue; } // enlarge and redo this pass
 		e->stats.alignments += total;
 		const size_t old = out.size();
 		out.resize(old + n);
@@ -589,7 +703,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		std::vector<Region> regions;
 		const uint32_t slack = 64;
 		for (const BoundRec &b : recs1) {
-			if (b.flags & (F_OOB | F_STACK)) continue;
+			if (b.flags & (F_OOB | F_STACK | F_TRUNC)) continue;
 			const Target &tg = e->targets[b.target];
 			Region r;
 			r.target = b.target;
@@ -629,7 +743,9 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	for (const BoundRec &b : recs1) sites.push_back(make_site(b, stage1.os[b.os]));
 	for (const BoundRec &b : recs2) sites.push_back(make_site(b, stage2.os[b.os]));
 	for (const BoundSite &s : sites)
-		if (s.flags & (F_OOB | F_STACK))
+		if (s.flags & F_TRUNC)
+			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
+		else if (s.flags & (F_OOB | F_STACK))
 			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
 	e->stats.bound_sites = sites.size();
 
@@ -729,8 +845,13 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
 	e->d_thermo.reserve(1, 0, e->stream);
 	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
-	e->d_out_count.reserve(1, 0, e->stream);
+	e->d_out_count.reserve(2, 0, e->stream);
 	e->d_cells.reserve(1, 0, e->stream);
+	{
+		std::vector<int32_t> p5(20);
+		build_p5_table(e->h_thermo, p5.data());
+		e->d_p5.upload(p5, e->stream);
+	}
 	e->exc_pos.reserve(16, 0, e->stream);
 	e->exc_code.reserve(16, 0, e->stream);
 	CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -924,7 +1045,7 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
 		r.valid = s.valid;
 		r.target_start = s.win_start;
 		r.target_stop = s.win_stop;
-		if (s.flags & (F_OOB | F_STACK)) r.valid = -1;
+		if (s.flags & (F_OOB | F_STACK | F_TRUNC)) r.valid = -1;
 		if (s.valid) {
 			r.anchor5 = s.anchor5; r.anchor3 = s.anchor3;
 			r.num_mismatch = s.num_mm; r.num_gap = s.num_gap; r.max_poly_degen = s.poly_degen;

@@ -316,6 +316,9 @@ constexpr int ALIGN_THREADS = 128;
 
 struct AlignUnit { uint32_t os; uint32_t begin; uint32_t count; }; // `begin` indexes cand[os*cap + ...]
 
+// A candidate the fast kernel hands to the generic one (window with non-ACGT target bases)
+struct SlowItem { uint32_t os; uint32_t slot; Candidate c; };
+
 struct AlignArgs {
 	DbView db;
 	const Thermo *thermo;
@@ -324,16 +327,95 @@ struct AlignArgs {
 	uint32_t cap;
 	const AlignUnit *units;
 	uint32_t nunits;
-	int max_lt;                // row stride of the shared DP rows: columns 0..max_lt
-	uint16_t *trace;           // [gridDim.x][MAX cells][ALIGN_THREADS]
-	uint32_t trace_cells;      // cells reserved per CTA
-	BoundRec *out;             // filtered mode: appended; all mode: out[unit.begin' + tid]
+	int max_lt;                // generic kernel: row stride of the shared DP rows (columns 0..max_lt)
+	uint16_t *trace;           // [gridDim.x][cells][ALIGN_THREADS]
+	uint32_t trace_cells;      // 16-bit cells reserved per CTA
+	BoundRec *out;             // filtered mode: appended; all mode: out[slot]
 	uint32_t *out_count;
 	uint32_t out_cap;
-	int emit_all;              // 1: write every result at out[units[u].begin + tid] (cap ignored)
+	int emit_all;              // 1: write every result at out[units[u].begin + tid] (or slot_map[...])
+	const uint32_t *slot_map;  // optional, emit_all only: output slot per candidate index
 	unsigned long long *cells; // sum of Lq*Lt
+	// fast kernel only
+	const int32_t *row_tab;    // per oligo strand: len rows x ROW_WORDS
+	const uint32_t *row_tab_off;
+	const int32_t *p5_tab;     // [20]
+	SlowItem *slow;
+	uint32_t *slow_count;
+	uint32_t slow_cap;
 };
 
+// Thresholds in the reference's order (bind_oligo.cpp:598-714), target coordinates
+// (:721-731 minus, :1424-1434 plus) and the output record.
+__device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, const OligoStrand &os, uint32_t os_index,
+	uint32_t target, uint32_t k, uint32_t t, uint32_t start, uint32_t stop, const uint8_t *tgt, int Lt,
+	const Best &best, const AlnState &best_aln, unsigned flags, uint32_t all_slot)
+{
+	const float tm = best.tm;
+	const float dG = __fsub_rn(best.dH, __fmul_rn(a.thermo->T, best.dS));
+	bool pass = !(tm < os.min_tm || tm > os.max_tm);
+	if (pass) pass = !(dG < os.min_dg || dG > os.max_dg);
+	unsigned anchor5 = 0, anchor3 = 0, mm = 0, gaps = 0, poly = 0;
+	const bool want = a.emit_all || pass;
+	if (want && best.valid) {
+		anchor5 = nc_anchor5(sh, tgt, Lt, best_aln);
+		anchor3 = nc_anchor3(sh, tgt, Lt, best_aln);
+		nc_counts(sh, best_aln, mm, gaps, poly);
+	}
+	else if (want) mm = (unsigned)os.len; // no alignment at all: refused by the host-side bounds check
+	if (pass) pass = anchor5 >= os.clamp5;
+	if (pass) pass = anchor3 >= os.clamp3;
+	if (pass) pass = mm <= os.max_mismatch;
+	if (pass) pass = gaps <= os.max_gap;
+	if (pass) pass = poly <= os.max_poly_degen;
+	if (flags & (F_OOB | F_STACK | F_TRUNC)) pass = true; // surfaced to the host, which reports it
+
+	if (!(a.emit_all || pass)) return;
+
+	uint32_t slot;
+	if (a.emit_all) slot = all_slot;
+	else {
+		slot = atomicAdd(a.out_count, 1u);
+		if (slot >= a.out_cap) return;
+	}
+	BoundRec &r = a.out[slot];
+	r.os = os_index;
+	r.target = target;
+	r.tm = tm; r.dH = best.dH; r.dS = best.dS; r.dG = dG;
+	r.anchor5 = (int16_t)anchor5; r.anchor3 = (int16_t)anchor3;
+	r.num_mm = (int16_t)mm; r.num_gap = (int16_t)gaps; r.poly_degen = (int16_t)poly;
+	r.valid = best.valid ? 1 : 0;
+	r.k = k; r.t = t;
+	r.win_start = (int32_t)start; r.win_stop = (int32_t)stop;
+	r.fm_q = (int16_t)best_aln.fm_q; r.fm_t = (int16_t)best_aln.fm_t;
+	r.lm_q = (int16_t)best_aln.lm_q; r.lm_t = (int16_t)best_aln.lm_t;
+	r.Lt = (uint8_t)Lt;
+	r.flags = (uint8_t)flags;
+	r.pad = 0;
+	const int ncols = best.valid ? best_aln.e - best_aln.b : 0;
+	r.ncols = (uint8_t)ncols;
+	for (int i = 0; i < ncols; ++i) { r.cols_q[i] = best_aln.q[best_aln.b + i]; r.cols_t[i] = best_aln.t[best_aln.b + i]; }
+	for (int i = 0; i < Lt; ++i) r.win[i] = tgt[i];
+
+	const int q_first = best_aln.fm_q, q_last = best_aln.lm_q, t_first = best_aln.lm_t, t_last = best_aln.fm_t;
+	int t5 = (int)start, t3 = (int)start;
+	if (os.plus) {
+		t5 += t_first;
+		t3 += t_last;
+		t3 += q_first;
+		t5 -= (os.len - 1) - q_last;
+	}
+	else {
+		t5 += (int)(stop - start) - 1 - t_last;
+		t3 += (int)(stop - start) - 1 - t_first;
+		t5 -= q_first;
+		t3 += (os.len - 1) - q_last;
+	}
+	r.loc5 = t5;
+	r.loc3 = t3;
+}
+
+// Generic kernel: any IUPAC / inosine content, DP rows in shared memory.
 __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 {
 	extern __shared__ __align__(16) unsigned char s_raw[];
@@ -388,80 +470,134 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 
 		if (Lt > 0) {
 			const DpResult dp = nc_fill<ALIGN_THREADS>(sh, tgt, Lt, rowM, rowIq, rowIt, trace);
-			nc_enumerate<ALIGN_THREADS>(sh, a.thermo, os.r_log_ct, tgt, Lt, trace, dp, work, best_aln, best, flags);
+			RowMajorTrace<ALIGN_THREADS> tv;
+			tv.trace = trace;
+			tv.Lt = Lt;
+			uint16_t cells[MAX_MAXCELLS];
+			const int ncells = collect_max_cells<ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
+			nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
 		}
-
-		// thresholds in the reference's order (bind_oligo.cpp:598-714)
-		const float tm = best.tm;
-		const float dG = __fsub_rn(best.dH, __fmul_rn(a.thermo->T, best.dS));
-		bool pass = !(tm < os.min_tm || tm > os.max_tm);
-		if (pass) pass = !(dG < os.min_dg || dG > os.max_dg);
-		unsigned anchor5 = 0, anchor3 = 0, mm = 0, gaps = 0, poly = 0;
-		const bool want = a.emit_all || pass;
-		if (want && best.valid) {
-			anchor5 = nc_anchor5(sh, tgt, Lt, best_aln);
-			anchor3 = nc_anchor3(sh, tgt, Lt, best_aln);
-			nc_counts(sh, best_aln, mm, gaps, poly);
-		}
-		else if (want) {
-			// No alignment at all: the reference evaluates the anchors on a cleared alignment
-			// (first/last match left over).  Tm is 0 there, so this only passes with min_tm <= 0.
-			mm = (unsigned)os.len;
-		}
-		if (pass) pass = anchor5 >= os.clamp5;
-		if (pass) pass = anchor3 >= os.clamp3;
-		if (pass) pass = mm <= os.max_mismatch;
-		if (pass) pass = gaps <= os.max_gap;
-		if (pass) pass = poly <= os.max_poly_degen;
-		if (flags & (F_OOB | F_STACK)) pass = true; // surface it to the host, which reports it
-
-		if (!(a.emit_all || pass)) continue;
-
-		uint32_t slot;
-		if (a.emit_all) slot = unit.begin + tid;
-		else {
-			slot = atomicAdd(a.out_count, 1u);
-			if (slot >= a.out_cap) continue;
-		}
-		BoundRec &r = a.out[slot];
-		r.os = unit.os;
-		r.target = target;
-		r.tm = tm; r.dH = best.dH; r.dS = best.dS; r.dG = dG;
-		r.anchor5 = (int16_t)anchor5; r.anchor3 = (int16_t)anchor3;
-		r.num_mm = (int16_t)mm; r.num_gap = (int16_t)gaps; r.poly_degen = (int16_t)poly;
-		r.valid = best.valid ? 1 : 0;
-		r.k = k; r.t = c.t;
-		r.win_start = (int32_t)start; r.win_stop = (int32_t)stop;
-		r.fm_q = (int16_t)best_aln.fm_q; r.fm_t = (int16_t)best_aln.fm_t;
-		r.lm_q = (int16_t)best_aln.lm_q; r.lm_t = (int16_t)best_aln.lm_t;
-		r.Lt = (uint8_t)Lt;
-		r.flags = (uint8_t)flags;
-		r.pad = 0;
-		const int ncols = best.valid ? best_aln.e - best_aln.b : 0;
-		r.ncols = (uint8_t)ncols;
-		for (int i = 0; i < ncols; ++i) { r.cols_q[i] = best_aln.q[best_aln.b + i]; r.cols_t[i] = best_aln.t[best_aln.b + i]; }
-		for (int i = 0; i < Lt; ++i) r.win[i] = tgt[i];
-
-		// target coordinates (bind_oligo.cpp:721-731 minus, :1424-1434 plus)
-		const int q_first = best_aln.fm_q, q_last = best_aln.lm_q, t_first = best_aln.lm_t, t_last = best_aln.fm_t;
-		int t5 = (int)start, t3 = (int)start;
-		if (os.plus) {
-			t5 += t_first;
-			t3 += t_last;
-			t3 += q_first;
-			t5 -= (os.len - 1) - q_last;
-		}
-		else {
-			t5 += (int)(stop - start) - 1 - t_last;
-			t3 += (int)(stop - start) - 1 - t_first;
-			t5 -= q_first;
-			t3 += (os.len - 1) - q_last;
-		}
-		r.loc5 = t5;
-		r.loc3 = t3;
+		const uint32_t idx = unit.begin + tid;
+		finish_alignment(a, sh, os, unit.os, target, k, c.t, start, stop, tgt, Lt, best, best_aln, flags,
+			a.slot_map ? a.slot_map[idx] : idx);
 	}
 
 	// one atomic per warp for the cell counter
+	for (int off = 16; off; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
+	if ((tid & 31) == 0 && my_cells) atomicAdd(a.cells, my_cells);
+}
+
+// Fast kernel: windows made of A/C/G/T only (the oligo may hold any code).  All units of one
+// launch belong to oligo strands of at most LQ bases.
+template <int LQ>
+__global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
+{
+	__shared__ int32_t s_tab[LQ*ROW_WORDS];
+	__shared__ int32_t s_p5[20];
+	__shared__ uint8_t s_bbp[NB*NB];
+	__shared__ uint8_t s_wc[52];
+	__shared__ uint8_t s_q[MAX_OLIGO];
+
+	const int tid = threadIdx.x;
+	for (int i = tid; i < NB*NB; i += ALIGN_THREADS) s_bbp[i] = a.thermo->bbp[i];
+	for (int i = tid; i < NPAIR; i += ALIGN_THREADS) s_wc[i] = a.thermo->wc[i];
+	if (tid < 20) s_p5[tid] = a.p5_tab[tid];
+
+	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*(a.trace_cells/2)*ALIGN_THREADS + tid;
+	unsigned long long my_cells = 0;
+	uint32_t cur_os = 0xffffffffu;
+
+	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+		const AlignUnit unit = a.units[u];
+		const OligoStrand &os = a.os[unit.os];
+		if (unit.os != cur_os) { // uniform across the block
+			__syncthreads();
+			const int32_t *src = a.row_tab + a.row_tab_off[unit.os];
+			const int nreal = os.len*ROW_WORDS;
+			for (int i = tid; i < LQ*ROW_WORDS; i += ALIGN_THREADS) s_tab[i] = i < nreal ? src[i] : ROW_PAD_PENALTY;
+			if (tid < os.len) s_q[tid] = os.seq[tid];
+			cur_os = unit.os;
+			__syncthreads();
+		}
+		if ((uint32_t)tid >= unit.count) continue;
+
+		DpShared sh;
+		sh.dg = nullptr; sh.bbp = s_bbp; sh.wc = s_wc; sh.q = s_q; sh.Lq = os.len;
+
+		const uint32_t idx = unit.begin + tid;
+		const Candidate c = a.cand[(size_t)unit.os*a.cap + idx];
+		const uint32_t target = c.target_k & 0xffffffu, k = c.target_k >> 24;
+		const Target tg = a.db.targets[target];
+		const int s0 = (int)c.t - (int)(k + NUM_FLANK);
+		const uint32_t start = s0 > 0 ? (uint32_t)s0 : 0u;
+		const uint32_t stop = min(start + (uint32_t)os.len + 2u*NUM_FLANK, tg.len);
+		const int Lt = (int)(stop - start);
+
+		// 2-bit window straight from the packed database (<= 64 bases -> three words)
+		const uint64_t g0 = tg.base + start;
+		const uint64_t wi = g0 >> 5;
+		const unsigned sh2 = (unsigned)(g0 & 31u)*2u;
+		const uint64_t w0 = __ldg(a.db.db2 + wi), w1 = __ldg(a.db.db2 + wi + 1), w2 = __ldg(a.db.db2 + wi + 2);
+		uint64_t lo = sh2 ? ((w0 >> sh2) | (w1 << (64u - sh2))) : w0;
+		uint64_t hi = sh2 ? ((w1 >> sh2) | (w2 << (64u - sh2))) : w1;
+		// non-ACGT bases anywhere in the window? -> generic kernel
+		const unsigned shm = (unsigned)(g0 & 31u);
+		const uint64_t m01 = (uint64_t)__ldg(a.db.nmask + wi) | ((uint64_t)__ldg(a.db.nmask + wi + 1) << 32);
+		const uint64_t m2 = (uint64_t)__ldg(a.db.nmask + wi + 2);
+		uint64_t mwin = shm ? ((m01 >> shm) | (m2 << (64u - shm))) : m01;
+		if (Lt < 64) mwin &= (1ull << Lt) - 1ull;
+		if (mwin != 0 || Lt <= 0) {
+			if (Lt > 0) {
+				const uint32_t sl = atomicAdd(a.slow_count, 1u);
+				if (sl < a.slow_cap) {
+					SlowItem it;
+					it.os = unit.os;
+					it.slot = a.slot_map ? a.slot_map[idx] : idx;
+					it.c = c;
+					a.slow[sl] = it;
+				}
+				continue;
+			}
+		}
+		my_cells += (unsigned long long)(os.len*Lt);
+
+		// NucCruc target 5'->3': the window as is (plus strand) or its reverse complement
+		uint8_t tgt[MAX_WINDOW];
+		uint64_t tlo = 0, thi = 0;
+		if (os.plus) {
+			tlo = lo;
+			thi = hi;
+			for (int j = 0; j < Lt; ++j) tgt[j] = (uint8_t)packed_base(lo, hi, j);
+		}
+		else {
+			for (int j = 0; j < Lt; ++j) {
+				const int b = 3 - packed_base(lo, hi, Lt - 1 - j);
+				tgt[j] = (uint8_t)b;
+				if (j < 32) tlo |= (uint64_t)b << (2*j);
+				else thi |= (uint64_t)b << (2*(j - 32));
+			}
+		}
+
+		unsigned flags = 0;
+		AlnState work, best_aln;
+		Best best;
+		best.valid = false;
+		best.dH = best.dS = best.tm = 0.0f;
+		best_aln.b = best_aln.e = 2;
+		best_aln.fm_q = best_aln.fm_t = best_aln.lm_q = best_aln.lm_t = 0;
+
+		if (Lt > 0) {
+			const FastDp dp = nc_fill_fast<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
+			ColMajorTrace<LQ, ALIGN_THREADS> tv;
+			tv.trace32 = trace32;
+			uint16_t cells[MAX_MAXCELLS];
+			const int ncells = collect_max_cells_fast<LQ, ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
+			nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
+		}
+		finish_alignment(a, sh, os, unit.os, target, k, c.t, start, stop, tgt, Lt, best, best_aln, flags,
+			a.slot_map ? a.slot_map[idx] : idx);
+	}
+
 	for (int off = 16; off; off >>= 1) my_cells += __shfl_down_sync(0xffffffffu, my_cells, off);
 	if ((tid & 31) == 0 && my_cells) atomicAdd(a.cells, my_cells);
 }

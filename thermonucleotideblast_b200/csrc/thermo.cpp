@@ -170,6 +170,45 @@ void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3)
 		}
 }
 
+// Per-row penalty tables of the fast alignment kernel.  Row i (1-based) of the DP matrix pairs
+// the reversed oligo base qb = q[L-i] (previous: pq = q[L-i+1], GAP for i == 1) with the target;
+// every delta_g lookup of align_dimer (nuc_cruc.cpp:529-646) is a function of (row, target
+// dinucleotide) only.  Target dinucleotide index td = 4*pt + tb with pt in {A,C,G,T,GAP(=4)}.
+void build_row_tables(const Thermo &th, const OligoStrand &os, int32_t *out)
+{
+	auto bbp = [&](int x, int y) { return (int)th.bbp[x*NB + y]; };
+	const int L = os.len;
+	for (int i = 1; i <= L; ++i) {
+		int32_t *row = out + (size_t)(i - 1)*72;
+		const int qb = os.seq[L - i];
+		const int pq = (i == 1) ? (int)bGAP : (int)os.seq[L - i + 1];
+		for (int td = 0; td < 20; ++td) {
+			const int pt = (td/4 == 4) ? (int)bGAP : td/4;
+			const int tb = td%4;
+			const int cur = bbp(tb, qb);
+			row[0 + td] = th.dg[sidx(bbp(pt, pq), cur)];              // M from M
+			row[20 + td] = th.dg[sidx(bbp(pt, bGAP), cur)];           // M from I_query
+			row[40 + td] = th.dg[sidx(bbp(pt, qb), bbp(tb, bGAP))];   // I_query from M
+		}
+		for (int tb = 0; tb < 4; ++tb) {
+			row[60 + tb] = th.dg[sidx(bbp(bGAP, pq), bbp(tb, qb))];   // M from I_target
+			row[64 + tb] = th.dg[sidx(bbp(tb, pq), bbp(bGAP, qb))];   // I_target from M
+		}
+		row[68] = th.dg[sidx(bbp(bGAP, pq), bbp(bGAP, qb))];          // I_target from I_target
+		row[69] = row[70] = row[71] = 0;
+	}
+}
+
+// I_query from I_query: the only penalty that does not depend on the oligo row
+void build_p5_table(const Thermo &th, int32_t *out)
+{
+	for (int td = 0; td < 20; ++td) {
+		const int pt = (td/4 == 4) ? (int)bGAP : td/4;
+		const int tb = td%4;
+		out[td] = th.dg[sidx(th.bbp[pt*NB + bGAP], th.bbp[tb*NB + bGAP])];
+	}
+}
+
 float r_log_ct(float ct)
 {
 	return 1.9872e-3f*std::log(ct*1.0f); // NC_R*log(strand*alpha), nuc_cruc.cpp:2291
