@@ -18,7 +18,7 @@ const char kBaseChar[] = "ACGTI$-MRSVWYHKDBN"; // nuc_cruc_output.cpp:11
 
 // Text form of an alignment, three lines, including the unaligned 5'/3' overhangs with ':' for
 // complementary-but-unaligned positions (nuc_cruc_output.cpp:87-204).
-std::string render_alignment(const BoundRec &r, const OligoStrand &os)
+std::string render_alignment_impl(const BoundRec &r, const OligoStrand &os)
 {
 	const int Lq = os.len, Lt = r.Lt;
 	auto q = [&](int i) -> int { return (i >= 0 && i < Lq) ? os.seq[i] : (int)bGAP; };
@@ -45,14 +45,6 @@ std::string render_alignment(const BoundRec &r, const OligoStrand &os)
 	return s;
 }
 
-uint32_t intern(std::string &arena, const std::string &s)
-{
-	const uint32_t off = (uint32_t)arena.size();
-	arena.append(s);
-	arena.push_back('\0');
-	return off;
-}
-
 tnt_bound_oligo empty_slot()
 {
 	// hybrid_sig::init() (hybrid_sig.h:52-107)
@@ -65,7 +57,7 @@ tnt_bound_oligo empty_slot()
 	return b;
 }
 
-tnt_bound_oligo slot_of(const BoundSite &s, int oligo, std::string &arena)
+tnt_bound_oligo slot_of(const BoundSite &s, int oligo)
 {
 	tnt_bound_oligo b{};
 	b.oligo = oligo;
@@ -78,7 +70,7 @@ tnt_bound_oligo slot_of(const BoundSite &s, int oligo, std::string &arena)
 	b.num_gap = (int8_t)s.num_gap;
 	b.anchor_5 = s.anchor5;
 	b.anchor_3 = s.anchor3;
-	b.align_off = intern(arena, s.alignment);
+	b.align_off = 0;
 	return b;
 }
 
@@ -107,7 +99,7 @@ void unique_sites(std::vector<const BoundSite *> &v, bool mask_variant)
 			if (a->loc5 != b->loc5) return a->loc5 < b->loc5;
 			if (a->loc3 != b->loc3) return a->loc3 < b->loc3;
 			if (a->tm == b->tm) {
-				if (a->num_mm == b->num_mm) return a->alignment.size() > b->alignment.size();
+				if (a->num_mm == b->num_mm) return a->align_len > b->align_len;
 				return a->num_mm > b->num_mm;
 			}
 			return a->tm > b->tm;
@@ -131,7 +123,7 @@ void unique_sites(std::vector<const BoundSite *> &v, bool mask_variant)
 }
 
 void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int assay_id, bool has_probe,
-	const AssembleOptions &opt, std::vector<tnt_hit> &hits, std::string &arena)
+	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
 	// per (role, strand) uniqueness, then one list ordered by (loc_5, loc_3)
 	std::vector<const BoundSite *> all;
@@ -171,17 +163,20 @@ void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int 
 				h.primer_strand = (f.role == TNT_OLIGO_F) ? TNT_PLUS : TNT_MINUS;
 				h.amp_first = f.loc5;
 				h.amp_last = r.loc3;
-				h.forward = slot_of(fo, f_oligo, arena);
-				h.reverse = slot_of(ro, r_oligo, arena);
+				h.forward = slot_of(fo, f_oligo);
+				h.reverse = slot_of(ro, r_oligo);
+				HitSites hs{(int)(&fo - base), (int)(&ro - base), -1};
 				h.forward_clamp = (int8_t)fo.anchor3;
 				h.reverse_clamp = (int8_t)ro.anchor3;
 				if (p) {
-					h.probe = slot_of(*p, TNT_OLIGO_P, arena);
+					h.probe = slot_of(*p, TNT_OLIGO_P);
 					h.probe_first = p->loc5;
 					h.probe_last = p->loc3;
 					h.probe_strand = p->plus ? TNT_PLUS : TNT_MINUS;
+					hs.probe = (int)(p - base);
 				}
 				hits.push_back(h);
+				refs.push_back(hs);
 			};
 
 			if (!has_probe) { emit(nullptr); continue; }
@@ -198,7 +193,7 @@ void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int 
 }
 
 void join_padlock(const std::vector<const BoundSite *> &group, int assay_index, int assay_id,
-	const AssembleOptions &opt, std::vector<tnt_hit> &hits, std::string &arena)
+	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
 	const int max_len = opt.assay_format == TNT_ASSAY_MIPS ? (int)opt.max_len : 0;
 	for (int plus = 0; plus < 2; ++plus) {
@@ -218,17 +213,18 @@ void join_padlock(const std::vector<const BoundSite *> &group, int assay_index, 
 				h.amp_first = plus ? u->loc5 : d->loc5;
 				h.amp_last = plus ? d->loc3 : u->loc3;
 				if (h.amp_first > h.amp_last) throw std::runtime_error(":padlock: start > stop");
-				h.forward = slot_of(*d, TNT_OLIGO_F, arena);
-				h.reverse = slot_of(*u, TNT_OLIGO_R, arena);
+				h.forward = slot_of(*d, TNT_OLIGO_F);
+				h.reverse = slot_of(*u, TNT_OLIGO_R);
 				h.forward_clamp = (int8_t)d->anchor3;
 				h.reverse_clamp = (int8_t)u->anchor5;
 				hits.push_back(h);
+				refs.push_back(HitSites{(int)(d - base), (int)(u - base), -1});
 			}
 	}
 }
 
 void join_probe(const std::vector<const BoundSite *> &group, int assay_index, int assay_id,
-	std::vector<tnt_hit> &hits, std::string &arena)
+	const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
 	for (int plus = 0; plus < 2; ++plus) { // minus strand first (probe_search.cpp:92-151)
 		std::vector<const BoundSite *> b;
@@ -237,59 +233,70 @@ void join_probe(const std::vector<const BoundSite *> &group, int assay_index, in
 		for (const BoundSite *s : b) {
 			if (s->loc5 > s->loc3) throw std::runtime_error(":hybrid: probe_start > probe_stop");
 			tnt_hit h = blank_hit(assay_index, assay_id, s->target);
-			h.probe = slot_of(*s, TNT_OLIGO_P, arena);
+			h.probe = slot_of(*s, TNT_OLIGO_P);
 			h.probe_first = s->loc5;
 			h.probe_last = s->loc3;
 			h.probe_strand = plus ? TNT_PLUS : TNT_MINUS;
 			hits.push_back(h);
+			refs.push_back(HitSites{-1, -1, (int)(s - base)});
 		}
 	}
 }
 
 } // namespace
 
-BoundSite make_site(const BoundRec &r, const OligoStrand &os)
+std::string render_alignment(const BoundRec &r, const OligoStrand &os)
+{
+	return r.valid ? render_alignment_impl(r, os) : std::string();
+}
+
+BoundSite make_site(const BoundHead &h, uint32_t index, const OligoStrand &os)
 {
 	BoundSite s;
 	s.assay = os.assay;
 	s.role = os.role;
 	s.plus = os.plus;
-	s.target = r.target;
-	s.loc5 = r.loc5;
-	s.loc3 = r.loc3;
-	s.tm = r.tm; s.dH = r.dH; s.dS = r.dS; s.dG = r.dG;
-	s.anchor5 = r.anchor5; s.anchor3 = r.anchor3;
-	s.num_mm = r.num_mm; s.num_gap = r.num_gap; s.poly_degen = r.poly_degen;
-	s.valid = r.valid;
-	s.flags = r.flags;
-	s.query_loc = r.k;
-	s.target_loc = r.t;
-	s.win_start = r.win_start;
-	s.win_stop = r.win_stop;
-	s.q_first = r.fm_q;
-	s.q_last = r.lm_q;
-	s.t_first = r.lm_t; // alignment_range_target (nuc_cruc_anchor.cpp:386-389)
-	s.t_last = r.fm_t;
-	if (r.valid) s.alignment = render_alignment(r, os);
+	s.index = index;
+	s.target = h.target;
+	s.loc5 = h.loc5;
+	s.loc3 = h.loc3;
+	s.tm = h.tm; s.dH = h.dH; s.dS = h.dS;
+	s.anchor5 = h.anchor5; s.anchor3 = h.anchor3;
+	s.num_mm = h.num_mm; s.num_gap = h.num_gap;
+	s.flags = h.flags;
+	s.query_loc = h.k;
+	s.target_loc = h.t;
+	s.align_len = h.align_len;
 	return s;
 }
 
-void assemble_hits(std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
+void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
 	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
-	std::vector<tnt_hit> &hits, std::string &arena)
+	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
 	// (fragment, assay) pairs in ascending order, like the reference's nested loops
-	std::map<std::pair<uint32_t, int>, std::vector<const BoundSite *>> groups;
-	for (const BoundSite &s : sites) groups[{s.target, s.assay}].push_back(&s);
-	for (auto &kv : groups) {
-		const int ai = kv.first.second;
+	std::vector<uint32_t> order(sites.size());
+	for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+		if (sites[a].target != sites[b].target) return sites[a].target < sites[b].target;
+		return sites[a].assay < sites[b].assay;
+	});
+	const BoundSite *base = sites.data();
+	std::vector<const BoundSite *> group;
+	for (size_t i = 0; i < order.size();) {
+		size_t j = i;
+		group.clear();
+		while (j < order.size() && sites[order[j]].target == sites[order[i]].target && sites[order[j]].assay == sites[order[i]].assay)
+			group.push_back(&sites[order[j++]]);
+		const int ai = sites[order[i]].assay;
 		const int id = assay_ids[(size_t)ai];
 		if (assay_has_primers[(size_t)ai]) { // tntblast_local.cpp:559-611
 			if (opt.assay_format == TNT_ASSAY_PADLOCK || opt.assay_format == TNT_ASSAY_MIPS)
-				join_padlock(kv.second, ai, id, opt, hits, arena);
-			else join_pcr(kv.second, ai, id, assay_has_probe[(size_t)ai] != 0, opt, hits, arena);
+				join_padlock(group, ai, id, opt, base, hits, refs);
+			else join_pcr(group, ai, id, assay_has_probe[(size_t)ai] != 0, opt, base, hits, refs);
 		}
-		else join_probe(kv.second, ai, id, hits, arena); // :612-625
+		else join_probe(group, ai, id, base, hits, refs); // :612-625
+		i = j;
 	}
 }
 

@@ -9,22 +9,27 @@
 
 namespace tnt {
 
-// One bound oligo site == oligo_info of the reference (tntblast.h:145-243)
+// One bound oligo site == oligo_info of the reference (tntblast.h:145-243), without the alignment
+// text: only its length takes part in the ordering (bind_oligo.cpp:69-74).
 struct BoundSite {
 	int assay, role, plus;
+	uint32_t index;      // record index in the device-side bound-site buffer
 	uint32_t target;
 	int loc5, loc3;
-	float tm, dH, dS, dG;
-	int anchor5, anchor3, num_mm, num_gap, poly_degen;
-	int valid;
+	float tm, dH, dS;
+	int anchor5, anchor3, num_mm, num_gap;
 	unsigned flags;
 	uint32_t query_loc, target_loc;   // the seed
-	int win_start, win_stop;
-	int q_first, q_last, t_first, t_last;
-	std::string alignment;            // NucCruc operator<< text (nuc_cruc_output.cpp:74-205)
+	uint32_t align_len;
 };
 
-BoundSite make_site(const BoundRec &rec, const OligoStrand &os);
+BoundSite make_site(const BoundHead &h, uint32_t index, const OligoStrand &os);
+
+// NucCruc operator<< text (nuc_cruc_output.cpp:74-205) of one record
+std::string render_alignment(const BoundRec &r, const OligoStrand &os);
+
+// which bound sites a hit is made of (indices into the `sites` array, -1: none)
+struct HitSites { int forward, reverse, probe; };
 
 struct AssembleOptions {
 	int assay_format;
@@ -35,9 +40,10 @@ struct AssembleOptions {
 
 // amplicon() join (amplicon_search.cpp:355-674), padlock() joins (padlock_search.cpp:130-358),
 // hybrid() (probe_search.cpp:103-227); `sites` holds everything that passed the per-oligo filters.
-void assemble_hits(std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
+// The alignment-text offsets of the hits are left at 0; `refs` tells the caller which sites to render.
+void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
 	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
-	std::vector<tnt_hit> &hits, std::string &arena);
+	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
 
 enum class SeqMode { PcrPlus, PcrMinus, ProbePlus, ProbeMinus, PadlockMinusStrand, PadlockPlusStrand };
 

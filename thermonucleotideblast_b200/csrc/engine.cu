@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +33,20 @@ using namespace tnt;
 namespace {
 
 thread_local std::string g_error;
+
+// TNT_PROFILE=1: wall-clock of the host-side sections of a search on stderr
+struct HostTimer {
+	const char *name;
+	std::chrono::steady_clock::time_point t0;
+	static bool enabled() { static const bool on = std::getenv("TNT_PROFILE") != nullptr; return on; }
+	explicit HostTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+	~HostTimer()
+	{
+		if (!enabled()) return;
+		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		fprintf(stderr, "[tnt] %-28s %9.3f ms\n", name, ms);
+	}
+};
 
 struct CudaError : std::runtime_error {
 	using std::runtime_error::runtime_error;
@@ -143,7 +159,12 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_cand_count;
 	DevBuf<AlignUnit> d_units;
 	DevBuf<uint16_t> d_trace;
-	DevBuf<BoundRec> d_out;
+	DevBuf<BoundRec> d_bound;    // every site that passed the per-oligo filters, all passes of a search
+	uint32_t n_bound = 0;
+	DevBuf<BoundRec> d_gather;
+	DevBuf<uint32_t> d_gather_idx;
+	BoundHead *h_heads = nullptr; // pinned
+	size_t h_heads_cap = 0;
 	DevBuf<uint32_t> d_out_count;
 	DevBuf<unsigned long long> d_cells;
 	DevBuf<Region> d_regions;
@@ -166,6 +187,7 @@ struct tnt_engine {
 			if (stage_free[i]) cudaEventDestroy(stage_free[i]);
 		}
 		if (h_total) cudaFreeHost(h_total);
+		if (h_heads) cudaFreeHost(h_heads);
 		if (d_total) cudaFree(d_total);
 		for (auto &e : ev) if (e) cudaEventDestroy(e);
 		if (stream) cudaStreamDestroy(stream);
@@ -419,7 +441,7 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector
 
 // Align every candidate currently in the buckets of `set`; append the survivors to `out`.
 // Returns false if a bucket overflowed (the caller shrinks the chunk and retries).
-bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec> &out, bool emit_all,
+bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bool emit_all,
 	std::vector<uint32_t> *counts_out = nullptr)
 {
 	const size_t nos = set.os.size();
@@ -434,8 +456,9 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec
 	}
 	e->stats.seeds += total;
 	if (total == 0) return true;
-	if (emit_all && nos != 1) throw std::runtime_error("emit_all needs a single oligo strand");
+	if (emit_all && (nos != 1 || e->n_bound != 0)) throw std::runtime_error("emit_all needs a single oligo strand and an empty site buffer");
 
+	HostTimer t_ab("  align_buckets");
 	// units per fast class
 	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));
 	std::vector<std::vector<AlignUnit>> by_class(nclass);
@@ -446,7 +469,8 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec
 			by_class[c].push_back(AlignUnit{(uint32_t)s, b, std::min<uint32_t>(ALIGN_THREADS, counts[s] - b)});
 	}
 
-	size_t out_cap = emit_all ? (size_t)total : std::max<size_t>(e->d_out.cap, 1u << 16);
+	const uint32_t base_count = e->n_bound;
+	size_t out_cap = emit_all ? (size_t)base_count + total : std::max<size_t>(e->d_bound.cap, (size_t)base_count + (1u << 16));
 	size_t slow_cap = std::max<size_t>(e->d_slow.cap, 1u << 16);
 	// snapshot of the DP-cell counter so that a retried pass is not counted twice
 	unsigned long long cells_before = 0;
@@ -454,9 +478,14 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 
 	for (;;) {
-		e->d_out.reserve(out_cap, 0, e->stream);
+		e->d_bound.reserve(out_cap, base_count, e->stream);
+		out_cap = e->d_bound.cap;
 		e->d_slow.reserve(slow_cap, 0, e->stream);
-		CUDA_OK(cudaMemsetAsync(e->d_out_count.p, 0, 2*sizeof(uint32_t), e->stream));
+		{
+			const uint32_t init[2] = {base_count, 0};
+			CUDA_OK(cudaMemcpyAsync(e->d_out_count.p, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+		}
 		CUDA_OK(cudaMemcpyAsync(e->d_cells.p, &cells_before, sizeof(cells_before), cudaMemcpyHostToDevice, e->stream));
 		AlignArgs a{};
 		a.db = e->view();
@@ -464,7 +493,8 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec
 		a.os = set.d_os.p;
 		a.cand = e->d_cand.p;
 		a.cap = cap;
-		a.out = e->d_out.p;
+		a.out = e->d_bound.p;
+		a.os_base = os_base;
 		a.out_count = e->d_out_count.p;
 		a.out_cap = (uint32_t)out_cap;
 		a.emit_all = emit_all ? 1 : 0;
@@ -516,19 +546,16 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, std::vector<BoundRec
 		e->stats.align_ms += ms;
 
 		uint32_t n = cnt[0];
-		if (emit_all) n = (uint32_t)total;
+		if (emit_all) n = base_count + (uint32_t)total;
 		else if (n > out_cap) { out_cap = (size_t)n + n/4; continue; } // enlarge and redo this pass
 		e->stats.alignments += total;
-		const size_t old = out.size();
-		out.resize(old + n);
-		if (n) CUDA_OK(cudaMemcpyAsync(out.data() + old, e->d_out.p, (size_t)n*sizeof(BoundRec), cudaMemcpyDeviceToHost, e->stream));
-		CUDA_OK(cudaStreamSynchronize(e->stream));
+		e->n_bound = n;
 		return true;
 	}
 }
 
 // Stage A+B over all fragments for one oligo-strand set, chunked so the candidate buckets fit.
-void scan_and_align(tnt_engine *e, OsSet &set, std::vector<BoundRec> &out)
+void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 {
 	if (set.os.empty() || e->tiles.empty()) return;
 	const size_t nos = set.os.size();
@@ -568,7 +595,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, std::vector<BoundRec> &out)
 			CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
 			e->stats.kernel_launches++;
 			const uint64_t seeds_before = e->stats.seeds;
-			const bool ok = align_buckets(e, set, cap, out, false);
+			const bool ok = align_buckets(e, set, cap, os_base, false);
 			float ms = 0;
 			CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
 			e->stats.scan_ms += ms;
@@ -587,7 +614,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, std::vector<BoundRec> &out)
 }
 
 // Stage-2: scan regions with the given set
-void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> &regions, std::vector<BoundRec> &out)
+void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> &regions, uint32_t os_base)
 {
 	if (set.os.empty() || regions.empty()) return;
 	const size_t nos = set.os.size();
@@ -614,13 +641,34 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 		CUDA_OK(cudaGetLastError());
 		CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
 		e->stats.kernel_launches++;
-		const bool ok = align_buckets(e, set, cap, out, false);
+		const bool ok = align_buckets(e, set, cap, os_base, false);
 		float ms = 0;
 		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
 		e->stats.scan_ms += ms;
 		if (ok) return;
 		if (cap >= (1u << 30)) throw std::runtime_error("stage-2 seed buckets overflow");
 		cap *= 2;
+	}
+}
+
+// Heads (48 B) of the bound-site records [from, to) -> pinned host array
+void fetch_heads(tnt_engine *e, uint32_t from, uint32_t to)
+{
+	if (to > e->h_heads_cap) {
+		size_t ncap = std::max<size_t>(to, e->h_heads_cap*2 + 4096);
+		BoundHead *np = nullptr;
+		CUDA_OK(cudaMallocHost(&np, ncap*sizeof(BoundHead)));
+		if (e->h_heads) {
+			std::memcpy(np, e->h_heads, (size_t)from*sizeof(BoundHead));
+			cudaFreeHost(e->h_heads);
+		}
+		e->h_heads = np;
+		e->h_heads_cap = ncap;
+	}
+	if (to > from) {
+		CUDA_OK(cudaMemcpy2DAsync(e->h_heads + from, sizeof(BoundHead), e->d_bound.p + from, sizeof(BoundRec),
+			sizeof(BoundHead), to - from, cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
 	}
 }
 
@@ -691,18 +739,23 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		}
 	}
 
-	std::vector<BoundRec> recs1, recs2;
-	finish_set(e, stage1);
-	scan_and_align(e, stage1, recs1);
+	e->n_bound = 0;
+	{ HostTimer t("finish_set stage1"); finish_set(e, stage1); }
+	{ HostTimer t("scan_and_align stage1"); scan_and_align(e, stage1, 0); }
+	const uint32_t n1 = e->n_bound;
+	fetch_heads(e, 0, n1);
 
-	if (!stage2.os.empty() && !recs1.empty()) {
+	if (!stage2.os.empty() && n1 != 0) {
+		HostTimer t_s2("stage2 total");
 		finish_set(e, stage2);
 		// Partner primers / probes can only matter downstream of a bound minus-strand primer
 		// (amplicon_search.cpp:359-441: f on the minus strand, r and p after it, amplicon <= max_len;
 		// cull_oligo_match :679-765 uses max_len + 50 on seed positions).
 		std::vector<Region> regions;
+		regions.reserve(n1);
 		const uint32_t slack = 64;
-		for (const BoundRec &b : recs1) {
+		for (uint32_t i = 0; i < n1; ++i) {
+			const BoundHead &b = e->h_heads[i];
 			if (b.flags & (F_OOB | F_STACK | F_TRUNC)) continue;
 			const Target &tg = e->targets[b.target];
 			Region r;
@@ -725,8 +778,10 @@ void search(tnt_engine *e, const tnt_search_options &o)
 				merged.back().stop = std::max(merged.back().stop, r.stop);
 			else merged.push_back(r);
 		}
-		region_scan_and_align(e, stage2, merged, recs2);
+		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, merged, (uint32_t)stage1.os.size()); }
 	}
+	const uint32_t n2 = e->n_bound;
+	fetch_heads(e, n1, n2);
 
 	CUDA_OK(cudaEventRecord(t_end, e->stream));
 	unsigned long long cells = 0;
@@ -738,15 +793,20 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	e->stats.total_ms = ms;
 
 	// Stage C
+	HostTimer t_sites("stage C total");
+	auto os_of = [&](uint32_t g) -> const OligoStrand & {
+		return g < stage1.os.size() ? stage1.os[g] : stage2.os[g - stage1.os.size()];
+	};
 	std::vector<BoundSite> sites;
-	sites.reserve(recs1.size() + recs2.size());
-	for (const BoundRec &b : recs1) sites.push_back(make_site(b, stage1.os[b.os]));
-	for (const BoundRec &b : recs2) sites.push_back(make_site(b, stage2.os[b.os]));
-	for (const BoundSite &s : sites)
-		if (s.flags & F_TRUNC)
+	sites.reserve(n2);
+	for (uint32_t i = 0; i < n2; ++i) {
+		const BoundHead &b = e->h_heads[i];
+		if (b.flags & F_TRUNC)
 			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
-		else if (s.flags & (F_OOB | F_STACK))
+		if (b.flags & (F_OOB | F_STACK))
 			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
+		sites.push_back(make_site(b, i, os_of(b.os)));
+	}
 	e->stats.bound_sites = sites.size();
 
 	AssembleOptions ao;
@@ -760,8 +820,43 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		assay_has_primers.push_back(!a.F.empty() && !a.R.empty());
 		assay_has_probe.push_back(!a.P.empty());
 	}
-	assemble_hits(sites, ao, assay_ids, assay_has_primers, assay_has_probe, e->hits, e->arena);
+	std::vector<HitSites> refs;
+	{ HostTimer t("assemble_hits"); assemble_hits(sites, ao, assay_ids, assay_has_primers, assay_has_probe, e->hits, refs); }
 	e->stats.hits = e->hits.size();
+
+	// Alignment text only for the sites that made it into a hit: gather their full records
+	std::vector<uint32_t> need;
+	for (const HitSites &h : refs)
+		for (int s : {h.forward, h.reverse, h.probe})
+			if (s >= 0) need.push_back(sites[(size_t)s].index);
+	std::sort(need.begin(), need.end());
+	need.erase(std::unique(need.begin(), need.end()), need.end());
+	std::vector<BoundRec> recs(need.size());
+	if (!need.empty()) {
+		e->d_gather_idx.upload(need, e->stream);
+		e->d_gather.reserve(need.size(), 0, e->stream);
+		k_gather_recs<<<(unsigned)std::min<size_t>(need.size(), 1024), 128, 0, e->stream>>>(e->d_bound.p, e->d_gather_idx.p, (uint32_t)need.size(), e->d_gather.p);
+		CUDA_OK(cudaGetLastError());
+		e->stats.kernel_launches++;
+		CUDA_OK(cudaMemcpyAsync(recs.data(), e->d_gather.p, recs.size()*sizeof(BoundRec), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+	}
+	std::vector<uint32_t> text_off(need.size());
+	for (size_t i = 0; i < need.size(); ++i) {
+		text_off[i] = (uint32_t)e->arena.size();
+		e->arena.append(render_alignment(recs[i], os_of(recs[i].h.os)));
+		e->arena.push_back('\0');
+	}
+	auto off_of = [&](int s) -> uint32_t {
+		if (s < 0) return 0;
+		const uint32_t idx = sites[(size_t)s].index;
+		return text_off[(size_t)(std::lower_bound(need.begin(), need.end(), idx) - need.begin())];
+	};
+	for (size_t i = 0; i < e->hits.size(); ++i) {
+		e->hits[i].forward.align_off = off_of(refs[i].forward);
+		e->hits[i].reverse.align_off = off_of(refs[i].reverse);
+		e->hits[i].probe.align_off = off_of(refs[i].probe);
+	}
 }
 
 long hit_sequence(tnt_engine *e, const tnt_hit *h, char *out, size_t cap)
@@ -1035,23 +1130,28 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
 	e->d_cand_count.reserve(1, 0, e->stream);
 	const uint32_t cnt = (uint32_t)n;
 	CUDA_OK(cudaMemcpyAsync(e->d_cand_count.p, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, e->stream));
-	std::vector<BoundRec> recs;
-	if (!align_buckets(e, set, cap, recs, true)) throw std::runtime_error("internal: bucket overflow");
+	e->n_bound = 0;
+	if (!align_buckets(e, set, cap, 0, true)) throw std::runtime_error("internal: bucket overflow");
+	std::vector<BoundRec> recs((size_t)n);
+	if (n) CUDA_OK(cudaMemcpyAsync(recs.data(), e->d_bound.p, (size_t)n*sizeof(BoundRec), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->n_bound = 0;
 	for (long i = 0; i < n; ++i) {
-		const BoundSite s = make_site(recs[(size_t)i], set.os[0]);
+		const BoundRec &b = recs[(size_t)i];
 		tnt_align_result &r = out[i];
 		std::memset(&r, 0, sizeof(r));
-		r.tm = s.tm; r.dH = s.dH; r.dS = s.dS; r.dG = s.dG;
-		r.valid = s.valid;
-		r.target_start = s.win_start;
-		r.target_stop = s.win_stop;
-		if (s.flags & (F_OOB | F_STACK | F_TRUNC)) r.valid = -1;
-		if (s.valid) {
-			r.anchor5 = s.anchor5; r.anchor3 = s.anchor3;
-			r.num_mismatch = s.num_mm; r.num_gap = s.num_gap; r.max_poly_degen = s.poly_degen;
-			r.q_first = s.q_first; r.q_last = s.q_last; r.t_first = s.t_first; r.t_last = s.t_last;
-			r.loc_5 = s.loc5; r.loc_3 = s.loc3;
-			std::strncpy(r.alignment, s.alignment.c_str(), sizeof(r.alignment) - 1);
+		r.tm = b.h.tm; r.dH = b.h.dH; r.dS = b.h.dS; r.dG = b.dG;
+		r.valid = b.valid;
+		r.target_start = b.win_start;
+		r.target_stop = b.win_stop;
+		if (b.h.flags & (F_OOB | F_STACK | F_TRUNC)) r.valid = -1;
+		if (b.valid) {
+			r.anchor5 = b.h.anchor5; r.anchor3 = b.h.anchor3;
+			r.num_mismatch = b.h.num_mm; r.num_gap = b.h.num_gap; r.max_poly_degen = b.poly_degen;
+			r.q_first = b.fm_q; r.q_last = b.lm_q;
+			r.t_first = b.lm_t; r.t_last = b.fm_t; // alignment_range_target, nuc_cruc_anchor.cpp:386-389
+			r.loc_5 = b.h.loc5; r.loc_3 = b.h.loc3;
+			std::strncpy(r.alignment, render_alignment(b, set.os[0]).c_str(), sizeof(r.alignment) - 1);
 		}
 	}
 	unsigned long long cells = 0;

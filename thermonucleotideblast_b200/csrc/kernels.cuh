@@ -333,6 +333,7 @@ struct AlignArgs {
 	BoundRec *out;             // filtered mode: appended; all mode: out[slot]
 	uint32_t *out_count;
 	uint32_t out_cap;
+	uint32_t os_base;          // added to the oligo-strand index stored in the records
 	int emit_all;              // 1: write every result at out[units[u].begin + tid] (or slot_map[...])
 	const uint32_t *slot_map;  // optional, emit_all only: output slot per candidate index
 	unsigned long long *cells; // sum of Lq*Lt
@@ -379,23 +380,32 @@ __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, 
 		if (slot >= a.out_cap) return;
 	}
 	BoundRec &r = a.out[slot];
-	r.os = os_index;
-	r.target = target;
-	r.tm = tm; r.dH = best.dH; r.dS = best.dS; r.dG = dG;
-	r.anchor5 = (int16_t)anchor5; r.anchor3 = (int16_t)anchor3;
-	r.num_mm = (int16_t)mm; r.num_gap = (int16_t)gaps; r.poly_degen = (int16_t)poly;
+	r.h.os = a.os_base + os_index;
+	r.h.target = target;
+	r.h.tm = tm; r.h.dH = best.dH; r.h.dS = best.dS;
+	r.dG = dG;
+	r.h.anchor5 = (int16_t)anchor5; r.h.anchor3 = (int16_t)anchor3;
+	r.h.num_mm = (int16_t)mm; r.h.num_gap = (int16_t)gaps;
+	r.poly_degen = (int16_t)poly;
 	r.valid = best.valid ? 1 : 0;
-	r.k = k; r.t = t;
+	r.h.k = (uint8_t)k; r.h.t = t;
+	r.h.flags = (uint8_t)flags;
+	r.h.pad = 0;
 	r.win_start = (int32_t)start; r.win_stop = (int32_t)stop;
 	r.fm_q = (int16_t)best_aln.fm_q; r.fm_t = (int16_t)best_aln.fm_t;
 	r.lm_q = (int16_t)best_aln.lm_q; r.lm_t = (int16_t)best_aln.lm_t;
 	r.Lt = (uint8_t)Lt;
-	r.flags = (uint8_t)flags;
-	r.pad = 0;
+	r.pad0 = r.pad1 = 0;
 	const int ncols = best.valid ? best_aln.e - best_aln.b : 0;
 	r.ncols = (uint8_t)ncols;
 	for (int i = 0; i < ncols; ++i) { r.cols_q[i] = best_aln.q[best_aln.b + i]; r.cols_t[i] = best_aln.t[best_aln.b + i]; }
 	for (int i = 0; i < Lt; ++i) r.win[i] = tgt[i];
+	{
+		// length of the text nuc_cruc_output.cpp:87-204 renders: unaligned prefix + columns + suffix
+		const int prefix = max(0, min(best_aln.fm_q, Lt - 1 - best_aln.fm_t));
+		const int suffix = max(0, min(os.len - 1 - best_aln.lm_q, best_aln.lm_t));
+		r.h.align_len = (uint16_t)(best.valid ? 3*(prefix + ncols + suffix) + 17 : 0);
+	}
 
 	const int q_first = best_aln.fm_q, q_last = best_aln.lm_q, t_first = best_aln.lm_t, t_last = best_aln.fm_t;
 	int t5 = (int)start, t3 = (int)start;
@@ -411,8 +421,19 @@ __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, 
 		t5 -= q_first;
 		t3 += (os.len - 1) - q_last;
 	}
-	r.loc5 = t5;
-	r.loc3 = t3;
+	r.h.loc5 = t5;
+	r.h.loc3 = t3;
+}
+
+// Copy selected records into a dense array (the hits' oligo sites, for text rendering)
+__global__ void k_gather_recs(const BoundRec *__restrict__ src, const uint32_t *__restrict__ index, uint32_t n, BoundRec *__restrict__ dst)
+{
+	const uint32_t words = sizeof(BoundRec)/4;
+	for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+		const uint32_t *s = reinterpret_cast<const uint32_t *>(src + index[i]);
+		uint32_t *d = reinterpret_cast<uint32_t *>(dst + i);
+		for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) d[w] = s[w];
+	}
 }
 
 // Generic kernel: any IUPAC / inosine content, DP rows in shared memory.

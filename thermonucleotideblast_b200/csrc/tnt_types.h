@@ -64,17 +64,29 @@ struct Candidate {
 };
 
 // Result of one alignment that passed the per-oligo filters (or every alignment in debug mode).
-struct BoundRec {
-	uint32_t os;
+// The 48-byte head is all the assembly stage needs; the tail (aligned columns + window) is only
+// fetched for the sites that end up in a reported hit, to render the alignment text.
+struct BoundHead {
+	uint32_t os;                 // global oligo-strand index (stage-1 set first, then stage-2 set)
 	uint32_t target;
 	int32_t loc5, loc3;
-	float tm, dH, dS, dG;
+	float tm, dH, dS;
 	int16_t anchor5, anchor3, num_mm, num_gap;
+	uint32_t t;                  // seed position (oligo_info::target_loc)
+	uint8_t k;                   // seed word index (oligo_info::query_loc)
+	uint8_t flags;
+	uint16_t align_len;          // length of the rendered alignment text
+	uint32_t pad;
+};
+static_assert(sizeof(BoundHead) == 48, "BoundHead layout");
+
+struct BoundRec {
+	BoundHead h;
+	float dG;
 	int16_t poly_degen, valid;
-	uint32_t k, t;               // seed that produced the window
 	int32_t win_start, win_stop; // window in fragment coordinates
 	int16_t fm_q, fm_t, lm_q, lm_t;
-	uint8_t ncols, Lt, flags, pad;
+	uint8_t ncols, Lt, pad0, pad1;
 	uint8_t cols_q[MAX_COLS];    // aligned columns (NucCruc codes), 5'->3' along the query
 	uint8_t cols_t[MAX_COLS];
 	uint8_t win[MAX_WINDOW];     // the NucCruc target (5'->3') the alignment ran against
