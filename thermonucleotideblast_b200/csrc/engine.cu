@@ -622,10 +622,10 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 	e->d_regions.upload(regions, e->stream);
 	// Size the buckets for the busiest assay: expected seeds = positions x words / 4^W; start with
 	// generous slack and double on overflow (repeat-rich fragments can exceed any estimate).
-	std::map<int, uint64_t> per_assay;
-	for (const Region &r : regions) per_assay[r.assay] += r.stop - r.start;
+	std::vector<uint64_t> per_assay(e->assays.size() + 1, 0);
+	for (const Region &r : regions) per_assay[(size_t)r.assay] += r.stop - r.start;
 	uint64_t worst = 0;
-	for (auto &kv : per_assay) worst = std::max(worst, kv.second);
+	for (uint64_t v : per_assay) worst = std::max(worst, v);
 	const double expect = (double)worst*(double)set.max_words/(double)set.nkeys;
 	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
 	for (;;) {
@@ -767,17 +767,10 @@ void search(tnt_engine *e, const tnt_search_options &o)
 			r.stop = (uint32_t)std::min<int64_t>(tg.len, std::max<int64_t>(hi, 0));
 			if (r.stop > r.start) regions.push_back(r);
 		}
-		std::sort(regions.begin(), regions.end(), [](const Region &a, const Region &b) {
-			if (a.target != b.target) return a.target < b.target;
-			if (a.assay != b.assay) return a.assay < b.assay;
-			return a.start < b.start;
-		});
-		std::vector<Region> merged;
-		for (const Region &r : regions) {
-			if (!merged.empty() && merged.back().target == r.target && merged.back().assay == r.assay && r.start <= merged.back().stop)
-				merged.back().stop = std::max(merged.back().stop, r.stop);
-			else merged.push_back(r);
-		}
+		// Overlapping regions are not merged: a seed found twice is aligned twice and collapses
+		// again in the per-(loc_5, loc_3) uniqueness step, exactly like duplicate windows do in
+		// the reference (bind_oligo.cpp:810-826).
+		const std::vector<Region> &merged = regions;
 		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, merged, (uint32_t)stage1.os.size()); }
 	}
 	const uint32_t n2 = e->n_bound;
@@ -797,17 +790,36 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	auto os_of = [&](uint32_t g) -> const OligoStrand & {
 		return g < stage1.os.size() ? stage1.os[g] : stage2.os[g - stage1.os.size()];
 	};
+	// PCR: an amplicon needs a plus-strand primer site, and those only come out of stage 2.  Drop
+	// the (fragment, assay) groups without one before any sorting happens.
+	std::vector<uint64_t> live_keys;
+	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty();
+	if (prefilter) {
+		for (uint32_t i = n1; i < n2; ++i) {
+			const BoundHead &b = e->h_heads[i];
+			const OligoStrand &os = os_of(b.os);
+			if (os.role != TNT_OLIGO_P) live_keys.push_back(((uint64_t)b.target << 32) | (uint32_t)os.assay);
+		}
+		std::sort(live_keys.begin(), live_keys.end());
+		live_keys.erase(std::unique(live_keys.begin(), live_keys.end()), live_keys.end());
+	}
+	uint64_t n_sites_total = 0;
 	std::vector<BoundSite> sites;
-	sites.reserve(n2);
+	sites.reserve(prefilter ? (size_t)(n2 - n1)*4 + 64 : n2);
 	for (uint32_t i = 0; i < n2; ++i) {
 		const BoundHead &b = e->h_heads[i];
+		++n_sites_total;
 		if (b.flags & F_TRUNC)
 			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
 		if (b.flags & (F_OOB | F_STACK))
 			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
-		sites.push_back(make_site(b, i, os_of(b.os)));
+		const OligoStrand &os = os_of(b.os);
+		if (prefilter && e->assays[(size_t)os.assay].F.size() &&
+			!std::binary_search(live_keys.begin(), live_keys.end(), ((uint64_t)b.target << 32) | (uint32_t)os.assay))
+			continue;
+		sites.push_back(make_site(b, i, os));
 	}
-	e->stats.bound_sites = sites.size();
+	e->stats.bound_sites = n_sites_total;
 
 	AssembleOptions ao;
 	ao.assay_format = o.assay_format;
