@@ -98,7 +98,7 @@ class ClockSampler:
         os.close(fd)
         self.f = open(self.path, "w")
         self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits", "-lms", "200"],
+                                      "--format=csv,noheader,nounits", "-lms", "250"],
                                      stdout=self.f, stderr=subprocess.DEVNULL)
 
     def stop(self):
@@ -290,8 +290,9 @@ def main():
     for _ in range(args.warmup):
         eng.search_raw(opts)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    time.sleep(0.3)   # let nvidia-smi attach before the timed region starts
+    barrier()
     t0 = time.perf_counter()
     dev_ms = scan_ms = align_ms = 0.0
     launches = 0
