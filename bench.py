@@ -59,17 +59,26 @@ def env_int(name, default):
         return default
 
 
-def build_workload(rank: int, mbp: int, n_assays: int):
-    """Synthetic shard of `mbp` Mbp (records of 5 Mbp) + TaqMan assays planted into it."""
+def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False):
+    """Synthetic shard of `mbp` Mbp (records of 5 Mbp) + TaqMan assays planted into it.
+
+    With pinned=True the bases live in one page-locked host allocation (the fragments are views
+    into it), so the engine's uploads are true pinned-memory H2D copies."""
     from thermonucleotideblast_b200.sharding import fragment_record
     rng = np.random.default_rng(2 + 1000 * rank)
     total = mbp * 1_000_000
+    if pinned:
+        import torch
+        store = torch.empty(total, dtype=torch.uint8, pin_memory=True).numpy()
+    else:
+        store = np.empty(total, dtype=np.uint8)
     records = []
-    left = total
-    while left > 0:
-        n = min(RECORD_BP, left)
-        records.append(gen.random_codes(n, rng))
-        left -= n
+    pos = 0
+    while pos < total:
+        n = min(RECORD_BP, total - pos)
+        store[pos:pos + n] = gen.random_codes(n, rng)
+        records.append(store[pos:pos + n])
+        pos += n
     arng = np.random.default_rng(99)  # same assays on every rank
     assays = gen.make_assays(arng, records, n_assays, "taqman", lens=(20, 21, 25), amp=(80, 400), variants=2)
     fragments = []
@@ -254,7 +263,7 @@ def main():
 
     from thermonucleotideblast_b200 import Assay, Engine, search_options
 
-    records, fragments, assays, db_bases = build_workload(rank, args.mbp, args.assays)
+    records, fragments, assays, db_bases = build_workload(rank, args.mbp, args.assays, pinned=True)
     frag_bases = int(sum(len(f) for f in fragments))
     opts = search_options(min_primer_tm=MIN_PRIMER_TM, min_probe_tm=MIN_PROBE_TM, max_len=MAX_LEN)
     eng = Engine(device=local_rank)

@@ -136,8 +136,22 @@ struct tnt_engine {
 	DevBuf<uint32_t> nmask;
 	DevBuf<uint64_t> exc_pos;
 	DevBuf<uint8_t> exc_code;
-	uint64_t nwords = 0; // 32-base words in use
+	uint64_t next_base = 0;     // first free global base index
+	uint64_t packed_words = 0;  // db2 words written so far
 	uint64_t nexc = 0;
+	// open upload batch: a contiguous range of the global base space mirrored in a staging buffer
+	bool batch_open = false;
+	int batch_slot = 0;
+	uint64_t batch_base = 0;
+	uint32_t batch_used = 0;
+	// exception emission of the previous batch, issued once its count has arrived
+	bool emit_pending = false;
+	int emit_slot = 0;
+	uint32_t emit_n = 0, emit_blocks = 0;
+	uint64_t emit_base = 0;
+	cudaEvent_t count_ready[2]{};
+	DevBuf<uint32_t> block_count2[2];
+	uint64_t upload_launches = 0;
 	uint64_t total_bases = 0;
 	std::vector<Target> targets;
 	DevBuf<Target> d_targets;
@@ -148,9 +162,8 @@ struct tnt_engine {
 	uint8_t *h_stage[2] = {nullptr, nullptr};
 	uint8_t *d_stage[2] = {nullptr, nullptr};
 	cudaEvent_t stage_free[2]{};
-	DevBuf<uint32_t> block_count;
-	uint64_t *h_total = nullptr; // pinned
-	uint64_t *d_total = nullptr;
+	uint64_t *h_total = nullptr; // pinned [2]
+	uint64_t *d_total = nullptr; // [2]
 
 	std::vector<AssayHost> assays;
 
@@ -185,6 +198,7 @@ struct tnt_engine {
 			if (h_stage[i]) cudaFreeHost(h_stage[i]);
 			if (d_stage[i]) cudaFree(d_stage[i]);
 			if (stage_free[i]) cudaEventDestroy(stage_free[i]);
+			if (count_ready[i]) cudaEventDestroy(count_ready[i]);
 		}
 		if (h_total) cudaFreeHost(h_total);
 		if (h_heads) cudaFreeHost(h_heads);
@@ -197,12 +211,15 @@ struct tnt_engine {
 	{
 		DbView v;
 		v.db2 = db2.p; v.nmask = nmask.p; v.exc_pos = exc_pos.p; v.exc_code = exc_code.p; v.targets = d_targets.p;
+		v.nexc = nexc;
 		return v;
 	}
 
+	void finish_upload();
 	void sync_targets()
 	{
 		if (!targets_dirty) return;
+		finish_upload();
 		d_targets.upload(targets, stream);
 		tiles.clear();
 		for (uint32_t t = 0; t < targets.size(); ++t)
@@ -215,66 +232,138 @@ struct tnt_engine {
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// Target upload: pinned double buffer -> H2D -> pack kernels
+// Target upload.  Fragments are laid out back to back (64-base aligned) in a global base space;
+// a staging buffer mirrors a contiguous 32 MB range of it ("batch").  Every fragment is copied
+// into the device staging buffer asynchronously (straight from the caller's buffer when that is
+// pinned, through the pinned host mirror otherwise); a full batch is packed by one k_pack launch.
+// The sparse non-ACGT list needs the exception count of a batch: it is read back asynchronously
+// and the ordered emission pass of batch i is issued while batch i+1 is being filled.
 // ------------------------------------------------------------------------------------------
+void issue_pending_emit(tnt_engine *e)
+{
+	if (!e->emit_pending) return;
+	const int slot = e->emit_slot;
+	CUDA_OK(cudaEventSynchronize(e->count_ready[slot]));
+	const uint64_t nexc = e->h_total[slot];
+	if (nexc) {
+		e->exc_pos.reserve(e->nexc + nexc, e->nexc, e->stream);
+		e->exc_code.reserve(e->exc_pos.cap, e->nexc, e->stream);
+		k_emit_exceptions<<<e->emit_blocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], e->emit_n, e->block_count2[slot].p,
+			e->nexc, e->emit_base, e->exc_pos.p, e->exc_code.p);
+		CUDA_OK(cudaGetLastError());
+		e->upload_launches++;
+		e->nexc += nexc;
+	}
+	// the staging slot may be refilled once everything queued so far has run
+	CUDA_OK(cudaEventRecord(e->stage_free[slot], e->stream));
+	e->emit_pending = false;
+}
+
+void flush_batch(tnt_engine *e)
+{
+	if (!e->batch_open) return;
+	issue_pending_emit(e); // previous batch (other slot)
+	const int slot = e->batch_slot;
+	const uint32_t n = e->batch_used;
+	if (n) {
+		const uint64_t first_word = e->batch_base/32u;
+		const uint64_t need_words = first_word + ((uint64_t)n + 31u)/32u + 8;
+		if (need_words > e->db2.cap) {
+			e->db2.reserve(need_words, e->packed_words, e->stream);
+			e->nmask.reserve(e->db2.cap, e->packed_words, e->stream);
+		}
+		const uint32_t nblocks = (n + PACK_BASES_PER_BLOCK - 1)/PACK_BASES_PER_BLOCK;
+		e->block_count2[slot].reserve(nblocks, 0, e->stream);
+		k_pack<<<nblocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], n, e->db2.p, e->nmask.p, first_word, e->block_count2[slot].p);
+		k_scan_counts<<<1, 1024, 0, e->stream>>>(e->block_count2[slot].p, nblocks, e->d_total + slot);
+		CUDA_OK(cudaGetLastError());
+		e->upload_launches += 2;
+		CUDA_OK(cudaMemcpyAsync(e->h_total + slot, e->d_total + slot, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaEventRecord(e->count_ready[slot], e->stream));
+		e->packed_words = first_word + ((uint64_t)n + 31u)/32u;
+		e->emit_pending = true;
+		e->emit_slot = slot;
+		e->emit_n = n;
+		e->emit_blocks = nblocks;
+		e->emit_base = e->batch_base;
+	}
+	e->batch_open = false;
+	e->batch_used = 0;
+	e->batch_slot = slot ^ 1;
+}
+
+void open_batch(tnt_engine *e, uint64_t base)
+{
+	const int slot = e->batch_slot;
+	CUDA_OK(cudaEventSynchronize(e->stage_free[slot])); // previous user of this slot fully consumed
+	CUDA_OK(cudaMemsetAsync(e->d_stage[slot], 0, STAGE_BYTES, e->stream)); // alignment gaps pack as zero words
+	e->batch_open = true;
+	e->batch_base = base;
+	e->batch_used = 0;
+}
+
+bool is_pinned(const void *p)
+{
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return at.type == cudaMemoryTypeHost;
+}
+
 void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_out)
 {
 	CUDA_OK(cudaSetDevice(e->prm.device));
 	if (e->targets.size() >= (1u << 24)) throw std::runtime_error("tnt_engine_add_target: too many fragments (limit 2^24)");
 
 	Target tg{};
-	tg.base = e->nwords*32u;
-	if (tg.base & 63u) tg.base += 32u; // fragments start on 64-base boundaries
+	tg.base = (e->next_base + 63u) & ~(uint64_t)63u; // fragments start on 64-base boundaries
 	tg.len = len;
-	tg.exc_begin = e->nexc;
 
-	const uint64_t first_word = tg.base/32u;
-	const uint64_t words = ((uint64_t)len + 31u)/32u;
-	const uint64_t need_words = first_word + words + 4; // +pad: the scan reads one word ahead
-	if (need_words > e->db2.cap) {
-		e->db2.reserve(need_words, e->nwords, e->stream);
-		e->nmask.reserve(e->db2.cap, e->nwords, e->stream);
-	}
-	// words skipped by the alignment and the read-ahead pad must be zero
-	CUDA_OK(cudaMemsetAsync(e->db2.p + e->nwords, 0, (need_words - e->nwords)*sizeof(uint64_t), e->stream));
-	CUDA_OK(cudaMemsetAsync(e->nmask.p + e->nwords, 0, (need_words - e->nwords)*sizeof(uint32_t), e->stream));
-
-	uint32_t done = 0;
-	int slot = 0;
-	while (done < len) {
-		const uint32_t n = (uint32_t)std::min<uint64_t>(STAGE_BYTES, len - done);
-		CUDA_OK(cudaEventSynchronize(e->stage_free[slot]));
-		std::memcpy(e->h_stage[slot], codes + done, n);
-		CUDA_OK(cudaMemcpyAsync(e->d_stage[slot], e->h_stage[slot], n, cudaMemcpyHostToDevice, e->stream));
-
-		const uint32_t nblocks = (n + PACK_BASES_PER_BLOCK - 1)/PACK_BASES_PER_BLOCK;
-		e->block_count.reserve(nblocks, 0, e->stream);
-		k_pack<<<nblocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], n, e->db2.p, e->nmask.p,
-			first_word + done/32u, e->block_count.p);
-		k_scan_counts<<<1, 1024, 0, e->stream>>>(e->block_count.p, nblocks, e->d_total);
-		CUDA_OK(cudaMemcpyAsync(e->h_total, e->d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-		CUDA_OK(cudaStreamSynchronize(e->stream));
-		const uint64_t nexc = *e->h_total;
-		if (nexc) {
-			e->exc_pos.reserve(e->nexc + nexc, e->nexc, e->stream);
-			e->exc_code.reserve(e->exc_pos.cap, e->nexc, e->stream);
-			k_emit_exceptions<<<nblocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], n, e->block_count.p,
-				e->nexc, tg.base + done, e->exc_pos.p, e->exc_code.p);
-			e->nexc += nexc;
+	const bool pinned = len && is_pinned(codes);
+	uint64_t pos = tg.base;
+	const uint8_t *src = codes;
+	uint32_t rem = len;
+	while (rem) {
+		if (e->batch_open && pos >= e->batch_base + STAGE_BYTES) flush_batch(e);
+		if (!e->batch_open) open_batch(e, pos);
+		const int slot = e->batch_slot;
+		const uint32_t off = (uint32_t)(pos - e->batch_base);
+		const uint32_t n = (uint32_t)std::min<uint64_t>(rem, STAGE_BYTES - off);
+		if (pinned) CUDA_OK(cudaMemcpyAsync(e->d_stage[slot] + off, src, n, cudaMemcpyHostToDevice, e->stream));
+		else {
+			std::memcpy(e->h_stage[slot] + off, src, n);
+			CUDA_OK(cudaMemcpyAsync(e->d_stage[slot] + off, e->h_stage[slot] + off, n, cudaMemcpyHostToDevice, e->stream));
 		}
-		CUDA_OK(cudaEventRecord(e->stage_free[slot], e->stream));
-		CUDA_OK(cudaGetLastError());
-		done += n;
-		slot ^= 1;
+		e->batch_used = off + n;
+		pos += n;
+		src += n;
+		rem -= n;
+		if (e->batch_used == STAGE_BYTES) flush_batch(e);
 	}
-	tg.exc_end = e->nexc;
-	e->nwords = first_word + words;
+	e->next_base = tg.base + len;
 	e->total_bases += len;
-	if (e->exc_pos.cap == 0) { e->exc_pos.reserve(16, 0, e->stream); e->exc_code.reserve(16, 0, e->stream); }
 	e->targets.push_back(tg);
 	e->targets_dirty = true;
 	if (id_out) *id_out = (uint32_t)e->targets.size() - 1;
 }
+
+} // namespace
+
+void tnt_engine::finish_upload()
+{
+	flush_batch(this);
+	issue_pending_emit(this);
+	// read-ahead pad of the scan / window loads
+	const uint64_t need = packed_words + 8;
+	if (need > db2.cap) {
+		db2.reserve(need, packed_words, stream);
+		nmask.reserve(db2.cap, packed_words, stream);
+	}
+	CUDA_OK(cudaMemsetAsync(db2.p + packed_words, 0, 8*sizeof(uint64_t), stream));
+	CUDA_OK(cudaMemsetAsync(nmask.p + packed_words, 0, 8*sizeof(uint32_t), stream));
+	if (exc_pos.cap == 0) { exc_pos.reserve(16, 0, stream); exc_code.reserve(16, 0, stream); }
+}
+
+namespace {
 
 // ------------------------------------------------------------------------------------------
 // Oligo strands
@@ -446,7 +535,8 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 {
 	const size_t nos = set.os.size();
 	std::vector<uint32_t> counts(nos);
-	CUDA_OK(cudaMemcpyAsync(counts.data(), e->d_cand_count.p, nos*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaMemcpy2DAsync(counts.data(), sizeof(uint32_t), e->d_cand_count.p, COUNT_STRIDE*sizeof(uint32_t),
+		sizeof(uint32_t), nos, cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	if (counts_out) *counts_out = counts;
 	uint64_t total = 0;
@@ -572,7 +662,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 		if (max_tiles < (double)tiles_per_chunk) tiles_per_chunk = (uint32_t)std::max(1.0, max_tiles);
 	}
 
-	e->d_cand_count.reserve(nos, 0, e->stream);
+	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
 	const size_t smem_scan = ((set.nkeys + 31)/32)*sizeof(uint32_t);
 	CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
 
@@ -584,7 +674,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 			uint32_t cap = (uint32_t)std::min<double>(4.0e9, 2.0*per_base*SCAN_TILE*ntiles + 2048.0);
 			cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(cap_budget, 4096)*(ntiles == 1 ? 64 : 1));
 			e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
-			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*sizeof(uint32_t), e->stream));
+			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 			ScanArgs a = scan_args(e, set, cap);
 			a.tile_begin = t0;
 			a.tile_end = t1;
@@ -618,7 +708,7 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 {
 	if (set.os.empty() || regions.empty()) return;
 	const size_t nos = set.os.size();
-	e->d_cand_count.reserve(nos, 0, e->stream);
+	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
 	e->d_regions.upload(regions, e->stream);
 	// Size the buckets for the busiest assay: expected seeds = positions x words / 4^W; start with
 	// generous slack and double on overflow (repeat-rich fragments can exceed any estimate).
@@ -630,7 +720,7 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
 	for (;;) {
 		e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
-		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*sizeof(uint32_t), e->stream));
+		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 		RegionScanArgs ra{};
 		ra.s = scan_args(e, set, cap);
 		ra.regions = e->d_regions.p;
@@ -946,9 +1036,10 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 		CUDA_OK(cudaMallocHost(&e->h_stage[i], STAGE_BYTES));
 		CUDA_OK(cudaMalloc(&e->d_stage[i], STAGE_BYTES));
 		CUDA_OK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
+		CUDA_OK(cudaEventCreateWithFlags(&e->count_ready[i], cudaEventDisableTiming));
 	}
-	CUDA_OK(cudaMallocHost(&e->h_total, sizeof(uint64_t)));
-	CUDA_OK(cudaMalloc(&e->d_total, sizeof(uint64_t)));
+	CUDA_OK(cudaMallocHost(&e->h_total, 2*sizeof(uint64_t)));
+	CUDA_OK(cudaMalloc(&e->d_total, 2*sizeof(uint64_t)));
 	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
 	e->d_thermo.reserve(1, 0, e->stream);
 	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
@@ -990,8 +1081,12 @@ int tnt_engine_clear_targets(tnt_engine *e)
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	e->targets.clear();
 	e->tiles.clear();
-	e->nwords = 0;
+	e->next_base = 0;
+	e->packed_words = 0;
 	e->nexc = 0;
+	e->batch_open = false;
+	e->batch_used = 0;
+	e->emit_pending = false;
 	e->total_bases = 0;
 	e->targets_dirty = true;
 	e->hits.clear();
@@ -1082,7 +1177,7 @@ long tnt_engine_seeds(tnt_engine *e, uint32_t target_id, const char *oligo, int3
 		std::vector<Candidate> cands;
 		if (t1 > t0 && set.os[0].nwords > 0) {
 			uint32_t cap = (uint32_t)std::min<uint64_t>((uint64_t)e->targets[target_id].len*2 + 64, 1u << 28);
-			e->d_cand_count.reserve(1, 0, e->stream);
+			e->d_cand_count.reserve(COUNT_STRIDE, 0, e->stream);
 			e->d_cand.reserve(cap, 0, e->stream);
 			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, sizeof(uint32_t), e->stream));
 			ScanArgs a = scan_args(e, set, cap);
@@ -1139,7 +1234,7 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
 	}
 	const uint32_t cap = (uint32_t)std::max<long>(n, 1);
 	e->d_cand.upload(cands, e->stream);
-	e->d_cand_count.reserve(1, 0, e->stream);
+	e->d_cand_count.reserve(COUNT_STRIDE, 0, e->stream);
 	const uint32_t cnt = (uint32_t)n;
 	CUDA_OK(cudaMemcpyAsync(e->d_cand_count.p, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, e->stream));
 	e->n_bound = 0;

@@ -22,6 +22,7 @@ struct DbView {
 	const uint64_t *exc_pos;
 	const uint8_t *exc_code;
 	const Target *targets;
+	uint64_t nexc;
 };
 
 constexpr int PACK_THREADS = 256;
@@ -154,7 +155,8 @@ __device__ __forceinline__ uint32_t kmer_at(const uint64_t *__restrict__ db2, ui
 
 __device__ inline int exception_code(const DbView &db, const Target &tg, uint64_t g)
 {
-	uint64_t lo = tg.exc_begin, hi = tg.exc_end;
+	(void)tg;
+	uint64_t lo = 0, hi = db.nexc; // one sorted list for the whole database
 	while (lo < hi) {
 		const uint64_t mid = (lo + hi) >> 1;
 		const uint64_t v = __ldg(db.exc_pos + mid);
@@ -202,6 +204,7 @@ struct WordTable {
 
 struct ScanTile { uint32_t target; uint32_t start; };
 
+constexpr int COUNT_STRIDE = 32; // bucket counters live in separate L2 lines (same-line atomics serialise)
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_THREADS*32;
 
@@ -214,7 +217,7 @@ struct ScanArgs {
 	uint32_t tile_begin, tile_end;
 	int W;
 	Candidate *cand;           // [nos][cap]
-	uint32_t *cand_count;      // [nos]
+	uint32_t *cand_count;      // [nos][COUNT_STRIDE]: one 128-byte line per bucket counter
 	uint32_t cap;
 };
 
@@ -235,7 +238,7 @@ __device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ d
 
 __device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t os, uint32_t target, uint32_t k, uint32_t t)
 {
-	const uint32_t slot = atomicAdd(a.cand_count + os, 1u);
+	const uint32_t slot = atomicAdd(a.cand_count + (size_t)os*COUNT_STRIDE, 1u);
 	if (slot < a.cap) {
 		Candidate c;
 		c.target_k = target | (k << 24);
@@ -244,28 +247,70 @@ __device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t os, u
 	}
 }
 
+// Two phases per 8192-base tile so that warps stay converged: (1) every thread tests its 32
+// positions against the k-mer bitmap in shared memory and the block compacts the hit positions
+// into a shared queue; (2) the queue is processed one hit per thread (CSR walk, diagonal test,
+// bucket append).
 __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 {
 	extern __shared__ uint32_t s_present[];
+	__shared__ uint16_t s_queue[SCAN_TILE];
+	__shared__ uint32_t s_warp[SCAN_THREADS/32];
+	__shared__ uint32_t s_total;
+
 	for (uint32_t i = threadIdx.x; i < (a.wt.nkeys + 31)/32; i += SCAN_THREADS) s_present[i] = a.wt.present[i];
 	__syncthreads();
 
 	const uint32_t kmask = a.wt.nkeys - 1;
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
 	for (uint32_t tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
 		const ScanTile tl = a.tiles[tile];
 		const Target tg = a.db.targets[tl.target];
 		const uint32_t p0 = tl.start + threadIdx.x*32u;
-		if (p0 >= tg.len) continue;
-		const uint64_t wi = (tg.base + p0) >> 5;
-		const uint64_t lo = __ldg(a.db.db2 + wi);
-		const uint64_t hi = __ldg(a.db.db2 + wi + 1); // the allocation is padded by one word
-#pragma unroll 4
-		for (uint32_t b = 0; b < 32; ++b) {
-			const uint32_t p = p0 + b;
-			if (p + (uint32_t)a.W > tg.len) break;
-			const uint64_t x = b ? ((lo >> (2*b)) | (hi << (64 - 2*b))) : lo;
-			const uint32_t key = (uint32_t)x & kmask;
-			if (!((s_present[key >> 5] >> (key & 31u)) & 1u)) continue;
+
+		// phase 1: 32 positions per thread -> bit mask of positions whose W-mer is in the table
+		uint32_t hitmask = 0;
+		if (p0 < tg.len) {
+			const uint64_t wi = (tg.base + p0) >> 5;
+			const uint64_t lo = __ldg(a.db.db2 + wi);
+			const uint64_t hi = __ldg(a.db.db2 + wi + 1); // the allocation is padded
+			const uint32_t nvalid = (p0 + (uint32_t)a.W <= tg.len) ? min(32u, tg.len - (uint32_t)a.W + 1u - p0) : 0u;
+#pragma unroll
+			for (uint32_t b = 0; b < 32; ++b) {
+				const uint64_t x = b ? ((lo >> (2*b)) | (hi << (64 - 2*b))) : lo;
+				const uint32_t key = (uint32_t)x & kmask;
+				hitmask |= ((s_present[key >> 5] >> (key & 31u)) & 1u) << b;
+			}
+			if (nvalid < 32) hitmask &= (nvalid ? ((1u << nvalid) - 1u) : 0u);
+		}
+
+		// block-wide exclusive scan of the hit counts
+		const uint32_t cnt = __popc(hitmask);
+		uint32_t incl = cnt;
+		for (int off = 1; off < 32; off <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= (unsigned)off) incl += v;
+		}
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		uint32_t base = 0;
+		for (unsigned w = 0; w < warp; ++w) base += s_warp[w];
+		if (threadIdx.x == SCAN_THREADS - 1) s_total = base + incl;
+		uint32_t slot = base + incl - cnt;
+		uint32_t m = hitmask;
+		while (m) {
+			const uint32_t b = __ffs(m) - 1;
+			m &= m - 1;
+			s_queue[slot++] = (uint16_t)(threadIdx.x*32u + b);
+		}
+		__syncthreads();
+
+		// phase 2: one queued position per thread
+		const uint32_t total = s_total;
+		for (uint32_t q = threadIdx.x; q < total; q += SCAN_THREADS) {
+			const uint32_t p = tl.start + s_queue[q];
+			const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
 			const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
 			for (uint32_t e = e0; e < e1; ++e) {
 				const uint32_t ent = __ldg(a.wt.entry + e);
@@ -274,6 +319,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 					emit_candidate(a, os, tl.target, k, p);
 			}
 		}
+		__syncthreads();
 	}
 }
 
