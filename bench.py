@@ -328,8 +328,11 @@ def main():
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    upload_s = 0.0
     for _ in range(e2e_steps):
+        tu = time.perf_counter()
         upload()
+        upload_s += time.perf_counter() - tu
         eng.search_raw(opts)
         hits = eng.hits()
         d2h = len(hits) * 172 + int(eng.stats().bound_sites) * 344
@@ -368,7 +371,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frag_bases, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps},
+                "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
+                "upload_call_ms_per_step": upload_s / e2e_steps * 1e3},
         "roofline": {"bound": "alu-int32", "achieved": alu_achieved, "peak": alu_peak, "unit": "TOP/s",
                      "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": None,
                      "kernel": "k_align (NucCruc DP + traceback + evaluation)",

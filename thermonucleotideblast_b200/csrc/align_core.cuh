@@ -176,6 +176,7 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 // (i, j), 1 <= i <= Lq, 1 <= j <= Lt, in the layout of the TW_* constants above.
 template <int NT>
 struct RowMajorTrace {
+	static constexpr bool kHasGapStates = true;
 	const uint16_t *trace;
 	int Lt;
 	__device__ __forceinline__ unsigned get(int i, int j) const { return trace[(size_t)((i - 1)*Lt + (j - 1))*NT]; }
@@ -250,6 +251,7 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 				--last_j;
 			}
 		}
+		else if (!TV::kHasGapStates && (local == T_LEFT || local == T_UP)) { flags |= F_NEEDGENERIC; return; }
 		else if (local == T_LEFT) { // a gap goes into the query
 			if (last_j < 1) valid = false;
 			else {
@@ -481,7 +483,7 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 			a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
 			a.dH = a.dS = a.tm = 0.0f;
 			nc_trace_back(sh, tgt, Lt, tv, cell, stack, nstack, zero_count, a, flags);
-			if (flags & (F_OOB | F_STACK)) return;
+			if (flags & (F_OOB | F_STACK | F_NEEDGENERIC)) return;
 
 			// frayed ends: drop columns until both ends are Watson-Crick (:1022-1054)
 			while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.e - 1]*NB + a.t[a.e - 1]]]) {
@@ -612,13 +614,160 @@ constexpr int ROW_P1 = 0, ROW_P2 = 20, ROW_P4 = 40, ROW_P3 = 60, ROW_P6 = 64, RO
 constexpr int32_t ROW_PAD_PENALTY = 1 << 28;
 constexpr int MAX_MAXCELLS = 64;
 
+// Trace byte of the fast fill (one per cell, four rows per 32-bit word, first row in the top byte):
+//   bit7 d1!=M   bit4 d2!=M   bit3 d3!=M   bit2 M<0   bit1 M>0   bit0 M below the running maximum
+// (bits 6,5 are filler).  The gap states keep no trace: an optimal path that wants to enter one is
+// handed to the generic kernel (F_NEEDGENERIC) -- gaps cost >= 2 kcal/mol to open, so this is rare.
 struct FastDp {
+	unsigned runkey;   // (max(M,0) << 12) | (4095 - sweep index of its first occurrence)
+	unsigned lastkey;  // (max(M,0) << 12) | sweep index of its last occurrence
+};
+
+template <int LQ, int NT>
+struct ColMajorTrace {
+	static constexpr bool kHasGapStates = false;
+	const uint32_t *trace32;
+	__device__ __forceinline__ unsigned raw(int i, int j) const
+	{
+		const uint32_t w = trace32[(size_t)((j - 1)*(LQ/4) + ((i - 1) >> 2))*NT];
+		return (w >> (8*(3 - ((i - 1) & 3)))) & 0xffu;
+	}
+	__device__ __forceinline__ unsigned get(int i, int j) const
+	{
+		const unsigned r = raw(i, j);
+		unsigned w = 0;
+		if (!(r & 0x80u)) w |= T_DIAG;
+		if (!(r & 0x10u)) w |= T_LEFT;
+		if (!(r & 0x08u)) w |= T_UP;
+		if (r & 0x04u) w |= TW_M_NEG;
+		else if (!(r & 0x02u)) w |= TW_M_ZERO;
+		if (!(r & 0x01u)) w |= TW_CAND;
+		return w;
+	}
+};
+
+// target base j (0-based, NucCruc orientation) from the 2-bit packed window
+__device__ __forceinline__ int packed_base(uint64_t lo, uint64_t hi, int j)
+{
+	return (int)(((j < 32) ? (lo >> (2*j)) : (hi >> (2*(j - 32)))) & 3u);
+}
+
+template <int LQ, int NT>
+__device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
+	uint64_t tlo, uint64_t thi, int Lt, uint32_t *__restrict__ trace32)
+{
+	static_assert(LQ % 4 == 0, "four rows share a trace word");
+	int cM[LQ], cIq[LQ], cIt[LQ];
+#pragma unroll
+	for (int r = 0; r < LQ; ++r) { cM[r] = 0; cIq[r] = 0; cIt[r] = 0; }
+
+	unsigned runkey = 0;  // nothing positive seen yet
+	unsigned lastkey = 0;
+	int runmax = 0;
+	int pt = 4;           // GAP in front of the first column
+	for (int j = 1; j <= Lt; ++j) {
+		const int tb = packed_base(tlo, thi, j - 1);
+		const int td = pt*4 + tb;
+		const int32_t *__restrict__ ptd = tab + td;
+		const int32_t *__restrict__ ptb = tab + tb;
+		const int p5 = p5tab[td];
+		uint32_t *__restrict__ col = trace32 + (size_t)(j - 1)*(LQ/4)*NT;
+		const unsigned colkey = 4095u - (unsigned)((j - 1)*LQ); // minus r: sweep index of the cell
+
+		int dM = 0, dIq = 0, dIt = 0; // (i-1, j-1)
+		int uM = 0, uIt = 0;          // (i-1, j)
+		unsigned acc = 0;
+#pragma unroll
+		for (int r = 0; r < LQ; ++r) {
+			const int oM = cM[r], oIq = cIq[r], oIt = cIt[r]; // (i, j-1)
+
+			const int d1 = dM - ptd[r*ROW_WORDS + ROW_P1];
+			const int d2 = dIq - ptd[r*ROW_WORDS + ROW_P2];
+			const int d3 = dIt - ptb[r*ROW_WORDS + ROW_P3];
+			const int M = max(max(d1, d2), d3);
+			const int Iq = max(oM - ptd[r*ROW_WORDS + ROW_P4], oIq - p5);
+			const int It = max(uM - ptb[r*ROW_WORDS + ROW_P6], uIt - tab[r*ROW_WORDS + ROW_P7]);
+			const int mM = max(M, 0);
+
+			// running maximum with the position of its first occurrence folded into the low bits
+			// (the host only sends oligos here whose best possible score stays below 2^20)
+			const unsigned below = (unsigned)(mM - runmax);  // sign set <=> max(M,0) < running maximum
+			runmax = max(runmax, mM);
+			runkey = max(runkey, (unsigned)mM*4096u + (colkey - (unsigned)r));
+			lastkey = max(lastkey, (unsigned)mM*4096u + (4095u - colkey + (unsigned)r));
+
+			acc = __funnelshift_l((unsigned)(d1 - M), acc, 3); // sign + 2 filler bits
+			acc = __funnelshift_l((unsigned)(d2 - M), acc, 1);
+			acc = __funnelshift_l((unsigned)(d3 - M), acc, 1);
+			acc = __funnelshift_l((unsigned)M, acc, 1);
+			acc = __funnelshift_l((unsigned)(-M), acc, 1);
+			acc = __funnelshift_l(below, acc, 1);
+			if ((r & 3) == 3) col[(r >> 2)*NT] = acc;
+
+			dM = oM; dIq = oIq; dIt = oIt;
+			cM[r] = mM;
+			cIq[r] = max(Iq, 0);
+			cIt[r] = max(It, 0);
+			uM = mM;
+			uIt = cIt[r];
+		}
+		pt = tb;
+	}
+	FastDp res;
+	res.runkey = runkey;
+	res.lastkey = lastkey;
+	return res;
+}
+
+// Maximal cells in the reference's (row-major) order from a fast fill.  Returns -1 when the
+// generic kernel has to take over (no positive score anywhere: the reference's ">= -1" rule then
+// decides, which the fast trace does not record).
+template <int LQ, int NT>
+__device__ inline int collect_max_cells_fast(const ColMajorTrace<LQ, NT> &tv, const FastDp &dp, int Lq, int Lt,
+	uint16_t *cells, unsigned &flags)
+{
+	if ((dp.runkey >> 12) == 0) return -1;
+	const int first = 4095 - (int)(dp.runkey & 4095u); // sweep index = (j-1)*LQ + (i-1)
+	const int fj = first/LQ + 1, fi = first%LQ + 1;
+	int n = 0;
+	cells[n++] = (uint16_t)((fi - 1)*Lt + (fj - 1));
+	// later cells that tie with the maximum carry a clear "below" bit; scan word-wise
+	(void)Lt;
+	const int last = (int)(dp.lastkey & 4095u);
+	if (last == first) return n; // a single maximal cell: the common case
+	for (int w = first/4; w <= last/4; ++w) {
+		uint32_t word = tv.trace32[(size_t)w*NT];
+		uint32_t cand = ~word & 0x01010101u;
+		while (cand) {
+			const int bit = 31 - __clz(cand);
+			cand &= ~(1u << bit);
+			const int rr = 3 - (bit >> 3);
+			const int idx = w*4 + rr;
+			if (idx <= first) continue;
+			const int j = idx/LQ + 1, i = idx%LQ + 1;
+			if (i > Lq) continue;
+			if (n == MAX_MAXCELLS) { flags |= F_TRUNC; return n; }
+			const uint16_t key = (uint16_t)((i - 1)*Lt + (j - 1));
+			int k = n++;
+			while (k > 0 && cells[k - 1] > key) { cells[k] = cells[k - 1]; --k; }
+			cells[k] = key;
+		}
+	}
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Full-trace variant of the fast fill: same sweep, 12-bit trace words that also record the gap
+// states (two rows per 32-bit store).  Used for the few candidates whose optimal path enters a
+// gap state, which the 8-bit trace above cannot follow.
+// ------------------------------------------------------------------------------------------
+struct FastDpFull {
 	int runmax, last_i, last_j, nmax;
 };
 
 // packed trace bits of the fast fill, most significant first (order of insertion)
 //   11 d1!=M  10 d2!=M  9 d3!=M  8 qi!=Iq  7 qe!=Iq  6 ti!=It  5 te!=It  4 M<0  3 M>0  2 Iq<0  1 It<0  0 M<runmax
-__device__ __forceinline__ unsigned decode_fast_trace(unsigned raw)
+__device__ __forceinline__ unsigned decode_full_trace(unsigned raw)
 {
 	unsigned w = 0;
 	if (!(raw & (1u << 11))) w |= T_DIAG;
@@ -637,24 +786,19 @@ __device__ __forceinline__ unsigned decode_fast_trace(unsigned raw)
 }
 
 template <int LQ, int NT>
-struct ColMajorTrace {
+struct ColMajorTraceFull {
+	static constexpr bool kHasGapStates = true;
 	const uint32_t *trace32;
 	__device__ __forceinline__ unsigned raw(int i, int j) const
 	{
 		const uint32_t w = trace32[(size_t)((j - 1)*(LQ/2) + ((i - 1) >> 1))*NT];
 		return ((i - 1) & 1) ? (w >> 16) : (w & 0xffffu);
 	}
-	__device__ __forceinline__ unsigned get(int i, int j) const { return decode_fast_trace(raw(i, j)); }
+	__device__ __forceinline__ unsigned get(int i, int j) const { return decode_full_trace(raw(i, j)); }
 };
 
-// target base j (0-based, NucCruc orientation) from the 2-bit packed window
-__device__ __forceinline__ int packed_base(uint64_t lo, uint64_t hi, int j)
-{
-	return (int)(((j < 32) ? (lo >> (2*j)) : (hi >> (2*(j - 32)))) & 3u);
-}
-
 template <int LQ, int NT>
-__device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
+__device__ __forceinline__ FastDpFull nc_fill_fast_full(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
 	uint64_t tlo, uint64_t thi, int Lt, uint32_t *__restrict__ trace32)
 {
 	static_assert(LQ % 2 == 0, "two rows share a trace store");
@@ -662,7 +806,7 @@ __device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, 
 #pragma unroll
 	for (int r = 0; r < LQ; ++r) { cM[r] = 0; cIq[r] = 0; cIt[r] = 0; }
 
-	FastDp res;
+	FastDpFull res;
 	res.runmax = -1;
 	res.last_i = res.last_j = 0;
 	res.nmax = 0;
@@ -734,7 +878,7 @@ __device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, 
 // matrix column by column, so the cells tied with the maximum are gathered from the sweep
 // position of the last strict raise onwards and then ordered by (row, column).
 template <int LQ, int NT>
-__device__ inline int collect_max_cells_fast(const ColMajorTrace<LQ, NT> &tv, const FastDp &dp, int Lq, int Lt,
+__device__ inline int collect_max_cells_full(const ColMajorTraceFull<LQ, NT> &tv, const FastDpFull &dp, int Lq, int Lt,
 	uint16_t *cells, unsigned &flags)
 {
 	if (dp.nmax == 0) return 0;

@@ -104,6 +104,7 @@ struct OsSet {
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
 	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
 	std::vector<uint32_t> row_tab_off;
+	std::vector<uint8_t> fast_ok;       // best possible DP score fits the fast kernel's packed maximum
 	DevBuf<int32_t> d_row_tab;
 	DevBuf<uint32_t> d_row_tab_off;
 	uint32_t nkeys = 0;
@@ -181,7 +182,7 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_out_count;
 	DevBuf<unsigned long long> d_cells;
 	DevBuf<Region> d_regions;
-	DevBuf<SlowItem> d_slow;
+	DevBuf<SlowItem> d_slow, d_retry;
 	DevBuf<Candidate> d_slow_cand;
 	DevBuf<uint32_t> d_slot_map;
 	DevBuf<int32_t> d_p5;
@@ -432,7 +433,19 @@ void finish_set(tnt_engine *e, OsSet &set)
 	size_t rows = 0;
 	for (size_t s = 0; s < nos; ++s) { set.row_tab_off[s] = (uint32_t)(rows*ROW_WORDS); rows += (size_t)set.os[s].len; }
 	set.row_tab.assign(std::max<size_t>(rows*ROW_WORDS, 1), 0);
-	for (size_t s = 0; s < nos; ++s) build_row_tables(e->h_thermo, set.os[s], set.row_tab.data() + set.row_tab_off[s]);
+	set.fast_ok.assign(nos, 1);
+	for (size_t s = 0; s < nos; ++s) {
+		int32_t *rows_s = set.row_tab.data() + set.row_tab_off[s];
+		build_row_tables(e->h_thermo, set.os[s], rows_s);
+		// upper bound of any cell: every row contributes at most its most favourable M-from-M term
+		int64_t bound = 0;
+		for (int r = 0; r < set.os[s].len; ++r) {
+			int32_t best = 0;
+			for (int td = 0; td < 20; ++td) best = std::max(best, -rows_s[r*ROW_WORDS + ROW_P1 + td]);
+			bound += best;
+		}
+		if (bound >= (1 << 20)) set.fast_ok[s] = 0;
+	}
 	set.d_row_tab.upload(set.row_tab, e->stream);
 	set.d_row_tab_off.upload(set.row_tab_off, e->stream);
 	set.d_os.upload(set.os, e->stream);
@@ -464,28 +477,36 @@ ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
 const int kFastClasses[] = {20, 24, 28, 32, 40, 56};
 
 template <int LQ>
-void launch_fast(const AlignArgs &a, uint32_t grid, cudaStream_t st)
+void launch_fast(const AlignArgs &a, uint32_t grid, bool full, cudaStream_t st)
 {
-	k_align_fast<LQ><<<grid, ALIGN_THREADS, 0, st>>>(a);
+	if (full) k_align_fast<LQ, true><<<grid, ALIGN_THREADS, 0, st>>>(a);
+	else k_align_fast<LQ, false><<<grid, ALIGN_THREADS, 0, st>>>(a);
 }
 
-int fast_blocks_per_sm(int lq)
+template <int LQ>
+int fast_occupancy(bool full)
 {
 	int n = 1;
-	switch (lq) {
-	case 20: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<20>, ALIGN_THREADS, 0); break;
-	case 24: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<24>, ALIGN_THREADS, 0); break;
-	case 28: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<28>, ALIGN_THREADS, 0); break;
-	case 32: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<32>, ALIGN_THREADS, 0); break;
-	case 40: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<40>, ALIGN_THREADS, 0); break;
-	default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<56>, ALIGN_THREADS, 0); break;
-	}
+	if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, true>, ALIGN_THREADS, 0);
+	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, 0);
 	return std::max(n, 1);
+}
+
+int fast_blocks_per_sm(int lq, bool full)
+{
+	switch (lq) {
+	case 20: return fast_occupancy<20>(full);
+	case 24: return fast_occupancy<24>(full);
+	case 28: return fast_occupancy<28>(full);
+	case 32: return fast_occupancy<32>(full);
+	case 40: return fast_occupancy<40>(full);
+	default: return fast_occupancy<56>(full);
+	}
 }
 
 // Run one alignment kernel (fast class `lq`, or the generic kernel when lq == 0) over `units`,
 // appending / writing results into e->d_out.  Returns the device time.
-float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector<AlignUnit> &units, int lq, int max_len)
+float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector<AlignUnit> &units, int lq, int max_len, bool full = false)
 {
 	e->d_units.upload(units, e->stream);
 	a.units = e->d_units.p;
@@ -503,20 +524,21 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector
 		a.trace_cells = (uint32_t)max_len*(uint32_t)max_lt;
 	}
 	else {
-		grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*fast_blocks_per_sm(lq));
+		grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*fast_blocks_per_sm(lq, full));
 		a.trace_cells = (uint32_t)lq*(uint32_t)(lq + 2*NUM_FLANK);
 	}
-	e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS + 64, 0, e->stream);
+	// d_trace counts 16-bit units; the fast kernel stores one byte per cell
+	e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS/((lq == 0 || full) ? 1 : 2) + 64, 0, e->stream);
 	a.trace = e->d_trace.p;
 	CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
 	switch (lq) {
 	case 0: k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a); break;
-	case 20: launch_fast<20>(a, grid, e->stream); break;
-	case 24: launch_fast<24>(a, grid, e->stream); break;
-	case 28: launch_fast<28>(a, grid, e->stream); break;
-	case 32: launch_fast<32>(a, grid, e->stream); break;
-	case 40: launch_fast<40>(a, grid, e->stream); break;
-	default: launch_fast<56>(a, grid, e->stream); break;
+	case 20: launch_fast<20>(a, grid, full, e->stream); break;
+	case 24: launch_fast<24>(a, grid, full, e->stream); break;
+	case 28: launch_fast<28>(a, grid, full, e->stream); break;
+	case 32: launch_fast<32>(a, grid, full, e->stream); break;
+	case 40: launch_fast<40>(a, grid, full, e->stream); break;
+	default: launch_fast<56>(a, grid, full, e->stream); break;
 	}
 	CUDA_OK(cudaGetLastError());
 	CUDA_OK(cudaEventRecord(e->ev[3], e->stream));
@@ -551,10 +573,11 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 	HostTimer t_ab("  align_buckets");
 	// units per fast class
 	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));
-	std::vector<std::vector<AlignUnit>> by_class(nclass);
+	std::vector<std::vector<AlignUnit>> by_class(nclass + 1); // [nclass] = generic kernel
 	for (size_t s = 0; s < nos; ++s) {
 		int c = 0;
 		while (c < nclass - 1 && kFastClasses[c] < set.os[s].len) ++c;
+		if (!set.fast_ok[s]) c = nclass;
 		for (uint32_t b = 0; b < counts[s]; b += ALIGN_THREADS)
 			by_class[c].push_back(AlignUnit{(uint32_t)s, b, std::min<uint32_t>(ALIGN_THREADS, counts[s] - b)});
 	}
@@ -571,8 +594,9 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		e->d_bound.reserve(out_cap, base_count, e->stream);
 		out_cap = e->d_bound.cap;
 		e->d_slow.reserve(slow_cap, 0, e->stream);
+		e->d_retry.reserve(slow_cap, 0, e->stream);
 		{
-			const uint32_t init[2] = {base_count, 0};
+			const uint32_t init[3] = {base_count, 0, 0};
 			CUDA_OK(cudaMemcpyAsync(e->d_out_count.p, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
 		}
@@ -595,39 +619,69 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		a.p5_tab = e->d_p5.p;
 		a.slow = e->d_slow.p;
 		a.slow_count = e->d_out_count.p + 1;
+		a.retry = e->d_retry.p;
+		a.retry_count = e->d_out_count.p + 2;
 		a.slow_cap = (uint32_t)slow_cap;
 
 		float ms = 0;
 		for (int c = 0; c < nclass; ++c)
 			if (!by_class[c].empty()) ms += run_align_kernel(e, set, a, by_class[c], kFastClasses[c], set.max_len);
+		if (!by_class[nclass].empty()) ms += run_align_kernel(e, set, a, by_class[nclass], 0, set.max_len);
 
-		uint32_t cnt[2] = {0, 0};
+		uint32_t cnt[3] = {0, 0, 0};
 		CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
 		CUDA_OK(cudaStreamSynchronize(e->stream));
-		if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1] + cnt[1]/4; continue; }
+		if (cnt[1] > slow_cap || cnt[2] > slow_cap) { slow_cap = (size_t)std::max(cnt[1], cnt[2])*5/4; continue; }
+		if (HostTimer::enabled())
+			fprintf(stderr, "[tnt]   candidates %llu, full-trace retry %u, generic %u, fast ms %.3f\n", (unsigned long long)total, cnt[2], cnt[1], ms);
 
-		if (cnt[1]) {
-			// windows with IUPAC / inosine / N target bases: generic kernel
-			std::vector<SlowItem> items(cnt[1]);
-			CUDA_OK(cudaMemcpyAsync(items.data(), e->d_slow.p, items.size()*sizeof(SlowItem), cudaMemcpyDeviceToHost, e->stream));
+		// Hand-over lists -> compact candidate arrays grouped by oligo strand (counting sort)
+		auto regroup = [&](const DevBuf<SlowItem> &list, uint32_t n, std::vector<std::vector<AlignUnit>> *per_class,
+			std::vector<AlignUnit> *flat) {
+			std::vector<SlowItem> items(n);
+			CUDA_OK(cudaMemcpyAsync(items.data(), list.p, (size_t)n*sizeof(SlowItem), cudaMemcpyDeviceToHost, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
-			std::stable_sort(items.begin(), items.end(), [](const SlowItem &x, const SlowItem &y) { return x.os < y.os; });
-			std::vector<Candidate> sc(items.size());
-			std::vector<uint32_t> slots(items.size());
-			std::vector<AlignUnit> units;
-			for (size_t i = 0; i < items.size();) {
-				size_t j = i;
-				while (j < items.size() && items[j].os == items[i].os) ++j;
-				for (size_t b = i; b < j; b += ALIGN_THREADS)
-					units.push_back(AlignUnit{items[i].os, (uint32_t)b, (uint32_t)std::min<size_t>(ALIGN_THREADS, j - b)});
-				i = j;
+			std::vector<uint32_t> start(nos + 1, 0);
+			for (const SlowItem &it : items) start[it.os + 1]++;
+			for (size_t s2 = 0; s2 < nos; ++s2) start[s2 + 1] += start[s2];
+			std::vector<Candidate> sc(n);
+			std::vector<uint32_t> slots(n);
+			std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+			for (const SlowItem &it : items) { const uint32_t d = fill[it.os]++; sc[d] = it.c; slots[d] = it.slot; }
+			for (size_t s2 = 0; s2 < nos; ++s2) {
+				int c = 0;
+				while (c < nclass - 1 && kFastClasses[c] < set.os[s2].len) ++c;
+				for (uint32_t b2 = start[s2]; b2 < start[s2 + 1]; b2 += ALIGN_THREADS) {
+					const AlignUnit u{(uint32_t)s2, b2, std::min<uint32_t>(ALIGN_THREADS, start[s2 + 1] - b2)};
+					if (per_class) (*per_class)[c].push_back(u);
+					if (flat) flat->push_back(u);
+				}
 			}
-			for (size_t i = 0; i < items.size(); ++i) { sc[i] = items[i].c; slots[i] = items[i].slot; }
 			e->d_slow_cand.upload(sc, e->stream);
 			e->d_slot_map.upload(slots, e->stream);
+		};
+
+		if (cnt[2]) {
+			// optimal path enters a gap state: full-trace variant of the fast kernel
+			std::vector<std::vector<AlignUnit>> retry_units(nclass);
+			regroup(e->d_retry, cnt[2], &retry_units, nullptr);
 			AlignArgs g = a;
 			g.cand = e->d_slow_cand.p;
 			g.cap = 0; // units index the compacted array directly
+			g.slot_map = emit_all ? e->d_slot_map.p : nullptr;
+			for (int c = 0; c < nclass; ++c)
+				if (!retry_units[c].empty()) ms += run_align_kernel(e, set, g, retry_units[c], kFastClasses[c], set.max_len, true);
+			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, 2*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+			if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1]*5/4; continue; }
+		}
+		if (cnt[1]) {
+			// windows with IUPAC / inosine / N target bases (or no positive score): generic kernel
+			std::vector<AlignUnit> units;
+			regroup(e->d_slow, cnt[1], nullptr, &units);
+			AlignArgs g = a;
+			g.cand = e->d_slow_cand.p;
+			g.cap = 0;
 			g.slot_map = emit_all ? e->d_slot_map.p : nullptr;
 			ms += run_align_kernel(e, set, g, units, 0, set.max_len);
 			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -1043,7 +1097,7 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
 	e->d_thermo.reserve(1, 0, e->stream);
 	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
-	e->d_out_count.reserve(2, 0, e->stream);
+	e->d_out_count.reserve(4, 0, e->stream);
 	e->d_cells.reserve(1, 0, e->stream);
 	{
 		std::vector<int32_t> p5(20);

@@ -375,7 +375,7 @@ struct AlignArgs {
 	uint32_t nunits;
 	int max_lt;                // generic kernel: row stride of the shared DP rows (columns 0..max_lt)
 	uint16_t *trace;           // [gridDim.x][cells][ALIGN_THREADS]
-	uint32_t trace_cells;      // 16-bit cells reserved per CTA
+	uint32_t trace_cells;      // generic: 16-bit cells per CTA and thread; fast: 8-bit cells
 	BoundRec *out;             // filtered mode: appended; all mode: out[slot]
 	uint32_t *out_count;
 	uint32_t out_cap;
@@ -387,9 +387,11 @@ struct AlignArgs {
 	const int32_t *row_tab;    // per oligo strand: len rows x ROW_WORDS
 	const uint32_t *row_tab_off;
 	const int32_t *p5_tab;     // [20]
-	SlowItem *slow;
+	SlowItem *slow;            // -> generic kernel
 	uint32_t *slow_count;
-	uint32_t slow_cap;
+	SlowItem *retry;           // -> full-trace fast kernel
+	uint32_t *retry_count;
+	uint32_t slow_cap;         // capacity of both lists
 };
 
 // Thresholds in the reference's order (bind_oligo.cpp:598-714), target coordinates
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 
 // Fast kernel: windows made of A/C/G/T only (the oligo may hold any code).  All units of one
 // launch belong to oligo strands of at most LQ bases.
-template <int LQ>
+template <int LQ, bool FULL>
 __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 {
 	__shared__ int32_t s_tab[LQ*ROW_WORDS];
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 	for (int i = tid; i < NPAIR; i += ALIGN_THREADS) s_wc[i] = a.thermo->wc[i];
 	if (tid < 20) s_p5[tid] = a.p5_tab[tid];
 
-	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*(a.trace_cells/2)*ALIGN_THREADS + tid;
+	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*(a.trace_cells/(FULL ? 2 : 4))*ALIGN_THREADS + tid;
 	unsigned long long my_cells = 0;
 	uint32_t cur_os = 0xffffffffu;
 
@@ -653,13 +655,45 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 		best_aln.b = best_aln.e = 2;
 		best_aln.fm_q = best_aln.fm_t = best_aln.lm_q = best_aln.lm_t = 0;
 
+		// 0: done here, 1: retry with the full-trace fill, 2: generic kernel
+		int handoff = 0;
 		if (Lt > 0) {
-			const FastDp dp = nc_fill_fast<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
-			ColMajorTrace<LQ, ALIGN_THREADS> tv;
-			tv.trace32 = trace32;
 			uint16_t cells[MAX_MAXCELLS];
-			const int ncells = collect_max_cells_fast<LQ, ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
-			nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
+			if (FULL) {
+				const FastDpFull dp = nc_fill_fast_full<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
+				ColMajorTraceFull<LQ, ALIGN_THREADS> tv;
+				tv.trace32 = trace32;
+				if (dp.runmax <= 0) handoff = 2; // the reference's ">= -1" rule decides: not recorded here
+				else {
+					const int ncells = collect_max_cells_full<LQ, ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
+					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
+				}
+			}
+			else {
+				const FastDp dp = nc_fill_fast<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
+				ColMajorTrace<LQ, ALIGN_THREADS> tv;
+				tv.trace32 = trace32;
+				const int ncells = collect_max_cells_fast<LQ, ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
+				if (ncells < 0) handoff = 2;
+				else {
+					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
+					if (flags & F_NEEDGENERIC) handoff = 1;
+				}
+			}
+		}
+		if (handoff) {
+			my_cells -= (unsigned long long)(os.len*Lt); // counted again by the kernel that takes over
+			uint32_t *counter = handoff == 1 ? a.retry_count : a.slow_count;
+			SlowItem *list = handoff == 1 ? a.retry : a.slow;
+			const uint32_t sl = atomicAdd(counter, 1u);
+			if (sl < a.slow_cap) {
+				SlowItem it;
+				it.os = unit.os;
+				it.slot = a.slot_map ? a.slot_map[idx] : idx;
+				it.c = c;
+				list[sl] = it;
+			}
+			continue;
 		}
 		finish_alignment(a, sh, os, unit.os, target, k, c.t, start, stop, tgt, Lt, best, best_aln, flags,
 			a.slot_map ? a.slot_map[idx] : idx);

@@ -95,6 +95,7 @@ struct BoundRec {
 constexpr uint8_t F_OOB = 1;        // the reference would have read out of range here
 constexpr uint8_t F_STACK = 2;      // branch stack overflow (never expected)
 constexpr uint8_t F_TRUNC = 4;      // alignment longer than MAX_COLS
+constexpr uint8_t F_NEEDGENERIC = 8; // fast kernel only: this candidate needs the generic kernel (gap on an optimal path)
 
 // Scan region of stage 2 (partner / probe search around a bound site)
 struct Region {
