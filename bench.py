@@ -59,7 +59,7 @@ def env_int(name, default):
         return default
 
 
-def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False):
+def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False, kind: str = "taqman"):
     """Synthetic shard of `mbp` Mbp (records of 5 Mbp) + TaqMan assays planted into it.
 
     With pinned=True the bases live in one page-locked host allocation (the fragments are views
@@ -80,7 +80,7 @@ def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False):
         records.append(store[pos:pos + n])
         pos += n
     arng = np.random.default_rng(99)  # same assays on every rank
-    assays = gen.make_assays(arng, records, n_assays, "taqman", lens=(20, 21, 25), amp=(80, 400), variants=2)
+    assays = gen.make_assays(arng, records, n_assays, kind, lens=(20, 21, 25), amp=(80, 400), variants=2)
     fragments = []
     for rec in records:
         for (a, b) in fragment_record(len(rec), FRAGMENT_BP):
@@ -89,54 +89,62 @@ def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md) through NVML.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Samples are taken synchronously between steps of the timed loop (at most `max_samples`, evenly
+    spaced): a concurrently polling nvidia-smi / NVML thread was measured to slow the CUDA API calls
+    of the step by >30 %, so the sampling cost is kept small and lands honestly inside the timing."""
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.path = None
-
-    def start(self):
-        if shutil.which("nvidia-smi") is None:
-            return
-        fd, self.path = tempfile.mkstemp(suffix=".csv")
-        os.close(fd)
-        self.f = open(self.path, "w")
-        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits", "-lms", "250"],
-                                     stdout=self.f, stderr=subprocess.DEVNULL)
-
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
+    def __init__(self, gpu_index: int, steps: int, max_samples: int = 4):
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self.cost_s = 0.0
+        self._h = None
+        stride = max(1, -(-steps // max_samples))
+        self.when = set(range(0, steps, stride)) | {steps - 1}
         try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.f.close()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 9:
-                continue
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = gpu_index
+            if vis:
+                parts = [x for x in vis.split(",") if x.strip() != ""]
+                if gpu_index < len(parts) and parts[gpu_index].strip().isdigit():
+                    idx = int(parts[gpu_index])
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def sample(self, step: int):
+        if self._h is None or step not in self.when:
+            return
+        t0 = time.perf_counter()
+        nv = self._nv
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
             try:
-                sm.append(float(p[1]))
-                smax.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, p[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                              ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                              ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+        self.cost_s += time.perf_counter() - t0
+
+    def result(self):
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+               "samples": len(self.samples), "source": "nvml, sampled between steps inside the timed region",
+               "sampling_ms_total": self.cost_s * 1e3}
+        if self.samples:
+            out["sm_mhz"] = float(np.median(self.samples))
         return out
 
 
@@ -164,7 +172,7 @@ def write_reference_inputs(tmp: str, records, assays, sample_bp: int):
     q = os.path.join(tmp, "assays.txt")
     with open(q, "w") as f:
         for i, (F, R, P) in enumerate(assays):
-            f.write("assay%d\t%s\t%s\t%s\n" % (i, F, R, P))
+            f.write("assay%d\t%s\t%s%s\n" % (i, F, R, ("\t" + P) if P else ""))
     return fa, q, sample_bp - max(left, 0)
 
 
@@ -213,14 +221,16 @@ def main():
     ap.add_argument("--mbp", type=int, default=1000, help="database size per GPU in Mbp")
     ap.add_argument("--assays", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kind", default="taqman", choices=["taqman", "pcr"], help="assay type (default: BASELINE configs[1])")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
-    workload = ("%d TaqMan primer+probe triplets (20/21/25-mers, -e %g -E %g) vs synthetic %.3g Gbp multi-record "
+    kind_txt = "TaqMan primer+probe triplets" if args.kind == "taqman" else "PCR primer pairs"
+    workload = ("%d %s (20/21/25-mers, -e %g -E %g) vs synthetic %.3g Gbp multi-record "
                 "database per GPU (%d Mbp records, <=%d kbp fragments + %d bp overlap)"
-                % (args.assays, MIN_PRIMER_TM, MIN_PROBE_TM, args.mbp / 1000.0, RECORD_BP // 1_000_000,
+                % (args.assays, kind_txt, MIN_PRIMER_TM, MIN_PROBE_TM, args.mbp / 1000.0, RECORD_BP // 1_000_000,
                    FRAGMENT_BP // 1000, OVERLAP))
 
     if args.impl == "reference":
@@ -230,7 +240,7 @@ def main():
         cores = host_cores()
         per_step_s = 6.0
         sample_mbp = max(1, int(per_step_s * 0.016e9 * cores / max(args.assays, 1) / 1e6))
-        records, _, assays, _ = build_workload(0, min(args.mbp, max(sample_mbp, 5)), args.assays)
+        records, _, assays, _ = build_workload(0, min(args.mbp, max(sample_mbp, 5)), args.assays, kind=args.kind)
         tmp = tempfile.mkdtemp(prefix="tntref_")
         try:
             fa, q, used = write_reference_inputs(tmp, records, assays, sample_mbp * 1_000_000)
@@ -263,7 +273,7 @@ def main():
 
     from thermonucleotideblast_b200 import Assay, Engine, search_options
 
-    records, fragments, assays, db_bases = build_workload(rank, args.mbp, args.assays, pinned=True)
+    records, fragments, assays, db_bases = build_workload(rank, args.mbp, args.assays, pinned=True, kind=args.kind)
     frag_bases = int(sum(len(f) for f in fragments))
     opts = search_options(min_primer_tm=MIN_PRIMER_TM, min_probe_tm=MIN_PROBE_TM, max_len=MAX_LEN)
     eng = Engine(device=local_rank)
@@ -298,15 +308,14 @@ def main():
     upload()
     for _ in range(args.warmup):
         eng.search_raw(opts)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)   # let nvidia-smi attach before the timed region starts
+    sampler = ClockSampler(local_rank, args.steps)
     barrier()
     t0 = time.perf_counter()
     dev_ms = scan_ms = align_ms = 0.0
     launches = 0
-    for _ in range(args.steps):
+    for step in range(args.steps):
         nhits = eng.search_raw(opts)
+        sampler.sample(step)
         st = eng.stats()
         dev_ms += st.total_ms
         scan_ms += st.scan_ms
@@ -314,7 +323,7 @@ def main():
         launches += st.kernel_launches
     barrier()
     dt = (time.perf_counter() - t0) / args.steps
-    clocks = sampler.stop()
+    clocks = sampler.result()
     dt = max_over_ranks(dt)
     st = eng.stats()
     units = sum_over_ranks(db_bases * len(assays) / 1e9)

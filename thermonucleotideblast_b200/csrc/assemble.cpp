@@ -125,6 +125,23 @@ void unique_sites(std::vector<const BoundSite *> &v, bool mask_variant)
 void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int assay_id, bool has_probe,
 	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
+	// Cheap exits before any sorting: an amplicon needs a minus-strand primer site f and a
+	// plus-strand primer site r with f.loc_3 < r.loc_5 and r.loc_3 - f.loc_5 + 1 <= max_len
+	// (amplicon_search.cpp:383-390), and a TaqMan assay a probe site as well (:399-406).
+	{
+		bool any_probe = false, any_pair = false;
+		for (const BoundSite *s : group) any_probe |= (s->role == TNT_OLIGO_P);
+		if (has_probe && !any_probe) return;
+		for (const BoundSite *f : group) {
+			if (f->plus || f->role == TNT_OLIGO_P) continue;
+			for (const BoundSite *r : group) {
+				if (!r->plus || r->role == TNT_OLIGO_P) continue;
+				if (f->loc3 < r->loc5 && (r->loc3 - f->loc5 + 1) <= (int)opt.max_len) { any_pair = true; break; }
+			}
+			if (any_pair) break;
+		}
+		if (!any_pair) return;
+	}
 	// per (role, strand) uniqueness, then one list ordered by (loc_5, loc_3)
 	std::vector<const BoundSite *> all;
 	for (int plus = 0; plus < 2; ++plus)

@@ -185,6 +185,7 @@ struct tnt_engine {
 	DevBuf<SlowItem> d_slow, d_retry;
 	DevBuf<Candidate> d_slow_cand;
 	DevBuf<uint32_t> d_slot_map;
+	DevBuf<uint32_t> d_group;
 	DevBuf<int32_t> d_p5;
 	DevBuf<uint8_t> d_extract;
 
@@ -638,16 +639,20 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		// Hand-over lists -> compact candidate arrays grouped by oligo strand (counting sort)
 		auto regroup = [&](const DevBuf<SlowItem> &list, uint32_t n, std::vector<std::vector<AlignUnit>> *per_class,
 			std::vector<AlignUnit> *flat) {
-			std::vector<SlowItem> items(n);
-			CUDA_OK(cudaMemcpyAsync(items.data(), list.p, (size_t)n*sizeof(SlowItem), cudaMemcpyDeviceToHost, e->stream));
-			CUDA_OK(cudaStreamSynchronize(e->stream));
+			e->d_group.reserve(3*nos + 2, 0, e->stream); // hist | start[nos+1] | fill
+			uint32_t *hist = e->d_group.p, *start_d = hist + nos, *fill = start_d + nos + 1;
+			e->d_slow_cand.reserve(n, 0, e->stream);
+			e->d_slot_map.reserve(n, 0, e->stream);
+			CUDA_OK(cudaMemsetAsync(hist, 0, nos*sizeof(uint32_t), e->stream));
+			const unsigned gb = (unsigned)std::min<size_t>(((size_t)n + 255)/256, (size_t)e->sm_count*8);
+			k_regroup_hist<<<gb, 256, 0, e->stream>>>(list.p, n, hist);
+			k_regroup_scan<<<1, 1024, 0, e->stream>>>(hist, (uint32_t)nos, start_d, fill);
+			k_regroup_scatter<<<gb, 256, 0, e->stream>>>(list.p, n, fill, e->d_slow_cand.p, e->d_slot_map.p);
+			CUDA_OK(cudaGetLastError());
+			e->stats.kernel_launches += 3;
 			std::vector<uint32_t> start(nos + 1, 0);
-			for (const SlowItem &it : items) start[it.os + 1]++;
-			for (size_t s2 = 0; s2 < nos; ++s2) start[s2 + 1] += start[s2];
-			std::vector<Candidate> sc(n);
-			std::vector<uint32_t> slots(n);
-			std::vector<uint32_t> fill(start.begin(), start.end() - 1);
-			for (const SlowItem &it : items) { const uint32_t d = fill[it.os]++; sc[d] = it.c; slots[d] = it.slot; }
+			CUDA_OK(cudaMemcpyAsync(start.data(), start_d, (nos + 1)*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
 			for (size_t s2 = 0; s2 < nos; ++s2) {
 				int c = 0;
 				while (c < nclass - 1 && kFastClasses[c] < set.os[s2].len) ++c;
@@ -657,8 +662,6 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 					if (flat) flat->push_back(u);
 				}
 			}
-			e->d_slow_cand.upload(sc, e->stream);
-			e->d_slot_map.upload(slots, e->stream);
 		};
 
 		if (cnt[2]) {
@@ -706,7 +709,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 	const double keys = (double)set.nkeys;
 	// expected candidates per base of database for the busiest oligo strand
 	const double per_base = (double)set.max_words/keys;
-	const size_t budget_bytes = (size_t)1 << 30;
+	const size_t budget_bytes = (size_t)4 << 30; // candidate buckets per pass (HBM is plentiful)
 	const size_t cap_budget = std::max<size_t>(budget_bytes/sizeof(Candidate)/nos, 4096);
 	uint32_t tiles_per_chunk = (uint32_t)e->tiles.size();
 	{
@@ -936,17 +939,32 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	};
 	// PCR: an amplicon needs a plus-strand primer site, and those only come out of stage 2.  Drop
 	// the (fragment, assay) groups without one before any sorting happens.
-	std::vector<uint64_t> live_keys;
 	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty();
+	const uint64_t n_assays = e->assays.size();
+	const uint64_t key_space = (uint64_t)e->targets.size()*n_assays;
+	const bool use_bitmap = prefilter && key_space <= ((uint64_t)1 << 32);
+	std::vector<uint64_t> live_bits;
+	std::vector<uint64_t> live_keys;
 	if (prefilter) {
+		if (use_bitmap) live_bits.assign((size_t)(key_space + 63)/64, 0);
 		for (uint32_t i = n1; i < n2; ++i) {
 			const BoundHead &b = e->h_heads[i];
 			const OligoStrand &os = os_of(b.os);
-			if (os.role != TNT_OLIGO_P) live_keys.push_back(((uint64_t)b.target << 32) | (uint32_t)os.assay);
+			if (os.role == TNT_OLIGO_P) continue;
+			const uint64_t key = (uint64_t)b.target*n_assays + (uint32_t)os.assay;
+			if (use_bitmap) live_bits[(size_t)(key >> 6)] |= (uint64_t)1 << (key & 63);
+			else live_keys.push_back(key);
 		}
-		std::sort(live_keys.begin(), live_keys.end());
-		live_keys.erase(std::unique(live_keys.begin(), live_keys.end()), live_keys.end());
+		if (!use_bitmap) {
+			std::sort(live_keys.begin(), live_keys.end());
+			live_keys.erase(std::unique(live_keys.begin(), live_keys.end()), live_keys.end());
+		}
 	}
+	auto is_live = [&](uint32_t target, int assay) {
+		const uint64_t key = (uint64_t)target*n_assays + (uint32_t)assay;
+		return use_bitmap ? ((live_bits[(size_t)(key >> 6)] >> (key & 63)) & 1) != 0
+		                  : std::binary_search(live_keys.begin(), live_keys.end(), key);
+	};
 	uint64_t n_sites_total = 0;
 	std::vector<BoundSite> sites;
 	sites.reserve(prefilter ? (size_t)(n2 - n1)*4 + 64 : n2);
@@ -958,9 +976,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		if (b.flags & (F_OOB | F_STACK))
 			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
 		const OligoStrand &os = os_of(b.os);
-		if (prefilter && e->assays[(size_t)os.assay].F.size() &&
-			!std::binary_search(live_keys.begin(), live_keys.end(), ((uint64_t)b.target << 32) | (uint32_t)os.assay))
-			continue;
+		if (prefilter && e->assays[(size_t)os.assay].F.size() && !is_live(b.target, os.assay)) continue;
 		sites.push_back(make_site(b, i, os));
 	}
 	e->stats.bound_sites = n_sites_total;

@@ -473,6 +473,49 @@ __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, 
 	r.h.loc3 = t3;
 }
 
+// Hand-over lists (SlowItem) -> candidate arrays grouped by oligo strand, on the device:
+// histogram, exclusive scan (one block), scatter.
+__global__ void k_regroup_hist(const SlowItem *__restrict__ items, uint32_t n, uint32_t *__restrict__ hist)
+{
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) atomicAdd(hist + items[i].os, 1u);
+}
+
+// start[0..nos] = exclusive prefix of hist; fill[] = copy of start[0..nos)
+__global__ void __launch_bounds__(1024) k_regroup_scan(const uint32_t *__restrict__ hist, uint32_t nos, uint32_t *__restrict__ start, uint32_t *__restrict__ fill)
+{
+	__shared__ uint32_t s_part[1024];
+	const uint32_t per = (nos + 1023)/1024;
+	const uint32_t b0 = threadIdx.x*per;
+	uint32_t sum = 0;
+	for (uint32_t k = 0; k < per && b0 + k < nos; ++k) sum += hist[b0 + k];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
+		for (int k = 0; k < 1024; ++k) { const uint32_t v = s_part[k]; s_part[k] = run; run += v; }
+		start[nos] = run;
+	}
+	__syncthreads();
+	uint32_t run = s_part[threadIdx.x];
+	for (uint32_t k = 0; k < per && b0 + k < nos; ++k) {
+		const uint32_t v = hist[b0 + k];
+		start[b0 + k] = run;
+		fill[b0 + k] = run;
+		run += v;
+	}
+}
+
+__global__ void k_regroup_scatter(const SlowItem *__restrict__ items, uint32_t n, uint32_t *__restrict__ fill,
+	Candidate *__restrict__ cand, uint32_t *__restrict__ slots)
+{
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		const SlowItem it = items[i];
+		const uint32_t d = atomicAdd(fill + it.os, 1u);
+		cand[d] = it.c;
+		slots[d] = it.slot;
+	}
+}
+
 // Copy selected records into a dense array (the hits' oligo sites, for text rendering)
 __global__ void k_gather_recs(const BoundRec *__restrict__ src, const uint32_t *__restrict__ index, uint32_t n, BoundRec *__restrict__ dst)
 {
