@@ -315,7 +315,8 @@ def main():
     launches = 0
     for step in range(args.steps):
         nhits = eng.search_raw(opts)
-        sampler.sample(step)
+        if not os.environ.get("TNT_NO_SAMPLER"):
+            sampler.sample(step)
         st = eng.stats()
         dev_ms += st.total_ms
         scan_ms += st.scan_ms

@@ -171,7 +171,7 @@ struct tnt_engine {
 	// scratch of the search
 	DevBuf<Candidate> d_cand;
 	DevBuf<uint32_t> d_cand_count;
-	DevBuf<AlignUnit> d_units;
+	DevBuf<AlignGroup> d_groups;
 	DevBuf<uint16_t> d_trace;
 	DevBuf<BoundRec> d_bound;    // every site that passed the per-oligo filters, all passes of a search
 	uint32_t n_bound = 0;
@@ -188,6 +188,12 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_group;
 	DevBuf<int32_t> d_p5;
 	DevBuf<uint8_t> d_extract;
+
+	// oligo-strand sets of the last search, reused while assays and options stay the same
+	std::unique_ptr<OsSet> set1, set2;
+	tnt_search_options set_opt{};
+	uint64_t assays_version = 0, set_version = ~(uint64_t)0;
+	std::vector<Region> regions;   // persistent: avoids re-faulting megabytes of host memory per search
 
 	std::vector<tnt_hit> hits;
 	std::string arena;
@@ -507,11 +513,15 @@ int fast_blocks_per_sm(int lq, bool full)
 
 // Run one alignment kernel (fast class `lq`, or the generic kernel when lq == 0) over `units`,
 // appending / writing results into e->d_out.  Returns the device time.
-float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector<AlignUnit> &units, int lq, int max_len, bool full = false)
+float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<AlignGroup> &groups, int lq, int max_len, bool full = false)
 {
-	e->d_units.upload(units, e->stream);
-	a.units = e->d_units.p;
-	a.nunits = (uint32_t)units.size();
+	// unit prefix over the groups
+	uint32_t nunits = 0;
+	for (AlignGroup &g : groups) { g.unit_prefix = nunits; nunits += (g.count + ALIGN_THREADS - 1)/ALIGN_THREADS; }
+	e->d_groups.upload(groups, e->stream);
+	a.groups = e->d_groups.p;
+	a.ngroups = (uint32_t)groups.size();
+	a.nunits = nunits;
 	uint32_t grid;
 	size_t smem = 0;
 	if (lq == 0) {
@@ -520,12 +530,12 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, const std::vector
 		CUDA_OK(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		int per_sm = 1;
 		CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_align, ALIGN_THREADS, smem));
-		grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*std::max(per_sm, 1));
+		grid = (uint32_t)std::min<size_t>(nunits, (size_t)e->sm_count*std::max(per_sm, 1));
 		a.max_lt = max_lt;
 		a.trace_cells = (uint32_t)max_len*(uint32_t)max_lt;
 	}
 	else {
-		grid = (uint32_t)std::min<size_t>(units.size(), (size_t)e->sm_count*fast_blocks_per_sm(lq, full));
+		grid = (uint32_t)std::min<size_t>(nunits, (size_t)e->sm_count*fast_blocks_per_sm(lq, full));
 		a.trace_cells = (uint32_t)lq*(uint32_t)(lq + 2*NUM_FLANK);
 	}
 	// d_trace counts 16-bit units; the fast kernel stores one byte per cell
@@ -574,14 +584,14 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 	HostTimer t_ab("  align_buckets");
 	// units per fast class
 	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));
-	std::vector<std::vector<AlignUnit>> by_class(nclass + 1); // [nclass] = generic kernel
-	for (size_t s = 0; s < nos; ++s) {
+	std::vector<std::vector<AlignGroup>> by_class(nclass + 1); // [nclass] = generic kernel
+	auto class_of = [&](size_t s) {
 		int c = 0;
 		while (c < nclass - 1 && kFastClasses[c] < set.os[s].len) ++c;
-		if (!set.fast_ok[s]) c = nclass;
-		for (uint32_t b = 0; b < counts[s]; b += ALIGN_THREADS)
-			by_class[c].push_back(AlignUnit{(uint32_t)s, b, std::min<uint32_t>(ALIGN_THREADS, counts[s] - b)});
-	}
+		return set.fast_ok[s] ? c : nclass;
+	};
+	for (size_t s = 0; s < nos; ++s)
+		if (counts[s]) by_class[class_of(s)].push_back(AlignGroup{(uint32_t)s, 0u, counts[s], 0u});
 
 	const uint32_t base_count = e->n_bound;
 	size_t out_cap = emit_all ? (size_t)base_count + total : std::max<size_t>(e->d_bound.cap, (size_t)base_count + (1u << 16));
@@ -637,8 +647,8 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			fprintf(stderr, "[tnt]   candidates %llu, full-trace retry %u, generic %u, fast ms %.3f\n", (unsigned long long)total, cnt[2], cnt[1], ms);
 
 		// Hand-over lists -> compact candidate arrays grouped by oligo strand (counting sort)
-		auto regroup = [&](const DevBuf<SlowItem> &list, uint32_t n, std::vector<std::vector<AlignUnit>> *per_class,
-			std::vector<AlignUnit> *flat) {
+		auto regroup = [&](const DevBuf<SlowItem> &list, uint32_t n, std::vector<std::vector<AlignGroup>> *per_class,
+			std::vector<AlignGroup> *flat) {
 			e->d_group.reserve(3*nos + 2, 0, e->stream); // hist | start[nos+1] | fill
 			uint32_t *hist = e->d_group.p, *start_d = hist + nos, *fill = start_d + nos + 1;
 			e->d_slow_cand.reserve(n, 0, e->stream);
@@ -654,19 +664,16 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			CUDA_OK(cudaMemcpyAsync(start.data(), start_d, (nos + 1)*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
 			for (size_t s2 = 0; s2 < nos; ++s2) {
-				int c = 0;
-				while (c < nclass - 1 && kFastClasses[c] < set.os[s2].len) ++c;
-				for (uint32_t b2 = start[s2]; b2 < start[s2 + 1]; b2 += ALIGN_THREADS) {
-					const AlignUnit u{(uint32_t)s2, b2, std::min<uint32_t>(ALIGN_THREADS, start[s2 + 1] - b2)};
-					if (per_class) (*per_class)[c].push_back(u);
-					if (flat) flat->push_back(u);
-				}
+				if (start[s2 + 1] == start[s2]) continue;
+				const AlignGroup g{(uint32_t)s2, start[s2], start[s2 + 1] - start[s2], 0u};
+				if (per_class) (*per_class)[std::min(class_of(s2), nclass - 1)].push_back(g);
+				if (flat) flat->push_back(g);
 			}
 		};
 
 		if (cnt[2]) {
 			// optimal path enters a gap state: full-trace variant of the fast kernel
-			std::vector<std::vector<AlignUnit>> retry_units(nclass);
+			std::vector<std::vector<AlignGroup>> retry_units(nclass);
 			regroup(e->d_retry, cnt[2], &retry_units, nullptr);
 			AlignArgs g = a;
 			g.cand = e->d_slow_cand.p;
@@ -680,7 +687,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		}
 		if (cnt[1]) {
 			// windows with IUPAC / inosine / N target bases (or no positive score): generic kernel
-			std::vector<AlignUnit> units;
+			std::vector<AlignGroup> units;
 			regroup(e->d_slow, cnt[1], nullptr, &units);
 			AlignArgs g = a;
 			g.cand = e->d_slow_cand.p;
@@ -840,65 +847,77 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		o.assay_format != TNT_ASSAY_PADLOCK && o.assay_format != TNT_ASSAY_MIPS)
 		throw std::runtime_error("unsupported assay format");
 
-	OsSet stage1, stage2;
-	const int W = e->prm.word_size;
-	(void)W;
+	const bool reuse_sets = e->set1 && e->set2 && e->set_version == e->assays_version &&
+		std::memcmp(&e->set_opt, &o, sizeof(o)) == 0;
+	if (!reuse_sets) {
+		e->set1.reset(new OsSet);
+		e->set2.reset(new OsSet);
+	}
+	OsSet &stage1 = *e->set1, &stage2 = *e->set2;
 
-	for (size_t ai = 0; ai < e->assays.size(); ++ai) {
-		const AssayHost &as = e->assays[ai];
-		const bool has_primers = !as.F.empty() && !as.R.empty();
-		const bool has_probe = !as.P.empty();
-		const float fct = o.forward_primer_strand/as.fdeg;
-		const float rct = o.reverse_primer_strand/as.rdeg;
-		const float pct = o.probe_strand/as.pdeg;
-		if (has_primers) {
-			if (o.assay_format == TNT_ASSAY_PCR) {
-				for (int plus = 0; plus < 2; ++plus) {
-					OsSet &dst = plus ? stage2 : stage1;
-					dst.os.push_back(make_os(e, (int)ai, TNT_OLIGO_F, plus, as.F, fct, o.min_primer_tm, o.max_primer_tm,
-						o.min_primer_dg, o.max_primer_dg, 0, o.primer_clamp, o));
-					dst.os.push_back(make_os(e, (int)ai, TNT_OLIGO_R, plus, as.R, rct, o.min_primer_tm, o.max_primer_tm,
-						o.min_primer_dg, o.max_primer_dg, 0, o.primer_clamp, o));
+	if (!reuse_sets) {
+
+		for (size_t ai = 0; ai < e->assays.size(); ++ai) {
+			const AssayHost &as = e->assays[ai];
+			const bool has_primers = !as.F.empty() && !as.R.empty();
+			const bool has_probe = !as.P.empty();
+			const float fct = o.forward_primer_strand/as.fdeg;
+			const float rct = o.reverse_primer_strand/as.rdeg;
+			const float pct = o.probe_strand/as.pdeg;
+			if (has_primers) {
+				if (o.assay_format == TNT_ASSAY_PCR) {
+					for (int plus = 0; plus < 2; ++plus) {
+						OsSet &dst = plus ? stage2 : stage1;
+						dst.os.push_back(make_os(e, (int)ai, TNT_OLIGO_F, plus, as.F, fct, o.min_primer_tm, o.max_primer_tm,
+							o.min_primer_dg, o.max_primer_dg, 0, o.primer_clamp, o));
+						dst.os.push_back(make_os(e, (int)ai, TNT_OLIGO_R, plus, as.R, rct, o.min_primer_tm, o.max_primer_tm,
+							o.min_primer_dg, o.max_primer_dg, 0, o.primer_clamp, o));
+					}
+					if (has_probe)
+						for (int plus = 0; plus < 2; ++plus)
+							stage2.os.push_back(make_os(e, (int)ai, TNT_OLIGO_P, plus, as.P, pct, o.min_probe_tm, o.max_probe_tm,
+								o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, o.probe_clamp_3, o));
 				}
-				if (has_probe)
-					for (int plus = 0; plus < 2; ++plus)
-						stage2.os.push_back(make_os(e, (int)ai, TNT_OLIGO_P, plus, as.P, pct, o.min_probe_tm, o.max_probe_tm,
-							o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, o.probe_clamp_3, o));
+				else if (o.assay_format == TNT_ASSAY_PADLOCK || o.assay_format == TNT_ASSAY_MIPS) {
+					for (int plus = 0; plus < 2; ++plus) {
+						if (!(o.target_strand & (plus ? TNT_STRAND_PLUS : TNT_STRAND_MINUS))) continue;
+						// upstream probe = "reverse" oligo with a 5' clamp, downstream = "forward" with a 3' clamp
+						stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_R, plus, as.R, rct, o.min_probe_tm, o.max_probe_tm,
+							o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, 0, o));
+						stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_F, plus, as.F, fct, o.min_probe_tm, o.max_probe_tm,
+							o.min_probe_dg, o.max_probe_dg, 0, o.probe_clamp_3, o));
+					}
+				}
+				else throw std::runtime_error("assay with primers in PROBE format");
 			}
-			else if (o.assay_format == TNT_ASSAY_PADLOCK || o.assay_format == TNT_ASSAY_MIPS) {
+			else if (has_probe) {
 				for (int plus = 0; plus < 2; ++plus) {
 					if (!(o.target_strand & (plus ? TNT_STRAND_PLUS : TNT_STRAND_MINUS))) continue;
-					// upstream probe = "reverse" oligo with a 5' clamp, downstream = "forward" with a 3' clamp
-					stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_R, plus, as.R, rct, o.min_probe_tm, o.max_probe_tm,
-						o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, 0, o));
-					stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_F, plus, as.F, fct, o.min_probe_tm, o.max_probe_tm,
-						o.min_probe_dg, o.max_probe_dg, 0, o.probe_clamp_3, o));
+					stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_P, plus, as.P, pct, o.min_probe_tm, o.max_probe_tm,
+						o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, o.probe_clamp_3, o));
 				}
 			}
-			else throw std::runtime_error("assay with primers in PROBE format");
 		}
-		else if (has_probe) {
-			for (int plus = 0; plus < 2; ++plus) {
-				if (!(o.target_strand & (plus ? TNT_STRAND_PLUS : TNT_STRAND_MINUS))) continue;
-				stage1.os.push_back(make_os(e, (int)ai, TNT_OLIGO_P, plus, as.P, pct, o.min_probe_tm, o.max_probe_tm,
-					o.min_probe_dg, o.max_probe_dg, o.probe_clamp_5, o.probe_clamp_3, o));
-			}
-		}
+
+
+		{ HostTimer t("finish_set stage1"); finish_set(e, stage1); }
+		if (!stage2.os.empty()) finish_set(e, stage2);
+		e->set_opt = o;
+		e->set_version = e->assays_version;
 	}
 
 	e->n_bound = 0;
-	{ HostTimer t("finish_set stage1"); finish_set(e, stage1); }
 	{ HostTimer t("scan_and_align stage1"); scan_and_align(e, stage1, 0); }
 	const uint32_t n1 = e->n_bound;
 	fetch_heads(e, 0, n1);
 
 	if (!stage2.os.empty() && n1 != 0) {
 		HostTimer t_s2("stage2 total");
-		finish_set(e, stage2);
 		// Partner primers / probes can only matter downstream of a bound minus-strand primer
 		// (amplicon_search.cpp:359-441: f on the minus strand, r and p after it, amplicon <= max_len;
 		// cull_oligo_match :679-765 uses max_len + 50 on seed positions).
-		std::vector<Region> regions;
+		std::vector<Region> &regions = e->regions;
+		regions.clear();
 		regions.reserve(n1);
 		const uint32_t slack = 64;
 		for (uint32_t i = 0; i < n1; ++i) {
@@ -1182,6 +1201,7 @@ int tnt_engine_set_assays(tnt_engine *e, const tnt_assay *assays, int32_t n)
 		v.push_back(a);
 	}
 	e->assays.swap(v);
+	e->assays_version++;
 	API_END
 }
 

@@ -362,6 +362,28 @@ constexpr int ALIGN_THREADS = 128;
 
 struct AlignUnit { uint32_t os; uint32_t begin; uint32_t count; }; // `begin` indexes cand[os*cap + ...]
 
+// Work of one launch = a few groups (one per oligo strand), each cut into units of ALIGN_THREADS
+// candidates.  Only the per-group arrays travel to the device; a CTA finds the group of unit u by
+// binary search in the prefix of unit counts.
+struct AlignGroup { uint32_t os; uint32_t first; uint32_t count; uint32_t unit_prefix; }; // first: index of the group's first candidate in cand[os*cap + ...]
+
+__device__ __forceinline__ AlignUnit unit_of(const AlignGroup *__restrict__ groups, uint32_t ngroups, uint32_t u)
+{
+	uint32_t lo = 0, hi = ngroups; // last group with unit_prefix <= u
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (groups[mid].unit_prefix <= u) lo = mid;
+		else hi = mid;
+	}
+	const AlignGroup g = groups[lo];
+	const uint32_t local = (u - g.unit_prefix)*ALIGN_THREADS;
+	AlignUnit r;
+	r.os = g.os;
+	r.begin = g.first + local;
+	r.count = min((uint32_t)ALIGN_THREADS, g.count - local);
+	return r;
+}
+
 // A candidate the fast kernel hands to the generic one (window with non-ACGT target bases)
 struct SlowItem { uint32_t os; uint32_t slot; Candidate c; };
 
@@ -371,7 +393,8 @@ struct AlignArgs {
 	const OligoStrand *os;
 	const Candidate *cand;
 	uint32_t cap;
-	const AlignUnit *units;
+	const AlignGroup *groups;
+	uint32_t ngroups;
 	uint32_t nunits;
 	int max_lt;                // generic kernel: row stride of the shared DP rows (columns 0..max_lt)
 	uint16_t *trace;           // [gridDim.x][cells][ALIGN_THREADS]
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 	unsigned long long my_cells = 0;
 
 	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-		const AlignUnit unit = a.units[u];
+		const AlignUnit unit = unit_of(a.groups, a.ngroups, u);
 		const OligoStrand &os = a.os[unit.os];
 		__syncthreads();
 		if (tid < os.len) s_q[tid] = os.seq[tid];
@@ -620,7 +643,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 	uint32_t cur_os = 0xffffffffu;
 
 	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-		const AlignUnit unit = a.units[u];
+		const AlignUnit unit = unit_of(a.groups, a.ngroups, u);
 		const OligoStrand &os = a.os[unit.os];
 		if (unit.os != cur_os) { // uniform across the block
 			__syncthreads();
