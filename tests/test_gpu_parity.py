@@ -329,3 +329,119 @@ def test_refuses_unsupported(engine_lib):
             e.set_assays([Assay(0, "ACGTACGTACGTACGTAC", None, None)])
     finally:
         e.close()
+
+
+def test_repeats_and_forced_multi_pass(engine_lib, oracle, monkeypatch):
+    """Low-complexity / tandem-repeat fragments overflow the seed buckets (estimated for random
+    sequence): the engine has to shrink the pass and retry, and the result must not change.  A tiny
+    candidate budget additionally forces many passes over the tiles."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    monkeypatch.setenv("TNT_CAND_BUDGET_MB", "1")
+    rng = np.random.default_rng(31337)
+    unit = gen.rand_oligo(37, rng)
+    F = unit[3:23]
+    R = gen.revcomp(unit[10:30])
+    frags = []
+    for k in range(3):
+        codes = gen.random_codes(60000, rng)
+        gen.plant(codes, 5000, unit * 400)            # 14.8 kb tandem repeat holding both primer sites
+        gen.plant(codes, 30000, "A" * 3000)
+        gen.plant(codes, 40000, gen.mutate(unit * 30, 25, rng))
+        frags.append(codes)
+    o = H.default_options(min_primer_tm=45.0, max_len=300)
+    e = Engine()
+    try:
+        for c in frags:
+            e.add_target(c)
+        assays = [(F, R, None), ("A" * 20, "T" * 20, None), (gen.rand_oligo(20, rng), gen.rand_oligo(22, rng), None)]
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        got = e.search(to_opts(o))
+        total = 0
+        for t, codes in enumerate(frags):
+            for i, a in enumerate(assays):
+                want = oracle.search(codes, a[0], a[1], a[2], o)
+                mine = [h for h in got if h.target_id == t and h.assay_index == i]
+                assert_hits_equal(e, mine, want, a)
+                total += len(want)
+        assert total > 100
+    finally:
+        e.close()
+
+
+def test_config3_like_degenerate_probes(eng, oracle):
+    """BASELINE config 3 in miniature: 30-mer probes with one inosine and one two-fold IUPAC code,
+    enumerated to two oligos with degeneracy 2 (expand_degenerate_signatures keeps the inosine,
+    degenerate_na.cpp:94-96), against a target with IUPAC codes and N runs, both strands."""
+    from thermonucleotideblast_b200 import Assay
+    rng = np.random.default_rng(333)
+    two_fold = {"R": "AG", "Y": "CT", "M": "AC", "K": "GT", "S": "CG", "W": "AT"}
+    total = 0
+    for it in range(4):
+        codes = gen.random_codes(80000, rng)
+        base = gen.rand_oligo(30, rng)
+        code = "RYMKSW"[int(rng.integers(0, 6))]
+        pi, pd = sorted(rng.choice(np.arange(8, 22), size=2, replace=False).tolist())
+        variants = []
+        for alt in two_fold[code]:
+            o = list(base)
+            o[pi] = "I"
+            o[pd] = alt
+            variants.append("".join(o))
+        for k in range(6):
+            site = list(base)
+            site[pd] = two_fold[code][k % 2]
+            gen.plant(codes, 3000 + 9000 * k, gen.mutate(gen.revcomp("".join(site)) if k % 2 else "".join(site), k % 3, rng))
+        gen.sprinkle_degenerate(codes, rng, frac=1e-3, n_runs_per_50kb=1)
+        o = H.default_options(assay_format=H.ASSAY_PROBE, min_probe_tm=50.0)
+        eng.clear_targets()
+        eng.add_target(codes)
+        eng.set_assays([Assay(i, None, None, v, probe_degen=2) for i, v in enumerate(variants)])
+        got = eng.search(to_opts(o))
+        for i, v in enumerate(variants):
+            want = oracle.search(codes, None, None, v, o, degen=(1, 1, 2))
+            mine = [h for h in got if h.assay_index == i]
+            assert_hits_equal(eng, mine, want, (None, None, v))
+            total += len(want)
+    assert total >= 8
+
+
+def test_full_size_properties(eng):
+    """Size-independent properties at a larger scale (50 Mbp x 20 TaqMan assays): every exactly
+    planted amplicon is reported with zero mismatches, searching twice gives identical hits, and
+    the hit set of a fragment does not depend on which other fragments are resident."""
+    from thermonucleotideblast_b200 import Assay, search_options
+    rng = np.random.default_rng(5150)
+    frags = [gen.random_codes(500000, rng) for _ in range(100)]
+    assays = []
+    planted = []
+    for a in range(20):
+        F, R, P = gen.rand_oligo(20, rng), gen.rand_oligo(21, rng), gen.rand_oligo(25, rng)
+        t = int(rng.integers(0, len(frags)))
+        pos = int(rng.integers(1000, 400000))
+        text = F + gen.rand_oligo(15, rng) + P + gen.rand_oligo(150, rng) + gen.revcomp(R)
+        gen.plant(frags[t], pos, text)
+        assays.append((F, R, P))
+        planted.append((a, t, pos, pos + len(text) - 1))
+    opts = search_options(min_primer_tm=45.0, min_probe_tm=50.0)
+    eng.clear_targets()
+    for c in frags:
+        eng.add_target(c)
+    eng.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+    hits1 = eng.search(opts)
+    key = lambda h: (h.target_id, h.assay_index, h.amp_first, h.amp_last, h.probe_first, h.probe_last, h.forward_align, h.reverse_align, h.probe_align, h.forward.tm, h.reverse.tm, h.probe.tm)
+    for (a, t, lo, hi) in planted:
+        mine = [h for h in hits1 if h.assay_index == a and h.target_id == t and h.amp_first == lo and h.amp_last == hi]
+        # (a probe may bind a second, partial site inside the same amplicon: at least one exact hit)
+        assert any(h.forward.num_mm == 0 and h.reverse.num_mm == 0 and h.probe.num_mm == 0 for h in mine), (a, t)
+    hits2 = eng.search(opts)
+    assert [key(h) for h in hits1] == [key(h) for h in hits2]
+    # a subset of the fragments, registered alone, yields the same hits for those fragments
+    sub = sorted({t for (_, t, _, _) in planted})[:5]
+    eng.clear_targets()
+    for t in sub:
+        eng.add_target(frags[t])
+    hits3 = eng.search(opts)
+    for new_id, t in enumerate(sub):
+        a = [key(h)[1:] for h in hits1 if h.target_id == t]
+        b = [key(h)[1:] for h in hits3 if h.target_id == new_id]
+        assert a == b

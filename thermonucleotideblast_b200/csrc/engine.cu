@@ -716,7 +716,8 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 	const double keys = (double)set.nkeys;
 	// expected candidates per base of database for the busiest oligo strand
 	const double per_base = (double)set.max_words/keys;
-	const size_t budget_bytes = (size_t)4 << 30; // candidate buckets per pass (HBM is plentiful)
+	size_t budget_bytes = (size_t)4 << 30; // candidate buckets per pass (HBM is plentiful)
+	if (const char *mb = std::getenv("TNT_CAND_BUDGET_MB")) budget_bytes = (size_t)std::max(1L, std::atol(mb)) << 20; // test hook: force many passes
 	const size_t cap_budget = std::max<size_t>(budget_bytes/sizeof(Candidate)/nos, 4096);
 	uint32_t tiles_per_chunk = (uint32_t)e->tiles.size();
 	{
@@ -733,10 +734,12 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 	uint32_t t0 = 0;
 	while (t0 < e->tiles.size()) {
 		uint32_t t1 = (uint32_t)std::min<size_t>(e->tiles.size(), (size_t)t0 + tiles_per_chunk);
+		uint32_t forced_cap = 0; // set after an overflow, when the real bucket sizes are known
 		for (;;) {
 			const uint32_t ntiles = t1 - t0;
 			uint32_t cap = (uint32_t)std::min<double>(4.0e9, 2.0*per_base*SCAN_TILE*ntiles + 2048.0);
-			cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(cap_budget, 4096)*(ntiles == 1 ? 64 : 1));
+			cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(cap_budget, 4096));
+			if (forced_cap) cap = forced_cap;
 			e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
 			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 			ScanArgs a = scan_args(e, set, cap);
@@ -749,7 +752,8 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 			CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
 			e->stats.kernel_launches++;
 			const uint64_t seeds_before = e->stats.seeds;
-			const bool ok = align_buckets(e, set, cap, os_base, false);
+			std::vector<uint32_t> counts;
+			const bool ok = align_buckets(e, set, cap, os_base, false, &counts);
 			float ms = 0;
 			CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
 			e->stats.scan_ms += ms;
@@ -760,8 +764,14 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 				e->stats.scan_bytes += bases/4 + bases/8 + (e->stats.seeds - seeds_before)*sizeof(Candidate);
 				break;
 			}
-			if (ntiles == 1) throw std::runtime_error("seed bucket overflow on a single tile (pathological repeat content)");
-			t1 = t0 + std::max<uint32_t>(1, ntiles/2); // shrink the chunk and retry
+			// A bucket overflowed (repeats, low-complexity sequence): the counters kept counting, so
+			// the true sizes are known.  Re-run the pass with exact capacity if that fits the
+			// budget, otherwise halve the pass; a single tile always gets what it needs.
+			uint32_t need = 0;
+			for (uint32_t c : counts) need = std::max(need, c);
+			need += need/16 + 64;
+			if (ntiles == 1 || (size_t)need*nos*sizeof(Candidate) <= std::max<size_t>(budget_bytes, (size_t)256 << 20)) forced_cap = need;
+			else { t1 = t0 + std::max<uint32_t>(1, ntiles/2); forced_cap = 0; }
 		}
 		t0 = t1;
 	}
@@ -795,13 +805,15 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 		CUDA_OK(cudaGetLastError());
 		CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
 		e->stats.kernel_launches++;
-		const bool ok = align_buckets(e, set, cap, os_base, false);
+		std::vector<uint32_t> counts;
+		const bool ok = align_buckets(e, set, cap, os_base, false, &counts);
 		float ms = 0;
 		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
 		e->stats.scan_ms += ms;
 		if (ok) return;
-		if (cap >= (1u << 30)) throw std::runtime_error("stage-2 seed buckets overflow");
-		cap *= 2;
+		uint32_t need = 0;
+		for (uint32_t c : counts) need = std::max(need, c);
+		cap = need + need/16 + 64; // exact sizes are known after the overflow
 	}
 }
 
