@@ -451,3 +451,51 @@ def test_full_size_properties(eng, oracle):
         a = [key(h)[1:] for h in hits1 if h.target_id == t]
         b = [key(h)[1:] for h in hits3 if h.target_id == new_id]
         assert a == b
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse"])
+def test_seeds_both_scan_kernels(eng, oracle, monkeypatch, mode):
+    """k_seed_scan (dense tables) and k_seed_scan_sparse (grouped pre-filter) give the same seeds."""
+    monkeypatch.setenv("TNT_SCAN_MODE", mode)
+    rng = np.random.default_rng(808)
+    eng.clear_targets()
+    frags = [gen.random_codes(n, rng) for n in (300000, 131072, 131073, 131072 + 70, 64, 7, 200001)]
+    gen.sprinkle_degenerate(frags[0], rng, frac=1e-3, n_runs_per_50kb=5)
+    ol = gen.rand_oligo(22, rng)
+    for f in frags:
+        if len(f) > 100:
+            gen.plant(f, len(f) - 22, ol)                     # site ending on the last base
+            gen.plant(f, 0, gen.revcomp(ol))                  # site on the first base
+    gen.plant(frags[0], 131072 - 10, ol)                      # straddles a sparse tile boundary
+    gen.plant(frags[0], 8192 - 5, gen.revcomp(ol))            # straddles a dense tile boundary
+    ids = [eng.add_target(c) for c in frags]
+    total = 0
+    for tid, codes in zip(ids, frags):
+        for o in (ol, "ACGTACGTAC", gen.rand_oligo(30, rng)):
+            for plus in (False, True):
+                want = oracle.seeds(codes, o, 7, plus, unique=True)
+                assert eng.seeds(tid, o, plus) == want, (mode, tid, o, plus)
+                total += len(want)
+    assert total > 300
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse"])
+def test_search_both_scan_kernels(engine_lib, oracle, monkeypatch, mode):
+    from thermonucleotideblast_b200 import Assay, Engine
+    monkeypatch.setenv("TNT_SCAN_MODE", mode)
+    rng = np.random.default_rng(909)
+    db = [gen.random_codes(int(rng.integers(100000, 300000)), rng) for _ in range(3)]
+    assays = gen.make_assays(rng, db, 4, "pcr", variants=3)
+    o = H.default_options(min_primer_tm=42.0)
+    e = Engine()
+    try:
+        for c in db:
+            e.add_target(c)
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        got = e.search(to_opts(o))
+        for t, codes in enumerate(db):
+            for i, a in enumerate(assays):
+                want = oracle.search(codes, a[0], a[1], a[2], o)
+                assert_hits_equal(e, [h for h in got if h.target_id == t and h.assay_index == i], want, a)
+    finally:
+        e.close()

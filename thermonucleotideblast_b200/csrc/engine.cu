@@ -104,6 +104,8 @@ struct OsSet {
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
 	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
 	std::vector<uint32_t> row_tab_off;
+	DevBuf<uint32_t> d_group_present;   // sparse scan: bitmap over (W+G-1)-mers
+	int group_G = 0;                    // 0: dense scan kernel
 	std::vector<uint8_t> fast_ok;       // best possible DP score fits the fast kernel's packed maximum
 	DevBuf<int32_t> d_row_tab;
 	DevBuf<uint32_t> d_row_tab_off;
@@ -157,7 +159,7 @@ struct tnt_engine {
 	std::vector<Target> targets;
 	DevBuf<Target> d_targets;
 	bool targets_dirty = true;
-	std::vector<ScanTile> tiles;
+	std::vector<ScanTile> tiles;      // SCAN_TILE-sized
 	DevBuf<ScanTile> d_tiles;
 
 	uint8_t *h_stage[2] = {nullptr, nullptr};
@@ -460,6 +462,23 @@ void finish_set(tnt_engine *e, OsSet &set)
 	set.d_present.upload(set.present, e->stream);
 	set.d_offset.upload(set.offset, e->stream);
 	set.d_entry.upload(set.entry, e->stream);
+
+	// Few words in the table -> most positions miss -> grouped pre-filter scan (k_seed_scan_sparse)
+	{
+		const int G = std::max(1, std::min(4, 11 - W));
+		uint64_t distinct = 0;
+		for (uint32_t k = 0; k < set.nkeys; ++k) distinct += set.offset[k + 1] > set.offset[k];
+		bool sparse = (double)distinct*G/(double)set.nkeys < 0.30;
+		if (const char *m = std::getenv("TNT_SCAN_MODE")) sparse = std::strcmp(m, "sparse") == 0 ? true : (std::strcmp(m, "dense") == 0 ? false : sparse);
+		set.group_G = 0;
+		if (sparse && set.total_words) {
+			const uint32_t nkeys2 = 1u << (2*(W + G - 1));
+			set.d_group_present.reserve(nkeys2/32, 0, e->stream);
+			k_build_group_bitmap<<<std::min<uint32_t>(nkeys2/256, 4096u), 256, 0, e->stream>>>(set.d_present.p, set.nkeys - 1, G, nkeys2, set.d_group_present.p);
+			CUDA_OK(cudaGetLastError());
+			set.group_G = G;
+		}
+	}
 }
 
 ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
@@ -478,6 +497,54 @@ ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
 	a.cand_count = e->d_cand_count.p;
 	a.cap = cap;
 	return a;
+}
+
+// Which seed-scan kernel serves this set, and over which tile list
+struct ScanPlan {
+	bool sparse;
+	uint32_t tile_bases;
+	const std::vector<ScanTile> *tiles;
+};
+
+ScanPlan scan_plan(tnt_engine *e, const OsSet &set)
+{
+	ScanPlan p;
+	p.sparse = set.group_G > 0;
+	p.tile_bases = (uint32_t)SCAN_TILE; // both kernels walk the same 8192-base tiles
+	p.tiles = &e->tiles;
+	return p;
+}
+
+// Scan tiles [t0, t1) of the plan's tile list into the candidate buckets (a.cap, a.cand set by the caller)
+void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1)
+{
+	const ScanPlan plan = scan_plan(e, set);
+	const uint32_t ntiles = t1 - t0;
+	if (plan.sparse) {
+		SparseScanArgs sa{};
+		sa.s = a;
+		sa.group_present = set.d_group_present.p;
+		sa.G = set.group_G;
+		sa.s.tiles = e->d_tiles.p;
+		sa.s.tile_begin = t0;
+		sa.s.tile_end = t1;
+		const size_t smem = ((size_t)1 << (2*(e->prm.word_size + set.group_G - 1)))/8 + ((set.nkeys + 31)/32)*sizeof(uint32_t);
+		static size_t sparse_attr = 0; // the opt-in is sticky per function: set it only when it has to grow
+		if (smem > sparse_attr) { CUDA_OK(cudaFuncSetAttribute(k_seed_scan_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); sparse_attr = smem; }
+		const uint32_t grid = std::min<uint32_t>((ntiles + SPARSE_THREADS/32 - 1)/(SPARSE_THREADS/32), (uint32_t)e->sm_count);
+		k_seed_scan_sparse<<<grid, SPARSE_THREADS, smem, e->stream>>>(sa);
+	}
+	else {
+		a.tiles = e->d_tiles.p;
+		a.tile_begin = t0;
+		a.tile_end = t1;
+		const size_t smem = ((set.nkeys + 31)/32)*sizeof(uint32_t);
+		static size_t dense_attr = 0;
+		if (smem > dense_attr) { CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); dense_attr = smem; }
+		const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)e->sm_count*8u);
+		k_seed_scan<<<grid, SCAN_THREADS, smem, e->stream>>>(a);
+	}
+	CUDA_OK(cudaGetLastError());
 }
 
 // Oligo length classes of the fast kernel (rows held in registers)
@@ -711,7 +778,9 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 // Stage A+B over all fragments for one oligo-strand set, chunked so the candidate buckets fit.
 void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 {
-	if (set.os.empty() || e->tiles.empty()) return;
+	const ScanPlan plan = scan_plan(e, set);
+	const std::vector<ScanTile> &tiles = *plan.tiles;
+	if (set.os.empty() || tiles.empty()) return;
 	const size_t nos = set.os.size();
 	const double keys = (double)set.nkeys;
 	// expected candidates per base of database for the busiest oligo strand
@@ -719,36 +788,29 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 	size_t budget_bytes = (size_t)4 << 30; // candidate buckets per pass (HBM is plentiful)
 	if (const char *mb = std::getenv("TNT_CAND_BUDGET_MB")) budget_bytes = (size_t)std::max(1L, std::atol(mb)) << 20; // test hook: force many passes
 	const size_t cap_budget = std::max<size_t>(budget_bytes/sizeof(Candidate)/nos, 4096);
-	uint32_t tiles_per_chunk = (uint32_t)e->tiles.size();
+	uint32_t tiles_per_chunk = (uint32_t)tiles.size();
 	{
 		// cap = 2 * expected + slack
-		const double exp_per_tile = per_base*SCAN_TILE;
+		const double exp_per_tile = per_base*plan.tile_bases;
 		const double max_tiles = ((double)cap_budget - 2048.0)/(2.0*std::max(exp_per_tile, 1e-9));
 		if (max_tiles < (double)tiles_per_chunk) tiles_per_chunk = (uint32_t)std::max(1.0, max_tiles);
 	}
 
 	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
-	const size_t smem_scan = ((set.nkeys + 31)/32)*sizeof(uint32_t);
-	CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
 
 	uint32_t t0 = 0;
-	while (t0 < e->tiles.size()) {
-		uint32_t t1 = (uint32_t)std::min<size_t>(e->tiles.size(), (size_t)t0 + tiles_per_chunk);
+	while (t0 < tiles.size()) {
+		uint32_t t1 = (uint32_t)std::min<size_t>(tiles.size(), (size_t)t0 + tiles_per_chunk);
 		uint32_t forced_cap = 0; // set after an overflow, when the real bucket sizes are known
 		for (;;) {
 			const uint32_t ntiles = t1 - t0;
-			uint32_t cap = (uint32_t)std::min<double>(4.0e9, 2.0*per_base*SCAN_TILE*ntiles + 2048.0);
+			uint32_t cap = (uint32_t)std::min<double>(4.0e9, 2.0*per_base*plan.tile_bases*ntiles + 2048.0);
 			cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(cap_budget, 4096));
 			if (forced_cap) cap = forced_cap;
 			e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
 			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
-			ScanArgs a = scan_args(e, set, cap);
-			a.tile_begin = t0;
-			a.tile_end = t1;
-			const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)e->sm_count*8u);
 			CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
-			k_seed_scan<<<grid, SCAN_THREADS, smem_scan, e->stream>>>(a);
-			CUDA_OK(cudaGetLastError());
+			launch_scan(e, set, scan_args(e, set, cap), t0, t1);
 			CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
 			e->stats.kernel_launches++;
 			const uint64_t seeds_before = e->stats.seeds;
@@ -760,7 +822,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 			if (ok) {
 				uint64_t bases = 0;
 				for (uint32_t t = t0; t < t1; ++t)
-					bases += std::min<uint32_t>(SCAN_TILE, e->targets[e->tiles[t].target].len - e->tiles[t].start);
+					bases += std::min<uint32_t>(plan.tile_bases, e->targets[tiles[t].target].len - tiles[t].start);
 				e->stats.scan_bytes += bases/4 + bases/8 + (e->stats.seeds - seeds_before)*sizeof(Candidate);
 				break;
 			}
@@ -838,27 +900,14 @@ void fetch_heads(tnt_engine *e, uint32_t from, uint32_t to)
 	}
 }
 
-// ------------------------------------------------------------------------------------------
-// Search
-// ------------------------------------------------------------------------------------------
-void search(tnt_engine *e, const tnt_search_options &o)
+// Oligo-strand sets for the registered assays under the given options: stage 1 = what is scanned
+// over the whole database, stage 2 = what is only searched around bound stage-1 sites (PCR).
+// Rebuilt only when assays or options changed.
+void prepare_sets(tnt_engine *e, const tnt_search_options &o)
 {
-	CUDA_OK(cudaSetDevice(e->prm.device));
-	e->hits.clear();
-	e->arena.clear();
-	e->arena.push_back('\0'); // offset 0 == empty string
-	e->stats = tnt_stats{};
-	e->last_opt = o;
-	e->stats.db_bases = e->total_bases;
-	e->sync_targets();
-	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
-	cudaEvent_t t_begin = e->ev[4], t_end = e->ev[5];
-	CUDA_OK(cudaEventRecord(t_begin, e->stream));
-
 	if (o.assay_format != TNT_ASSAY_PCR && o.assay_format != TNT_ASSAY_PROBE &&
 		o.assay_format != TNT_ASSAY_PADLOCK && o.assay_format != TNT_ASSAY_MIPS)
 		throw std::runtime_error("unsupported assay format");
-
 	const bool reuse_sets = e->set1 && e->set2 && e->set_version == e->assays_version &&
 		std::memcmp(&e->set_opt, &o, sizeof(o)) == 0;
 	if (!reuse_sets) {
@@ -917,6 +966,31 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		e->set_opt = o;
 		e->set_version = e->assays_version;
 	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Search
+// ------------------------------------------------------------------------------------------
+void search(tnt_engine *e, const tnt_search_options &o)
+{
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->hits.clear();
+	e->arena.clear();
+	e->arena.push_back('\0'); // offset 0 == empty string
+	e->stats = tnt_stats{};
+	e->last_opt = o;
+	e->stats.db_bases = e->total_bases;
+	e->sync_targets();
+	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
+	cudaEvent_t t_begin = e->ev[4], t_end = e->ev[5];
+	CUDA_OK(cudaEventRecord(t_begin, e->stream));
+
+	if (o.assay_format != TNT_ASSAY_PCR && o.assay_format != TNT_ASSAY_PROBE &&
+		o.assay_format != TNT_ASSAY_PADLOCK && o.assay_format != TNT_ASSAY_MIPS)
+		throw std::runtime_error("unsupported assay format");
+
+	prepare_sets(e, o);
+	OsSet &stage1 = *e->set1, &stage2 = *e->set2;
 
 	e->n_bound = 0;
 	{ HostTimer t("scan_and_align stage1"); scan_and_align(e, stage1, 0); }
@@ -1269,10 +1343,11 @@ long tnt_engine_seeds(tnt_engine *e, uint32_t target_id, const char *oligo, int3
 		set.os.push_back(make_os(e, 0, TNT_OLIGO_P, plus_strand != 0, oligo, 1.0e-6f, 1.0f, 9999.0f, -9999.0f, 0.0f, 0, 0, o));
 		finish_set(e, set);
 		// tiles of this fragment only
+		const ScanPlan plan = scan_plan(e, set);
 		uint32_t t0 = 0, t1 = 0;
 		bool found = false;
-		for (uint32_t t = 0; t < e->tiles.size(); ++t) {
-			if (e->tiles[t].target != target_id) continue;
+		for (uint32_t t = 0; t < plan.tiles->size(); ++t) {
+			if ((*plan.tiles)[t].target != target_id) continue;
 			if (!found) { t0 = t; found = true; }
 			t1 = t + 1;
 		}
@@ -1282,13 +1357,7 @@ long tnt_engine_seeds(tnt_engine *e, uint32_t target_id, const char *oligo, int3
 			e->d_cand_count.reserve(COUNT_STRIDE, 0, e->stream);
 			e->d_cand.reserve(cap, 0, e->stream);
 			CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, sizeof(uint32_t), e->stream));
-			ScanArgs a = scan_args(e, set, cap);
-			a.tile_begin = t0;
-			a.tile_end = t1;
-			const size_t smem_scan = ((set.nkeys + 31)/32)*sizeof(uint32_t);
-			CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
-			k_seed_scan<<<std::min<uint32_t>(t1 - t0, (uint32_t)e->sm_count*8u), SCAN_THREADS, smem_scan, e->stream>>>(a);
-			CUDA_OK(cudaGetLastError());
+			launch_scan(e, set, scan_args(e, set, cap), t0, t1);
 			uint32_t n = 0;
 			CUDA_OK(cudaMemcpyAsync(&n, e->d_cand_count.p, sizeof(n), cudaMemcpyDeviceToHost, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -1390,8 +1459,31 @@ int tnt_debug_words(const char *oligo, int32_t word_size, int32_t complement, ui
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms)
 {
 	API_BEGIN
-	(void)e; (void)opt; (void)candidates; (void)ms;
-	throw std::runtime_error("tnt_engine_scan_only: not implemented yet");
+	if (!e || !opt) throw std::runtime_error("null argument");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->sync_targets();
+	prepare_sets(e, *opt);
+	OsSet &set = *e->set1;
+	uint64_t total = 0;
+	float t_ms = 0;
+	if (!set.os.empty() && !e->tiles.empty()) {
+		const size_t nos = set.os.size();
+		e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
+		e->d_cand.reserve(1, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
+		const ScanPlan plan = scan_plan(e, set);
+		CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
+		launch_scan(e, set, scan_args(e, set, 0), 0, (uint32_t)plan.tiles->size()); // capacity 0: count, do not store
+		CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
+		std::vector<uint32_t> counts(nos);
+		CUDA_OK(cudaMemcpy2DAsync(counts.data(), sizeof(uint32_t), e->d_cand_count.p, COUNT_STRIDE*sizeof(uint32_t),
+			sizeof(uint32_t), nos, cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		CUDA_OK(cudaEventElapsedTime(&t_ms, e->ev[0], e->ev[1]));
+		for (uint32_t c : counts) total += c;
+	}
+	if (candidates) *candidates = total;
+	if (ms) *ms = t_ms;
 	API_END
 }
 

@@ -236,9 +236,19 @@ __device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ d
 	return true;
 }
 
+// Append to the bucket of `os`.  Lanes of the warp that append to the same bucket in the same step
+// share one atomic (a scan with one or two oligo strands would otherwise serialise on a single
+// counter).
 __device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t os, uint32_t target, uint32_t k, uint32_t t)
 {
-	const uint32_t slot = atomicAdd(a.cand_count + (size_t)os*COUNT_STRIDE, 1u);
+	const unsigned active = __activemask();
+	const unsigned peers = __match_any_sync(active, os);
+	const unsigned lane = threadIdx.x & 31u;
+	const int leader = __ffs(peers) - 1;
+	uint32_t base = 0;
+	if ((int)lane == leader) base = atomicAdd(a.cand_count + (size_t)os*COUNT_STRIDE, (uint32_t)__popc(peers));
+	base = __shfl_sync(peers, base, leader);
+	const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 	if (slot < a.cap) {
 		Candidate c;
 		c.target_k = target | (k << 24);
@@ -320,6 +330,231 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 			}
 		}
 		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Sparse-table variant of the seed scan (few oligo strands: most positions miss).
+//
+// The work per base has to shrink to a couple of instructions for the scan to approach the HBM
+// roofline (0.375 B/base), so positions are tested G at a time: a second bitmap, indexed by the
+// (W+G-1)-mer that covers G consecutive W-mers, says whether any of them is in the table.  Only
+// groups that pass are looked at base by base.  Each thread streams 4 x 64 bases with all loads
+// issued up front (coalesced 16-byte loads, the word that follows a segment comes from the
+// neighbouring lane by shuffle), hit positions go through a small shared-memory queue so that the
+// rare hit path runs converged.
+// ------------------------------------------------------------------------------------------
+constexpr int SPARSE_THREADS = 512;
+constexpr int SPARSE_SEGS = 4;                       // 64-base segments per lane: one warp covers one SCAN_TILE
+constexpr int SPARSE_QUEUE = 256;                    // queued four-base groups per warp
+static_assert(32*SPARSE_SEGS*64 == SCAN_TILE, "a warp scans exactly one tile");
+
+struct SparseScanArgs {
+	ScanArgs s;
+	const uint32_t *group_present;   // bitmap over the 4^(W+G-1) group keys
+	int G;                           // positions per group (1..4)
+};
+
+// one bit per (W+G-1)-mer: does any of its G W-mers occur in the table?
+__global__ void k_build_group_bitmap(const uint32_t *__restrict__ present, uint32_t kmask, int G, uint32_t nkeys2,
+	uint32_t *__restrict__ out)
+{
+	for (uint32_t key = blockIdx.x*blockDim.x + threadIdx.x; key < nkeys2; key += gridDim.x*blockDim.x) {
+		bool any = false;
+		for (int i = 0; i < G; ++i) {
+			const uint32_t k = (key >> (2*i)) & kmask;
+			any |= ((present[k >> 5] >> (k & 31u)) & 1u) != 0;
+		}
+		const uint32_t word = __ballot_sync(0xffffffffu, any);
+		if ((threadIdx.x & 31) == 0) out[key >> 5] = word;
+	}
+}
+
+__device__ __forceinline__ void scan_process_hit(const ScanArgs &a, const Target &tg, uint32_t target, uint32_t p, uint32_t kmask)
+{
+	const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
+	const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
+	for (uint32_t e = e0; e < e1; ++e) {
+		const uint32_t ent = __ldg(a.wt.entry + e);
+		const uint32_t os = ent >> 8, k = ent & 0xffu;
+		if (first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask))
+			emit_candidate(a, os, target, k, p);
+	}
+}
+
+// Warp-cooperative hit handling of the sparse scan.  Lanes that found a table hit are served one
+// after the other; for each (oligo strand, word k) entry the "first on its diagonal" test runs
+// with one earlier word per lane.  Surviving candidates are staged in a per-warp buffer and
+// appended to the global buckets with one atomic per bucket and flush.
+struct StagedCand { uint32_t os, target_k, t; };
+
+__device__ __forceinline__ void sparse_flush(const ScanArgs &a, StagedCand *cbuf, uint32_t &cn)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	__syncwarp();
+	if (lane < cn) {
+		const StagedCand c = cbuf[lane];
+		const unsigned active = __activemask();
+		const unsigned peers = __match_any_sync(active, c.os);
+		const int leader = __ffs(peers) - 1;
+		uint32_t base = 0;
+		if ((int)lane == leader) base = atomicAdd(a.cand_count + (size_t)c.os*COUNT_STRIDE, (uint32_t)__popc(peers));
+		base = __shfl_sync(peers, base, leader);
+		const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+		if (slot < a.cap) {
+			Candidate out;
+			out.target_k = c.target_k;
+			out.t = c.t;
+			a.cand[(size_t)c.os*a.cap + slot] = out;
+		}
+	}
+	__syncwarp();
+	cn = 0;
+}
+
+__device__ __forceinline__ void sparse_process_hits(const ScanArgs &a, const Target &tg, uint32_t target, bool hit, uint32_t p,
+	uint32_t key, uint32_t kmask, StagedCand *cbuf, uint32_t &cn)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	unsigned hm = __ballot_sync(0xffffffffu, hit);
+	while (hm) {
+		const int src = __ffs(hm) - 1;
+		hm &= hm - 1;
+		const uint32_t pp = __shfl_sync(0xffffffffu, p, src);
+		const uint32_t kk_key = __shfl_sync(0xffffffffu, key, src);
+		const uint32_t e0 = __ldg(a.wt.offset + kk_key), e1 = __ldg(a.wt.offset + kk_key + 1);
+		for (uint32_t e = e0; e < e1; ++e) {
+			const uint32_t ent = __ldg(a.wt.entry + e);
+			const uint32_t os = ent >> 8, k = ent & 0xffu;
+			const uint16_t *__restrict__ keys = a.os_keys + (size_t)os*MAX_OLIGO;
+			bool earlier = false;
+			for (uint32_t kk = lane; kk < k; kk += 32) {
+				const uint32_t back = k - kk;
+				if (pp >= back) earlier |= kmer_at(a.db.db2, tg.base + pp - back, kmask) == keys[kk];
+			}
+			if (!__any_sync(0xffffffffu, earlier)) {
+				if (cn == 32) sparse_flush(a, cbuf, cn);
+				if (lane == 0) { cbuf[cn].os = os; cbuf[cn].target_k = target | (k << 24); cbuf[cn].t = pp; }
+				++cn;
+			}
+		}
+	}
+}
+
+// Warps work independently (own tiles, own queue, no block-wide barrier after the bitmaps are
+// staged), so loads, filtering and the rare hit processing of different warps overlap.
+__global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanArgs sa)
+{
+	extern __shared__ uint32_t s_dyn[];       // [group bitmap | W-mer bitmap]
+	__shared__ uint32_t s_queue[SPARSE_THREADS/32][SPARSE_QUEUE];
+	__shared__ uint32_t s_qn[SPARSE_THREADS/32];
+	__shared__ StagedCand s_cbuf[SPARSE_THREADS/32][32];
+	const ScanArgs &a = sa.s;
+	const uint32_t kmask = a.wt.nkeys - 1;
+	const int gbits = 2*(a.W + sa.G - 1);
+	const uint32_t nkeys2 = 1u << gbits;
+	uint32_t *s_group = s_dyn;
+	uint32_t *s_present = s_dyn + nkeys2/32;
+	for (uint32_t i = threadIdx.x; i < nkeys2/32; i += SPARSE_THREADS) s_group[i] = sa.group_present[i];
+	for (uint32_t i = threadIdx.x; i < (a.wt.nkeys + 31)/32; i += SPARSE_THREADS) s_present[i] = a.wt.present[i];
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	if (lane == 0) s_qn[warp] = 0;
+	__syncthreads();
+
+	const uint32_t gmask = nkeys2 - 1;
+	const int G = sa.G;
+	uint32_t *queue = s_queue[warp];
+	StagedCand *cbuf = s_cbuf[warp];
+	uint32_t cn = 0; // staged candidates (warp-uniform)
+	const uint32_t nwarps = gridDim.x*(SPARSE_THREADS/32);
+
+	for (uint32_t tile = a.tile_begin + blockIdx.x*(SPARSE_THREADS/32) + warp; tile < a.tile_end; tile += nwarps) {
+		const ScanTile tl = a.tiles[tile];
+		const Target tg = a.db.targets[tl.target];
+		const uint64_t w0 = (tg.base + tl.start) >> 5;         // first 32-base word of the tile (64-base aligned)
+		const bool any_valid = tg.len >= (uint32_t)a.W;
+		const uint32_t last_valid = any_valid ? tg.len - (uint32_t)a.W : 0u; // last position with a whole W-mer
+
+		bool overflow = false;
+		// all loads first: segment sgi of this lane = bases [ (sgi*32 + lane)*64, +64 ) of the tile
+		uint4 seg[SPARSE_SEGS];
+#pragma unroll
+		for (int sgi = 0; sgi < SPARSE_SEGS; ++sgi) {
+			const uint32_t segbase = tl.start + (uint32_t)(sgi*32 + lane)*64u;
+			if (segbase < tg.len) seg[sgi] = __ldg(reinterpret_cast<const uint4 *>(a.db.db2 + w0) + (sgi*32 + lane));
+			else seg[sgi] = make_uint4(0, 0, 0, 0);
+		}
+#pragma unroll
+		for (int sgi = 0; sgi < SPARSE_SEGS; ++sgi) {
+			const uint32_t segbase = tl.start + (uint32_t)(sgi*32 + lane)*64u;
+			const uint64_t lo = (uint64_t)seg[sgi].x | ((uint64_t)seg[sgi].y << 32);
+			const uint64_t hi = (uint64_t)seg[sgi].z | ((uint64_t)seg[sgi].w << 32);
+			// the 32 bases after the segment: first word of the next lane's segment
+			uint64_t nx = __shfl_down_sync(0xffffffffu, lo, 1);
+			if (lane == 31) nx = (segbase < tg.len) ? __ldg(a.db.db2 + w0 + (uint64_t)(sgi*32 + lane)*2u + 2u) : 0ull;
+			// branch-free pass over the 16 four-base groups: one bit per (sub)group that may hold a hit
+			uint32_t gm = 0;
+#pragma unroll
+			for (int g = 0; g < 16; ++g) {
+				const int bit = 8*g;
+				uint64_t x;
+				if (bit < 64) x = bit ? ((lo >> bit) | (hi << (64 - bit))) : lo;
+				else x = (bit - 64) ? ((hi >> (bit - 64)) | (nx << (128 - bit))) : hi;
+				if (G == 4) {
+					const uint32_t gkey = (uint32_t)x & gmask;
+					gm |= ((s_group[gkey >> 5] >> (gkey & 31u)) & 1u) << (2*g);
+				}
+				else { // two sub-groups per four bases (W = 8: G = 3 -> positions 0..2 and 3; smaller G: conservative)
+					const uint32_t k0 = (uint32_t)x & gmask, k1 = (uint32_t)(x >> (2*G)) & gmask;
+					gm |= ((s_group[k0 >> 5] >> (k0 & 31u)) & 1u) << (2*g);
+					gm |= ((s_group[k1 >> 5] >> (k1 & 31u)) & 1u) << (2*g + 1);
+				}
+			}
+			if (segbase >= tg.len || !any_valid) gm = 0;
+			// rare: queue the four-base groups that passed (phase 2 looks at the bases one by one)
+			while (gm) {
+				const int grp = (__ffs(gm) - 1) >> 1;
+				gm &= ~(3u << (2*grp)); // one queue entry per four-base group
+				const uint32_t slot = atomicAdd(&s_qn[warp], 1u);
+				if (slot < SPARSE_QUEUE) queue[slot] = segbase + (uint32_t)(4*grp);
+				else overflow = true;
+			}
+		}
+		__syncwarp();
+		if (__any_sync(0xffffffffu, overflow)) {
+			// more groups passed the pre-filter than the queue holds (dense table / repeats): redo
+			// this tile base by base, one position per lane
+			for (uint32_t p = tl.start + lane; p < min(tl.start + (uint32_t)SCAN_TILE, tg.len); p += 32) {
+				bool hit = false;
+				uint32_t key = 0;
+				if (any_valid && p <= last_valid) {
+					key = kmer_at(a.db.db2, tg.base + p, kmask);
+					hit = ((s_present[key >> 5] >> (key & 31u)) & 1u) != 0;
+				}
+				sparse_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
+			}
+		}
+		else {
+			// phase 2: eight queued groups at a time, one position per lane
+			const uint32_t total = s_qn[warp];
+			for (uint32_t base = 0; base < total; base += 8) {
+				const uint32_t q = base + (lane >> 2);
+				bool hit = false;
+				uint32_t p = 0, key = 0;
+				if (q < total) {
+					p = queue[q] + (lane & 3u);
+					if (p <= last_valid) {
+						key = kmer_at(a.db.db2, tg.base + p, kmask);
+						hit = ((s_present[key >> 5] >> (key & 31u)) & 1u) != 0;
+					}
+				}
+				sparse_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
+			}
+		}
+		sparse_flush(a, cbuf, cn); // per tile: keeps the buffer logic simple
+		__syncwarp();
+		if (lane == 0) s_qn[warp] = 0;
+		__syncwarp();
 	}
 }
 

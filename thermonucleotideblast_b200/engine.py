@@ -272,6 +272,13 @@ class Engine:
         self.L.tnt_engine_hit_sequence(self.h, C.byref(raw), buf, n + 1)
         return buf.value.decode()
 
+    def scan_only(self, opts: SearchOptions):
+        """Seed scan of all fragments with the stage-1 oligo strands; returns (candidates, ms)."""
+        n = C.c_uint64()
+        ms = C.c_double()
+        self._check(self.L.tnt_engine_scan_only(self.h, C.byref(opts), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
     # -- stage-level entry points ------------------------------------------------------------
     def seeds(self, target_id: int, oligo: str, plus: bool) -> List[Tuple[int, int]]:
         cap = 1 << 16
