@@ -34,6 +34,7 @@ constexpr unsigned TW_M_ZERO = 1u << 8;
 constexpr unsigned TW_IQ_NEG = 1u << 9;
 constexpr unsigned TW_IT_NEG = 1u << 10;
 constexpr unsigned TW_CAND = 1u << 11;   // M >= running maximum when the cell was computed
+constexpr unsigned TW_UNCLEAN = 1u << 12; // lean trace only: not "the diagonal predecessor alone gives the maximum"
 // word of a never-written cell (row 0 / column 0 of the reference matrix, nuc_cruc.h:531-536)
 constexpr unsigned TW_BORDER = TW_M_NEG | TW_IQ_NEG | TW_IT_NEG;
 
@@ -177,6 +178,8 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 template <int NT>
 struct RowMajorTrace {
 	static constexpr bool kHasGapStates = true;
+	static constexpr bool kCleanOnly = false;
+	__device__ __forceinline__ void begin_path() const {}
 	const uint16_t *trace;
 	int Lt;
 	__device__ __forceinline__ unsigned get(int i, int j) const { return trace[(size_t)((i - 1)*Lt + (j - 1))*NT]; }
@@ -210,6 +213,7 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 
 	unsigned cur_id = 0;        // 0 == the static first_match byte of the reference
 	unsigned cur_mask = T_DIAG;
+	tv.begin_path();
 
 	for (;;) {
 		bool valid = true;
@@ -245,6 +249,8 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 				else flags |= F_TRUNC;
 				a.lm_q = Lq - last_i;
 				a.lm_t = last_j - 1;
+				// lean trace: the path may only go on through "diagonal alone is the maximum" cells
+				if (TV::kCleanOnly && valid && (w & TW_UNCLEAN)) { flags |= F_NEEDGENERIC; return; }
 				cur_id = (unsigned)(cell + 1)*3u + 0u;
 				cur_mask = inside ? (w & 7u) : T_INVALID;
 				--last_i;
@@ -614,36 +620,33 @@ constexpr int ROW_P1 = 0, ROW_P2 = 20, ROW_P4 = 40, ROW_P3 = 60, ROW_P6 = 64, RO
 constexpr int32_t ROW_PAD_PENALTY = 1 << 28;
 constexpr int MAX_MAXCELLS = 64;
 
-// Trace byte of the fast fill (one per cell, four rows per 32-bit word, first row in the top byte):
-//   bit7 d1!=M   bit4 d2!=M   bit3 d3!=M   bit2 M<0   bit1 M>0   bit0 M below the running maximum
-// (bits 6,5 are filler).  The gap states keep no trace: an optimal path that wants to enter one is
-// handed to the generic kernel (F_NEEDGENERIC) -- gaps cost >= 2 kcal/mol to open, so this is rare.
+// ------------------------------------------------------------------------------------------
+// Lean tier of the fast fill: what nearly every window needs and nothing more.
+//
+// A traceback that never leaves the match state only needs, per cell, (a) "the diagonal
+// predecessor alone gives the maximum" and (b) "M < 0"; the value of M along such a path can be
+// rebuilt backwards from the maximal score, because there M(i,j) = max(M(i-1,j-1), 0) - P1(i,j).
+// So the trace shrinks to two bits per cell (16 rows per 32-bit store).  Anything else -- a tie
+// or a gap state on the optimal path, several cells tied for the maximum -- hands the candidate
+// to the full-trace tier below.
+//
+// The gap penalties of the reference's table have structure (update_dp_param,
+// nuc_cruc.cpp:340-487: a gap pair next to a real pair costs a "terminal" penalty that depends on
+// the real pair only; gap next to gap costs the bulge constant).  For rows >= 2 and columns >= 2
+//   M from I_query  ==  M from I_target  ==: V(row, tb)
+//   I_target from M (row)  ==  V(row - 1, tb)
+//   I_target from I_target  ==  one constant
+// which the host *verifies* per oligo strand on the actual table (lean_tables_ok, thermo.cpp);
+// an oligo for which any identity fails goes to the full-trace tier.  Row 1 and column 1 (GAP
+// neighbours) use their own entries.  Per cell that leaves three 32-bit shared-memory words
+// (P1 and P4 as one 64-bit load, V) instead of six.
+// ------------------------------------------------------------------------------------------
+constexpr int LEAN_WORDS = 64;     // {P1,P4}[20] V[4] P2c1[4] P3[4] P6[4] P7 pad[7]
+constexpr int LEAN_T = 0, LEAN_V = 40, LEAN_P2C1 = 44, LEAN_P3 = 48, LEAN_P6 = 52, LEAN_P7 = 56;
+
 struct FastDp {
 	unsigned runkey;   // (max(M,0) << 12) | (4095 - sweep index of its first occurrence)
 	unsigned lastkey;  // (max(M,0) << 12) | sweep index of its last occurrence
-};
-
-template <int LQ, int NT>
-struct ColMajorTrace {
-	static constexpr bool kHasGapStates = false;
-	const uint32_t *trace32;
-	__device__ __forceinline__ unsigned raw(int i, int j) const
-	{
-		const uint32_t w = trace32[(size_t)((j - 1)*(LQ/4) + ((i - 1) >> 2))*NT];
-		return (w >> (8*(3 - ((i - 1) & 3)))) & 0xffu;
-	}
-	__device__ __forceinline__ unsigned get(int i, int j) const
-	{
-		const unsigned r = raw(i, j);
-		unsigned w = 0;
-		if (!(r & 0x80u)) w |= T_DIAG;
-		if (!(r & 0x10u)) w |= T_LEFT;
-		if (!(r & 0x08u)) w |= T_UP;
-		if (r & 0x04u) w |= TW_M_NEG;
-		else if (!(r & 0x02u)) w |= TW_M_ZERO;
-		if (!(r & 0x01u)) w |= TW_CAND;
-		return w;
-	}
 };
 
 // target base j (0-based, NucCruc orientation) from the 2-bit packed window
@@ -652,65 +655,106 @@ __device__ __forceinline__ int packed_base(uint64_t lo, uint64_t hi, int j)
 	return (int)(((j < 32) ? (lo >> (2*j)) : (hi >> (2*(j - 32)))) & 3u);
 }
 
+template <int LQ>
+struct LeanGeom {
+	static constexpr int kWordsPerCol = (LQ + 15)/16;
+};
+
+// Trace view of the lean fill.  get() must be called once per visited cell, in path order,
+// after begin_path(): it carries the value of M along the diagonal.
 template <int LQ, int NT>
-__device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
+struct ColMajorLean {
+	static constexpr bool kHasGapStates = false;
+	static constexpr bool kCleanOnly = true;
+	const uint32_t *trace32;
+	const int32_t *tab;      // lean rows in shared memory
+	const uint8_t *tgt;
+	int maxscore;
+	mutable int m;
+	__device__ __forceinline__ void begin_path() const { m = maxscore; }
+	__device__ __forceinline__ unsigned get(int i, int j) const
+	{
+		const int g = (i - 1) >> 4, p = (i - 1) & 15;
+		const int n = (LQ - 16*g) < 16 ? (LQ - 16*g) : 16;
+		const uint32_t word = trace32[(size_t)((j - 1)*LeanGeom<LQ>::kWordsPerCol + g)*NT];
+		const unsigned bits = (word >> (2*(n - 1 - p))) & 3u;
+		unsigned w = T_DIAG;
+		if (!(bits & 2u)) w |= TW_UNCLEAN;
+		if (m <= 0) w |= (bits & 1u) ? TW_M_NEG : TW_M_ZERO;
+		const int tb = tgt[j - 1], pt = j >= 2 ? (int)tgt[j - 2] : 4;
+		m = max(m, 0) + tab[(i - 1)*LEAN_WORDS + LEAN_T + 2*(pt*4 + tb)];
+		return w;
+	}
+};
+
+template <int LQ, int NT, bool FIRST>
+__device__ __forceinline__ void lean_column(const int32_t *__restrict__ tab, int tb, int td, int p5, int p7c, unsigned colidx,
+	uint32_t *__restrict__ col, int (&cM)[LQ], int (&cIq)[LQ], int (&cIt)[LQ], unsigned &runkey, unsigned &lastkey)
+{
+	int dM = 0, dIq = 0, dIt = 0; // (i-1, j-1)
+	int uM = 0, uIt = 0;          // (i-1, j)
+	int prevV = 0;
+	unsigned acc = 0;
+#pragma unroll
+	for (int r = 0; r < LQ; ++r) {
+		const int32_t *__restrict__ row = tab + r*LEAN_WORDS;
+		const int oM = cM[r], oIq = cIq[r], oIt = cIt[r]; // (i, j-1)
+		const int2 t14 = *reinterpret_cast<const int2 *>(row + LEAN_T + 2*td);
+		const int d1 = dM - t14.x;
+		int m23, It;
+		if (FIRST || r == 0) {
+			const int p2 = FIRST ? row[LEAN_P2C1 + tb] : row[LEAN_V + tb];
+			m23 = max(dIq - p2, dIt - row[LEAN_P3 + tb]);
+			It = max(uM - row[LEAN_P6 + tb], uIt - row[LEAN_P7]);
+			if (!FIRST) prevV = p2;
+		}
+		else {
+			const int v = row[LEAN_V + tb];
+			m23 = max(dIq, dIt) - v;
+			It = max(uM - prevV, uIt - p7c);
+			prevV = v;
+		}
+		const int M = max(d1, m23);
+		const int Iq = max(oM - t14.y, oIq - p5);
+		const int mM = max(M, 0);
+
+		const unsigned idx = colidx + (unsigned)r;
+		runkey = max(runkey, (unsigned)mM*4096u + (4095u - idx));
+		lastkey = max(lastkey, (unsigned)mM*4096u + idx);
+
+		acc = __funnelshift_l((unsigned)(m23 - d1), acc, 1); // set <=> the diagonal alone is the maximum
+		acc = __funnelshift_l((unsigned)M, acc, 1);
+		if ((r & 15) == 15 || r == LQ - 1) col[(r >> 4)*NT] = acc;
+
+		dM = oM; dIq = oIq; dIt = oIt;
+		cM[r] = mM;
+		cIq[r] = max(Iq, 0);
+		cIt[r] = max(It, 0);
+		uM = mM;
+		uIt = cIt[r];
+	}
+}
+
+template <int LQ, int NT>
+__device__ __forceinline__ FastDp nc_fill_lean(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
 	uint64_t tlo, uint64_t thi, int Lt, uint32_t *__restrict__ trace32)
 {
-	static_assert(LQ % 4 == 0, "four rows share a trace word");
+	static_assert(LQ % 2 == 0 && LQ >= 2, "row classes are even");
+	constexpr int WPC = LeanGeom<LQ>::kWordsPerCol;
 	int cM[LQ], cIq[LQ], cIt[LQ];
 #pragma unroll
 	for (int r = 0; r < LQ; ++r) { cM[r] = 0; cIq[r] = 0; cIt[r] = 0; }
 
-	unsigned runkey = 0;  // nothing positive seen yet
-	unsigned lastkey = 0;
-	int runmax = 0;
-	int pt = 4;           // GAP in front of the first column
-	for (int j = 1; j <= Lt; ++j) {
+	unsigned runkey = 0, lastkey = 0;
+	const int p7c = tab[LEAN_WORDS + LEAN_P7];
+	int pt = packed_base(tlo, thi, 0);
+	// column 1: GAP in front of it
+	lean_column<LQ, NT, true>(tab, pt, 16 + pt, p5tab[16 + pt], p7c, 0u, trace32, cM, cIq, cIt, runkey, lastkey);
+	for (int j = 2; j <= Lt; ++j) {
 		const int tb = packed_base(tlo, thi, j - 1);
 		const int td = pt*4 + tb;
-		const int32_t *__restrict__ ptd = tab + td;
-		const int32_t *__restrict__ ptb = tab + tb;
-		const int p5 = p5tab[td];
-		uint32_t *__restrict__ col = trace32 + (size_t)(j - 1)*(LQ/4)*NT;
-		const unsigned colkey = 4095u - (unsigned)((j - 1)*LQ); // minus r: sweep index of the cell
-
-		int dM = 0, dIq = 0, dIt = 0; // (i-1, j-1)
-		int uM = 0, uIt = 0;          // (i-1, j)
-		unsigned acc = 0;
-#pragma unroll
-		for (int r = 0; r < LQ; ++r) {
-			const int oM = cM[r], oIq = cIq[r], oIt = cIt[r]; // (i, j-1)
-
-			const int d1 = dM - ptd[r*ROW_WORDS + ROW_P1];
-			const int d2 = dIq - ptd[r*ROW_WORDS + ROW_P2];
-			const int d3 = dIt - ptb[r*ROW_WORDS + ROW_P3];
-			const int M = max(max(d1, d2), d3);
-			const int Iq = max(oM - ptd[r*ROW_WORDS + ROW_P4], oIq - p5);
-			const int It = max(uM - ptb[r*ROW_WORDS + ROW_P6], uIt - tab[r*ROW_WORDS + ROW_P7]);
-			const int mM = max(M, 0);
-
-			// running maximum with the position of its first occurrence folded into the low bits
-			// (the host only sends oligos here whose best possible score stays below 2^20)
-			const unsigned below = (unsigned)(mM - runmax);  // sign set <=> max(M,0) < running maximum
-			runmax = max(runmax, mM);
-			runkey = max(runkey, (unsigned)mM*4096u + (colkey - (unsigned)r));
-			lastkey = max(lastkey, (unsigned)mM*4096u + (4095u - colkey + (unsigned)r));
-
-			acc = __funnelshift_l((unsigned)(d1 - M), acc, 3); // sign + 2 filler bits
-			acc = __funnelshift_l((unsigned)(d2 - M), acc, 1);
-			acc = __funnelshift_l((unsigned)(d3 - M), acc, 1);
-			acc = __funnelshift_l((unsigned)M, acc, 1);
-			acc = __funnelshift_l((unsigned)(-M), acc, 1);
-			acc = __funnelshift_l(below, acc, 1);
-			if ((r & 3) == 3) col[(r >> 2)*NT] = acc;
-
-			dM = oM; dIq = oIq; dIt = oIt;
-			cM[r] = mM;
-			cIq[r] = max(Iq, 0);
-			cIt[r] = max(It, 0);
-			uM = mM;
-			uIt = cIt[r];
-		}
+		lean_column<LQ, NT, false>(tab, tb, td, p5tab[td], p7c, (unsigned)((j - 1)*LQ),
+			trace32 + (size_t)(j - 1)*WPC*NT, cM, cIq, cIt, runkey, lastkey);
 		pt = tb;
 	}
 	FastDp res;
@@ -719,41 +763,18 @@ __device__ __forceinline__ FastDp nc_fill_fast(const int32_t *__restrict__ tab, 
 	return res;
 }
 
-// Maximal cells in the reference's (row-major) order from a fast fill.  Returns -1 when the
-// generic kernel has to take over (no positive score anywhere: the reference's ">= -1" rule then
-// decides, which the fast trace does not record).
-template <int LQ, int NT>
-__device__ inline int collect_max_cells_fast(const ColMajorTrace<LQ, NT> &tv, const FastDp &dp, int Lq, int Lt,
-	uint16_t *cells, unsigned &flags)
+// The maximal cell of a lean fill.  Returns 1 (cells[0] set), -1 when no cell is positive (the
+// reference's ">= -1" rule then decides: generic kernel) or -2 when several cells tie for the
+// maximum (full-trace tier).
+template <int LQ>
+__device__ __forceinline__ int lean_max_cell(const FastDp &dp, int Lt, uint16_t *cells)
 {
 	if ((dp.runkey >> 12) == 0) return -1;
 	const int first = 4095 - (int)(dp.runkey & 4095u); // sweep index = (j-1)*LQ + (i-1)
+	if ((int)(dp.lastkey & 4095u) != first) return -2;
 	const int fj = first/LQ + 1, fi = first%LQ + 1;
-	int n = 0;
-	cells[n++] = (uint16_t)((fi - 1)*Lt + (fj - 1));
-	// later cells that tie with the maximum carry a clear "below" bit; scan word-wise
-	(void)Lt;
-	const int last = (int)(dp.lastkey & 4095u);
-	if (last == first) return n; // a single maximal cell: the common case
-	for (int w = first/4; w <= last/4; ++w) {
-		uint32_t word = tv.trace32[(size_t)w*NT];
-		uint32_t cand = ~word & 0x01010101u;
-		while (cand) {
-			const int bit = 31 - __clz(cand);
-			cand &= ~(1u << bit);
-			const int rr = 3 - (bit >> 3);
-			const int idx = w*4 + rr;
-			if (idx <= first) continue;
-			const int j = idx/LQ + 1, i = idx%LQ + 1;
-			if (i > Lq) continue;
-			if (n == MAX_MAXCELLS) { flags |= F_TRUNC; return n; }
-			const uint16_t key = (uint16_t)((i - 1)*Lt + (j - 1));
-			int k = n++;
-			while (k > 0 && cells[k - 1] > key) { cells[k] = cells[k - 1]; --k; }
-			cells[k] = key;
-		}
-	}
-	return n;
+	cells[0] = (uint16_t)((fi - 1)*Lt + (fj - 1));
+	return 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -788,6 +809,8 @@ __device__ __forceinline__ unsigned decode_full_trace(unsigned raw)
 template <int LQ, int NT>
 struct ColMajorTraceFull {
 	static constexpr bool kHasGapStates = true;
+	static constexpr bool kCleanOnly = false;
+	__device__ __forceinline__ void begin_path() const {}
 	const uint32_t *trace32;
 	__device__ __forceinline__ unsigned raw(int i, int j) const
 	{

@@ -103,7 +103,10 @@ struct OsSet {
 	DevBuf<uint16_t> d_keys;
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
 	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
-	std::vector<uint32_t> row_tab_off;
+	std::vector<int32_t> lean_tab;      // lean-tier rows, [sum of len][LEAN_WORDS]
+	std::vector<uint32_t> row_tab_off;  // first row of each oligo strand
+	std::vector<uint8_t> lean_ok;       // the table has the structure the lean tier relies on
+	DevBuf<int32_t> d_lean_tab;
 	DevBuf<uint32_t> d_group_present;   // sparse scan: bitmap over (W+G-1)-mers
 	int group_G = 0;                    // 0: dense scan kernel
 	std::vector<uint8_t> fast_ok;       // best possible DP score fits the fast kernel's packed maximum
@@ -440,12 +443,16 @@ void finish_set(tnt_engine *e, OsSet &set)
 			set.entry[fill[set.keys[s*MAX_OLIGO + k]]++] = (uint32_t)(s << 8) | (uint32_t)k;
 	set.row_tab_off.assign(nos, 0);
 	size_t rows = 0;
-	for (size_t s = 0; s < nos; ++s) { set.row_tab_off[s] = (uint32_t)(rows*ROW_WORDS); rows += (size_t)set.os[s].len; }
+	for (size_t s = 0; s < nos; ++s) { set.row_tab_off[s] = (uint32_t)rows; rows += (size_t)set.os[s].len; }
 	set.row_tab.assign(std::max<size_t>(rows*ROW_WORDS, 1), 0);
+	set.lean_tab.assign(std::max<size_t>(rows*LEAN_WORDS, 1), 0);
 	set.fast_ok.assign(nos, 1);
+	set.lean_ok.assign(nos, 1);
+	const bool no_lean = std::getenv("TNT_NO_LEAN") != nullptr; // test hook: everything through the full-trace tier
 	for (size_t s = 0; s < nos; ++s) {
-		int32_t *rows_s = set.row_tab.data() + set.row_tab_off[s];
+		int32_t *rows_s = set.row_tab.data() + (size_t)set.row_tab_off[s]*ROW_WORDS;
 		build_row_tables(e->h_thermo, set.os[s], rows_s);
+		set.lean_ok[s] = build_lean_tables(rows_s, set.os[s].len, set.lean_tab.data() + (size_t)set.row_tab_off[s]*LEAN_WORDS) && !no_lean;
 		// upper bound of any cell: every row contributes at most its most favourable M-from-M term
 		int64_t bound = 0;
 		for (int r = 0; r < set.os[s].len; ++r) {
@@ -456,6 +463,7 @@ void finish_set(tnt_engine *e, OsSet &set)
 		if (bound >= (1 << 20)) set.fast_ok[s] = 0;
 	}
 	set.d_row_tab.upload(set.row_tab, e->stream);
+	set.d_lean_tab.upload(set.lean_tab, e->stream);
 	set.d_row_tab_off.upload(set.row_tab_off, e->stream);
 	set.d_os.upload(set.os, e->stream);
 	set.d_keys.upload(set.keys, e->stream);
@@ -547,8 +555,11 @@ void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1
 	CUDA_OK(cudaGetLastError());
 }
 
-// Oligo length classes of the fast kernel (rows held in registers)
-const int kFastClasses[] = {20, 24, 28, 32, 40, 56};
+// Oligo length classes of the fast kernels (rows held in registers)
+#define TNT_FAST_CLASSES(X) X(20) X(22) X(24) X(26) X(28) X(32) X(40) X(56)
+#define TNT_CLASS_ENTRY(L) L,
+const int kFastClasses[] = {TNT_FAST_CLASSES(TNT_CLASS_ENTRY)};
+#undef TNT_CLASS_ENTRY
 
 template <int LQ>
 void launch_fast(const AlignArgs &a, uint32_t grid, bool full, cudaStream_t st)
@@ -560,22 +571,31 @@ void launch_fast(const AlignArgs &a, uint32_t grid, bool full, cudaStream_t st)
 template <int LQ>
 int fast_occupancy(bool full)
 {
-	int n = 1;
-	if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, true>, ALIGN_THREADS, 0);
-	else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, 0);
-	return std::max(n, 1);
+	static int cached[2] = {0, 0};
+	int &n = cached[full ? 1 : 0];
+	if (n == 0) {
+		if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, true>, ALIGN_THREADS, 0);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, 0);
+		n = std::max(n, 1);
+	}
+	return n;
 }
 
 int fast_blocks_per_sm(int lq, bool full)
 {
 	switch (lq) {
-	case 20: return fast_occupancy<20>(full);
-	case 24: return fast_occupancy<24>(full);
-	case 28: return fast_occupancy<28>(full);
-	case 32: return fast_occupancy<32>(full);
-	case 40: return fast_occupancy<40>(full);
-	default: return fast_occupancy<56>(full);
+#define TNT_CLASS_CASE(L) case L: return fast_occupancy<L>(full);
+	TNT_FAST_CLASSES(TNT_CLASS_CASE)
+#undef TNT_CLASS_CASE
+	default: throw std::runtime_error("internal: unknown oligo length class");
 	}
+}
+
+// 32-bit trace words per thread of the fast tiers
+uint32_t fast_trace_words(int lq, bool full)
+{
+	const uint32_t cols = (uint32_t)(lq + 2*NUM_FLANK);
+	return full ? cols*(uint32_t)(lq/2) : cols*(uint32_t)((lq + 15)/16);
 }
 
 // Run one alignment kernel (fast class `lq`, or the generic kernel when lq == 0) over `units`,
@@ -603,20 +623,18 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 	}
 	else {
 		grid = (uint32_t)std::min<size_t>(nunits, (size_t)e->sm_count*fast_blocks_per_sm(lq, full));
-		a.trace_cells = (uint32_t)lq*(uint32_t)(lq + 2*NUM_FLANK);
+		a.trace_cells = fast_trace_words(lq, full);
 	}
-	// d_trace counts 16-bit units; the fast kernel stores one byte per cell
-	e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS/((lq == 0 || full) ? 1 : 2) + 64, 0, e->stream);
+	// d_trace counts 16-bit units
+	e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS*(lq == 0 ? 1 : 2) + 64, 0, e->stream);
 	a.trace = e->d_trace.p;
 	CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
 	switch (lq) {
 	case 0: k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a); break;
-	case 20: launch_fast<20>(a, grid, full, e->stream); break;
-	case 24: launch_fast<24>(a, grid, full, e->stream); break;
-	case 28: launch_fast<28>(a, grid, full, e->stream); break;
-	case 32: launch_fast<32>(a, grid, full, e->stream); break;
-	case 40: launch_fast<40>(a, grid, full, e->stream); break;
-	default: launch_fast<56>(a, grid, full, e->stream); break;
+#define TNT_CLASS_CASE(L) case L: launch_fast<L>(a, grid, full, e->stream); break;
+	TNT_FAST_CLASSES(TNT_CLASS_CASE)
+#undef TNT_CLASS_CASE
+	default: throw std::runtime_error("internal: unknown oligo length class");
 	}
 	CUDA_OK(cudaGetLastError());
 	CUDA_OK(cudaEventRecord(e->ev[3], e->stream));
@@ -652,13 +670,19 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 	// units per fast class
 	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));
 	std::vector<std::vector<AlignGroup>> by_class(nclass + 1); // [nclass] = generic kernel
+	std::vector<std::vector<AlignGroup>> by_class_full(nclass); // oligo strands the lean tier cannot take
 	auto class_of = [&](size_t s) {
 		int c = 0;
 		while (c < nclass - 1 && kFastClasses[c] < set.os[s].len) ++c;
 		return set.fast_ok[s] ? c : nclass;
 	};
 	for (size_t s = 0; s < nos; ++s)
-		if (counts[s]) by_class[class_of(s)].push_back(AlignGroup{(uint32_t)s, 0u, counts[s], 0u});
+		if (counts[s]) {
+			const int c = class_of(s);
+			const AlignGroup g{(uint32_t)s, 0u, counts[s], 0u};
+			if (c < nclass && !set.lean_ok[s]) by_class_full[c].push_back(g);
+			else by_class[c].push_back(g);
+		}
 
 	const uint32_t base_count = e->n_bound;
 	size_t out_cap = emit_all ? (size_t)base_count + total : std::max<size_t>(e->d_bound.cap, (size_t)base_count + (1u << 16));
@@ -693,7 +717,8 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		a.slot_map = nullptr;
 		a.cells = e->d_cells.p;
 		a.row_tab = set.d_row_tab.p;
-		a.row_tab_off = set.d_row_tab_off.p;
+		a.lean_tab = set.d_lean_tab.p;
+		a.row_off = set.d_row_tab_off.p;
 		a.p5_tab = e->d_p5.p;
 		a.slow = e->d_slow.p;
 		a.slow_count = e->d_out_count.p + 1;
@@ -704,6 +729,8 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		float ms = 0;
 		for (int c = 0; c < nclass; ++c)
 			if (!by_class[c].empty()) ms += run_align_kernel(e, set, a, by_class[c], kFastClasses[c], set.max_len);
+		for (int c = 0; c < nclass; ++c)
+			if (!by_class_full[c].empty()) ms += run_align_kernel(e, set, a, by_class_full[c], kFastClasses[c], set.max_len, true);
 		if (!by_class[nclass].empty()) ms += run_align_kernel(e, set, a, by_class[nclass], 0, set.max_len);
 
 		uint32_t cnt[3] = {0, 0, 0};

@@ -633,7 +633,7 @@ struct AlignArgs {
 	uint32_t nunits;
 	int max_lt;                // generic kernel: row stride of the shared DP rows (columns 0..max_lt)
 	uint16_t *trace;           // [gridDim.x][cells][ALIGN_THREADS]
-	uint32_t trace_cells;      // generic: 16-bit cells per CTA and thread; fast: 8-bit cells
+	uint32_t trace_cells;      // generic: 16-bit cells per CTA and thread; fast tiers: 32-bit words
 	BoundRec *out;             // filtered mode: appended; all mode: out[slot]
 	uint32_t *out_count;
 	uint32_t out_cap;
@@ -642,8 +642,9 @@ struct AlignArgs {
 	const uint32_t *slot_map;  // optional, emit_all only: output slot per candidate index
 	unsigned long long *cells; // sum of Lq*Lt
 	// fast kernel only
-	const int32_t *row_tab;    // per oligo strand: len rows x ROW_WORDS
-	const uint32_t *row_tab_off;
+	const int32_t *row_tab;    // per oligo strand: len rows x ROW_WORDS (full-trace tier)
+	const int32_t *lean_tab;   // per oligo strand: len rows x LEAN_WORDS (lean tier)
+	const uint32_t *row_off;   // first row of each oligo strand in both tables
 	const int32_t *p5_tab;     // [20]
 	SlowItem *slow;            // -> generic kernel
 	uint32_t *slow_count;
@@ -862,7 +863,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 template <int LQ, bool FULL>
 __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 {
-	__shared__ int32_t s_tab[LQ*ROW_WORDS];
+	constexpr int TAB_WORDS = FULL ? ROW_WORDS : LEAN_WORDS;
+	__shared__ __align__(16) int32_t s_tab[LQ*TAB_WORDS];
 	__shared__ int32_t s_p5[20];
 	__shared__ uint8_t s_bbp[NB*NB];
 	__shared__ uint8_t s_wc[52];
@@ -873,7 +875,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 	for (int i = tid; i < NPAIR; i += ALIGN_THREADS) s_wc[i] = a.thermo->wc[i];
 	if (tid < 20) s_p5[tid] = a.p5_tab[tid];
 
-	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*(a.trace_cells/(FULL ? 2 : 4))*ALIGN_THREADS + tid;
+	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*a.trace_cells*ALIGN_THREADS + tid;
 	unsigned long long my_cells = 0;
 	uint32_t cur_os = 0xffffffffu;
 
@@ -882,9 +884,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 		const OligoStrand &os = a.os[unit.os];
 		if (unit.os != cur_os) { // uniform across the block
 			__syncthreads();
-			const int32_t *src = a.row_tab + a.row_tab_off[unit.os];
-			const int nreal = os.len*ROW_WORDS;
-			for (int i = tid; i < LQ*ROW_WORDS; i += ALIGN_THREADS) s_tab[i] = i < nreal ? src[i] : ROW_PAD_PENALTY;
+			const int32_t *src = (FULL ? a.row_tab : a.lean_tab) + (size_t)a.row_off[unit.os]*TAB_WORDS;
+			const int nreal = os.len*TAB_WORDS;
+			for (int i = tid; i < LQ*TAB_WORDS; i += ALIGN_THREADS) s_tab[i] = i < nreal ? src[i] : ROW_PAD_PENALTY;
 			if (tid < os.len) s_q[tid] = os.seq[tid];
 			cur_os = unit.os;
 			__syncthreads();
@@ -971,11 +973,15 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 				}
 			}
 			else {
-				const FastDp dp = nc_fill_fast<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
-				ColMajorTrace<LQ, ALIGN_THREADS> tv;
+				const FastDp dp = nc_fill_lean<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
+				ColMajorLean<LQ, ALIGN_THREADS> tv;
 				tv.trace32 = trace32;
-				const int ncells = collect_max_cells_fast<LQ, ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
-				if (ncells < 0) handoff = 2;
+				tv.tab = s_tab;
+				tv.tgt = tgt;
+				tv.maxscore = (int)(dp.runkey >> 12);
+				tv.m = 0;
+				const int ncells = lean_max_cell<LQ>(dp, Lt, cells);
+				if (ncells < 0) handoff = ncells == -1 ? 2 : 1;
 				else {
 					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
 					if (flags & F_NEEDGENERIC) handoff = 1;

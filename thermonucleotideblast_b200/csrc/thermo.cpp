@@ -199,6 +199,37 @@ void build_row_tables(const Thermo &th, const OligoStrand &os, int32_t *out)
 	}
 }
 
+// Lean-tier rows (align_core.cuh, LEAN_*), derived from the rows of build_row_tables:
+//   {P1,P4}[20] interleaved | V[4] = M-from-I_query for a real previous target base | column-1
+//   M-from-I_query[4] | M-from-I_target[4] | I_target-from-M[4] | I_target-from-I_target
+// Returns false when the table lacks the structure the lean fill relies on (see align_core.cuh);
+// such an oligo strand is aligned by the full-trace tier instead.
+bool build_lean_tables(const int32_t *rows, int len, int32_t *out)
+{
+	bool ok = len >= 2;
+	for (int r = 0; r < len; ++r) {
+		const int32_t *row = rows + (size_t)r*72;
+		int32_t *o = out + (size_t)r*64;
+		for (int k = 0; k < 64; ++k) o[k] = 0;
+		for (int td = 0; td < 20; ++td) { o[2*td] = row[0 + td]; o[2*td + 1] = row[40 + td]; }
+		for (int tb = 0; tb < 4; ++tb) {
+			o[40 + tb] = row[20 + tb];
+			o[44 + tb] = row[20 + 16 + tb];
+			o[48 + tb] = row[60 + tb];
+			o[52 + tb] = row[64 + tb];
+			// M from I_query must not depend on the previous target base
+			for (int pt = 1; pt < 4; ++pt) ok = ok && row[20 + pt*4 + tb] == row[20 + tb];
+			if (r >= 1) {
+				ok = ok && row[60 + tb] == row[20 + tb];                     // M from I_target == V(r, tb)
+				ok = ok && row[64 + tb] == rows[(size_t)(r - 1)*72 + 20 + tb]; // I_target from M == V(r-1, tb)
+			}
+		}
+		o[56] = row[68];
+		if (r >= 2) ok = ok && row[68] == rows[72 + 68];
+	}
+	return ok;
+}
+
 // I_query from I_query: the only penalty that does not depend on the oligo row
 void build_p5_table(const Thermo &th, int32_t *out)
 {
