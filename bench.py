@@ -345,7 +345,8 @@ def main():
         upload_s += time.perf_counter() - tu
         eng.search_raw(opts)
         hits = eng.hits()
-        d2h = len(hits) * 172 + int(eng.stats().bound_sites) * 344
+        # result bytes the engine copied back (site heads of live groups, records of hit sites)
+        d2h = int(eng.stats().d2h_bytes)
     barrier()
     e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = units / e2e_dt

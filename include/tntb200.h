@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TNTB200_ABI_VERSION 1
+#define TNTB200_ABI_VERSION 2
 
 /* hybrid_sig.h:19 */
 enum { TNT_ASSAY_PCR = 0, TNT_ASSAY_PROBE = 1, TNT_ASSAY_PADLOCK = 2, TNT_ASSAY_MIPS = 3 };
@@ -124,6 +124,7 @@ typedef struct {
 	uint64_t kernel_launches;        /* CUDA kernels launched by the call */
 	double scan_ms, align_ms, pair_ms, total_ms;   /* device time (CUDA events) */
 	uint64_t scan_bytes;             /* algorithmic bytes of the seed scan */
+	uint64_t d2h_bytes;              /* result bytes copied device -> host by the search (counters excluded) */
 } tnt_stats;
 
 const char *tnt_last_error(void);

@@ -36,12 +36,13 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, extra: list[str] | None = None) -> str:
+    """`out` / `extra` build a variant library (extra nvcc flags, e.g. -DTNT_ALIGN_THREADS=32) for A/B runs."""
+    if out == LIB and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    cmd = [nvcc] + NVCC_FLAGS + (extra or []) + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)
@@ -49,5 +50,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
-    print(LIB)
+    args = [a for a in sys.argv[1:] if a != "-v"]
+    out = LIB
+    if args and args[0] == "-o":
+        out = os.path.abspath(args[1])
+        args = args[2:]
+    print(build(force=True, verbose="-v" in sys.argv, out=out, extra=args))

@@ -645,8 +645,8 @@ constexpr int LEAN_WORDS = 64;     // {P1,P4}[20] V[4] P2c1[4] P3[4] P6[4] P7 pa
 constexpr int LEAN_T = 0, LEAN_V = 40, LEAN_P2C1 = 44, LEAN_P3 = 48, LEAN_P6 = 52, LEAN_P7 = 56;
 
 struct FastDp {
-	unsigned runkey;   // (max(M,0) << 12) | (4095 - sweep index of its first occurrence)
-	unsigned lastkey;  // (max(M,0) << 12) | sweep index of its last occurrence
+	unsigned runkey;   // score << 12 | (63 - row) << 6 | (63 - col) of the first maximal cell (row-major)
+	unsigned lastkey;  // score << 12 | row << 6 | col of the last maximal cell
 };
 
 // target base j (0-based, NucCruc orientation) from the 2-bit packed window
@@ -687,93 +687,111 @@ struct ColMajorLean {
 	}
 };
 
+// One column of the lean sweep.  All lean-table values (hence all scores) are multiples of 64
+// (LEAN_SCALE): the low six bits of max(M,0) carry the row, so "column maximum + first / last row
+// attaining it" costs one fused add-max each; the column results are folded into the running keys
+//   key1 = score << 12 | (63 - row) << 6 | (63 - col)      key2 = score << 12 | row << 6 | col
+// (first / last maximal cell in row-major order; they name the same cell iff the maximum is unique).
+// The inputs of row r+1 that come from column j-1 (d1, max of the two gap states) are formed
+// while row r still holds its old values, so the state arrays are updated in place.
+constexpr int LEAN_SCALE = 64;
+
 template <int LQ, int NT, bool FIRST>
-__device__ __forceinline__ void lean_column(const int32_t *__restrict__ tab, int tb, int td, int p5, int p7c, unsigned colidx,
-	uint32_t *__restrict__ col, int (&cM)[LQ], int (&cIq)[LQ], int (&cIt)[LQ], unsigned &runkey, unsigned &lastkey)
+__device__ __forceinline__ void lean_column(const int32_t *__restrict__ tab, int tb, int td, int p5, int p7c, unsigned jj,
+	uint32_t *__restrict__ col, int (&cM)[LQ], int (&cIq)[LQ], int (&cIt)[LQ], unsigned &key1, unsigned &key2)
 {
-	int dM = 0, dIq = 0, dIt = 0; // (i-1, j-1)
+	unsigned ck1 = 0, ck2 = 0;
 	int uM = 0, uIt = 0;          // (i-1, j)
 	int prevV = 0;
 	unsigned acc = 0;
+	int2 tcur = *reinterpret_cast<const int2 *>(tab + LEAN_T + 2*td);
+	int d1 = -tcur.x;             // nothing above the first row
+	int gmax = 0;                 // max(I_query, I_target) of (i-1, j-1)
 #pragma unroll
 	for (int r = 0; r < LQ; ++r) {
 		const int32_t *__restrict__ row = tab + r*LEAN_WORDS;
 		const int oM = cM[r], oIq = cIq[r], oIt = cIt[r]; // (i, j-1)
-		const int2 t14 = *reinterpret_cast<const int2 *>(row + LEAN_T + 2*td);
-		const int d1 = dM - t14.x;
 		int m23, It;
 		if (FIRST || r == 0) {
+			// both diagonal gap states are zero here (column 0 / row 0)
 			const int p2 = FIRST ? row[LEAN_P2C1 + tb] : row[LEAN_V + tb];
-			m23 = max(dIq - p2, dIt - row[LEAN_P3 + tb]);
+			m23 = -min(p2, row[LEAN_P3 + tb]);
 			It = max(uM - row[LEAN_P6 + tb], uIt - row[LEAN_P7]);
 			if (!FIRST) prevV = p2;
 		}
 		else {
 			const int v = row[LEAN_V + tb];
-			m23 = max(dIq, dIt) - v;
+			m23 = gmax - v;
 			It = max(uM - prevV, uIt - p7c);
 			prevV = v;
 		}
 		const int M = max(d1, m23);
-		const int Iq = max(oM - t14.y, oIq - p5);
+		const int Iq = max(oM - tcur.y, oIq - p5);
 		const int mM = max(M, 0);
 
-		const unsigned idx = colidx + (unsigned)r;
-		runkey = max(runkey, (unsigned)mM*4096u + (4095u - idx));
-		lastkey = max(lastkey, (unsigned)mM*4096u + idx);
+		ck1 = max(ck1, (unsigned)mM + (unsigned)(63 - r));
+		ck2 = max(ck2, (unsigned)mM + (unsigned)r);
 
 		acc = __funnelshift_l((unsigned)(m23 - d1), acc, 1); // set <=> the diagonal alone is the maximum
 		acc = __funnelshift_l((unsigned)M, acc, 1);
 		if ((r & 15) == 15 || r == LQ - 1) col[(r >> 4)*NT] = acc;
 
-		dM = oM; dIq = oIq; dIt = oIt;
+		if (r + 1 < LQ) {
+			tcur = *reinterpret_cast<const int2 *>(row + LEAN_WORDS + LEAN_T + 2*td);
+			d1 = oM - tcur.x;
+			gmax = max(oIq, oIt);
+		}
 		cM[r] = mM;
 		cIq[r] = max(Iq, 0);
 		cIt[r] = max(It, 0);
 		uM = mM;
 		uIt = cIt[r];
 	}
+	key1 = max(key1, ck1*64u + (63u - jj));
+	key2 = max(key2, ck2*64u + jj);
 }
 
+#ifndef TNT_FILL_INLINE
+#define TNT_FILL_INLINE __forceinline__
+#endif
 template <int LQ, int NT>
-__device__ __forceinline__ FastDp nc_fill_lean(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
+__device__ TNT_FILL_INLINE FastDp nc_fill_lean(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
 	uint64_t tlo, uint64_t thi, int Lt, uint32_t *__restrict__ trace32)
 {
-	static_assert(LQ % 2 == 0 && LQ >= 2, "row classes are even");
+	static_assert(LQ % 2 == 0 && LQ >= 2 && LQ <= 64, "row classes are even, rows fit six key bits");
 	constexpr int WPC = LeanGeom<LQ>::kWordsPerCol;
 	int cM[LQ], cIq[LQ], cIt[LQ];
 #pragma unroll
 	for (int r = 0; r < LQ; ++r) { cM[r] = 0; cIq[r] = 0; cIt[r] = 0; }
 
-	unsigned runkey = 0, lastkey = 0;
+	unsigned key1 = 0, key2 = 0;
 	const int p7c = tab[LEAN_WORDS + LEAN_P7];
 	int pt = packed_base(tlo, thi, 0);
 	// column 1: GAP in front of it
-	lean_column<LQ, NT, true>(tab, pt, 16 + pt, p5tab[16 + pt], p7c, 0u, trace32, cM, cIq, cIt, runkey, lastkey);
+	lean_column<LQ, NT, true>(tab, pt, 16 + pt, p5tab[16 + pt], p7c, 0u, trace32, cM, cIq, cIt, key1, key2);
 	for (int j = 2; j <= Lt; ++j) {
 		const int tb = packed_base(tlo, thi, j - 1);
 		const int td = pt*4 + tb;
-		lean_column<LQ, NT, false>(tab, tb, td, p5tab[td], p7c, (unsigned)((j - 1)*LQ),
-			trace32 + (size_t)(j - 1)*WPC*NT, cM, cIq, cIt, runkey, lastkey);
+		lean_column<LQ, NT, false>(tab, tb, td, p5tab[td], p7c, (unsigned)(j - 1),
+			trace32 + (size_t)(j - 1)*WPC*NT, cM, cIq, cIt, key1, key2);
 		pt = tb;
 	}
 	FastDp res;
-	res.runkey = runkey;
-	res.lastkey = lastkey;
+	res.runkey = key1;
+	res.lastkey = key2;
 	return res;
 }
 
 // The maximal cell of a lean fill.  Returns 1 (cells[0] set), -1 when no cell is positive (the
 // reference's ">= -1" rule then decides: generic kernel) or -2 when several cells tie for the
 // maximum (full-trace tier).
-template <int LQ>
 __device__ __forceinline__ int lean_max_cell(const FastDp &dp, int Lt, uint16_t *cells)
 {
 	if ((dp.runkey >> 12) == 0) return -1;
-	const int first = 4095 - (int)(dp.runkey & 4095u); // sweep index = (j-1)*LQ + (i-1)
-	if ((int)(dp.lastkey & 4095u) != first) return -2;
-	const int fj = first/LQ + 1, fi = first%LQ + 1;
-	cells[0] = (uint16_t)((fi - 1)*Lt + (fj - 1));
+	const int r1 = 63 - (int)((dp.runkey >> 6) & 63u), j1 = 63 - (int)(dp.runkey & 63u);
+	const int r2 = (int)((dp.lastkey >> 6) & 63u), j2 = (int)(dp.lastkey & 63u);
+	if (r1 != r2 || j1 != j2) return -2;
+	cells[0] = (uint16_t)(r1*Lt + j1);
 	return 1;
 }
 

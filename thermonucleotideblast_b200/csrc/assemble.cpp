@@ -291,13 +291,30 @@ void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &o
 	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
 	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
-	// (fragment, assay) pairs in ascending order, like the reference's nested loops
+	// (fragment, assay) pairs in ascending order, like the reference's nested loops; ties keep the
+	// input order (one packed 64-bit key per site: group rank, then index)
 	std::vector<uint32_t> order(sites.size());
-	for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-		if (sites[a].target != sites[b].target) return sites[a].target < sites[b].target;
-		return sites[a].assay < sites[b].assay;
-	});
+	{
+		int max_assay = 0;
+		for (const BoundSite &s : sites) max_assay = std::max(max_assay, s.assay);
+		const uint64_t na = (uint64_t)max_assay + 1;
+		bool packed = sites.size() < ((uint64_t)1 << 24);
+		for (const BoundSite &s : sites) packed = packed && ((uint64_t)s.target*na + (uint64_t)s.assay) < ((uint64_t)1 << 40);
+		if (packed) {
+			std::vector<uint64_t> keys(sites.size());
+			for (size_t i = 0; i < sites.size(); ++i)
+				keys[i] = (((uint64_t)sites[i].target*na + (uint64_t)sites[i].assay) << 24) | (uint64_t)i;
+			std::sort(keys.begin(), keys.end());
+			for (size_t i = 0; i < keys.size(); ++i) order[i] = (uint32_t)(keys[i] & 0xffffffu);
+		}
+		else {
+			for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+			std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+				if (sites[a].target != sites[b].target) return sites[a].target < sites[b].target;
+				return sites[a].assay < sites[b].assay;
+			});
+		}
+	}
 	const BoundSite *base = sites.data();
 	std::vector<const BoundSite *> group;
 	for (size_t i = 0; i < order.size();) {

@@ -187,6 +187,13 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_out_count;
 	DevBuf<unsigned long long> d_cells;
 	DevBuf<Region> d_regions;
+	DevBuf<unsigned long long> d_per_assay;
+	DevBuf<uint32_t> d_live;        // bitmap over (fragment, assay) groups; word 0..1 of d_live_ctl = count, error flags
+	DevBuf<uint32_t> d_live_ctl;
+	DevBuf<BoundHead> d_live_heads;
+	DevBuf<uint32_t> d_live_index;
+	uint32_t *h_live_index = nullptr; // pinned
+	size_t h_live_index_cap = 0;
 	DevBuf<SlowItem> d_slow, d_retry;
 	DevBuf<Candidate> d_slow_cand;
 	DevBuf<uint32_t> d_slot_map;
@@ -198,7 +205,6 @@ struct tnt_engine {
 	std::unique_ptr<OsSet> set1, set2;
 	tnt_search_options set_opt{};
 	uint64_t assays_version = 0, set_version = ~(uint64_t)0;
-	std::vector<Region> regions;   // persistent: avoids re-faulting megabytes of host memory per search
 
 	std::vector<tnt_hit> hits;
 	std::string arena;
@@ -215,6 +221,7 @@ struct tnt_engine {
 		}
 		if (h_total) cudaFreeHost(h_total);
 		if (h_heads) cudaFreeHost(h_heads);
+		if (h_live_index) cudaFreeHost(h_live_index);
 		if (d_total) cudaFree(d_total);
 		for (auto &e : ev) if (e) cudaEventDestroy(e);
 		if (stream) cudaStreamDestroy(stream);
@@ -229,6 +236,7 @@ struct tnt_engine {
 	}
 
 	void finish_upload();
+	void reserve_heads(size_t n);
 	void sync_targets()
 	{
 		if (!targets_dirty) return;
@@ -360,6 +368,24 @@ void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_
 }
 
 } // namespace
+
+void tnt_engine::reserve_heads(size_t n)
+{
+	if (n > h_heads_cap) {
+		const size_t ncap = std::max<size_t>(n, h_heads_cap*2 + 4096);
+		if (h_heads) cudaFreeHost(h_heads);
+		h_heads = nullptr;
+		CUDA_OK(cudaMallocHost(&h_heads, ncap*sizeof(BoundHead)));
+		h_heads_cap = ncap;
+	}
+	if (n > h_live_index_cap) {
+		const size_t ncap = std::max<size_t>(n, h_live_index_cap*2 + 4096);
+		if (h_live_index) cudaFreeHost(h_live_index);
+		h_live_index = nullptr;
+		CUDA_OK(cudaMallocHost(&h_live_index, ncap*sizeof(uint32_t)));
+		h_live_index_cap = ncap;
+	}
+}
 
 void tnt_engine::finish_upload()
 {
@@ -867,18 +893,15 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 }
 
 // Stage-2: scan regions with the given set
-void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> &regions, uint32_t os_base)
+// (regions in e->d_regions; `worst` = most region positions of any one assay)
+void region_scan_and_align(tnt_engine *e, OsSet &set, uint32_t nregions, uint64_t worst, uint32_t os_base)
 {
-	if (set.os.empty() || regions.empty()) return;
+	if (set.os.empty() || nregions == 0) return;
 	const size_t nos = set.os.size();
 	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
-	e->d_regions.upload(regions, e->stream);
 	// Size the buckets for the busiest assay: expected seeds = positions x words / 4^W; start with
-	// generous slack and double on overflow (repeat-rich fragments can exceed any estimate).
-	std::vector<uint64_t> per_assay(e->assays.size() + 1, 0);
-	for (const Region &r : regions) per_assay[(size_t)r.assay] += r.stop - r.start;
-	uint64_t worst = 0;
-	for (uint64_t v : per_assay) worst = std::max(worst, v);
+	// generous slack and use the exact counts after an overflow (repeat-rich fragments can exceed
+	// any estimate).
 	const double expect = (double)worst*(double)set.max_words/(double)set.nkeys;
 	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
 	for (;;) {
@@ -887,8 +910,8 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 		RegionScanArgs ra{};
 		ra.s = scan_args(e, set, cap);
 		ra.regions = e->d_regions.p;
-		ra.nregions = (uint32_t)regions.size();
-		const uint32_t grid = std::min<uint32_t>((uint32_t)regions.size(), (uint32_t)e->sm_count*8u);
+		ra.nregions = nregions;
+		const uint32_t grid = std::min<uint32_t>(nregions, (uint32_t)e->sm_count*8u);
 		CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
 		k_region_scan<<<grid, SCAN_THREADS, 0, e->stream>>>(ra);
 		CUDA_OK(cudaGetLastError());
@@ -909,17 +932,7 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, const std::vector<Region> 
 // Heads (48 B) of the bound-site records [from, to) -> pinned host array
 void fetch_heads(tnt_engine *e, uint32_t from, uint32_t to)
 {
-	if (to > e->h_heads_cap) {
-		size_t ncap = std::max<size_t>(to, e->h_heads_cap*2 + 4096);
-		BoundHead *np = nullptr;
-		CUDA_OK(cudaMallocHost(&np, ncap*sizeof(BoundHead)));
-		if (e->h_heads) {
-			std::memcpy(np, e->h_heads, (size_t)from*sizeof(BoundHead));
-			cudaFreeHost(e->h_heads);
-		}
-		e->h_heads = np;
-		e->h_heads_cap = ncap;
-	}
+	e->reserve_heads(to);
 	if (to > from) {
 		CUDA_OK(cudaMemcpy2DAsync(e->h_heads + from, sizeof(BoundHead), e->d_bound.p + from, sizeof(BoundRec),
 			sizeof(BoundHead), to - from, cudaMemcpyDeviceToHost, e->stream));
@@ -1022,38 +1035,77 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	e->n_bound = 0;
 	{ HostTimer t("scan_and_align stage1"); scan_and_align(e, stage1, 0); }
 	const uint32_t n1 = e->n_bound;
-	fetch_heads(e, 0, n1);
+	const uint32_t nos1 = (uint32_t)stage1.os.size();
+	const uint32_t n_assays = (uint32_t)e->assays.size();
+	const unsigned gen_grid = (unsigned)e->sm_count*8u;
 
 	if (!stage2.os.empty() && n1 != 0) {
 		HostTimer t_s2("stage2 total");
-		// Partner primers / probes can only matter downstream of a bound minus-strand primer
-		// (amplicon_search.cpp:359-441: f on the minus strand, r and p after it, amplicon <= max_len;
-		// cull_oligo_match :679-765 uses max_len + 50 on seed positions).
-		std::vector<Region> &regions = e->regions;
-		regions.clear();
-		regions.reserve(n1);
-		const uint32_t slack = 64;
-		for (uint32_t i = 0; i < n1; ++i) {
-			const BoundHead &b = e->h_heads[i];
-			if (b.flags & (F_OOB | F_STACK | F_TRUNC)) continue;
-			const Target &tg = e->targets[b.target];
-			Region r;
-			r.target = b.target;
-			r.assay = stage1.os[b.os].assay;
-			const int64_t lo = std::min<int64_t>((int64_t)b.t, (int64_t)b.loc5) - slack;
-			const int64_t hi = std::max<int64_t>((int64_t)b.t, (int64_t)b.loc5) + (int64_t)o.max_len + 50 + slack;
-			r.start = (uint32_t)std::max<int64_t>(0, lo);
-			r.stop = (uint32_t)std::min<int64_t>(tg.len, std::max<int64_t>(hi, 0));
-			if (r.stop > r.start) regions.push_back(r);
-		}
-		// Overlapping regions are not merged: a seed found twice is aligned twice and collapses
-		// again in the per-(loc_5, loc_3) uniqueness step, exactly like duplicate windows do in
-		// the reference (bind_oligo.cpp:810-826).
-		const std::vector<Region> &merged = regions;
-		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, merged, (uint32_t)stage1.os.size()); }
+		// Regions around the bound minus-strand primer sites, built on the device.  Overlapping
+		// regions are not merged: a seed found twice is aligned twice and collapses again in the
+		// per-(loc_5, loc_3) uniqueness step, exactly like duplicate windows do in the reference
+		// (bind_oligo.cpp:810-826).
+		e->d_regions.reserve(n1, 0, e->stream);
+		e->d_per_assay.reserve(n_assays + 1, 0, e->stream);
+		e->d_live_ctl.reserve(2, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_per_assay.p, 0, (n_assays + 1)*sizeof(unsigned long long), e->stream));
+		CUDA_OK(cudaMemsetAsync(e->d_live_ctl.p, 0, 2*sizeof(uint32_t), e->stream));
+		k_make_regions<<<gen_grid, 256, 0, e->stream>>>(e->d_bound.p, n1, stage1.d_os.p, e->d_targets.p, o.max_len,
+			e->d_regions.p, e->d_per_assay.p, e->d_live_ctl.p + 1);
+		CUDA_OK(cudaGetLastError());
+		e->stats.kernel_launches++;
+		std::vector<unsigned long long> per_assay(n_assays + 1, 0);
+		CUDA_OK(cudaMemcpyAsync(per_assay.data(), e->d_per_assay.p, per_assay.size()*sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		uint64_t worst = 0;
+		for (unsigned long long v : per_assay) worst = std::max<uint64_t>(worst, v);
+		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, n1, worst, nos1); }
 	}
 	const uint32_t n2 = e->n_bound;
-	fetch_heads(e, n1, n2);
+
+	// Stage C
+	auto os_of = [&](uint32_t g) -> const OligoStrand & {
+		return g < stage1.os.size() ? stage1.os[g] : stage2.os[g - stage1.os.size()];
+	};
+	// PCR: an amplicon needs a plus-strand primer site, and those only come out of stage 2.  Only
+	// the sites of (fragment, assay) groups that own one leave the device.
+	const uint64_t key_space = (uint64_t)e->targets.size()*n_assays;
+	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty() && key_space <= ((uint64_t)1 << 32);
+	uint32_t n_live = n2;
+	const uint32_t *site_index = nullptr; // record index of each downloaded head (nullptr: identity)
+	if (prefilter && n2 != 0) {
+		const size_t words = (size_t)((key_space + 31)/32);
+		e->d_live.reserve(words, 0, e->stream);
+		e->d_live_ctl.reserve(2, 0, e->stream);
+		e->d_live_heads.reserve(n2, 0, e->stream);
+		e->d_live_index.reserve(n2, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_live.p, 0, words*sizeof(uint32_t), e->stream));
+		CUDA_OK(cudaMemsetAsync(e->d_live_ctl.p, 0, 2*sizeof(uint32_t), e->stream));
+		if (n2 > n1) k_mark_live<<<gen_grid, 256, 0, e->stream>>>(e->d_bound.p, n1, n2, stage2.d_os.p, nos1, n_assays, e->d_live.p);
+		k_compact_live<<<gen_grid, 256, 0, e->stream>>>(e->d_bound.p, n2, stage1.d_os.p, stage2.d_os.p, nos1, n_assays, e->d_live.p,
+			e->d_live_heads.p, e->d_live_index.p, e->d_live_ctl.p, e->d_live_ctl.p + 1);
+		CUDA_OK(cudaGetLastError());
+		e->stats.kernel_launches += 2;
+		uint32_t ctl[2] = {0, 0};
+		CUDA_OK(cudaMemcpyAsync(ctl, e->d_live_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		if (ctl[1] & F_TRUNC)
+			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
+		if (ctl[1] & (F_OOB | F_STACK))
+			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
+		n_live = ctl[0];
+		e->reserve_heads(n_live);
+		if (n_live) {
+			CUDA_OK(cudaMemcpyAsync(e->h_heads, e->d_live_heads.p, (size_t)n_live*sizeof(BoundHead), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaMemcpyAsync(e->h_live_index, e->d_live_index.p, (size_t)n_live*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+		}
+		site_index = e->h_live_index;
+		e->stats.d2h_bytes += (uint64_t)n_live*(sizeof(BoundHead) + sizeof(uint32_t));
+	}
+	else {
+		fetch_heads(e, 0, n2);
+		e->stats.d2h_bytes += (uint64_t)n2*sizeof(BoundHead);
+	}
 
 	CUDA_OK(cudaEventRecord(t_end, e->stream));
 	unsigned long long cells = 0;
@@ -1064,54 +1116,18 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	CUDA_OK(cudaEventElapsedTime(&ms, t_begin, t_end));
 	e->stats.total_ms = ms;
 
-	// Stage C
 	HostTimer t_sites("stage C total");
-	auto os_of = [&](uint32_t g) -> const OligoStrand & {
-		return g < stage1.os.size() ? stage1.os[g] : stage2.os[g - stage1.os.size()];
-	};
-	// PCR: an amplicon needs a plus-strand primer site, and those only come out of stage 2.  Drop
-	// the (fragment, assay) groups without one before any sorting happens.
-	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty();
-	const uint64_t n_assays = e->assays.size();
-	const uint64_t key_space = (uint64_t)e->targets.size()*n_assays;
-	const bool use_bitmap = prefilter && key_space <= ((uint64_t)1 << 32);
-	std::vector<uint64_t> live_bits;
-	std::vector<uint64_t> live_keys;
-	if (prefilter) {
-		if (use_bitmap) live_bits.assign((size_t)(key_space + 63)/64, 0);
-		for (uint32_t i = n1; i < n2; ++i) {
-			const BoundHead &b = e->h_heads[i];
-			const OligoStrand &os = os_of(b.os);
-			if (os.role == TNT_OLIGO_P) continue;
-			const uint64_t key = (uint64_t)b.target*n_assays + (uint32_t)os.assay;
-			if (use_bitmap) live_bits[(size_t)(key >> 6)] |= (uint64_t)1 << (key & 63);
-			else live_keys.push_back(key);
-		}
-		if (!use_bitmap) {
-			std::sort(live_keys.begin(), live_keys.end());
-			live_keys.erase(std::unique(live_keys.begin(), live_keys.end()), live_keys.end());
-		}
-	}
-	auto is_live = [&](uint32_t target, int assay) {
-		const uint64_t key = (uint64_t)target*n_assays + (uint32_t)assay;
-		return use_bitmap ? ((live_bits[(size_t)(key >> 6)] >> (key & 63)) & 1) != 0
-		                  : std::binary_search(live_keys.begin(), live_keys.end(), key);
-	};
-	uint64_t n_sites_total = 0;
 	std::vector<BoundSite> sites;
-	sites.reserve(prefilter ? (size_t)(n2 - n1)*4 + 64 : n2);
-	for (uint32_t i = 0; i < n2; ++i) {
+	sites.reserve(n_live);
+	for (uint32_t i = 0; i < n_live; ++i) {
 		const BoundHead &b = e->h_heads[i];
-		++n_sites_total;
 		if (b.flags & F_TRUNC)
 			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
 		if (b.flags & (F_OOB | F_STACK))
 			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
-		const OligoStrand &os = os_of(b.os);
-		if (prefilter && e->assays[(size_t)os.assay].F.size() && !is_live(b.target, os.assay)) continue;
-		sites.push_back(make_site(b, i, os));
+		sites.push_back(make_site(b, site_index ? site_index[i] : i, os_of(b.os)));
 	}
-	e->stats.bound_sites = n_sites_total;
+	e->stats.bound_sites = n2;
 
 	AssembleOptions ao;
 	ao.assay_format = o.assay_format;
@@ -1143,6 +1159,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		CUDA_OK(cudaGetLastError());
 		e->stats.kernel_launches++;
 		CUDA_OK(cudaMemcpyAsync(recs.data(), e->d_gather.p, recs.size()*sizeof(BoundRec), cudaMemcpyDeviceToHost, e->stream));
+		e->stats.d2h_bytes += recs.size()*sizeof(BoundRec);
 		CUDA_OK(cudaStreamSynchronize(e->stream));
 	}
 	std::vector<uint32_t> text_off(need.size());

@@ -593,7 +593,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_region_scan(RegionScanArgs ra)
 // NucCruc alignment of candidate windows + per-oligo filters
 // (bind_oligo_to_{minus,plus}_strand, bind_oligo.cpp:456-827 / :1159-1530, one seed per thread)
 // ------------------------------------------------------------------------------------------
-constexpr int ALIGN_THREADS = 128;
+#ifndef TNT_ALIGN_THREADS
+#define TNT_ALIGN_THREADS 128
+#endif
+constexpr int ALIGN_THREADS = TNT_ALIGN_THREADS;
 
 struct AlignUnit { uint32_t os; uint32_t begin; uint32_t count; }; // `begin` indexes cand[os*cap + ...]
 
@@ -602,14 +605,22 @@ struct AlignUnit { uint32_t os; uint32_t begin; uint32_t count; }; // `begin` in
 // binary search in the prefix of unit counts.
 struct AlignGroup { uint32_t os; uint32_t first; uint32_t count; uint32_t unit_prefix; }; // first: index of the group's first candidate in cand[os*cap + ...]
 
-__device__ __forceinline__ AlignUnit unit_of(const AlignGroup *__restrict__ groups, uint32_t ngroups, uint32_t u)
+// `hint` carries the group of the CTA's previous unit (units only move forward): the first call
+// (hint == ~0u) searches, later calls step.
+__device__ __forceinline__ AlignUnit unit_of(const AlignGroup *__restrict__ groups, uint32_t ngroups, uint32_t u, uint32_t &hint)
 {
-	uint32_t lo = 0, hi = ngroups; // last group with unit_prefix <= u
-	while (hi - lo > 1) {
-		const uint32_t mid = (lo + hi) >> 1;
-		if (groups[mid].unit_prefix <= u) lo = mid;
-		else hi = mid;
+	uint32_t lo = hint;
+	if (lo == 0xffffffffu) {
+		lo = 0;
+		uint32_t hi = ngroups; // last group with unit_prefix <= u
+		while (hi - lo > 1) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (groups[mid].unit_prefix <= u) lo = mid;
+			else hi = mid;
+		}
 	}
+	else while (lo + 1 < ngroups && groups[lo + 1].unit_prefix <= u) ++lo;
+	hint = lo;
 	const AlignGroup g = groups[lo];
 	const uint32_t local = (u - g.unit_prefix)*ALIGN_THREADS;
 	AlignUnit r;
@@ -775,6 +786,73 @@ __global__ void k_regroup_scatter(const SlowItem *__restrict__ items, uint32_t n
 	}
 }
 
+// ------------------------------------------------------------------------------------------
+// PCR staging on the device (the reference's bind + cull sequence, amplicon_search.cpp:58-441)
+// ------------------------------------------------------------------------------------------
+// Stage-2 search region of every bound stage-1 (minus strand) primer site: partner primers and
+// probes can only matter downstream of it, amplicon <= max_len (cull_oligo_match
+// amplicon_search.cpp:679-765 uses max_len + 50 on seed positions).  One region per record (empty
+// when the record carries an error flag); per-assay totals size the stage-2 candidate buckets.
+__global__ void k_make_regions(const BoundRec *__restrict__ recs, uint32_t n, const OligoStrand *__restrict__ os,
+	const Target *__restrict__ targets, int max_len, Region *__restrict__ out,
+	unsigned long long *__restrict__ per_assay, uint32_t *__restrict__ err_flags)
+{
+	const int64_t slack = 64;
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		const BoundHead b = recs[i].h;
+		Region r;
+		r.target = b.target;
+		r.assay = os[b.os].assay;
+		r.start = r.stop = 0;
+		if (b.flags & (F_OOB | F_STACK | F_TRUNC)) atomicOr(err_flags, (uint32_t)b.flags);
+		else {
+			const int64_t t = (int64_t)b.t, l5 = (int64_t)b.loc5;
+			const int64_t lo = (t < l5 ? t : l5) - slack;
+			const int64_t hi = (t > l5 ? t : l5) + (int64_t)max_len + 50 + slack;
+			const int64_t len = (int64_t)targets[b.target].len;
+			const int64_t start = lo > 0 ? lo : 0;
+			const int64_t stop = hi < len ? (hi > 0 ? hi : 0) : len;
+			if (stop > start) {
+				r.start = (uint32_t)start;
+				r.stop = (uint32_t)stop;
+				atomicAdd(per_assay + r.assay, (unsigned long long)(stop - start));
+			}
+		}
+		out[i] = r;
+	}
+}
+
+// (fragment, assay) groups that own a plus-strand primer site: only those can yield an amplicon.
+__global__ void k_mark_live(const BoundRec *__restrict__ recs, uint32_t from, uint32_t to,
+	const OligoStrand *__restrict__ os2, uint32_t nos1, uint32_t nassay, uint32_t *__restrict__ live)
+{
+	for (uint32_t i = from + blockIdx.x*blockDim.x + threadIdx.x; i < to; i += gridDim.x*blockDim.x) {
+		const BoundHead b = recs[i].h;
+		const OligoStrand &o = os2[b.os - nos1];
+		if (o.role == 2 /* TNT_OLIGO_P */) continue;
+		const uint64_t key = (uint64_t)b.target*nassay + (uint32_t)o.assay;
+		atomicOr(live + (key >> 5), 1u << (key & 31u));
+	}
+}
+
+// Heads of the records of live groups -> dense array (+ their record indices)
+__global__ void k_compact_live(const BoundRec *__restrict__ recs, uint32_t n, const OligoStrand *__restrict__ os1,
+	const OligoStrand *__restrict__ os2, uint32_t nos1, uint32_t nassay, const uint32_t *__restrict__ live,
+	BoundHead *__restrict__ out_heads, uint32_t *__restrict__ out_index, uint32_t *__restrict__ count,
+	uint32_t *__restrict__ err_flags)
+{
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		const BoundHead b = recs[i].h;
+		if (b.flags & (F_OOB | F_STACK | F_TRUNC)) atomicOr(err_flags, (uint32_t)b.flags);
+		const int assay = b.os < nos1 ? os1[b.os].assay : os2[b.os - nos1].assay;
+		const uint64_t key = (uint64_t)b.target*nassay + (uint32_t)assay;
+		if (!((live[key >> 5] >> (key & 31u)) & 1u)) continue;
+		const uint32_t slot = atomicAdd(count, 1u);
+		out_heads[slot] = b;
+		out_index[slot] = i;
+	}
+}
+
 // Copy selected records into a dense array (the hits' oligo sites, for text rendering)
 __global__ void k_gather_recs(const BoundRec *__restrict__ src, const uint32_t *__restrict__ index, uint32_t n, BoundRec *__restrict__ dst)
 {
@@ -806,11 +884,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 	int32_t *rowM = s_rows + tid, *rowIq = rowM + row_stride, *rowIt = rowIq + row_stride;
 	unsigned long long my_cells = 0;
 
+	uint32_t group_hint = 0xffffffffu;
 	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-		const AlignUnit unit = unit_of(a.groups, a.ngroups, u);
+		const AlignUnit unit = unit_of(a.groups, a.ngroups, u, group_hint);
 		const OligoStrand &os = a.os[unit.os];
 		__syncthreads();
-		if (tid < os.len) s_q[tid] = os.seq[tid];
+		for (int i = tid; i < os.len; i += ALIGN_THREADS) s_q[i] = os.seq[i];
 		__syncthreads();
 
 		if ((uint32_t)tid >= unit.count) continue;
@@ -860,8 +939,25 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 
 // Fast kernel: windows made of A/C/G/T only (the oligo may hold any code).  All units of one
 // launch belong to oligo strands of at most LQ bases.
+// Resident CTAs per SM the register allocation has to allow (other modes: experiments with
+// -DTNT_OCC_MODE=n).  Mode 3 = four CTAs for rows <= 24 (128 registers, no spills), three up to 28;
+// measured on B200: 91.0 ms vs 98.2 ms without a bound for the 100-assay workload.
+#ifndef TNT_OCC_MODE
+#define TNT_OCC_MODE 3
+#endif
+#if TNT_OCC_MODE == 1
+#define TNT_FAST_MIN_BLOCKS(LQ, FULL) ((FULL) ? 1 : ((LQ) <= 22 ? 5 : ((LQ) <= 28 ? 4 : 1))*(128/ALIGN_THREADS))
+#elif TNT_OCC_MODE == 2
+#define TNT_FAST_MIN_BLOCKS(LQ, FULL) ((FULL) ? 1 : ((LQ) <= 28 ? 4 : 1)*(128/ALIGN_THREADS))
+#elif TNT_OCC_MODE == 3
+#define TNT_FAST_MIN_BLOCKS(LQ, FULL) ((FULL) ? 1 : ((LQ) <= 24 ? 4 : ((LQ) <= 28 ? 3 : 1))*(128/ALIGN_THREADS))
+#elif TNT_OCC_MODE == 4
+#define TNT_FAST_MIN_BLOCKS(LQ, FULL) ((FULL) ? 1 : ((LQ) <= 20 ? 5 : ((LQ) <= 24 ? 4 : ((LQ) <= 28 ? 3 : 1)))*(128/ALIGN_THREADS))
+#else
+#define TNT_FAST_MIN_BLOCKS(LQ, FULL) 1
+#endif
 template <int LQ, bool FULL>
-__global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
+__global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) k_align_fast(AlignArgs a)
 {
 	constexpr int TAB_WORDS = FULL ? ROW_WORDS : LEAN_WORDS;
 	__shared__ __align__(16) int32_t s_tab[LQ*TAB_WORDS];
@@ -873,21 +969,22 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 	const int tid = threadIdx.x;
 	for (int i = tid; i < NB*NB; i += ALIGN_THREADS) s_bbp[i] = a.thermo->bbp[i];
 	for (int i = tid; i < NPAIR; i += ALIGN_THREADS) s_wc[i] = a.thermo->wc[i];
-	if (tid < 20) s_p5[tid] = a.p5_tab[tid];
+	for (int i = tid; i < 20; i += ALIGN_THREADS) s_p5[i] = FULL ? a.p5_tab[i] : a.p5_tab[i]*LEAN_SCALE;
 
 	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*a.trace_cells*ALIGN_THREADS + tid;
 	unsigned long long my_cells = 0;
 	uint32_t cur_os = 0xffffffffu;
 
+	uint32_t group_hint = 0xffffffffu;
 	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
-		const AlignUnit unit = unit_of(a.groups, a.ngroups, u);
+		const AlignUnit unit = unit_of(a.groups, a.ngroups, u, group_hint);
 		const OligoStrand &os = a.os[unit.os];
 		if (unit.os != cur_os) { // uniform across the block
 			__syncthreads();
 			const int32_t *src = (FULL ? a.row_tab : a.lean_tab) + (size_t)a.row_off[unit.os]*TAB_WORDS;
 			const int nreal = os.len*TAB_WORDS;
 			for (int i = tid; i < LQ*TAB_WORDS; i += ALIGN_THREADS) s_tab[i] = i < nreal ? src[i] : ROW_PAD_PENALTY;
-			if (tid < os.len) s_q[tid] = os.seq[tid];
+			for (int i = tid; i < os.len; i += ALIGN_THREADS) s_q[i] = os.seq[i];
 			cur_os = unit.os;
 			__syncthreads();
 		}
@@ -978,9 +1075,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align_fast(AlignArgs a)
 				tv.trace32 = trace32;
 				tv.tab = s_tab;
 				tv.tgt = tgt;
-				tv.maxscore = (int)(dp.runkey >> 12);
+				tv.maxscore = (int)(dp.runkey >> 12)*LEAN_SCALE;
 				tv.m = 0;
-				const int ncells = lean_max_cell<LQ>(dp, Lt, cells);
+				const int ncells = lean_max_cell(dp, Lt, cells);
 				if (ncells < 0) handoff = ncells == -1 ? 2 : 1;
 				else {
 					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);

@@ -202,6 +202,7 @@ void build_row_tables(const Thermo &th, const OligoStrand &os, int32_t *out)
 // Lean-tier rows (align_core.cuh, LEAN_*), derived from the rows of build_row_tables:
 //   {P1,P4}[20] interleaved | V[4] = M-from-I_query for a real previous target base | column-1
 //   M-from-I_query[4] | M-from-I_target[4] | I_target-from-M[4] | I_target-from-I_target
+// All values are multiplied by 64 (LEAN_SCALE).
 // Returns false when the table lacks the structure the lean fill relies on (see align_core.cuh);
 // such an oligo strand is aligned by the full-trace tier instead.
 bool build_lean_tables(const int32_t *rows, int len, int32_t *out)
@@ -226,6 +227,11 @@ bool build_lean_tables(const int32_t *rows, int len, int32_t *out)
 		}
 		o[56] = row[68];
 		if (r >= 2) ok = ok && row[68] == rows[72 + 68];
+		// scores are kept in units of 1/64 (the low six bits of a score carry the row index)
+		for (int k = 0; k < 57; ++k) {
+			ok = ok && o[k] > -(1 << 24) && o[k] < (1 << 24);
+			o[k] = (int32_t)((int64_t)o[k]*64);
+		}
 	}
 	return ok;
 }

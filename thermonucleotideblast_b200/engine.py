@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtntb200.so")
+# TNT_LIB: developer hook to load an alternatively built library (kernel variants under test)
+LIB_PATH = os.environ.get("TNT_LIB") or os.path.join(HERE, "libtntb200.so")
 
 ASSAY_PCR, ASSAY_PROBE, ASSAY_PADLOCK, ASSAY_MIPS = 0, 1, 2, 3
 STRAND_PLUS, STRAND_MINUS, STRAND_BOTH = 1, 2, 3
@@ -89,7 +90,7 @@ class Stats(C.Structure):
                 ("dp_cells", C.c_uint64), ("bound_sites", C.c_uint64), ("hits", C.c_uint64),
                 ("kernel_launches", C.c_uint64),
                 ("scan_ms", C.c_double), ("align_ms", C.c_double), ("pair_ms", C.c_double),
-                ("total_ms", C.c_double), ("scan_bytes", C.c_uint64)]
+                ("total_ms", C.c_double), ("scan_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
