@@ -34,7 +34,6 @@ constexpr unsigned TW_M_ZERO = 1u << 8;
 constexpr unsigned TW_IQ_NEG = 1u << 9;
 constexpr unsigned TW_IT_NEG = 1u << 10;
 constexpr unsigned TW_CAND = 1u << 11;   // M >= running maximum when the cell was computed
-constexpr unsigned TW_UNCLEAN = 1u << 12; // lean trace only: not "the diagonal predecessor alone gives the maximum"
 // word of a never-written cell (row 0 / column 0 of the reference matrix, nuc_cruc.h:531-536)
 constexpr unsigned TW_BORDER = TW_M_NEG | TW_IQ_NEG | TW_IT_NEG;
 
@@ -52,6 +51,19 @@ __device__ __forceinline__ bool dev_complementary(int q, int t)
 	const unsigned tc = ((ts & 1u) << 3) | ((ts & 8u) >> 3) | ((ts & 2u) << 1) | ((ts & 4u) >> 1);
 	return (c_base_set[q] & tc) != 0;
 }
+
+// target base j (0-based, NucCruc orientation) from the 2-bit packed window
+__device__ __forceinline__ int packed_base(uint64_t lo, uint64_t hi, int j)
+{
+	return (int)(((j < 32) ? (lo >> (2*j)) : (hi >> (2*(j - 32)))) & 3u);
+}
+
+// ACGT-only target window (<= 64 bases) held in two registers; indexes like the byte array the
+// generic kernel uses (NucCruc codes A..T == 0..3)
+struct PackedTgt {
+	uint64_t lo, hi;
+	__device__ __forceinline__ int operator[](int j) const { return packed_base(lo, hi, j); }
+};
 
 struct AlnState {
 	uint8_t q[MAX_COLS];
@@ -178,8 +190,6 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 template <int NT>
 struct RowMajorTrace {
 	static constexpr bool kHasGapStates = true;
-	static constexpr bool kCleanOnly = false;
-	__device__ __forceinline__ void begin_path() const {}
 	const uint16_t *trace;
 	int Lt;
 	__device__ __forceinline__ unsigned get(int i, int j) const { return trace[(size_t)((i - 1)*Lt + (j - 1))*NT]; }
@@ -197,8 +207,8 @@ constexpr int MAX_BRANCH = 3*(MAX_OLIGO + MAX_WINDOW);
 
 __device__ __forceinline__ bool path_split(unsigned m) { return __popc(m & 7u) > 1; }
 
-template <class TV>
-__device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, const TV &tv,
+template <class TV, class TG>
+__device__ void nc_trace_back(const DpShared &sh, const TG &tgt, int Lt, const TV &tv,
 	int start_cell, Branch *stack, int &nstack, int &zero_count, AlnState &a, unsigned &flags)
 {
 	const int Lq = sh.Lq;
@@ -213,7 +223,6 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 
 	unsigned cur_id = 0;        // 0 == the static first_match byte of the reference
 	unsigned cur_mask = T_DIAG;
-	tv.begin_path();
 
 	for (;;) {
 		bool valid = true;
@@ -245,12 +254,10 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 					else if (--truncate_at_zero == 0) valid = false;
 				}
 				if (last_i < 1) { flags |= F_OOB; return; } // the reference reads query[len] here
-				if (a.e < MAX_COLS) { a.q[a.e] = sh.q[Lq - last_i]; a.t[a.e] = tgt[last_j - 1]; ++a.e; }
+				if (a.e < MAX_COLS) { a.q[a.e] = sh.q[Lq - last_i]; a.t[a.e] = (uint8_t)tgt[last_j - 1]; ++a.e; }
 				else flags |= F_TRUNC;
 				a.lm_q = Lq - last_i;
 				a.lm_t = last_j - 1;
-				// lean trace: the path may only go on through "diagonal alone is the maximum" cells
-				if (TV::kCleanOnly && valid && (w & TW_UNCLEAN)) { flags |= F_NEEDGENERIC; return; }
 				cur_id = (unsigned)(cell + 1)*3u + 0u;
 				cur_mask = inside ? (w & 7u) : T_INVALID;
 				--last_i;
@@ -262,7 +269,7 @@ __device__ void nc_trace_back(const DpShared &sh, const uint8_t *tgt, int Lt, co
 			if (last_j < 1) valid = false;
 			else {
 				if (w & TW_IQ_NEG) valid = false;
-				if (a.e < MAX_COLS) { a.q[a.e] = bGAP; a.t[a.e] = tgt[last_j - 1]; ++a.e; }
+				if (a.e < MAX_COLS) { a.q[a.e] = bGAP; a.t[a.e] = (uint8_t)tgt[last_j - 1]; ++a.e; }
 				else flags |= F_TRUNC;
 				a.lm_q = Lq - last_i + 1;
 				a.lm_t = last_j - 1;
@@ -455,11 +462,54 @@ struct Best {
 	float dH, dS, tm;
 };
 
+// frayed ends: drop columns until both ends are Watson-Crick (nuc_cruc.cpp:1022-1054)
+__device__ __forceinline__ void nc_trim_frayed_ends(const DpShared &sh, AlnState &a)
+{
+	while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.e - 1]*NB + a.t[a.e - 1]]]) {
+		if (!is_virtual(a.q[a.e - 1])) --a.lm_q;
+		if (!is_virtual(a.t[a.e - 1])) ++a.lm_t;
+		--a.e;
+	}
+	while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.b]*NB + a.t[a.b]]]) {
+		if (!is_virtual(a.q[a.b])) ++a.fm_q;
+		if (!is_virtual(a.t[a.b])) --a.fm_t;
+		++a.b;
+	}
+}
+
+// optional dangling-end virtual bases (nuc_cruc.cpp:1088-1137); false: F_OOB raised
+template <class TG>
+__device__ __forceinline__ bool nc_dangling_ends(const DpShared &sh, const Thermo *__restrict__ th, const TG &tgt, int Lt,
+	AlnState &a, unsigned &flags)
+{
+	const int Lq = sh.Lq;
+	if (th->dangle5 && (a.fm_q != 0 || a.fm_t != Lt - 1)) {
+		int qb, tb;
+		if (a.fm_q == 0) qb = bE;
+		else { --a.fm_q; if (a.fm_q < 0 || a.fm_q >= Lq) { flags |= F_OOB; return false; } qb = sh.q[a.fm_q]; }
+		if (a.fm_t == Lt - 1) tb = bE;
+		else { ++a.fm_t; if (a.fm_t < 0 || a.fm_t >= Lt) { flags |= F_OOB; return false; } tb = tgt[a.fm_t]; }
+		--a.b;
+		a.q[a.b] = (uint8_t)qb;
+		a.t[a.b] = (uint8_t)tb;
+	}
+	if (th->dangle3 && (a.lm_q != Lq - 1 || a.lm_t != 0)) {
+		int qb, tb;
+		if (a.lm_q == Lq - 1) qb = bE;
+		else { ++a.lm_q; if (a.lm_q < 0 || a.lm_q >= Lq) { flags |= F_OOB; return false; } qb = sh.q[a.lm_q]; }
+		if (a.lm_t == 0) tb = bE;
+		else { --a.lm_t; if (a.lm_t < 0 || a.lm_t >= Lt) { flags |= F_OOB; return false; } tb = tgt[a.lm_t]; }
+		if (a.e < MAX_COLS) { a.q[a.e] = (uint8_t)qb; a.t[a.e] = (uint8_t)tb; ++a.e; }
+		else flags |= F_TRUNC;
+	}
+	return true;
+}
+
 // `cells` lists the maximal DP cells as linear indices (i-1)*Lt + (j-1) in row-major order,
 // i.e. the order of the reference's max_ptr vector.
-template <class TV>
+template <class TV, class TG>
 __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct,
-	const uint8_t *tgt, int Lt, const TV &tv, const uint16_t *cells, int ncells,
+	const TG &tgt, int Lt, const TV &tv, const uint16_t *cells, int ncells,
 	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags)
 {
 	const int Lq = sh.Lq;
@@ -491,17 +541,7 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 			nc_trace_back(sh, tgt, Lt, tv, cell, stack, nstack, zero_count, a, flags);
 			if (flags & (F_OOB | F_STACK | F_NEEDGENERIC)) return;
 
-			// frayed ends: drop columns until both ends are Watson-Crick (:1022-1054)
-			while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.e - 1]*NB + a.t[a.e - 1]]]) {
-				if (!is_virtual(a.q[a.e - 1])) --a.lm_q;
-				if (!is_virtual(a.t[a.e - 1])) ++a.lm_t;
-				--a.e;
-			}
-			while (a.e > a.b && !sh.wc[sh.bbp[a.q[a.b]*NB + a.t[a.b]]]) {
-				if (!is_virtual(a.q[a.b])) ++a.fm_q;
-				if (!is_virtual(a.t[a.b])) --a.fm_t;
-				++a.b;
-			}
+			nc_trim_frayed_ends(sh, a);
 
 			if (zero_count == 0 && nstack > 0) {
 				while (nstack > 0) {
@@ -514,29 +554,13 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 				zero_count = -1;
 			}
 
-			// optional dangling-end virtual bases (:1088-1137)
-			if (th->dangle5 && (a.fm_q != 0 || a.fm_t != Lt - 1)) {
-				int qb, tb;
-				if (a.fm_q == 0) qb = bE;
-				else { --a.fm_q; if (a.fm_q < 0 || a.fm_q >= Lq) { flags |= F_OOB; return; } qb = sh.q[a.fm_q]; }
-				if (a.fm_t == Lt - 1) tb = bE;
-				else { ++a.fm_t; if (a.fm_t < 0 || a.fm_t >= Lt) { flags |= F_OOB; return; } tb = tgt[a.fm_t]; }
-				--a.b;
-				a.q[a.b] = (uint8_t)qb;
-				a.t[a.b] = (uint8_t)tb;
-			}
-			if (th->dangle3 && (a.lm_q != Lq - 1 || a.lm_t != 0)) {
-				int qb, tb;
-				if (a.lm_q == Lq - 1) qb = bE;
-				else { ++a.lm_q; if (a.lm_q < 0 || a.lm_q >= Lq) { flags |= F_OOB; return; } qb = sh.q[a.lm_q]; }
-				if (a.lm_t == 0) tb = bE;
-				else { --a.lm_t; if (a.lm_t < 0 || a.lm_t >= Lt) { flags |= F_OOB; return; } tb = tgt[a.lm_t]; }
-				if (a.e < MAX_COLS) { a.q[a.e] = (uint8_t)qb; a.t[a.e] = (uint8_t)tb; ++a.e; }
-				else flags |= F_TRUNC;
-			}
+			if (!nc_dangling_ends(sh, th, tgt, Lt, a, flags)) return;
 
 			if (a.e - a.b < 3) continue;
 
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 2
+			if (a.e == 1000) // timing experiment only: traceback without evaluation
+#endif
 			if (nc_evaluate(sh, th, r_log_ct, a)) {
 				const float local_dg = TNT_SUB(a.dH, TNT_MUL(T, a.dS));
 				if (!best.valid || local_dg < best_dg) {
@@ -559,7 +583,8 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 // ------------------------------------------------------------------------------------------
 // Per-oligo filters' inputs (nuc_cruc_anchor.cpp:143-192, :249-298; nuc_cruc.h:389-483)
 // ------------------------------------------------------------------------------------------
-__device__ inline unsigned nc_anchor5(const DpShared &sh, const uint8_t *tgt, int Lt, const AlnState &a)
+template <class TG>
+__device__ inline unsigned nc_anchor5(const DpShared &sh, const TG &tgt, int Lt, const AlnState &a)
 {
 	unsigned anchor = 0;
 	int qi = 0, ti = a.fm_q + a.fm_t;
@@ -570,7 +595,8 @@ __device__ inline unsigned nc_anchor5(const DpShared &sh, const uint8_t *tgt, in
 	return anchor;
 }
 
-__device__ inline unsigned nc_anchor3(const DpShared &sh, const uint8_t *tgt, int Lt, const AlnState &a)
+template <class TG>
+__device__ inline unsigned nc_anchor3(const DpShared &sh, const TG &tgt, int Lt, const AlnState &a)
 {
 	unsigned anchor = 0;
 	int qi = sh.Lq - 1, ti = (a.lm_q + a.lm_t + 1) - sh.Lq;
@@ -641,49 +667,33 @@ constexpr int MAX_MAXCELLS = 64;
 // neighbours) use their own entries.  Per cell that leaves three 32-bit shared-memory words
 // (P1 and P4 as one 64-bit load, V) instead of six.
 // ------------------------------------------------------------------------------------------
-constexpr int LEAN_WORDS = 64;     // {P1,P4}[20] V[4] P2c1[4] P3[4] P6[4] P7 pad[7]
-constexpr int LEAN_T = 0, LEAN_V = 40, LEAN_P2C1 = 44, LEAN_P3 = 48, LEAN_P6 = 52, LEAN_P7 = 56;
+constexpr int LEAN_WORDS = 64;     // {P1,P4}[20] V[4] P2c1[4] P3[4] P6[4] P7 PAIR pad[6]
+constexpr int LEAN_T = 0, LEAN_V = 40, LEAN_P2C1 = 44, LEAN_P3 = 48, LEAN_P6 = 52, LEAN_P7 = 56, LEAN_PAIR = 57;
 
 struct FastDp {
 	unsigned runkey;   // score << 12 | (63 - row) << 6 | (63 - col) of the first maximal cell (row-major)
 	unsigned lastkey;  // score << 12 | row << 6 | col of the last maximal cell
 };
 
-// target base j (0-based, NucCruc orientation) from the 2-bit packed window
-__device__ __forceinline__ int packed_base(uint64_t lo, uint64_t hi, int j)
-{
-	return (int)(((j < 32) ? (lo >> (2*j)) : (hi >> (2*(j - 32)))) & 3u);
-}
-
 template <int LQ>
 struct LeanGeom {
 	static constexpr int kWordsPerCol = (LQ + 15)/16;
 };
 
-// Trace view of the lean fill.  get() must be called once per visited cell, in path order,
-// after begin_path(): it carries the value of M along the diagonal.
+// Trace view of the lean fill (trace in shared memory, [word][thread]).
 template <int LQ, int NT>
 struct ColMajorLean {
-	static constexpr bool kHasGapStates = false;
-	static constexpr bool kCleanOnly = true;
 	const uint32_t *trace32;
 	const int32_t *tab;      // lean rows in shared memory
-	const uint8_t *tgt;
+	PackedTgt tgt;
 	int maxscore;
-	mutable int m;
-	__device__ __forceinline__ void begin_path() const { m = maxscore; }
-	__device__ __forceinline__ unsigned get(int i, int j) const
+	// bit 1: the diagonal alone gives the maximum, bit 0: M < 0
+	__device__ __forceinline__ unsigned cell_bits(int i, int j) const
 	{
 		const int g = (i - 1) >> 4, p = (i - 1) & 15;
 		const int n = (LQ - 16*g) < 16 ? (LQ - 16*g) : 16;
-		const uint32_t word = trace32[(size_t)((j - 1)*LeanGeom<LQ>::kWordsPerCol + g)*NT];
-		const unsigned bits = (word >> (2*(n - 1 - p))) & 3u;
-		unsigned w = T_DIAG;
-		if (!(bits & 2u)) w |= TW_UNCLEAN;
-		if (m <= 0) w |= (bits & 1u) ? TW_M_NEG : TW_M_ZERO;
-		const int tb = tgt[j - 1], pt = j >= 2 ? (int)tgt[j - 2] : 4;
-		m = max(m, 0) + tab[(i - 1)*LEAN_WORDS + LEAN_T + 2*(pt*4 + tb)];
-		return w;
+		const uint32_t word = trace32[((j - 1)*LeanGeom<LQ>::kWordsPerCol + g)*NT];
+		return (word >> (2*(n - 1 - p))) & 3u;
 	}
 };
 
@@ -795,6 +805,144 @@ __device__ __forceinline__ int lean_max_cell(const FastDp &dp, int Lt, uint16_t 
 	return 1;
 }
 
+// Column k of a gapless alignment that starts at (query fm_q, target fm_t): the oligo base
+// fm_q + k against the target base fm_t - k.  Each lean row carries, per target base, the
+// reference's pair code 7*query + target (best_base_pair) in bits 0..5 and "Watson-Crick" in bit 7.
+__device__ __forceinline__ unsigned lean_pair(const int32_t *__restrict__ tab, int Lq, const PackedTgt &tgt, int fm_q, int fm_t, int k)
+{
+	const int tb = tgt[fm_t - k];
+	return ((unsigned)tab[(Lq - 1 - (fm_q + k))*LEAN_WORDS + LEAN_PAIR] >> (8*tb)) & 0xffu;
+}
+
+// evaluate_alignment (nuc_cruc.cpp:1620-2299) restricted to what a trimmed gapless alignment can
+// reach: no gap columns, no virtual bases, first and last column Watson-Crick.  Same float
+// operations in the same order as nc_evaluate (including the subtract-then-add pairs of the
+// internal-loop branch, which do not cancel in binary32).
+__device__ __forceinline__ bool lean_evaluate(const int32_t *__restrict__ tab, int Lq, const Thermo *__restrict__ th, float r_log_ct,
+	const PackedTgt &tgt, int fm_q, int fm_t, int n, float &out_dH, float &out_dS, float &out_tm)
+{
+	const float *__restrict__ H = th->H;
+	const float *__restrict__ S = th->S;
+#define ADD_HS(idx) do { const int _x = (idx); dH = TNT_ADD(dH, __ldg(H + _x)); dS = TNT_ADD(dS, __ldg(S + _x)); } while (0)
+#define SUB_HS(idx) do { const int _x = (idx); dH = TNT_SUB(dH, __ldg(H + _x)); dS = TNT_SUB(dS, __ldg(S + _x)); } while (0)
+	float dH = th->init_H, dS = TNT_ADD(th->init_S, 0.0f);
+	unsigned c = lean_pair(tab, Lq, tgt, fm_q, fm_t, 0);
+	int cur = (int)(c & 63u);
+	bool cur_wc = (c & 0x80u) != 0; // true after trimming
+	if (cur_wc && (cur == P_AT || cur == P_TA)) { dH = TNT_ADD(dH, th->at_H); dS = TNT_ADD(dS, th->at_S); }
+	unsigned num_base = 2, nmm = 0;
+	int terminal = P_NONE, last = P_NONE;
+	int loop_pm = P_NONE, loop_mm = P_NONE; // the pair in front of the open mismatch run and its first mismatch
+
+	for (int k = 1; k < n; ++k) {
+		const bool last_wc = cur_wc;
+		last = cur;
+		c = lean_pair(tab, Lq, tgt, fm_q, fm_t, k);
+		cur = (int)(c & 63u);
+		cur_wc = (c & 0x80u) != 0;
+		if (last_wc || cur_wc) { // not inside a loop
+			ADD_HS(last*NPAIR + cur);
+			num_base += 2;
+		}
+		if (cur_wc) {
+			terminal = cur;
+			if (nmm > 1) {
+				// an internal loop of nmm mismatches closes on this column
+				dS = TNT_ADD(dS, __ldg(th->loop_S + 2*nmm));
+				dS = TNT_ADD(dS, TNT_MUL(0.0f, th->asym_loop_dS));
+				SUB_HS(last*NPAIR + cur);
+				ADD_HS(last*NPAIR + cur);
+				SUB_HS(loop_pm*NPAIR + loop_mm);
+				ADD_HS(loop_pm*NPAIR + loop_mm);
+				num_base += 2;
+			}
+			nmm = 0;
+		}
+		else {
+			if (nmm == 0) { loop_pm = last; loop_mm = cur; }
+			++nmm;
+		}
+	}
+	if (terminal == P_AT || terminal == P_TA) { dH = TNT_ADD(dH, th->at_H); dS = TNT_ADD(dS, th->at_S); }
+	out_dH = dH;
+	out_dS = dS;
+	if (dH >= 0.0f) return false;
+	dS = TNT_ADD(dS, TNT_MUL(TNT_MUL(th->salt, TNT_SUB(TNT_MUL(0.5f, (float)num_base), 1.0f)), th->log_na));
+	out_dS = dS;
+	const float tm = TNT_SUB(__fdiv_rn(dH, TNT_ADD(r_log_ct, dS)), 273.15f);
+	out_tm = fmaxf(0.0f, tm);
+	return true;
+#undef ADD_HS
+#undef SUB_HS
+}
+
+// The whole post-fill work of a lean candidate: one traceback down the diagonal of the single
+// maximal cell, frayed ends, dangling ends, evaluation.  Handles the ordinary case only -- a run of
+// cells with M > 0 whose maximum comes from the diagonal alone, closed by a cell with M < 0 inside
+// the matrix (the first pair of the duplex: it carries a terminal penalty, no stack).  Anything
+// else (a tie or gap on the path, M == 0 on the path, the matrix border) returns false: the
+// full-trace tier then follows the reference's trace_back rules literally.
+// The alignment is a diagonal segment, so nothing is materialised unless the record can be
+// written (`keep_all`, or Tm inside [min_tm, max_tm], the first filter of finish_alignment).
+template <int LQ, int NT>
+__device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct,
+	const ColMajorLean<LQ, NT> &tv, int Lt, int cell, bool keep_all, float min_tm, float max_tm,
+	AlnState &a, Best &best, unsigned &flags)
+{
+	const int Lq = sh.Lq;
+	int i = cell/Lt + 1, j = cell%Lt + 1;
+	int fm_q = Lq - i, fm_t = j - 1;
+	int n = 0;
+	int m = tv.maxscore;
+	for (;;) {
+		const unsigned bits = tv.cell_bits(i, j);
+		if (m <= 0 && !(bits & 1u)) return false;      // M == 0 on the path
+		++n;
+		if (m <= 0) break;                             // M < 0: the closing pair
+		if (!(bits & 2u)) return false;                // tie or gap state
+		if (i == 1 || j == 1) return false;            // border next
+		const int tb = tv.tgt[j - 1], pt = tv.tgt[j - 2];
+		m += tv.tab[(i - 1)*LEAN_WORDS + LEAN_T + 2*(pt*4 + tb)];
+		--i;
+		--j;
+	}
+	best.valid = false;
+	a.b = a.e = 2;
+	a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
+	a.dH = a.dS = a.tm = 0.0f;
+
+	if (th->dangle5 || th->dangle3) {
+		// dangling-end columns can hold virtual bases: materialise and use the general code
+		a.fm_q = fm_q; a.fm_t = fm_t;
+		for (int k = 0; k < n; ++k) { a.q[a.e] = sh.q[fm_q + k]; a.t[a.e] = (uint8_t)tv.tgt[fm_t - k]; ++a.e; }
+		a.lm_q = fm_q + n - 1; a.lm_t = fm_t - (n - 1);
+		nc_trim_frayed_ends(sh, a);
+		if (!nc_dangling_ends(sh, th, tv.tgt, Lt, a, flags)) return true; // F_OOB is reported, not retried
+		if (a.e - a.b >= 3 && nc_evaluate(sh, th, r_log_ct, a)) {
+			best.valid = true;
+			best.dH = a.dH; best.dS = a.dS; best.tm = a.tm;
+		}
+		else { a.b = a.e = 2; a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0; }
+		return true;
+	}
+
+	// frayed ends (nuc_cruc.cpp:1022-1054): back, then front
+	while (n > 0 && !(lean_pair(tv.tab, Lq, tv.tgt, fm_q, fm_t, n - 1) & 0x80u)) --n;
+	while (n > 0 && !(lean_pair(tv.tab, Lq, tv.tgt, fm_q, fm_t, 0) & 0x80u)) { ++fm_q; --fm_t; --n; }
+	if (n < 3) return true;
+	float dH, dS, tm = 0.0f;
+	if (!lean_evaluate(tv.tab, Lq, th, r_log_ct, tv.tgt, fm_q, fm_t, n, dH, dS, tm)) return true;
+	best.valid = true;
+	best.dH = dH; best.dS = dS; best.tm = tm;
+	a.dH = dH; a.dS = dS; a.tm = tm;
+	a.fm_q = fm_q; a.fm_t = fm_t;
+	a.lm_q = fm_q + n - 1; a.lm_t = fm_t - (n - 1);
+	a.e = 2 + n;
+	if (keep_all || !(tm < min_tm || tm > max_tm))
+		for (int k = 0; k < n; ++k) { a.q[2 + k] = sh.q[fm_q + k]; a.t[2 + k] = (uint8_t)tv.tgt[fm_t - k]; }
+	return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Full-trace variant of the fast fill: same sweep, 12-bit trace words that also record the gap
 // states (two rows per 32-bit store).  Used for the few candidates whose optimal path enters a
@@ -827,8 +975,6 @@ __device__ __forceinline__ unsigned decode_full_trace(unsigned raw)
 template <int LQ, int NT>
 struct ColMajorTraceFull {
 	static constexpr bool kHasGapStates = true;
-	static constexpr bool kCleanOnly = false;
-	__device__ __forceinline__ void begin_path() const {}
 	const uint32_t *trace32;
 	__device__ __forceinline__ unsigned raw(int i, int j) const
 	{

@@ -478,7 +478,7 @@ void finish_set(tnt_engine *e, OsSet &set)
 	for (size_t s = 0; s < nos; ++s) {
 		int32_t *rows_s = set.row_tab.data() + (size_t)set.row_tab_off[s]*ROW_WORDS;
 		build_row_tables(e->h_thermo, set.os[s], rows_s);
-		set.lean_ok[s] = build_lean_tables(rows_s, set.os[s].len, set.lean_tab.data() + (size_t)set.row_tab_off[s]*LEAN_WORDS) && !no_lean;
+		set.lean_ok[s] = build_lean_tables(e->h_thermo, set.os[s], rows_s, set.lean_tab.data() + (size_t)set.row_tab_off[s]*LEAN_WORDS) && !no_lean;
 		// upper bound of any cell: every row contributes at most its most favourable M-from-M term
 		int64_t bound = 0;
 		for (int r = 0; r < set.os[s].len; ++r) {
@@ -587,11 +587,24 @@ void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1
 const int kFastClasses[] = {TNT_FAST_CLASSES(TNT_CLASS_ENTRY)};
 #undef TNT_CLASS_ENTRY
 
+// 32-bit trace words per thread of the fast tiers
+uint32_t fast_trace_words(int lq, bool full)
+{
+	const uint32_t cols = (uint32_t)(lq + 2*NUM_FLANK);
+	return full ? cols*(uint32_t)(lq/2) : cols*(uint32_t)((lq + 15)/16);
+}
+
+// dynamic shared memory of a fast kernel: the lean tier keeps its trace there
+size_t fast_smem(int lq, bool full)
+{
+	return full ? 0 : (size_t)fast_trace_words(lq, false)*ALIGN_THREADS*sizeof(uint32_t);
+}
+
 template <int LQ>
 void launch_fast(const AlignArgs &a, uint32_t grid, bool full, cudaStream_t st)
 {
 	if (full) k_align_fast<LQ, true><<<grid, ALIGN_THREADS, 0, st>>>(a);
-	else k_align_fast<LQ, false><<<grid, ALIGN_THREADS, 0, st>>>(a);
+	else k_align_fast<LQ, false><<<grid, ALIGN_THREADS, fast_smem(LQ, false), st>>>(a);
 }
 
 template <int LQ>
@@ -601,7 +614,11 @@ int fast_occupancy(bool full)
 	int &n = cached[full ? 1 : 0];
 	if (n == 0) {
 		if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, true>, ALIGN_THREADS, 0);
-		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, 0);
+		else {
+			const size_t smem = fast_smem(LQ, false);
+			CUDA_OK(cudaFuncSetAttribute(k_align_fast<LQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, smem);
+		}
 		n = std::max(n, 1);
 	}
 	return n;
@@ -615,13 +632,6 @@ int fast_blocks_per_sm(int lq, bool full)
 #undef TNT_CLASS_CASE
 	default: throw std::runtime_error("internal: unknown oligo length class");
 	}
-}
-
-// 32-bit trace words per thread of the fast tiers
-uint32_t fast_trace_words(int lq, bool full)
-{
-	const uint32_t cols = (uint32_t)(lq + 2*NUM_FLANK);
-	return full ? cols*(uint32_t)(lq/2) : cols*(uint32_t)((lq + 15)/16);
 }
 
 // Run one alignment kernel (fast class `lq`, or the generic kernel when lq == 0) over `units`,
@@ -651,8 +661,8 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 		grid = (uint32_t)std::min<size_t>(nunits, (size_t)e->sm_count*fast_blocks_per_sm(lq, full));
 		a.trace_cells = fast_trace_words(lq, full);
 	}
-	// d_trace counts 16-bit units
-	e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS*(lq == 0 ? 1 : 2) + 64, 0, e->stream);
+	// d_trace counts 16-bit units; the lean tier needs none (shared memory)
+	if (lq == 0 || full) e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS*(lq == 0 ? 1 : 2) + 64, 0, e->stream);
 	a.trace = e->d_trace.p;
 	CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
 	switch (lq) {

@@ -666,8 +666,9 @@ struct AlignArgs {
 
 // Thresholds in the reference's order (bind_oligo.cpp:598-714), target coordinates
 // (:721-731 minus, :1424-1434 plus) and the output record.
+template <class TG>
 __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, const OligoStrand &os, uint32_t os_index,
-	uint32_t target, uint32_t k, uint32_t t, uint32_t start, uint32_t stop, const uint8_t *tgt, int Lt,
+	uint32_t target, uint32_t k, uint32_t t, uint32_t start, uint32_t stop, const TG &tgt, int Lt,
 	const Best &best, const AlnState &best_aln, unsigned flags, uint32_t all_slot)
 {
 	const float tm = best.tm;
@@ -717,7 +718,7 @@ __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, 
 	const int ncols = best.valid ? best_aln.e - best_aln.b : 0;
 	r.ncols = (uint8_t)ncols;
 	for (int i = 0; i < ncols; ++i) { r.cols_q[i] = best_aln.q[best_aln.b + i]; r.cols_t[i] = best_aln.t[best_aln.b + i]; }
-	for (int i = 0; i < Lt; ++i) r.win[i] = tgt[i];
+	for (int i = 0; i < Lt; ++i) r.win[i] = (uint8_t)tgt[i];
 	{
 		// length of the text nuc_cruc_output.cpp:87-204 renders: unaligned prefix + columns + suffix
 		const int prefix = max(0, min(best_aln.fm_q, Lt - 1 - best_aln.fm_t));
@@ -971,7 +972,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 	for (int i = tid; i < NPAIR; i += ALIGN_THREADS) s_wc[i] = a.thermo->wc[i];
 	for (int i = tid; i < 20; i += ALIGN_THREADS) s_p5[i] = FULL ? a.p5_tab[i] : a.p5_tab[i]*LEAN_SCALE;
 
-	uint32_t *trace32 = reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*a.trace_cells*ALIGN_THREADS + tid;
+	// trace scratch: the lean tier's 2 bit/cell fit shared memory ([word][thread]: every lane its own
+	// bank, for the column stores as well as for the per-lane reads of the traceback); the
+	// full-trace tier keeps its 16 bit/cell in a per-CTA slab of global memory
+	extern __shared__ __align__(16) uint32_t s_trace[];
+	uint32_t *trace32 = FULL ? reinterpret_cast<uint32_t *>(a.trace) + (size_t)blockIdx.x*a.trace_cells*ALIGN_THREADS + tid
+	                         : s_trace + tid;
 	unsigned long long my_cells = 0;
 	uint32_t cur_os = 0xffffffffu;
 
@@ -1030,22 +1036,26 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 		}
 		my_cells += (unsigned long long)(os.len*Lt);
 
-		// NucCruc target 5'->3': the window as is (plus strand) or its reverse complement
-		uint8_t tgt[MAX_WINDOW];
-		uint64_t tlo = 0, thi = 0;
-		if (os.plus) {
-			tlo = lo;
-			thi = hi;
-			for (int j = 0; j < Lt; ++j) tgt[j] = (uint8_t)packed_base(lo, hi, j);
+		// NucCruc target 5'->3': the window as is (plus strand) or its reverse complement, 2 bit/base
+		PackedTgt tgt;
+		tgt.lo = lo;
+		tgt.hi = hi;
+		if (!os.plus && Lt > 0) {
+			// reverse the 2-bit groups of the 128-bit window, drop the unused tail, complement (3 - b == b ^ 3)
+			const uint64_t odd = 0xaaaaaaaaaaaaaaaaull;
+			uint64_t rl = __brevll(hi), rh = __brevll(lo);
+			rl = ((rl & odd) >> 1) | ((rl & ~odd) << 1);
+			rh = ((rh & odd) >> 1) | ((rh & ~odd) << 1);
+			const unsigned drop = 128u - 2u*(unsigned)Lt; // Lt >= 1
+			if (drop >= 64u) { rl = rh >> (drop - 64u); rh = 0; }
+			else if (drop) { rl = (rl >> drop) | (rh << (64u - drop)); rh >>= drop; }
+			tgt.lo = ~rl;
+			tgt.hi = ~rh;
 		}
-		else {
-			for (int j = 0; j < Lt; ++j) {
-				const int b = 3 - packed_base(lo, hi, Lt - 1 - j);
-				tgt[j] = (uint8_t)b;
-				if (j < 32) tlo |= (uint64_t)b << (2*j);
-				else thi |= (uint64_t)b << (2*(j - 32));
-			}
-		}
+		if (Lt <= 0) tgt.lo = tgt.hi = 0;
+		else if (Lt < 32) { tgt.lo &= (1ull << (2*Lt)) - 1ull; tgt.hi = 0; }
+		else if (Lt < 64) tgt.hi &= (1ull << (2*(Lt - 32))) - 1ull;
+		const uint64_t tlo = tgt.lo, thi = tgt.hi;
 
 		unsigned flags = 0;
 		AlnState work, best_aln;
@@ -1076,13 +1086,14 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 				tv.tab = s_tab;
 				tv.tgt = tgt;
 				tv.maxscore = (int)(dp.runkey >> 12)*LEAN_SCALE;
-				tv.m = 0;
 				const int ncells = lean_max_cell(dp, Lt, cells);
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 1
+				// timing experiment only: fill without traceback / evaluation
+				if (dp.runkey == 0xfffffff1u) handoff = 1;
+				continue;
+#endif
 				if (ncells < 0) handoff = ncells == -1 ? 2 : 1;
-				else {
-					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
-					if (flags & F_NEEDGENERIC) handoff = 1;
-				}
+				else if (!lean_finish(sh, a.thermo, os.r_log_ct, tv, Lt, cells[0], a.emit_all != 0, os.min_tm, os.max_tm, best_aln, best, flags)) handoff = 1;
 			}
 		}
 		if (handoff) {

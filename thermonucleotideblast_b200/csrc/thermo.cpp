@@ -205,8 +205,9 @@ void build_row_tables(const Thermo &th, const OligoStrand &os, int32_t *out)
 // All values are multiplied by 64 (LEAN_SCALE).
 // Returns false when the table lacks the structure the lean fill relies on (see align_core.cuh);
 // such an oligo strand is aligned by the full-trace tier instead.
-bool build_lean_tables(const int32_t *rows, int len, int32_t *out)
+bool build_lean_tables(const Thermo &th, const OligoStrand &os, const int32_t *rows, int32_t *out)
 {
+	const int len = os.len;
 	bool ok = len >= 2;
 	for (int r = 0; r < len; ++r) {
 		const int32_t *row = rows + (size_t)r*72;
@@ -232,6 +233,16 @@ bool build_lean_tables(const int32_t *rows, int len, int32_t *out)
 			ok = ok && o[k] > -(1 << 24) && o[k] < (1 << 24);
 			o[k] = (int32_t)((int64_t)o[k]*64);
 		}
+		// evaluation side: pair code 7*query + target (best_base_pair) and the Watson-Crick flag of
+		// this row's oligo base against each target base, one byte each
+		const int qb = os.seq[len - 1 - r];
+		uint32_t pairs = 0;
+		for (int tb = 0; tb < 4; ++tb) {
+			const unsigned code = th.bbp[qb*NB + tb];
+			if (code >= 64) ok = false;
+			pairs |= ((code & 63u) | (th.wc[code] ? 0x80u : 0u)) << (8*tb);
+		}
+		o[57] = (int32_t)pairs;
 	}
 	return ok;
 }

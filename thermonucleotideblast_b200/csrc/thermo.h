@@ -10,7 +10,7 @@ void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3);
 void build_row_tables(const Thermo &th, const OligoStrand &os, int32_t *out);
 void build_p5_table(const Thermo &th, int32_t *out);
 // lean-tier rows out[len][64] from rows[len][72]; false: structure not present, use the full-trace tier
-bool build_lean_tables(const int32_t *rows, int len, int32_t *out);
+bool build_lean_tables(const Thermo &th, const OligoStrand &os, const int32_t *rows, int32_t *out);
 
 // NC_R*log(Ct) with the host libm (reference nuc_cruc.cpp:2291)
 float r_log_ct(float ct);
