@@ -512,7 +512,6 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 	const TG &tgt, int Lt, const TV &tv, const uint16_t *cells, int ncells,
 	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags)
 {
-	const int Lq = sh.Lq;
 	const float T = th->T;
 	best.valid = false;
 	best.dH = best.dS = best.tm = 0.0f;

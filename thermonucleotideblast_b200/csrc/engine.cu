@@ -1077,25 +1077,46 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	auto os_of = [&](uint32_t g) -> const OligoStrand & {
 		return g < stage1.os.size() ? stage1.os[g] : stage2.os[g - stage1.os.size()];
 	};
-	// PCR: an amplicon needs a plus-strand primer site, and those only come out of stage 2.  Only
-	// the sites of (fragment, assay) groups that own one leave the device.
+	// PCR: an amplicon needs a minus-strand primer site with a plus-strand primer site of the same
+	// (fragment, assay) less than max_len downstream.  Only sites that can be part of such a pair
+	// leave the device (k_live_*: position buckets at least max_len wide).
 	const uint64_t key_space = (uint64_t)e->targets.size()*n_assays;
-	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty() && key_space <= ((uint64_t)1 << 32);
+	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty() && key_space <= ((uint64_t)1 << 31);
 	uint32_t n_live = n2;
 	const uint32_t *site_index = nullptr; // record index of each downloaded head (nullptr: identity)
 	if (prefilter && n2 != 0) {
-		const size_t words = (size_t)((key_space + 31)/32);
-		e->d_live.reserve(words, 0, e->stream);
+		uint32_t max_target_len = 1;
+		for (const Target &t : e->targets) max_target_len = std::max(max_target_len, t.len);
+		uint32_t shift = 6;
+		while (((uint32_t)1 << shift) < (uint32_t)std::max<int64_t>(o.max_len, 64) && shift < 31) ++shift;
+		uint32_t nbucket = (max_target_len >> shift) + 2;
+		while (key_space*nbucket > ((uint64_t)1 << 33) && shift < 31) { ++shift; nbucket = (max_target_len >> shift) + 2; }
+		const size_t words = (size_t)((key_space*nbucket + 31)/32) + 1;
+		e->d_live.reserve(2*words, 0, e->stream);
 		e->d_live_ctl.reserve(2, 0, e->stream);
 		e->d_live_heads.reserve(n2, 0, e->stream);
 		e->d_live_index.reserve(n2, 0, e->stream);
-		CUDA_OK(cudaMemsetAsync(e->d_live.p, 0, words*sizeof(uint32_t), e->stream));
+		CUDA_OK(cudaMemsetAsync(e->d_live.p, 0, 2*words*sizeof(uint32_t), e->stream));
 		CUDA_OK(cudaMemsetAsync(e->d_live_ctl.p, 0, 2*sizeof(uint32_t), e->stream));
-		if (n2 > n1) k_mark_live<<<gen_grid, 256, 0, e->stream>>>(e->d_bound.p, n1, n2, stage2.d_os.p, nos1, n_assays, e->d_live.p);
-		k_compact_live<<<gen_grid, 256, 0, e->stream>>>(e->d_bound.p, n2, stage1.d_os.p, stage2.d_os.p, nos1, n_assays, e->d_live.p,
-			e->d_live_heads.p, e->d_live_index.p, e->d_live_ctl.p, e->d_live_ctl.p + 1);
+		LiveArgs la{};
+		la.recs = e->d_bound.p;
+		la.os1 = stage1.d_os.p;
+		la.os2 = stage2.d_os.p;
+		la.nos1 = nos1;
+		la.nassay = n_assays;
+		la.nbucket = nbucket;
+		la.shift = shift;
+		la.live_r = e->d_live.p;
+		la.live_f = e->d_live.p + words;
+		la.out_heads = e->d_live_heads.p;
+		la.out_index = e->d_live_index.p;
+		la.count = e->d_live_ctl.p;
+		la.err_flags = e->d_live_ctl.p + 1;
+		if (n2 > n1) k_live_mark_plus<<<gen_grid, 256, 0, e->stream>>>(la, n1, n2);
+		if (n1) k_live_compact<<<gen_grid, 256, 0, e->stream>>>(la, 0, n1, 1);
+		if (n2 > n1) k_live_compact<<<gen_grid, 256, 0, e->stream>>>(la, n1, n2, 2);
 		CUDA_OK(cudaGetLastError());
-		e->stats.kernel_launches += 2;
+		e->stats.kernel_launches += 3;
 		uint32_t ctl[2] = {0, 0};
 		CUDA_OK(cudaMemcpyAsync(ctl, e->d_live_ctl.p, sizeof(ctl), cudaMemcpyDeviceToHost, e->stream));
 		CUDA_OK(cudaStreamSynchronize(e->stream));

@@ -823,34 +823,68 @@ __global__ void k_make_regions(const BoundRec *__restrict__ recs, uint32_t n, co
 	}
 }
 
-// (fragment, assay) groups that own a plus-strand primer site: only those can yield an amplicon.
-__global__ void k_mark_live(const BoundRec *__restrict__ recs, uint32_t from, uint32_t to,
-	const OligoStrand *__restrict__ os2, uint32_t nos1, uint32_t nassay, uint32_t *__restrict__ live)
+// Which bound sites can take part in an amplicon at all?  A hit needs a minus-strand primer site
+// f and a plus-strand primer site r of the same (fragment, assay) with
+// f.loc_3 < r.loc_5 and r.loc_3 - f.loc_5 + 1 <= max_len (amplicon_search.cpp:383-390), and a
+// probe inside [f.loc_5, r.loc_3] (:399-406).  With position buckets at least max_len wide,
+// r.loc_5 (and a probe's loc_5) falls into the bucket of f.loc_5 or the next one.  Three passes
+// over the site heads: plus primers mark `live_r`; minus primers that see a mark survive and
+// mark `live_f`; plus primers and probes that see a live minus primer survive.  Only survivors
+// (heads + record indices) leave the device.
+struct LiveArgs {
+	const BoundRec *recs;
+	const OligoStrand *os1, *os2;
+	uint32_t nos1, nassay;
+	uint32_t nbucket, shift;      // buckets per fragment, log2(bucket width)
+	uint32_t *live_r, *live_f;
+	BoundHead *out_heads;
+	uint32_t *out_index;
+	uint32_t *count;
+	uint32_t *err_flags;
+};
+
+__device__ __forceinline__ uint64_t live_key(const LiveArgs &a, uint32_t target, int assay, int32_t loc5)
+{
+	const uint32_t b = min((uint32_t)max(loc5, 0) >> a.shift, a.nbucket - 2u);
+	return ((uint64_t)target*a.nassay + (uint32_t)assay)*a.nbucket + b;
+}
+__device__ __forceinline__ bool live_test(const uint32_t *bits, uint64_t key) { return (bits[key >> 5] >> (key & 31u)) & 1u; }
+
+// pass 0: stage-2 records [from, to), plus-strand primers mark live_r
+__global__ void k_live_mark_plus(LiveArgs a, uint32_t from, uint32_t to)
 {
 	for (uint32_t i = from + blockIdx.x*blockDim.x + threadIdx.x; i < to; i += gridDim.x*blockDim.x) {
-		const BoundHead b = recs[i].h;
-		const OligoStrand &o = os2[b.os - nos1];
-		if (o.role == 2 /* TNT_OLIGO_P */) continue;
-		const uint64_t key = (uint64_t)b.target*nassay + (uint32_t)o.assay;
-		atomicOr(live + (key >> 5), 1u << (key & 31u));
+		const BoundHead b = a.recs[i].h;
+		if (b.flags & (F_OOB | F_STACK | F_TRUNC)) atomicOr(a.err_flags, (uint32_t)b.flags);
+		const OligoStrand &o = a.os2[b.os - a.nos1];
+		if (o.role == 2 /* TNT_OLIGO_P */ || !o.plus) continue;
+		const uint64_t key = live_key(a, b.target, o.assay, b.loc5);
+		atomicOr(a.live_r + (key >> 5), 1u << (key & 31u));
 	}
 }
 
-// Heads of the records of live groups -> dense array (+ their record indices)
-__global__ void k_compact_live(const BoundRec *__restrict__ recs, uint32_t n, const OligoStrand *__restrict__ os1,
-	const OligoStrand *__restrict__ os2, uint32_t nos1, uint32_t nassay, const uint32_t *__restrict__ live,
-	BoundHead *__restrict__ out_heads, uint32_t *__restrict__ out_index, uint32_t *__restrict__ count,
-	uint32_t *__restrict__ err_flags)
+// pass 1: stage-1 records [0, n1) (minus-strand primers); pass 2: stage-2 records [from, to)
+__global__ void k_live_compact(LiveArgs a, uint32_t from, uint32_t to, int pass)
 {
-	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
-		const BoundHead b = recs[i].h;
-		if (b.flags & (F_OOB | F_STACK | F_TRUNC)) atomicOr(err_flags, (uint32_t)b.flags);
-		const int assay = b.os < nos1 ? os1[b.os].assay : os2[b.os - nos1].assay;
-		const uint64_t key = (uint64_t)b.target*nassay + (uint32_t)assay;
-		if (!((live[key >> 5] >> (key & 31u)) & 1u)) continue;
-		const uint32_t slot = atomicAdd(count, 1u);
-		out_heads[slot] = b;
-		out_index[slot] = i;
+	for (uint32_t i = from + blockIdx.x*blockDim.x + threadIdx.x; i < to; i += gridDim.x*blockDim.x) {
+		const BoundHead b = a.recs[i].h;
+		bool keep;
+		if (pass == 1) {
+			if (b.flags & (F_OOB | F_STACK | F_TRUNC)) atomicOr(a.err_flags, (uint32_t)b.flags);
+			const uint64_t key = live_key(a, b.target, a.os1[b.os].assay, b.loc5);
+			keep = live_test(a.live_r, key) || live_test(a.live_r, key + 1); // bucket nbucket-1 is never marked
+			if (keep) atomicOr(a.live_f + (key >> 5), 1u << (key & 31u));
+		}
+		else {
+			const uint64_t key = live_key(a, b.target, a.os2[b.os - a.nos1].assay, b.loc5);
+			// a mark in the bucket before belongs to this group only if this is not the group's first bucket
+			const bool first = (key % a.nbucket) == 0;
+			keep = live_test(a.live_f, key) || (!first && live_test(a.live_f, key - 1));
+		}
+		if (!keep) continue;
+		const uint32_t slot = atomicAdd(a.count, 1u);
+		a.out_heads[slot] = b;
+		a.out_index[slot] = i;
 	}
 }
 
