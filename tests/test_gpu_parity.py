@@ -499,3 +499,68 @@ def test_search_both_scan_kernels(engine_lib, oracle, monkeypatch, mode):
                 assert_hits_equal(e, [h for h in got if h.target_id == t and h.assay_index == i], want, a)
     finally:
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Alignment tiers.  The lean tier (2-bit trace, gapless evaluator) takes most windows, the
+# full-trace tier the rest; TNT_NO_LEAN routes every window through the full-trace tier.  All of
+# them must reproduce the oracle for other temperatures / salt and with dangling ends enabled
+# (virtual bases in the alignment: the lean tier then falls back to the general evaluator).
+@pytest.mark.parametrize("T,na,d5,d3,no_lean", [
+    (310.15, 0.05, 1, 1, False),
+    (310.15, 0.05, 1, 0, False),
+    (310.15, 0.05, 0, 1, False),
+    (330.15, 0.1, 0, 0, False),
+    (295.15, 1.0, 0, 0, False),
+    (310.15, 0.05, 0, 0, True),
+    (310.15, 0.05, 1, 1, True),
+])
+def test_align_tiers_and_parameters(engine_lib, oracle, monkeypatch, T, na, d5, d3, no_lean):
+    from thermonucleotideblast_b200 import Engine
+    if no_lean:
+        monkeypatch.setenv("TNT_NO_LEAN", "1")
+    rng = np.random.default_rng(int(T * 10) + d5 * 2 + d3 + (7 if no_lean else 0))
+    n = 60000
+    codes = gen.random_codes(n, rng)
+    oligos = [gen.rand_oligo(L, rng) for L in (17, 19, 21, 22, 23, 26, 27, 33, 41, 55)]
+    for i, ol in enumerate(oligos):
+        for k in range(10):
+            text = gen.mutate(gen.revcomp(ol) if k % 2 else ol, k % 5, rng)
+            gen.plant(codes, 1500 + (i * 10 + k) * 450, text)
+    gen.plant(codes, 0, gen.revcomp(oligos[3])[2:])
+    gen.plant(codes, n - 12, oligos[4][:12])
+    with Engine(target_T=T, salt=na, dangle5=bool(d5), dangle3=bool(d3)) as e:
+        tid = e.add_target(codes)
+        nvalid = 0
+        for ol in oligos:
+            for plus in (False, True):
+                seeds = oracle.seeds(codes, ol, 7, plus, unique=True)
+                nvalid += _compare_align(e, oracle, tid, codes, ol, plus, seeds, T=T, na=na, d5=d5, d3=d3)
+        assert nvalid > 500
+
+
+def test_search_lean_and_full_tiers_agree(engine_lib, oracle, monkeypatch):
+    """The same TaqMan batch search with and without the lean tier: both equal the oracle."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(97531)
+    db = [gen.random_codes(int(rng.integers(15000, 30000)), rng) for _ in range(4)]
+    assays = gen.make_assays(rng, db, 6, "taqman", variants=3)
+    o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+    want = {(t, i): oracle.search(codes, a[0], a[1], a[2], o) for t, codes in enumerate(db) for i, a in enumerate(assays)}
+    assert sum(len(v) for v in want.values()) >= 6
+    for no_lean in (False, True):
+        if no_lean:
+            monkeypatch.setenv("TNT_NO_LEAN", "1")
+        else:
+            monkeypatch.delenv("TNT_NO_LEAN", raising=False)
+        with Engine() as e:
+            for c in db:
+                e.add_target(c)
+            e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+            got = e.search(to_opts(o))
+            n = 0
+            for (t, i), w in want.items():
+                mine = [h for h in got if h.target_id == t and h.assay_index == i]
+                assert_hits_equal(e, mine, w, assays[i])
+                n += len(mine)
+            assert n == len(got)
