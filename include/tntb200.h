@@ -138,6 +138,13 @@ void tnt_engine_destroy(tnt_engine *e);
  * staged through pinned memory, packed on the device to 2 bit/base + a 1 bit/base non-ACGT
  * mask + a sparse list of the non-ACGT codes, and stay resident in HBM until cleared. */
 int tnt_engine_add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *target_id);
+/* The same for n fragments in one call (ids first_target_id .. first_target_id + n - 1): what the
+ * reference's work loop (tntblast_local.cpp:400-534) does for a run of queue entries.
+ * Transfers are asynchronous: when a `codes` buffer is page-locked (cudaHostAlloc /
+ * cudaHostRegister) it is read by DMA after the call returns and must stay valid and unchanged
+ * until the next tnt_engine_search (or any other call that reads the fragments) has returned;
+ * pageable buffers are copied before the call returns. */
+int tnt_engine_add_targets(tnt_engine *e, const uint8_t *const *codes, const uint32_t *lens, uint32_t n, uint32_t *first_target_id);
 int tnt_engine_clear_targets(tnt_engine *e);
 
 int tnt_engine_set_assays(tnt_engine *e, const tnt_assay *assays, int32_t n);

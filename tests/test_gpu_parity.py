@@ -564,3 +564,52 @@ def test_search_lean_and_full_tiers_agree(engine_lib, oracle, monkeypatch):
                 assert_hits_equal(e, mine, w, assays[i])
                 n += len(mine)
             assert n == len(got)
+
+
+def test_upload_paths_agree(engine_lib, monkeypatch):
+    """Fragments reach the device through a ring of staging slots on an upload stream while stage 1
+    already runs on the first batches.  Pageable vs page-locked sources, one call per fragment vs
+    tnt_engine_add_targets, a full-size ring vs a two-slot ring that has to recycle slots (and with
+    them the lazy emission of the non-ACGT lists): the hit lists must be identical."""
+    import torch
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(20261)
+    nfrag, flen = 5, 24_000_000              # 120 MB: four upload batches
+    F, R, P = gen.rand_oligo(20, rng), gen.rand_oligo(21, rng), gen.rand_oligo(25, rng)
+    amp = F + gen.rand_oligo(30, rng) + P + gen.rand_oligo(40, rng) + gen.revcomp(R)
+    pinned = torch.empty(nfrag * flen, dtype=torch.uint8, pin_memory=True).numpy()
+    pinned[:] = rng.integers(0, 4, size=nfrag * flen, dtype=np.uint8)
+    frags_pinned = [pinned[i * flen:(i + 1) * flen] for i in range(nfrag)]
+    for i, f in enumerate(frags_pinned):
+        gen.plant(f, 1000 + i * 4_000_000, amp if i % 2 == 0 else gen.revcomp(amp))
+        gen.plant(f, flen - 5000, gen.mutate(amp, 2, rng))
+        f[rng.integers(0, flen, size=2000)] = 15       # N: exceptions in every batch
+        f[10_000_000:10_000_400] = 15
+    frags_pageable = [f.copy() for f in frags_pinned]
+    opts = H.default_options(min_primer_tm=45.0, min_probe_tm=45.0)
+    assays = [Assay(0, F, R, P)]
+
+    def run(frags, batch_call, slots):
+        if slots:
+            monkeypatch.setenv("TNT_UPLOAD_SLOTS", str(slots))
+        else:
+            monkeypatch.delenv("TNT_UPLOAD_SLOTS", raising=False)
+        with Engine() as e:
+            e.set_assays(assays)
+            if batch_call:
+                e.add_targets(frags)
+            else:
+                for f in frags:
+                    e.add_target(f)
+            hits = e.search(to_opts(opts))
+            out = [(h.target_id,) + hit_key(e, h, (F, R, P)) + hit_floats(h) for h in hits]
+            # a second search on the now resident fragments must not change anything
+            again = e.search(to_opts(opts))
+            assert [(h.target_id,) + hit_key(e, h, (F, R, P)) + hit_floats(h) for h in again] == out
+            return out
+
+    base = run(frags_pageable, False, 0)
+    assert len(base) >= 2 * nfrag
+    assert run(frags_pinned, True, 0) == base
+    assert run(frags_pageable, True, 2) == base
+    assert run(frags_pinned, False, 2) == base

@@ -6,8 +6,8 @@ The CUDA shared library is required; there is no CPU fallback.
 """
 from .engine import (ASSAY_MIPS, ASSAY_PADLOCK, ASSAY_PCR, ASSAY_PROBE, MINUS, OLIGO_F, OLIGO_NONE,  # noqa: F401
                      OLIGO_P, OLIGO_R, PLUS, STRAND_BOTH, STRAND_MINUS, STRAND_PLUS, Assay, Engine,
-                     EngineError, Hit, SearchOptions, load_library, search_options)
+                     EngineError, FragmentList, Hit, SearchOptions, load_library, search_options)
 from .sharding import shard_targets  # noqa: F401
 
-__all__ = ["Engine", "EngineError", "Assay", "Hit", "SearchOptions", "search_options", "load_library",
+__all__ = ["Engine", "EngineError", "FragmentList", "Assay", "Hit", "SearchOptions", "search_options", "load_library",
            "shard_targets"]

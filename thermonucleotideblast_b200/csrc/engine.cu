@@ -66,6 +66,10 @@ template <class T>
 struct DevBuf {
 	T *p = nullptr;
 	size_t cap = 0;
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	DevBuf(DevBuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
 	~DevBuf() { if (p) cudaFree(p); }
 	// grow to at least n elements; `keep` elements of the old contents survive
 	void reserve(size_t n, size_t keep, cudaStream_t st)
@@ -86,7 +90,8 @@ struct DevBuf {
 	}
 };
 
-constexpr size_t STAGE_BYTES = 32u << 20; // pinned staging buffers (x2)
+constexpr size_t STAGE_BYTES = 32u << 20; // one upload batch
+constexpr size_t MAX_SLOTS = 32;          // device staging ring: up to 1 GB of fragment bytes in flight
 
 struct AssayHost {
 	int id;
@@ -150,13 +155,30 @@ struct tnt_engine {
 	int batch_slot = 0;
 	uint64_t batch_base = 0;
 	uint32_t batch_used = 0;
-	// exception emission of the previous batch, issued once its count has arrived
-	bool emit_pending = false;
-	int emit_slot = 0;
-	uint32_t emit_n = 0, emit_blocks = 0;
-	uint64_t emit_base = 0;
-	cudaEvent_t count_ready[2]{};
-	DevBuf<uint32_t> block_count2[2];
+	// Upload pipeline (own stream): a ring of device staging slots, one per batch in flight.  A
+	// slot is recycled once the exceptions (non-ACGT codes) of its batch have been emitted, which
+	// needs the batch's exception count on the host; emission is therefore lazy (polled), and a
+	// search can start on the first batches while later ones are still crossing PCIe.
+	cudaStream_t up_stream = nullptr;
+	cudaStream_t emit_stream = nullptr; // exception emission: ordered by per-batch events, not behind later copies
+	cudaEvent_t pads_ev = nullptr;      // read-ahead pads behind the last batch written
+	struct Slot {
+		uint8_t *d_stage = nullptr;
+		cudaEvent_t free_ev = nullptr;    // slot contents fully consumed (pack + exception emission)
+		cudaEvent_t count_ev = nullptr;   // exception count of the batch is on the host
+		cudaEvent_t packed_ev = nullptr;  // db2 / nmask of the batch are written
+		DevBuf<uint32_t> block_count;
+	};
+	std::vector<Slot> slots;
+	size_t max_slots = 0;             // ring size (MAX_SLOTS; TNT_UPLOAD_SLOTS shrinks it for tests)
+	struct Batch { uint64_t base; uint32_t used; int slot; uint32_t nblocks; };
+	std::vector<Batch> batches;       // of the registered fragments, ascending base
+	size_t next_emit = 0;             // batches[next_emit..] still owe their exceptions
+	// host -> staging copies of the open batch, issued as one batched copy when the batch is flushed
+	std::vector<void *> piece_dst, piece_src;
+	std::vector<size_t> piece_size;
+	bool piece_uses_mirror = false;
+	cudaEvent_t emit_done = nullptr;  // recorded on emit_stream after the latest emission
 	uint64_t upload_launches = 0;
 	uint64_t total_bases = 0;
 	std::vector<Target> targets;
@@ -165,11 +187,11 @@ struct tnt_engine {
 	std::vector<ScanTile> tiles;      // SCAN_TILE-sized
 	DevBuf<ScanTile> d_tiles;
 
-	uint8_t *h_stage[2] = {nullptr, nullptr};
-	uint8_t *d_stage[2] = {nullptr, nullptr};
-	cudaEvent_t stage_free[2]{};
-	uint64_t *h_total = nullptr; // pinned [2]
-	uint64_t *d_total = nullptr; // [2]
+	uint8_t *h_stage[2] = {nullptr, nullptr}; // pinned mirrors for pageable sources (batch k uses k & 1)
+	cudaEvent_t h_free[2]{};
+	size_t h_mirror_batch[2] = {~(size_t)0, ~(size_t)0}; // batch each mirror currently serves
+	uint64_t *h_total = nullptr; // pinned [MAX_SLOTS]
+	uint64_t *d_total = nullptr; // [MAX_SLOTS]
 
 	std::vector<AssayHost> assays;
 
@@ -213,12 +235,22 @@ struct tnt_engine {
 
 	~tnt_engine()
 	{
+		if (up_stream) cudaStreamSynchronize(up_stream);
+		if (emit_stream) cudaStreamSynchronize(emit_stream);
 		for (int i = 0; i < 2; ++i) {
 			if (h_stage[i]) cudaFreeHost(h_stage[i]);
-			if (d_stage[i]) cudaFree(d_stage[i]);
-			if (stage_free[i]) cudaEventDestroy(stage_free[i]);
-			if (count_ready[i]) cudaEventDestroy(count_ready[i]);
+			if (h_free[i]) cudaEventDestroy(h_free[i]);
 		}
+		for (Slot &sl : slots) {
+			if (sl.d_stage) cudaFree(sl.d_stage);
+			if (sl.free_ev) cudaEventDestroy(sl.free_ev);
+			if (sl.count_ev) cudaEventDestroy(sl.count_ev);
+			if (sl.packed_ev) cudaEventDestroy(sl.packed_ev);
+		}
+		if (emit_done) cudaEventDestroy(emit_done);
+		if (pads_ev) cudaEventDestroy(pads_ev);
+		if (emit_stream) cudaStreamDestroy(emit_stream);
+		if (up_stream) cudaStreamDestroy(up_stream);
 		if (h_total) cudaFreeHost(h_total);
 		if (h_heads) cudaFreeHost(h_heads);
 		if (h_live_index) cudaFreeHost(h_live_index);
@@ -236,11 +268,14 @@ struct tnt_engine {
 	}
 
 	void finish_upload();
+	void settle_upload();
+	bool upload_settled = false;
 	void reserve_heads(size_t n);
-	void sync_targets()
+	// `wait_upload` false: the caller (search stage 1) orders its work behind the per-batch events
+	void sync_targets(bool wait_upload = true)
 	{
+		if (wait_upload) finish_upload();
 		if (!targets_dirty) return;
-		finish_upload();
 		d_targets.upload(targets, stream);
 		tiles.clear();
 		for (uint32_t t = 0; t < targets.size(); ++t)
@@ -260,65 +295,107 @@ namespace {
 // The sparse non-ACGT list needs the exception count of a batch: it is read back asynchronously
 // and the ordered emission pass of batch i is issued while batch i+1 is being filled.
 // ------------------------------------------------------------------------------------------
-void issue_pending_emit(tnt_engine *e)
+// Emit the exceptions of batches whose count has arrived (all of them up to `through` when
+// `block`), in batch order: the list stays sorted by global position.
+void emit_ready(tnt_engine *e, bool block, size_t through = ~(size_t)0)
 {
-	if (!e->emit_pending) return;
-	const int slot = e->emit_slot;
-	CUDA_OK(cudaEventSynchronize(e->count_ready[slot]));
-	const uint64_t nexc = e->h_total[slot];
-	if (nexc) {
-		e->exc_pos.reserve(e->nexc + nexc, e->nexc, e->stream);
-		e->exc_code.reserve(e->exc_pos.cap, e->nexc, e->stream);
-		k_emit_exceptions<<<e->emit_blocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], e->emit_n, e->block_count2[slot].p,
-			e->nexc, e->emit_base, e->exc_pos.p, e->exc_code.p);
-		CUDA_OK(cudaGetLastError());
-		e->upload_launches++;
-		e->nexc += nexc;
+	bool any = false;
+	while (e->next_emit < e->batches.size()) {
+		if (!block || e->next_emit > through) {
+			if (!block && cudaEventQuery(e->slots[(size_t)e->batches[e->next_emit].slot].count_ev) != cudaSuccess) { cudaGetLastError(); break; }
+			if (block && e->next_emit > through) break;
+		}
+		const tnt_engine::Batch &bt = e->batches[e->next_emit];
+		tnt_engine::Slot &sl = e->slots[(size_t)bt.slot];
+		CUDA_OK(cudaEventSynchronize(sl.count_ev));
+		const uint64_t nexc = e->h_total[bt.slot];
+		if (nexc) {
+			if (e->nexc + nexc > e->exc_pos.cap) {
+				// growing frees the old arrays: nothing on the search stream may still read them
+				CUDA_OK(cudaStreamSynchronize(e->stream));
+				e->exc_pos.reserve(e->nexc + nexc, e->nexc, e->emit_stream);
+				e->exc_code.reserve(e->exc_pos.cap, e->nexc, e->emit_stream);
+			}
+			k_emit_exceptions<<<bt.nblocks, PACK_THREADS, 0, e->emit_stream>>>(sl.d_stage, bt.used, sl.block_count.p,
+				e->nexc, bt.base, e->exc_pos.p, e->exc_code.p);
+			CUDA_OK(cudaGetLastError());
+			e->upload_launches++;
+			e->nexc += nexc;
+		}
+		// the staging slot may be refilled once its emission has run (the count event already
+		// implies that the pack kernel is done with it)
+		CUDA_OK(cudaEventRecord(sl.free_ev, e->emit_stream));
+		++e->next_emit;
+		any = true;
 	}
-	// the staging slot may be refilled once everything queued so far has run
-	CUDA_OK(cudaEventRecord(e->stage_free[slot], e->stream));
-	e->emit_pending = false;
+	if (any) CUDA_OK(cudaEventRecord(e->emit_done, e->emit_stream));
 }
 
 void flush_batch(tnt_engine *e)
 {
 	if (!e->batch_open) return;
-	issue_pending_emit(e); // previous batch (other slot)
 	const int slot = e->batch_slot;
 	const uint32_t n = e->batch_used;
 	if (n) {
+		tnt_engine::Slot &sl = e->slots[(size_t)slot];
+		if (!e->piece_dst.empty()) {
+			// all fragment pieces of the batch in one call (a 1 Gbp database is ~2000 fragments: one
+			// cudaMemcpyAsync each costs more host and copy-engine time than the bytes themselves)
+			cudaMemcpyAttributes attr{};
+			attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+			size_t attr_idx = 0, fail = 0;
+			CUDA_OK(cudaMemcpyBatchAsync(e->piece_dst.data(), e->piece_src.data(), e->piece_size.data(), e->piece_dst.size(),
+				&attr, &attr_idx, 1, &fail, e->up_stream));
+			if (e->piece_uses_mirror) CUDA_OK(cudaEventRecord(e->h_free[e->batches.size() & 1u], e->up_stream));
+			e->piece_dst.clear();
+			e->piece_src.clear();
+			e->piece_size.clear();
+			e->piece_uses_mirror = false;
+		}
 		const uint64_t first_word = e->batch_base/32u;
 		const uint64_t need_words = first_word + ((uint64_t)n + 31u)/32u + 8;
 		if (need_words > e->db2.cap) {
-			e->db2.reserve(need_words, e->packed_words, e->stream);
-			e->nmask.reserve(e->db2.cap, e->packed_words, e->stream);
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+			e->db2.reserve(need_words, e->packed_words, e->up_stream);
+			e->nmask.reserve(e->db2.cap, e->packed_words, e->up_stream);
 		}
 		const uint32_t nblocks = (n + PACK_BASES_PER_BLOCK - 1)/PACK_BASES_PER_BLOCK;
-		e->block_count2[slot].reserve(nblocks, 0, e->stream);
-		k_pack<<<nblocks, PACK_THREADS, 0, e->stream>>>(e->d_stage[slot], n, e->db2.p, e->nmask.p, first_word, e->block_count2[slot].p);
-		k_scan_counts<<<1, 1024, 0, e->stream>>>(e->block_count2[slot].p, nblocks, e->d_total + slot);
+		sl.block_count.reserve(nblocks, 0, e->up_stream);
+		k_pack<<<nblocks, PACK_THREADS, 0, e->up_stream>>>(sl.d_stage, n, e->db2.p, e->nmask.p, first_word, sl.block_count.p);
+		CUDA_OK(cudaEventRecord(sl.packed_ev, e->up_stream));
+		k_scan_counts<<<1, 1024, 0, e->up_stream>>>(sl.block_count.p, nblocks, e->d_total + slot);
 		CUDA_OK(cudaGetLastError());
 		e->upload_launches += 2;
-		CUDA_OK(cudaMemcpyAsync(e->h_total + slot, e->d_total + slot, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
-		CUDA_OK(cudaEventRecord(e->count_ready[slot], e->stream));
+		CUDA_OK(cudaMemcpyAsync(e->h_total + slot, e->d_total + slot, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->up_stream));
+		CUDA_OK(cudaEventRecord(sl.count_ev, e->up_stream));
 		e->packed_words = first_word + ((uint64_t)n + 31u)/32u;
-		e->emit_pending = true;
-		e->emit_slot = slot;
-		e->emit_n = n;
-		e->emit_blocks = nblocks;
-		e->emit_base = e->batch_base;
+		e->batches.push_back(tnt_engine::Batch{e->batch_base, n, slot, nblocks});
 	}
 	e->batch_open = false;
 	e->batch_used = 0;
-	e->batch_slot = slot ^ 1;
+	emit_ready(e, false);
 }
 
 void open_batch(tnt_engine *e, uint64_t base)
 {
-	const int slot = e->batch_slot;
-	CUDA_OK(cudaEventSynchronize(e->stage_free[slot])); // previous user of this slot fully consumed
-	CUDA_OK(cudaMemsetAsync(e->d_stage[slot], 0, STAGE_BYTES, e->stream)); // alignment gaps pack as zero words
+	// next ring slot; a slot still owned by an older batch is released by emitting that batch
+	const size_t k = e->batches.size();
+	const size_t slot = k % e->max_slots;
+	if (slot >= e->slots.size()) {
+		e->slots.emplace_back();
+		tnt_engine::Slot &sl = e->slots.back();
+		CUDA_OK(cudaMalloc(&sl.d_stage, STAGE_BYTES));
+		CUDA_OK(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
+		CUDA_OK(cudaEventCreateWithFlags(&sl.count_ev, cudaEventDisableTiming));
+		CUDA_OK(cudaEventCreateWithFlags(&sl.packed_ev, cudaEventDisableTiming));
+	}
+	else if (k >= e->max_slots) {
+		emit_ready(e, true, k - e->max_slots);
+		CUDA_OK(cudaEventSynchronize(e->slots[slot].free_ev));
+	}
+	CUDA_OK(cudaMemsetAsync(e->slots[slot].d_stage, 0, STAGE_BYTES, e->up_stream)); // alignment gaps pack as zero words
 	e->batch_open = true;
+	e->batch_slot = (int)slot;
 	e->batch_base = base;
 	e->batch_used = 0;
 }
@@ -346,14 +423,24 @@ void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_
 	while (rem) {
 		if (e->batch_open && pos >= e->batch_base + STAGE_BYTES) flush_batch(e);
 		if (!e->batch_open) open_batch(e, pos);
-		const int slot = e->batch_slot;
+		uint8_t *dst = e->slots[(size_t)e->batch_slot].d_stage;
 		const uint32_t off = (uint32_t)(pos - e->batch_base);
 		const uint32_t n = (uint32_t)std::min<uint64_t>(rem, STAGE_BYTES - off);
-		if (pinned) CUDA_OK(cudaMemcpyAsync(e->d_stage[slot] + off, src, n, cudaMemcpyHostToDevice, e->stream));
-		else {
-			std::memcpy(e->h_stage[slot] + off, src, n);
-			CUDA_OK(cudaMemcpyAsync(e->d_stage[slot] + off, e->h_stage[slot] + off, n, cudaMemcpyHostToDevice, e->stream));
+		const uint8_t *from = src;
+		if (!pinned) {
+			// pageable source: through one of two pinned mirrors (alternating per batch)
+			const int hs = (int)(e->batches.size() & 1u);
+			if (e->h_mirror_batch[hs] != e->batches.size()) {
+				CUDA_OK(cudaEventSynchronize(e->h_free[hs]));
+				e->h_mirror_batch[hs] = e->batches.size();
+			}
+			std::memcpy(e->h_stage[hs] + off, src, n);
+			from = e->h_stage[hs] + off;
+			e->piece_uses_mirror = true;
 		}
+		e->piece_dst.push_back(dst + off);
+		e->piece_src.push_back(const_cast<uint8_t *>(from));
+		e->piece_size.push_back(n);
 		e->batch_used = off + n;
 		pos += n;
 		src += n;
@@ -364,6 +451,7 @@ void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_
 	e->total_bases += len;
 	e->targets.push_back(tg);
 	e->targets_dirty = true;
+	e->upload_settled = false;
 	if (id_out) *id_out = (uint32_t)e->targets.size() - 1;
 }
 
@@ -387,19 +475,36 @@ void tnt_engine::reserve_heads(size_t n)
 	}
 }
 
+// Everything registered so far packed, exceptions emitted, visible to the search stream.
 void tnt_engine::finish_upload()
 {
+	if (!batch_open && next_emit == batches.size() && upload_settled) return;
 	flush_batch(this);
-	issue_pending_emit(this);
+	emit_ready(this, true);
+	settle_upload();
+}
+
+// Pads and ordering once all batches are enqueued (does not wait for the emission of exceptions).
+void tnt_engine::settle_upload()
+{
 	// read-ahead pad of the scan / window loads
 	const uint64_t need = packed_words + 8;
 	if (need > db2.cap) {
-		db2.reserve(need, packed_words, stream);
-		nmask.reserve(db2.cap, packed_words, stream);
+		CUDA_OK(cudaStreamSynchronize(stream));
+		db2.reserve(need, packed_words, up_stream);
+		nmask.reserve(db2.cap, packed_words, up_stream);
 	}
-	CUDA_OK(cudaMemsetAsync(db2.p + packed_words, 0, 8*sizeof(uint64_t), stream));
-	CUDA_OK(cudaMemsetAsync(nmask.p + packed_words, 0, 8*sizeof(uint32_t), stream));
-	if (exc_pos.cap == 0) { exc_pos.reserve(16, 0, stream); exc_code.reserve(16, 0, stream); }
+	CUDA_OK(cudaMemsetAsync(db2.p + packed_words, 0, 8*sizeof(uint64_t), up_stream));
+	CUDA_OK(cudaMemsetAsync(nmask.p + packed_words, 0, 8*sizeof(uint32_t), up_stream));
+	CUDA_OK(cudaEventRecord(pads_ev, up_stream));
+	if (exc_pos.cap == 0) { exc_pos.reserve(16, 0, emit_stream); exc_code.reserve(16, 0, emit_stream); }
+	if (next_emit == batches.size()) {
+		// fully uploaded: later work on the search stream simply follows the upload streams
+		CUDA_OK(cudaEventRecord(emit_done, emit_stream));
+		CUDA_OK(cudaStreamWaitEvent(stream, emit_done, 0));
+		CUDA_OK(cudaStreamWaitEvent(stream, pads_ev, 0));
+		upload_settled = true;
+	}
 }
 
 namespace {
@@ -861,9 +966,50 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 
 	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
 
+	// Fragments may still be on their way to the device (upload stream).  Then the pass is cut at
+	// groups of upload batches and every chunk is ordered behind the batches it reads, so the
+	// first chunks are scanned and aligned while the rest of the database crosses PCIe.
+	struct Gate { uint32_t tile_end; size_t batch; };
+	std::vector<Gate> gates;
+	if (!e->upload_settled && !e->batches.empty()) {
+		const size_t group = 1; // batches per gate (32 MB); a chunk takes every gate that is already open
+		uint32_t t = 0;
+		for (size_t b = group - 1;; b += group) {
+			const size_t bi = std::min(b, e->batches.size() - 1);
+			const bool last = bi + 1 == e->batches.size();
+			const uint64_t gend = e->batches[bi].base + e->batches[bi].used;
+			while (t < tiles.size()) {
+				const Target &tg = e->targets[tiles[t].target];
+				// k-mers and alignment windows read a little past the tile, never past the fragment
+				const uint64_t need = tg.base + std::min<uint64_t>((uint64_t)tiles[t].start + plan.tile_bases + 192, tg.len);
+				if (!last && need > gend) break;
+				++t;
+			}
+			if (last) t = (uint32_t)tiles.size();
+			if (gates.empty() || t > gates.back().tile_end) gates.push_back(Gate{t, bi});
+			else gates.back().batch = bi;
+			if (last) break;
+		}
+	}
+	size_t gate = 0;
+
 	uint32_t t0 = 0;
 	while (t0 < tiles.size()) {
 		uint32_t t1 = (uint32_t)std::min<size_t>(tiles.size(), (size_t)t0 + tiles_per_chunk);
+		if (!gates.empty()) {
+			while (gates[gate].tile_end <= t0) ++gate;
+			// as far as the upload has come (at least one gate: the stream then waits for it)
+			while (gate + 1 < gates.size() &&
+				cudaEventQuery(e->slots[(size_t)e->batches[gates[gate + 1].batch].slot].count_ev) == cudaSuccess) ++gate;
+			cudaGetLastError();
+			t1 = std::min(t1, gates[gate].tile_end);
+			const size_t bi = gates[gate].batch;
+			HostTimer t_gate("  upload gate (host wait)");
+			emit_ready(e, true, bi); // exceptions of these batches (the host waits for their counts only)
+			if (bi + 1 == e->batches.size()) CUDA_OK(cudaStreamWaitEvent(e->stream, e->pads_ev, 0)); // + the read-ahead pads
+			CUDA_OK(cudaStreamWaitEvent(e->stream, e->slots[(size_t)e->batches[bi].slot].packed_ev, 0));
+			CUDA_OK(cudaStreamWaitEvent(e->stream, e->emit_done, 0));
+		}
 		uint32_t forced_cap = 0; // set after an overflow, when the real bucket sizes are known
 		for (;;) {
 			const uint32_t ntiles = t1 - t0;
@@ -882,6 +1028,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 			float ms = 0;
 			CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
 			e->stats.scan_ms += ms;
+			if (HostTimer::enabled()) fprintf(stderr, "[tnt]   scan of tiles [%u, %u): %.3f ms, bucket capacity %u\n", t0, t1, ms, cap);
 			if (ok) {
 				uint64_t bases = 0;
 				for (uint32_t t = t0; t < t1; ++t)
@@ -900,6 +1047,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 		}
 		t0 = t1;
 	}
+	if (!gates.empty() && e->next_emit == e->batches.size()) e->upload_settled = true; // everything waited for
 }
 
 // Stage-2: scan regions with the given set
@@ -1030,7 +1178,10 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	e->stats = tnt_stats{};
 	e->last_opt = o;
 	e->stats.db_bases = e->total_bases;
-	e->sync_targets();
+	// no waiting for fragments still in flight: stage 1 orders itself behind the upload batches
+	flush_batch(e);
+	e->settle_upload();
+	e->sync_targets(false);
 	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
 	cudaEvent_t t_begin = e->ev[4], t_end = e->ev[5];
 	CUDA_OK(cudaEventRecord(t_begin, e->stream));
@@ -1282,14 +1433,19 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 	e->sm_count = prop.multiProcessorCount;
 	CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
 	for (auto &ev : e->ev) CUDA_OK(cudaEventCreate(&ev));
+	CUDA_OK(cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
+	e->slots.reserve(MAX_SLOTS);
+	e->max_slots = MAX_SLOTS;
+	if (const char *v = std::getenv("TNT_UPLOAD_SLOTS")) e->max_slots = (size_t)std::min<long>(MAX_SLOTS, std::max<long>(2, std::atol(v)));
+	CUDA_OK(cudaEventCreateWithFlags(&e->emit_done, cudaEventDisableTiming));
+	CUDA_OK(cudaStreamCreateWithFlags(&e->emit_stream, cudaStreamNonBlocking));
+	CUDA_OK(cudaEventCreateWithFlags(&e->pads_ev, cudaEventDisableTiming));
 	for (int i = 0; i < 2; ++i) {
 		CUDA_OK(cudaMallocHost(&e->h_stage[i], STAGE_BYTES));
-		CUDA_OK(cudaMalloc(&e->d_stage[i], STAGE_BYTES));
-		CUDA_OK(cudaEventCreateWithFlags(&e->stage_free[i], cudaEventDisableTiming));
-		CUDA_OK(cudaEventCreateWithFlags(&e->count_ready[i], cudaEventDisableTiming));
+		CUDA_OK(cudaEventCreateWithFlags(&e->h_free[i], cudaEventDisableTiming));
 	}
-	CUDA_OK(cudaMallocHost(&e->h_total, 2*sizeof(uint64_t)));
-	CUDA_OK(cudaMalloc(&e->d_total, 2*sizeof(uint64_t)));
+	CUDA_OK(cudaMallocHost(&e->h_total, MAX_SLOTS*sizeof(uint64_t)));
+	CUDA_OK(cudaMalloc(&e->d_total, MAX_SLOTS*sizeof(uint64_t)));
 	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
 	e->d_thermo.reserve(1, 0, e->stream);
 	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
@@ -1323,11 +1479,25 @@ int tnt_engine_add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uin
 	API_END
 }
 
+int tnt_engine_add_targets(tnt_engine *e, const uint8_t *const *codes, const uint32_t *lens, uint32_t n, uint32_t *first_target_id)
+{
+	API_BEGIN
+	if (!e || ((!codes || !lens) && n)) throw std::runtime_error("null argument");
+	if (first_target_id) *first_target_id = (uint32_t)e->targets.size();
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!codes[i] && lens[i]) throw std::runtime_error("null argument");
+		add_target(e, codes[i], lens[i], nullptr);
+	}
+	API_END
+}
+
 int tnt_engine_clear_targets(tnt_engine *e)
 {
 	API_BEGIN
 	if (!e) throw std::runtime_error("null argument");
 	CUDA_OK(cudaSetDevice(e->prm.device));
+	CUDA_OK(cudaStreamSynchronize(e->up_stream));
+	CUDA_OK(cudaStreamSynchronize(e->emit_stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	e->targets.clear();
 	e->tiles.clear();
@@ -1336,7 +1506,14 @@ int tnt_engine_clear_targets(tnt_engine *e)
 	e->nexc = 0;
 	e->batch_open = false;
 	e->batch_used = 0;
-	e->emit_pending = false;
+	e->batches.clear();
+	e->piece_dst.clear();
+	e->piece_src.clear();
+	e->piece_size.clear();
+	e->piece_uses_mirror = false;
+	e->next_emit = 0;
+	e->upload_settled = false;
+	e->h_mirror_batch[0] = e->h_mirror_batch[1] = ~(size_t)0;
 	e->total_bases = 0;
 	e->targets_dirty = true;
 	e->hits.clear();

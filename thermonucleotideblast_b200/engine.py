@@ -150,6 +150,7 @@ def load_library() -> C.CDLL:
     L.tnt_engine_destroy.argtypes = [vp]
     L.tnt_engine_destroy.restype = None
     L.tnt_engine_add_target.argtypes = [vp, u8p, C.c_uint32, u32p]
+    L.tnt_engine_add_targets.argtypes = [vp, C.POINTER(C.c_void_p), u32p, C.c_uint32, u32p]
     L.tnt_engine_clear_targets.argtypes = [vp]
     L.tnt_engine_set_assays.argtypes = [vp, C.POINTER(CAssay), C.c_int32]
     L.tnt_engine_search.argtypes = [vp, C.POINTER(SearchOptions)]
@@ -169,6 +170,17 @@ def load_library() -> C.CDLL:
 
 class EngineError(RuntimeError):
     pass
+
+
+class FragmentList:
+    """Pointer and length arrays of a list of host fragments, as tnt_engine_add_targets takes them
+    (what a C++ host holds anyway).  Keeps the arrays alive."""
+
+    def __init__(self, fragments: Sequence[np.ndarray]):
+        self.arrays = [np.ascontiguousarray(f, dtype=np.uint8) for f in fragments]
+        self.n = len(self.arrays)
+        self.ptrs = (C.c_void_p * max(self.n, 1))(*[a.ctypes.data for a in self.arrays])
+        self.lens = (C.c_uint32 * max(self.n, 1))(*[a.size for a in self.arrays])
 
 
 class Engine:
@@ -213,6 +225,15 @@ class Engine:
         tid = C.c_uint32()
         self._check(self.L.tnt_engine_add_target(self.h, a.ctypes.data_as(C.POINTER(C.c_uint8)), a.size, C.byref(tid)))
         return tid.value
+
+    def add_targets(self, fragments) -> int:
+        """Register many fragments with one call; returns the id of the first.  `fragments` is a
+        sequence of uint8 arrays or a FragmentList (the marshalled pointer / length arrays, reusable
+        when the same host buffers are registered again)."""
+        fl = fragments if isinstance(fragments, FragmentList) else FragmentList(fragments)
+        first = C.c_uint32()
+        self._check(self.L.tnt_engine_add_targets(self.h, fl.ptrs, fl.lens, fl.n, C.byref(first)))
+        return first.value
 
     def clear_targets(self):
         self._check(self.L.tnt_engine_clear_targets(self.h))
