@@ -216,7 +216,10 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_live_index;
 	uint32_t *h_live_index = nullptr; // pinned
 	size_t h_live_index_cap = 0;
-	DevBuf<SlowItem> d_slow, d_retry;
+	DevBuf<SlowItem> d_slow;
+	DevBuf<Candidate> d_retry_cand;   // hand-over to the full-trace tier, one segment per oligo strand
+	DevBuf<uint32_t> d_retry_slot;
+	DevBuf<uint32_t> d_retry_ctl;     // base[nos] | cap[nos] | fill[nos*COUNT_STRIDE]
 	DevBuf<Candidate> d_slow_cand;
 	DevBuf<uint32_t> d_slot_map;
 	DevBuf<uint32_t> d_group;
@@ -828,6 +831,20 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 	const uint32_t base_count = e->n_bound;
 	size_t out_cap = emit_all ? (size_t)base_count + total : std::max<size_t>(e->d_bound.cap, (size_t)base_count + (1u << 16));
 	size_t slow_cap = std::max<size_t>(e->d_slow.cap, 1u << 16);
+	// full-trace hand-over segments: a few per cent of a strand's candidates are expected
+	std::vector<uint32_t> retry_ctl(2*nos, 0); // base | cap
+	auto size_retry_segments = [&](const std::vector<uint32_t> *need) {
+		uint64_t at = 0;
+		for (size_t s = 0; s < nos; ++s) {
+			const uint64_t cap_s = need ? (uint64_t)(*need)[s] + (*need)[s]/8 + 64 : (counts[s] ? (uint64_t)counts[s]/8 + 256 : 0);
+			retry_ctl[s] = (uint32_t)at;
+			retry_ctl[nos + s] = (uint32_t)std::min<uint64_t>(cap_s, counts[s]);
+			at += retry_ctl[nos + s];
+		}
+		if (at >= ((uint64_t)1 << 32)) throw std::runtime_error("internal: hand-over list too large");
+		return (size_t)at;
+	};
+	size_t retry_total = size_retry_segments(nullptr);
 	// snapshot of the DP-cell counter so that a retried pass is not counted twice
 	unsigned long long cells_before = 0;
 	CUDA_OK(cudaMemcpyAsync(&cells_before, e->d_cells.p, sizeof(cells_before), cudaMemcpyDeviceToHost, e->stream));
@@ -837,7 +854,11 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		e->d_bound.reserve(out_cap, base_count, e->stream);
 		out_cap = e->d_bound.cap;
 		e->d_slow.reserve(slow_cap, 0, e->stream);
-		e->d_retry.reserve(slow_cap, 0, e->stream);
+		e->d_retry_cand.reserve(std::max<size_t>(retry_total, 1), 0, e->stream);
+		e->d_retry_slot.reserve(std::max<size_t>(retry_total, 1), 0, e->stream);
+		e->d_retry_ctl.reserve(2*nos + nos*COUNT_STRIDE, 0, e->stream);
+		CUDA_OK(cudaMemcpyAsync(e->d_retry_ctl.p, retry_ctl.data(), 2*nos*sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+		CUDA_OK(cudaMemsetAsync(e->d_retry_ctl.p + 2*nos, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 		{
 			const uint32_t init[3] = {base_count, 0, 0};
 			CUDA_OK(cudaMemcpyAsync(e->d_out_count.p, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
@@ -863,8 +884,11 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		a.p5_tab = e->d_p5.p;
 		a.slow = e->d_slow.p;
 		a.slow_count = e->d_out_count.p + 1;
-		a.retry = e->d_retry.p;
-		a.retry_count = e->d_out_count.p + 2;
+		a.retry_cand = e->d_retry_cand.p;
+		a.retry_slot = e->d_retry_slot.p;
+		a.retry_base = e->d_retry_ctl.p;
+		a.retry_cap = e->d_retry_ctl.p + nos;
+		a.retry_fill = e->d_retry_ctl.p + 2*nos;
 		a.slow_cap = (uint32_t)slow_cap;
 
 		float ms = 0;
@@ -875,9 +899,19 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		if (!by_class[nclass].empty()) ms += run_align_kernel(e, set, a, by_class[nclass], 0, set.max_len);
 
 		uint32_t cnt[3] = {0, 0, 0};
+		std::vector<uint32_t> retry_fill(nos);
 		CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaMemcpy2DAsync(retry_fill.data(), sizeof(uint32_t), e->d_retry_ctl.p + 2*nos, COUNT_STRIDE*sizeof(uint32_t),
+			sizeof(uint32_t), nos, cudaMemcpyDeviceToHost, e->stream));
 		CUDA_OK(cudaStreamSynchronize(e->stream));
-		if (cnt[1] > slow_cap || cnt[2] > slow_cap) { slow_cap = (size_t)std::max(cnt[1], cnt[2])*5/4; continue; }
+		if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1]*5/4; continue; }
+		{
+			bool overflow = false;
+			uint64_t n_retry = 0;
+			for (size_t s = 0; s < nos; ++s) { overflow = overflow || retry_fill[s] > retry_ctl[nos + s]; n_retry += retry_fill[s]; }
+			if (overflow) { retry_total = size_retry_segments(&retry_fill); continue; } // the counters kept counting: exact sizes now
+			cnt[2] = (uint32_t)n_retry;
+		}
 		if (HostTimer::enabled())
 			fprintf(stderr, "[tnt]   candidates %llu, full-trace retry %u, generic %u, fast ms %.3f\n", (unsigned long long)total, cnt[2], cnt[1], ms);
 
@@ -909,11 +943,12 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		if (cnt[2]) {
 			// optimal path enters a gap state: full-trace variant of the fast kernel
 			std::vector<std::vector<AlignGroup>> retry_units(nclass);
-			regroup(e->d_retry, cnt[2], &retry_units, nullptr);
+			for (size_t s2 = 0; s2 < nos; ++s2)
+				if (retry_fill[s2]) retry_units[std::min(class_of(s2), nclass - 1)].push_back(AlignGroup{(uint32_t)s2, retry_ctl[s2], retry_fill[s2], 0u});
 			AlignArgs g = a;
-			g.cand = e->d_slow_cand.p;
-			g.cap = 0; // units index the compacted array directly
-			g.slot_map = emit_all ? e->d_slot_map.p : nullptr;
+			g.cand = e->d_retry_cand.p;
+			g.cap = 0; // units index the segments directly
+			g.slot_map = emit_all ? e->d_retry_slot.p : nullptr;
 			for (int c = 0; c < nclass; ++c)
 				if (!retry_units[c].empty()) ms += run_align_kernel(e, set, g, retry_units[c], kFastClasses[c], set.max_len, true);
 			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, 2*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));

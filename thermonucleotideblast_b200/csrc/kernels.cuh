@@ -659,8 +659,12 @@ struct AlignArgs {
 	const int32_t *p5_tab;     // [20]
 	SlowItem *slow;            // -> generic kernel
 	uint32_t *slow_count;
-	SlowItem *retry;           // -> full-trace fast kernel
-	uint32_t *retry_count;
+	// -> full-trace fast kernel: handed over in per-oligo-strand segments (no regrouping pass)
+	Candidate *retry_cand;      // segment of strand s: [retry_base[s], retry_base[s] + retry_cap[s])
+	uint32_t *retry_slot;       // output slot of each handed-over candidate (emit_all)
+	const uint32_t *retry_base;
+	const uint32_t *retry_cap;
+	uint32_t *retry_fill;       // per strand, COUNT_STRIDE apart; keeps counting past the capacity
 	uint32_t slow_cap;         // capacity of both lists
 };
 
@@ -1132,15 +1136,24 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 		}
 		if (handoff) {
 			my_cells -= (unsigned long long)(os.len*Lt); // counted again by the kernel that takes over
-			uint32_t *counter = handoff == 1 ? a.retry_count : a.slow_count;
-			SlowItem *list = handoff == 1 ? a.retry : a.slow;
-			const uint32_t sl = atomicAdd(counter, 1u);
-			if (sl < a.slow_cap) {
-				SlowItem it;
-				it.os = unit.os;
-				it.slot = a.slot_map ? a.slot_map[idx] : idx;
-				it.c = c;
-				list[sl] = it;
+			const uint32_t out_slot = a.slot_map ? a.slot_map[idx] : idx;
+			if (handoff == 1 && !FULL) {
+				const uint32_t sl = atomicAdd(a.retry_fill + (size_t)unit.os*COUNT_STRIDE, 1u);
+				if (sl < a.retry_cap[unit.os]) {
+					const uint32_t at = a.retry_base[unit.os] + sl;
+					a.retry_cand[at] = c;
+					a.retry_slot[at] = out_slot;
+				}
+			}
+			else {
+				const uint32_t sl = atomicAdd(a.slow_count, 1u);
+				if (sl < a.slow_cap) {
+					SlowItem it;
+					it.os = unit.os;
+					it.slot = out_slot;
+					it.c = c;
+					a.slow[sl] = it;
+				}
 			}
 			continue;
 		}
