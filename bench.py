@@ -91,9 +91,11 @@ def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False, kin
 class ClockSampler:
     """SM clock / throttle reasons during the timed region (B200_PROFILING.md) through NVML.
 
-    Samples are taken synchronously between steps of the timed loop (at most `max_samples`, evenly
-    spaced): a concurrently polling nvidia-smi / NVML thread was measured to slow the CUDA API calls
-    of the step by >30 %, so the sampling cost is kept small and lands honestly inside the timing."""
+    At most `max_samples` steps are sampled, each exactly once, from a helper thread that fires a
+    fixed delay into the step, i.e. while the alignment kernels are running (a continuously
+    polling nvidia-smi / NVML thread was measured to slow the CUDA API calls of a step by >30 %,
+    and on some boxes one NVML query takes ~20 ms).  The step waits for its sample before it ends,
+    so whatever the query costs lands inside the timing."""
 
     def __init__(self, gpu_index: int, steps: int, max_samples: int = 4):
         self.samples = []
@@ -118,6 +120,23 @@ class ClockSampler:
         except Exception:
             self._h = None
 
+    def start_step(self, step: int, delay_s: float):
+        self._thread = None
+        if self._h is None or step not in self.when:
+            return
+
+        def run():
+            time.sleep(max(0.0, delay_s))
+            self.sample(step)
+
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+
+    def end_step(self):
+        if getattr(self, "_thread", None) is not None:
+            self._thread.join()
+            self._thread = None
+
     def sample(self, step: int):
         if self._h is None or step not in self.when:
             return
@@ -141,7 +160,7 @@ class ClockSampler:
 
     def result(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-               "samples": len(self.samples), "source": "nvml, sampled between steps inside the timed region",
+               "samples": len(self.samples), "source": "nvml, one query per sampled step, issued while the step's kernels run",
                "sampling_ms_total": self.cost_s * 1e3}
         if self.samples:
             out["sm_mhz"] = float(np.median(self.samples))
@@ -309,17 +328,21 @@ def main():
 
     # ---- resident: search only -----------------------------------------------------------
     upload()
+    warm_s = 0.1
     for _ in range(args.warmup):
+        tw = time.perf_counter()
         eng.search_raw(opts)
+        warm_s = time.perf_counter() - tw
     sampler = ClockSampler(local_rank, args.steps)
     barrier()
     t0 = time.perf_counter()
     dev_ms = scan_ms = align_ms = 0.0
     launches = 0
     for step in range(args.steps):
-        nhits = eng.search_raw(opts)
         if not os.environ.get("TNT_NO_SAMPLER"):
-            sampler.sample(step)
+            sampler.start_step(step, 0.2 * warm_s)
+        nhits = eng.search_raw(opts)
+        sampler.end_step()
         st = eng.stats()
         dev_ms += st.total_ms
         scan_ms += st.scan_ms

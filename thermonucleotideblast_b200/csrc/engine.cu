@@ -106,6 +106,8 @@ struct OsSet {
 	std::vector<uint32_t> present, offset, entry;
 	DevBuf<OligoStrand> d_os;
 	DevBuf<uint16_t> d_keys;
+	std::vector<uint64_t> packed;       // [nos][2] seed-orientation oligos, 2 bit/base (bit 127: contiguous word list)
+	DevBuf<uint64_t> d_packed;
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
 	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
 	std::vector<int32_t> lean_tab;      // lean-tier rows, [sum of len][LEAN_WORDS]
@@ -600,6 +602,22 @@ void finish_set(tnt_engine *e, OsSet &set)
 	set.d_lean_tab.upload(set.lean_tab, e->stream);
 	set.d_row_tab_off.upload(set.row_tab_off, e->stream);
 	set.d_os.upload(set.os, e->stream);
+	// 2-bit form of every oligo whose word list has no holes (no degenerate letter): base i is the
+	// first base of word i, the tail comes from the last word
+	set.packed.assign(2*nos, 0);
+	for (size_t s = 0; s < nos; ++s) {
+		const OligoStrand &o = set.os[s];
+		if (o.nwords <= 0 || o.nwords != o.len - W + 1) continue;
+		uint64_t w[2] = {0, 0};
+		for (int i = 0; i < o.len; ++i) {
+			const int word = std::min(i, o.nwords - 1);
+			const uint64_t b = (set.keys[s*MAX_OLIGO + (size_t)word] >> (2*(i - word))) & 3u;
+			w[i >> 5] |= b << (2*(i & 31));
+		}
+		set.packed[2*s] = w[0];
+		set.packed[2*s + 1] = w[1] | ((uint64_t)1 << 63);
+	}
+	set.d_packed.upload(set.packed, e->stream);
 	set.d_keys.upload(set.keys, e->stream);
 	set.d_present.upload(set.present, e->stream);
 	set.d_offset.upload(set.offset, e->stream);
@@ -633,6 +651,7 @@ ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
 	a.wt.nkeys = set.nkeys;
 	a.os = set.d_os.p;
 	a.os_keys = set.d_keys.p;
+	a.os_packed = set.d_packed.p;
 	a.tiles = e->d_tiles.p;
 	a.W = e->prm.word_size;
 	a.cand = e->d_cand.p;

@@ -213,6 +213,7 @@ struct ScanArgs {
 	WordTable wt;
 	const OligoStrand *os;
 	const uint16_t *os_keys;   // [nos][MAX_OLIGO] little-endian keys of the compacted word list
+	const uint64_t *os_packed; // [nos][2] seed-orientation oligo, 2 bit/base; bit 127 set: words are contiguous (no degenerate letter)
 	const ScanTile *tiles;
 	uint32_t tile_begin, tile_end;
 	int W;
@@ -226,8 +227,40 @@ struct ScanArgs {
 // at t - (k - k') (same q - t).  `lo` bounds how far back that test may look (0 for a whole
 // fragment, the region start in a region scan).
 __device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ db2, uint64_t tbase, uint32_t t,
-	uint32_t k, uint32_t lo, const uint16_t *__restrict__ keys, uint32_t kmask)
+	uint32_t k, uint32_t lo, const uint16_t *__restrict__ keys, uint32_t kmask, int W, const uint64_t *__restrict__ packed)
 {
+	if (k == 0) return true;
+	const uint64_t phi = __ldg(packed + 1);
+	if ((phi >> 63) && t >= lo + k) {
+		// Oligo without degenerate letters: word kk is oligo[kk, kk+W), so "an earlier word matches
+		// on this diagonal" is a run of W equal bases starting before base k when the oligo is laid
+		// against the target at t - k.  One XOR of the 2-bit strings, runs by shift-and-AND.
+		const uint64_t g0 = tbase + t - k;
+		const uint64_t wi = g0 >> 5;
+		const unsigned sh = (unsigned)(g0 & 31u)*2u;
+		const uint64_t w0 = __ldg(db2 + wi), w1 = __ldg(db2 + wi + 1), w2 = __ldg(db2 + wi + 2);
+		const uint64_t tl = sh ? ((w0 >> sh) | (w1 << (64u - sh))) : w0;
+		const uint64_t th = sh ? ((w1 >> sh) | (w2 << (64u - sh))) : w1;
+		const uint64_t xl = tl ^ __ldg(packed), xh = th ^ (phi & ~(1ull << 63));
+		const uint64_t even = 0x5555555555555555ull;
+		uint64_t rl = ~(xl | (xl >> 1)) & even, rh = ~(xh | (xh >> 1)) & even; // bit 2i: base i equal
+		int len = 1;
+		while (2*len <= W) {
+			const unsigned s2 = 2u*(unsigned)len;
+			rl &= (rl >> s2) | (rh << (64u - s2));
+			rh &= rh >> s2;
+			len *= 2;
+		}
+		if (len < W) {
+			const unsigned s2 = 2u*(unsigned)(W - len);
+			rl &= (rl >> s2) | (rh << (64u - s2));
+			rh &= rh >> s2;
+		}
+		// words 0 .. k-1
+		const uint64_t ml = k >= 32 ? ~0ull : ((1ull << (2*k)) - 1ull);
+		const uint64_t mh = k > 32 ? ((1ull << (2*(k - 32))) - 1ull) : 0ull;
+		return ((rl & ml) | (rh & mh)) == 0;
+	}
 	for (uint32_t kk = 0; kk < k; ++kk) {
 		const uint32_t back = k - kk;
 		if (t < lo + back) continue;
@@ -257,6 +290,34 @@ __device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t os, u
 	}
 }
 
+// Candidates a warp has found but not yet appended to the buckets
+struct StagedCand { uint32_t os, target_k, t; };
+
+// Append the first n (<= 32) staged candidates of a warp: lane i takes entry i; lanes that target
+// the same bucket share one atomic.
+__device__ __forceinline__ void staged_flush(const ScanArgs &a, const StagedCand *cbuf, uint32_t n)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	__syncwarp();
+	if (lane < n) {
+		const StagedCand c = cbuf[lane];
+		const unsigned active = __activemask();
+		const unsigned peers = __match_any_sync(active, c.os);
+		const int leader = __ffs(peers) - 1;
+		uint32_t base = 0;
+		if ((int)lane == leader) base = atomicAdd(a.cand_count + (size_t)c.os*COUNT_STRIDE, (uint32_t)__popc(peers));
+		base = __shfl_sync(peers, base, leader);
+		const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+		if (slot < a.cap) {
+			Candidate out;
+			out.target_k = c.target_k;
+			out.t = c.t;
+			a.cand[(size_t)c.os*a.cap + slot] = out;
+		}
+	}
+	__syncwarp();
+}
+
 // Two phases per 8192-base tile so that warps stay converged: (1) every thread tests its 32
 // positions against the k-mer bitmap in shared memory and the block compacts the hit positions
 // into a shared queue; (2) the queue is processed one hit per thread (CSR walk, diagonal test,
@@ -267,12 +328,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 	__shared__ uint16_t s_queue[SCAN_TILE];
 	__shared__ uint32_t s_warp[SCAN_THREADS/32];
 	__shared__ uint32_t s_total;
+	__shared__ StagedCand s_cbuf[SCAN_THREADS/32][64];
 
 	for (uint32_t i = threadIdx.x; i < (a.wt.nkeys + 31)/32; i += SCAN_THREADS) s_present[i] = a.wt.present[i];
 	__syncthreads();
 
 	const uint32_t kmask = a.wt.nkeys - 1;
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	StagedCand *cbuf = s_cbuf[warp];
+	uint32_t cn = 0; // staged candidates of this warp (warp-uniform)
 
 	for (uint32_t tile = a.tile_begin + blockIdx.x; tile < a.tile_end; tile += gridDim.x) {
 		const ScanTile tl = a.tiles[tile];
@@ -316,21 +380,52 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 		}
 		__syncthreads();
 
-		// phase 2: one queued position per thread
+		// phase 2: every warp takes 32 queued positions at a time, one per lane.  The table entries
+		// of the 32 hits are walked in lock step; survivors of the diagonal test are compacted into
+		// the warp's staging buffer, and a full buffer is appended to the buckets by all 32 lanes at
+		// once (one atomic per distinct bucket, issued in parallel: one L2 round trip per 32
+		// candidates instead of one per divergent emit).
 		const uint32_t total = s_total;
-		for (uint32_t q = threadIdx.x; q < total; q += SCAN_THREADS) {
-			const uint32_t p = tl.start + s_queue[q];
-			const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
-			const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
-			for (uint32_t e = e0; e < e1; ++e) {
-				const uint32_t ent = __ldg(a.wt.entry + e);
-				const uint32_t os = ent >> 8, k = ent & 0xffu;
-				if (first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask))
-					emit_candidate(a, os, tl.target, k, p);
+		for (uint32_t q0 = warp*32u; q0 < total; q0 += SCAN_THREADS) {
+			const uint32_t q = q0 + lane;
+			uint32_t p = 0, e0 = 0, e1 = 0;
+			if (q < total) {
+				p = tl.start + s_queue[q];
+				const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
+				e0 = __ldg(a.wt.offset + key);
+				e1 = __ldg(a.wt.offset + key + 1);
+			}
+			uint32_t more = __ballot_sync(0xffffffffu, e0 < e1);
+			while (more) {
+				bool keep = false;
+				uint32_t os = 0, k = 0;
+				if (e0 < e1) {
+					const uint32_t ent = __ldg(a.wt.entry + e0);
+					os = ent >> 8;
+					k = ent & 0xffu;
+					keep = first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os);
+					++e0;
+				}
+				const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+				if (keep) {
+					StagedCand &c = cbuf[cn + (uint32_t)__popc(kept & ((1u << lane) - 1u))];
+					c.os = os;
+					c.target_k = tl.target | (k << 24);
+					c.t = p;
+				}
+				cn += (uint32_t)__popc(kept);
+				if (cn >= 32) {
+					staged_flush(a, cbuf, 32u);
+					cn -= 32;
+					if (lane < cn) cbuf[lane] = cbuf[32 + lane]; // the overhang moves to the front
+					__syncwarp();
+				}
+				more = __ballot_sync(0xffffffffu, e0 < e1);
 			}
 		}
 		__syncthreads();
 	}
+	staged_flush(a, cbuf, cn);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -377,7 +472,7 @@ __device__ __forceinline__ void scan_process_hit(const ScanArgs &a, const Target
 	for (uint32_t e = e0; e < e1; ++e) {
 		const uint32_t ent = __ldg(a.wt.entry + e);
 		const uint32_t os = ent >> 8, k = ent & 0xffu;
-		if (first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask))
+		if (first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os))
 			emit_candidate(a, os, target, k, p);
 	}
 }
@@ -386,29 +481,9 @@ __device__ __forceinline__ void scan_process_hit(const ScanArgs &a, const Target
 // after the other; for each (oligo strand, word k) entry the "first on its diagonal" test runs
 // with one earlier word per lane.  Surviving candidates are staged in a per-warp buffer and
 // appended to the global buckets with one atomic per bucket and flush.
-struct StagedCand { uint32_t os, target_k, t; };
-
 __device__ __forceinline__ void sparse_flush(const ScanArgs &a, StagedCand *cbuf, uint32_t &cn)
 {
-	const unsigned lane = threadIdx.x & 31u;
-	__syncwarp();
-	if (lane < cn) {
-		const StagedCand c = cbuf[lane];
-		const unsigned active = __activemask();
-		const unsigned peers = __match_any_sync(active, c.os);
-		const int leader = __ffs(peers) - 1;
-		uint32_t base = 0;
-		if ((int)lane == leader) base = atomicAdd(a.cand_count + (size_t)c.os*COUNT_STRIDE, (uint32_t)__popc(peers));
-		base = __shfl_sync(peers, base, leader);
-		const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-		if (slot < a.cap) {
-			Candidate out;
-			out.target_k = c.target_k;
-			out.t = c.t;
-			a.cand[(size_t)c.os*a.cap + slot] = out;
-		}
-	}
-	__syncwarp();
+	staged_flush(a, cbuf, cn);
 	cn = 0;
 }
 
@@ -582,7 +657,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_region_scan(RegionScanArgs ra)
 				const uint32_t ent = __ldg(a.wt.entry + e);
 				const uint32_t os = ent >> 8, k = ent & 0xffu;
 				if (a.os[os].assay != rg.assay) continue;
-				if (first_on_diagonal(a.db.db2, tg.base, p, k, rg.start, a.os_keys + (size_t)os*MAX_OLIGO, kmask))
+				if (first_on_diagonal(a.db.db2, tg.base, p, k, rg.start, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os))
 					emit_candidate(a, os, rg.target, k, p);
 			}
 		}
