@@ -80,7 +80,25 @@ def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False, kin
         records.append(store[pos:pos + n])
         pos += n
     arng = np.random.default_rng(99)  # same assays on every rank
-    assays = gen.make_assays(arng, records, n_assays, kind, lens=(20, 21, 25), amp=(80, 400), variants=2)
+    if kind == "probe":
+        # BASELINE configs[2] flavour: 30-mer probes carrying one inosine and one two-fold code
+        # (expanded by the caller into two concrete oligos of degeneracy 2, like the reference's
+        # expand_degenerate_signatures), database with 0.1 % IUPAC codes and N runs
+        base = gen.make_assays(arng, records, n_assays, "probe", lens=(20, 21, 30), amp=(80, 400), variants=2)
+        assays = []
+        for (_, _, P) in base:
+            p = list(P)
+            i_pos, d_pos = 10, 20
+            p[i_pos] = "I"
+            two = {"A": "AG", "G": "AG", "C": "CT", "T": "CT"}[p[d_pos]]
+            for b in two:
+                q = list(p)
+                q[d_pos] = b
+                assays.append((None, None, "".join(q), 2))
+        for rec in records:
+            gen.sprinkle_degenerate(rec, rng, frac=1e-3, n_runs_per_50kb=1.0)
+    else:
+        assays = gen.make_assays(arng, records, n_assays, kind, lens=(20, 21, 25), amp=(80, 400), variants=2)
     fragments = []
     for rec in records:
         for (a, b) in fragment_record(len(rec), FRAGMENT_BP):
@@ -240,13 +258,16 @@ def main():
     ap.add_argument("--mbp", type=int, default=1000, help="database size per GPU in Mbp")
     ap.add_argument("--assays", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kind", default="taqman", choices=["taqman", "pcr"], help="assay type (default: BASELINE configs[1])")
+    ap.add_argument("--kind", default="taqman", choices=["taqman", "pcr", "probe", "padlock"],
+                    help="assay type (default: BASELINE configs[1]; probe / padlock: the flavours of configs[2] / configs[3])")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
-    kind_txt = "TaqMan primer+probe triplets" if args.kind == "taqman" else "PCR primer pairs"
+    kind_txt = {"taqman": "TaqMan primer+probe triplets", "pcr": "PCR primer pairs",
+                "probe": "hybridisation probes (30-mers with one inosine and one two-fold code, expanded; DB with 0.1 % IUPAC codes and N runs)",
+                "padlock": "padlock probe pairs (20+20)"}[args.kind]
     workload = ("%d %s (20/21/25-mers, -e %g -E %g) vs synthetic %.3g Gbp multi-record "
                 "database per GPU (%d Mbp records, <=%d kbp fragments + %d bp overlap)"
                 % (args.assays, kind_txt, MIN_PRIMER_TM, MIN_PROBE_TM, args.mbp / 1000.0, RECORD_BP // 1_000_000,
@@ -255,6 +276,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if args.kind not in ("taqman", "pcr"):
+            raise SystemExit("--impl reference supports --kind taqman | pcr")
         # bounded per-step sample so that warmup + steps end within a few minutes
         cores = host_cores()
         per_step_s = 6.0
@@ -295,8 +318,13 @@ def main():
     records, fragments, assays, db_bases = build_workload(rank, args.mbp, args.assays, pinned=True, kind=args.kind)
     frag_bases = int(sum(len(f) for f in fragments))
     opts = search_options(min_primer_tm=MIN_PRIMER_TM, min_probe_tm=MIN_PROBE_TM, max_len=MAX_LEN)
+    if args.kind == "probe":
+        opts.assay_format = 1   # TNT_ASSAY_PROBE
+    elif args.kind == "padlock":
+        opts.assay_format = 2   # TNT_ASSAY_PADLOCK
+        opts.min_probe_tm = 40.0
     eng = Engine(device=local_rank)
-    eng.set_assays([Assay(i, F, R, P) for i, (F, R, P) in enumerate(assays)])
+    eng.set_assays([Assay(i, a[0], a[1], a[2], probe_degen=(a[3] if len(a) > 3 else 1)) for i, a in enumerate(assays)])
 
     def barrier():
         torch.cuda.synchronize()
@@ -437,7 +465,11 @@ def main():
                                "single_assay": scan1},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(records, assays)
+        if args.kind in ("taqman", "pcr"):
+            line["cpu_baseline"] = cpu_baseline(records, assays)
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                    "sample": "not measured for this workload flavour (bench line of record: --kind taqman)"}
     elif rank == 0:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "only measured at N=1"}
     if rank == 0:

@@ -850,20 +850,17 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 	const uint32_t base_count = e->n_bound;
 	size_t out_cap = emit_all ? (size_t)base_count + total : std::max<size_t>(e->d_bound.cap, (size_t)base_count + (1u << 16));
 	size_t slow_cap = std::max<size_t>(e->d_slow.cap, 1u << 16);
-	// full-trace hand-over segments: a few per cent of a strand's candidates are expected
+	// Full-trace hand-over segments.  A few per cent of a strand's candidates are typical, but an
+	// oligo with an internal repeat ties its maximal cells in most windows: every segment can take
+	// all candidates of its strand (12 bytes each; only what is handed over is ever touched).
 	std::vector<uint32_t> retry_ctl(2*nos, 0); // base | cap
-	auto size_retry_segments = [&](const std::vector<uint32_t> *need) {
-		uint64_t at = 0;
-		for (size_t s = 0; s < nos; ++s) {
-			const uint64_t cap_s = need ? (uint64_t)(*need)[s] + (*need)[s]/8 + 64 : (counts[s] ? (uint64_t)counts[s]/8 + 256 : 0);
-			retry_ctl[s] = (uint32_t)at;
-			retry_ctl[nos + s] = (uint32_t)std::min<uint64_t>(cap_s, counts[s]);
-			at += retry_ctl[nos + s];
-		}
-		if (at >= ((uint64_t)1 << 32)) throw std::runtime_error("internal: hand-over list too large");
-		return (size_t)at;
-	};
-	size_t retry_total = size_retry_segments(nullptr);
+	size_t retry_total = 0;
+	for (size_t s = 0; s < nos; ++s) {
+		retry_ctl[s] = (uint32_t)retry_total;
+		retry_ctl[nos + s] = counts[s];
+		retry_total += counts[s];
+	}
+	if (retry_total >= ((uint64_t)1 << 32)) throw std::runtime_error("internal: hand-over list too large");
 	// snapshot of the DP-cell counter so that a retried pass is not counted twice
 	unsigned long long cells_before = 0;
 	CUDA_OK(cudaMemcpyAsync(&cells_before, e->d_cells.p, sizeof(cells_before), cudaMemcpyDeviceToHost, e->stream));
@@ -911,6 +908,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		a.slow_cap = (uint32_t)slow_cap;
 
 		float ms = 0;
+		std::unique_ptr<HostTimer> t_phase(new HostTimer("    lean / first pass"));
 		for (int c = 0; c < nclass; ++c)
 			if (!by_class[c].empty()) ms += run_align_kernel(e, set, a, by_class[c], kFastClasses[c], set.max_len);
 		for (int c = 0; c < nclass; ++c)
@@ -928,7 +926,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			bool overflow = false;
 			uint64_t n_retry = 0;
 			for (size_t s = 0; s < nos; ++s) { overflow = overflow || retry_fill[s] > retry_ctl[nos + s]; n_retry += retry_fill[s]; }
-			if (overflow) { retry_total = size_retry_segments(&retry_fill); continue; } // the counters kept counting: exact sizes now
+			if (overflow) throw std::runtime_error("internal: hand-over segment overflow");
 			cnt[2] = (uint32_t)n_retry;
 		}
 		if (HostTimer::enabled())
@@ -959,6 +957,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			}
 		};
 
+		t_phase.reset(new HostTimer("    full-trace tier"));
 		if (cnt[2]) {
 			// optimal path enters a gap state: full-trace variant of the fast kernel
 			std::vector<std::vector<AlignGroup>> retry_units(nclass);
@@ -974,6 +973,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			CUDA_OK(cudaStreamSynchronize(e->stream));
 			if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1]*5/4; continue; }
 		}
+		t_phase.reset(new HostTimer("    generic tier"));
 		if (cnt[1]) {
 			// windows with IUPAC / inosine / N target bases (or no positive score): generic kernel
 			std::vector<AlignGroup> units;
@@ -986,6 +986,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
 		}
+		t_phase.reset();
 		e->stats.align_ms += ms;
 
 		uint32_t n = cnt[0];
@@ -1285,17 +1286,20 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	// PCR: an amplicon needs a minus-strand primer site with a plus-strand primer site of the same
 	// (fragment, assay) less than max_len downstream.  Only sites that can be part of such a pair
 	// leave the device (k_live_*: position buckets at least max_len wide).
-	const uint64_t key_space = (uint64_t)e->targets.size()*n_assays;
-	const bool prefilter = (o.assay_format == TNT_ASSAY_PCR) && !stage2.os.empty() && key_space <= ((uint64_t)1 << 31);
+	const bool padlock_format = o.assay_format == TNT_ASSAY_PADLOCK || o.assay_format == TNT_ASSAY_MIPS;
+	const uint64_t key_space = (uint64_t)e->targets.size()*n_assays*(padlock_format ? 2u : 1u);
+	const bool prefilter = ((o.assay_format == TNT_ASSAY_PCR && !stage2.os.empty()) || padlock_format) && key_space <= ((uint64_t)1 << 31);
 	uint32_t n_live = n2;
 	const uint32_t *site_index = nullptr; // record index of each downloaded head (nullptr: identity)
 	if (prefilter && n2 != 0) {
 		uint32_t max_target_len = 1;
 		for (const Target &t : e->targets) max_target_len = std::max(max_target_len, t.len);
+		// bucket width: >= max_len for PCR; >= gap limit + two oligos for padlock / MIPS
+		const int64_t span = padlock_format ? (o.assay_format == TNT_ASSAY_MIPS ? (int64_t)o.max_len : 0) + 128 : std::max<int64_t>(o.max_len, 64);
 		uint32_t shift = 6;
-		while (((uint32_t)1 << shift) < (uint32_t)std::max<int64_t>(o.max_len, 64) && shift < 31) ++shift;
-		uint32_t nbucket = (max_target_len >> shift) + 2;
-		while (key_space*nbucket > ((uint64_t)1 << 33) && shift < 31) { ++shift; nbucket = (max_target_len >> shift) + 2; }
+		while (((uint32_t)1 << shift) < (uint32_t)span && shift < 31) ++shift;
+		uint32_t nbucket = (max_target_len >> shift) + 4;
+		while (key_space*nbucket > ((uint64_t)1 << 33) && shift < 31) { ++shift; nbucket = (max_target_len >> shift) + 4; }
 		const size_t words = (size_t)((key_space*nbucket + 31)/32) + 1;
 		e->d_live.reserve(2*words, 0, e->stream);
 		e->d_live_ctl.reserve(2, 0, e->stream);
@@ -1317,9 +1321,14 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		la.out_index = e->d_live_index.p;
 		la.count = e->d_live_ctl.p;
 		la.err_flags = e->d_live_ctl.p + 1;
-		if (n2 > n1) k_live_mark_plus<<<gen_grid, 256, 0, e->stream>>>(la, n1, n2);
-		if (n1) k_live_compact<<<gen_grid, 256, 0, e->stream>>>(la, 0, n1, 1);
-		if (n2 > n1) k_live_compact<<<gen_grid, 256, 0, e->stream>>>(la, n1, n2, 2);
+		if (padlock_format) {
+			for (int pass = 0; pass < 3; ++pass) k_live_padlock<<<gen_grid, 256, 0, e->stream>>>(la, n2, pass);
+		}
+		else {
+			if (n2 > n1) k_live_mark_plus<<<gen_grid, 256, 0, e->stream>>>(la, n1, n2);
+			if (n1) k_live_compact<<<gen_grid, 256, 0, e->stream>>>(la, 0, n1, 1);
+			if (n2 > n1) k_live_compact<<<gen_grid, 256, 0, e->stream>>>(la, n1, n2, 2);
+		}
 		CUDA_OK(cudaGetLastError());
 		e->stats.kernel_launches += 3;
 		uint32_t ctl[2] = {0, 0};

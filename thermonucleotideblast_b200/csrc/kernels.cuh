@@ -967,6 +967,32 @@ __global__ void k_live_compact(LiveArgs a, uint32_t from, uint32_t to, int pass)
 	}
 }
 
+// The same idea for padlock / MIPS assays (padlock_search.cpp:62-361): a ligation site needs an
+// upstream probe site u (role R) and a downstream probe site d (role F) of the same (fragment,
+// assay) on the same strand, 0 <= gap <= max_len bases apart.  All sites come from stage 1.  Keys
+// carry the strand; with buckets at least max_len + 128 wide the partner's loc_5 lies in the same
+// bucket or a neighbouring one.  pass 0: d marks live_r; pass 1: u with a mark nearby survives and
+// marks live_f; pass 2: d with a live u nearby survives.
+__global__ void k_live_padlock(LiveArgs a, uint32_t n, int pass)
+{
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+		const BoundHead b = a.recs[i].h;
+		const OligoStrand &o = a.os1[b.os];
+		if (pass == 0 && (b.flags & (F_OOB | F_STACK | F_TRUNC))) atomicOr(a.err_flags, (uint32_t)b.flags);
+		const bool downstream = o.role == 0; /* TNT_OLIGO_F */
+		if ((pass == 1) == downstream) continue;
+		const uint32_t bk = min((uint32_t)max(b.loc5, 0) >> a.shift, a.nbucket - 3u) + 1u; // buckets 0 and nbucket-1 stay empty
+		const uint64_t key = (((uint64_t)b.target*a.nassay + (uint32_t)o.assay)*2u + (o.plus ? 1u : 0u))*a.nbucket + bk;
+		if (pass == 0) { atomicOr(a.live_r + (key >> 5), 1u << (key & 31u)); continue; }
+		const uint32_t *bits = pass == 1 ? a.live_r : a.live_f;
+		if (!(live_test(bits, key - 1) || live_test(bits, key) || live_test(bits, key + 1))) continue;
+		if (pass == 1) atomicOr(a.live_f + (key >> 5), 1u << (key & 31u));
+		const uint32_t slot = atomicAdd(a.count, 1u);
+		a.out_heads[slot] = b;
+		a.out_index[slot] = i;
+	}
+}
+
 // Copy selected records into a dense array (the hits' oligo sites, for text rendering)
 __global__ void k_gather_recs(const BoundRec *__restrict__ src, const uint32_t *__restrict__ index, uint32_t n, BoundRec *__restrict__ dst)
 {
