@@ -398,7 +398,7 @@ def main():
         upload()
         upload_s += time.perf_counter() - tu
         eng.search_raw(opts)
-        hits = eng.hits()
+        n_e2e_hits, hit_bytes, text_bytes = eng.hit_records()   # the step's result, read on the host
         # result bytes the engine copied back (site heads of live groups, records of hit sites)
         d2h = int(eng.stats().d2h_bytes)
     barrier()
@@ -408,7 +408,7 @@ def main():
     # ---- seed scan alone with a single assay (the HBM-bound case of SURVEY 8d) -------------------
     scan1 = None
     try:
-        eng.set_assays([Assay(0, *assays[0])])
+        eng.set_assays([Assay(0, assays[0][0], assays[0][1], assays[0][2])])
         eng.scan_only(opts)
         best = None
         for _ in range(3):

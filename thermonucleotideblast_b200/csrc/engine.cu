@@ -21,6 +21,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tntb200.h"
@@ -1408,10 +1409,26 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		CUDA_OK(cudaStreamSynchronize(e->stream));
 	}
 	std::vector<uint32_t> text_off(need.size());
-	for (size_t i = 0; i < need.size(); ++i) {
-		text_off[i] = (uint32_t)e->arena.size();
-		e->arena.append(render_alignment(recs[i], os_of(recs[i].h.os)));
-		e->arena.push_back('\0');
+	{
+		// text of every site (nuc_cruc_output.cpp:74-205); many hits -> a few host threads
+		std::vector<std::string> text(need.size());
+		const unsigned nthreads = need.size() < 2048 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		auto work = [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) text[i] = render_alignment(recs[i], os_of(recs[i].h.os)); };
+		if (nthreads == 1) work(0, need.size());
+		else {
+			std::vector<std::thread> pool;
+			const size_t per = (need.size() + nthreads - 1)/nthreads;
+			for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(work, std::min(need.size(), t*per), std::min(need.size(), (t + 1)*per));
+			for (std::thread &t : pool) t.join();
+		}
+		size_t total = e->arena.size();
+		for (const std::string &t : text) total += t.size() + 1;
+		e->arena.reserve(total);
+		for (size_t i = 0; i < need.size(); ++i) {
+			text_off[i] = (uint32_t)e->arena.size();
+			e->arena.append(text[i]);
+			e->arena.push_back('\0');
+		}
 	}
 	auto off_of = [&](int s) -> uint32_t {
 		if (s < 0) return 0;

@@ -280,6 +280,18 @@ class Engine:
             out.append(Hit(h, s(h.forward.align_off), s(h.reverse.align_off), s(h.probe.align_off)))
         return out
 
+    def hit_records(self):
+        """The hit array and the string arena as the C ABI hands them out: copies of the raw bytes
+        (tnt_hit records, alignment strings), no per-hit Python objects."""
+        ph = C.POINTER(CHit)()
+        n = C.c_size_t()
+        arena = C.c_void_p()
+        asz = C.c_size_t()
+        self._check(self.L.tnt_engine_get_hits(self.h, C.byref(ph), C.byref(n), C.byref(arena), C.byref(asz)))
+        recs = C.string_at(ph, n.value * C.sizeof(CHit)) if n.value else b""
+        text = C.string_at(arena.value, asz.value) if asz.value else b""
+        return n.value, recs, text
+
     def stats(self) -> Stats:
         st = Stats()
         self._check(self.L.tnt_engine_get_stats(self.h, C.byref(st)))
