@@ -875,6 +875,9 @@ __device__ __forceinline__ bool lean_evaluate(const int32_t *__restrict__ tab, i
 #undef SUB_HS
 }
 
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 6
+__device__ uint32_t *tnt_dbg_why; // timing / statistics experiment only
+#endif
 // The whole post-fill work of a lean candidate: one traceback down the diagonal of the single
 // maximal cell, frayed ends, dangling ends, evaluation.  Handles the ordinary case only -- a run of
 // cells with M > 0 whose maximum comes from the diagonal alone, closed by a cell with M < 0 inside
@@ -895,11 +898,19 @@ __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__
 	int m = tv.maxscore;
 	for (;;) {
 		const unsigned bits = tv.cell_bits(i, j);
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 6
+		if (m <= 0 && !(bits & 1u)) { atomicAdd(tnt_dbg_why + 2, 1u); return false; }
+		++n;
+		if (m <= 0) break;
+		if (!(bits & 2u)) { atomicAdd(tnt_dbg_why + 1, 1u); return false; }
+		if (i == 1 || j == 1) { atomicAdd(tnt_dbg_why + 3, 1u); return false; }
+#else
 		if (m <= 0 && !(bits & 1u)) return false;      // M == 0 on the path
 		++n;
 		if (m <= 0) break;                             // M < 0: the closing pair
 		if (!(bits & 2u)) return false;                // tie or gap state
 		if (i == 1 || j == 1) return false;            // border next
+#endif
 		const int tb = tv.tgt[j - 1], pt = tv.tgt[j - 2];
 		m += tv.tab[(i - 1)*LEAN_WORDS + LEAN_T + 2*(pt*4 + tb)];
 		--i;
@@ -909,6 +920,9 @@ __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__
 	a.b = a.e = 2;
 	a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
 	a.dH = a.dS = a.tm = 0.0f;
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 5
+	if (n < 1000) return true; // timing experiment only: diagonal walk, then nothing
+#endif
 
 	if (th->dangle5 || th->dangle3) {
 		// dangling-end columns can hold virtual bases: materialise and use the general code
@@ -930,6 +944,9 @@ __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__
 	while (n > 0 && !(lean_pair(tv.tab, Lq, tv.tgt, fm_q, fm_t, 0) & 0x80u)) { ++fm_q; --fm_t; --n; }
 	if (n < 3) return true;
 	float dH, dS, tm = 0.0f;
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 4
+	if (n < 1000) return true; // timing experiment only: no evaluation
+#endif
 	if (!lean_evaluate(tv.tab, Lq, th, r_log_ct, tv.tgt, fm_q, fm_t, n, dH, dS, tm)) return true;
 	best.valid = true;
 	best.dH = dH; best.dS = dS; best.tm = tm;

@@ -932,6 +932,13 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		}
 		if (HostTimer::enabled())
 			fprintf(stderr, "[tnt]   candidates %llu, full-trace retry %u, generic %u, fast ms %.3f\n", (unsigned long long)total, cnt[2], cnt[1], ms);
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 6
+		{
+			uint32_t why[4];
+			CUDA_OK(cudaMemcpy(why, e->d_out_count.p + 8, sizeof(why), cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[tnt]   hand-over reasons (cumulative): tied maxima %u, tie/gap on path %u, M==0 on path %u, border %u\n", why[0], why[1], why[2], why[3]);
+		}
+#endif
 
 		// Hand-over lists -> compact candidate arrays grouped by oligo strand (counting sort)
 		auto regroup = [&](const DevBuf<SlowItem> &list, uint32_t n, std::vector<std::vector<AlignGroup>> *per_class,
@@ -1529,7 +1536,8 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
 	e->d_thermo.reserve(1, 0, e->stream);
 	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
-	e->d_out_count.reserve(4, 0, e->stream);
+	e->d_out_count.reserve(16, 0, e->stream);
+	CUDA_OK(cudaMemsetAsync(e->d_out_count.p, 0, 16*sizeof(uint32_t), e->stream));
 	e->d_cells.reserve(1, 0, e->stream);
 	{
 		std::vector<int32_t> p5(20);
