@@ -92,7 +92,7 @@ struct DevBuf {
 };
 
 constexpr size_t STAGE_BYTES = 32u << 20; // one upload batch
-constexpr size_t MAX_SLOTS = 32;          // device staging ring: up to 1 GB of fragment bytes in flight
+constexpr size_t MAX_SLOTS = 128;         // device staging ring (slots are allocated as needed): up to 4 GB of fragment bytes in flight
 
 struct AssayHost {
 	int id;
@@ -168,13 +168,17 @@ struct tnt_engine {
 	struct Slot {
 		uint8_t *d_stage = nullptr;
 		cudaEvent_t free_ev = nullptr;    // slot contents fully consumed (pack + exception emission)
-		cudaEvent_t count_ev = nullptr;   // exception count of the batch is on the host
-		cudaEvent_t packed_ev = nullptr;  // db2 / nmask of the batch are written
 		DevBuf<uint32_t> block_count;
 	};
 	std::vector<Slot> slots;
 	size_t max_slots = 0;             // ring size (MAX_SLOTS; TNT_UPLOAD_SLOTS shrinks it for tests)
 	struct Batch { uint64_t base; uint32_t used; int slot; uint32_t nblocks; };
+	// per batch (not per slot: a slot is reused within one upload when the ring wraps)
+	struct BatchEvents {
+		cudaEvent_t count_ev = nullptr;   // exception count of the batch is on the host
+		cudaEvent_t packed_ev = nullptr;  // db2 / nmask of the batch are written
+	};
+	std::vector<BatchEvents> batch_ev; // grows to the largest number of batches seen, reused across uploads
 	std::vector<Batch> batches;       // of the registered fragments, ascending base
 	size_t next_emit = 0;             // batches[next_emit..] still owe their exceptions
 	// host -> staging copies of the open batch, issued as one batched copy when the batch is flushed
@@ -250,8 +254,10 @@ struct tnt_engine {
 		for (Slot &sl : slots) {
 			if (sl.d_stage) cudaFree(sl.d_stage);
 			if (sl.free_ev) cudaEventDestroy(sl.free_ev);
-			if (sl.count_ev) cudaEventDestroy(sl.count_ev);
-			if (sl.packed_ev) cudaEventDestroy(sl.packed_ev);
+		}
+		for (BatchEvents &b : batch_ev) {
+			if (b.count_ev) cudaEventDestroy(b.count_ev);
+			if (b.packed_ev) cudaEventDestroy(b.packed_ev);
 		}
 		if (emit_done) cudaEventDestroy(emit_done);
 		if (pads_ev) cudaEventDestroy(pads_ev);
@@ -308,12 +314,12 @@ void emit_ready(tnt_engine *e, bool block, size_t through = ~(size_t)0)
 	bool any = false;
 	while (e->next_emit < e->batches.size()) {
 		if (!block || e->next_emit > through) {
-			if (!block && cudaEventQuery(e->slots[(size_t)e->batches[e->next_emit].slot].count_ev) != cudaSuccess) { cudaGetLastError(); break; }
+			if (!block && cudaEventQuery(e->batch_ev[e->next_emit].count_ev) != cudaSuccess) { cudaGetLastError(); break; }
 			if (block && e->next_emit > through) break;
 		}
 		const tnt_engine::Batch &bt = e->batches[e->next_emit];
 		tnt_engine::Slot &sl = e->slots[(size_t)bt.slot];
-		CUDA_OK(cudaEventSynchronize(sl.count_ev));
+		CUDA_OK(cudaEventSynchronize(e->batch_ev[e->next_emit].count_ev));
 		const uint64_t nexc = e->h_total[bt.slot];
 		if (nexc) {
 			if (e->nexc + nexc > e->exc_pos.cap) {
@@ -368,12 +374,18 @@ void flush_batch(tnt_engine *e)
 		const uint32_t nblocks = (n + PACK_BASES_PER_BLOCK - 1)/PACK_BASES_PER_BLOCK;
 		sl.block_count.reserve(nblocks, 0, e->up_stream);
 		k_pack<<<nblocks, PACK_THREADS, 0, e->up_stream>>>(sl.d_stage, n, e->db2.p, e->nmask.p, first_word, sl.block_count.p);
-		CUDA_OK(cudaEventRecord(sl.packed_ev, e->up_stream));
+		const size_t bi = e->batches.size();
+		if (bi >= e->batch_ev.size()) {
+			e->batch_ev.emplace_back();
+			CUDA_OK(cudaEventCreateWithFlags(&e->batch_ev.back().count_ev, cudaEventDisableTiming));
+			CUDA_OK(cudaEventCreateWithFlags(&e->batch_ev.back().packed_ev, cudaEventDisableTiming));
+		}
+		CUDA_OK(cudaEventRecord(e->batch_ev[bi].packed_ev, e->up_stream));
 		k_scan_counts<<<1, 1024, 0, e->up_stream>>>(sl.block_count.p, nblocks, e->d_total + slot);
 		CUDA_OK(cudaGetLastError());
 		e->upload_launches += 2;
 		CUDA_OK(cudaMemcpyAsync(e->h_total + slot, e->d_total + slot, sizeof(uint64_t), cudaMemcpyDeviceToHost, e->up_stream));
-		CUDA_OK(cudaEventRecord(sl.count_ev, e->up_stream));
+		CUDA_OK(cudaEventRecord(e->batch_ev[bi].count_ev, e->up_stream));
 		e->packed_words = first_word + ((uint64_t)n + 31u)/32u;
 		e->batches.push_back(tnt_engine::Batch{e->batch_base, n, slot, nblocks});
 	}
@@ -392,8 +404,6 @@ void open_batch(tnt_engine *e, uint64_t base)
 		tnt_engine::Slot &sl = e->slots.back();
 		CUDA_OK(cudaMalloc(&sl.d_stage, STAGE_BYTES));
 		CUDA_OK(cudaEventCreateWithFlags(&sl.free_ev, cudaEventDisableTiming));
-		CUDA_OK(cudaEventCreateWithFlags(&sl.count_ev, cudaEventDisableTiming));
-		CUDA_OK(cudaEventCreateWithFlags(&sl.packed_ev, cudaEventDisableTiming));
 	}
 	else if (k >= e->max_slots) {
 		emit_ready(e, true, k - e->max_slots);
@@ -786,7 +796,13 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 		a.trace_cells = (uint32_t)max_len*(uint32_t)max_lt;
 	}
 	else {
-		grid = (uint32_t)std::min<size_t>(nunits, (size_t)e->sm_count*fast_blocks_per_sm(lq, full));
+		const size_t resident = (size_t)e->sm_count*fast_blocks_per_sm(lq, full);
+		grid = (uint32_t)std::min<size_t>(nunits, resident);
+		// The lean tier (trace in shared memory) runs as several waves of CTAs with ~8 units each
+		// instead of one persistent wave: CTAs retire every few hundred microseconds, so the
+		// pack kernels of the (higher-priority) upload stream are not locked out for the whole
+		// launch while fragments are still arriving.
+		if (!full && nunits > 8*resident) grid = (uint32_t)((nunits + 7)/8);
 		a.trace_cells = fast_trace_words(lq, full);
 	}
 	// d_trace counts 16-bit units; the lean tier needs none (shared memory)
@@ -1063,17 +1079,18 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 			while (gates[gate].tile_end <= t0) ++gate;
 			// as far as the upload has come (at least one gate: the stream then waits for it)
 			while (gate + 1 < gates.size() &&
-				cudaEventQuery(e->slots[(size_t)e->batches[gates[gate + 1].batch].slot].count_ev) == cudaSuccess) ++gate;
+				cudaEventQuery(e->batch_ev[gates[gate + 1].batch].count_ev) == cudaSuccess) ++gate;
 			cudaGetLastError();
 			t1 = std::min(t1, gates[gate].tile_end);
 			const size_t bi = gates[gate].batch;
 			HostTimer t_gate("  upload gate (host wait)");
 			emit_ready(e, true, bi); // exceptions of these batches (the host waits for their counts only)
 			if (bi + 1 == e->batches.size()) CUDA_OK(cudaStreamWaitEvent(e->stream, e->pads_ev, 0)); // + the read-ahead pads
-			CUDA_OK(cudaStreamWaitEvent(e->stream, e->slots[(size_t)e->batches[bi].slot].packed_ev, 0));
+			CUDA_OK(cudaStreamWaitEvent(e->stream, e->batch_ev[bi].packed_ev, 0));
 			CUDA_OK(cudaStreamWaitEvent(e->stream, e->emit_done, 0));
 		}
 		uint32_t forced_cap = 0; // set after an overflow, when the real bucket sizes are known
+		HostTimer t_chunk("  chunk (scan + align)");
 		for (;;) {
 			const uint32_t ntiles = t1 - t0;
 			uint32_t cap = (uint32_t)std::min<double>(4.0e9, 2.0*per_base*plan.tile_bases*ntiles + 2048.0);
@@ -1520,7 +1537,11 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 	e->sm_count = prop.multiProcessorCount;
 	CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
 	for (auto &ev : e->ev) CUDA_OK(cudaEventCreate(&ev));
-	CUDA_OK(cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
+	{
+		int prio_lo = 0, prio_hi = 0;
+		CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CUDA_OK(cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, prio_hi));
+	}
 	e->slots.reserve(MAX_SLOTS);
 	e->max_slots = MAX_SLOTS;
 	if (const char *v = std::getenv("TNT_UPLOAD_SLOTS")) e->max_slots = (size_t)std::min<long>(MAX_SLOTS, std::max<long>(2, std::atol(v)));
