@@ -802,7 +802,8 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 		// instead of one persistent wave: CTAs retire every few hundred microseconds, so the
 		// pack kernels of the (higher-priority) upload stream are not locked out for the whole
 		// launch while fragments are still arriving.
-		if (!full && nunits > 8*resident) grid = (uint32_t)((nunits + 7)/8);
+		static const size_t per_cta = []() { const char *v = std::getenv("TNT_LEAN_UNITS"); return (size_t)(v ? std::max(1L, std::atol(v)) : 8L); }();
+		if (!full && nunits > per_cta*resident) grid = (uint32_t)((nunits + per_cta - 1)/per_cta);
 		a.trace_cells = fast_trace_words(lq, full);
 	}
 	// d_trace counts 16-bit units; the lean tier needs none (shared memory)
