@@ -540,7 +540,8 @@ def test_align_tiers_and_parameters(engine_lib, oracle, monkeypatch, T, na, d5, 
 
 
 def test_search_lean_and_full_tiers_agree(engine_lib, oracle, monkeypatch):
-    """The same TaqMan batch search with and without the lean tier: both equal the oracle."""
+    """The same TaqMan batch search (a) as shipped, (b) without the lean tier, (c) with the lean
+    tier but without its "too few columns to reach min Tm" shortcut: all equal the oracle."""
     from thermonucleotideblast_b200 import Assay, Engine
     rng = np.random.default_rng(97531)
     db = [gen.random_codes(int(rng.integers(15000, 30000)), rng) for _ in range(4)]
@@ -548,11 +549,11 @@ def test_search_lean_and_full_tiers_agree(engine_lib, oracle, monkeypatch):
     o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
     want = {(t, i): oracle.search(codes, a[0], a[1], a[2], o) for t, codes in enumerate(db) for i, a in enumerate(assays)}
     assert sum(len(v) for v in want.values()) >= 6
-    for no_lean in (False, True):
-        if no_lean:
-            monkeypatch.setenv("TNT_NO_LEAN", "1")
-        else:
-            monkeypatch.delenv("TNT_NO_LEAN", raising=False)
+    for env in ({}, {"TNT_NO_LEAN": "1"}, {"TNT_NO_LEAN_SKIP": "1"}):
+        for k in ("TNT_NO_LEAN", "TNT_NO_LEAN_SKIP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with Engine() as e:
             for c in db:
                 e.add_target(c)

@@ -878,6 +878,9 @@ __device__ __forceinline__ bool lean_evaluate(const int32_t *__restrict__ tab, i
 #if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 6
 __device__ uint32_t *tnt_dbg_why; // timing / statistics experiment only
 #endif
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 7
+__device__ uint32_t *tnt_dbg_skip; // [0] evaluations skipped, [1] skipped although Tm >= min_tm (must stay 0)
+#endif
 // The whole post-fill work of a lean candidate: one traceback down the diagonal of the single
 // maximal cell, frayed ends, dangling ends, evaluation.  Handles the ordinary case only -- a run of
 // cells with M > 0 whose maximum comes from the diagonal alone, closed by a cell with M < 0 inside
@@ -888,7 +891,7 @@ __device__ uint32_t *tnt_dbg_why; // timing / statistics experiment only
 // written (`keep_all`, or Tm inside [min_tm, max_tm], the first filter of finish_alignment).
 template <int LQ, int NT>
 __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct,
-	const ColMajorLean<LQ, NT> &tv, int Lt, int cell, bool keep_all, float min_tm, float max_tm,
+	const ColMajorLean<LQ, NT> &tv, int Lt, int cell, bool keep_all, float min_tm, float max_tm, int min_cols,
 	AlnState &a, Best &best, unsigned &flags)
 {
 	const int Lq = sh.Lq;
@@ -943,6 +946,19 @@ __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__
 	while (n > 0 && !(lean_pair(tv.tab, Lq, tv.tgt, fm_q, fm_t, n - 1) & 0x80u)) --n;
 	while (n > 0 && !(lean_pair(tv.tab, Lq, tv.tgt, fm_q, fm_t, 0) & 0x80u)) { ++fm_q; --fm_t; --n; }
 	if (n < 3) return true;
+	// too short to reach min_tm whatever the bases are (lean_min_columns, thermo.cpp): the Tm
+	// filter would reject it, so it is not evaluated (unless every result is wanted)
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 7
+	// verification build: evaluate what would have been skipped and count contradictions
+	if (!keep_all && n < min_cols) {
+		float vH, vS, vT = 0.0f;
+		atomicAdd(tnt_dbg_skip, 1u);
+		if (lean_evaluate(tv.tab, Lq, th, r_log_ct, tv.tgt, fm_q, fm_t, n, vH, vS, vT) && !(vT < min_tm)) atomicAdd(tnt_dbg_skip + 1, 1u);
+		return true;
+	}
+#else
+	if (!keep_all && n < min_cols) return true;
+#endif
 	float dH, dS, tm = 0.0f;
 #if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 4
 	if (n < 1000) return true; // timing experiment only: no evaluation

@@ -549,6 +549,7 @@ OligoStrand make_os(const tnt_engine *e, int assay_index, int role, bool plus, c
 	if (!(ct > 0.0f)) throw std::runtime_error(":NucCruc::tm_dimer: Invalid strand_concentration");
 	s.r_log_ct = r_log_ct(ct);
 	s.min_tm = min_tm; s.max_tm = max_tm; s.min_dg = min_dg; s.max_dg = max_dg;
+	s.lean_min_cols = std::getenv("TNT_NO_LEAN_SKIP") ? 0 : lean_min_columns(e->h_thermo, s, min_tm);
 	s.clamp5 = clamp5; s.clamp3 = clamp3;
 	s.max_gap = o.max_gap; s.max_mismatch = o.max_mismatch; s.max_poly_degen = o.max_poly_degen;
 	// A window without any alignment has Tm = 0 and dG = 0 in the reference and is then
@@ -949,6 +950,13 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		}
 		if (HostTimer::enabled())
 			fprintf(stderr, "[tnt]   candidates %llu, full-trace retry %u, generic %u, fast ms %.3f\n", (unsigned long long)total, cnt[2], cnt[1], ms);
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 7
+		{
+			uint32_t sk[2];
+			CUDA_OK(cudaMemcpy(sk, e->d_out_count.p + 12, sizeof(sk), cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[tnt]   evaluations skipped (cumulative) %u, contradictions %u\n", sk[0], sk[1]);
+		}
+#endif
 #if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 6
 		{
 			uint32_t why[4];

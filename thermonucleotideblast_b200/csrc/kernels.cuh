@@ -1234,12 +1234,15 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 				if (dp.runkey == 0xfffffff1u) handoff = 1;
 				continue;
 #endif
+#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 7
+				tnt_dbg_skip = a.out_count + 12;
+#endif
 #if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 6
 				if (tid == 0 && blockIdx.x == 0) tnt_dbg_why = a.out_count + 8;
 				if (ncells == -2) atomicAdd(a.out_count + 8, 1u);
 #endif
 				if (ncells < 0) handoff = ncells == -1 ? 2 : 1;
-				else if (!lean_finish(sh, a.thermo, os.r_log_ct, tv, Lt, cells[0], a.emit_all != 0, os.min_tm, os.max_tm, best_aln, best, flags)) handoff = 1;
+				else if (!lean_finish(sh, a.thermo, os.r_log_ct, tv, Lt, cells[0], a.emit_all != 0, os.min_tm, os.max_tm, os.lean_min_cols, best_aln, best, flags)) handoff = 1;
 			}
 		}
 		if (handoff) {

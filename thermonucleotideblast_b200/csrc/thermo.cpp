@@ -12,6 +12,7 @@
 #include "thermo.h"
 
 #include <cmath>
+#include <vector>
 #include <cstring>
 #include <stdexcept>
 
@@ -255,6 +256,75 @@ void build_p5_table(const Thermo &th, int32_t *out)
 		const int tb = td%4;
 		out[td] = th.dg[sidx(th.bbp[pt*NB + bGAP], th.bbp[tb*NB + bGAP])];
 	}
+}
+
+// Tm >= theta  <=>  dH/(R ln Ct + dS_total) >= K  (K = theta + 273.15, denominator negative)
+//              <=>  G_K := dH - K*dS_total <= K * R ln Ct,
+// and every other outcome of the evaluation (dH >= 0, non-negative denominator) reports Tm = 0.
+// G_K of a gapless alignment is a sum over its columns (lean_evaluate, align_core.cuh):
+//   initiation; A.T closing at both ends; per column outside an internal loop the stack term
+//   H - K*S of (previous pair, pair) and one salt increment; per closed internal loop of m > 1
+//   mismatches -K*loop_S[2m] and one salt increment (the subtract / add pairs cancel).
+// For one oligo, the minimum over all start positions and all target strings of n columns is a
+// shortest path over (oligo position, target base of the last column, open mismatch run).  The
+// bound is taken 0.05 K below min_tm: binary32 evaluation of a few dozen terms differs from exact
+// arithmetic by ~1e-3 K.  Alignments of n >= the returned value are evaluated normally.
+int lean_min_columns(const Thermo &th, const OligoStrand &os, float min_tm)
+{
+	if (!(min_tm > 0.1f)) return 0; // Tm = 0 outcomes would pass: evaluate everything
+	const int L = os.len;
+	const int NMAX = std::min(L, 24);
+	const double K = (double)min_tm - 0.05 + 273.15;
+	const double limit = K*(double)os.r_log_ct;
+	const double c_s = -K*(double)th.salt*(double)th.log_na; // salt term per unit of 0.5*num_base
+	const double at_g = (double)th.at_H - K*(double)th.at_S;
+	const double INF = 1e300;
+	auto code_of = [&](int x, int t) { return (int)th.bbp[os.seq[x]*NB + t]; };
+	auto is_at = [&](int c) { return c == 7*bA + bT || c == 7*bT + bA; };
+	const int M = NMAX + 1;
+	// f[(x*4 + t)*M + m]: cheapest G_K of an alignment whose last column is (oligo base x, target
+	// base t) with an open run of m mismatch columns
+	std::vector<double> f((size_t)L*4*M, INF), g((size_t)L*4*M, INF);
+	for (int x = 0; x < L; ++x)
+		for (int t = 0; t < 4; ++t) {
+			const int c = code_of(x, t);
+			if (th.wc[c]) f[(size_t)(x*4 + t)*M] = (double)th.init_H - K*(double)th.init_S + (is_at(c) ? at_g : 0.0);
+		}
+	for (int n = 2; n <= NMAX; ++n) {
+		std::fill(g.begin(), g.end(), INF);
+		for (int x = 0; x + 1 < L; ++x)
+			for (int t1 = 0; t1 < 4; ++t1) {
+				const int last = code_of(x, t1);
+				for (int m = 0; m < n; ++m) {
+					const double base = f[(size_t)(x*4 + t1)*M + m];
+					if (base >= INF) continue;
+					for (int t2 = 0; t2 < 4; ++t2) {
+						const int cur = code_of(x + 1, t2);
+						double v = base;
+						if (th.wc[last] || th.wc[cur]) v += (double)th.H[last*NPAIR + cur] - K*(double)th.S[last*NPAIR + cur] + c_s;
+						int m2;
+						if (th.wc[cur]) {
+							if (m > 1) v += -K*(double)th.loop_S[2*m] + c_s;
+							m2 = 0;
+						}
+						else m2 = m + 1;
+						double &slot = g[(size_t)((x + 1)*4 + t2)*M + m2];
+						if (v < slot) slot = v;
+					}
+				}
+			}
+		f.swap(g);
+		if (n >= 3) {
+			double best = INF;
+			for (int x = 0; x < L; ++x)
+				for (int t = 0; t < 4; ++t) {
+					const int c = code_of(x, t);
+					if (th.wc[c]) best = std::min(best, f[(size_t)(x*4 + t)*M] + (is_at(c) ? at_g : 0.0));
+				}
+			if (best <= limit) return n;
+		}
+	}
+	return NMAX + 1;
 }
 
 float r_log_ct(float ct)

@@ -16,6 +16,12 @@ bool build_lean_tables(const Thermo &th, const OligoStrand &os, const int32_t *r
 float r_log_ct(float ct);
 
 // compacted seed word list of an oligo (complement = reverse complement, plus-strand search)
+// Smallest number of columns a trimmed gapless alignment of this oligo (first and last column
+// Watson-Crick, the only kind the lean alignment tier evaluates) needs to reach a melting
+// temperature of min_tm, whatever the target is.  Shorter alignments fail the Tm filter and are
+// not evaluated.
+int lean_min_columns(const Thermo &th, const OligoStrand &os, float min_tm);
+
 int build_words(const char *oligo, int W, bool complement, uint16_t *words);
 
 int base_from_ascii(char c);

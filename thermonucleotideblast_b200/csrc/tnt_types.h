@@ -46,6 +46,8 @@ struct OligoStrand {
 	float r_log_ct;              // NC_R*logf(Ct) (nuc_cruc.cpp:2291), computed with the host libm
 	float min_tm, max_tm, min_dg, max_dg;
 	uint32_t clamp5, clamp3, max_gap, max_mismatch, max_poly_degen;
+	int32_t lean_min_cols;       // gapless alignments with fewer columns cannot reach min_tm (thermo.cpp, lean_min_columns)
+	int32_t pad_;
 };
 
 // Resident fragment descriptor.
