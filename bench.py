@@ -109,20 +109,22 @@ def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False, kin
 class ClockSampler:
     """SM clock / throttle reasons during the timed region (B200_PROFILING.md) through NVML.
 
-    At most `max_samples` steps are sampled, each exactly once, from a helper thread that fires a
-    fixed delay into the step, i.e. while the alignment kernels are running (a continuously
-    polling nvidia-smi / NVML thread was measured to slow the CUDA API calls of a step by >30 %,
-    and on some boxes one NVML query takes ~20 ms).  The step waits for its sample before it ends,
-    so whatever the query costs lands inside the timing."""
+    One step in the middle of the timed region is sampled, exactly once, from a helper thread
+    that fires a fixed delay into the step, i.e. while the alignment kernels are running; the step
+    waits for its sample before it ends, so whatever the query costs lands inside the timing.  A
+    continuously polling nvidia-smi / NVML thread was measured to slow the CUDA API calls of a step
+    by >30 %, and on some boxes a single NVML query takes 20-50 ms and stalls concurrent CUDA
+    calls for as long -- hence one query in the timed region, and further samples from an extra,
+    untimed repetition of the same step right after it (`extra_step`)."""
 
-    def __init__(self, gpu_index: int, steps: int, max_samples: int = 4):
+    def __init__(self, gpu_index: int, steps: int):
         self.samples = []
         self.reasons = set()
         self.sm_max = None
         self.cost_s = 0.0
         self._h = None
-        stride = max(1, -(-steps // max_samples))
-        self.when = set(range(0, steps, stride)) | {steps - 1}
+        self.timed_samples = 0
+        self.when = {steps // 2}
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -155,9 +157,21 @@ class ClockSampler:
             self._thread.join()
             self._thread = None
 
+    def extra_step(self, run_step, delay_s: float, n: int = 2):
+        """Untimed repetition(s) of the step, sampled like the timed one."""
+        if self._h is None:
+            return
+        for _ in range(n):
+            self.when = {-1}
+            self.start_step(-1, delay_s)
+            run_step()
+            self.end_step()
+
     def sample(self, step: int):
         if self._h is None or step not in self.when:
             return
+        if step >= 0:
+            self.timed_samples += 1
         t0 = time.perf_counter()
         nv = self._nv
         try:
@@ -178,7 +192,9 @@ class ClockSampler:
 
     def result(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-               "samples": len(self.samples), "source": "nvml, one query per sampled step, issued while the step's kernels run",
+               "samples": len(self.samples), "samples_in_timed_region": self.timed_samples,
+               "source": "nvml, one query per sampled step, issued while the step's kernels run; "
+                         "one step of the timed region + untimed repetitions of the same step right after it",
                "sampling_ms_total": self.cost_s * 1e3}
         if self.samples:
             out["sm_mhz"] = float(np.median(self.samples))
@@ -378,6 +394,8 @@ def main():
         launches += st.kernel_launches
     barrier()
     dt = (time.perf_counter() - t0) / args.steps
+    if not os.environ.get("TNT_NO_SAMPLER"):
+        sampler.extra_step(lambda: eng.search_raw(opts), 0.2 * warm_s)
     clocks = sampler.result()
     dt = max_over_ranks(dt)
     st = eng.stats()
