@@ -557,9 +557,6 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 
 			if (a.e - a.b < 3) continue;
 
-#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 2
-			if (a.e == 1000) // timing experiment only: traceback without evaluation
-#endif
 			if (nc_evaluate(sh, th, r_log_ct, a)) {
 				const float local_dg = TNT_SUB(a.dH, TNT_MUL(T, a.dS));
 				if (!best.valid || local_dg < best_dg) {
@@ -923,9 +920,6 @@ __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__
 	a.b = a.e = 2;
 	a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
 	a.dH = a.dS = a.tm = 0.0f;
-#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 5
-	if (n < 1000) return true; // timing experiment only: diagonal walk, then nothing
-#endif
 
 	if (th->dangle5 || th->dangle3) {
 		// dangling-end columns can hold virtual bases: materialise and use the general code
@@ -960,9 +954,6 @@ __device__ __forceinline__ bool lean_finish(const DpShared &sh, const Thermo *__
 	if (!keep_all && n < min_cols) return true;
 #endif
 	float dH, dS, tm = 0.0f;
-#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 4
-	if (n < 1000) return true; // timing experiment only: no evaluation
-#endif
 	if (!lean_evaluate(tv.tab, Lq, th, r_log_ct, tv.tgt, fm_q, fm_t, n, dH, dS, tm)) return true;
 	best.valid = true;
 	best.dH = dH; best.dS = dS; best.tm = tm;

@@ -1229,11 +1229,6 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 				tv.tgt = tgt;
 				tv.maxscore = (int)(dp.runkey >> 12)*LEAN_SCALE;
 				const int ncells = lean_max_cell(dp, Lt, cells);
-#if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 1
-				// timing experiment only: fill without traceback / evaluation
-				if (dp.runkey == 0xfffffff1u) handoff = 1;
-				continue;
-#endif
 #if defined(TNT_EXPERIMENT) && TNT_EXPERIMENT == 7
 				tnt_dbg_skip = a.out_count + 12;
 #endif
