@@ -108,6 +108,8 @@ struct OsSet {
 	DevBuf<OligoStrand> d_os;
 	DevBuf<uint16_t> d_keys;
 	std::vector<uint64_t> packed;       // [nos][2] seed-orientation oligos, 2 bit/base (bit 127: contiguous word list)
+	std::vector<uint32_t> assay_present; // [n_assays][nkeys/32] k-mer bitmap per assay
+	DevBuf<uint32_t> d_assay_present;
 	DevBuf<uint64_t> d_packed;
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
 	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
@@ -630,6 +632,16 @@ void finish_set(tnt_engine *e, OsSet &set)
 		set.packed[2*s + 1] = w[1] | ((uint64_t)1 << 63);
 	}
 	set.d_packed.upload(set.packed, e->stream);
+	if (set.nkeys >= 32) {
+		const size_t words = set.nkeys/32, na = e->assays.size();
+		set.assay_present.assign(words*std::max<size_t>(na, 1), 0);
+		for (size_t s = 0; s < nos; ++s)
+			for (int k = 0; k < set.os[s].nwords; ++k) {
+				const uint32_t key = set.keys[s*MAX_OLIGO + (size_t)k];
+				set.assay_present[(size_t)set.os[s].assay*words + (key >> 5)] |= 1u << (key & 31u);
+			}
+		set.d_assay_present.upload(set.assay_present, e->stream);
+	}
 	set.d_keys.upload(set.keys, e->stream);
 	set.d_present.upload(set.present, e->stream);
 	set.d_offset.upload(set.offset, e->stream);
@@ -664,6 +676,7 @@ ScanArgs scan_args(tnt_engine *e, OsSet &set, uint32_t cap)
 	a.os = set.d_os.p;
 	a.os_keys = set.d_keys.p;
 	a.os_packed = set.d_packed.p;
+	a.assay_present = set.nkeys >= 32 ? set.d_assay_present.p : nullptr;
 	a.tiles = e->d_tiles.p;
 	a.W = e->prm.word_size;
 	a.cand = e->d_cand.p;

@@ -214,6 +214,7 @@ struct ScanArgs {
 	const OligoStrand *os;
 	const uint16_t *os_keys;   // [nos][MAX_OLIGO] little-endian keys of the compacted word list
 	const uint64_t *os_packed; // [nos][2] seed-orientation oligo, 2 bit/base; bit 127 set: words are contiguous (no degenerate letter)
+	const uint32_t *assay_present; // [n_assays][nkeys/32] k-mer bitmap per assay (region scan: a region belongs to one assay)
 	const ScanTile *tiles;
 	uint32_t tile_begin, tile_end;
 	int W;
@@ -648,10 +649,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_region_scan(RegionScanArgs ra)
 	for (uint32_t r = blockIdx.x; r < ra.nregions; r += gridDim.x) {
 		const Region rg = ra.regions[r];
 		const Target tg = a.db.targets[rg.target];
+		// only the words of this region's assay matter: its own bitmap rejects the rest of the table
+		const uint32_t *__restrict__ present = a.assay_present ? a.assay_present + (size_t)rg.assay*(a.wt.nkeys/32u) : a.wt.present;
 		for (uint32_t p = rg.start + threadIdx.x; p < rg.stop; p += SCAN_THREADS) {
 			if (p + (uint32_t)a.W > tg.len) break;
 			const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
-			if (!((__ldg(a.wt.present + (key >> 5)) >> (key & 31u)) & 1u)) continue;
+			if (!((__ldg(present + (key >> 5)) >> (key & 31u)) & 1u)) continue;
 			const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
 			for (uint32_t e = e0; e < e1; ++e) {
 				const uint32_t ent = __ldg(a.wt.entry + e);
