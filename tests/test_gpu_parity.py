@@ -614,3 +614,32 @@ def test_upload_paths_agree(engine_lib, monkeypatch):
     assert run(frags_pinned, True, 0) == base
     assert run(frags_pageable, True, 2) == base
     assert run(frags_pinned, False, 2) == base
+
+
+def test_incremental_targets(engine_lib, oracle):
+    """Fragments registered after a search join the resident set: the next search covers old and
+    new fragments and equals a fresh engine that got all of them at once."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(1717)
+    db = [gen.random_codes(int(rng.integers(20000, 40000)), rng) for _ in range(5)]
+    assays = gen.make_assays(rng, db, 4, "taqman", variants=2)
+    o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+
+    def keys(e, hits):
+        return [(h.target_id, h.assay_index) + hit_key(e, h, assays[h.assay_index]) + hit_floats(h) for h in hits]
+
+    with Engine() as e:
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        for c in db[:2]:
+            e.add_target(c)
+        first = keys(e, e.search(to_opts(o)))
+        for c in db[2:]:
+            e.add_target(c)
+        both = keys(e, e.search(to_opts(o)))
+    with Engine() as e:
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        e.add_targets(db)
+        fresh = keys(e, e.search(to_opts(o)))
+    assert both == fresh
+    assert [k for k in both if k[0] < 2] == first
+    assert len(fresh) >= 4
