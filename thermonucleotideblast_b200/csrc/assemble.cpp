@@ -7,6 +7,8 @@
 #include <cstring>
 #include <map>
 #include <stdexcept>
+#include <string>
+#include <thread>
 
 #include "thermo.h"
 
@@ -316,21 +318,57 @@ void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &o
 		}
 	}
 	const BoundSite *base = sites.data();
-	std::vector<const BoundSite *> group;
+	// group boundaries in `order`
+	std::vector<size_t> starts;
 	for (size_t i = 0; i < order.size();) {
+		starts.push_back(i);
 		size_t j = i;
-		group.clear();
-		while (j < order.size() && sites[order[j]].target == sites[order[i]].target && sites[order[j]].assay == sites[order[i]].assay)
-			group.push_back(&sites[order[j++]]);
-		const int ai = sites[order[i]].assay;
-		const int id = assay_ids[(size_t)ai];
-		if (assay_has_primers[(size_t)ai]) { // tntblast_local.cpp:559-611
-			if (opt.assay_format == TNT_ASSAY_PADLOCK || opt.assay_format == TNT_ASSAY_MIPS)
-				join_padlock(group, ai, id, opt, base, hits, refs);
-			else join_pcr(group, ai, id, assay_has_probe[(size_t)ai] != 0, opt, base, hits, refs);
-		}
-		else join_probe(group, ai, id, base, hits, refs); // :612-625
+		while (j < order.size() && sites[order[j]].target == sites[order[i]].target && sites[order[j]].assay == sites[order[i]].assay) ++j;
 		i = j;
+	}
+	starts.push_back(order.size());
+	const size_t ngroups = starts.size() - 1;
+
+	auto join_range = [&](size_t g0, size_t g1, std::vector<tnt_hit> &out_hits, std::vector<HitSites> &out_refs) {
+		std::vector<const BoundSite *> group;
+		for (size_t g = g0; g < g1; ++g) {
+			group.clear();
+			for (size_t k = starts[g]; k < starts[g + 1]; ++k) group.push_back(&sites[order[k]]);
+			const int ai = group[0]->assay;
+			const int id = assay_ids[(size_t)ai];
+			if (assay_has_primers[(size_t)ai]) { // tntblast_local.cpp:559-611
+				if (opt.assay_format == TNT_ASSAY_PADLOCK || opt.assay_format == TNT_ASSAY_MIPS)
+					join_padlock(group, ai, id, opt, base, out_hits, out_refs);
+				else join_pcr(group, ai, id, assay_has_probe[(size_t)ai] != 0, opt, base, out_hits, out_refs);
+			}
+			else join_probe(group, ai, id, base, out_hits, out_refs); // :612-625
+		}
+	};
+
+	// The groups are independent; many sites -> a few host threads, results concatenated in group order
+	const unsigned nthreads = order.size() < 20000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+	if (nthreads == 1) { join_range(0, ngroups, hits, refs); return; }
+	std::vector<std::vector<tnt_hit>> part_hits(nthreads);
+	std::vector<std::vector<HitSites>> part_refs(nthreads);
+	std::vector<std::string> errors(nthreads);
+	std::vector<std::thread> pool;
+	// equal numbers of sites per thread
+	std::vector<size_t> cut(nthreads + 1, ngroups);
+	cut[0] = 0;
+	for (unsigned t = 1; t < nthreads; ++t) {
+		const size_t want = order.size()*t/nthreads;
+		cut[t] = (size_t)(std::lower_bound(starts.begin(), starts.end() - 1, want) - starts.begin());
+	}
+	for (unsigned t = 0; t < nthreads; ++t)
+		pool.emplace_back([&, t]() {
+			try { join_range(cut[t], cut[t + 1], part_hits[t], part_refs[t]); }
+			catch (const std::exception &ex) { errors[t] = ex.what(); }
+		});
+	for (std::thread &t : pool) t.join();
+	for (const std::string &err : errors) if (!err.empty()) throw std::runtime_error(err);
+	for (unsigned t = 0; t < nthreads; ++t) {
+		hits.insert(hits.end(), part_hits[t].begin(), part_hits[t].end());
+		refs.insert(refs.end(), part_refs[t].begin(), part_refs[t].end());
 	}
 }
 
