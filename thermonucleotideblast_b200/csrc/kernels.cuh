@@ -319,6 +319,49 @@ __device__ __forceinline__ void staged_flush(const ScanArgs &a, const StagedCand
 	__syncwarp();
 }
 
+// Hit handling of the scan kernels, one table hit per lane: the table entries of the 32 hits are
+// walked in lock step; survivors of the diagonal test are compacted into the warp's staging
+// buffer (64 entries), and a full buffer is appended to the buckets by all 32 lanes at once (one
+// atomic per distinct bucket, issued in parallel: one L2 round trip per 32 candidates instead of
+// one per divergent append).
+__device__ __forceinline__ void warp_process_hits(const ScanArgs &a, const Target &tg, uint32_t target, bool hit, uint32_t p,
+	uint32_t key, uint32_t kmask, StagedCand *cbuf, uint32_t &cn)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	uint32_t e0 = 0, e1 = 0;
+	if (hit) {
+		e0 = __ldg(a.wt.offset + key);
+		e1 = __ldg(a.wt.offset + key + 1);
+	}
+	uint32_t more = __ballot_sync(0xffffffffu, e0 < e1);
+	while (more) {
+		bool keep = false;
+		uint32_t os = 0, k = 0;
+		if (e0 < e1) {
+			const uint32_t ent = __ldg(a.wt.entry + e0);
+			os = ent >> 8;
+			k = ent & 0xffu;
+			keep = first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os);
+			++e0;
+		}
+		const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+		if (keep) {
+			StagedCand &c = cbuf[cn + (uint32_t)__popc(kept & ((1u << lane) - 1u))];
+			c.os = os;
+			c.target_k = target | (k << 24);
+			c.t = p;
+		}
+		cn += (uint32_t)__popc(kept);
+		if (cn >= 32) {
+			staged_flush(a, cbuf, 32u);
+			cn -= 32;
+			if (lane < cn) cbuf[lane] = cbuf[32 + lane]; // the overhang moves to the front
+			__syncwarp();
+		}
+		more = __ballot_sync(0xffffffffu, e0 < e1);
+	}
+}
+
 // Two phases per 8192-base tile so that warps stay converged: (1) every thread tests its 32
 // positions against the k-mer bitmap in shared memory and the block compacts the hit positions
 // into a shared queue; (2) the queue is processed one hit per thread (CSR walk, diagonal test,
@@ -381,48 +424,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 		}
 		__syncthreads();
 
-		// phase 2: every warp takes 32 queued positions at a time, one per lane.  The table entries
-		// of the 32 hits are walked in lock step; survivors of the diagonal test are compacted into
-		// the warp's staging buffer, and a full buffer is appended to the buckets by all 32 lanes at
-		// once (one atomic per distinct bucket, issued in parallel: one L2 round trip per 32
-		// candidates instead of one per divergent emit).
+		// phase 2: every warp takes 32 queued positions at a time, one per lane
 		const uint32_t total = s_total;
 		for (uint32_t q0 = warp*32u; q0 < total; q0 += SCAN_THREADS) {
 			const uint32_t q = q0 + lane;
-			uint32_t p = 0, e0 = 0, e1 = 0;
+			uint32_t p = 0, key = 0;
 			if (q < total) {
 				p = tl.start + s_queue[q];
-				const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
-				e0 = __ldg(a.wt.offset + key);
-				e1 = __ldg(a.wt.offset + key + 1);
+				key = kmer_at(a.db.db2, tg.base + p, kmask);
 			}
-			uint32_t more = __ballot_sync(0xffffffffu, e0 < e1);
-			while (more) {
-				bool keep = false;
-				uint32_t os = 0, k = 0;
-				if (e0 < e1) {
-					const uint32_t ent = __ldg(a.wt.entry + e0);
-					os = ent >> 8;
-					k = ent & 0xffu;
-					keep = first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os);
-					++e0;
-				}
-				const uint32_t kept = __ballot_sync(0xffffffffu, keep);
-				if (keep) {
-					StagedCand &c = cbuf[cn + (uint32_t)__popc(kept & ((1u << lane) - 1u))];
-					c.os = os;
-					c.target_k = tl.target | (k << 24);
-					c.t = p;
-				}
-				cn += (uint32_t)__popc(kept);
-				if (cn >= 32) {
-					staged_flush(a, cbuf, 32u);
-					cn -= 32;
-					if (lane < cn) cbuf[lane] = cbuf[32 + lane]; // the overhang moves to the front
-					__syncwarp();
-				}
-				more = __ballot_sync(0xffffffffu, e0 < e1);
-			}
+			warp_process_hits(a, tg, tl.target, q < total, p, key, kmask, cbuf, cn);
 		}
 		__syncthreads();
 	}
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 // groups that pass are looked at base by base.  Each thread streams 4 x 64 bases with all loads
 // issued up front (coalesced 16-byte loads, the word that follows a segment comes from the
 // neighbouring lane by shuffle), hit positions go through a small shared-memory queue so that the
-// rare hit path runs converged.
+// rare hit path runs converged (warp_process_hits: one hit per lane, staged emission).
 // ------------------------------------------------------------------------------------------
 constexpr int SPARSE_THREADS = 512;
 constexpr int SPARSE_SEGS = 4;                       // 64-base segments per lane: one warp covers one SCAN_TILE
@@ -466,57 +477,6 @@ __global__ void k_build_group_bitmap(const uint32_t *__restrict__ present, uint3
 	}
 }
 
-__device__ __forceinline__ void scan_process_hit(const ScanArgs &a, const Target &tg, uint32_t target, uint32_t p, uint32_t kmask)
-{
-	const uint32_t key = kmer_at(a.db.db2, tg.base + p, kmask);
-	const uint32_t e0 = __ldg(a.wt.offset + key), e1 = __ldg(a.wt.offset + key + 1);
-	for (uint32_t e = e0; e < e1; ++e) {
-		const uint32_t ent = __ldg(a.wt.entry + e);
-		const uint32_t os = ent >> 8, k = ent & 0xffu;
-		if (first_on_diagonal(a.db.db2, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os))
-			emit_candidate(a, os, target, k, p);
-	}
-}
-
-// Warp-cooperative hit handling of the sparse scan.  Lanes that found a table hit are served one
-// after the other; for each (oligo strand, word k) entry the "first on its diagonal" test runs
-// with one earlier word per lane.  Surviving candidates are staged in a per-warp buffer and
-// appended to the global buckets with one atomic per bucket and flush.
-__device__ __forceinline__ void sparse_flush(const ScanArgs &a, StagedCand *cbuf, uint32_t &cn)
-{
-	staged_flush(a, cbuf, cn);
-	cn = 0;
-}
-
-__device__ __forceinline__ void sparse_process_hits(const ScanArgs &a, const Target &tg, uint32_t target, bool hit, uint32_t p,
-	uint32_t key, uint32_t kmask, StagedCand *cbuf, uint32_t &cn)
-{
-	const unsigned lane = threadIdx.x & 31u;
-	unsigned hm = __ballot_sync(0xffffffffu, hit);
-	while (hm) {
-		const int src = __ffs(hm) - 1;
-		hm &= hm - 1;
-		const uint32_t pp = __shfl_sync(0xffffffffu, p, src);
-		const uint32_t kk_key = __shfl_sync(0xffffffffu, key, src);
-		const uint32_t e0 = __ldg(a.wt.offset + kk_key), e1 = __ldg(a.wt.offset + kk_key + 1);
-		for (uint32_t e = e0; e < e1; ++e) {
-			const uint32_t ent = __ldg(a.wt.entry + e);
-			const uint32_t os = ent >> 8, k = ent & 0xffu;
-			const uint16_t *__restrict__ keys = a.os_keys + (size_t)os*MAX_OLIGO;
-			bool earlier = false;
-			for (uint32_t kk = lane; kk < k; kk += 32) {
-				const uint32_t back = k - kk;
-				if (pp >= back) earlier |= kmer_at(a.db.db2, tg.base + pp - back, kmask) == keys[kk];
-			}
-			if (!__any_sync(0xffffffffu, earlier)) {
-				if (cn == 32) sparse_flush(a, cbuf, cn);
-				if (lane == 0) { cbuf[cn].os = os; cbuf[cn].target_k = target | (k << 24); cbuf[cn].t = pp; }
-				++cn;
-			}
-		}
-	}
-}
-
 // Warps work independently (own tiles, own queue, no block-wide barrier after the bitmaps are
 // staged), so loads, filtering and the rare hit processing of different warps overlap.
 __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanArgs sa)
@@ -524,7 +484,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 	extern __shared__ uint32_t s_dyn[];       // [group bitmap | W-mer bitmap]
 	__shared__ uint32_t s_queue[SPARSE_THREADS/32][SPARSE_QUEUE];
 	__shared__ uint32_t s_qn[SPARSE_THREADS/32];
-	__shared__ StagedCand s_cbuf[SPARSE_THREADS/32][32];
+	__shared__ StagedCand s_cbuf[SPARSE_THREADS/32][64];
 	const ScanArgs &a = sa.s;
 	const uint32_t kmask = a.wt.nkeys - 1;
 	const int gbits = 2*(a.W + sa.G - 1);
@@ -607,7 +567,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 					key = kmer_at(a.db.db2, tg.base + p, kmask);
 					hit = ((s_present[key >> 5] >> (key & 31u)) & 1u) != 0;
 				}
-				sparse_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
+				warp_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
 			}
 		}
 		else {
@@ -624,14 +584,14 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 						hit = ((s_present[key >> 5] >> (key & 31u)) & 1u) != 0;
 					}
 				}
-				sparse_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
+				warp_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
 			}
 		}
-		sparse_flush(a, cbuf, cn); // per tile: keeps the buffer logic simple
 		__syncwarp();
 		if (lane == 0) s_qn[warp] = 0;
 		__syncwarp();
 	}
+	staged_flush(a, cbuf, cn);
 }
 
 // Stage-2 scan: only the oligo strands of the region's assay, only inside the region
