@@ -714,7 +714,8 @@ void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1
 		sa.s.tiles = e->d_tiles.p;
 		sa.s.tile_begin = t0;
 		sa.s.tile_end = t1;
-		const size_t smem = ((size_t)1 << (2*(e->prm.word_size + set.group_G - 1)))/8 + ((set.nkeys + 31)/32)*sizeof(uint32_t);
+		const size_t smem = ((size_t)1 << (2*(e->prm.word_size + set.group_G - 1)))/8 + ((set.nkeys + 31)/32)*sizeof(uint32_t) +
+			(size_t)(SPARSE_THREADS/32)*(SPARSE_QUEUE*sizeof(uint32_t) + 64*sizeof(StagedCand));
 		static size_t sparse_attr = 0; // the opt-in is sticky per function: set it only when it has to grow
 		if (smem > sparse_attr) { CUDA_OK(cudaFuncSetAttribute(k_seed_scan_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); sparse_attr = smem; }
 		const uint32_t grid = std::min<uint32_t>((ntiles + SPARSE_THREADS/32 - 1)/(SPARSE_THREADS/32), (uint32_t)e->sm_count);

@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 // neighbouring lane by shuffle), hit positions go through a small shared-memory queue so that the
 // rare hit path runs converged (warp_process_hits: one hit per lane, staged emission).
 // ------------------------------------------------------------------------------------------
-constexpr int SPARSE_THREADS = 512;
+constexpr int SPARSE_THREADS = 1024;
 constexpr int SPARSE_SEGS = 4;                       // 64-base segments per lane: one warp covers one SCAN_TILE
 constexpr int SPARSE_QUEUE = 256;                    // queued four-base groups per warp
 static_assert(32*SPARSE_SEGS*64 == SCAN_TILE, "a warp scans exactly one tile");
@@ -481,26 +481,24 @@ __global__ void k_build_group_bitmap(const uint32_t *__restrict__ present, uint3
 // staged), so loads, filtering and the rare hit processing of different warps overlap.
 __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanArgs sa)
 {
-	extern __shared__ uint32_t s_dyn[];       // [group bitmap | W-mer bitmap]
-	__shared__ uint32_t s_queue[SPARSE_THREADS/32][SPARSE_QUEUE];
-	__shared__ uint32_t s_qn[SPARSE_THREADS/32];
-	__shared__ StagedCand s_cbuf[SPARSE_THREADS/32][64];
+	extern __shared__ uint32_t s_dyn[];       // [group bitmap | W-mer bitmap | per-warp queues | per-warp staging]
 	const ScanArgs &a = sa.s;
 	const uint32_t kmask = a.wt.nkeys - 1;
 	const int gbits = 2*(a.W + sa.G - 1);
 	const uint32_t nkeys2 = 1u << gbits;
 	uint32_t *s_group = s_dyn;
 	uint32_t *s_present = s_dyn + nkeys2/32;
+	uint32_t *s_queue_all = s_present + (a.wt.nkeys + 31)/32;
+	StagedCand *s_cbuf_all = reinterpret_cast<StagedCand *>(s_queue_all + (SPARSE_THREADS/32)*SPARSE_QUEUE);
 	for (uint32_t i = threadIdx.x; i < nkeys2/32; i += SPARSE_THREADS) s_group[i] = sa.group_present[i];
 	for (uint32_t i = threadIdx.x; i < (a.wt.nkeys + 31)/32; i += SPARSE_THREADS) s_present[i] = a.wt.present[i];
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	if (lane == 0) s_qn[warp] = 0;
 	__syncthreads();
 
 	const uint32_t gmask = nkeys2 - 1;
 	const int G = sa.G;
-	uint32_t *queue = s_queue[warp];
-	StagedCand *cbuf = s_cbuf[warp];
+	uint32_t *queue = s_queue_all + warp*SPARSE_QUEUE;
+	StagedCand *cbuf = s_cbuf_all + warp*64;
 	uint32_t cn = 0; // staged candidates (warp-uniform)
 	const uint32_t nwarps = gridDim.x*(SPARSE_THREADS/32);
 
@@ -511,7 +509,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 		const bool any_valid = tg.len >= (uint32_t)a.W;
 		const uint32_t last_valid = any_valid ? tg.len - (uint32_t)a.W : 0u; // last position with a whole W-mer
 
-		bool overflow = false;
+		uint32_t qn = 0; // queued groups of this tile (warp-uniform)
 		// all loads first: segment sgi of this lane = bases [ (sgi*32 + lane)*64, +64 ) of the tile
 		uint4 seg[SPARSE_SEGS];
 #pragma unroll
@@ -528,36 +526,53 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 			// the 32 bases after the segment: first word of the next lane's segment
 			uint64_t nx = __shfl_down_sync(0xffffffffu, lo, 1);
 			if (lane == 31) nx = (segbase < tg.len) ? __ldg(a.db.db2 + w0 + (uint64_t)(sgi*32 + lane)*2u + 2u) : 0ull;
-			// branch-free pass over the 16 four-base groups: one bit per (sub)group that may hold a hit
-			uint32_t gm = 0;
+			// branch-free pass over the 16 four-base groups: one bit per group that may hold a hit.
+			// The segment is a stream of 32-bit words; a group key starts at bit 8g, i.e. inside
+			// word g/4 (it spills into the next word for two of the four phases).
+			const uint32_t w[5] = {seg[sgi].x, seg[sgi].y, seg[sgi].z, seg[sgi].w, (uint32_t)nx};
+			uint32_t gm = 0; // G == 4: bit g <-> group g; otherwise two bits per group
+			if (G == 4) {
 #pragma unroll
-			for (int g = 0; g < 16; ++g) {
-				const int bit = 8*g;
-				uint64_t x;
-				if (bit < 64) x = bit ? ((lo >> bit) | (hi << (64 - bit))) : lo;
-				else x = (bit - 64) ? ((hi >> (bit - 64)) | (nx << (128 - bit))) : hi;
-				if (G == 4) {
-					const uint32_t gkey = (uint32_t)x & gmask;
-					gm |= ((s_group[gkey >> 5] >> (gkey & 31u)) & 1u) << (2*g);
+				for (int g = 0; g < 16; ++g) {
+					const int sh = (8*g) & 31;
+					const uint32_t x = sh <= 12 ? (w[g >> 2] >> sh) : __funnelshift_r(w[g >> 2], w[(g >> 2) + 1], sh);
+					const uint32_t gkey = x & gmask;
+					const uint32_t word = s_group[gkey >> 5];
+					// shift the key's bit down to bit 0 and push it into gm from the top
+					gm = __funnelshift_r(gm, __funnelshift_r(word, 0u, gkey), 1);
 				}
-				else { // two sub-groups per four bases (W = 8: G = 3 -> positions 0..2 and 3; smaller G: conservative)
+				gm >>= 16; // group 0 arrives at bit 16, group 15 at bit 31
+			}
+			else {
+#pragma unroll
+				for (int g = 0; g < 16; ++g) {
+					const int bit = 8*g;
+					uint64_t x;
+					if (bit < 64) x = bit ? ((lo >> bit) | (hi << (64 - bit))) : lo;
+					else x = (bit - 64) ? ((hi >> (bit - 64)) | (nx << (128 - bit))) : hi;
+					// two sub-groups per four bases (W = 8: G = 3 -> positions 0..2 and 3; smaller G: conservative)
 					const uint32_t k0 = (uint32_t)x & gmask, k1 = (uint32_t)(x >> (2*G)) & gmask;
-					gm |= ((s_group[k0 >> 5] >> (k0 & 31u)) & 1u) << (2*g);
-					gm |= ((s_group[k1 >> 5] >> (k1 & 31u)) & 1u) << (2*g + 1);
+					const uint32_t any = ((s_group[k0 >> 5] >> (k0 & 31u)) | (s_group[k1 >> 5] >> (k1 & 31u))) & 1u;
+					gm |= any << g;
 				}
 			}
 			if (segbase >= tg.len || !any_valid) gm = 0;
-			// rare: queue the four-base groups that passed (phase 2 looks at the bases one by one)
-			while (gm) {
-				const int grp = (__ffs(gm) - 1) >> 1;
-				gm &= ~(3u << (2*grp)); // one queue entry per four-base group
-				const uint32_t slot = atomicAdd(&s_qn[warp], 1u);
-				if (slot < SPARSE_QUEUE) queue[slot] = segbase + (uint32_t)(4*grp);
-				else overflow = true;
+			// rare: queue the four-base groups that passed (phase 2 looks at the bases one by one);
+			// slots come from a warp-wide ballot, the queue length lives in a register
+			uint32_t pend = gm;
+			while (__any_sync(0xffffffffu, pend != 0u)) {
+				const bool has = pend != 0u;
+				const int grp = __ffs(pend) - 1;
+				pend &= pend - 1u;
+				const uint32_t bal = __ballot_sync(0xffffffffu, has);
+				const uint32_t slot = qn + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+				if (has && slot < SPARSE_QUEUE) queue[slot] = segbase + (uint32_t)(4*grp);
+				qn += (uint32_t)__popc(bal);
 			}
 		}
+		const bool overflow = qn > SPARSE_QUEUE;
 		__syncwarp();
-		if (__any_sync(0xffffffffu, overflow)) {
+		if (overflow) {
 			// more groups passed the pre-filter than the queue holds (dense table / repeats): redo
 			// this tile base by base, one position per lane
 			for (uint32_t p = tl.start + lane; p < min(tl.start + (uint32_t)SCAN_TILE, tg.len); p += 32) {
@@ -572,7 +587,7 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 		}
 		else {
 			// phase 2: eight queued groups at a time, one position per lane
-			const uint32_t total = s_qn[warp];
+			const uint32_t total = qn;
 			for (uint32_t base = 0; base < total; base += 8) {
 				const uint32_t q = base + (lane >> 2);
 				bool hit = false;
@@ -587,8 +602,6 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 				warp_process_hits(a, tg, tl.target, hit, p, key, kmask, cbuf, cn);
 			}
 		}
-		__syncwarp();
-		if (lane == 0) s_qn[warp] = 0;
 		__syncwarp();
 	}
 	staged_flush(a, cbuf, cn);
