@@ -202,6 +202,10 @@ int tnt_debug_thermo(float T, float na, int32_t *dg, uint8_t *bbp);
 /* Compacted seed word list of an oligo (DNAHash_iterator::build_word_list, seq_hash.h:287-374);
  * returns the number of words written (at most TNT_MAX_OLIGO_LEN). */
 int tnt_debug_words(const char *oligo, int32_t word_size, int32_t complement, uint16_t *words);
+/* Host-side bound of the lean alignment tier: the smallest number of columns a trimmed gapless
+ * alignment of `oligo` needs to reach a melting temperature of min_tm at the given conditions
+ * (shorter alignments are rejected without evaluating them).  Negative on error. */
+int tnt_debug_min_columns(float T, float na, const char *oligo, float strand_concentration, float min_tm);
 
 #ifdef __cplusplus
 }

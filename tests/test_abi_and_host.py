@@ -95,3 +95,40 @@ def test_host_word_lists_match_oracle_seeds(engine_lib, oracle):
                     assert words[k] == val
                     k += 1
             assert k == n
+
+
+def test_min_columns_bound_against_the_oracle(engine_lib, oracle):
+    """The lean alignment tier does not evaluate gapless alignments that are too short to reach the
+    Tm threshold (lean_min_columns, thermo.cpp).  Check the bound against the oracle: the most
+    stable gapless duplex of n columns is a perfect match, so for every n below the bound and every
+    window of the oligo, the oracle's Tm of oligo vs (perfect complement of the window, blocked on
+    both sides) must stay below the threshold."""
+    import numpy as np
+    import gen
+    f = engine_lib.tnt_debug_min_columns
+    f.argtypes = [C.c_float, C.c_float, C.c_char_p, C.c_float, C.c_float]
+    f.restype = C.c_int
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rng = np.random.default_rng(8128)
+    checked = 0
+    for (T, na, ct, min_tm) in [(310.15, 0.05, 9.0e-7, 45.0), (310.15, 0.05, 2.5e-7, 50.0), (330.15, 0.1, 9.0e-7, 40.0)]:
+        for _ in range(12):
+            L = int(rng.integers(18, 31))
+            ol = gen.rand_oligo(L, rng)
+            b = f(T, na, ol.encode(), ct, min_tm)
+            assert 3 <= b <= min(L, 24) + 1
+            # thresholds that accept Tm = 0 outcomes switch the shortcut off
+            assert f(T, na, ol.encode(), ct, 0.0) == 0
+            for n in range(max(3, b - 4), b):
+                for x in range(0, L - n + 1):
+                    window = ol[x:x + n]
+                    target = "".join(comp[c] for c in reversed(window))
+                    # a base never pairs with itself: block the extension on both sides
+                    left = ol[x + n] if x + n < L else "A"     # faces the oligo base after the window
+                    right = ol[x - 1] if x > 0 else "A"        # faces the oligo base before it
+                    tb = np.array([code[c] for c in (left + target + right)], dtype=np.uint8)
+                    a = oracle.align(ol, tb, T=T, na=na, ct=ct)
+                    assert (not a.valid) or a.tm < min_tm, (ol, n, x, a.tm, b)
+                    checked += 1
+    assert checked > 1000

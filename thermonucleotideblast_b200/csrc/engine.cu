@@ -1840,6 +1840,27 @@ int tnt_debug_words(const char *oligo, int32_t word_size, int32_t complement, ui
 	return build_words(oligo, word_size, complement != 0, words);
 }
 
+int tnt_debug_min_columns(float T, float na, const char *oligo, float strand_concentration, float min_tm)
+{
+	try {
+		if (!oligo || !(strand_concentration > 0.0f)) { g_error = "bad argument"; return -1; }
+		const size_t L = std::strlen(oligo);
+		if (L == 0 || L > (size_t)MAX_OLIGO) { g_error = "oligo longer than TNT_MAX_OLIGO_LEN"; return -1; }
+		Thermo th;
+		build_thermo(th, T, na, false, false);
+		OligoStrand os{};
+		os.len = (int)L;
+		for (size_t i = 0; i < L; ++i) {
+			const int b = base_from_ascii(oligo[i]);
+			if (b < 0) { g_error = ":char_to_nucleic_acid: Illegal base"; return -1; }
+			os.seq[i] = (uint8_t)b;
+		}
+		os.r_log_ct = r_log_ct(strand_concentration);
+		return lean_min_columns(th, os, min_tm);
+	}
+	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
+}
+
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms)
 {
 	API_BEGIN

@@ -1072,6 +1072,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 #define TNT_FAST_MIN_BLOCKS(LQ, FULL) ((FULL) ? 1 : ((LQ) <= 20 ? 5 : ((LQ) <= 24 ? 4 : ((LQ) <= 28 ? 3 : 1)))*(128/ALIGN_THREADS))
 #elif TNT_OCC_MODE == 5
 #define TNT_FAST_MIN_BLOCKS(LQ, FULL) (((LQ) <= 24 ? 4 : ((LQ) <= 28 ? 3 : 1))*(128/ALIGN_THREADS))
+#elif TNT_OCC_MODE == 6
+#define TNT_FAST_MIN_BLOCKS(LQ, FULL) (((LQ) <= 24 ? 4 : ((LQ) <= 32 ? 3 : ((LQ) <= 40 ? 2 : 1)))*(128/ALIGN_THREADS))
 #else
 #define TNT_FAST_MIN_BLOCKS(LQ, FULL) 1
 #endif
