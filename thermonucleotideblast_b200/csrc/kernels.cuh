@@ -1056,11 +1056,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 // Fast kernel: windows made of A/C/G/T only (the oligo may hold any code).  All units of one
 // launch belong to oligo strands of at most LQ bases.
 // Resident CTAs per SM the register allocation has to allow (other modes: experiments with
-// -DTNT_OCC_MODE=n).  Mode 5 = four CTAs for rows <= 24 (128 registers, no spills in the lean tier,
-// a few bytes in the full-trace tier), three up to 28.  Measured on B200 for the 100-assay
-// workload: lean tier 91.0 ms vs 98.2 ms without a bound, full-trace tier 9.2 ms vs 10.2 ms.
+// -DTNT_OCC_MODE=n).  Mode 6 = four CTAs for rows <= 24 (128 registers, no spills in the lean tier,
+// a few bytes in the full-trace tier), three up to 32, two up to 40.  Measured on B200: 100 TaqMan
+// assays, lean tier 91.0 ms vs 98.2 ms without a bound, full-trace tier 9.2 ms vs 10.2 ms; 30-mer
+// probes (class 32), lean tier 112 ms vs 126 ms with two CTAs.
 #ifndef TNT_OCC_MODE
-#define TNT_OCC_MODE 5
+#define TNT_OCC_MODE 6
 #endif
 #if TNT_OCC_MODE == 1
 #define TNT_FAST_MIN_BLOCKS(LQ, FULL) ((FULL) ? 1 : ((LQ) <= 22 ? 5 : ((LQ) <= 28 ? 4 : 1))*(128/ALIGN_THREADS))
