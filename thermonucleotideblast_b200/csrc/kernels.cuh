@@ -171,11 +171,24 @@ __device__ inline int exception_code(const DbView &db, const Target &tg, uint64_
 __device__ inline int load_window(const DbView &db, const Target &tg, uint32_t start, uint32_t stop, bool plus, uint8_t *out)
 {
 	int n = 0;
+	// the non-ACGT codes of a window are consecutive entries of the sorted exception list: one
+	// binary search for the first masked base, then a walk
+	uint64_t exc_at = ~0ull;
 	for (uint32_t p = start; p < stop; ++p) {
 		const uint64_t g = tg.base + p;
 		int code = (int)((__ldg(db.db2 + (g >> 5)) >> ((g & 31u)*2u)) & 3u);
 		if ((__ldg(db.nmask + (g >> 5)) >> (g & 31u)) & 1u) {
-			code = exception_code(db, tg, g);
+			if (exc_at == ~0ull) {
+				uint64_t lo = 0, hi = db.nexc;
+				while (lo < hi) {
+					const uint64_t mid = (lo + hi) >> 1;
+					if (__ldg(db.exc_pos + mid) < g) lo = mid + 1;
+					else hi = mid;
+				}
+				exc_at = lo;
+			}
+			code = (int)__ldg(db.exc_code + exc_at);
+			++exc_at;
 			if (code > 15) continue; // DB_GAP / DB_UNKNOWN are skipped silently
 		}
 		int b;
