@@ -147,6 +147,48 @@ int tnt_engine_add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uin
 int tnt_engine_add_targets(tnt_engine *e, const uint8_t *const *codes, const uint32_t *lens, uint32_t n, uint32_t *first_target_id);
 int tnt_engine_clear_targets(tnt_engine *e);
 
+/* ---- FASTA text -> resident fragments (host ingest) ----
+ * Replaces, for a FASTA database, sequence_data::load_fasta (sequence_data_fastx.cpp:13-79: a
+ * record starts at the first '>' of a line), read_bio_seq_fasta_slow (:190-382: defline up to
+ * the first '\n' / '\r'; every later character of the record that is not white space, '*' or
+ * '-' is a base), ascii_to_hash_base (seq.h:148-189) and the fragment loop of the driver
+ * (tntblast_local.cpp:282-289,448-468 with seq_len_increment, sequence_data.cpp:739-754: a
+ * record whose *byte* length exceeds `fragment_threshold` is cut into n equal pieces, each read
+ * with `overlap` extra bases on the right, tntblast_local.cpp:174,510-511).  The text is parsed
+ * on the device; the caller's text must stay valid until the call returns (page-locked text is
+ * read by DMA while earlier parts are being parsed).  Text in front of the first record is
+ * ignored like the reference does.  A defline that is empty or not terminated (the reference
+ * throws "Truncated fasta file detected!" or takes the next line for the defline) is refused;
+ * after an error the set of registered fragments is undefined: call tnt_engine_clear_targets. */
+typedef struct {
+	uint64_t text_offset;      /* byte offset of the record's '>' */
+	uint64_t text_bytes;       /* bytes up to the next record: the reference's approx_seq_len */
+	uint64_t defline_offset;   /* first byte of the defline (after '>' and leading white space) */
+	uint32_t defline_len;
+	uint32_t n_fragments;
+	uint64_t bases;            /* sequence characters of the record */
+	uint32_t first_fragment;   /* index into the fragment table of this call */
+	uint32_t pad;
+} tnt_fasta_record;
+
+typedef struct {
+	uint32_t record;           /* index into the record table of this call */
+	uint32_t start;            /* first base of the piece (reference local_target_start) */
+	uint32_t stop;             /* nominal inclusive stop (local_target_stop) */
+	uint32_t max_stop;         /* local_target_max_stop = text_bytes - 1 */
+	uint32_t len;              /* bases held: piece + right overlap, clipped at the record end */
+	uint32_t target_id;        /* engine fragment id; 0xffffffff for an empty piece (not registered) */
+} tnt_fasta_fragment;
+
+/* `fragment_threshold` 0: records are never cut.  Tables stay valid until the next
+ * tnt_engine_add_fasta, clear or destroy. */
+int tnt_engine_add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t fragment_threshold, uint32_t overlap,
+	const tnt_fasta_record **records, size_t *n_records, const tnt_fasta_fragment **fragments, size_t *n_fragments);
+
+/* seq.h codes of bases [start, start+n) of a registered fragment, read back from the packed
+ * database (parity tests of the ingest path). */
+int tnt_engine_target_codes(tnt_engine *e, uint32_t target_id, uint32_t start, uint32_t n, uint8_t *out);
+
 int tnt_engine_set_assays(tnt_engine *e, const tnt_assay *assays, int32_t n);
 
 /* All registered assays against all registered fragments: seed scan -> NucCruc alignment of

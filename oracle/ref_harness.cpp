@@ -32,6 +32,7 @@
 #include "seq_hash.h"
 #include "hybrid_sig.h"
 #include "compress.h"
+#include "sequence_data.h"
 
 #include "ref_harness.h"
 
@@ -414,4 +415,55 @@ extern "C" int ref_get_hits(ref_hit *out, long cap)
 	const long n = std::min<long>(cap, (long)g_hits.size());
 	if (n > 0) memcpy(out, g_hits.data(), n*sizeof(ref_hit));
 	return (int)n;
+}
+
+// ---------------------------------------------------------------------------
+// FASTA reader: the reference's own sequence_data class on a file
+// ---------------------------------------------------------------------------
+static sequence_data *g_fasta = nullptr;
+
+extern "C" void ref_fasta_close()
+{
+	if (g_fasta) { g_fasta->close(); delete g_fasta; g_fasta = nullptr; }
+}
+
+extern "C" long ref_fasta_open(const char *path)
+{
+	GUARD_BEGIN
+	ref_fasta_close();
+	g_fasta = new sequence_data;
+	g_fasta->open(path, std::vector<std::string>(), std::vector<std::string>());
+	return (long)g_fasta->size();
+	GUARD_END
+}
+
+extern "C" long ref_fasta_approx_len(long index)
+{
+	return g_fasta ? (long)g_fasta->approx_seq_len((size_t)index) : -1;
+}
+
+extern "C" long ref_fasta_read(long index, uint32_t start, uint32_t stop, int whole, uint8_t *out, long cap,
+	char *defline, long defline_cap)
+{
+	GUARD_BEGIN
+	if (!g_fasta) throw "no file open";
+	std::pair<std::string, SEQPTR> seq;
+	seq.second = NULL;
+	const unsigned int n = whole ? g_fasta->read_bio_seq(seq, (unsigned int)index)
+		: g_fasta->read_bio_seq(seq, (unsigned int)index, start, stop);
+	for (unsigned int i = 0; i < n && (long)i < cap; ++i) out[i] = SEQ_START(seq.second)[i];
+	if (defline && defline_cap > 0) {
+		strncpy(defline, seq.first.c_str(), (size_t)defline_cap - 1);
+		defline[defline_cap - 1] = '\0';
+	}
+	delete [] seq.second;
+	return (long)n;
+	GUARD_END
+}
+
+extern "C" void ref_seq_len_increment(uint32_t len, uint32_t max_len, uint32_t *delta, uint32_t *pieces)
+{
+	const std::pair<unsigned int, unsigned int> r = seq_len_increment(len, max_len);
+	*delta = r.first;
+	*pieces = r.second;
 }

@@ -93,6 +93,14 @@ long ref_search(const uint8_t *codes, uint32_t len, const char *forward, const c
 	const ref_options *o);
 int ref_get_hits(ref_hit *out, long cap);
 
+/* FASTA reader of the reference (sequence_data, sequence_data_fastx.cpp) on a file */
+long ref_fasta_open(const char *path);                      /* number of records, -1 on error */
+long ref_fasta_approx_len(long index);                      /* sequence_data::approx_seq_len */
+long ref_fasta_read(long index, uint32_t start, uint32_t stop, int whole, uint8_t *out, long cap,
+	char *defline, long defline_cap);                       /* read_bio_seq; bases, -1 on throw */
+void ref_fasta_close(void);
+void ref_seq_len_increment(uint32_t len, uint32_t max_len, uint32_t *delta, uint32_t *pieces);
+
 #ifdef __cplusplus
 }
 #endif

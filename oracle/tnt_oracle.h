@@ -32,6 +32,13 @@ int orc_get_hits(ref_hit *out, long cap);
  * executed by the last orc_search call -- the unit of the "alignments/s" metric */
 long orc_last_alignment_count(void);
 
+/* FASTA reader + fragment rule (tnt_oracle_fasta.c) */
+long orc_fasta_index(const char *text, uint64_t n, uint64_t *pos, long cap);
+long orc_fasta_read(const char *text, uint64_t rec_begin, uint64_t rec_end, uint32_t start, uint32_t stop,
+	uint8_t *out, long cap, uint64_t *def_begin, uint32_t *def_len);
+void orc_seq_len_increment(uint32_t len, uint32_t max_len, uint32_t *delta, uint32_t *pieces);
+long orc_fragments(uint32_t len, uint32_t max_len, uint32_t *start_out, uint32_t *stop_out, long cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,36 @@ def make_assays(rng: np.random.Generator, db: List[np.ndarray], n_assays: int, k
         else:
             assays.append((F, R, None))
     return assays
+
+
+# -- FASTA texts ------------------------------------------------------------------------------
+FASTA_EDGE_CASES = [
+    b">r1\nACGT\n",
+    b"junk in front\nmore junk\n>rec1 first >x\nACGTNNacgu\nRY*-K \tM\n\n>  rec2\r\nAC>GT\r\nTTTT\n>r3\rACGT>AC\nGG\n>r4\nAAAA",
+    b">a\nACGT\n>b\n\n>c\nNNNN\n",                       # an empty record
+    b">x desc\r\nacgtuACGTU\r\nIMRSVWYHKDBN\r\n",         # CRLF, lower case, RNA, IUPAC
+    b">q\nAC GT\tAC\x0bGT\x0cAC*GT-AC\n>p\nZZ..@@12\n",   # blanks, skipped and unknown characters
+    b">only header line\n",
+    b"\n\n>late start\nACGTACGTAC",                       # no trailing newline
+    b">t >u >v\nAC\n >w\nGT\n",                           # several '>' in a defline; '>' after a blank
+]
+
+
+def rand_fasta(rng, n_records=6, max_len=5000, width=60, iupac=0.01, crlf=False, lower=0.1):
+    """A random multi-record FASTA text (bytes) with occasional IUPAC codes, lower case and blank lines."""
+    eol = b"\r\n" if crlf else b"\n"
+    out = []
+    for r in range(n_records):
+        n = int(rng.integers(0, max_len))
+        seq = rng.choice(list(b"ACGT"), size=n).astype(np.uint8)
+        m = rng.random(n) < iupac
+        seq[m] = rng.choice(list(b"NRYKMSWBDHVI"), size=int(m.sum())).astype(np.uint8)
+        lo = rng.random(n) < lower
+        seq[lo] |= 0x20
+        out.append(b">rec%d some description %d" % (r, n) + eol)
+        w = width if width else max(n, 1)
+        for i in range(0, n, w):
+            out.append(seq[i:i + w].tobytes() + eol)
+        if rng.random() < 0.3:
+            out.append(eol)
+    return b"".join(out)

@@ -123,6 +123,46 @@ def main():
     json.dump(searches, open(os.path.join(HERE, "searches.json"), "w"))
     print("hits in fixtures:", sum(len(s["hits"]) for s in searches))
 
+    # 5. FASTA reader + fragment queue (sequence_data on a file; written separately so that the
+    #    fixtures above need not be regenerated: `make_golden.py fasta`)
+    make_fasta(r)
+
+
+def fasta_texts():
+    rng = np.random.default_rng(777)
+    texts = list(gen.FASTA_EDGE_CASES)
+    for it in range(6):
+        texts.append(gen.rand_fasta(rng, n_records=int(rng.integers(1, 6)), max_len=900, width=[60, 70, 0][it % 3],
+                                    crlf=bool(it % 2)))
+    return texts
+
+
+def make_fasta(r):
+    import base64
+    import tempfile
+    out = []
+    for text in fasta_texts():
+        with tempfile.NamedTemporaryFile(suffix=".fna", delete=False) as f:
+            f.write(text)
+        try:
+            for threshold, overlap in [(0, 0), (100, 12)]:
+                try:
+                    recs = r.fasta_records(text, f.name, threshold=threshold, overlap=overlap)
+                    out.append({"text": base64.b64encode(text).decode(), "threshold": threshold, "overlap": overlap,
+                                "records": [{"approx_len": a, "defline": d, "codes": gen.codes_to_str(w),
+                                             "pieces": [[s0, s1, gen.codes_to_str(c)] for s0, s1, c in pcs]}
+                                            for _, a, d, w, pcs in recs]})
+                except RuntimeError as ex:
+                    out.append({"text": base64.b64encode(text).decode(), "threshold": threshold, "overlap": overlap,
+                                "error": str(ex)})
+        finally:
+            os.unlink(f.name)
+    json.dump(out, open(os.path.join(HERE, "fasta.json"), "w"))
+    print("fasta fixtures:", len(out), "errors:", sum("error" in o for o in out))
+
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["fasta"]:
+        make_fasta(H.ref())
+    else:
+        main()

@@ -201,6 +201,19 @@ class _Lib:
         self._bind_window = fn("bind_window", C.c_int, [u8p, C.c_uint32, C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(AlignOut)])
         self._search = fn("search", C.c_long, [u8p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(Options)])
         self._get_hits = fn("get_hits", C.c_int, [C.POINTER(Hit), C.c_long])
+        u64p = C.POINTER(C.c_uint64)
+        self._seq_len_increment = fn("seq_len_increment", None, [C.c_uint32, C.c_uint32, u32p, u32p])
+        if prefix == "orc_":
+            self._fasta_index = fn("fasta_index", C.c_long, [C.c_char_p, C.c_uint64, u64p, C.c_long])
+            self._fasta_read = fn("fasta_read", C.c_long, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                         u8p, C.c_long, u64p, u32p])
+            self._fragments = fn("fragments", C.c_long, [C.c_uint32, C.c_uint32, u32p, u32p, C.c_long])
+        else:
+            self._fasta_open = fn("fasta_open", C.c_long, [C.c_char_p])
+            self._fasta_approx_len = fn("fasta_approx_len", C.c_long, [C.c_long])
+            self._fasta_read_file = fn("fasta_read", C.c_long, [C.c_long, C.c_uint32, C.c_uint32, C.c_int, u8p, C.c_long,
+                                                              C.c_char_p, C.c_long])
+            self._fasta_close = fn("fasta_close", None, [])
 
     def _check(self, rc):
         if rc < 0:
@@ -253,6 +266,73 @@ class _Lib:
         arr = (Hit * max(n, 1))()
         got = self._get_hits(arr, n)
         return [arr[i] for i in range(got)]
+
+
+    # -- FASTA reader ------------------------------------------------------------------------
+    def seq_len_increment(self, length: int, max_len: int) -> Tuple[int, int]:
+        d, n = C.c_uint32(), C.c_uint32()
+        self._seq_len_increment(length, max_len, C.byref(d), C.byref(n))
+        return d.value, n.value
+
+    def fasta_records(self, text: bytes, path: Optional[str] = None, threshold: int = 0, overlap: int = 0):
+        """Parse a FASTA text like the reference: per record (offset, approx_len, defline, codes of
+        the whole record, [(start, stop, codes of [start, stop + overlap])] per driver fragment).
+        The oracle works on the bytes, the compiled reference on the file `path` holding them."""
+        out = []
+        if self.prefix == "orc_":
+            cap = max(text.count(b">"), 1)
+            pos = np.zeros(cap, dtype=np.uint64)
+            n = self._fasta_index(text, len(text), pos.ctypes.data_as(C.POINTER(C.c_uint64)), cap)
+            ends = list(pos[1:n]) + [len(text)]
+            for i in range(n):
+                b, e = int(pos[i]), int(ends[i])
+                buf = np.zeros(max(e - b, 1), dtype=np.uint8)
+                d0, dl = C.c_uint64(), C.c_uint32()
+
+                def read(start, stop):
+                    m = self._fasta_read(text, b, e, start, stop, buf.ctypes.data_as(C.POINTER(C.c_uint8)), buf.size,
+                                         C.byref(d0), C.byref(dl))
+                    if m < 0:
+                        raise RuntimeError("Truncated fasta file detected!")
+                    return buf[:m].copy()
+
+                whole = read(0, 0xffffffff)
+                defline = text[d0.value:d0.value + dl.value].decode("latin-1")
+                out.append((b, e - b, defline, whole, self._pieces(e - b, threshold, overlap, read)))
+        else:
+            n = self._check(self._fasta_open(path.encode()))
+            try:
+                for i in range(n):
+                    alen = self._fasta_approx_len(i)
+                    buf = np.zeros(max(alen, 1), dtype=np.uint8)
+                    dbuf = C.create_string_buffer(4096)
+
+                    def read(start, stop, whole=0):
+                        m = self._check(self._fasta_read_file(i, start, stop, whole, buf.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                              buf.size, dbuf, 4096))
+                        return buf[:m].copy()
+
+                    whole = read(0, 0, 1)
+                    out.append((None, alen, dbuf.value.decode("latin-1"), whole, self._pieces(alen, threshold, overlap, read)))
+            finally:
+                self._fasta_close()
+        return out
+
+    def _pieces(self, alen, threshold, overlap, read):
+        """tntblast_local.cpp:282-289,448-468: the (start, stop) queue of one record."""
+        if not threshold:
+            return []
+        delta, _ = self.seq_len_increment(alen, threshold)
+        max_stop = alen - 1
+        start, stop = 0, delta
+        pieces = []
+        while True:
+            pieces.append((start, stop, read(start, stop + overlap)))
+            if stop == max_stop:
+                break
+            start = stop + 1
+            stop = min(stop + delta, max_stop)
+        return pieces
 
 
 _ref = None

@@ -122,3 +122,35 @@ def test_oracle_vs_compiled_reference(oracle, ref):
         o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
         a, b = ref.search(codes, F, R, P, o), oracle.search(codes, F, R, P, o)
         assert [(h.exact_key(), h.floats()) for h in a] == [(h.exact_key(), h.floats()) for h in b]
+
+
+def _fasta_view(recs):
+    return [{"approx_len": a, "defline": d, "codes": gen.codes_to_str(w),
+             "pieces": [[s0, s1, gen.codes_to_str(c)] for s0, s1, c in pcs]} for _, a, d, w, pcs in recs]
+
+
+def test_fasta_reader_golden(oracle):
+    """FASTA index, defline, base codes and the driver's fragment queue against vectors produced by
+    the compiled reference's own sequence_data class (tests/golden/make_golden.py fasta)."""
+    import base64
+    fixtures = load("fasta.json")
+    assert len(fixtures) >= 20
+    for fx in fixtures:
+        text = base64.b64decode(fx["text"])
+        got = _fasta_view(oracle.fasta_records(text, threshold=fx["threshold"], overlap=fx["overlap"]))
+        assert got == fx["records"]
+
+
+def test_fasta_reader_vs_compiled_reference(oracle, ref, tmp_path):
+    rng = np.random.default_rng(11)
+    for it in range(20):
+        text = gen.rand_fasta(rng, n_records=int(rng.integers(1, 8)), max_len=3000, width=[60, 80, 0, 7][it % 4],
+                              crlf=bool(it % 3 == 1), iupac=0.02)
+        path = tmp_path / ("t%d.fna" % it)
+        path.write_bytes(text)
+        for threshold, overlap in [(0, 0), (500, 30), (64, 5)]:
+            a = _fasta_view(ref.fasta_records(text, str(path), threshold=threshold, overlap=overlap))
+            b = _fasta_view(oracle.fasta_records(text, threshold=threshold, overlap=overlap))
+            assert a == b
+    for length, max_len in [(1, 10), (10, 10), (11, 10), (1000, 7), (500000, 500000), (500001, 500000), (5062500, 500000)]:
+        assert ref.seq_len_increment(length, max_len) == oracle.seq_len_increment(length, max_len)

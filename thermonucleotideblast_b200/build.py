@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtntb200.so")
 
 SOURCES = ["engine.cu", "assemble.cpp", "thermo.cpp"]
-HEADERS = ["kernels.cuh", "align_core.cuh", "tnt_types.h", "thermo.h", "assemble.h",
+HEADERS = ["kernels.cuh", "fasta.cuh", "align_core.cuh", "tnt_types.h", "thermo.h", "assemble.h",
            "santalucia_tables.inc", os.path.join("..", "..", "include", "tntb200.h")]
 
 NVCC_FLAGS = [

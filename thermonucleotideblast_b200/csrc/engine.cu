@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -27,6 +28,7 @@
 #include "../../include/tntb200.h"
 #include "assemble.h"
 #include "kernels.cuh"
+#include "fasta.cuh"
 #include "thermo.h"
 
 using namespace tnt;
@@ -204,6 +206,23 @@ struct tnt_engine {
 
 	std::vector<AssayHost> assays;
 
+	// FASTA ingest (tnt_engine_add_fasta): text slabs in flight, the codes of the text (1 B/base,
+	// transient: the source of the fragment copies), parse state, record table
+	static constexpr int FA_BUFS = 3;
+	cudaStream_t fa_copy_stream = nullptr;
+	uint8_t *fa_text[FA_BUFS] = {nullptr, nullptr, nullptr};
+	cudaEvent_t fa_copied[FA_BUFS]{}, fa_parsed[FA_BUFS]{};
+	cudaEvent_t fa_scanned = nullptr;
+	DevBuf<uint8_t> fa_codes;
+	DevBuf<FaTables> fa_tables;
+	DevBuf<uint4> fa_block_map;
+	DevBuf<FaCarry> fa_block_entry;
+	DevBuf<FaCarry> fa_carry;
+	FaCarry *h_fa_carry = nullptr; // pinned
+	DevBuf<uint64_t> fa_rec_pos, fa_rec_base;
+	std::vector<tnt_fasta_record> fa_records;
+	std::vector<tnt_fasta_fragment> fa_fragments;
+
 	// scratch of the search
 	DevBuf<Candidate> d_cand;
 	DevBuf<uint32_t> d_cand_count;
@@ -261,6 +280,14 @@ struct tnt_engine {
 			if (b.count_ev) cudaEventDestroy(b.count_ev);
 			if (b.packed_ev) cudaEventDestroy(b.packed_ev);
 		}
+		if (fa_copy_stream) { cudaStreamSynchronize(fa_copy_stream); cudaStreamDestroy(fa_copy_stream); }
+		for (int i = 0; i < FA_BUFS; ++i) {
+			if (fa_text[i]) cudaFree(fa_text[i]);
+			if (fa_copied[i]) cudaEventDestroy(fa_copied[i]);
+			if (fa_parsed[i]) cudaEventDestroy(fa_parsed[i]);
+		}
+		if (fa_scanned) cudaEventDestroy(fa_scanned);
+		if (h_fa_carry) cudaFreeHost(h_fa_carry);
 		if (emit_done) cudaEventDestroy(emit_done);
 		if (pads_ev) cudaEventDestroy(pads_ev);
 		if (emit_stream) cudaStreamDestroy(emit_stream);
@@ -418,11 +445,12 @@ void open_batch(tnt_engine *e, uint64_t base)
 	e->batch_used = 0;
 }
 
+// page-locked host memory or device memory: the copy engine reads the source itself
 bool is_pinned(const void *p)
 {
 	cudaPointerAttributes at;
 	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-	return at.type == cudaMemoryTypeHost;
+	return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice;
 }
 
 void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_out)
@@ -471,6 +499,189 @@ void add_target(tnt_engine *e, const uint8_t *codes, uint32_t len, uint32_t *id_
 	e->targets_dirty = true;
 	e->upload_settled = false;
 	if (id_out) *id_out = (uint32_t)e->targets.size() - 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// FASTA ingest (fasta.cuh).  The text crosses PCIe in 64 MB slabs on its own copy stream (three
+// slab buffers); every slab is parsed on the upload stream: k_fa_summary, k_fa_scan, [record
+// count to the host], k_fa_emit.  Records whose end is known are cut like the reference driver
+// cuts them and their pieces registered straight from the device-resident codes (device ->
+// staging copies, then the ordinary k_pack path), so packing overlaps the transfer of the
+// following slabs.
+// ------------------------------------------------------------------------------------------
+void build_fasta_tables(FaTables &t)
+{
+	for (int c = 0; c < 256; ++c) {
+		const bool lf = c == '\n', cr = c == '\r', gt = c == '>';
+		const bool blank = c == ' ' || c == '\t' || c == '\v' || c == '\f';
+		const bool skip = c == '*' || c == '-';
+		// sequence_data_fastx.cpp:369: !isspace && != '*' && != '-' && != '\r'
+		const bool base = !(lf || cr || blank || skip);
+		t.lut[FS_SEQ][c] = gt ? (FS_LEAD | FA_REC_ONE) : (FS_SEQ | (base ? FA_BASE_ONE : 0u));
+		t.lut[FS_LEAD][c] = blank ? FS_LEAD : lf ? (FS_SEQ | FA_ERR) : cr ? (FS_SAMELINE | FA_ERR) : FS_DEFLINE;
+		t.lut[FS_DEFLINE][c] = lf ? FS_SEQ : cr ? FS_SAMELINE : FS_DEFLINE;
+		t.lut[FS_SAMELINE][c] = lf ? FS_SEQ : (FS_SAMELINE | (base ? FA_BASE_ONE : 0u));
+		// ascii_to_hash_base (seq.h:148-189)
+		int code = 17;
+		switch (std::toupper(c)) {
+			case 'A': code = 0; break;  case 'C': code = 1; break;  case 'G': code = 2; break;
+			case 'T': case 'U': code = 3; break;
+			case 'I': code = 4; break;  case 'M': code = 5; break;  case 'R': code = 6; break;
+			case 'S': code = 7; break;  case 'V': code = 8; break;  case 'W': code = 9; break;
+			case 'Y': code = 10; break; case 'H': code = 11; break; case 'K': code = 12; break;
+			case 'D': code = 13; break; case 'B': code = 14; break; case 'N': code = 15; break;
+			case '-': code = 16; break;
+			default: break;
+		}
+		t.code[c] = (uint8_t)code;
+	}
+}
+
+// seq_len_increment(...).first (sequence_data.cpp:739-754)
+uint32_t fragment_delta(uint32_t len, uint32_t max_len)
+{
+	if (max_len == 0 || len <= max_len) return len - 1;
+	uint64_t n = 2;
+	while ((uint64_t)len > n*max_len) ++n;
+	return (uint32_t)(len/n + ((len % n) ? 1 : 0));
+}
+
+// Cut one record like the driver's work queue (tntblast_local.cpp:282-289,448-468) and register
+// the pieces from the device-resident codes.
+void register_fasta_record(tnt_engine *e, const char *text, uint64_t pos, uint64_t end, uint64_t base0, uint64_t base1,
+	uint32_t threshold, uint32_t overlap)
+{
+	if (end - pos >= (1ull << 32)) throw std::runtime_error("tnt_engine_add_fasta: a record of 4 GB or more (the reference keeps record sizes in 32 bits)");
+	tnt_fasta_record r{};
+	r.text_offset = pos;
+	r.text_bytes = end - pos;
+	r.bases = base1 - base0;
+	uint64_t p = pos + 1;
+	while (p < end && std::isspace((unsigned char)text[p])) ++p;
+	r.defline_offset = p;
+	while (p < end && text[p] != '\n' && text[p] != '\r') ++p;
+	r.defline_len = (uint32_t)(p - r.defline_offset);
+	r.first_fragment = (uint32_t)e->fa_fragments.size();
+	const uint32_t len = (uint32_t)r.text_bytes, max_stop = len - 1;
+	const uint32_t delta = fragment_delta(len, threshold);
+	uint32_t start = 0, stop = delta;
+	while (true) {
+		tnt_fasta_fragment f{};
+		f.record = (uint32_t)e->fa_records.size();
+		f.start = start;
+		f.stop = stop;
+		f.max_stop = max_stop;
+		f.target_id = 0xffffffffu;
+		if (start < r.bases) {
+			const uint64_t last = std::min<uint64_t>((uint64_t)stop + overlap, r.bases - 1);
+			f.len = (uint32_t)(last - start + 1);
+			add_target(e, e->fa_codes.p + base0 + start, f.len, &f.target_id);
+		}
+		e->fa_fragments.push_back(f);
+		++r.n_fragments;
+		if (stop == max_stop) break;
+		start = stop + 1;
+		stop = (uint32_t)std::min<uint64_t>((uint64_t)stop + delta, max_stop);
+	}
+	e->fa_records.push_back(r);
+}
+
+void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshold, uint32_t overlap)
+{
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->fa_records.clear();
+	e->fa_fragments.clear();
+	const char *gt = nbytes ? (const char *)std::memchr(text, '>', nbytes) : nullptr;
+	if (!gt) return;
+	const size_t first = (size_t)(gt - text), n = nbytes - first;
+	const uint8_t *src = (const uint8_t *)text + first;
+
+	if (!e->fa_copy_stream) {
+		CUDA_OK(cudaStreamCreateWithFlags(&e->fa_copy_stream, cudaStreamNonBlocking));
+		for (int i = 0; i < tnt_engine::FA_BUFS; ++i) {
+			CUDA_OK(cudaEventCreateWithFlags(&e->fa_copied[i], cudaEventDisableTiming));
+			CUDA_OK(cudaEventCreateWithFlags(&e->fa_parsed[i], cudaEventDisableTiming));
+		}
+		CUDA_OK(cudaEventCreateWithFlags(&e->fa_scanned, cudaEventDisableTiming));
+		CUDA_OK(cudaMallocHost(&e->h_fa_carry, sizeof(FaCarry)));
+		std::unique_ptr<FaTables> t(new FaTables);
+		build_fasta_tables(*t);
+		e->fa_tables.reserve(1, 0, e->up_stream);
+		CUDA_OK(cudaMemcpyAsync(e->fa_tables.p, t.get(), sizeof(FaTables), cudaMemcpyHostToDevice, e->up_stream));
+		CUDA_OK(cudaStreamSynchronize(e->up_stream));
+		e->fa_carry.reserve(1, 0, e->up_stream);
+	}
+	const size_t nslabs = (n + FA_SLAB_BYTES - 1)/FA_SLAB_BYTES;
+	for (int i = 0; i < tnt_engine::FA_BUFS && (size_t)i < nslabs; ++i)
+		if (!e->fa_text[i]) CUDA_OK(cudaMalloc(&e->fa_text[i], FA_SLAB_BYTES));
+	// earlier fragment copies may still read the old codes: reserve() waits for the stream before it frees
+	e->fa_codes.reserve(n + 16, 0, e->up_stream);
+	const uint32_t max_blocks = (uint32_t)((std::min(n, FA_SLAB_BYTES) + FA_BLOCK_BYTES - 1)/FA_BLOCK_BYTES);
+	e->fa_block_map.reserve(max_blocks, 0, e->up_stream);
+	e->fa_block_entry.reserve(max_blocks, 0, e->up_stream);
+	*e->h_fa_carry = FaCarry{0, 0, FS_SEQ, 0};
+	CUDA_OK(cudaMemcpyAsync(e->fa_carry.p, e->h_fa_carry, sizeof(FaCarry), cudaMemcpyHostToDevice, e->up_stream));
+	CUDA_OK(cudaStreamSynchronize(e->up_stream)); // the pinned carry is reused as the download target
+
+	auto slab_bytes = [&](size_t k) { return std::min(FA_SLAB_BYTES, n - k*FA_SLAB_BYTES); };
+	auto enqueue_copy = [&](size_t k) {
+		const int b = (int)(k % tnt_engine::FA_BUFS);
+		if (k >= (size_t)tnt_engine::FA_BUFS) CUDA_OK(cudaStreamWaitEvent(e->fa_copy_stream, e->fa_parsed[b], 0));
+		CUDA_OK(cudaMemcpyAsync(e->fa_text[b], src + k*FA_SLAB_BYTES, slab_bytes(k), cudaMemcpyHostToDevice, e->fa_copy_stream));
+		CUDA_OK(cudaEventRecord(e->fa_copied[b], e->fa_copy_stream));
+	};
+
+	std::vector<uint64_t> rpos, rbase; // record table on the host, grows slab by slab
+	size_t registered = 0;             // records already cut and registered
+	auto register_known = [&](uint64_t end_pos, uint64_t end_base, bool final_record) {
+		// a record ends where the next one starts; the last one at the end of the text
+		while (registered + 1 < rpos.size() || (final_record && registered < rpos.size())) {
+			const bool last = registered + 1 == rpos.size();
+			register_fasta_record(e, text, rpos[registered], last ? end_pos : rpos[registered + 1],
+				rbase[registered], last ? end_base : rbase[registered + 1], threshold, overlap);
+			++registered;
+		}
+	};
+
+	size_t copies = 0;
+	for (; copies < nslabs && copies < 2; ++copies) enqueue_copy(copies);
+	for (size_t k = 0; k < nslabs; ++k) {
+		const int b = (int)(k % tnt_engine::FA_BUFS);
+		const uint32_t m = (uint32_t)slab_bytes(k);
+		const uint32_t nblocks = (m + FA_BLOCK_BYTES - 1)/FA_BLOCK_BYTES;
+		CUDA_OK(cudaStreamWaitEvent(e->up_stream, e->fa_copied[b], 0));
+		k_fa_summary<<<nblocks, FA_THREADS, 0, e->up_stream>>>(e->fa_text[b], m, e->fa_tables.p, e->fa_block_map.p);
+		k_fa_scan<<<1, FA_SCAN_THREADS, 0, e->up_stream>>>(e->fa_block_map.p, nblocks, e->fa_carry.p, e->fa_block_entry.p);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaMemcpyAsync(e->h_fa_carry, e->fa_carry.p, sizeof(FaCarry), cudaMemcpyDeviceToHost, e->up_stream));
+		CUDA_OK(cudaEventRecord(e->fa_scanned, e->up_stream));
+		CUDA_OK(cudaEventSynchronize(e->fa_scanned));
+		const FaCarry after = *e->h_fa_carry;
+		const size_t had = rpos.size();
+		if (after.recs > had) {
+			e->fa_rec_pos.reserve(after.recs, had, e->up_stream);
+			e->fa_rec_base.reserve(after.recs, had, e->up_stream);
+		}
+		k_fa_emit<<<nblocks, FA_THREADS, 0, e->up_stream>>>(e->fa_text[b], m, (uint64_t)first + k*FA_SLAB_BYTES, e->fa_tables.p,
+			e->fa_block_entry.p, e->fa_codes.p, e->fa_rec_pos.p, e->fa_rec_base.p);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaEventRecord(e->fa_parsed[b], e->up_stream));
+		e->upload_launches += 3;
+		if (copies < nslabs) enqueue_copy(copies++);
+		if (after.recs > had) {
+			rpos.resize(after.recs);
+			rbase.resize(after.recs);
+			CUDA_OK(cudaMemcpyAsync(rpos.data() + had, e->fa_rec_pos.p + had, (after.recs - had)*sizeof(uint64_t), cudaMemcpyDeviceToHost, e->up_stream));
+			CUDA_OK(cudaMemcpyAsync(rbase.data() + had, e->fa_rec_base.p + had, (after.recs - had)*sizeof(uint64_t), cudaMemcpyDeviceToHost, e->up_stream));
+			CUDA_OK(cudaStreamSynchronize(e->up_stream));
+		}
+		const bool final_slab = k + 1 == nslabs;
+		if (final_slab) {
+			if (after.err) throw std::runtime_error("tnt_engine_add_fasta: empty defline (the reference reader takes the next line for the defline or throws \"Truncated fasta file detected!\")");
+			if (after.state == FS_DEFLINE || after.state == FS_LEAD) throw std::runtime_error("Truncated fasta file detected!");
+		}
+		register_known((uint64_t)nbytes, after.bases, final_slab);
+	}
 }
 
 } // namespace
@@ -1623,6 +1834,37 @@ int tnt_engine_add_targets(tnt_engine *e, const uint8_t *const *codes, const uin
 	API_END
 }
 
+int tnt_engine_add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t fragment_threshold, uint32_t overlap,
+	const tnt_fasta_record **records, size_t *n_records, const tnt_fasta_fragment **fragments, size_t *n_fragments)
+{
+	API_BEGIN
+	if (!e || (!text && nbytes)) throw std::runtime_error("null argument");
+	add_fasta(e, text, nbytes, fragment_threshold, overlap);
+	if (records) *records = e->fa_records.data();
+	if (n_records) *n_records = e->fa_records.size();
+	if (fragments) *fragments = e->fa_fragments.data();
+	if (n_fragments) *n_fragments = e->fa_fragments.size();
+	API_END
+}
+
+int tnt_engine_target_codes(tnt_engine *e, uint32_t target_id, uint32_t start, uint32_t n, uint8_t *out)
+{
+	API_BEGIN
+	if (!e || (!out && n)) throw std::runtime_error("null argument");
+	if (target_id >= e->targets.size()) throw std::runtime_error("bad target id");
+	if ((uint64_t)start + n > e->targets[target_id].len) throw std::runtime_error("range outside the fragment");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->sync_targets();
+	if (n) {
+		e->d_extract.reserve(n, 0, e->stream);
+		k_extract_codes<<<std::min<uint32_t>((n + 255)/256, 1024u), 256, 0, e->stream>>>(e->view(), target_id, start, n, e->d_extract.p);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaMemcpyAsync(out, e->d_extract.p, n, cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+	}
+	API_END
+}
+
 int tnt_engine_clear_targets(tnt_engine *e)
 {
 	API_BEGIN
@@ -1631,6 +1873,9 @@ int tnt_engine_clear_targets(tnt_engine *e)
 	CUDA_OK(cudaStreamSynchronize(e->up_stream));
 	CUDA_OK(cudaStreamSynchronize(e->emit_stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
+	if (e->fa_copy_stream) CUDA_OK(cudaStreamSynchronize(e->fa_copy_stream));
+	e->fa_records.clear();
+	e->fa_fragments.clear();
 	e->targets.clear();
 	e->tiles.clear();
 	e->next_base = 0;

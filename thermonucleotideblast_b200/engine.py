@@ -106,6 +106,19 @@ class AlignResult(C.Structure):
                 ("alignment", C.c_char * 512)]
 
 
+class FastaRecord(C.Structure):
+    """tnt_fasta_record (include/tntb200.h)."""
+    _fields_ = [("text_offset", C.c_uint64), ("text_bytes", C.c_uint64), ("defline_offset", C.c_uint64),
+                ("defline_len", C.c_uint32), ("n_fragments", C.c_uint32), ("bases", C.c_uint64),
+                ("first_fragment", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class FastaFragment(C.Structure):
+    """tnt_fasta_fragment (include/tntb200.h)."""
+    _fields_ = [("record", C.c_uint32), ("start", C.c_uint32), ("stop", C.c_uint32), ("max_stop", C.c_uint32),
+                ("len", C.c_uint32), ("target_id", C.c_uint32)]
+
+
 @dataclass
 class Assay:
     id: int
@@ -152,6 +165,10 @@ def load_library() -> C.CDLL:
     L.tnt_engine_add_target.argtypes = [vp, u8p, C.c_uint32, u32p]
     L.tnt_engine_add_targets.argtypes = [vp, C.POINTER(C.c_void_p), u32p, C.c_uint32, u32p]
     L.tnt_engine_clear_targets.argtypes = [vp]
+    L.tnt_engine_add_fasta.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                       C.POINTER(C.POINTER(FastaRecord)), C.POINTER(C.c_size_t),
+                                       C.POINTER(C.POINTER(FastaFragment)), C.POINTER(C.c_size_t)]
+    L.tnt_engine_target_codes.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, u8p]
     L.tnt_engine_set_assays.argtypes = [vp, C.POINTER(CAssay), C.c_int32]
     L.tnt_engine_search.argtypes = [vp, C.POINTER(SearchOptions)]
     L.tnt_engine_get_hits.argtypes = [vp, C.POINTER(C.POINTER(CHit)), C.POINTER(C.c_size_t),
@@ -234,6 +251,32 @@ class Engine:
         first = C.c_uint32()
         self._check(self.L.tnt_engine_add_targets(self.h, fl.ptrs, fl.lens, fl.n, C.byref(first)))
         return first.value
+
+    def add_fasta(self, text, fragment_threshold: int = 500000, overlap: int = 2002, address: int = 0, nbytes: int = 0):
+        """Register the records of a FASTA text (bytes / uint8 array, or a raw `address` + `nbytes` of
+        e.g. a page-locked buffer): parsed, cut into fragments and packed on the device
+        (tnt_engine_add_fasta).  Returns (records, fragments) as lists of ctypes structs."""
+        if address:
+            ptr, n = C.c_void_p(address), nbytes
+        elif isinstance(text, (bytes, bytearray)):
+            keep = np.frombuffer(text, dtype=np.uint8)
+            ptr, n = C.c_void_p(keep.ctypes.data if keep.size else 0), keep.size
+        else:
+            keep = np.ascontiguousarray(text, dtype=np.uint8)
+            ptr, n = C.c_void_p(keep.ctypes.data if keep.size else 0), keep.size
+        pr, pf = C.POINTER(FastaRecord)(), C.POINTER(FastaFragment)()
+        nr, nf = C.c_size_t(), C.c_size_t()
+        self._check(self.L.tnt_engine_add_fasta(self.h, ptr, n, fragment_threshold, overlap,
+                                                C.byref(pr), C.byref(nr), C.byref(pf), C.byref(nf)))
+        recs = [FastaRecord.from_buffer_copy(pr[i]) for i in range(nr.value)]
+        frags = [FastaFragment.from_buffer_copy(pf[i]) for i in range(nf.value)]
+        return recs, frags
+
+    def target_codes(self, target_id: int, start: int, n: int) -> np.ndarray:
+        """seq.h codes of a range of a registered fragment, read back from the packed database."""
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self.L.tnt_engine_target_codes(self.h, target_id, start, n, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out[:n]
 
     def clear_targets(self):
         self._check(self.L.tnt_engine_clear_targets(self.h))
