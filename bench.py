@@ -271,6 +271,101 @@ def cpu_baseline(records, assays, seconds_target: float = 15.0):
                       % (used / 1e6, len(assays), cores, dt)}
 
 
+def fasta_text_pinned(records):
+    """The records as one 80-column FASTA text in page-locked host memory (uint8 view, nbytes)."""
+    import torch
+    lut = np.frombuffer(b"ACGTIMRSVWYHKDBN-N", dtype=np.uint8)
+    heads = [b">rec%d synthetic\n" % i for i in range(len(records))]
+    total = sum(len(h) + len(r) + (len(r) + 79) // 80 for h, r in zip(heads, records))
+    buf = torch.empty(total, dtype=torch.uint8, pin_memory=True).numpy()
+    pos = 0
+    for h, rec in zip(heads, records):
+        buf[pos:pos + len(h)] = np.frombuffer(h, dtype=np.uint8)
+        pos += len(h)
+        n = len(rec)
+        txt = lut[rec]
+        full = (n // 80) * 80
+        if full:
+            body = buf[pos:pos + full // 80 * 81].reshape(-1, 81)
+            body[:, :80] = txt[:full].reshape(-1, 80)
+            body[:, 80] = 10
+            pos += full // 80 * 81
+        if n > full:
+            buf[pos:pos + n - full] = txt[full:]
+            buf[pos + n - full] = 10
+            pos += n - full + 1
+    assert pos == total
+    return buf, total
+
+
+def fasta_leg(eng, records, opts, units, want_hits, max_over_ranks, barrier, steps):
+    text, nbytes = fasta_text_pinned(records)
+    addr = int(text.ctypes.data)
+
+    def step():
+        eng.clear_targets()
+        eng.add_fasta_raw(addr, nbytes, FRAGMENT_BP, OVERLAP)
+        n = eng.search_raw(opts)
+        eng.hit_records()
+        return n
+
+    nh = step()
+    barrier()
+    t0 = time.perf_counter()
+    parse_ms = call_ms = 0.0
+    for _ in range(steps):
+        nh = step()
+        ist = eng.ingest_stats()
+        parse_ms += ist.parse_ms
+        call_ms += ist.call_ms
+    barrier()
+    dt = max_over_ranks((time.perf_counter() - t0) / steps)
+    ist = eng.ingest_stats()
+    algo = float(ist.text_bytes + ist.bases)
+    return {"value": units / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": steps,
+            "h2d_bytes_per_step": int(nbytes), "text": "80-column FASTA, %d records, page-locked host memory" % len(records),
+            "records": int(ist.records), "fragments": int(ist.fragments), "bases": int(ist.bases),
+            "hits_equal_fragment_upload": bool(nh == want_hits),
+            "add_fasta_call_ms": call_ms / steps, "parser_kernel_ms": parse_ms / steps,
+            "parser_launches": int(ist.launches),
+            "parse_GBps": algo / (parse_ms / steps / 1e3) / 1e9 if parse_ms else None,
+            "parse_algorithmic_bytes": "text read once + 1 B per base written (the parser reads the text twice: summary pass + emission pass)"}
+
+
+def packed_leg(eng, frag_list, opts, units, want_hits, max_over_ranks, barrier, steps):
+    import torch
+    eng.clear_targets()
+    eng.add_targets(frag_list)
+    snap = eng.export_packed()
+    pinned = {}
+    for k, v in snap.items():
+        if k == "info" or v.size == 0:
+            pinned[k] = v
+            continue
+        t = torch.empty(v.nbytes, dtype=torch.uint8, pin_memory=True).numpy().view(v.dtype)
+        t[:] = v
+        pinned[k] = t
+    nbytes = int(sum(v.nbytes for k, v in pinned.items() if k != "info"))
+
+    def step():
+        eng.clear_targets()
+        eng.import_packed(pinned)
+        n = eng.search_raw(opts)
+        eng.hit_records()
+        return n
+
+    nh = step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nh = step()
+    barrier()
+    dt = max_over_ranks((time.perf_counter() - t0) / steps)
+    return {"value": units / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": steps, "h2d_bytes_per_step": nbytes,
+            "hits_equal_fragment_upload": bool(nh == want_hits),
+            "what": "tnt_engine_import_packed (2 bit/base + mask + non-ACGT list + fragment table, page-locked host memory) + search + hit read-back"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -280,6 +375,7 @@ def main():
     ap.add_argument("--mbp", type=int, default=1000, help="database size per GPU in Mbp")
     ap.add_argument("--assays", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fasta", action="store_true", help="skip the FASTA-text ingest leg")
     ap.add_argument("--kind", default="taqman", choices=["taqman", "pcr", "probe", "padlock"],
                     help="assay type (default: BASELINE configs[1]; probe / padlock: the flavours of configs[2] / configs[3])")
     args = ap.parse_args()
@@ -429,6 +525,24 @@ def main():
     e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     e2e_value = units / e2e_dt
 
+    # ---- FASTA text -> hits (SURVEY 8f ingest row): the same database as 80-column FASTA text in
+    #      page-locked host memory, parsed / cut / packed on the device (tnt_engine_add_fasta)
+    ingest = None
+    if not args.no_fasta:
+        try:
+            ingest = fasta_leg(eng, records, opts, units, n_e2e_hits, max_over_ranks, barrier, e2e_steps)
+        except Exception as ex:
+            ingest = {"error": str(ex)}
+
+    # ---- packed snapshot -> hits: the resident 2-bit database exported once, re-imported from
+    #      page-locked host memory every step (0.375 B/base over PCIe instead of 1 B/base)
+    packed = None
+    if not args.no_fasta:
+        try:
+            packed = packed_leg(eng, frag_list, opts, units, n_e2e_hits, max_over_ranks, barrier, e2e_steps)
+        except Exception as ex:
+            packed = {"error": str(ex)}
+
     # ---- seed scan alone with a single assay (the HBM-bound case of SURVEY 8d) -------------------
     scan1 = None
     try:
@@ -488,6 +602,12 @@ def main():
                                        "strands the scan is bound by table walks and bucket atomics, not HBM" % (2 * len(assays)),
                                "single_assay": scan1},
     }
+    if packed is not None:
+        line["e2e_packed_snapshot"] = packed
+    if ingest is not None:
+        if "parse_GBps" in ingest:
+            ingest["parse_frac_of_hbm_peak"] = ingest["parse_GBps"] / hbm_peak if hbm_peak else None
+        line["ingest_fasta"] = ingest
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.kind in ("taqman", "pcr"):
             line["cpu_baseline"] = cpu_baseline(records, assays)

@@ -185,6 +185,49 @@ typedef struct {
 int tnt_engine_add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t fragment_threshold, uint32_t overlap,
 	const tnt_fasta_record **records, size_t *n_records, const tnt_fasta_fragment **fragments, size_t *n_fragments);
 
+/* Counters of the last tnt_engine_add_fasta call.  parse_ms = device time of the parser kernels
+ * (k_fa_summary + k_fa_scan + k_fa_emit, CUDA events on the upload stream, summed over slabs);
+ * call_ms = host wall clock of the call (text transfer included, fragment packing enqueued). */
+typedef struct {
+	uint64_t text_bytes, bases, records, fragments;
+	uint64_t slabs, launches;
+	double parse_ms, call_ms;
+} tnt_ingest_stats;
+int tnt_engine_get_ingest_stats(tnt_engine *e, tnt_ingest_stats *out);
+
+/* ---- Packed database snapshot (persistent packed-DB cache) ----
+ * The resident form of the registered fragments -- 2 bit/base words, 1 bit/base non-ACGT mask,
+ * sparse list of the non-ACGT codes, fragment table -- copied out to caller memory and back in,
+ * so that a database parsed once (tnt_engine_add_target[s] / tnt_engine_add_fasta) can be kept
+ * on disk at 0.375 B/base and re-loaded without reading, parsing or packing sequence text: the
+ * counterpart of DNAHash::hash (seq_hash.h:524-642) being re-run for every fragment of every run.
+ * Export with NULL buffers fills `info` only (sizes to allocate).  Import needs an engine without
+ * fragments (tnt_engine_clear_targets) and registers the fragments under the same ids; buffers
+ * that are page-locked are read by DMA after the call returns (same rule as
+ * tnt_engine_add_targets). */
+typedef struct {
+	uint64_t base;             /* global base index of position 0 (multiple of 64) */
+	uint32_t len;
+	uint32_t pad;
+	uint64_t exc_begin, exc_end;
+} tnt_packed_target;
+
+typedef struct {
+	uint32_t format;           /* TNTB200_PACKED_FORMAT */
+	uint32_t word_size;        /* informational: the engine's seed word size */
+	uint64_t n_targets;        /* tnt_packed_target records */
+	uint64_t n_words;          /* uint64 words of db2 == uint32 words of nmask (32 bases each) */
+	uint64_t n_exceptions;     /* entries of exc_pos / exc_code */
+	uint64_t next_base;        /* first free global base index */
+	uint64_t total_bases;
+} tnt_packed_info;
+#define TNTB200_PACKED_FORMAT 1u
+
+int tnt_engine_export_packed(tnt_engine *e, tnt_packed_info *info, tnt_packed_target *targets, uint64_t *db2,
+	uint32_t *nmask, uint64_t *exc_pos, uint8_t *exc_code);
+int tnt_engine_import_packed(tnt_engine *e, const tnt_packed_info *info, const tnt_packed_target *targets,
+	const uint64_t *db2, const uint32_t *nmask, const uint64_t *exc_pos, const uint8_t *exc_code);
+
 /* seq.h codes of bases [start, start+n) of a registered fragment, read back from the packed
  * database (parity tests of the ingest path). */
 int tnt_engine_target_codes(tnt_engine *e, uint32_t target_id, uint32_t start, uint32_t n, uint8_t *out);

@@ -154,3 +154,54 @@ def test_search_on_ingested_fasta_equals_fragment_upload(engine_lib, oracle):
         e.add_targets(pieces)
         want = keys(e, e.search(to_opts(o)))
     assert got == want and len(got) >= 5
+
+
+def test_packed_snapshot_round_trip(engine_lib, oracle, tmp_path):
+    """Export of the resident packed database, a trip through a file, import into a fresh engine:
+    identical fragments (codes read back), identical hits; damaged snapshots are refused."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    from thermonucleotideblast_b200.engine import EngineError
+    rng = np.random.default_rng(808)
+    db = [gen.random_codes(int(rng.integers(20000, 70000)), rng) for _ in range(7)]
+    gen.sprinkle_degenerate(db[2], rng, frac=3e-3, n_runs_per_50kb=8)
+    gen.sprinkle_degenerate(db[5], rng, frac=1e-3, n_runs_per_50kb=2)
+    db.append(gen.random_codes(5, rng))      # shorter than a seed word
+    assays = gen.make_assays(rng, db[:7], 5, "taqman", variants=2)
+    o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+
+    def keys(e, hits):
+        return [(h.target_id, h.assay_index) + hit_key(e, h, assays[h.assay_index]) + hit_floats(h) for h in hits]
+
+    with Engine() as e:
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        e.add_targets(db)
+        want = keys(e, e.search(to_opts(o)))
+        snap = e.export_packed()
+    assert len(want) >= 5
+    assert int(snap["info"][2]) == len(db) and int(snap["info"][6]) == sum(len(c) for c in db)
+    # 0.375 B/base (+ alignment gaps of < 64 bases per fragment) + the sparse non-ACGT list
+    assert snap["db2"].nbytes + snap["nmask"].nbytes <= 0.375 * (sum(len(c) for c in db) + 64 * len(db)) + 64
+    path = tmp_path / "db.tntpacked.npz"
+    np.savez(path, **snap)
+    loaded = dict(np.load(path))
+    with Engine() as e:
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        e.import_packed(loaded)
+        for t, c in enumerate(db):
+            assert e.target_codes(t, 0, len(c)).tolist() == c.tolist()
+        assert keys(e, e.search(to_opts(o))) == want
+        # fragments registered after an import join the set like after any other upload
+        extra = db[0].copy()
+        assert e.add_target(extra) == len(db)
+        more = keys(e, e.search(to_opts(o)))
+        assert [k for k in more if k[0] < len(db)] == want
+        assert [k[1:] for k in more if k[0] == len(db)] == [k[1:] for k in want if k[0] == 0]
+        with pytest.raises(EngineError):
+            e.import_packed(loaded)              # engine not empty
+        e.clear_targets()
+        bad = dict(loaded)
+        bad["db2"] = loaded["db2"][:-4]
+        bad["info"] = loaded["info"].copy()
+        bad["info"][3] -= 4                      # fewer words than the fragment table needs
+        with pytest.raises(EngineError):
+            e.import_packed(bad)

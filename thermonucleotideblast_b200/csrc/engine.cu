@@ -222,6 +222,9 @@ struct tnt_engine {
 	DevBuf<uint64_t> fa_rec_pos, fa_rec_base;
 	std::vector<tnt_fasta_record> fa_records;
 	std::vector<tnt_fasta_fragment> fa_fragments;
+	std::vector<cudaEvent_t> fa_ev;   // four per slab: [summary .. scan], [emit]
+	size_t fa_ev_used = 0;
+	tnt_ingest_stats fa_stats{};
 
 	// scratch of the search
 	DevBuf<Candidate> d_cand;
@@ -287,6 +290,7 @@ struct tnt_engine {
 			if (fa_parsed[i]) cudaEventDestroy(fa_parsed[i]);
 		}
 		if (fa_scanned) cudaEventDestroy(fa_scanned);
+		for (cudaEvent_t ev : fa_ev) cudaEventDestroy(ev);
 		if (h_fa_carry) cudaFreeHost(h_fa_carry);
 		if (emit_done) cudaEventDestroy(emit_done);
 		if (pads_ev) cudaEventDestroy(pads_ev);
@@ -589,8 +593,12 @@ void register_fasta_record(tnt_engine *e, const char *text, uint64_t pos, uint64
 void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshold, uint32_t overlap)
 {
 	CUDA_OK(cudaSetDevice(e->prm.device));
+	const auto wall0 = std::chrono::steady_clock::now();
 	e->fa_records.clear();
 	e->fa_fragments.clear();
+	e->fa_ev_used = 0;
+	e->fa_stats = tnt_ingest_stats{};
+	e->fa_stats.text_bytes = nbytes;
 	const char *gt = nbytes ? (const char *)std::memchr(text, '>', nbytes) : nullptr;
 	if (!gt) return;
 	const size_t first = (size_t)(gt - text), n = nbytes - first;
@@ -643,6 +651,13 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 		}
 	};
 
+	auto mark = [&]() {
+		if (e->fa_ev_used == e->fa_ev.size()) {
+			e->fa_ev.emplace_back();
+			CUDA_OK(cudaEventCreate(&e->fa_ev.back()));
+		}
+		CUDA_OK(cudaEventRecord(e->fa_ev[e->fa_ev_used++], e->up_stream));
+	};
 	size_t copies = 0;
 	for (; copies < nslabs && copies < 2; ++copies) enqueue_copy(copies);
 	for (size_t k = 0; k < nslabs; ++k) {
@@ -650,9 +665,11 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 		const uint32_t m = (uint32_t)slab_bytes(k);
 		const uint32_t nblocks = (m + FA_BLOCK_BYTES - 1)/FA_BLOCK_BYTES;
 		CUDA_OK(cudaStreamWaitEvent(e->up_stream, e->fa_copied[b], 0));
+		mark();
 		k_fa_summary<<<nblocks, FA_THREADS, 0, e->up_stream>>>(e->fa_text[b], m, e->fa_tables.p, e->fa_block_map.p);
 		k_fa_scan<<<1, FA_SCAN_THREADS, 0, e->up_stream>>>(e->fa_block_map.p, nblocks, e->fa_carry.p, e->fa_block_entry.p);
 		CUDA_OK(cudaGetLastError());
+		mark();
 		CUDA_OK(cudaMemcpyAsync(e->h_fa_carry, e->fa_carry.p, sizeof(FaCarry), cudaMemcpyDeviceToHost, e->up_stream));
 		CUDA_OK(cudaEventRecord(e->fa_scanned, e->up_stream));
 		CUDA_OK(cudaEventSynchronize(e->fa_scanned));
@@ -662,11 +679,15 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 			e->fa_rec_pos.reserve(after.recs, had, e->up_stream);
 			e->fa_rec_base.reserve(after.recs, had, e->up_stream);
 		}
+		mark();
 		k_fa_emit<<<nblocks, FA_THREADS, 0, e->up_stream>>>(e->fa_text[b], m, (uint64_t)first + k*FA_SLAB_BYTES, e->fa_tables.p,
 			e->fa_block_entry.p, e->fa_codes.p, e->fa_rec_pos.p, e->fa_rec_base.p);
 		CUDA_OK(cudaGetLastError());
+		mark();
 		CUDA_OK(cudaEventRecord(e->fa_parsed[b], e->up_stream));
 		e->upload_launches += 3;
+		e->fa_stats.launches += 3;
+		e->fa_stats.slabs++;
 		if (copies < nslabs) enqueue_copy(copies++);
 		if (after.recs > had) {
 			rpos.resize(after.recs);
@@ -681,7 +702,11 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 			if (after.state == FS_DEFLINE || after.state == FS_LEAD) throw std::runtime_error("Truncated fasta file detected!");
 		}
 		register_known((uint64_t)nbytes, after.bases, final_slab);
+		e->fa_stats.bases = after.bases;
 	}
+	e->fa_stats.records = e->fa_records.size();
+	e->fa_stats.fragments = e->fa_fragments.size();
+	e->fa_stats.call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 }
 
 } // namespace
@@ -1844,6 +1869,98 @@ int tnt_engine_add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_
 	if (n_records) *n_records = e->fa_records.size();
 	if (fragments) *fragments = e->fa_fragments.data();
 	if (n_fragments) *n_fragments = e->fa_fragments.size();
+	API_END
+}
+
+static_assert(sizeof(tnt_packed_target) == sizeof(Target), "tnt_packed_target mirrors tnt::Target");
+
+int tnt_engine_export_packed(tnt_engine *e, tnt_packed_info *info, tnt_packed_target *targets, uint64_t *db2,
+	uint32_t *nmask, uint64_t *exc_pos, uint8_t *exc_code)
+{
+	API_BEGIN
+	if (!e || !info) throw std::runtime_error("null argument");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->finish_upload();
+	CUDA_OK(cudaStreamSynchronize(e->up_stream));
+	CUDA_OK(cudaStreamSynchronize(e->emit_stream));
+	tnt_packed_info pi{};
+	pi.format = TNTB200_PACKED_FORMAT;
+	pi.word_size = (uint32_t)e->prm.word_size;
+	pi.n_targets = e->targets.size();
+	pi.n_words = e->packed_words;
+	pi.n_exceptions = e->nexc;
+	pi.next_base = e->next_base;
+	pi.total_bases = e->total_bases;
+	*info = pi;
+	if (targets && pi.n_targets) std::memcpy(targets, e->targets.data(), pi.n_targets*sizeof(Target));
+	if (db2 && pi.n_words) CUDA_OK(cudaMemcpyAsync(db2, e->db2.p, pi.n_words*sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+	if (nmask && pi.n_words) CUDA_OK(cudaMemcpyAsync(nmask, e->nmask.p, pi.n_words*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	if (exc_pos && pi.n_exceptions) CUDA_OK(cudaMemcpyAsync(exc_pos, e->exc_pos.p, pi.n_exceptions*sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+	if (exc_code && pi.n_exceptions) CUDA_OK(cudaMemcpyAsync(exc_code, e->exc_code.p, pi.n_exceptions, cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	API_END
+}
+
+int tnt_engine_import_packed(tnt_engine *e, const tnt_packed_info *info, const tnt_packed_target *targets,
+	const uint64_t *db2, const uint32_t *nmask, const uint64_t *exc_pos, const uint8_t *exc_code)
+{
+	API_BEGIN
+	if (!e || !info) throw std::runtime_error("null argument");
+	if (info->format != TNTB200_PACKED_FORMAT) throw std::runtime_error("tnt_engine_import_packed: unknown snapshot format");
+	if (!e->targets.empty() || e->batch_open) throw std::runtime_error("tnt_engine_import_packed: the engine already holds fragments (call tnt_engine_clear_targets first)");
+	if (info->n_targets >= (1u << 24)) throw std::runtime_error("tnt_engine_import_packed: too many fragments (limit 2^24)");
+	if ((info->n_targets && !targets) || (info->n_words && (!db2 || !nmask)) || (info->n_exceptions && (!exc_pos || !exc_code)))
+		throw std::runtime_error("null argument");
+	// consistency of the fragment table with the arrays (a damaged file must not turn into wild reads)
+	uint64_t prev_end = 0, bases = 0;
+	for (uint64_t i = 0; i < info->n_targets; ++i) {
+		const tnt_packed_target &t = targets[i];
+		if ((t.base & 63u) || t.base < prev_end || t.base + t.len > info->next_base || t.exc_begin > t.exc_end || t.exc_end > info->n_exceptions)
+			throw std::runtime_error("tnt_engine_import_packed: inconsistent fragment table");
+		prev_end = t.base + t.len;
+		bases += t.len;
+	}
+	if ((info->next_base + 31u)/32u > info->n_words || bases != info->total_bases)
+		throw std::runtime_error("tnt_engine_import_packed: inconsistent sizes");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	CUDA_OK(cudaStreamSynchronize(e->stream)); // nothing may still read arrays that reserve() replaces
+	e->db2.reserve(info->n_words + 8, 0, e->up_stream);
+	e->nmask.reserve(e->db2.cap, 0, e->up_stream);
+	if (info->n_words) {
+		CUDA_OK(cudaMemcpyAsync(e->db2.p, db2, info->n_words*sizeof(uint64_t), cudaMemcpyHostToDevice, e->up_stream));
+		CUDA_OK(cudaMemcpyAsync(e->nmask.p, nmask, info->n_words*sizeof(uint32_t), cudaMemcpyHostToDevice, e->up_stream));
+	}
+	if (info->n_exceptions) {
+		e->exc_pos.reserve(info->n_exceptions, 0, e->up_stream);
+		e->exc_code.reserve(e->exc_pos.cap, 0, e->up_stream);
+		CUDA_OK(cudaMemcpyAsync(e->exc_pos.p, exc_pos, info->n_exceptions*sizeof(uint64_t), cudaMemcpyHostToDevice, e->up_stream));
+		CUDA_OK(cudaMemcpyAsync(e->exc_code.p, exc_code, info->n_exceptions, cudaMemcpyHostToDevice, e->up_stream));
+	}
+	e->targets.resize(info->n_targets);
+	if (info->n_targets) std::memcpy(e->targets.data(), targets, info->n_targets*sizeof(Target));
+	e->packed_words = info->n_words;
+	e->next_base = info->next_base;
+	e->nexc = info->n_exceptions;
+	e->total_bases = info->total_bases;
+	e->targets_dirty = true;
+	e->upload_settled = false;
+	API_END
+}
+
+int tnt_engine_get_ingest_stats(tnt_engine *e, tnt_ingest_stats *out)
+{
+	API_BEGIN
+	if (!e || !out) throw std::runtime_error("null argument");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	double ms = 0.0;
+	for (size_t i = 0; i + 1 < e->fa_ev_used; i += 2) {
+		float t = 0.0f;
+		CUDA_OK(cudaEventSynchronize(e->fa_ev[i + 1]));
+		CUDA_OK(cudaEventElapsedTime(&t, e->fa_ev[i], e->fa_ev[i + 1]));
+		ms += t;
+	}
+	e->fa_stats.parse_ms = ms;
+	*out = e->fa_stats;
 	API_END
 }
 

@@ -32,7 +32,7 @@ constexpr uint32_t FA_BASE_ONE = 1u << 17;
 constexpr int FA_THREADS = 256;
 constexpr int FA_BYTES_PER_THREAD = 64;
 constexpr int FA_BLOCK_BYTES = FA_THREADS*FA_BYTES_PER_THREAD; // 16 KB: 14-bit record and 15-bit base counts suffice
-constexpr size_t FA_SLAB_BYTES = (size_t)256 << 20;           // text bytes parsed per pass (32-bit offsets inside a slab)
+constexpr size_t FA_SLAB_BYTES = (size_t)64 << 20;            // text bytes parsed per pass (32-bit offsets inside a slab)
 constexpr uint32_t FA_SCAN_THREADS = 1024;
 
 struct FaMap { uint32_t v[4]; };
@@ -80,6 +80,13 @@ __device__ __forceinline__ void fa_load_tables(const FaTables *__restrict__ g, u
 	if (s_code) for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_code[i] = g->code[i];
 }
 
+// All four bytes >= 0x41: letters (and bytes >= 0x80).  The line ends, '>', the blanks, '*' and
+// '-' all lie below 'A', so such a word holds four sequence characters whatever the state.
+__device__ __forceinline__ bool fa_plain_word(uint32_t x)
+{
+	return ((((x & 0x7f7f7f7fu) + 0x3f3f3f3fu) | x) & 0x80808080u) == 0x80808080u;
+}
+
 // Effect of this thread's (up to) 64 bytes for all four entry states.  `w` receives the bytes.
 __device__ __forceinline__ FaMap fa_thread_map(const uint8_t *__restrict__ text, uint32_t n, uint32_t off,
 	const uint32_t (*s_lut)[256], uint32_t w[16], uint32_t &m)
@@ -105,23 +112,45 @@ __device__ __forceinline__ FaMap fa_thread_map(const uint8_t *__restrict__ text,
 			w[k] = x;
 		}
 	}
-	if (m == FA_BYTES_PER_THREAD) {
+	// Words of four ordinary sequence characters need no table walk: +4 bases in the sequence
+	// states (even), a defline stays a defline, LEAD has met its first defline character.  Which
+	// words are ordinary differs from lane to lane, so they are found first (branch-free) and only
+	// the others are walked, one per loop iteration (an 80-column file has about one per thread).
+	uint32_t special = 0;
 #pragma unroll
-		for (int k = 0; k < 16; ++k) {
+	for (int k = 0; k < 16; ++k)
+		if (!(4u*k + 4u <= m && fa_plain_word(w[k])) && 4u*k < m) special |= 1u << k;
+	const uint32_t nwords = (m + 3u)/4u;
+	uint32_t done = 0; // words handled so far
+	while (true) {
+		const uint32_t k = special ? (uint32_t)__ffs((int)special) - 1u : nwords;
+		const uint32_t plain = k - done;
+		if (plain) {
 #pragma unroll
-			for (int s = 0; s < 4; ++s) {
-				const uint32_t c = (w[k] >> (8*s)) & 0xffu;
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t st = r.v[q] & 3u;
+				r.v[q] += (st & 1u) ? 0u : 4u*plain*FA_BASE_ONE;
+				if (st == FS_LEAD) r.v[q] ^= (FS_LEAD ^ FS_DEFLINE);
+			}
+		}
+		if (!special) break;
+		special &= special - 1u;
+		// the word again, from L1 (a dynamic index into w[] would put the array into local memory)
+		uint32_t x;
+		if (4u*k + 4u <= m) x = __ldg(reinterpret_cast<const uint32_t *>(text + off) + k);
+		else {
+			x = 0;
+			for (uint32_t s = 0; 4u*k + s < m; ++s) x |= (uint32_t)text[off + 4u*k + s] << (8u*s);
+		}
+#pragma unroll
+		for (int s = 0; s < 4; ++s) {
+			if (4u*k + s < m) {
+				const uint32_t c = (x >> (8*s)) & 0xffu;
 #pragma unroll
 				for (int q = 0; q < 4; ++q) r.v[q] = fa_step(r.v[q], s_lut[r.v[q] & 3u][c]);
 			}
 		}
-	}
-	else {
-		for (uint32_t i = 0; i < m; ++i) {
-			const uint32_t c = (w[i >> 2] >> (8*(i & 3u))) & 0xffu;
-#pragma unroll
-			for (int q = 0; q < 4; ++q) r.v[q] = fa_step(r.v[q], s_lut[r.v[q] & 3u][c]);
-		}
+		done = k + 1u;
 	}
 	return r;
 }
@@ -187,7 +216,9 @@ __global__ void __launch_bounds__(FA_SCAN_THREADS) k_fa_scan(const uint4 *__rest
 {
 	__shared__ uint64_t s_map[FA_SCAN_THREADS][4];
 	__shared__ uint64_t s_entry[FA_SCAN_THREADS];
-	const uint32_t per = (nblocks + FA_SCAN_THREADS - 1)/FA_SCAN_THREADS;
+	// at least 16 blocks per thread: the serial pass of thread 0 below is the latency of this kernel
+	const uint32_t per = max(16u, (nblocks + FA_SCAN_THREADS - 1)/FA_SCAN_THREADS);
+	const uint32_t nact = (nblocks + per - 1)/per;
 	const uint32_t b0 = threadIdx.x*per;
 	uint64_t acc[4] = {0, 1, 2, 3};
 	for (uint32_t k = 0; k < per && b0 + k < nblocks; ++k) {
@@ -202,7 +233,7 @@ __global__ void __launch_bounds__(FA_SCAN_THREADS) k_fa_scan(const uint4 *__rest
 	if (threadIdx.x == 0) {
 		// counts relative to the slab; the carry's own counts are added when the entries are written
 		uint64_t cur = (uint64_t)(carry->state & 3u) | (carry->err ? FA_ERR : 0u);
-		for (uint32_t k = 0; k < FA_SCAN_THREADS; ++k) {
+		for (uint32_t k = 0; k < nact; ++k) {
 			s_entry[k] = cur;
 			cur = fa_step64(cur, s_map[k][cur & 3u]);
 		}
@@ -255,16 +286,22 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_emit(const uint8_t *__restric
 	uint32_t st = pv & 3u;
 	uint32_t nb = pv >> 17;                    // bases of the block in front of this thread
 	uint64_t rec = en.recs + ((pv >> 3) & 0x3fffu);
-	for (uint32_t i = 0; i < m; ++i) {
-		const uint32_t c = (w[i >> 2] >> (8*(i & 3u))) & 0xffu;
-		const uint32_t e = s_lut[st][c];
-		if (e & FA_BASE_ONE) s_out[nb++] = s_code[c];
-		if (e & FA_REC_ONE) {
-			rec_pos[rec] = text_pos0 + off + i;
-			rec_base[rec] = en.bases + nb;
-			++rec;
+#pragma unroll
+	for (int k = 0; k < 16; ++k) {
+#pragma unroll
+		for (int s = 0; s < 4; ++s) {
+			if (4u*k + s < m) {
+				const uint32_t c = (w[k] >> (8*s)) & 0xffu;
+				const uint32_t e = s_lut[st][c];
+				if (e & FA_BASE_ONE) s_out[nb++] = s_code[c];
+				if (e & FA_REC_ONE) {
+					rec_pos[rec] = text_pos0 + off + 4u*k + s;
+					rec_base[rec] = en.bases + nb;
+					++rec;
+				}
+				st = e & 3u;
+			}
 		}
-		st = e & 3u;
 	}
 	__syncthreads();
 	const uint32_t block_bases = fa_pick(total, en.state) >> 17;

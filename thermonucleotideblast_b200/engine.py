@@ -113,6 +113,23 @@ class FastaRecord(C.Structure):
                 ("first_fragment", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class IngestStats(C.Structure):
+    """tnt_ingest_stats (include/tntb200.h)."""
+    _fields_ = [("text_bytes", C.c_uint64), ("bases", C.c_uint64), ("records", C.c_uint64), ("fragments", C.c_uint64),
+                ("slabs", C.c_uint64), ("launches", C.c_uint64), ("parse_ms", C.c_double), ("call_ms", C.c_double)]
+
+
+class PackedTarget(C.Structure):
+    """tnt_packed_target (include/tntb200.h)."""
+    _fields_ = [("base", C.c_uint64), ("len", C.c_uint32), ("pad", C.c_uint32), ("exc_begin", C.c_uint64), ("exc_end", C.c_uint64)]
+
+
+class PackedInfo(C.Structure):
+    """tnt_packed_info (include/tntb200.h)."""
+    _fields_ = [("format", C.c_uint32), ("word_size", C.c_uint32), ("n_targets", C.c_uint64), ("n_words", C.c_uint64),
+                ("n_exceptions", C.c_uint64), ("next_base", C.c_uint64), ("total_bases", C.c_uint64)]
+
+
 class FastaFragment(C.Structure):
     """tnt_fasta_fragment (include/tntb200.h)."""
     _fields_ = [("record", C.c_uint32), ("start", C.c_uint32), ("stop", C.c_uint32), ("max_stop", C.c_uint32),
@@ -168,6 +185,9 @@ def load_library() -> C.CDLL:
     L.tnt_engine_add_fasta.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
                                        C.POINTER(C.POINTER(FastaRecord)), C.POINTER(C.c_size_t),
                                        C.POINTER(C.POINTER(FastaFragment)), C.POINTER(C.c_size_t)]
+    L.tnt_engine_export_packed.argtypes = [vp, C.POINTER(PackedInfo), vp, vp, vp, vp, vp]
+    L.tnt_engine_import_packed.argtypes = [vp, C.POINTER(PackedInfo), vp, vp, vp, vp, vp]
+    L.tnt_engine_get_ingest_stats.argtypes = [vp, C.POINTER(IngestStats)]
     L.tnt_engine_target_codes.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, u8p]
     L.tnt_engine_set_assays.argtypes = [vp, C.POINTER(CAssay), C.c_int32]
     L.tnt_engine_search.argtypes = [vp, C.POINTER(SearchOptions)]
@@ -271,6 +291,49 @@ class Engine:
         recs = [FastaRecord.from_buffer_copy(pr[i]) for i in range(nr.value)]
         frags = [FastaFragment.from_buffer_copy(pf[i]) for i in range(nf.value)]
         return recs, frags
+
+    def add_fasta_raw(self, address: int, nbytes: int, fragment_threshold: int = 500000, overlap: int = 2002) -> int:
+        """tnt_engine_add_fasta without materialising the tables in Python; returns the fragment count."""
+        nf = C.c_size_t()
+        self._check(self.L.tnt_engine_add_fasta(self.h, C.c_void_p(address), nbytes, fragment_threshold, overlap,
+                                                None, None, None, C.byref(nf)))
+        return nf.value
+
+    # -- packed database snapshot ---------------------------------------------------------------
+    PACKED_FIELDS = (("targets", np.uint8, 32), ("db2", np.uint64, 1), ("nmask", np.uint32, 1),
+                     ("exc_pos", np.uint64, 1), ("exc_code", np.uint8, 1))
+
+    def export_packed(self) -> dict:
+        """Resident packed database -> numpy arrays (tnt_engine_export_packed); `np.savez(path, **d)`
+        makes the persistent cache file, `import_packed(dict(np.load(path)))` brings it back."""
+        info = PackedInfo()
+        self._check(self.L.tnt_engine_export_packed(self.h, C.byref(info), None, None, None, None, None))
+        n = {"targets": info.n_targets, "db2": info.n_words, "nmask": info.n_words,
+             "exc_pos": info.n_exceptions, "exc_code": info.n_exceptions}
+        d = {name: np.zeros(max(int(n[name]) * k, 1), dtype=dt)[:int(n[name]) * k] for name, dt, k in self.PACKED_FIELDS}
+        self._check(self.L.tnt_engine_export_packed(self.h, C.byref(info), *[C.c_void_p(d[name].ctypes.data) for name, _, _ in self.PACKED_FIELDS]))
+        d["info"] = np.array([info.format, info.word_size, info.n_targets, info.n_words, info.n_exceptions,
+                              info.next_base, info.total_bases], dtype=np.uint64)
+        return d
+
+    def import_packed(self, d: dict):
+        """tnt_engine_import_packed from the arrays of export_packed (page-locked arrays are read by DMA
+        after the call returns: keep them alive and unchanged until the next search has returned)."""
+        i = [int(x) for x in d["info"]]
+        info = PackedInfo(i[0], i[1], i[2], i[3], i[4], i[5], i[6])
+        arrs = []
+        for name, dt, _ in self.PACKED_FIELDS:
+            a = d[name]
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                a = np.ascontiguousarray(a, dtype=dt)
+            arrs.append(a)
+        self._keep = arrs
+        self._check(self.L.tnt_engine_import_packed(self.h, C.byref(info), *[C.c_void_p(a.ctypes.data if a.size else 0) for a in arrs]))
+
+    def ingest_stats(self) -> IngestStats:
+        st = IngestStats()
+        self._check(self.L.tnt_engine_get_ingest_stats(self.h, C.byref(st)))
+        return st
 
     def target_codes(self, target_id: int, start: int, n: int) -> np.ndarray:
         """seq.h codes of a range of a registered fragment, read back from the packed database."""
