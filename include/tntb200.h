@@ -244,6 +244,14 @@ int tnt_engine_search(tnt_engine *e, const tnt_search_options *opt);
 int tnt_engine_get_hits(tnt_engine *e, const tnt_hit **hits, size_t *n, const char **arena, size_t *arena_size);
 int tnt_engine_get_stats(tnt_engine *e, tnt_stats *out);
 
+/* Hits of the last search that sit on a threshold: some bound oligo has its Tm within `tm_tol`
+ * (deg C) of the min / max Tm bound it was filtered with, or dH - T*dS within `dg_tol` (kcal/mol)
+ * of the min / max dG bound.  These are the hits BASELINE.json's north_star wants listed
+ * separately when two implementations are compared at 0.01 C / 0.001 kcal/mol: a last-digit
+ * difference in Tm may move them across the filter (bind_oligo.cpp:598-640).  Writes at most
+ * `cap` indices into the hit array, returns the full count. */
+long tnt_engine_hits_near_threshold(tnt_engine *e, float tm_tol, float dg_tol, uint32_t *indices, size_t cap);
+
 /* Amplicon / probe-site text of a hit as the reference builds it from the fragment
  * (amplicon_search.cpp:508-537, padlock_search.cpp:203-218,338-352, probe_search.cpp:127-143):
  * writes at most cap-1 characters + NUL, returns the full length. */

@@ -643,3 +643,29 @@ def test_incremental_targets(engine_lib, oracle):
     assert both == fresh
     assert [k for k in both if k[0] < 2] == first
     assert len(fresh) >= 4
+
+
+def test_hits_on_a_threshold_are_listed_separately(engine_lib, oracle):
+    """north_star: hits whose Tm lies within the comparison tolerance (0.01 C / 0.001 kcal/mol) of
+    a filter bound are listed separately.  With the bound put exactly on the Tm of a known hit the
+    hit is still reported (the reference rejects `tm < min`, bind_oligo.cpp:598-607), equals the
+    oracle's, and tnt_engine_hits_near_threshold names it; with the default bounds nothing is listed."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(606)
+    codes, F, R, P = gen.make_pcr_case(rng, 40000, n_sites=3, probe=True)
+    with Engine() as e:
+        e.add_target(codes)
+        e.set_assays([Assay(0, F, R, P)])
+        o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+        hits = e.search(to_opts(o))
+        assert len(hits) >= 1 and e.hits_near_threshold() == []
+        # the weaker primer of the best hit: that hit stays and sits exactly on the bound
+        edge = float(np.float32(max(min(h.forward.tm, h.reverse.tm) for h in hits)))
+        o2 = H.default_options(min_primer_tm=edge, min_probe_tm=40.0)
+        got = e.search(to_opts(o2))
+        want = oracle.search(codes, F, R, P, o2)
+        assert_hits_equal(e, got, want, (F, R, P))
+        near = e.hits_near_threshold()
+        assert near and all(min(abs(got[i].forward.tm - edge), abs(got[i].reverse.tm - edge)) <= TM_TOL for i in near)
+        others = [i for i in range(len(got)) if i not in near]
+        assert all(min(abs(got[i].forward.tm - edge), abs(got[i].reverse.tm - edge)) > TM_TOL for i in others)

@@ -2064,6 +2064,38 @@ int tnt_engine_get_stats(tnt_engine *e, tnt_stats *out)
 	API_END
 }
 
+long tnt_engine_hits_near_threshold(tnt_engine *e, float tm_tol, float dg_tol, uint32_t *indices, size_t cap)
+{
+	try {
+		if (!e || (!indices && cap)) throw std::runtime_error("null argument");
+		const tnt_search_options &o = e->last_opt;
+		const float T = e->prm.target_T;
+		size_t n = 0;
+		for (size_t i = 0; i < e->hits.size(); ++i) {
+			const tnt_hit &h = e->hits[i];
+			bool near = false;
+			for (const tnt_bound_oligo *b : {&h.forward, &h.reverse, &h.probe}) {
+				if (b->oligo == TNT_OLIGO_NONE) continue;
+				// the bounds the oligo was filtered with (prepare_sets): primer bounds for the primers of a
+				// PCR assay, probe bounds for everything else
+				const bool primer = o.assay_format == TNT_ASSAY_PCR && b->oligo != TNT_OLIGO_P;
+				const float lo_tm = primer ? o.min_primer_tm : o.min_probe_tm, hi_tm = primer ? o.max_primer_tm : o.max_probe_tm;
+				const float lo_dg = primer ? o.min_primer_dg : o.min_probe_dg, hi_dg = primer ? o.max_primer_dg : o.max_probe_dg;
+				const float dg = b->dH - T*b->dS;
+				near |= std::fabs(b->tm - lo_tm) <= tm_tol || std::fabs(b->tm - hi_tm) <= tm_tol ||
+					std::fabs(dg - lo_dg) <= dg_tol || std::fabs(dg - hi_dg) <= dg_tol;
+			}
+			if (near) {
+				if (n < cap) indices[n] = (uint32_t)i;
+				++n;
+			}
+		}
+		return (long)n;
+	}
+	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
+	catch (...) { g_error = "unknown error"; return -1; }
+}
+
 long tnt_engine_hit_sequence(tnt_engine *e, const tnt_hit *hit, char *out, size_t cap)
 {
 	try {

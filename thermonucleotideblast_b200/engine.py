@@ -185,6 +185,8 @@ def load_library() -> C.CDLL:
     L.tnt_engine_add_fasta.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
                                        C.POINTER(C.POINTER(FastaRecord)), C.POINTER(C.c_size_t),
                                        C.POINTER(C.POINTER(FastaFragment)), C.POINTER(C.c_size_t)]
+    L.tnt_engine_hits_near_threshold.argtypes = [vp, C.c_float, C.c_float, u32p, C.c_size_t]
+    L.tnt_engine_hits_near_threshold.restype = C.c_long
     L.tnt_engine_export_packed.argtypes = [vp, C.POINTER(PackedInfo), vp, vp, vp, vp, vp]
     L.tnt_engine_import_packed.argtypes = [vp, C.POINTER(PackedInfo), vp, vp, vp, vp, vp]
     L.tnt_engine_get_ingest_stats.argtypes = [vp, C.POINTER(IngestStats)]
@@ -397,6 +399,16 @@ class Engine:
         recs = C.string_at(ph, n.value * C.sizeof(CHit)) if n.value else b""
         text = C.string_at(arena.value, asz.value) if asz.value else b""
         return n.value, recs, text
+
+    def hits_near_threshold(self, tm_tol: float = 0.01, dg_tol: float = 0.001) -> List[int]:
+        """Indices of the hits of the last search that sit within the comparison tolerance of a Tm / dG
+        bound (to be listed separately when hit sets of two implementations are compared)."""
+        n = self.L.tnt_engine_hits_near_threshold(self.h, tm_tol, dg_tol, None, 0)
+        if n < 0:
+            raise EngineError(self.L.tnt_last_error().decode())
+        idx = np.zeros(max(n, 1), dtype=np.uint32)
+        self.L.tnt_engine_hits_near_threshold(self.h, tm_tol, dg_tol, idx.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+        return idx[:n].tolist()
 
     def stats(self) -> Stats:
         st = Stats()
