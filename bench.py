@@ -12,6 +12,9 @@ Metric: DB Gbp*assay/s (database bases x input assays per second), whole job ove
   value : inputs already resident in HBM when the timed region starts (search only)
   e2e   : the same through the C ABI with host buffers: clear + upload of every fragment
           (pinned staging, H2D, 2-bit pack) + search + hit read-back inside the timed region
+  ingest_fasta         : the same database as 80-column FASTA text in page-locked memory -> tnt_engine_add_fasta
+                         (parsed, cut and packed on the device) + search + hit read-back
+  e2e_packed_snapshot  : tnt_engine_import_packed of the exported 2-bit database + search + hit read-back
 Extra keys: alignments_per_s (NucCruc heterodimer evaluations), roofline (NucCruc DP kernel,
 int32 issue roofline of SURVEY 8d), roofline_seed_scan (HBM), cpu_baseline (the unmodified
 reference OpenMP build on the host cores on a bounded slice of the same workload).

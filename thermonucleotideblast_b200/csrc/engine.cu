@@ -619,6 +619,8 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 		CUDA_OK(cudaStreamSynchronize(e->up_stream));
 		e->fa_carry.reserve(1, 0, e->up_stream);
 	}
+	// the slab buffers may still be read by the parser kernels of an earlier call
+	for (int i = 0; i < tnt_engine::FA_BUFS; ++i) CUDA_OK(cudaStreamWaitEvent(e->fa_copy_stream, e->fa_parsed[i], 0));
 	const size_t nslabs = (n + FA_SLAB_BYTES - 1)/FA_SLAB_BYTES;
 	for (int i = 0; i < tnt_engine::FA_BUFS && (size_t)i < nslabs; ++i)
 		if (!e->fa_text[i]) CUDA_OK(cudaMalloc(&e->fa_text[i], FA_SLAB_BYTES));

@@ -264,6 +264,8 @@ __global__ void __launch_bounds__(FA_SCAN_THREADS) k_fa_scan(const uint4 *__rest
 	}
 }
 
+__device__ __forceinline__ uint32_t fa_pad(uint32_t i) { return i + 8u*(i >> 7); }
+
 // Pass 3: codes and record table.  `text_pos0` = offset of the slab in the caller's text,
 // `codes` = the output array for the whole text (base index counted from the first record).
 __global__ void __launch_bounds__(FA_THREADS) k_fa_emit(const uint8_t *__restrict__ text, uint32_t n, uint64_t text_pos0,
@@ -273,7 +275,10 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_emit(const uint8_t *__restric
 	__shared__ uint32_t s_lut[4][256];
 	__shared__ uint8_t s_code[256];
 	__shared__ FaMap s_warp[FA_THREADS/32];
-	__shared__ __align__(16) uint8_t s_out[FA_BLOCK_BYTES];
+	// Codes of the block, compacted.  A lane's output starts ~63 bytes after its neighbour's, i.e.
+	// every second lane would hit the same bank (ncu: half of the shared-memory wavefronts of the
+	// first version were bank conflicts): two pad words per 128 bytes spread the lanes over the banks.
+	__shared__ __align__(16) uint8_t s_out[FA_BLOCK_BYTES + 8*(FA_BLOCK_BYTES/128)];
 	fa_load_tables(tables, s_lut, s_code);
 	__syncthreads();
 	uint32_t w[16], m;
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_emit(const uint8_t *__restric
 			if (4u*k + s < m) {
 				const uint32_t c = (w[k] >> (8*s)) & 0xffu;
 				const uint32_t e = s_lut[st][c];
-				if (e & FA_BASE_ONE) s_out[nb++] = s_code[c];
+				if (e & FA_BASE_ONE) { s_out[fa_pad(nb)] = s_code[c]; ++nb; }
 				if (e & FA_REC_ONE) {
 					rec_pos[rec] = text_pos0 + off + 4u*k + s;
 					rec_base[rec] = en.bases + nb;
@@ -306,20 +311,20 @@ __global__ void __launch_bounds__(FA_THREADS) k_fa_emit(const uint8_t *__restric
 	__syncthreads();
 	const uint32_t block_bases = fa_pick(total, en.state) >> 17;
 	uint8_t *dst = codes + en.bases;
-	// head up to a 16-byte boundary of the destination, 16-byte body, tail
-	const uint32_t head = min(block_bases, (uint32_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u));
-	if (threadIdx.x < head) dst[threadIdx.x] = s_out[threadIdx.x];
-	const uint32_t nvec = (block_bases - head)/16u;
+	// head up to a 4-byte boundary of the destination, body, tail
+	const uint32_t head = min(block_bases, (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));
+	if (threadIdx.x < head) dst[threadIdx.x] = s_out[fa_pad(threadIdx.x)];
+	// body: one aligned 32-bit store per lane (consecutive lanes read consecutive words of s_out:
+	// no bank conflicts; a warp writes 128 contiguous bytes)
+	const uint32_t nvec = (block_bases - head)/4u;
 	for (uint32_t k = threadIdx.x; k < nvec; k += FA_THREADS) {
-		const uint8_t *src = s_out + head + 16u*k;
-		uint32_t x[4];
-#pragma unroll
-		for (int q = 0; q < 4; ++q)
-			x[q] = (uint32_t)src[4*q] | ((uint32_t)src[4*q + 1] << 8) | ((uint32_t)src[4*q + 2] << 16) | ((uint32_t)src[4*q + 3] << 24);
-		*reinterpret_cast<uint4 *>(dst + head + 16u*k) = make_uint4(x[0], x[1], x[2], x[3]);
+		const uint32_t at = head + 4u*k;
+		const uint32_t x = (uint32_t)s_out[fa_pad(at)] | ((uint32_t)s_out[fa_pad(at + 1)] << 8) |
+			((uint32_t)s_out[fa_pad(at + 2)] << 16) | ((uint32_t)s_out[fa_pad(at + 3)] << 24);
+		*reinterpret_cast<uint32_t *>(dst + at) = x;
 	}
-	const uint32_t done = head + 16u*nvec;
-	if (threadIdx.x < block_bases - done) dst[done + threadIdx.x] = s_out[done + threadIdx.x];
+	const uint32_t done = head + 4u*nvec;
+	if (threadIdx.x < block_bases - done) dst[done + threadIdx.x] = s_out[fa_pad(done + threadIdx.x)];
 }
 
 } // namespace tnt
