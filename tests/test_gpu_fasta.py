@@ -205,3 +205,27 @@ def test_packed_snapshot_round_trip(engine_lib, oracle, tmp_path):
         bad["info"][3] -= 4                      # fewer words than the fragment table needs
         with pytest.raises(EngineError):
             e.import_packed(bad)
+
+
+def test_sharded_fasta_ingest_equals_whole(eng):
+    """A FASTA text split with sharding.shard_fasta_text (what one process per GPU would ingest):
+    the ranges, ingested one after the other, give the records, pieces and codes of the whole text."""
+    from thermonucleotideblast_b200.sharding import shard_fasta_text
+    rng = np.random.default_rng(2718)
+    text = gen.rand_fasta(rng, n_records=23, max_len=30000, width=70, iupac=0.01)
+
+    def ingest(ranges):
+        eng.clear_targets()
+        out = []
+        for a, b in ranges:
+            recs, frags = eng.add_fasta(text[a:b], fragment_threshold=8000, overlap=300)
+            for r in recs:
+                for f in frags[r.first_fragment:r.first_fragment + r.n_fragments]:
+                    codes = eng.target_codes(f.target_id, 0, f.len).tolist() if f.len else []
+                    out.append((r.text_offset + a, r.text_bytes, r.bases, f.start, f.stop, f.max_stop, codes))
+        return out
+
+    whole = ingest([(0, len(text))])
+    assert len({w[0] for w in whole}) == 23
+    for world in (2, 4, 8):
+        assert ingest(shard_fasta_text(text, world)) == whole

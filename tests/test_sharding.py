@@ -98,3 +98,25 @@ def test_world_size_2_gloo_shards_cover_the_database():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and n >= 3
+
+
+def test_fasta_text_shards_hold_whole_records(oracle):
+    """Sharding a FASTA text by byte ranges: every range starts where the reference's indexer is in
+    its start state, so the records of the ranges, concatenated, are the records of the text."""
+    import gen
+    from thermonucleotideblast_b200.sharding import shard_fasta_text
+    rng = np.random.default_rng(8)
+    texts = list(gen.FASTA_EDGE_CASES) + [gen.rand_fasta(rng, n_records=int(rng.integers(1, 12)), max_len=2000,
+                                                         width=[60, 0, 7][i % 3], crlf=bool(i % 2)) for i in range(9)]
+    for text in texts:
+        whole = oracle.fasta_records(text, threshold=300, overlap=20)
+        for world in (1, 2, 3, 8):
+            ranges = shard_fasta_text(text, world)
+            assert len(ranges) == world and ranges[-1][1] == len(text)
+            assert all(a <= b for a, b in ranges) and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+            parts = []
+            for a, b in ranges:
+                for off, alen, defline, codes, pieces in oracle.fasta_records(text[a:b], threshold=300, overlap=20):
+                    parts.append((off + a, alen, defline, codes.tolist(), [(p[0], p[1], p[2].tolist()) for p in pieces]))
+            want = [(off, alen, d, c.tolist(), [(p[0], p[1], p[2].tolist()) for p in pcs]) for off, alen, d, c, pcs in whole]
+            assert parts == want

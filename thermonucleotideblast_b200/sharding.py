@@ -59,3 +59,27 @@ def fragment_record(length: int, max_fragment: int = 500000) -> List[Tuple[int, 
         start = stop + 1
         stop = stop + delta
     return out
+
+
+def shard_fasta_text(text, world_size: int) -> List[Tuple[int, int]]:
+    """Byte ranges [begin, end) of a FASTA text, one per rank, for tnt_engine_add_fasta.
+
+    Every range starts at a '>' that follows a '\\n' (or at the first '>' of the text), i.e. at a point
+    where the reference's indexer is in its start state (sequence_data_fastx.cpp:33-58: `read_fasta` is
+    false after a '\\n', so that '>' opens a record), hence parsing the ranges one by one yields exactly
+    the records of the whole text, in order.  Cuts are the record starts nearest after the equal-size
+    byte marks; a rank may get an empty range when there are fewer records than ranks."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    data = text if isinstance(text, (bytes, bytearray, memoryview)) else bytes(text)
+    n = len(data)
+    first = data.find(b">")
+    if first < 0:
+        return [(0, 0)] * world_size
+    cuts = [first]
+    for r in range(1, world_size):
+        mark = max(cuts[-1], first + (n - first) * r // world_size)
+        at = data.find(b"\n>", max(mark - 1, 0))
+        cuts.append(n if at < 0 else max(at + 1, cuts[-1]))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
