@@ -184,6 +184,11 @@ struct tnt_engine {
 	};
 	std::vector<BatchEvents> batch_ev; // grows to the largest number of batches seen, reused across uploads
 	std::vector<Batch> batches;       // of the registered fragments, ascending base
+	// chunks of an imported snapshot still on their way (tnt_engine_import_packed): they gate stage 1
+	// like upload batches do, in front of them (an import starts at base 0)
+	struct ImportChunk { uint64_t end_base; cudaEvent_t ev; };
+	std::vector<ImportChunk> import_chunks;
+	std::vector<cudaEvent_t> import_ev_pool;
 	size_t next_emit = 0;             // batches[next_emit..] still owe their exceptions
 	// host -> staging copies of the open batch, issued as one batched copy when the batch is flushed
 	std::vector<void *> piece_dst, piece_src;
@@ -292,6 +297,7 @@ struct tnt_engine {
 		if (fa_scanned) cudaEventDestroy(fa_scanned);
 		for (cudaEvent_t ev : fa_ev) cudaEventDestroy(ev);
 		if (h_fa_carry) cudaFreeHost(h_fa_carry);
+		for (cudaEvent_t ev : import_ev_pool) cudaEventDestroy(ev);
 		if (emit_done) cudaEventDestroy(emit_done);
 		if (pads_ev) cudaEventDestroy(pads_ev);
 		if (emit_stream) cudaStreamDestroy(emit_stream);
@@ -737,6 +743,7 @@ void tnt_engine::finish_upload()
 	if (!batch_open && next_emit == batches.size() && upload_settled) return;
 	flush_batch(this);
 	emit_ready(this, true);
+	import_chunks.clear(); // callers of finish_upload want everything: the search stream follows the whole upload stream
 	settle_upload();
 }
 
@@ -754,7 +761,7 @@ void tnt_engine::settle_upload()
 	CUDA_OK(cudaMemsetAsync(nmask.p + packed_words, 0, 8*sizeof(uint32_t), up_stream));
 	CUDA_OK(cudaEventRecord(pads_ev, up_stream));
 	if (exc_pos.cap == 0) { exc_pos.reserve(16, 0, emit_stream); exc_code.reserve(16, 0, emit_stream); }
-	if (next_emit == batches.size()) {
+	if (next_emit == batches.size() && import_chunks.empty()) {
 		// fully uploaded: later work on the search stream simply follows the upload streams
 		CUDA_OK(cudaEventRecord(emit_done, emit_stream));
 		CUDA_OK(cudaStreamWaitEvent(stream, emit_done, 0));
@@ -1309,15 +1316,24 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 	// Fragments may still be on their way to the device (upload stream).  Then the pass is cut at
 	// groups of upload batches and every chunk is ordered behind the batches it reads, so the
 	// first chunks are scanned and aligned while the rest of the database crosses PCIe.
+	// what stage 1 may have to wait for, ascending in the base space: the chunks of an imported
+	// snapshot, then the upload batches
+	struct Arrival { uint64_t end_base; cudaEvent_t arrived, ready; long batch; };
+	std::vector<Arrival> arrivals;
+	if (!e->upload_settled) {
+		for (const tnt_engine::ImportChunk &c : e->import_chunks) arrivals.push_back(Arrival{c.end_base, c.ev, c.ev, -1});
+		for (size_t bi = 0; bi < e->batches.size(); ++bi)
+			arrivals.push_back(Arrival{e->batches[bi].base + e->batches[bi].used, e->batch_ev[bi].count_ev, e->batch_ev[bi].packed_ev, (long)bi});
+	}
 	struct Gate { uint32_t tile_end; size_t batch; };
 	std::vector<Gate> gates;
-	if (!e->upload_settled && !e->batches.empty()) {
-		const size_t group = 1; // batches per gate (32 MB); a chunk takes every gate that is already open
+	if (!arrivals.empty()) {
+		const size_t group = 1; // arrivals per gate (32 MB of bases); a chunk takes every gate that is already open
 		uint32_t t = 0;
 		for (size_t b = group - 1;; b += group) {
-			const size_t bi = std::min(b, e->batches.size() - 1);
-			const bool last = bi + 1 == e->batches.size();
-			const uint64_t gend = e->batches[bi].base + e->batches[bi].used;
+			const size_t bi = std::min(b, arrivals.size() - 1);
+			const bool last = bi + 1 == arrivals.size();
+			const uint64_t gend = arrivals[bi].end_base;
 			while (t < tiles.size()) {
 				const Target &tg = e->targets[tiles[t].target];
 				// k-mers and alignment windows read a little past the tile, never past the fragment
@@ -1340,15 +1356,15 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 			while (gates[gate].tile_end <= t0) ++gate;
 			// as far as the upload has come (at least one gate: the stream then waits for it)
 			while (gate + 1 < gates.size() &&
-				cudaEventQuery(e->batch_ev[gates[gate + 1].batch].count_ev) == cudaSuccess) ++gate;
+				cudaEventQuery(arrivals[gates[gate + 1].batch].arrived) == cudaSuccess) ++gate;
 			cudaGetLastError();
 			t1 = std::min(t1, gates[gate].tile_end);
-			const size_t bi = gates[gate].batch;
+			const Arrival &ar = arrivals[gates[gate].batch];
 			HostTimer t_gate("  upload gate (host wait)");
-			emit_ready(e, true, bi); // exceptions of these batches (the host waits for their counts only)
-			if (bi + 1 == e->batches.size()) CUDA_OK(cudaStreamWaitEvent(e->stream, e->pads_ev, 0)); // + the read-ahead pads
-			CUDA_OK(cudaStreamWaitEvent(e->stream, e->batch_ev[bi].packed_ev, 0));
-			CUDA_OK(cudaStreamWaitEvent(e->stream, e->emit_done, 0));
+			if (ar.batch >= 0) emit_ready(e, true, (size_t)ar.batch); // exceptions of these batches (the host waits for their counts only)
+			if (gates[gate].batch + 1 == arrivals.size()) CUDA_OK(cudaStreamWaitEvent(e->stream, e->pads_ev, 0)); // + the read-ahead pads
+			CUDA_OK(cudaStreamWaitEvent(e->stream, ar.ready, 0));
+			if (ar.batch >= 0) CUDA_OK(cudaStreamWaitEvent(e->stream, e->emit_done, 0));
 		}
 		uint32_t forced_cap = 0; // set after an overflow, when the real bucket sizes are known
 		HostTimer t_chunk("  chunk (scan + align)");
@@ -1388,7 +1404,7 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 		}
 		t0 = t1;
 	}
-	if (!gates.empty() && e->next_emit == e->batches.size()) e->upload_settled = true; // everything waited for
+	if (!gates.empty() && e->next_emit == e->batches.size()) { e->upload_settled = true; e->import_chunks.clear(); } // everything waited for
 }
 
 // Stage-2: scan regions with the given set
@@ -1928,23 +1944,50 @@ int tnt_engine_import_packed(tnt_engine *e, const tnt_packed_info *info, const t
 	CUDA_OK(cudaStreamSynchronize(e->stream)); // nothing may still read arrays that reserve() replaces
 	e->db2.reserve(info->n_words + 8, 0, e->up_stream);
 	e->nmask.reserve(e->db2.cap, 0, e->up_stream);
-	if (info->n_words) {
-		CUDA_OK(cudaMemcpyAsync(e->db2.p, db2, info->n_words*sizeof(uint64_t), cudaMemcpyHostToDevice, e->up_stream));
-		CUDA_OK(cudaMemcpyAsync(e->nmask.p, nmask, info->n_words*sizeof(uint32_t), cudaMemcpyHostToDevice, e->up_stream));
-	}
+	// The fragment and tile tables go first: the copy engine serves host-to-device copies in the
+	// order they were issued, so a table upload issued by the search would sit behind the whole
+	// snapshot (measured: the first scan started 6 ms late).
+	e->targets.resize(info->n_targets);
+	if (info->n_targets) std::memcpy(e->targets.data(), targets, info->n_targets*sizeof(Target));
+	e->targets_dirty = true;
+	e->sync_targets(false);
+	// the sparse non-ACGT list first (every chunk event then implies it), then the words in chunks of
+	// 32 M bases, each followed by an event: stage 1 of a search starts on the chunks that have
+	// arrived, like it does with upload batches
 	if (info->n_exceptions) {
 		e->exc_pos.reserve(info->n_exceptions, 0, e->up_stream);
 		e->exc_code.reserve(e->exc_pos.cap, 0, e->up_stream);
 		CUDA_OK(cudaMemcpyAsync(e->exc_pos.p, exc_pos, info->n_exceptions*sizeof(uint64_t), cudaMemcpyHostToDevice, e->up_stream));
 		CUDA_OK(cudaMemcpyAsync(e->exc_code.p, exc_code, info->n_exceptions, cudaMemcpyHostToDevice, e->up_stream));
 	}
-	e->targets.resize(info->n_targets);
-	if (info->n_targets) std::memcpy(e->targets.data(), targets, info->n_targets*sizeof(Target));
+	e->import_chunks.clear();
+	const uint64_t chunk_words = STAGE_BYTES/32u; // 32 M bases
+	for (uint64_t w0 = 0; w0 < info->n_words; w0 += chunk_words) {
+		const uint64_t nw = std::min<uint64_t>(chunk_words, info->n_words - w0);
+		{
+			// the batched form, like the fragment upload: plain cudaMemcpyAsync calls were observed to
+			// hold back the small host-to-device copies of a concurrent search until the whole
+			// snapshot had crossed
+			void *dsts[2] = {e->db2.p + w0, e->nmask.p + w0};
+			void *srcs[2] = {const_cast<uint64_t *>(db2 + w0), const_cast<uint32_t *>(nmask + w0)};
+			size_t sizes[2] = {nw*sizeof(uint64_t), nw*sizeof(uint32_t)};
+			cudaMemcpyAttributes attr{};
+			attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+			size_t attr_idx = 0, fail = 0;
+			CUDA_OK(cudaMemcpyBatchAsync(dsts, srcs, sizes, 2, &attr, &attr_idx, 1, &fail, e->up_stream));
+		}
+		const size_t ci = e->import_chunks.size();
+		if (ci >= e->import_ev_pool.size()) {
+			e->import_ev_pool.emplace_back();
+			CUDA_OK(cudaEventCreateWithFlags(&e->import_ev_pool.back(), cudaEventDisableTiming));
+		}
+		CUDA_OK(cudaEventRecord(e->import_ev_pool[ci], e->up_stream));
+		e->import_chunks.push_back(tnt_engine::ImportChunk{(w0 + nw)*32u, e->import_ev_pool[ci]});
+	}
 	e->packed_words = info->n_words;
 	e->next_base = info->next_base;
 	e->nexc = info->n_exceptions;
 	e->total_bases = info->total_bases;
-	e->targets_dirty = true;
 	e->upload_settled = false;
 	API_END
 }
@@ -1995,6 +2038,7 @@ int tnt_engine_clear_targets(tnt_engine *e)
 	if (e->fa_copy_stream) CUDA_OK(cudaStreamSynchronize(e->fa_copy_stream));
 	e->fa_records.clear();
 	e->fa_fragments.clear();
+	e->import_chunks.clear();
 	e->targets.clear();
 	e->tiles.clear();
 	e->next_base = 0;
