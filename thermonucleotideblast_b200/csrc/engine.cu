@@ -93,6 +93,25 @@ struct DevBuf {
 	}
 };
 
+// Host -> device for parameter blocks of a few KB (multiples of 4 bytes): kernel arguments, not the
+// copy engine (k_poke); larger blocks fall back to an ordinary copy.
+void poke(void *dst, const void *src, size_t bytes, cudaStream_t st, uint64_t *launches = nullptr)
+{
+	if (bytes == 0) return;
+	if ((bytes & 3u) || bytes > 8*sizeof(PokePayload)) {
+		CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+		return;
+	}
+	PokePayload p;
+	for (size_t off = 0; off < bytes; off += sizeof(PokePayload)) {
+		const size_t n = std::min(sizeof(PokePayload), bytes - off);
+		std::memcpy(p.w, (const char *)src + off, n);
+		k_poke<<<1, 256, 0, st>>>((uint32_t *)((char *)dst + off), (uint32_t)(n/4), p);
+		if (launches) ++*launches;
+	}
+	CUDA_OK(cudaGetLastError());
+}
+
 constexpr size_t STAGE_BYTES = 32u << 20; // one upload batch
 constexpr size_t MAX_SLOTS = 128;         // device staging ring (slots are allocated as needed): up to 4 GB of fragment bytes in flight
 
@@ -1039,7 +1058,8 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 	// unit prefix over the groups
 	uint32_t nunits = 0;
 	for (AlignGroup &g : groups) { g.unit_prefix = nunits; nunits += (g.count + ALIGN_THREADS - 1)/ALIGN_THREADS; }
-	e->d_groups.upload(groups, e->stream);
+	e->d_groups.reserve(std::max<size_t>(groups.size(), 1), 0, e->stream);
+	poke(e->d_groups.p, groups.data(), groups.size()*sizeof(AlignGroup), e->stream, &e->stats.kernel_launches);
 	a.groups = e->d_groups.p;
 	a.ngroups = (uint32_t)groups.size();
 	a.nunits = nunits;
@@ -1151,14 +1171,13 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		e->d_retry_cand.reserve(std::max<size_t>(retry_total, 1), 0, e->stream);
 		e->d_retry_slot.reserve(std::max<size_t>(retry_total, 1), 0, e->stream);
 		e->d_retry_ctl.reserve(2*nos + nos*COUNT_STRIDE, 0, e->stream);
-		CUDA_OK(cudaMemcpyAsync(e->d_retry_ctl.p, retry_ctl.data(), 2*nos*sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+		poke(e->d_retry_ctl.p, retry_ctl.data(), 2*nos*sizeof(uint32_t), e->stream, &e->stats.kernel_launches);
 		CUDA_OK(cudaMemsetAsync(e->d_retry_ctl.p + 2*nos, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 		{
 			const uint32_t init[3] = {base_count, 0, 0};
-			CUDA_OK(cudaMemcpyAsync(e->d_out_count.p, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
-			CUDA_OK(cudaStreamSynchronize(e->stream));
+			poke(e->d_out_count.p, init, sizeof(init), e->stream, &e->stats.kernel_launches);
 		}
-		CUDA_OK(cudaMemcpyAsync(e->d_cells.p, &cells_before, sizeof(cells_before), cudaMemcpyHostToDevice, e->stream));
+		poke(e->d_cells.p, &cells_before, sizeof(cells_before), e->stream, &e->stats.kernel_launches);
 		AlignArgs a{};
 		a.db = e->view();
 		a.thermo = e->d_thermo.p;

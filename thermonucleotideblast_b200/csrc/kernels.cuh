@@ -140,6 +140,15 @@ __global__ void __launch_bounds__(PACK_THREADS) k_emit_exceptions(const uint8_t 
 	}
 }
 
+// Small host -> device parameter blocks travel as kernel arguments instead of copy-engine
+// transfers: the copy engine serves host-to-device copies in issue order, so a 16-byte
+// descriptor upload issued while fragments are streaming in waits behind a 32 MB batch.
+struct PokePayload { uint32_t w[1000]; };
+__global__ void k_poke(uint32_t *__restrict__ dst, uint32_t nwords, PokePayload p)
+{
+	for (uint32_t i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = p.w[i];
+}
+
 // ------------------------------------------------------------------------------------------
 // Base access helpers
 // ------------------------------------------------------------------------------------------
