@@ -27,5 +27,15 @@ with Engine() as e:
         nf = e.add_fasta_raw(int(text.ctypes.data), nbytes, 500000, 2002)
         dt = time.perf_counter() - t0
         st = e.ingest_stats()
+        if it == 0:
+            # spot check at the far end of the database (offsets beyond 4 GB for large runs)
+            recs, frags = None, None
+            last = e.target_codes(nf - 1, 0, 1000)
+            # the last registered fragment is the tail piece of the last record
+            from thermonucleotideblast_b200.sharding import fragment_record
+            a, b = fragment_record(len(records[-1]) + len(b">rec%d synthetic\n" % (len(records) - 1)) + (len(records[-1]) + 79) // 80, 500000)[-1]
+            want = records[-1][a:a + 1000]
+            assert last.tolist() == want.tolist(), "tail fragment differs"
+            print("tail fragment verified (start %d of record %d)" % (a, len(records) - 1), file=sys.stderr)
         print(json.dumps({"fragments": nf, "call_ms": dt * 1e3, "parse_ms": st.parse_ms, "slabs": st.slabs,
                           "text_bytes": st.text_bytes, "bases": st.bases}), file=sys.stderr)
