@@ -120,3 +120,56 @@ def test_fasta_text_shards_hold_whole_records(oracle):
                     parts.append((off + a, alen, defline, codes.tolist(), [(p[0], p[1], p[2].tolist()) for p in pieces]))
             want = [(off, alen, d, c.tolist(), [(p[0], p[1], p[2].tolist()) for p in pcs]) for off, alen, d, c, pcs in whole]
             assert parts == want
+
+
+def _fasta_worker(rank, world, port, q):
+    """Each rank reads its byte range of one FASTA text (the reader stands in through the oracle
+    here: no GPU in this container), searches its records and rank 0 compares the gathered hits
+    with a single-process run over the whole text."""
+    import torch.distributed as dist
+    from thermonucleotideblast_b200.sharding import shard_fasta_text
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(23)
+    db = [gen.random_codes(int(rng.integers(6000, 15000)), rng) for _ in range(7)]
+    assays = gen.make_assays(rng, db, 3, "pcr", variants=2)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    text = b"".join(b">r%d\n" % i + b"\n".join(letters[c][k:k + 60].tobytes() for k in range(0, len(c), 60)) + b"\n"
+                    for i, c in enumerate(db))
+    o = H.default_options(min_primer_tm=40.0)
+
+    def search(byte_range):
+        a, b = byte_range
+        out = []
+        for off, alen, defline, codes, _ in H.oracle().fasta_records(text[a:b]):
+            for ai, (F, R, P) in enumerate(assays):
+                for h in H.oracle().search(codes, F, R, P, o):
+                    out.append((defline, ai, h.amp_first, h.amp_last, h.forward_align.decode()))
+        return out
+
+    mine = search(shard_fasta_text(text, world)[rank])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    if rank == 0:
+        merged = [x for part in gathered for x in part]   # ranges are ordered: no sort needed
+        single = search((0, len(text)))
+        q.put((merged == single, len(single)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_fasta_shards():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fasta_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, n = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and n >= 3
