@@ -575,6 +575,13 @@ def main():
     alu_achieved = ALU_OPS_PER_CELL * st.dp_cells / align_s / 1e12 if align_s > 0 else 0.0
     scan_achieved = st.scan_bytes / scan_s / 1e9 if scan_s > 0 else 0.0
 
+    # DRAM traffic of the kernels behind the two rooflines, from one ncu capture of this very workload
+    # (profiles/dram_r01_v7.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the launches
+    # of one search); only quoted when the run is that workload
+    record_cfg = args.kind == "taqman" and args.mbp == 1000 and args.assays == 100
+    nuccruc_traffic = 32.4e9 if record_cfg else None   # lean tier 25.5 GB read (window fetches), full-trace tier 1.4 GB read + 5.1 GB written (trace slabs)
+    scan_traffic = 1.29e9 if record_cfg else None      # 0.255 GB read (the scan needs the 2-bit words only) + 1.03 GB of candidates written
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -594,12 +601,13 @@ def main():
                 "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
                 "upload_call_ms_per_step": upload_s / e2e_steps * 1e3},
         "roofline": {"bound": "alu-int32", "achieved": alu_achieved, "peak": alu_peak, "unit": "TOP/s",
-                     "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": None,
+                     "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": nuccruc_traffic,
+                     "traffic_note": "bytes per step over all NucCruc launches (ncu, profiles/dram_r01_v7.csv): ~450 GB/s, 7 % of the HBM peak -- the kernels are ALU-bound, not memory-bound",
                      "kernel": "k_align (NucCruc DP + traceback + evaluation)",
                      "note": "27 int32 ALU ops per DP cell (SURVEY 8d) x %d cells per step / CUDA-event time of the kernel; "
                              "peak = 148 SM x 128 lanes x %.0f MHz (nominal issue peak, no measured figure exists)" % (st.dp_cells, sm_max)},
         "roofline_seed_scan": {"bound": "hbm", "achieved": scan_achieved, "peak": hbm_peak, "unit": "GB/s",
-                               "frac": scan_achieved / hbm_peak if hbm_peak else None, "traffic": None,
+                               "frac": scan_achieved / hbm_peak if hbm_peak else None, "traffic": scan_traffic,
                                "kernel": "k_seed_scan", "peak_source": hbm_src,
                                "note": "0.375 B per base per pass + 8 B per emitted candidate (SURVEY 8d); with %d oligo "
                                        "strands the scan is bound by table walks and bucket atomics, not HBM" % (2 * len(assays)),

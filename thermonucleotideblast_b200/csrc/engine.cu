@@ -1146,7 +1146,11 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		}
 
 	const uint32_t base_count = e->n_bound;
-	size_t out_cap = emit_all ? (size_t)base_count + total : std::max<size_t>(e->d_bound.cap, (size_t)base_count + (1u << 16));
+	// room for 1 % of the candidates to pass (0.3 % do at -e 45 -E 50): a first search should not have
+	// to redo its largest pass because the site buffer started small (seen in the ncu launch list of a
+	// cold search: every lean-tier launch twice)
+	size_t out_cap = emit_all ? (size_t)base_count + total
+		: std::max<size_t>(e->d_bound.cap, (size_t)base_count + std::max<size_t>(1u << 16, (size_t)(total/100)));
 	size_t slow_cap = std::max<size_t>(e->d_slow.cap, 1u << 16);
 	// Full-trace hand-over segments.  A few per cent of a strand's candidates are typical, but an
 	// oligo with an internal repeat ties its maximal cells in most windows: every segment can take
