@@ -282,6 +282,20 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
 	float strand_conc, const uint32_t *query_loc, const uint32_t *target_loc, long n,
 	tnt_align_result *out);
 
+/* ---- Oligo-only duplexes (the dimer part) ----
+ * The temperatures the driver attaches to every hit but that depend on the assay's oligos only
+ * (tntblast_local.cpp:657-686): `target` NULL or "": approximate_tm_homodimer of `query`
+ * (nuc_cruc.cpp:2457-2516: the query against itself, symmetry entropy in the initiation term,
+ * :1632), as called for forward_dimer_tm / reverse_dimer_tm / probe_dimer_tm; otherwise
+ * approximate_tm_heterodimer with `target` as the second strand, 5'->3' (:2397-2455), as called
+ * for primer_dimer_tm (query = forward primer, target = reverse primer).  The strand
+ * concentration follows NucCruc::strand(c_a, c_b) (nuc_cruc.h:893-910).  Runs the generic
+ * NucCruc kernel on the device with the second oligo as an explicit target (<= 64 bases).  The
+ * hairpin temperatures (approximate_tm_hairpin) are not built yet. */
+int tnt_engine_oligo_dimer(tnt_engine *e, const char *query, const char *target, float conc_a, float conc_b,
+	tnt_align_result *out);
+
+
 /* Seed-scan-only pass over every registered fragment with the registered assays (timing aid for
  * the HBM roofline): returns the number of unique candidates and the device time. */
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms);

@@ -212,6 +212,29 @@ extern "C" int ref_align(const char *query, const uint8_t *target, int target_le
 	GUARD_END
 }
 
+// The oligo-only duplex temperatures of tntblast_local.cpp:657-686.
+extern "C" int ref_dimer(const char *query, const char *target, float T, float na, float conc_a, float conc_b, ref_align_out *out)
+{
+	GUARD_BEGIN
+	NucCruc *melt = get_melt(T, na);
+	melt->dangle(false, false);
+	float tm;
+	if (target) {
+		melt->set_query(std::string(query));
+		melt->set_target(std::string(target));
+		melt->strand(conc_a, conc_b);
+		tm = melt->approximate_tm_heterodimer();
+	}
+	else {
+		melt->set_duplex(std::string(query));
+		melt->strand(conc_a, conc_b);
+		tm = melt->approximate_tm_homodimer();
+	}
+	fill_align_out(*melt, tm, out);
+	return 0;
+	GUARD_END
+}
+
 // Replay of one candidate exactly as bind_oligo_to_{minus,plus}_strand would see it:
 // fragment codes (seq.h DB_* values), seed (query_loc, target_loc), strand.
 // Fills the window bounds and the mapped target coordinates as well.

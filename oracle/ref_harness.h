@@ -92,6 +92,8 @@ long ref_search(const uint8_t *codes, uint32_t len, const char *forward, const c
 	const char *probe, int forward_degen, int reverse_degen, int probe_degen,
 	const ref_options *o);
 int ref_get_hits(ref_hit *out, long cap);
+/* homodimer (target == NULL) / heterodimer of two oligos, as tntblast_local.cpp:657-686 computes them */
+int ref_dimer(const char *query, const char *target, float T, float na, float conc_a, float conc_b, ref_align_out *out);
 
 /* FASTA reader of the reference (sequence_data, sequence_data_fastx.cpp) on a file */
 long ref_fasta_open(const char *path);                      /* number of records, -1 on error */

@@ -282,6 +282,7 @@ typedef struct {
 	int n_max, cap_max;
 	aln_t best;
 	int oob; /* an unchecked out-of-range read of the reference would have happened */
+	int homo; /* HOMO_DIMER mode: the symmetry entropy joins the initiation term (nuc_cruc.cpp:1632) */
 } nc_t;
 
 /* align_dimer (nuc_cruc.cpp:492-696).  Rows follow the *reversed* query, columns the target. */
@@ -503,7 +504,7 @@ static int evaluate_alignment(const nc_t *nc, aln_t *a)
 	const float *LTH = SL_PARAM_H, *LTS = SL_PARAM_S; /* loop-terminal tables are copies */
 
 	int terminal = P_NONE, last_last = P_NONE, last = P_NONE, cur;
-	float dH = SL_INIT_H, dS = SL_INIT_S + 0.0f;
+	float dH = SL_INIT_H, dS = SL_INIT_S + (nc->homo ? SL_SYMMETRY_S : 0.0f);
 	unsigned nqgap = 0, ntgap = 0, nmm = 0, num_base = 0;
 	int terminal_5 = 0;
 
@@ -879,6 +880,29 @@ int orc_align(const char *query, const uint8_t *target, int target_len, float T,
 	nc->dangle3 = dangle3;
 	float dp_dg;
 	if (nc_run(nc, &dp_dg) < 0) return -1;
+	fill_out(nc, dp_dg, out);
+	return nc->oob ? 1 : 0;
+}
+
+/* Oligo-only duplexes the driver attaches to every hit (tntblast_local.cpp:657-686):
+ * target == NULL: approximate_tm_homodimer (nuc_cruc.cpp:2457-2516) -- the query against itself
+ * (align_homodimer, nuc_cruc.h:718-723), symmetry entropy in the initiation term (:1632);
+ * otherwise approximate_tm_heterodimer (:2397-2455) with `target` as the second strand, 5'->3'
+ * (set_query / set_target, nuc_cruc.h:947-990).  Ct follows strand(c_a, c_b) (nuc_cruc.h:893-910). */
+int orc_dimer(const char *query, const char *target, float T, float na, float conc_a, float conc_b, ref_align_out *out)
+{
+	nc_t *nc = get_nc(T, na);
+	if (set_query(nc, target ? target : query) < 0) return -1;
+	memcpy(nc->t, nc->q, (size_t)nc->Lq);
+	nc->Lt = nc->Lq;
+	if (set_query(nc, query) < 0) return -1;
+	nc->strand = (conc_a > conc_b) ? conc_a - 0.5f*conc_b : conc_b - 0.5f*conc_a;
+	nc->dangle5 = nc->dangle3 = 0;
+	nc->homo = target ? 0 : 1;
+	float dp_dg;
+	const int rc = nc_run(nc, &dp_dg);
+	nc->homo = 0;
+	if (rc < 0) return -1;
 	fill_out(nc, dp_dg, out);
 	return nc->oob ? 1 : 0;
 }

@@ -126,6 +126,36 @@ def main():
     # 5. FASTA reader + fragment queue (sequence_data on a file; written separately so that the
     #    fixtures above need not be regenerated: `make_golden.py fasta`)
     make_fasta(r)
+    make_dimers(r)
+
+
+def dimer_cases():
+    rng = np.random.default_rng(4711)
+    cases = []
+    for it in range(120):
+        L = int(rng.integers(10, 40))
+        q = gen.rand_oligo(L, rng)
+        if it % 5 == 0:                      # self-complementary
+            h = gen.rand_oligo(L // 2, rng)
+            q = h + gen.revcomp(h)
+        t = gen.rand_oligo(int(rng.integers(10, 40)), rng) if it % 2 else None
+        if it % 7 == 0 and t:
+            t = gen.mutate(gen.revcomp(q), 2, rng)   # a real primer dimer
+        if it % 11 == 0:
+            q = q[:5] + "I" + q[6:]
+        ca, cb = (9e-7, 9e-7) if it % 3 else (2e-6, 5e-7)
+        cases.append((q, t, ca, cb))
+    return cases
+
+
+def make_dimers(r):
+    out = []
+    for q, t, ca, cb in dimer_cases():
+        a = r.dimer(q, t, conc_a=ca, conc_b=cb)
+        out.append({"q": q, "t": t, "ca": ca, "cb": cb, "tm": f32(a.tm), "dH": f32(a.dH), "dS": f32(a.dS), "dG": f32(a.dG),
+                    "valid": a.valid, "alignment": a.alignment.decode() if t else None})
+    json.dump(out, open(os.path.join(HERE, "dimers.json"), "w"))
+    print("dimer fixtures:", len(out))
 
 
 def fasta_texts():
@@ -164,5 +194,7 @@ def make_fasta(r):
 if __name__ == "__main__":
     if sys.argv[1:] == ["fasta"]:
         make_fasta(H.ref())
+    elif sys.argv[1:] == ["dimers"]:
+        make_dimers(H.ref())
     else:
         main()

@@ -201,6 +201,7 @@ class _Lib:
         self._bind_window = fn("bind_window", C.c_int, [u8p, C.c_uint32, C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(AlignOut)])
         self._search = fn("search", C.c_long, [u8p, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(Options)])
         self._get_hits = fn("get_hits", C.c_int, [C.POINTER(Hit), C.c_long])
+        self._dimer = fn("dimer", C.c_int, [C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(AlignOut)])
         u64p = C.POINTER(C.c_uint64)
         self._seq_len_increment = fn("seq_len_increment", None, [C.c_uint32, C.c_uint32, u32p, u32p])
         if prefix == "orc_":
@@ -267,6 +268,12 @@ class _Lib:
         got = self._get_hits(arr, n)
         return [arr[i] for i in range(got)]
 
+
+    def dimer(self, query: str, target: Optional[str] = None, T=310.15, na=0.05, conc_a=9.0e-7, conc_b=9.0e-7) -> AlignOut:
+        """Homodimer (target None) or heterodimer Tm of oligos, as tntblast_local.cpp:657-686 computes them."""
+        out = AlignOut()
+        self._check(self._dimer(query.encode(), target.encode() if target is not None else None, T, na, conc_a, conc_b, C.byref(out)))
+        return out
 
     # -- FASTA reader ------------------------------------------------------------------------
     def seq_len_increment(self, length: int, max_len: int) -> Tuple[int, int]:

@@ -669,3 +669,43 @@ def test_hits_on_a_threshold_are_listed_separately(engine_lib, oracle):
         assert near and all(min(abs(got[i].forward.tm - edge), abs(got[i].reverse.tm - edge)) <= TM_TOL for i in near)
         others = [i for i in range(len(got)) if i not in near]
         assert all(min(abs(got[i].forward.tm - edge), abs(got[i].reverse.tm - edge)) > TM_TOL for i in others)
+
+
+def test_oligo_dimers_on_the_device(eng, oracle):
+    """tnt_engine_oligo_dimer (generic NucCruc kernel with the second oligo as an explicit target,
+    symmetry entropy for homodimers) against the oracle: bit-identical Tm / dH / dS, identical text."""
+    import json
+    import os
+    rng = np.random.default_rng(515)
+    cases = [(fx["q"], fx["t"], fx["ca"], fx["cb"]) for fx in
+             json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dimers.json")))]
+    for it in range(150):
+        L = int(rng.integers(8, 45))
+        q = gen.rand_oligo(L, rng)
+        if it % 4 == 0:
+            h = gen.rand_oligo(L // 2, rng)
+            q = h + gen.revcomp(h)
+        t = gen.rand_oligo(int(rng.integers(8, 60)), rng) if it % 2 else None
+        if it % 6 == 1:
+            t = gen.mutate(gen.revcomp(q), int(rng.integers(0, 4)), rng)
+        cases.append((q, t, *[(9e-7, 9e-7), (2e-6, 5e-7)][it % 2]))
+    for q, t, ca, cb in cases:
+        want = oracle.dimer(q, t, conc_a=ca, conc_b=cb)
+        got = eng.oligo_dimer(q, t, ca, cb)
+        assert got.valid == want.valid, (q, t)
+        assert abs(got.tm - want.tm) <= TM_TOL
+        assert (got.tm, got.dH, got.dS) == (want.tm, want.dH, want.dS), (q, t)
+        if want.valid:
+            assert got.alignment == want.alignment, (q, t)
+    # a resident database and a search are not disturbed by the explicit-target launches
+    codes, F, R, P = gen.make_pcr_case(rng, 30000, n_sites=2, probe=True)
+    eng.clear_targets()
+    eng.add_target(codes)
+    from thermonucleotideblast_b200 import Assay
+    eng.set_assays([Assay(0, F, R, P)])
+    o = H.default_options(min_primer_tm=40.0, min_probe_tm=40.0)
+    before = [hit_key(eng, h, (F, R, P)) for h in eng.search(to_opts(o))]
+    eng.oligo_dimer(F, R)
+    eng.oligo_dimer(P)
+    assert [hit_key(eng, h, (F, R, P)) for h in eng.search(to_opts(o))] == before and before
+    eng.clear_targets()

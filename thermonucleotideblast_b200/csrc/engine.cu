@@ -167,6 +167,13 @@ struct tnt_engine {
 
 	Thermo h_thermo{};
 	DevBuf<Thermo> d_thermo;
+	// oligo-only duplexes (tnt_engine_oligo_dimer): explicit target of the generic kernel, and the
+	// tables with the symmetry entropy folded into the initiation term for homodimers
+	DevBuf<Thermo> d_thermo_homo;
+	DevBuf<uint8_t> d_explicit;
+	const Thermo *thermo_override = nullptr;
+	const uint8_t *explicit_tgt = nullptr;
+	int explicit_len = 0;
 
 	// resident database
 	DevBuf<uint64_t> db2;
@@ -1066,7 +1073,7 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 	uint32_t grid;
 	size_t smem = 0;
 	if (lq == 0) {
-		const int max_lt = max_len + 2*NUM_FLANK;
+		const int max_lt = std::max(max_len + 2*NUM_FLANK, e->explicit_len);
 		smem = ((TABLE*4 + NB*NB + 52 + MAX_OLIGO + 15) & ~15) + (size_t)3*(max_lt + 1)*ALIGN_THREADS*sizeof(int32_t);
 		CUDA_OK(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		int per_sm = 1;
@@ -1184,7 +1191,9 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		poke(e->d_cells.p, &cells_before, sizeof(cells_before), e->stream, &e->stats.kernel_launches);
 		AlignArgs a{};
 		a.db = e->view();
-		a.thermo = e->d_thermo.p;
+		a.thermo = e->thermo_override ? e->thermo_override : e->d_thermo.p;
+		a.explicit_tgt = e->explicit_tgt;
+		a.explicit_len = e->explicit_len;
 		a.os = set.d_os.p;
 		a.cand = e->d_cand.p;
 		a.cap = cap;
@@ -2283,6 +2292,75 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
 	CUDA_OK(cudaMemcpyAsync(&cells, e->d_cells.p, sizeof(cells), cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	e->stats.dp_cells = cells;
+	API_END
+}
+
+int tnt_engine_oligo_dimer(tnt_engine *e, const char *query, const char *target, float conc_a, float conc_b, tnt_align_result *out)
+{
+	API_BEGIN
+	if (!e || !query || !out) throw std::runtime_error("null argument");
+	const bool homo = !target || !*target;
+	const std::string tseq = homo ? std::string(query) : std::string(target);
+	if (tseq.size() > (size_t)MAX_WINDOW) throw std::runtime_error("second oligo longer than 64 bases");
+	if (!(conc_a >= 0.0f) || !(conc_b >= 0.0f)) throw std::runtime_error(":strand: negative concentration");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->stats = tnt_stats{};
+	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
+	// strand(c_a, c_b), nuc_cruc.h:893-910
+	const float ct = (conc_a > conc_b) ? conc_a - 0.5f*conc_b : conc_b - 0.5f*conc_a;
+	OsSet set;
+	tnt_search_options o{};
+	o.max_gap = o.max_mismatch = o.max_poly_degen = 999;
+	set.os.push_back(make_os(e, 0, TNT_OLIGO_P, true, query, ct, 1.0f, 9999.0f, -9999.0f, 0.0f, 0, 0, o));
+	finish_set(e, set);
+	set.fast_ok[0] = 0; // the generic kernel takes the explicit target
+	std::vector<uint8_t> tcodes(tseq.size());
+	for (size_t i = 0; i < tseq.size(); ++i) {
+		const int b = base_from_ascii(tseq[i]);
+		if (b < 0) throw std::runtime_error(":char_to_nucleic_acid: Illegal base");
+		tcodes[i] = (uint8_t)b;
+	}
+	e->d_explicit.upload(tcodes, e->stream);
+	if (homo && !e->d_thermo_homo.p) {
+		// local_align.dS = param_init_S + param_symmetry_S (nuc_cruc.cpp:1632): one float addition,
+		// done here exactly as the reference does it per evaluation
+		std::unique_ptr<Thermo> th(new Thermo(e->h_thermo));
+		th->init_S = th->init_S + symmetry_S();
+		e->d_thermo_homo.reserve(1, 0, e->stream);
+		CUDA_OK(cudaMemcpyAsync(e->d_thermo_homo.p, th.get(), sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+	}
+	std::vector<Candidate> cands(1);
+	cands[0].target_k = 0;
+	cands[0].t = 0;
+	e->d_cand.upload(cands, e->stream);
+	e->d_cand_count.reserve(COUNT_STRIDE, 0, e->stream);
+	const uint32_t cnt = 1;
+	CUDA_OK(cudaMemcpyAsync(e->d_cand_count.p, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, e->stream));
+	e->n_bound = 0;
+	struct Restore {
+		tnt_engine *e;
+		~Restore() { e->thermo_override = nullptr; e->explicit_tgt = nullptr; e->explicit_len = 0; }
+	} restore{e};
+	e->thermo_override = homo ? e->d_thermo_homo.p : nullptr;
+	e->explicit_tgt = e->d_explicit.p;
+	e->explicit_len = (int)tcodes.size();
+	if (!align_buckets(e, set, 1, 0, true)) throw std::runtime_error("internal: bucket overflow");
+	BoundRec b;
+	CUDA_OK(cudaMemcpyAsync(&b, e->d_bound.p, sizeof(BoundRec), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->n_bound = 0;
+	tnt_align_result &r = *out;
+	std::memset(&r, 0, sizeof(r));
+	r.tm = b.h.tm; r.dH = b.h.dH; r.dS = b.h.dS; r.dG = b.dG;
+	r.valid = b.valid;
+	if (b.h.flags & (F_OOB | F_STACK | F_TRUNC)) r.valid = -1;
+	if (b.valid) {
+		r.num_mismatch = b.h.num_mm; r.num_gap = b.h.num_gap;
+		r.q_first = b.fm_q; r.q_last = b.lm_q;
+		r.t_first = b.lm_t; r.t_last = b.fm_t;
+		std::strncpy(r.alignment, render_alignment(b, set.os[0]).c_str(), sizeof(r.alignment) - 1);
+	}
 	API_END
 }
 

@@ -739,6 +739,10 @@ struct AlignArgs {
 	const uint32_t *retry_cap;
 	uint32_t *retry_fill;       // per strand, COUNT_STRIDE apart; keeps counting past the capacity
 	uint32_t slow_cap;         // capacity of both lists
+	// generic kernel only: align against this sequence (NucCruc codes, 5'->3') instead of a database
+	// window -- the oligo-only duplexes of tntblast_local.cpp:657-686
+	const uint8_t *explicit_tgt;
+	int explicit_len;
 };
 
 // Thresholds in the reference's order (bind_oligo.cpp:598-714), target coordinates
@@ -1037,15 +1041,22 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 
 		const Candidate c = a.cand[(size_t)unit.os*a.cap + unit.begin + tid];
 		const uint32_t target = c.target_k & 0xffffffu, k = c.target_k >> 24;
-		const Target tg = a.db.targets[target];
-
-		// window (bind_oligo.cpp:502-505)
-		const int s0 = (int)c.t - (int)(k + NUM_FLANK);
-		const uint32_t start = s0 > 0 ? (uint32_t)s0 : 0u;
-		const uint32_t stop = min(start + (uint32_t)os.len + 2u*NUM_FLANK, tg.len);
-
 		uint8_t tgt[MAX_WINDOW];
-		const int Lt = load_window(a.db, tg, start, stop, os.plus != 0, tgt);
+		uint32_t start = 0, stop = 0;
+		int Lt;
+		if (a.explicit_tgt) {
+			Lt = a.explicit_len;
+			for (int i = 0; i < Lt; ++i) tgt[i] = a.explicit_tgt[i];
+			stop = (uint32_t)Lt;
+		}
+		else {
+			const Target tg = a.db.targets[target];
+			// window (bind_oligo.cpp:502-505)
+			const int s0 = (int)c.t - (int)(k + NUM_FLANK);
+			start = s0 > 0 ? (uint32_t)s0 : 0u;
+			stop = min(start + (uint32_t)os.len + 2u*NUM_FLANK, tg.len);
+			Lt = load_window(a.db, tg, start, stop, os.plus != 0, tgt);
+		}
 		my_cells += (unsigned long long)(os.len*Lt);
 
 		unsigned flags = 0;

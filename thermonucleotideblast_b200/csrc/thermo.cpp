@@ -327,6 +327,8 @@ int lean_min_columns(const Thermo &th, const OligoStrand &os, float min_tm)
 	return NMAX + 1;
 }
 
+float symmetry_S() { return SL_SYMMETRY_S; }
+
 float r_log_ct(float ct)
 {
 	return 1.9872e-3f*std::log(ct*1.0f); // NC_R*log(strand*alpha), nuc_cruc.cpp:2291

@@ -14,6 +14,8 @@ bool build_lean_tables(const Thermo &th, const OligoStrand &os, const int32_t *r
 
 // NC_R*log(Ct) with the host libm (reference nuc_cruc.cpp:2291)
 float r_log_ct(float ct);
+// param_symmetry_S (nuc_cruc_santa_lucia.cpp): joins the initiation entropy of a homodimer (nuc_cruc.cpp:1632)
+float symmetry_S();
 
 // compacted seed word list of an oligo (complement = reverse complement, plus-strand search)
 // Smallest number of columns a trimmed gapless alignment of this oligo (first and last column

@@ -202,6 +202,7 @@ def load_library() -> C.CDLL:
     L.tnt_engine_seeds.restype = C.c_long
     L.tnt_engine_align.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, C.c_float, u32p, u32p,
                                    C.c_long, C.POINTER(AlignResult)]
+    L.tnt_engine_oligo_dimer.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.POINTER(AlignResult)]
     L.tnt_engine_scan_only.argtypes = [vp, C.POINTER(SearchOptions), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -423,6 +424,12 @@ class Engine:
         buf = C.create_string_buffer(n + 1)
         self.L.tnt_engine_hit_sequence(self.h, C.byref(raw), buf, n + 1)
         return buf.value.decode()
+
+    def oligo_dimer(self, query: str, target: Optional[str] = None, conc_a: float = 9.0e-7, conc_b: float = 9.0e-7) -> AlignResult:
+        """Homodimer (target None) or heterodimer Tm of oligos (tntblast_local.cpp:657-686) on the device."""
+        out = AlignResult()
+        self._check(self.L.tnt_engine_oligo_dimer(self.h, query.encode(), target.encode() if target else None, conc_a, conc_b, C.byref(out)))
+        return out
 
     def scan_only(self, opts: SearchOptions):
         """Seed scan of all fragments with the stage-1 oligo strands; returns (candidates, ms)."""
