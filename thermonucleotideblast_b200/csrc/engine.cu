@@ -260,6 +260,7 @@ struct tnt_engine {
 	// scratch of the search
 	DevBuf<Candidate> d_cand;
 	DevBuf<uint32_t> d_cand_count;
+	DevBuf<uint32_t> d_tile_counter;  // dense seed scan: dynamic tile distribution
 	DevBuf<AlignGroup> d_groups;
 	DevBuf<uint16_t> d_trace;
 	DevBuf<BoundRec> d_bound;    // every site that passed the per-oligo filters, all passes of a search
@@ -999,7 +1000,18 @@ void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1
 		const size_t smem = ((set.nkeys + 31)/32)*sizeof(uint32_t);
 		static size_t dense_attr = 0;
 		if (smem > dense_attr) { CUDA_OK(cudaFuncSetAttribute(k_seed_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); dense_attr = smem; }
-		const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)e->sm_count*8u);
+		// one resident wave of CTAs; tiles beyond the first are drawn from a counter (k_seed_scan)
+		static int scan_ctas_per_sm = 0;
+		static size_t scan_ctas_smem = ~(size_t)0;
+		if (scan_ctas_smem != smem) {
+			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_ctas_per_sm, k_seed_scan, SCAN_THREADS, smem));
+			scan_ctas_per_sm = std::max(scan_ctas_per_sm, 1);
+			scan_ctas_smem = smem;
+		}
+		e->d_tile_counter.reserve(1, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_tile_counter.p, 0, sizeof(uint32_t), e->stream));
+		a.tile_counter = e->d_tile_counter.p;
+		const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(e->sm_count*scan_ctas_per_sm));
 		k_seed_scan<<<grid, SCAN_THREADS, smem, e->stream>>>(a);
 	}
 	CUDA_OK(cudaGetLastError());
