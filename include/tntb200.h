@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TNTB200_ABI_VERSION 2
+#define TNTB200_ABI_VERSION 3
 
 /* hybrid_sig.h:19 */
 enum { TNT_ASSAY_PCR = 0, TNT_ASSAY_PROBE = 1, TNT_ASSAY_PADLOCK = 2, TNT_ASSAY_MIPS = 3 };
@@ -125,6 +125,9 @@ typedef struct {
 	double scan_ms, align_ms, pair_ms, total_ms;   /* device time (CUDA events) */
 	uint64_t scan_bytes;             /* algorithmic bytes of the seed scan */
 	uint64_t d2h_bytes;              /* result bytes copied device -> host by the search (counters excluded) */
+	uint64_t nonbinding_dropped;     /* windows without any alignment (Tm = 0, dG = 0) that the bounds would have
+	                                  * accepted: the reference reports them with the coordinates of an earlier
+	                                  * alignment (nuc_cruc.h:360-371); the engine drops and counts them */
 } tnt_stats;
 
 const char *tnt_last_error(void);
@@ -256,6 +259,13 @@ long tnt_engine_hits_near_threshold(tnt_engine *e, float tm_tol, float dg_tol, u
  * (amplicon_search.cpp:508-537, padlock_search.cpp:203-218,338-352, probe_search.cpp:127-143):
  * writes at most cap-1 characters + NUL, returns the full length. */
 long tnt_engine_hit_sequence(tnt_engine *e, const tnt_hit *hit, char *out, size_t cap);
+
+/* The same text for every hit of the last search at once: the fragment ranges are read back from
+ * the packed database with one kernel launch and one device-to-host copy (the per-hit call above
+ * costs a launch and a synchronisation each).  Hit i occupies text[offsets[i] .. offsets[i+1] - 1),
+ * NUL-terminated; `offsets` has n_hits + 1 entries.  Pointers stay valid until the next search,
+ * clear or destroy. */
+int tnt_engine_hit_sequences(tnt_engine *e, const char **text, const uint64_t **offsets, size_t *n_hits);
 
 /* ---- Stage-level entry points (used by the parity tests and the roofline benchmark) ---- */
 

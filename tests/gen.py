@@ -168,3 +168,44 @@ def rand_fasta(rng, n_records=6, max_len=5000, width=60, iupac=0.01, crlf=False,
         if rng.random() < 0.3:
             out.append(eol)
     return b"".join(out)
+
+
+# -- files for the reference command line ------------------------------------------------------
+def write_fasta(path: str, records: List[np.ndarray], names: Optional[List[str]] = None, width: int = 80,
+                limit_bp: Optional[int] = None) -> int:
+    """80-column FASTA of the records (seq.h codes), optionally only the leading `limit_bp` bases.
+    Returns the number of bases written."""
+    lut = np.frombuffer(b"ACGTIMRSVWYHKDBN-N", dtype=np.uint8)
+    left = sum(len(r) for r in records) if limit_bp is None else limit_bp
+    done = 0
+    with open(path, "wb") as f:
+        for i, rec in enumerate(records):
+            if left <= 0:
+                break
+            n = min(len(rec), left)
+            f.write((">%s\n" % (names[i] if names else "rec%d synthetic" % i)).encode())
+            txt = lut[rec[:n]]
+            full = (n // width) * width
+            if full:
+                body = np.empty((full // width, width + 1), dtype=np.uint8)
+                body[:, :width] = txt[:full].reshape(-1, width)
+                body[:, width] = ord("\n")
+                f.write(body.tobytes())
+            if n > full:
+                f.write(txt[full:].tobytes() + b"\n")
+            left -= n
+            done += n
+    return done
+
+
+def write_assays(path: str, assays) -> None:
+    """Assay file of the reference (input.cpp:43-168): name, then F R [P] or P, tab separated."""
+    with open(path, "w") as f:
+        for i, a in enumerate(assays):
+            F, R, P = a[0], a[1], a[2]
+            cols = ["assay%d" % i]
+            if F and R:
+                cols += [F, R]
+            if P:
+                cols.append(P)
+            f.write("\t".join(cols) + "\n")

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(engine_lib):
     assert len(syms) >= 15
     for s in syms:
         assert hasattr(engine_lib, s), s
-    assert engine_lib.tnt_abi_version() == 2
+    assert engine_lib.tnt_abi_version() == 3
 
 
 def test_no_cpu_fallback(engine_lib):

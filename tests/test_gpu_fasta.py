@@ -205,6 +205,41 @@ def test_packed_snapshot_round_trip(engine_lib, oracle, tmp_path):
         bad["info"][3] -= 4                      # fewer words than the fragment table needs
         with pytest.raises(EngineError):
             e.import_packed(bad)
+        # a non-ACGT list that is not strictly ascending, or leaves the base space, is refused as well
+        assert loaded["exc_pos"].size >= 2
+        for damage in ("order", "range", "code"):
+            bad = dict(loaded)
+            bad["exc_pos"] = loaded["exc_pos"].copy()
+            bad["exc_code"] = loaded["exc_code"].copy()
+            if damage == "order":
+                bad["exc_pos"][1] = bad["exc_pos"][0]
+            elif damage == "range":
+                bad["exc_pos"][-1] = int(loaded["info"][5]) + 5
+            else:
+                bad["exc_code"][0] = 2
+            with pytest.raises(EngineError):
+                e.import_packed(bad)
+            e.clear_targets()
+
+
+def test_add_fasta_twice_without_a_read_in_between(eng, oracle):
+    """Two tnt_engine_add_fasta calls back to back (several FASTA files): the pieces of the first call
+    are still queued as device-to-staging copies from the transient code buffer when the second call
+    starts, and must be issued before that buffer is reused."""
+    rng = np.random.default_rng(1331)
+    texts = [gen.rand_fasta(rng, n_records=5, max_len=60000, width=80, iupac=0.005) for _ in range(3)]
+    texts.append(gen.rand_fasta(rng, n_records=2, max_len=900000, width=60))   # grows the code buffer: reserve() path
+    eng.clear_targets()
+    tables = [eng.add_fasta(t, fragment_threshold=20000, overlap=500) for t in texts]   # no read-back in between
+    for text, (recs, frags) in zip(texts, tables):
+        want = oracle.fasta_records(text, threshold=20000, overlap=500)
+        assert len(recs) == len(want)
+        for r, (off, alen, defline, codes, pieces) in zip(recs, want):
+            mine = frags[r.first_fragment:r.first_fragment + r.n_fragments]
+            assert [(f.start, f.stop) for f in mine] == [(p[0], p[1]) for p in pieces]
+            for f, (s0, s1, pc) in zip(mine, pieces):
+                if len(pc):
+                    assert eng.target_codes(f.target_id, 0, f.len).tolist() == np.asarray(pc).tolist()
 
 
 def test_sharded_fasta_ingest_equals_whole(eng):

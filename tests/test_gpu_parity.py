@@ -267,6 +267,7 @@ def test_search_probe_and_padlock(eng, oracle):
         eng.set_assays([Assay(3, F, R, P)])
         got = eng.search(to_opts(o))
         assert_hits_equal(eng, got, want, (F, R, P))
+        assert eng.hit_sequences() == [eng.hit_sequence(h) for h in got]
         total += len(want)
     assert total > 5
 
@@ -285,6 +286,8 @@ def test_search_multi_fragment_multi_assay(eng, oracle):
     got = eng.search(to_opts(o))
     st = eng.stats()
     assert st.alignments > 0 and st.dp_cells > 0 and st.kernel_launches >= 2
+    # the text of all hits in one call == the per-hit calls (which assert_hits_equal checks against the oracle)
+    assert eng.hit_sequences() == [eng.hit_sequence(h) for h in got] and len(got) >= 8
     k = 0
     total = 0
     for t, codes in enumerate(db):
@@ -322,13 +325,34 @@ def test_refuses_unsupported(engine_lib):
         e.set_assays([Assay(0, "A" * 60, "ACGTACGTACGTACGTAC", None)])
         with pytest.raises(EngineError):
             e.search(search_options(min_primer_tm=40.0))
-        e.set_assays([Assay(0, "ACGTACGTACGTACGTAC", "ACGTACGTACGTACGTAC", None)])
-        with pytest.raises(EngineError):  # bounds that accept non-binding sites
-            e.search(search_options())
         with pytest.raises(EngineError):
             e.set_assays([Assay(0, "ACGTACGTACGTACGTAC", None, None)])
     finally:
         e.close()
+
+
+def test_bounds_that_accept_everything(eng, oracle):
+    """The bounds of tntblast.h:31-38 (Tm in [0, 9999], dG in [-9999, 0]) -- what a user gets who only
+    gives e.g. `-x 70`: every seed window with an alignment is a bound site.  Windows without any
+    alignment (Tm = 0, dG = 0 in the reference, reported there with the coordinates of whatever the
+    thread aligned before) are dropped and counted; here every window holds its exact seed word, so
+    none occurs and the hit list equals the oracle's."""
+    from thermonucleotideblast_b200 import Assay
+    rng = np.random.default_rng(515)
+    total = 0
+    for probe in (False, True):
+        codes, F, R, P = gen.make_pcr_case(rng, 30000, n_sites=3, probe=probe)
+        o = H.default_options(max_len=300)
+        assert o.min_primer_tm == 0.0 and o.max_primer_dg == 0.0
+        want = oracle.search(codes, F, R, P, o)
+        eng.clear_targets()
+        eng.add_target(codes)
+        eng.set_assays([Assay(0, F, R, P)])
+        got = eng.search(to_opts(o))
+        assert eng.stats().nonbinding_dropped == 0
+        assert_hits_equal(eng, got, want, (F, R, P))
+        total += len(want)
+    assert total >= 6
 
 
 def test_repeats_and_forced_multi_pass(engine_lib, oracle, monkeypatch):

@@ -120,6 +120,9 @@ def test_fasta_text_shards_hold_whole_records(oracle):
                     parts.append((off + a, alen, defline, codes.tolist(), [(p[0], p[1], p[2].tolist()) for p in pieces]))
             want = [(off, alen, d, c.tolist(), [(p[0], p[1], p[2].tolist()) for p in pcs]) for off, alen, d, c, pcs in whole]
             assert parts == want
+            # every buffer-like input type gives the same cuts
+            for other in (bytearray(text), memoryview(text), np.frombuffer(text, dtype=np.uint8), text.decode("latin-1")):
+                assert shard_fasta_text(other, world) == ranges
 
 
 def _fasta_worker(rank, world, port, q):

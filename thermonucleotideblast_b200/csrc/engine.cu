@@ -296,6 +296,11 @@ struct tnt_engine {
 
 	std::vector<tnt_hit> hits;
 	std::string arena;
+	// text of every hit (tnt_engine_hit_sequences), built on the first request after a search
+	bool seq_ready = false;
+	std::string seq_text;
+	std::vector<uint64_t> seq_off;
+	DevBuf<ExtractItem> d_extract_items;
 	tnt_stats stats{};
 	tnt_search_options last_opt{};
 
@@ -657,7 +662,10 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 	const size_t nslabs = (n + FA_SLAB_BYTES - 1)/FA_SLAB_BYTES;
 	for (int i = 0; i < tnt_engine::FA_BUFS && (size_t)i < nslabs; ++i)
 		if (!e->fa_text[i]) CUDA_OK(cudaMalloc(&e->fa_text[i], FA_SLAB_BYTES));
-	// earlier fragment copies may still read the old codes: reserve() waits for the stream before it frees
+	// Pieces registered by an earlier call are only *queued* (piece_src points into fa_codes) until
+	// their batch is flushed: issue those copies now, before fa_codes is overwritten or replaced
+	// (reserve() then waits for the stream before it frees the old array).
+	flush_batch(e);
 	e->fa_codes.reserve(n + 16, 0, e->up_stream);
 	const uint32_t max_blocks = (uint32_t)((std::min(n, FA_SLAB_BYTES) + FA_BLOCK_BYTES - 1)/FA_BLOCK_BYTES);
 	e->fa_block_map.reserve(max_blocks, 0, e->up_stream);
@@ -739,6 +747,9 @@ void add_fasta(tnt_engine *e, const char *text, size_t nbytes, uint32_t threshol
 		register_known((uint64_t)nbytes, after.bases, final_slab);
 		e->fa_stats.bases = after.bases;
 	}
+	// the queued device-to-staging copies of the last pieces source fa_codes: put them on the stream
+	// before the caller can start another ingest (or anything else that reuses the code buffer)
+	flush_batch(e);
 	e->fa_stats.records = e->fa_records.size();
 	e->fa_stats.fragments = e->fa_fragments.size();
 	e->fa_stats.call_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
@@ -826,10 +837,8 @@ OligoStrand make_os(const tnt_engine *e, int assay_index, int role, bool plus, c
 	s.lean_min_cols = std::getenv("TNT_NO_LEAN_SKIP") ? 0 : lean_min_columns(e->h_thermo, s, min_tm);
 	s.clamp5 = clamp5; s.clamp3 = clamp3;
 	s.max_gap = o.max_gap; s.max_mismatch = o.max_mismatch; s.max_poly_degen = o.max_poly_degen;
-	// A window without any alignment has Tm = 0 and dG = 0 in the reference and is then
-	// reported with stale coordinates.  Bounds that would let it through are refused.
-	if (min_tm <= 0.0f && max_tm >= 0.0f && min_dg <= 0.0f && max_dg >= 0.0f)
-		throw std::runtime_error("search bounds accept non-binding sites (Tm = 0, dG = 0): set a minimum Tm > 0 or a maximum dG < 0");
+	// Bounds that accept Tm = 0 and dG = 0 also accept windows without any alignment; the kernels
+	// drop those and count them (finish_alignment, tnt_stats::nonbinding_dropped).
 	return s;
 }
 
@@ -1182,9 +1191,11 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		retry_total += counts[s];
 	}
 	if (retry_total >= ((uint64_t)1 << 32)) throw std::runtime_error("internal: hand-over list too large");
-	// snapshot of the DP-cell counter so that a retried pass is not counted twice
+	// snapshot of the DP-cell and dropped-window counters so that a retried pass is not counted twice
 	unsigned long long cells_before = 0;
+	uint32_t nonbinding_before = 0;
 	CUDA_OK(cudaMemcpyAsync(&cells_before, e->d_cells.p, sizeof(cells_before), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaMemcpyAsync(&nonbinding_before, e->d_out_count.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 
 	for (;;) {
@@ -1197,7 +1208,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		poke(e->d_retry_ctl.p, retry_ctl.data(), 2*nos*sizeof(uint32_t), e->stream, &e->stats.kernel_launches);
 		CUDA_OK(cudaMemsetAsync(e->d_retry_ctl.p + 2*nos, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 		{
-			const uint32_t init[3] = {base_count, 0, 0};
+			const uint32_t init[4] = {base_count, 0, 0, nonbinding_before};
 			poke(e->d_out_count.p, init, sizeof(init), e->stream, &e->stats.kernel_launches);
 		}
 		poke(e->d_cells.p, &cells_before, sizeof(cells_before), e->stream, &e->stats.kernel_launches);
@@ -1578,6 +1589,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 {
 	CUDA_OK(cudaSetDevice(e->prm.device));
 	e->hits.clear();
+	e->seq_ready = false;
 	e->arena.clear();
 	e->arena.push_back('\0'); // offset 0 == empty string
 	e->stats = tnt_stats{};
@@ -1588,6 +1600,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	e->settle_upload();
 	e->sync_targets(false);
 	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
+	CUDA_OK(cudaMemsetAsync(e->d_out_count.p + 3, 0, sizeof(uint32_t), e->stream));
 	cudaEvent_t t_begin = e->ev[4], t_end = e->ev[5];
 	CUDA_OK(cudaEventRecord(t_begin, e->stream));
 
@@ -1704,9 +1717,12 @@ void search(tnt_engine *e, const tnt_search_options &o)
 
 	CUDA_OK(cudaEventRecord(t_end, e->stream));
 	unsigned long long cells = 0;
+	uint32_t nonbinding = 0;
 	CUDA_OK(cudaMemcpyAsync(&cells, e->d_cells.p, sizeof(cells), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaMemcpyAsync(&nonbinding, e->d_out_count.p + 3, sizeof(nonbinding), cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	e->stats.dp_cells = cells;
+	e->stats.nonbinding_dropped = nonbinding;
 	float ms = 0;
 	CUDA_OK(cudaEventElapsedTime(&ms, t_begin, t_end));
 	e->stats.total_ms = ms;
@@ -1821,6 +1837,75 @@ long hit_sequence(tnt_engine *e, const tnt_hit *h, char *out, size_t cap)
 		out[m] = '\0';
 	}
 	return (long)s.size();
+}
+
+// Text of all hits of the last search: the fragment ranges are read back from the packed database
+// with one kernel and one device-to-host copy, the strings are built on a few host threads.
+void hit_sequences(tnt_engine *e)
+{
+	if (e->seq_ready) return;
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	e->sync_targets();
+	const size_t n = e->hits.size();
+	struct Plan { int start, stop, lo; SeqMode mode; uint32_t m; uint64_t off; };
+	std::vector<Plan> plan(n);
+	std::vector<ExtractItem> items;
+	items.reserve(n);
+	uint64_t total = 0, text_total = 0;
+	for (size_t i = 0; i < n; ++i) {
+		const tnt_hit &h = e->hits[i];
+		if (h.target_id >= e->targets.size()) throw std::runtime_error("bad target id");
+		const Target &tg = e->targets[h.target_id];
+		Plan &p = plan[i];
+		hit_sequence_plan(h, e->last_opt.assay_format, p.start, p.stop, p.mode);
+		if (p.stop < p.start) throw std::runtime_error("hit with start > stop");
+		const int lo = std::max(p.start, 0), hi = (int)std::min<int64_t>(p.stop, (int64_t)tg.len - 1);
+		p.lo = lo;
+		p.m = hi >= lo ? (uint32_t)(hi - lo + 1) : 0u;
+		p.off = total;
+		if (p.m) items.push_back(ExtractItem{h.target_id, (uint32_t)lo, p.m, 0u, total});
+		total += p.m;
+		text_total += (uint64_t)(p.stop - p.start + 1) + 1;
+	}
+	std::vector<uint8_t> codes(total);
+	if (total) {
+		e->d_extract_items.upload(items, e->stream);
+		e->d_extract.reserve(total, 0, e->stream);
+		k_extract_many<<<(unsigned)std::min<size_t>(items.size(), (size_t)e->sm_count*16), 256, 0, e->stream>>>(e->view(),
+			e->d_extract_items.p, (uint32_t)items.size(), e->d_extract.p);
+		CUDA_OK(cudaGetLastError());
+		e->stats.kernel_launches++;
+		CUDA_OK(cudaMemcpyAsync(codes.data(), e->d_extract.p, total, cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		e->stats.d2h_bytes += total;
+	}
+	e->seq_off.assign(n + 1, 0);
+	for (size_t i = 0; i < n; ++i) e->seq_off[i + 1] = e->seq_off[i] + (uint64_t)(plan[i].stop - plan[i].start + 1) + 1;
+	e->seq_text.assign(text_total, '\0');
+	auto work = [&](size_t lo, size_t hi) {
+		std::vector<uint8_t> tmp;
+		for (size_t i = lo; i < hi; ++i) {
+			const Plan &p = plan[i];
+			tmp.assign(codes.begin() + (ptrdiff_t)p.off, codes.begin() + (ptrdiff_t)(p.off + p.m));
+			const std::string s = render_hit_sequence(p.start, p.stop, p.mode, (int)e->targets[e->hits[i].target_id].len, p.lo, tmp);
+			std::memcpy(&e->seq_text[e->seq_off[i]], s.data(), s.size());
+		}
+	};
+	const unsigned nthreads = n < 4096 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+	if (nthreads == 1) work(0, n);
+	else {
+		std::vector<std::thread> pool;
+		std::vector<std::string> errors(nthreads);
+		const size_t per = (n + nthreads - 1)/nthreads;
+		for (unsigned t = 0; t < nthreads; ++t)
+			pool.emplace_back([&, t]() {
+				try { work(std::min(n, t*per), std::min(n, (t + 1)*per)); }
+				catch (const std::exception &ex) { errors[t] = ex.what(); }
+			});
+		for (std::thread &t : pool) t.join();
+		for (const std::string &err : errors) if (!err.empty()) throw std::runtime_error(err);
+	}
+	e->seq_ready = true;
 }
 
 } // namespace
@@ -1977,7 +2062,8 @@ int tnt_engine_import_packed(tnt_engine *e, const tnt_packed_info *info, const t
 	if (info->n_targets >= (1u << 24)) throw std::runtime_error("tnt_engine_import_packed: too many fragments (limit 2^24)");
 	if ((info->n_targets && !targets) || (info->n_words && (!db2 || !nmask)) || (info->n_exceptions && (!exc_pos || !exc_code)))
 		throw std::runtime_error("null argument");
-	// consistency of the fragment table with the arrays (a damaged file must not turn into wild reads)
+	// consistency of the fragment table and the non-ACGT list with the arrays (a damaged file must
+	// not turn into wild reads)
 	uint64_t prev_end = 0, bases = 0;
 	for (uint64_t i = 0; i < info->n_targets; ++i) {
 		const tnt_packed_target &t = targets[i];
@@ -1988,6 +2074,13 @@ int tnt_engine_import_packed(tnt_engine *e, const tnt_packed_info *info, const t
 	}
 	if ((info->next_base + 31u)/32u > info->n_words || bases != info->total_bases)
 		throw std::runtime_error("tnt_engine_import_packed: inconsistent sizes");
+	// the sparse list is binary-searched and then walked entry by entry (load_window): it has to be
+	// strictly ascending, inside the base space, with codes of the non-ACGT range; the device side
+	// additionally never reads past the list, whatever the mask words say
+	for (uint64_t i = 0; i < info->n_exceptions; ++i) {
+		if (exc_pos[i] >= info->next_base || (i && exc_pos[i] <= exc_pos[i - 1]) || exc_code[i] < 4 || exc_code[i] > 17)
+			throw std::runtime_error("tnt_engine_import_packed: inconsistent non-ACGT list");
+	}
 	CUDA_OK(cudaSetDevice(e->prm.device));
 	CUDA_OK(cudaStreamSynchronize(e->stream)); // nothing may still read arrays that reserve() replaces
 	e->db2.reserve(info->n_words + 8, 0, e->up_stream);
@@ -2105,6 +2198,7 @@ int tnt_engine_clear_targets(tnt_engine *e)
 	e->total_bases = 0;
 	e->targets_dirty = true;
 	e->hits.clear();
+	e->seq_ready = false;
 	API_END
 }
 
@@ -2198,6 +2292,17 @@ long tnt_engine_hit_sequence(tnt_engine *e, const tnt_hit *hit, char *out, size_
 	}
 	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
 	catch (...) { g_error = "unknown error"; return -1; }
+}
+
+int tnt_engine_hit_sequences(tnt_engine *e, const char **text, const uint64_t **offsets, size_t *n_hits)
+{
+	API_BEGIN
+	if (!e) throw std::runtime_error("null argument");
+	hit_sequences(e);
+	if (text) *text = e->seq_text.data();
+	if (offsets) *offsets = e->seq_off.data();
+	if (n_hits) *n_hits = e->hits.size();
+	API_END
 }
 
 long tnt_engine_seeds(tnt_engine *e, uint32_t target_id, const char *oligo, int32_t plus_strand,

@@ -172,7 +172,8 @@ __device__ inline int exception_code(const DbView &db, const Target &tg, uint64_
 		if (v < g) lo = mid + 1;
 		else hi = mid;
 	}
-	return (int)__ldg(db.exc_code + lo);
+	// a mask bit without a list entry (damaged snapshot) reads as N instead of past the array
+	return lo < db.nexc ? (int)__ldg(db.exc_code + lo) : 15;
 }
 
 // Load the NucCruc target for the window [start, stop) of a fragment
@@ -196,7 +197,7 @@ __device__ inline int load_window(const DbView &db, const Target &tg, uint32_t s
 				}
 				exc_at = lo;
 			}
-			code = (int)__ldg(db.exc_code + exc_at);
+			code = exc_at < db.nexc ? (int)__ldg(db.exc_code + exc_at) : 15; // never past the list (damaged snapshot)
 			++exc_at;
 			if (code > 15) continue; // DB_GAP / DB_UNKNOWN are skipped silently
 		}
@@ -771,7 +772,15 @@ __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, 
 		anchor3 = nc_anchor3(sh, tgt, Lt, best_aln);
 		nc_counts(sh, best_aln, mm, gaps, poly);
 	}
-	else if (want) mm = (unsigned)os.len; // no alignment at all: refused by the host-side bounds check
+	else if (want) mm = (unsigned)os.len;
+	// A window without any alignment has Tm = 0 and dG = 0 in the reference; bounds that accept those
+	// values let it through there with whatever coordinates the thread's previous valid alignment
+	// left behind (alignment::clear() keeps first_match / last_match, nuc_cruc.h:360-371).  Such a
+	// window is not a binding site: it is dropped and counted (tnt_stats::nonbinding_dropped).
+	if (!best.valid && pass && !a.emit_all) {
+		atomicAdd(a.out_count + 3, 1u);
+		pass = false;
+	}
 	if (pass) pass = anchor5 >= os.clamp5;
 	if (pass) pass = anchor3 >= os.clamp3;
 	if (pass) pass = mm <= os.max_mismatch;
@@ -1300,6 +1309,24 @@ __global__ void k_extract_codes(DbView db, uint32_t target, uint32_t start, uint
 		int code = (int)((__ldg(db.db2 + (g >> 5)) >> ((g & 31u)*2u)) & 3u);
 		if ((__ldg(db.nmask + (g >> 5)) >> (g & 31u)) & 1u) code = exception_code(db, tg, g);
 		out[i] = (uint8_t)code;
+	}
+}
+
+// The same for many ranges at once (tnt_engine_hit_sequences: the text of every hit of a search
+// with one launch and one device-to-host copy): one CTA per range, grid-stride.
+struct ExtractItem { uint32_t target, start, n, pad; uint64_t out_off; };
+
+__global__ void __launch_bounds__(256) k_extract_many(DbView db, const ExtractItem *__restrict__ items, uint32_t nitems, uint8_t *__restrict__ out)
+{
+	for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+		const ExtractItem x = items[it];
+		const Target tg = db.targets[x.target];
+		for (uint32_t i = threadIdx.x; i < x.n; i += blockDim.x) {
+			const uint64_t g = tg.base + x.start + i;
+			int code = (int)((__ldg(db.db2 + (g >> 5)) >> ((g & 31u)*2u)) & 3u);
+			if ((__ldg(db.nmask + (g >> 5)) >> (g & 31u)) & 1u) code = exception_code(db, tg, g);
+			out[x.out_off + i] = (uint8_t)code;
+		}
 	}
 }
 

@@ -90,7 +90,8 @@ class Stats(C.Structure):
                 ("dp_cells", C.c_uint64), ("bound_sites", C.c_uint64), ("hits", C.c_uint64),
                 ("kernel_launches", C.c_uint64),
                 ("scan_ms", C.c_double), ("align_ms", C.c_double), ("pair_ms", C.c_double),
-                ("total_ms", C.c_double), ("scan_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("total_ms", C.c_double), ("scan_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("nonbinding_dropped", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -198,6 +199,7 @@ def load_library() -> C.CDLL:
     L.tnt_engine_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.tnt_engine_hit_sequence.argtypes = [vp, C.POINTER(CHit), C.c_char_p, C.c_size_t]
     L.tnt_engine_hit_sequence.restype = C.c_long
+    L.tnt_engine_hit_sequences.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_size_t)]
     L.tnt_engine_seeds.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, u32p, u32p, C.c_long]
     L.tnt_engine_seeds.restype = C.c_long
     L.tnt_engine_align.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, C.c_float, u32p, u32p,
@@ -424,6 +426,22 @@ class Engine:
         buf = C.create_string_buffer(n + 1)
         self.L.tnt_engine_hit_sequence(self.h, C.byref(raw), buf, n + 1)
         return buf.value.decode()
+
+    def hit_sequences(self) -> List[str]:
+        """Amplicon / probe-site text of every hit of the last search (tnt_engine_hit_sequences: one
+        kernel launch and one device-to-host copy for all of them)."""
+        n, text, offs = self.hit_sequences_raw()
+        return [text[offs[i]:offs[i + 1] - 1].decode() for i in range(n)]
+
+    def hit_sequences_raw(self):
+        """(n_hits, text bytes, offsets) as the C ABI hands them out."""
+        text = C.c_void_p()
+        offs = C.POINTER(C.c_uint64)()
+        n = C.c_size_t()
+        self._check(self.L.tnt_engine_hit_sequences(self.h, C.byref(text), C.byref(offs), C.byref(n)))
+        o = [offs[i] for i in range(n.value + 1)] if n.value else [0]
+        buf = C.string_at(text.value, o[-1]) if o[-1] else b""
+        return n.value, buf, o
 
     def oligo_dimer(self, query: str, target: Optional[str] = None, conc_a: float = 9.0e-7, conc_b: float = 9.0e-7) -> AlignResult:
         """Homodimer (target None) or heterodimer Tm of oligos (tntblast_local.cpp:657-686) on the device."""

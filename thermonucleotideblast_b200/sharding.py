@@ -71,7 +71,12 @@ def shard_fasta_text(text, world_size: int) -> List[Tuple[int, int]]:
     byte marks; a rank may get an empty range when there are fewer records than ranks."""
     if world_size < 1:
         raise ValueError("world_size must be >= 1")
-    data = text if isinstance(text, (bytes, bytearray, memoryview)) else bytes(text)
+    if isinstance(text, str):
+        data = text.encode("latin-1")
+    elif isinstance(text, (bytes, bytearray)):
+        data = text
+    else:
+        data = bytes(text)  # memoryview, numpy uint8 array, anything with the buffer protocol
     n = len(data)
     first = data.find(b">")
     if first < 0:
