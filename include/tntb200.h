@@ -52,8 +52,15 @@ typedef struct {
 	int32_t dinkelbach;  /* must be 0: the iterative Tm mode is not implemented */
 	int32_t word_size;   /* hash word size W, 3..8, default 7 (tntblast.h:68) */
 	int32_t device;      /* CUDA device ordinal */
-	int32_t reserved;
+	int32_t reserved;    /* flags, TNT_ENGINE_*; 0 = behave exactly like the reference */
 } tnt_engine_params;
+
+/* amplicon() culls its match list between the binding steps (cull_oligo_match,
+ * amplicon_search.cpp:679-765).  When two bound sites of one assay overlap (e.g. a primer that
+ * binds both strands of a palindromic site), the cull's mixed ordering can drop a site that is part
+ * of a real amplicon.  By default the engine reproduces this (the affected groups are searched again
+ * step by step like the reference does); with this flag it reports every amplicon its sites allow. */
+#define TNT_ENGINE_KEEP_CULLED_SITES 1
 
 /* Scalars the reference passes to amplicon()/padlock()/hybrid() on every call
  * (tntblast.h:409-472; values from Options, options.h:25-76). */
@@ -125,6 +132,8 @@ typedef struct {
 	double scan_ms, align_ms, pair_ms, total_ms;   /* device time (CUDA events) */
 	uint64_t scan_bytes;             /* algorithmic bytes of the seed scan */
 	uint64_t d2h_bytes;              /* result bytes copied device -> host by the search (counters excluded) */
+	uint64_t replayed_groups;        /* (fragment, assay) groups searched again step by step like amplicon() does
+	                                  * (its culls can lose a site there, see TNT_ENGINE_KEEP_CULLED_SITES) */
 	uint64_t nonbinding_dropped;     /* windows without any alignment (Tm = 0, dG = 0) that the bounds would have
 	                                  * accepted: the reference reports them with the coordinates of an earlier
 	                                  * alignment (nuc_cruc.h:360-371); the engine drops and counts them */

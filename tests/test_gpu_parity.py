@@ -355,6 +355,77 @@ def test_bounds_that_accept_everything(eng, oracle):
     assert total >= 6
 
 
+def test_cull_anomaly_is_reproduced(engine_lib, oracle, monkeypatch):
+    """SURVEY 8a row C1.  cull_oligo_match (amplicon_search.cpp:679-765) sorts bound sites by loc_5 and
+    unbound seeds by seed position in one list and ends its partner scan on an unsigned seed
+    distance; when a primer binds both strands of a palindromic site the two bound sites overlap
+    and the reference loses the amplicon that the later one opens.  Two such neighbourhoods from the
+    config-5 data (tests/golden/cull_cases.json, answers recorded from the compiled reference): the
+    engine reproduces the reference by default, and reports the lost amplicon as well when asked to
+    keep culled sites."""
+    import json
+    import os
+    from thermonucleotideblast_b200 import Assay, Engine
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cull_cases.json")))
+    for c in cases:
+        codes = gen.str_to_codes(c["codes"])
+        F, R = c["forward"], c["reverse"]
+        o = H.default_options(min_primer_tm=c["min_primer_tm"])
+        want = oracle.search(codes, F, R, None, o)
+        assert [(h.amp_first, h.amp_last) for h in want] == [(h["amp_first"], h["amp_last"]) for h in c["reference_hits"]]
+        lost = tuple(c["lost_amplicon"])
+        with Engine() as e:
+            e.add_target(codes)
+            e.set_assays([Assay(0, F, R, None)])
+            got = e.search(to_opts(o))
+            assert e.stats().replayed_groups == 1
+            assert_hits_equal(e, got, want, (F, R, None))
+            assert lost not in [(h.amp_first, h.amp_last) for h in got]
+        with Engine(keep_culled_sites=True) as e:
+            e.add_target(codes)
+            e.set_assays([Assay(0, F, R, None)])
+            more = e.search(to_opts(o))
+            assert e.stats().replayed_groups == 0
+            coords = [(h.amp_first, h.amp_last) for h in more]
+            assert lost in coords and set((h.amp_first, h.amp_last) for h in got) < set(coords)
+
+
+def test_replay_of_every_group_changes_nothing(engine_lib, oracle, monkeypatch):
+    """The step-by-step replay (every seed of the group aligned, the reference's list operations
+    followed literally) applied to *every* group with a hit must give what the selective default
+    gives -- and what the oracle gives."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(60221)
+    db = [gen.random_codes(int(rng.integers(30000, 60000)), rng) for _ in range(5)]
+    gen.sprinkle_degenerate(db[1], rng, frac=1e-3, n_runs_per_50kb=3)
+    # planted copies with indels bind through two seed diagonals (duplicate sites: replayed by default);
+    # exact copies alone leave nothing for the culls to confuse (not replayed unless forced)
+    assays = gen.make_assays(rng, db, 4, "taqman", variants=3) + gen.make_assays(rng, db, 4, "pcr", variants=3) + \
+        gen.make_assays(rng, db, 4, "taqman", variants=0) + gen.make_assays(rng, db, 4, "pcr", variants=0)
+    o = H.default_options(min_primer_tm=38.0, min_probe_tm=38.0, max_len=1000)
+
+    def run():
+        with Engine() as e:
+            e.add_targets(db)
+            e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+            hits = e.search(to_opts(o))
+            return [(h.target_id, h.assay_index) + hit_key(e, h, assays[h.assay_index]) + hit_floats(h) for h in hits], e.stats().replayed_groups
+
+    base, n_default = run()
+    monkeypatch.setenv("TNT_REPLAY_ALL", "1")
+    forced, n_forced = run()
+    assert forced == base and len(base) >= 12
+    assert n_forced >= 12 and n_forced >= n_default + 8   # the eight exact-copy assays
+    k = 0
+    for t, codes in enumerate(db):
+        for i, a in enumerate(assays):
+            want = oracle.search(codes, a[0], a[1], a[2], o)
+            mine = [x for x in forced if x[0] == t and x[1] == i]
+            assert [x[2:2 + len(w.exact_key())] for x, w in zip(mine, want)] == [w.exact_key() for w in want] and len(mine) == len(want)
+            k += len(want)
+    assert k == len(forced)
+
+
 def test_repeats_and_forced_multi_pass(engine_lib, oracle, monkeypatch):
     """Low-complexity / tandem-repeat fragments overflow the seed buckets (estimated for random
     sequence): the engine has to shrink the pass and retry, and the result must not change.  A tiny

@@ -51,11 +51,18 @@ def run_pair(tmp_path, records, assays, flags, limit_bp=None, threads=None, env_
     info = dict(zip(("prefetched", "fragments", "bases", "batches", "alignments", "hits", "device_ms", "table", "direct"),
                     [float(x) for x in m.groups()]))
     a, b = open(out_ref, "rb").read(), open(out_gpu, "rb").read()
+    keep = os.environ.get("TNT_SHIM_KEEP")   # debugging aid: keep differing outputs (e.g. under gpurun_out/)
+    if keep and a != b:
+        os.makedirs(keep, exist_ok=True)
+        import shutil
+        shutil.copy(out_ref, os.path.join(keep, tmp_path.name + ".ref.out"))
+        shutil.copy(out_gpu, os.path.join(keep, tmp_path.name + ".gpu.out"))
     # the stdout summary (counts, Tm / dG / length ranges of all matches) has to agree as well, apart
     # from the elapsed-time line and the progress meter
     def summary(s):
         s = s[s.index("Found"):] if "Found" in s else s
-        keep = [ln for ln in s.splitlines() if not ln.startswith("Search completed") and not ln.startswith("Searching database")]
+        keep = [ln for ln in s.splitlines() if not ln.startswith("Search completed") and not ln.startswith("Searching database")
+                and not ln.startswith("\tOutput = ")]
         return "\n".join(keep)
     assert summary(r.stdout) == summary(g.stdout)
     return a, b, info, used
@@ -82,7 +89,7 @@ def test_config1_single_pcr_pair_5mbp_full(tmp_path):
     records = [gen.random_codes(5_000_000, rng)]
     assays = gen.make_assays(np.random.default_rng(11), records, 1, "pcr", lens=(20, 20, 25), amp=(450, 550), variants=6)
     a, b, info, used = run_pair(tmp_path, records, assays, ["-e", "40"])
-    assert used == 5_000_000 and info["fragments"] == 10
+    assert used == 5_000_000 and info["fragments"] >= 10   # cut by the byte length of the FASTA record
     check_identical(a, b, info, 2)
 
 

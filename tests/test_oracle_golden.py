@@ -186,3 +186,20 @@ def test_oligo_dimers_vs_compiled_reference(oracle, ref):
         assert (a.tm, a.dH, a.dS, a.dG, a.valid) == (b.tm, b.dH, b.dS, b.dG, b.valid)
         if t:
             assert a.alignment == b.alignment
+
+
+def test_cull_anomaly_cases(oracle):
+    """Two neighbourhoods of the config-5 data in which the reference's cull loses a real amplicon
+    (tests/golden/make_cull_cases.py): the oracle has to report what the compiled reference reported,
+    i.e. without the lost amplicon."""
+    cases = load("cull_cases.json")
+    assert len(cases) == 2
+    for c in cases:
+        codes = gen.str_to_codes(c["codes"])
+        o = H.default_options(min_primer_tm=c["min_primer_tm"])
+        hits = oracle.search(codes, c["forward"], c["reverse"], None, o)
+        got = [{"amp_first": h.amp_first, "amp_last": h.amp_last, "primer_strand": h.primer_strand,
+                "forward_tm": float(np.float32(h.forward_tm)), "reverse_tm": float(np.float32(h.reverse_tm)),
+                "forward_align": h.forward_align.decode(), "reverse_align": h.reverse_align.decode()} for h in hits]
+        assert got == c["reference_hits"]
+        assert tuple(c["lost_amplicon"]) not in [(h.amp_first, h.amp_last) for h in hits]

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <list>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -124,6 +125,9 @@ void unique_sites(std::vector<const BoundSite *> &v, bool mask_variant)
 	v.resize(m);
 }
 
+void join_pcr_sorted(const std::vector<const BoundSite *> &all, int assay_index, int assay_id, bool has_probe,
+	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
+
 void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int assay_id, bool has_probe,
 	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
@@ -158,6 +162,13 @@ void join_pcr(const std::vector<const BoundSite *> &group, int assay_index, int 
 		return a->loc5 < b->loc5;
 	});
 
+	join_pcr_sorted(all, assay_index, assay_id, has_probe, opt, base, hits, refs);
+}
+
+// The final F x R (x P) loops of amplicon() over the list in its final order (amplicon_search.cpp:355-674)
+void join_pcr_sorted(const std::vector<const BoundSite *> &all, int assay_index, int assay_id, bool has_probe,
+	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
+{
 	const bool apply_mmc = opt.min_max_primer_clamp >= 0;
 	const unsigned mmc = apply_mmc ? (unsigned)opt.min_max_primer_clamp : 0u;
 
@@ -370,6 +381,175 @@ void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &o
 		hits.insert(hits.end(), part_hits[t].begin(), part_hits[t].end());
 		refs.insert(refs.end(), part_refs[t].begin(), part_refs[t].end());
 	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Replay of amplicon()'s staged bind / cull sequence (amplicon_search.cpp:92-355)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+enum : uint8_t { M_F = 1, M_R = 2, M_P = 4, M_PLUS = 8, M_MINUS = 16, M_VALID = 32 }; // oligo_info, tntblast.h:147-154
+
+struct El {                       // oligo_info (tntblast.h:145-243) without the alignment text
+	int loc5 = 0, loc3 = 0;
+	float tm = -1.0f;
+	int num_mm = 0;
+	uint32_t align_len = 0;
+	uint32_t q = 0, t = 0;
+	uint8_t mask = 0;
+	int site = -1;
+};
+
+bool less_oligo_loc(const El &a, const El &b) // sort_by_oligo_loc, amplicon_search.cpp:12-26
+{
+	if (!(a.loc5 + a.loc3) || !(b.loc5 + b.loc3)) return a.t < b.t;
+	if (a.loc5 == b.loc5) return a.loc3 < b.loc3;
+	return a.loc5 < b.loc5;
+}
+
+bool less_bound_match(const El &a, const El &b) // sort_by_bound_match, bind_oligo.cpp:49-82
+{
+	if (a.loc5 != b.loc5) return a.loc5 < b.loc5;
+	if (a.loc3 != b.loc3) return a.loc3 < b.loc3;
+	if (a.tm == b.tm) {
+		if (a.num_mm == b.num_mm) return a.align_len > b.align_len;
+		return a.num_mm > b.num_mm;
+	}
+	return a.tm > b.tm;
+}
+
+// cull_oligo_match (amplicon_search.cpp:679-765), unsigned wrap of the seed distance included.  The
+// strand counts are taken from the element *after* each kept one, as the reference does (:748-753;
+// its read of end() counts as neither strand).
+void cull(std::list<El> &l, unsigned max_amplicon_len, bool has_probe, bool single_primer_pcr, unsigned *n_minus, unsigned *n_plus)
+{
+	const unsigned threshold = max_amplicon_len + 50;
+	l.sort(less_oligo_loc);
+	for (El &e : l) e.mask &= (uint8_t)~M_VALID;
+	for (auto f = l.begin(); f != l.end(); ++f) {
+		if (f->mask & (M_PLUS | M_P)) continue;
+		auto r = f;
+		for (++r; r != l.end(); ++r) {
+			if ((unsigned)(r->t - f->t) > threshold) break;
+			if (r->mask & (M_MINUS | M_P)) continue;
+			if (!single_primer_pcr && ((f->mask & (M_R | M_F)) == (r->mask & (M_R | M_F)))) continue;
+			if (has_probe) {
+				auto p = f;
+				for (++p; p != r; ++p)
+					if (p->mask & M_P) { p->mask |= M_VALID; f->mask |= M_VALID; r->mask |= M_VALID; }
+			}
+			else { f->mask |= M_VALID; r->mask |= M_VALID; }
+		}
+	}
+	unsigned cm = 0, cp = 0;
+	for (auto i = l.begin(); i != l.end();) {
+		if (i->mask & M_VALID) {
+			++i;
+			const uint8_t next = i != l.end() ? i->mask : (uint8_t)0;
+			cm += (next & M_MINUS) ? 1u : 0u;
+			cp += (next & M_PLUS) ? 1u : 0u;
+			continue;
+		}
+		i = l.erase(i);
+	}
+	if (n_minus) *n_minus = cm;
+	if (n_plus) *n_plus = cp;
+}
+
+// bind_oligo_to_{minus,plus}_strand, mask variant (bind_oligo.cpp:456-827, :1159-1530): the elements
+// of one (oligo, strand) leave the list; those whose window passes every filter come back as bound
+// sites, one per (loc_5, loc_3), behind everything else.
+void bind_masked(std::list<El> &l, uint8_t want, const std::vector<BoundSite> &sites)
+{
+	std::list<El> cur;
+	for (auto it = l.begin(); it != l.end();) {
+		if ((it->mask & want) != want) { ++it; continue; }
+		El e = *it;
+		it = l.erase(it);
+		if (e.site < 0) continue;
+		const BoundSite &b = sites[(size_t)e.site];
+		e.loc5 = b.loc5; e.loc3 = b.loc3;
+		e.tm = b.tm;
+		e.num_mm = b.num_mm;
+		e.align_len = b.align_len;
+		cur.push_front(e);
+	}
+	if (cur.empty()) return;
+	cur.sort(less_bound_match);
+	l.push_back(cur.front());
+	cur.pop_front();
+	while (!cur.empty()) {
+		if (l.back().loc5 != cur.front().loc5 || l.back().loc3 != cur.front().loc3) l.push_back(cur.front());
+		cur.pop_front();
+	}
+}
+
+} // namespace
+
+void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
+	bool has_probe, int assay_index, int assay_id, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
+{
+	// match_oligo_to_*_strand (bind_oligo.cpp:84-122): per (oligo, strand) one seed per diagonal,
+	// ordered by q - t; the merge of all-unbound lists is an append
+	std::stable_sort(seeds.begin(), seeds.end(), [](const ReplaySeed &a, const ReplaySeed &b) {
+		if (a.cat != b.cat) return a.cat < b.cat;
+		return ((int)a.q - (int)a.t) < ((int)b.q - (int)b.t);
+	});
+	static const uint8_t kMask[6] = {M_F | M_MINUS, M_R | M_MINUS, M_F | M_PLUS, M_R | M_PLUS, M_P | M_MINUS, M_P | M_PLUS};
+	std::list<El> ml;
+	size_t k = 0;
+	auto append = [&](int cat) {
+		for (; k < seeds.size() && seeds[k].cat == cat; ++k) {
+			El e;
+			e.q = seeds[k].q; e.t = seeds[k].t;
+			e.mask = kMask[cat];
+			e.site = seeds[k].site;
+			ml.push_back(e);
+		}
+	};
+	append(0); append(1);
+	const size_t n_minus = ml.size();
+	if (n_minus == 0) return;                       // amplicon_search.cpp:103-105
+	append(2); append(3);
+	const size_t n_plus = ml.size();
+	if (n_plus == n_minus) return;                  // :113-115
+	if (has_probe) {
+		append(4); append(5);
+		if (ml.size() == n_plus) return;            // :123-125
+	}
+
+	unsigned cm = 0, cp = 0;
+	cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, &cm, &cp);
+	const bool first_plus = !(cm < cp);             // :131 vs :218
+	for (int stage = 0; stage < 4; ++stage) {
+		const bool plus = (stage < 2) ? first_plus : !first_plus;
+		const bool is_r = stage & 1;
+		bind_masked(ml, (uint8_t)((is_r ? M_R : M_F) | (plus ? M_PLUS : M_MINUS)), sites);
+		if (stage < 3) {
+			cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
+			// early exits at :153, :177, :240, :264, :288 -- none after the third bind of the minus-first path (:199)
+			if (ml.empty() && !(stage == 2 && !first_plus)) return;
+		}
+	}
+	if (has_probe) {
+		cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
+		if (ml.empty()) return;
+		bind_masked(ml, (uint8_t)(M_P | M_MINUS), sites);
+		bind_masked(ml, (uint8_t)(M_P | M_PLUS), sites);
+	}
+	ml.sort(less_oligo_loc);                        // :353
+	std::vector<const BoundSite *> all;
+	all.reserve(ml.size());
+	for (const El &e : ml) if (e.site >= 0) all.push_back(&sites[(size_t)e.site]);
+	join_pcr_sorted(all, assay_index, assay_id, has_probe, opt, sites.data(), hits, refs);
+}
+
+bool hit_order_is_safe(const BoundSite &f, const BoundSite &r, const BoundSite *p, uint32_t max_len)
+{
+	const uint32_t threshold = max_len + 50;
+	if (!(f.target_loc < r.target_loc) || r.target_loc - f.target_loc > threshold) return false;
+	if (p && !(f.target_loc < p->target_loc && p->target_loc < r.target_loc)) return false;
+	return true;
 }
 
 void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop, SeqMode &mode)

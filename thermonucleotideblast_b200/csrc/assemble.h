@@ -45,6 +45,30 @@ void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &o
 	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
 	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
 
+// ---- exact replay of the reference's staged PCR search for one (fragment, assay) group ----------
+// amplicon() binds the four primer categories one after the other and culls its match list in
+// between (amplicon_search.cpp:131-355).  The cull sorts a list of bound sites and not-yet-bound
+// seeds with a comparator that is no strict weak ordering once the two kinds mix, and ends its
+// partner scan on an unsigned difference of seed positions (:12-26, :709): when two bound sites
+// of one assay overlap, a site that is part of a real amplicon can be dropped.  For the groups
+// where that can happen the engine aligns *every* seed of the group and hands seeds + bound sites
+// to this function, which walks through the reference's sequence of list operations literally
+// (std::list and its sort included: the outcome depends on the merge order).
+struct ReplaySeed {
+	int cat;             // 0 F-minus, 1 R-minus, 2 F-plus, 3 R-plus, 4 P-minus, 5 P-plus
+	uint32_t q, t;       // seed: word index (oligo_info::query_loc), target position
+	int site;            // index into `sites` when the seed's window passes every filter, else -1
+};
+
+void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
+	bool has_probe, int assay_index, int assay_id, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
+
+// Can the reference's culls lose this amplicon although every site binds?  Not if the seed
+// positions of its sites are ordered like the sites themselves and within reach of each other
+// (then the sites mark each other valid in every cull, whichever of them are bound at that
+// point) -- provided no other bound site of the group sits close by (k_crowd).
+bool hit_order_is_safe(const BoundSite &minus_primer, const BoundSite &plus_primer, const BoundSite *probe, uint32_t max_len);
+
 enum class SeqMode { PcrPlus, PcrMinus, ProbePlus, ProbeMinus, PadlockMinusStrand, PadlockPlusStrand };
 
 void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop, SeqMode &mode);

@@ -289,8 +289,14 @@ struct tnt_engine {
 	DevBuf<int32_t> d_p5;
 	DevBuf<uint8_t> d_extract;
 
+	// exact replay of the reference's staged PCR search (groups where its culls can lose a site)
+	DevBuf<uint32_t> d_crowd_bits;
+	DevBuf<uint64_t> d_crowd_out;
+	DevBuf<CandSpan> d_spans;
+	DevBuf<ReplaySeedRec> d_replay_seeds;
+
 	// oligo-strand sets of the last search, reused while assays and options stay the same
-	std::unique_ptr<OsSet> set1, set2;
+	std::unique_ptr<OsSet> set1, set2, set_all;
 	tnt_search_options set_opt{};
 	uint64_t assays_version = 0, set_version = ~(uint64_t)0;
 
@@ -1527,6 +1533,7 @@ void prepare_sets(tnt_engine *e, const tnt_search_options &o)
 	if (!reuse_sets) {
 		e->set1.reset(new OsSet);
 		e->set2.reset(new OsSet);
+		e->set_all.reset();
 	}
 	OsSet &stage1 = *e->set1, &stage2 = *e->set2;
 
@@ -1580,6 +1587,154 @@ void prepare_sets(tnt_engine *e, const tnt_search_options &o)
 		e->set_opt = o;
 		e->set_version = e->assays_version;
 	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact replay of the reference's staged PCR search for a list of (fragment, assay) groups
+// (assemble.h: replay_pcr_group).  Device side: every oligo strand of the group's assay is
+// scanned over the whole fragment (k_region_scan with one region per group), every seed is
+// aligned (the survivors join the bound-site buffer), and the seeds themselves come back to the
+// host as one dense array.
+// ------------------------------------------------------------------------------------------
+struct GroupKey {
+	uint32_t target;
+	int assay;
+	bool operator<(const GroupKey &o) const { return target != o.target ? target < o.target : assay < o.assay; }
+	bool operator==(const GroupKey &o) const { return target == o.target && assay == o.assay; }
+};
+
+void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOptions &ao, const std::vector<GroupKey> &groups,
+	std::vector<BoundSite> &sites, std::vector<tnt_hit> &out_hits, std::vector<HitSites> &out_refs)
+{
+	if (groups.empty()) return;
+	HostTimer t_all("replay of culled groups");
+	OsSet &stage1 = *e->set1, &stage2 = *e->set2;
+	if (!e->set_all) {
+		e->set_all.reset(new OsSet);
+		e->set_all->os = stage1.os;
+		e->set_all->os.insert(e->set_all->os.end(), stage2.os.begin(), stage2.os.end());
+		finish_set(e, *e->set_all);
+	}
+	OsSet &set = *e->set_all;
+	const size_t nos = set.os.size();
+	const size_t n_assays = e->assays.size();
+
+	std::vector<Region> regions(groups.size());
+	std::vector<uint64_t> per_assay(n_assays, 0);
+	for (size_t g = 0; g < groups.size(); ++g) {
+		const uint32_t len = e->targets[groups[g].target].len;
+		regions[g] = Region{groups[g].target, 0u, len, groups[g].assay};
+		per_assay[(size_t)groups[g].assay] += len;
+	}
+	uint64_t worst = 0;
+	for (uint64_t v : per_assay) worst = std::max(worst, v);
+	e->d_regions.upload(regions, e->stream);
+
+	const uint32_t rec_before = e->n_bound;
+	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
+	const double expect = (double)worst*(double)set.max_words/(double)set.nkeys;
+	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
+	std::vector<uint32_t> counts;
+	for (;;) {
+		e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
+		RegionScanArgs ra{};
+		ra.s = scan_args(e, set, cap);
+		ra.regions = e->d_regions.p;
+		ra.nregions = (uint32_t)regions.size();
+		const uint32_t grid = std::min<uint32_t>((uint32_t)regions.size(), (uint32_t)e->sm_count*64u);
+		CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
+		k_region_scan<<<grid, SCAN_THREADS, 0, e->stream>>>(ra);
+		CUDA_OK(cudaGetLastError());
+		CUDA_OK(cudaEventRecord(e->ev[1], e->stream));
+		e->stats.kernel_launches++;
+		const bool ok = align_buckets(e, set, cap, 0, false, &counts);
+		float ms = 0;
+		CUDA_OK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+		e->stats.scan_ms += ms;
+		if (ok) break;
+		uint32_t need = 0;
+		for (uint32_t c : counts) need = std::max(need, c);
+		cap = need + need/16 + 64;
+	}
+
+	// seeds -> host
+	std::vector<CandSpan> spans;
+	uint64_t nseeds = 0;
+	for (size_t s = 0; s < nos; ++s)
+		if (counts[s]) { spans.push_back(CandSpan{(uint32_t)s, counts[s], nseeds}); nseeds += counts[s]; }
+	std::vector<ReplaySeedRec> seeds(nseeds);
+	if (nseeds) {
+		e->d_spans.upload(spans, e->stream);
+		e->d_replay_seeds.reserve(nseeds, 0, e->stream);
+		k_compact_cands<<<(unsigned)std::min<size_t>(spans.size(), (size_t)e->sm_count*8), 256, 0, e->stream>>>(e->d_cand.p, cap,
+			e->d_spans.p, (uint32_t)spans.size(), e->d_replay_seeds.p);
+		CUDA_OK(cudaGetLastError());
+		e->stats.kernel_launches++;
+		CUDA_OK(cudaMemcpyAsync(seeds.data(), e->d_replay_seeds.p, nseeds*sizeof(ReplaySeedRec), cudaMemcpyDeviceToHost, e->stream));
+		e->stats.d2h_bytes += nseeds*sizeof(ReplaySeedRec);
+	}
+	// heads of the sites bound in this pass
+	const uint32_t rec_after = e->n_bound;
+	std::vector<BoundHead> heads(rec_after - rec_before);
+	if (!heads.empty()) {
+		CUDA_OK(cudaMemcpy2DAsync(heads.data(), sizeof(BoundHead), e->d_bound.p + rec_before, sizeof(BoundRec),
+			sizeof(BoundHead), heads.size(), cudaMemcpyDeviceToHost, e->stream));
+		e->stats.d2h_bytes += heads.size()*sizeof(BoundHead);
+	}
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+
+	// (group, oligo strand, position, word) -> site
+	struct Key { uint32_t target, os, t, k; int idx; };
+	auto key_less = [](const Key &a, const Key &b) {
+		if (a.target != b.target) return a.target < b.target;
+		if (a.os != b.os) return a.os < b.os;
+		if (a.t != b.t) return a.t < b.t;
+		return a.k < b.k;
+	};
+	const size_t site_base = sites.size();
+	std::vector<Key> site_keys(heads.size());
+	for (size_t i = 0; i < heads.size(); ++i) {
+		const BoundHead &b = heads[i];
+		if (b.flags & F_TRUNC)
+			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
+		if (b.flags & (F_OOB | F_STACK))
+			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
+		sites.push_back(make_site(b, rec_before + (uint32_t)i, set.os[b.os]));
+		site_keys[i] = Key{b.target, b.os, b.t, b.k, (int)(site_base + i)};
+	}
+	std::sort(site_keys.begin(), site_keys.end(), key_less);
+
+	// seeds per group: ordered by (fragment, assay) through (target, os)
+	std::vector<Key> seed_keys(nseeds);
+	for (size_t i = 0; i < nseeds; ++i)
+		seed_keys[i] = Key{seeds[i].target_k & 0xffffffu, seeds[i].os, seeds[i].t, seeds[i].target_k >> 24, 0};
+	std::sort(seed_keys.begin(), seed_keys.end(), [&](const Key &a, const Key &b) {
+		if (a.target != b.target) return a.target < b.target;
+		const int aa = set.os[a.os].assay, ab = set.os[b.os].assay;
+		if (aa != ab) return aa < ab;
+		return key_less(a, b);
+	});
+	size_t at = 0;
+	for (const GroupKey &g : groups) {
+		std::vector<ReplaySeed> gs;
+		while (at < seed_keys.size() && (seed_keys[at].target < g.target ||
+			(seed_keys[at].target == g.target && set.os[seed_keys[at].os].assay < g.assay))) ++at;
+		for (; at < seed_keys.size() && seed_keys[at].target == g.target && set.os[seed_keys[at].os].assay == g.assay; ++at) {
+			const Key &k = seed_keys[at];
+			const OligoStrand &os = set.os[k.os];
+			ReplaySeed r;
+			r.cat = (os.role == TNT_OLIGO_P ? 4 : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0)) + (os.role == TNT_OLIGO_P && os.plus ? 1 : 0);
+			r.q = k.k;
+			r.t = k.t;
+			const auto it = std::lower_bound(site_keys.begin(), site_keys.end(), k, key_less);
+			r.site = (it != site_keys.end() && !key_less(k, *it)) ? it->idx : -1;
+			gs.push_back(r);
+		}
+		const AssayHost &as = e->assays[(size_t)g.assay];
+		replay_pcr_group(std::move(gs), sites, ao, !as.P.empty(), g.assay, as.id, out_hits, out_refs);
+	}
+	(void)o;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1641,6 +1796,46 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, n1, worst, nos1); }
 	}
 	const uint32_t n2 = e->n_bound;
+
+	// Groups with bound sites close to each other (k_crowd): candidates for the exact replay below
+	const bool pcr_primers = o.assay_format == TNT_ASSAY_PCR && !stage2.os.empty();
+	std::vector<uint64_t> crowded;
+	if (pcr_primers && n2 != 0 && !(e->prm.reserved & TNT_ENGINE_KEEP_CULLED_SITES)) {
+		uint32_t log2_bits = 22;
+		while (log2_bits < 33 && ((uint64_t)1 << log2_bits) < (uint64_t)n2*1024u) ++log2_bits;
+		const size_t words = (size_t)(((uint64_t)1 << log2_bits)/32u);
+		uint32_t out_cap = (uint32_t)std::max<size_t>(e->d_crowd_out.cap, 1u << 16);
+		for (;;) {
+			e->d_crowd_bits.reserve(words + 1, 0, e->stream);
+			e->d_crowd_out.reserve(out_cap, 0, e->stream);
+			CUDA_OK(cudaMemsetAsync(e->d_crowd_bits.p, 0, (words + 1)*sizeof(uint32_t), e->stream));
+			CrowdArgs ca{};
+			ca.recs = e->d_bound.p;
+			ca.os1 = stage1.d_os.p;
+			ca.os2 = stage2.d_os.p;
+			ca.nos1 = nos1;
+			ca.n = n2;
+			ca.bits = e->d_crowd_bits.p;
+			ca.log2_bits = log2_bits;
+			ca.out = e->d_crowd_out.p;
+			ca.out_count = e->d_crowd_bits.p + words;
+			ca.out_cap = out_cap;
+			k_crowd<<<gen_grid, 256, 0, e->stream>>>(ca, 0);
+			k_crowd<<<gen_grid, 256, 0, e->stream>>>(ca, 1);
+			CUDA_OK(cudaGetLastError());
+			e->stats.kernel_launches += 2;
+			uint32_t cnt = 0;
+			CUDA_OK(cudaMemcpyAsync(&cnt, ca.out_count, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+			if (cnt > out_cap) { out_cap = cnt + cnt/8; continue; }
+			crowded.resize(cnt);
+			if (cnt) {
+				CUDA_OK(cudaMemcpyAsync(crowded.data(), e->d_crowd_out.p, (size_t)cnt*sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+				CUDA_OK(cudaStreamSynchronize(e->stream));
+			}
+			break;
+		}
+	}
 
 	// Stage C
 	auto os_of = [&](uint32_t g) -> const OligoStrand & {
@@ -1753,6 +1948,62 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	}
 	std::vector<HitSites> refs;
 	{ HostTimer t("assemble_hits"); assemble_hits(sites, ao, assay_ids, assay_has_primers, assay_has_probe, e->hits, refs); }
+
+	// PCR: the join above runs over every bound site.  The reference culls its match list between
+	// the binding steps and can lose a site when bound sites of one assay overlap
+	// (amplicon_search.cpp:679-765, see assemble.h); groups in which that is possible are
+	// searched again step by step, exactly like the reference does it, and their hits replaced.
+	if (pcr_primers && !e->hits.empty() && !(e->prm.reserved & TNT_ENGINE_KEEP_CULLED_SITES)) {
+		const bool replay_all = std::getenv("TNT_REPLAY_ALL") != nullptr; // verification: every group with a hit
+		std::sort(crowded.begin(), crowded.end());
+		crowded.erase(std::unique(crowded.begin(), crowded.end()), crowded.end());
+		std::vector<GroupKey> groups;
+		for (size_t i = 0; i < e->hits.size(); ++i) {
+			const tnt_hit &h = e->hits[i];
+			if (h.forward.oligo == TNT_OLIGO_NONE) continue; // probe-only assay in a PCR run
+			const GroupKey g{h.target_id, h.assay_index};
+			if (!groups.empty() && groups.back() == g) continue; // hits are ordered by group
+			bool need = replay_all || std::binary_search(crowded.begin(), crowded.end(), ((uint64_t)g.target << 32) | (uint32_t)g.assay);
+			for (size_t j = i; !need && j < e->hits.size() && e->hits[j].target_id == g.target && e->hits[j].assay_index == g.assay; ++j) {
+				const BoundSite &a = sites[(size_t)refs[j].forward], &b = sites[(size_t)refs[j].reverse];
+				const BoundSite &minus_site = a.plus ? b : a, &plus_site = a.plus ? a : b;
+				need = !hit_order_is_safe(minus_site, plus_site, refs[j].probe >= 0 ? &sites[(size_t)refs[j].probe] : nullptr, o.max_len);
+			}
+			if (need) groups.push_back(g);
+		}
+		e->stats.replayed_groups = groups.size();
+		if (!groups.empty()) {
+			std::vector<tnt_hit> rhits;
+			std::vector<HitSites> rrefs;
+			replay_groups(e, o, ao, groups, sites, rhits, rrefs);
+			// merge: replayed groups take their hits from the replay, in (fragment, assay) order
+			std::vector<tnt_hit> merged;
+			std::vector<HitSites> mrefs;
+			merged.reserve(e->hits.size());
+			mrefs.reserve(e->hits.size());
+			size_t i = 0, j = 0, gi = 0;
+			auto key_of = [](const tnt_hit &h) { return GroupKey{h.target_id, h.assay_index}; };
+			while (i < e->hits.size() || j < rhits.size()) {
+				if (i < e->hits.size()) {
+					const GroupKey k = key_of(e->hits[i]);
+					while (gi < groups.size() && groups[gi] < k) ++gi;
+					if (gi < groups.size() && groups[gi] == k) { ++i; continue; } // replayed group: superseded
+				}
+				if (j >= rhits.size() || (i < e->hits.size() && key_of(e->hits[i]) < key_of(rhits[j]))) {
+					merged.push_back(e->hits[i]);
+					mrefs.push_back(refs[i]);
+					++i;
+				}
+				else {
+					merged.push_back(rhits[j]);
+					mrefs.push_back(rrefs[j]);
+					++j;
+				}
+			}
+			e->hits.swap(merged);
+			refs.swap(mrefs);
+		}
+	}
 	e->stats.hits = e->hits.size();
 
 	// Alignment text only for the sites that made it into a hit: gather their full records

@@ -896,7 +896,9 @@ __global__ void k_make_regions(const BoundRec *__restrict__ recs, uint32_t n, co
 	const Target *__restrict__ targets, int max_len, Region *__restrict__ out,
 	unsigned long long *__restrict__ per_assay, uint32_t *__restrict__ err_flags)
 {
-	const int64_t slack = 64;
+	// slack: seed positions and loc_5 of one site lie within an oligo length (+ flanks) of each other;
+	// everything that can interleave with this site in the reference's sorted list is inside the region
+	const int64_t slack = 2*MAX_OLIGO + 16;
 	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
 		const BoundHead b = recs[i].h;
 		Region r;
@@ -1009,6 +1011,88 @@ __global__ void k_live_padlock(LiveArgs a, uint32_t n, int pass)
 		const uint32_t slot = atomicAdd(a.count, 1u);
 		a.out_heads[slot] = b;
 		a.out_index[slot] = i;
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Which (fragment, assay) groups hold two bound sites close to each other?
+//
+// The reference's cull_oligo_match (amplicon_search.cpp:679-765) sorts a list that mixes bound sites
+// (ordered by loc_5 / loc_3) with not-yet-bound seeds (ordered by seed position) and stops its partner
+// scan on an unsigned difference of seed positions (:709).  That is only the pure optimisation it is
+// meant to be while bound sites of one assay keep their distance: two bound sites whose order by
+// loc_5 differs from their order by seed position (possible within about one oligo length) make
+// the scan break early and a real site is culled.  Such groups are searched again the way the
+// reference does it, step by step (engine.cu: replay).  This pair of kernels finds them: every
+// bound site sets a bit for (fragment, assay, loc_5 >> CROWD_SHIFT) in a hashed bitmap; a site that
+// finds its own bit already set, or a bit of a neighbouring bucket set, reports its group.  Hash
+// collisions only add groups to the replay list (which is exact for any group).
+// ------------------------------------------------------------------------------------------
+constexpr int CROWD_SHIFT = 8;
+
+struct CrowdArgs {
+	const BoundRec *recs;
+	const OligoStrand *os1, *os2;
+	uint32_t nos1, n;
+	uint32_t *bits;               // 2^log2_bits bits, zero at the start of the mark pass
+	uint32_t log2_bits;
+	uint64_t *out;                // reported groups: target << 32 | assay
+	uint32_t *out_count;
+	uint32_t out_cap;
+};
+
+__device__ __forceinline__ uint64_t crowd_hash(uint32_t target, uint32_t assay, uint32_t bucket)
+{
+	uint64_t x = ((uint64_t)target << 40) ^ ((uint64_t)assay << 20) ^ (uint64_t)bucket;
+	x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+	x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+	x ^= x >> 33;
+	return x;
+}
+
+__device__ __forceinline__ void crowd_report(const CrowdArgs &a, uint32_t target, uint32_t assay)
+{
+	const uint32_t slot = atomicAdd(a.out_count, 1u);
+	if (slot < a.out_cap) a.out[slot] = ((uint64_t)target << 32) | assay;
+}
+
+__global__ void k_crowd(CrowdArgs a, int pass)
+{
+	const uint64_t mask = ((uint64_t)1 << a.log2_bits) - 1u;
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += gridDim.x*blockDim.x) {
+		const BoundHead b = a.recs[i].h;
+		const OligoStrand &o = b.os < a.nos1 ? a.os1[b.os] : a.os2[b.os - a.nos1];
+		const uint32_t bucket = ((uint32_t)max(b.loc5, 0) >> CROWD_SHIFT) + 1u;
+		if (pass == 0) {
+			const uint64_t h = crowd_hash(b.target, (uint32_t)o.assay, bucket) & mask;
+			const uint32_t bit = 1u << (h & 31u);
+			if (atomicOr(a.bits + (h >> 5), bit) & bit) crowd_report(a, b.target, (uint32_t)o.assay);
+		}
+		else {
+			const uint64_t h0 = crowd_hash(b.target, (uint32_t)o.assay, bucket - 1u) & mask;
+			const uint64_t h1 = crowd_hash(b.target, (uint32_t)o.assay, bucket + 1u) & mask;
+			if (((a.bits[h0 >> 5] >> (h0 & 31u)) | (a.bits[h1 >> 5] >> (h1 & 31u))) & 1u) crowd_report(a, b.target, (uint32_t)o.assay);
+		}
+	}
+}
+
+// Seeds of the replayed groups -> one dense array (oligo strand, word index, position), bucket by bucket
+struct CandSpan { uint32_t os, count; uint64_t out_off; };
+struct ReplaySeedRec { uint32_t os, target_k, t; };
+
+__global__ void k_compact_cands(const Candidate *__restrict__ cand, uint32_t cap, const CandSpan *__restrict__ spans, uint32_t nspans,
+	ReplaySeedRec *__restrict__ out)
+{
+	for (uint32_t s = blockIdx.x; s < nspans; s += gridDim.x) {
+		const CandSpan sp = spans[s];
+		for (uint32_t i = threadIdx.x; i < sp.count; i += blockDim.x) {
+			const Candidate c = cand[(size_t)sp.os*cap + i];
+			ReplaySeedRec r;
+			r.os = sp.os;
+			r.target_k = c.target_k;
+			r.t = c.t;
+			out[sp.out_off + i] = r;
+		}
 	}
 }
 

@@ -91,7 +91,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64),
                 ("scan_ms", C.c_double), ("align_ms", C.c_double), ("pair_ms", C.c_double),
                 ("total_ms", C.c_double), ("scan_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("nonbinding_dropped", C.c_uint64)]
+                ("replayed_groups", C.c_uint64), ("nonbinding_dropped", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -230,10 +230,11 @@ class Engine:
     reference (tntblast_local.cpp:345-372)."""
 
     def __init__(self, target_T: float = 310.15, salt: float = 50.0e-3, dangle5: bool = False,
-                 dangle3: bool = False, word_size: int = 7, device: int = 0):
+                 dangle3: bool = False, word_size: int = 7, device: int = 0, keep_culled_sites: bool = False):
         self.L = load_library()
         prm = EngineParams(target_T=target_T, salt=salt, dangle5=int(dangle5), dangle3=int(dangle3),
-                           dinkelbach=0, word_size=word_size, device=device, reserved=0)
+                           dinkelbach=0, word_size=word_size, device=device,
+                           reserved=1 if keep_culled_sites else 0)   # TNT_ENGINE_KEEP_CULLED_SITES
         self.h = C.c_void_p()
         self._check(self.L.tnt_engine_create(C.byref(prm), C.byref(self.h)))
         self.target_T = target_T
