@@ -232,20 +232,91 @@ def write_reference_inputs(tmp: str, records, assays, sample_bp: int):
                 f.write(txt[full:].tobytes() + b"\n")
             left -= n
     q = os.path.join(tmp, "assays.txt")
-    with open(q, "w") as f:
-        for i, (F, R, P) in enumerate(assays):
-            f.write("assay%d\t%s\t%s%s\n" % (i, F, R, ("\t" + P) if P else ""))
+    gen.write_assays(q, assays)
     return fa, q, sample_bp - max(left, 0)
 
 
-def run_reference_once(fa, q, cores: int, tmp: str) -> float:
-    exe = os.path.join(ROOT, "oracle", "_ref", "tntblast")
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "tntblast")
+REF_COUNTED_EXE = os.path.join(ROOT, "oracle", "_ref", "tntblast_counted")   # + a call counter (oracle/count_wrap.cpp)
+GPU_EXE = os.path.join(ROOT, "tests", "shim", "_build", "tntblast_gpu")     # the reference objects on the engine
+
+
+def reference_assays(assays, kind: str):
+    """The assay list as the reference's input file holds it: the probe flavour carries a two-fold code
+    that the reference expands itself (expand_degenerate_signatures), the engine gets the two expansions."""
+    if kind != "probe":
+        return assays
+    return [(None, None, a[2][:20] + {"A": "R", "G": "R", "C": "Y", "T": "Y"}[a[2][20]] + a[2][21:]) for a in assays[::2]]
+
+
+def reference_flags(kind: str):
+    if kind == "probe":
+        return ["-A", "PROBE", "-E", str(MIN_PROBE_TM)]
+    if kind == "padlock":
+        return ["-A", "PADLOCK", "-e", "40"]
+    if kind == "pcr":
+        return ["-e", str(MIN_PRIMER_TM)]
+    return ["-e", str(MIN_PRIMER_TM), "-E", str(MIN_PROBE_TM)]
+
+
+def run_reference_once(fa, q, cores: int, tmp: str, kind: str = "taqman", exe: str = None, out: str = "out.txt") -> float:
     env = dict(os.environ, OMP_NUM_THREADS=str(cores))
     t0 = time.perf_counter()
-    subprocess.run([exe, "-i", q, "-d", fa, "-e", str(MIN_PRIMER_TM), "-E", str(MIN_PROBE_TM),
-                    "-o", os.path.join(tmp, "out.txt")], check=True, env=env,
-                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run([exe or REF_EXE, "-i", q, "-d", fa, "-o", os.path.join(tmp, out)] + reference_flags(kind),
+                       check=True, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    run_reference_once.last_stderr = r.stderr
     return time.perf_counter() - t0
+
+
+def hit_blocks(path: str):
+    """The hit records of a tntblast text output (one block per reported match: 'name = ...' up to the blank line)."""
+    blocks, cur = [], []
+    with open(path, "rb") as f:
+        for ln in f:
+            if ln.startswith(b"name = ") and cur:
+                blocks.append(b"".join(cur))
+                cur = []
+            if ln.startswith(b"####"):
+                continue
+            cur.append(ln)
+    if cur:
+        blocks.append(b"".join(cur))
+    return [b for b in blocks if b.startswith(b"name = ")]
+
+
+def parity_at_scale(fa, q, cores: int, tmp: str, kind: str):
+    """The same slice through tests/shim/_build/tntblast_gpu (the unmodified reference objects with
+    amplicon()/padlock()/hybrid() resolved to the engine's C ABI): its text output against the text
+    output the reference binary wrote in the timed run."""
+    import re
+    from collections import Counter
+    if not os.path.exists(GPU_EXE):
+        return {"checked": False, "why": "tests/shim/_build/tntblast_gpu not built (needs /root/reference at build time)"}
+    try:
+        run_reference_once(fa, q, cores, tmp, kind, exe=GPU_EXE, out="out_gpu.txt")
+    except subprocess.CalledProcessError as ex:
+        return {"checked": False, "why": "tntblast_gpu failed: %s" % (ex.stderr or "")[-300:]}
+    shim_line = [ln for ln in run_reference_once.last_stderr.splitlines() if ln.startswith("[tntb200]")]
+    a, b = os.path.join(tmp, "out.txt"), os.path.join(tmp, "out_gpu.txt")
+    identical = open(a, "rb").read() == open(b, "rb").read()
+    ra, rb = hit_blocks(a), hit_blocks(b)
+    ca, cb = Counter(ra), Counter(rb)
+    only_ref, only_gpu = sum((ca - cb).values()), sum((cb - ca).values())
+    # hits with a Tm within 0.01 C of the bound it was filtered with (north_star: listed separately)
+    bounds = {b"forward primer tm": MIN_PRIMER_TM, b"reverse primer tm": MIN_PRIMER_TM, b"probe tm": MIN_PROBE_TM}
+    if kind == "padlock":
+        bounds = {b"forward primer tm": 40.0, b"reverse primer tm": 40.0}
+    near = 0
+    pat = re.compile(rb"^(forward primer tm|reverse primer tm|probe tm) = ([-0-9.e+]+)$", re.M)
+    for blk in ra:
+        if any(abs(float(v) - bounds[k]) <= 0.0105 for k, v in pat.findall(blk) if k in bounds):
+            near += 1
+    return {"checked": True, "byte_identical_output": bool(identical), "hits": len(ra), "hits_engine": len(rb),
+            "mismatches": int(only_ref + only_gpu), "only_in_reference": int(only_ref), "only_in_engine": int(only_gpu),
+            "near_threshold": int(near),
+            "how": "text output of tests/shim/_build/tntblast_gpu (reference objects + C-ABI shim) vs the reference binary's, "
+                   "same command line, same slice; hit blocks compared as multisets, files byte for byte",
+            "shim": shim_line[-1] if shim_line else None}
 
 
 def host_cores() -> int:
@@ -255,23 +326,45 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_baseline(records, assays, seconds_target: float = 15.0):
-    exe = os.path.join(ROOT, "oracle", "_ref", "tntblast")
-    if not os.path.exists(exe):
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                "sample": "oracle/_ref/tntblast missing (build it with make -C oracle ref where /root/reference exists)"}
+def reference_alignment_count(fa, q, cores, tmp, kind):
+    """NucCruc heterodimer evaluations of the reference on this input (untimed run of the counted binary)."""
+    import re
+    if not os.path.exists(REF_COUNTED_EXE):
+        return None
+    try:
+        run_reference_once(fa, q, cores, tmp, kind, exe=REF_COUNTED_EXE, out="out_counted.txt")
+    except subprocess.CalledProcessError:
+        return None
+    m = re.search(r"approximate_tm_heterodimer calls: (\d+)", run_reference_once.last_stderr)
+    return int(m.group(1)) if m else None
+
+
+def cpu_baseline(records, assays, kind: str = "taqman", seconds_target: float = 15.0):
+    """(cpu_baseline, parity_at_scale): the reference binary timed on a leading slice of the same
+    database, its alignment count, and its text output compared with the engine-backed program's."""
+    if not os.path.exists(REF_EXE):
+        return ({"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                 "sample": "oracle/_ref/tntblast missing (build it with make -C oracle ref where /root/reference exists)"}, None)
     cores = host_cores()
     # measured in the survey: ~0.016 Gbp*assay/s per core on 100 TaqMan assays
     sample_bp = int(min(sum(len(r) for r in records), max(2_000_000, seconds_target * 0.016e9 * cores / max(len(assays), 1))))
     tmp = tempfile.mkdtemp(prefix="tntref_")
     try:
         fa, q, used = write_reference_inputs(tmp, records, assays, sample_bp)
-        dt = run_reference_once(fa, q, cores, tmp)
+        dt = run_reference_once(fa, q, cores, tmp, kind)
+        aligns = reference_alignment_count(fa, q, cores, tmp, kind)
+        parity = parity_at_scale(fa, q, cores, tmp, kind)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    return {"value": used * len(assays) / 1e9 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+    base = {"value": used * len(assays) / 1e9 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": "first %.1f Mbp of the same database x %d assays, OMP_NUM_THREADS=%d, %.1f s wall (file read + search + output)"
-                      % (used / 1e6, len(assays), cores, dt)}
+                      % (used / 1e6, len(assays), cores, dt),
+            "alignments": aligns, "alignments_per_s": (aligns / dt if aligns else None),
+            "alignments_how": "calls of NucCruc::approximate_tm_heterodimer in an untimed run of the same command with "
+                              "oracle/_ref/tntblast_counted (link-time wrapper, oracle/count_wrap.cpp)"}
+    if parity is not None:
+        parity["slice"] = "first %.1f Mbp x %d assays" % (used / 1e6, len(assays))
+    return base, parity
 
 
 def fasta_text_pinned(records):
@@ -397,8 +490,6 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        if args.kind not in ("taqman", "pcr"):
-            raise SystemExit("--impl reference supports --kind taqman | pcr")
         # bounded per-step sample so that warmup + steps end within a few minutes
         cores = host_cores()
         per_step_s = 6.0
@@ -406,10 +497,11 @@ def main():
         records, _, assays, _ = build_workload(0, min(args.mbp, max(sample_mbp, 5)), args.assays, kind=args.kind)
         tmp = tempfile.mkdtemp(prefix="tntref_")
         try:
-            fa, q, used = write_reference_inputs(tmp, records, assays, sample_mbp * 1_000_000)
+            fa, q, used = write_reference_inputs(tmp, records, reference_assays(assays, args.kind), sample_mbp * 1_000_000)
             for _ in range(args.warmup):
-                run_reference_once(fa, q, cores, tmp)
-            times = [run_reference_once(fa, q, cores, tmp) for _ in range(args.steps)]
+                run_reference_once(fa, q, cores, tmp, args.kind)
+            times = [run_reference_once(fa, q, cores, tmp, args.kind) for _ in range(args.steps)]
+            ref_aligns = reference_alignment_count(fa, q, cores, tmp, args.kind)
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         dt = sum(times) / len(times)
@@ -420,7 +512,9 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
             "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                             "alignments": ref_aligns, "alignments_per_s": (ref_aligns / dt if ref_aligns else None)},
+            "alignments_per_s": (ref_aligns / dt if ref_aligns else None),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
@@ -521,7 +615,8 @@ def main():
         upload()
         upload_s += time.perf_counter() - tu
         eng.search_raw(opts)
-        n_e2e_hits, hit_bytes, text_bytes = eng.hit_records()   # the step's result, read on the host
+        n_e2e_hits, hit_bytes, text_bytes = eng.hit_records()   # the step's result, read on the host ...
+        n_seq, seq_bytes = eng.hit_sequences_bytes()             # ... with the amplicon / site text of every hit
         # result bytes the engine copied back (site heads of live groups, records of hit sites)
         d2h = int(eng.stats().d2h_bytes)
     barrier()
@@ -599,7 +694,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frag_bases, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
-                "upload_call_ms_per_step": upload_s / e2e_steps * 1e3},
+                "upload_call_ms_per_step": upload_s / e2e_steps * 1e3,
+                "result": "tnt_hit records + alignment strings + amplicon / site text of every hit (tnt_engine_hit_sequences)",
+                "hit_text_bytes_per_step": int(seq_bytes)},
         "roofline": {"bound": "alu-int32", "achieved": alu_achieved, "peak": alu_peak, "unit": "TOP/s",
                      "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": nuccruc_traffic,
                      "traffic_note": "bytes per step over all NucCruc launches (ncu, profiles/dram_r01_v7.csv): ~450 GB/s, 7 % of the HBM peak -- the kernels are ALU-bound, not memory-bound",
@@ -620,11 +717,10 @@ def main():
             ingest["parse_frac_of_hbm_peak"] = ingest["parse_GBps"] / hbm_peak if hbm_peak else None
         line["ingest_fasta"] = ingest
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        if args.kind in ("taqman", "pcr"):
-            line["cpu_baseline"] = cpu_baseline(records, assays)
-        else:
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
-                                    "sample": "not measured for this workload flavour (bench line of record: --kind taqman)"}
+        # the engine (and its HBM) stays alive meanwhile; the engine-backed program creates its own
+        line["cpu_baseline"], parity = cpu_baseline(records, reference_assays(assays, args.kind), args.kind)
+        if parity is not None:
+            line["parity_at_scale"] = parity
     elif rank == 0:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "only measured at N=1"}
     if rank == 0:

@@ -134,6 +134,9 @@ typedef struct {
 	uint64_t d2h_bytes;              /* result bytes copied device -> host by the search (counters excluded) */
 	uint64_t replayed_groups;        /* (fragment, assay) groups searched again step by step like amplicon() does
 	                                  * (its culls can lose a site there, see TNT_ENGINE_KEEP_CULLED_SITES) */
+	uint64_t undefined_dropped;      /* windows whose traceback leaves the DP matrix: the reference reads unchecked
+	                                  * ring-buffer memory there (nuc_cruc.cpp:1497-1541; only when a terminal penalty
+	                                  * clamps to zero, T < ~205 K), no defined answer exists; dropped and counted */
 	uint64_t nonbinding_dropped;     /* windows without any alignment (Tm = 0, dG = 0) that the bounds would have
 	                                  * accepted: the reference reports them with the coordinates of an earlier
 	                                  * alignment (nuc_cruc.h:360-371); the engine drops and counts them */

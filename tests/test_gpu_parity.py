@@ -398,8 +398,7 @@ def test_replay_of_every_group_changes_nothing(engine_lib, oracle, monkeypatch):
     rng = np.random.default_rng(60221)
     db = [gen.random_codes(int(rng.integers(30000, 60000)), rng) for _ in range(5)]
     gen.sprinkle_degenerate(db[1], rng, frac=1e-3, n_runs_per_50kb=3)
-    # planted copies with indels bind through two seed diagonals (duplicate sites: replayed by default);
-    # exact copies alone leave nothing for the culls to confuse (not replayed unless forced)
+    # nothing here makes the orders of bound sites disagree: no group is replayed unless forced
     assays = gen.make_assays(rng, db, 4, "taqman", variants=3) + gen.make_assays(rng, db, 4, "pcr", variants=3) + \
         gen.make_assays(rng, db, 4, "taqman", variants=0) + gen.make_assays(rng, db, 4, "pcr", variants=0)
     o = H.default_options(min_primer_tm=38.0, min_probe_tm=38.0, max_len=1000)
@@ -415,7 +414,7 @@ def test_replay_of_every_group_changes_nothing(engine_lib, oracle, monkeypatch):
     monkeypatch.setenv("TNT_REPLAY_ALL", "1")
     forced, n_forced = run()
     assert forced == base and len(base) >= 12
-    assert n_forced >= 12 and n_forced >= n_default + 8   # the eight exact-copy assays
+    assert n_forced >= 12 and n_default <= 2
     k = 0
     for t, codes in enumerate(db):
         for i, a in enumerate(assays):

@@ -507,14 +507,18 @@ __device__ __forceinline__ bool nc_dangling_ends(const DpShared &sh, const Therm
 
 // `cells` lists the maximal DP cells as linear indices (i-1)*Lt + (j-1) in row-major order,
 // i.e. the order of the reference's max_ptr vector.
+// `fresh` false: continue with the best alignment found so far (the maximal cells of one window
+// arrive in several chunks when there are more than MAX_MAXCELLS of them).
 template <class TV, class TG>
 __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct,
 	const TG &tgt, int Lt, const TV &tv, const uint16_t *cells, int ncells,
-	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags)
+	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags, bool fresh = true)
 {
 	const float T = th->T;
-	best.valid = false;
-	best.dH = best.dS = best.tm = 0.0f;
+	if (fresh) {
+		best.valid = false;
+		best.dH = best.dS = best.tm = 0.0f;
+	}
 	if (ncells == 0) return;
 
 	Branch stack[MAX_BRANCH];
@@ -640,7 +644,10 @@ __device__ inline void nc_counts(const DpShared &sh, const AlnState &a, unsigned
 constexpr int ROW_WORDS = 72;      // P1[20] P2[20] P4[20] P3[4] P6[4] P7 pad[3]
 constexpr int ROW_P1 = 0, ROW_P2 = 20, ROW_P4 = 40, ROW_P3 = 60, ROW_P6 = 64, ROW_P7 = 68;
 constexpr int32_t ROW_PAD_PENALTY = 1 << 28;
-constexpr int MAX_MAXCELLS = 64;
+#ifndef TNT_MAX_MAXCELLS
+#define TNT_MAX_MAXCELLS 64
+#endif
+constexpr int MAX_MAXCELLS = TNT_MAX_MAXCELLS;   // tied maximal cells handled per chunk (a test build uses 2)
 
 // ------------------------------------------------------------------------------------------
 // Lean tier of the fast fill: what nearly every window needs and nothing more.
@@ -1102,7 +1109,7 @@ __device__ inline int collect_max_cells_full(const ColMajorTraceFull<LQ, NT> &tv
 		const int i0 = (j == j0 && dp.last_j > 0) ? dp.last_i : 1;
 		for (int i = i0; i <= Lq && n < dp.nmax; ++i) {
 			if (tv.raw(i, j) & 1u) continue; // below the running maximum
-			if (n == MAX_MAXCELLS) { flags |= F_TRUNC; return n; }
+			if (n == MAX_MAXCELLS) return n; // not reached: the caller hands windows with more tied cells to the generic kernel
 			// insertion sort by row-major index
 			const uint16_t key = (uint16_t)((i - 1)*Lt + (j - 1));
 			int k = n++;
@@ -1113,19 +1120,21 @@ __device__ inline int collect_max_cells_full(const ColMajorTraceFull<LQ, NT> &tv
 	return n;
 }
 
-// The same list for the row-major (generic) fill.
+// The same list for the row-major (generic) fill, at most MAX_MAXCELLS cells per call: `cursor`
+// (start it at dp.last_raise, or 0) remembers where the scan stopped, `remaining` (start it at
+// dp.nmax) how many cells are still to come.  Low-complexity windows tie hundreds of cells; the
+// reference enumerates all of them (nuc_cruc.cpp:2531-2536), so does the caller, chunk by chunk.
 template <int NT>
-__device__ inline int collect_max_cells(const RowMajorTrace<NT> &tv, const DpResult &dp, int Lq, int Lt,
-	uint16_t *cells, unsigned &flags)
+__device__ inline int collect_max_cells(const RowMajorTrace<NT> &tv, int Lq, int Lt, int &cursor, int &remaining, uint16_t *cells)
 {
-	if (dp.nmax == 0) return 0;
 	int n = 0;
 	const int ncell = Lq*Lt;
-	for (int cell = dp.last_raise < 0 ? 0 : dp.last_raise; cell < ncell && n < dp.nmax; ++cell) {
-		if (!(tv.trace[(size_t)cell*NT] & TW_CAND)) continue;
-		if (n == MAX_MAXCELLS) { flags |= F_TRUNC; return n; }
-		cells[n++] = (uint16_t)cell;
+	for (; cursor < ncell && remaining > 0 && n < MAX_MAXCELLS; ++cursor) {
+		if (!(tv.trace[(size_t)cursor*NT] & TW_CAND)) continue;
+		cells[n++] = (uint16_t)cursor;
+		--remaining;
 	}
+	if (cursor >= ncell) remaining = 0;
 	return n;
 }
 

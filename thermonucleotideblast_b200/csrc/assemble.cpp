@@ -286,6 +286,7 @@ BoundSite make_site(const BoundHead &h, uint32_t index, const OligoStrand &os)
 	s.assay = os.assay;
 	s.role = os.role;
 	s.plus = os.plus;
+	s.os_index = h.os;
 	s.index = index;
 	s.target = h.target;
 	s.loc5 = h.loc5;
@@ -542,14 +543,6 @@ void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite
 	all.reserve(ml.size());
 	for (const El &e : ml) if (e.site >= 0) all.push_back(&sites[(size_t)e.site]);
 	join_pcr_sorted(all, assay_index, assay_id, has_probe, opt, sites.data(), hits, refs);
-}
-
-bool hit_order_is_safe(const BoundSite &f, const BoundSite &r, const BoundSite *p, uint32_t max_len)
-{
-	const uint32_t threshold = max_len + 50;
-	if (!(f.target_loc < r.target_loc) || r.target_loc - f.target_loc > threshold) return false;
-	if (p && !(f.target_loc < p->target_loc && p->target_loc < r.target_loc)) return false;
-	return true;
 }
 
 void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop, SeqMode &mode)

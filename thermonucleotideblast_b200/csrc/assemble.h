@@ -13,6 +13,7 @@ namespace tnt {
 // text: only its length takes part in the ordering (bind_oligo.cpp:69-74).
 struct BoundSite {
 	int assay, role, plus;
+	uint32_t os_index;   // global oligo-strand index (BoundHead::os)
 	uint32_t index;      // record index in the device-side bound-site buffer
 	uint32_t target;
 	int loc5, loc3;
@@ -62,12 +63,6 @@ struct ReplaySeed {
 
 void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
 	bool has_probe, int assay_index, int assay_id, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
-
-// Can the reference's culls lose this amplicon although every site binds?  Not if the seed
-// positions of its sites are ordered like the sites themselves and within reach of each other
-// (then the sites mark each other valid in every cull, whichever of them are bound at that
-// point) -- provided no other bound site of the group sits close by (k_crowd).
-bool hit_order_is_safe(const BoundSite &minus_primer, const BoundSite &plus_primer, const BoundSite *probe, uint32_t max_len);
 
 enum class SeqMode { PcrPlus, PcrMinus, ProbePlus, ProbeMinus, PadlockMinusStrand, PadlockPlusStrand };
 

@@ -291,7 +291,7 @@ struct tnt_engine {
 
 	// exact replay of the reference's staged PCR search (groups where its culls can lose a site)
 	DevBuf<uint32_t> d_crowd_bits;
-	DevBuf<uint64_t> d_crowd_out;
+	DevBuf<CrowdRec> d_crowd_out;
 	DevBuf<CandSpan> d_spans;
 	DevBuf<ReplaySeedRec> d_replay_seeds;
 
@@ -1199,9 +1199,9 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 	if (retry_total >= ((uint64_t)1 << 32)) throw std::runtime_error("internal: hand-over list too large");
 	// snapshot of the DP-cell and dropped-window counters so that a retried pass is not counted twice
 	unsigned long long cells_before = 0;
-	uint32_t nonbinding_before = 0;
+	uint32_t dropped_before[2] = {0, 0}; // non-binding windows, windows without a defined answer
 	CUDA_OK(cudaMemcpyAsync(&cells_before, e->d_cells.p, sizeof(cells_before), cudaMemcpyDeviceToHost, e->stream));
-	CUDA_OK(cudaMemcpyAsync(&nonbinding_before, e->d_out_count.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaMemcpyAsync(dropped_before, e->d_out_count.p + 3, sizeof(dropped_before), cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 
 	for (;;) {
@@ -1214,7 +1214,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		poke(e->d_retry_ctl.p, retry_ctl.data(), 2*nos*sizeof(uint32_t), e->stream, &e->stats.kernel_launches);
 		CUDA_OK(cudaMemsetAsync(e->d_retry_ctl.p + 2*nos, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 		{
-			const uint32_t init[4] = {base_count, 0, 0, nonbinding_before};
+			const uint32_t init[5] = {base_count, 0, 0, dropped_before[0], dropped_before[1]};
 			poke(e->d_out_count.p, init, sizeof(init), e->stream, &e->stats.kernel_launches);
 		}
 		poke(e->d_cells.p, &cells_before, sizeof(cells_before), e->stream, &e->stats.kernel_launches);
@@ -1619,11 +1619,13 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	const size_t nos = set.os.size();
 	const size_t n_assays = e->assays.size();
 
-	std::vector<Region> regions(groups.size());
+	// one whole fragment per group, cut into pieces so that a few groups still fill the device
+	const uint32_t piece = 16384;
+	std::vector<Region> regions;
 	std::vector<uint64_t> per_assay(n_assays, 0);
 	for (size_t g = 0; g < groups.size(); ++g) {
 		const uint32_t len = e->targets[groups[g].target].len;
-		regions[g] = Region{groups[g].target, 0u, len, groups[g].assay};
+		for (uint32_t s0 = 0; s0 < len; s0 += piece) regions.push_back(Region{groups[g].target, s0, std::min(len, s0 + piece), groups[g].assay});
 		per_assay[(size_t)groups[g].assay] += len;
 	}
 	uint64_t worst = 0;
@@ -1642,6 +1644,7 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 		ra.s = scan_args(e, set, cap);
 		ra.regions = e->d_regions.p;
 		ra.nregions = (uint32_t)regions.size();
+		ra.whole_fragment = 1;
 		const uint32_t grid = std::min<uint32_t>((uint32_t)regions.size(), (uint32_t)e->sm_count*64u);
 		CUDA_OK(cudaEventRecord(e->ev[0], e->stream));
 		k_region_scan<<<grid, SCAN_THREADS, 0, e->stream>>>(ra);
@@ -1716,8 +1719,10 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 		return key_less(a, b);
 	});
 	size_t at = 0;
-	for (const GroupKey &g : groups) {
-		std::vector<ReplaySeed> gs;
+	std::vector<std::vector<ReplaySeed>> group_seeds(groups.size());
+	for (size_t gidx = 0; gidx < groups.size(); ++gidx) {
+		const GroupKey &g = groups[gidx];
+		std::vector<ReplaySeed> &gs = group_seeds[gidx];
 		while (at < seed_keys.size() && (seed_keys[at].target < g.target ||
 			(seed_keys[at].target == g.target && set.os[seed_keys[at].os].assay < g.assay))) ++at;
 		for (; at < seed_keys.size() && seed_keys[at].target == g.target && set.os[seed_keys[at].os].assay == g.assay; ++at) {
@@ -1731,10 +1736,116 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 			r.site = (it != site_keys.end() && !key_less(k, *it)) ? it->idx : -1;
 			gs.push_back(r);
 		}
-		const AssayHost &as = e->assays[(size_t)g.assay];
-		replay_pcr_group(std::move(gs), sites, ao, !as.P.empty(), g.assay, as.id, out_hits, out_refs);
+	}
+	// the groups are independent: a few host threads when there are many, results in group order
+	const unsigned nthreads = groups.size() < 16 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+	std::vector<std::vector<tnt_hit>> part_hits(nthreads);
+	std::vector<std::vector<HitSites>> part_refs(nthreads);
+	std::vector<std::string> errors(nthreads);
+	auto work = [&](unsigned t) {
+		const size_t per = (groups.size() + nthreads - 1)/nthreads;
+		try {
+			for (size_t gidx = t*per; gidx < std::min(groups.size(), (t + 1)*per); ++gidx) {
+				const AssayHost &as = e->assays[(size_t)groups[gidx].assay];
+				replay_pcr_group(std::move(group_seeds[gidx]), sites, ao, !as.P.empty(), groups[gidx].assay, as.id, part_hits[t], part_refs[t]);
+			}
+		}
+		catch (const std::exception &ex) { errors[t] = ex.what(); }
+	};
+	if (nthreads == 1) work(0);
+	else {
+		std::vector<std::thread> pool;
+		for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
+		for (std::thread &t : pool) t.join();
+	}
+	for (const std::string &err : errors) if (!err.empty()) throw std::runtime_error(err);
+	for (unsigned t = 0; t < nthreads; ++t) {
+		out_hits.insert(out_hits.end(), part_hits[t].begin(), part_hits[t].end());
+		out_refs.insert(out_refs.end(), part_refs[t].begin(), part_refs[t].end());
 	}
 	(void)o;
+}
+
+// Which groups with a hit does the reference possibly treat differently from a join over all bound
+// sites?  Two ways the culls of amplicon() can lose a site (assemble.h):
+//  (1) two bound sites of the group whose order by (loc_5, loc_3) is not strictly their order by
+//      seed position (only possible within CROWD_REACH bases; `crowded` holds every site with such a
+//      neighbour).  Exact duplicates -- one oligo strand, one (loc_5, loc_3), two seed diagonals --
+//      are no such pair: a bind step hands back one site per range, so they never meet as bound
+//      sites; they count as alternative seeds of their site in (2).
+//  (2) a hit whose own sites do not validate each other in every cull: the culls see the seed
+//      positions, so forward site, probe site and reverse site must follow each other strictly by
+//      seed position and within reach -- for every duplicate seed of each site.
+// Everything else is reported by the reference exactly as the join over all sites reports it.
+std::vector<GroupKey> groups_to_replay(tnt_engine *e, const tnt_search_options &o, const std::vector<BoundSite> &sites,
+	const std::vector<HitSites> &refs, std::vector<CrowdRec> &crowded, bool replay_all)
+{
+	auto group_of_rec = [&](const CrowdRec &c) { return GroupKey{c.target, (int)c.assay}; };
+	{
+		// only the groups with a hit matter: drop the rest before sorting
+		std::vector<GroupKey> hit_groups;
+		for (const tnt_hit &h : e->hits)
+			if (hit_groups.empty() || !(hit_groups.back() == GroupKey{h.target_id, h.assay_index})) hit_groups.push_back(GroupKey{h.target_id, h.assay_index});
+		size_t m = 0;
+		for (const CrowdRec &c : crowded)
+			if (std::binary_search(hit_groups.begin(), hit_groups.end(), group_of_rec(c))) crowded[m++] = c;
+		crowded.resize(m);
+	}
+	std::sort(crowded.begin(), crowded.end(), [&](const CrowdRec &a, const CrowdRec &b) {
+		if (a.target != b.target) return a.target < b.target;
+		if (a.assay != b.assay) return a.assay < b.assay;
+		if (a.loc5 != b.loc5) return a.loc5 < b.loc5;
+		if (a.loc3 != b.loc3) return a.loc3 < b.loc3;
+		return a.rec < b.rec;
+	});
+	auto group_range = [&](const GroupKey &g) {
+		const auto lo = std::lower_bound(crowded.begin(), crowded.end(), g, [&](const CrowdRec &c, const GroupKey &k) { return group_of_rec(c) < k; });
+		auto hi = lo;
+		while (hi != crowded.end() && group_of_rec(*hi) == g) ++hi;
+		return std::make_pair(lo, hi);
+	};
+	std::vector<GroupKey> groups;
+	for (size_t i = 0; i < e->hits.size();) {
+		const tnt_hit &h = e->hits[i];
+		const GroupKey g{h.target_id, h.assay_index};
+		size_t j = i;
+		while (j < e->hits.size() && e->hits[j].target_id == g.target && e->hits[j].assay_index == g.assay) ++j;
+		if (h.forward.oligo == TNT_OLIGO_NONE) { i = j; continue; } // probe-only assay in a PCR run
+		bool need = replay_all;
+		const auto range = group_range(g);
+		// (1) neighbours whose two orders disagree
+		for (auto a = range.first; !need && a != range.second; ++a)
+			for (auto b = a + 1; !need && b != range.second && b->loc5 - a->loc5 <= CROWD_REACH; ++b) {
+				if (a->rec == b->rec) continue; // reported twice (hash collision)
+				const bool same_range = a->loc5 == b->loc5 && a->loc3 == b->loc3;
+				if (same_range && a->os == b->os) continue; // duplicate seeds of one site
+				if (same_range || !(a->t < b->t)) need = true; // sorted by (loc_5, loc_3): the seeds must ascend strictly
+			}
+		// (2) every hit validates itself, whichever duplicate seed represents a site
+		auto seeds_of = [&](const BoundSite &s, uint32_t os_index, std::vector<uint32_t> &out) {
+			out.assign(1, s.target_loc);
+			for (auto c = range.first; c != range.second; ++c)
+				if (c->os == os_index && c->loc5 == s.loc5 && c->loc3 == s.loc3 && c->t != s.target_loc) out.push_back(c->t);
+		};
+		std::vector<uint32_t> tf, tr, tp;
+		const uint32_t threshold = o.max_len + 50;
+		for (size_t k = i; !need && k < j; ++k) {
+			const BoundSite &a = sites[(size_t)refs[k].forward], &b = sites[(size_t)refs[k].reverse];
+			const BoundSite &f = a.plus ? b : a, &r = a.plus ? a : b;
+			const BoundSite *p = refs[k].probe >= 0 ? &sites[(size_t)refs[k].probe] : nullptr;
+			seeds_of(f, f.os_index, tf);
+			seeds_of(r, r.os_index, tr);
+			if (p) seeds_of(*p, p->os_index, tp);
+			for (uint32_t x : tf)
+				for (uint32_t y : tr) {
+					if (!(x < y) || y - x > threshold) need = true;
+					if (p) for (uint32_t z : tp) if (!(x < z && z < y)) need = true;
+				}
+		}
+		if (need) groups.push_back(g);
+		i = j;
+	}
+	return groups;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1755,7 +1866,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	e->settle_upload();
 	e->sync_targets(false);
 	CUDA_OK(cudaMemsetAsync(e->d_cells.p, 0, sizeof(unsigned long long), e->stream));
-	CUDA_OK(cudaMemsetAsync(e->d_out_count.p + 3, 0, sizeof(uint32_t), e->stream));
+	CUDA_OK(cudaMemsetAsync(e->d_out_count.p + 3, 0, 2*sizeof(uint32_t), e->stream));
 	cudaEvent_t t_begin = e->ev[4], t_end = e->ev[5];
 	CUDA_OK(cudaEventRecord(t_begin, e->stream));
 
@@ -1797,28 +1908,30 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	}
 	const uint32_t n2 = e->n_bound;
 
-	// Groups with bound sites close to each other (k_crowd): candidates for the exact replay below
+	// Bound sites with a neighbour of their own group close by (k_crowd): input of the decision which
+	// groups have to be searched again step by step (groups_to_replay)
 	const bool pcr_primers = o.assay_format == TNT_ASSAY_PCR && !stage2.os.empty();
-	std::vector<uint64_t> crowded;
+	std::vector<CrowdRec> crowded;
 	if (pcr_primers && n2 != 0 && !(e->prm.reserved & TNT_ENGINE_KEEP_CULLED_SITES)) {
+		HostTimer t_crowd("crowded sites (k_crowd)");
 		uint32_t log2_bits = 22;
-		while (log2_bits < 33 && ((uint64_t)1 << log2_bits) < (uint64_t)n2*1024u) ++log2_bits;
+		while (log2_bits < 32 && ((uint64_t)1 << log2_bits) < (uint64_t)n2*1024u) ++log2_bits;
 		const size_t words = (size_t)(((uint64_t)1 << log2_bits)/32u);
 		uint32_t out_cap = (uint32_t)std::max<size_t>(e->d_crowd_out.cap, 1u << 16);
 		for (;;) {
-			e->d_crowd_bits.reserve(words + 1, 0, e->stream);
+			e->d_crowd_bits.reserve(2*words + 1, 0, e->stream);
 			e->d_crowd_out.reserve(out_cap, 0, e->stream);
-			CUDA_OK(cudaMemsetAsync(e->d_crowd_bits.p, 0, (words + 1)*sizeof(uint32_t), e->stream));
+			CUDA_OK(cudaMemsetAsync(e->d_crowd_bits.p, 0, (2*words + 1)*sizeof(uint32_t), e->stream));
 			CrowdArgs ca{};
 			ca.recs = e->d_bound.p;
+			ca.n = n2;
 			ca.os1 = stage1.d_os.p;
 			ca.os2 = stage2.d_os.p;
 			ca.nos1 = nos1;
-			ca.n = n2;
 			ca.bits = e->d_crowd_bits.p;
 			ca.log2_bits = log2_bits;
 			ca.out = e->d_crowd_out.p;
-			ca.out_count = e->d_crowd_bits.p + words;
+			ca.out_count = e->d_crowd_bits.p + 2*words;
 			ca.out_cap = out_cap;
 			k_crowd<<<gen_grid, 256, 0, e->stream>>>(ca, 0);
 			k_crowd<<<gen_grid, 256, 0, e->stream>>>(ca, 1);
@@ -1830,8 +1943,9 @@ void search(tnt_engine *e, const tnt_search_options &o)
 			if (cnt > out_cap) { out_cap = cnt + cnt/8; continue; }
 			crowded.resize(cnt);
 			if (cnt) {
-				CUDA_OK(cudaMemcpyAsync(crowded.data(), e->d_crowd_out.p, (size_t)cnt*sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+				CUDA_OK(cudaMemcpyAsync(crowded.data(), e->d_crowd_out.p, (size_t)cnt*sizeof(CrowdRec), cudaMemcpyDeviceToHost, e->stream));
 				CUDA_OK(cudaStreamSynchronize(e->stream));
+				e->stats.d2h_bytes += (uint64_t)cnt*sizeof(CrowdRec);
 			}
 			break;
 		}
@@ -1912,12 +2026,13 @@ void search(tnt_engine *e, const tnt_search_options &o)
 
 	CUDA_OK(cudaEventRecord(t_end, e->stream));
 	unsigned long long cells = 0;
-	uint32_t nonbinding = 0;
+	uint32_t dropped[2] = {0, 0};
 	CUDA_OK(cudaMemcpyAsync(&cells, e->d_cells.p, sizeof(cells), cudaMemcpyDeviceToHost, e->stream));
-	CUDA_OK(cudaMemcpyAsync(&nonbinding, e->d_out_count.p + 3, sizeof(nonbinding), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaMemcpyAsync(dropped, e->d_out_count.p + 3, sizeof(dropped), cudaMemcpyDeviceToHost, e->stream));
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 	e->stats.dp_cells = cells;
-	e->stats.nonbinding_dropped = nonbinding;
+	e->stats.nonbinding_dropped = dropped[0];
+	e->stats.undefined_dropped = dropped[1];
 	float ms = 0;
 	CUDA_OK(cudaEventElapsedTime(&ms, t_begin, t_end));
 	e->stats.total_ms = ms;
@@ -1955,21 +2070,11 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	// searched again step by step, exactly like the reference does it, and their hits replaced.
 	if (pcr_primers && !e->hits.empty() && !(e->prm.reserved & TNT_ENGINE_KEEP_CULLED_SITES)) {
 		const bool replay_all = std::getenv("TNT_REPLAY_ALL") != nullptr; // verification: every group with a hit
-		std::sort(crowded.begin(), crowded.end());
-		crowded.erase(std::unique(crowded.begin(), crowded.end()), crowded.end());
 		std::vector<GroupKey> groups;
-		for (size_t i = 0; i < e->hits.size(); ++i) {
-			const tnt_hit &h = e->hits[i];
-			if (h.forward.oligo == TNT_OLIGO_NONE) continue; // probe-only assay in a PCR run
-			const GroupKey g{h.target_id, h.assay_index};
-			if (!groups.empty() && groups.back() == g) continue; // hits are ordered by group
-			bool need = replay_all || std::binary_search(crowded.begin(), crowded.end(), ((uint64_t)g.target << 32) | (uint32_t)g.assay);
-			for (size_t j = i; !need && j < e->hits.size() && e->hits[j].target_id == g.target && e->hits[j].assay_index == g.assay; ++j) {
-				const BoundSite &a = sites[(size_t)refs[j].forward], &b = sites[(size_t)refs[j].reverse];
-				const BoundSite &minus_site = a.plus ? b : a, &plus_site = a.plus ? a : b;
-				need = !hit_order_is_safe(minus_site, plus_site, refs[j].probe >= 0 ? &sites[(size_t)refs[j].probe] : nullptr, o.max_len);
-			}
-			if (need) groups.push_back(g);
+		{
+			HostTimer t_sel("groups_to_replay");
+			groups = groups_to_replay(e, o, sites, refs, crowded, replay_all);
+			if (HostTimer::enabled()) fprintf(stderr, "[tnt]   crowded sites %zu, groups to replay %zu\n", crowded.size(), groups.size());
 		}
 		e->stats.replayed_groups = groups.size();
 		if (!groups.empty()) {

@@ -644,6 +644,8 @@ struct RegionScanArgs {
 	ScanArgs s;
 	const Region *regions;
 	uint32_t nregions;
+	uint32_t whole_fragment;   // 1: the regions are pieces of whole fragments (replay): the one-seed-per-diagonal
+	                           // rule looks back to the start of the fragment, not to the start of the piece
 };
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_region_scan(RegionScanArgs ra)
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_region_scan(RegionScanArgs ra)
 				const uint32_t ent = __ldg(a.wt.entry + e);
 				const uint32_t os = ent >> 8, k = ent & 0xffu;
 				if (a.os[os].assay != rg.assay) continue;
-				if (first_on_diagonal(a.db.db2, tg.base, p, k, rg.start, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os))
+				if (first_on_diagonal(a.db.db2, tg.base, p, k, ra.whole_fragment ? 0u : rg.start, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W, a.os_packed + 2*(size_t)os))
 					emit_candidate(a, os, rg.target, k, p);
 			}
 		}
@@ -786,7 +788,14 @@ __device__ inline void finish_alignment(const AlignArgs &a, const DpShared &sh, 
 	if (pass) pass = mm <= os.max_mismatch;
 	if (pass) pass = gaps <= os.max_gap;
 	if (pass) pass = poly <= os.max_poly_degen;
-	if (flags & (F_OOB | F_STACK | F_TRUNC)) pass = true; // surfaced to the host, which reports it
+	// The traceback left the matrix where the reference reads unchecked ring-buffer memory
+	// (nuc_cruc.cpp:1497-1541, only when a terminal penalty clamps to zero): no defined answer
+	// exists for this window; it is dropped and counted (tnt_stats::undefined_dropped), the rest of
+	// the search is unaffected.
+	if (flags & (F_OOB | F_STACK | F_TRUNC)) {
+		if (!a.emit_all) atomicAdd(a.out_count + 4, 1u);
+		pass = false;
+	}
 
 	if (!(a.emit_all || pass)) return;
 
@@ -1015,28 +1024,33 @@ __global__ void k_live_padlock(LiveArgs a, uint32_t n, int pass)
 }
 
 // ------------------------------------------------------------------------------------------
-// Which (fragment, assay) groups hold two bound sites close to each other?
+// Which bound sites have another bound site of their (fragment, assay) group close by?
 //
 // The reference's cull_oligo_match (amplicon_search.cpp:679-765) sorts a list that mixes bound sites
 // (ordered by loc_5 / loc_3) with not-yet-bound seeds (ordered by seed position) and stops its partner
 // scan on an unsigned difference of seed positions (:709).  That is only the pure optimisation it is
-// meant to be while bound sites of one assay keep their distance: two bound sites whose order by
-// loc_5 differs from their order by seed position (possible within about one oligo length) make
-// the scan break early and a real site is culled.  Such groups are searched again the way the
-// reference does it, step by step (engine.cu: replay).  This pair of kernels finds them: every
-// bound site sets a bit for (fragment, assay, loc_5 >> CROWD_SHIFT) in a hashed bitmap; a site that
-// finds its own bit already set, or a bit of a neighbouring bucket set, reports its group.  Hash
-// collisions only add groups to the replay list (which is exact for any group).
+// meant to be while the order of the bound sites by loc_5 agrees with their order by seed position;
+// the two can disagree only for sites less than an oligo length apart (a seed lies inside its
+// site).  When they do, the scan breaks early and a real site is culled.  The host decides that
+// pair by pair (engine.cu: groups_to_replay); this pair of kernels hands it the few sites that have
+// a neighbour at all: every bound site sets a bit for (fragment, assay, loc_5 >> CROWD_SHIFT) in a
+// hashed bitmap (a second bitmap records buckets hit twice); a site whose own bucket was hit twice
+// or whose neighbouring bucket is occupied is reported.  Hash collisions only add reports.
 // ------------------------------------------------------------------------------------------
-constexpr int CROWD_SHIFT = 8;
+constexpr int CROWD_SHIFT = 7;                      // buckets of 128 bases >= CROWD_REACH
+constexpr int CROWD_REACH = 2*MAX_OLIGO + 16;       // farthest two sites can be with their orders disagreeing
+static_assert((1 << CROWD_SHIFT) >= CROWD_REACH, "sites within reach share a bucket or sit in adjacent ones");
+
+struct CrowdRec { uint32_t target, assay, os; int32_t loc5, loc3; uint32_t t, rec, pad; };
 
 struct CrowdArgs {
 	const BoundRec *recs;
+	uint32_t n;
 	const OligoStrand *os1, *os2;
-	uint32_t nos1, n;
-	uint32_t *bits;               // 2^log2_bits bits, zero at the start of the mark pass
+	uint32_t nos1;
+	uint32_t *bits;               // [2][2^log2_bits bits]: occupied | hit twice; zero before pass 0
 	uint32_t log2_bits;
-	uint64_t *out;                // reported groups: target << 32 | assay
+	CrowdRec *out;
 	uint32_t *out_count;
 	uint32_t out_cap;
 };
@@ -1050,29 +1064,25 @@ __device__ __forceinline__ uint64_t crowd_hash(uint32_t target, uint32_t assay, 
 	return x;
 }
 
-__device__ __forceinline__ void crowd_report(const CrowdArgs &a, uint32_t target, uint32_t assay)
-{
-	const uint32_t slot = atomicAdd(a.out_count, 1u);
-	if (slot < a.out_cap) a.out[slot] = ((uint64_t)target << 32) | assay;
-}
-
 __global__ void k_crowd(CrowdArgs a, int pass)
 {
 	const uint64_t mask = ((uint64_t)1 << a.log2_bits) - 1u;
+	uint32_t *occupied = a.bits, *twice = a.bits + ((size_t)1 << (a.log2_bits - 5));
 	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += gridDim.x*blockDim.x) {
 		const BoundHead b = a.recs[i].h;
 		const OligoStrand &o = b.os < a.nos1 ? a.os1[b.os] : a.os2[b.os - a.nos1];
 		const uint32_t bucket = ((uint32_t)max(b.loc5, 0) >> CROWD_SHIFT) + 1u;
+		const uint64_t h = crowd_hash(b.target, (uint32_t)o.assay, bucket) & mask;
+		const uint32_t bit = 1u << (h & 31u);
 		if (pass == 0) {
-			const uint64_t h = crowd_hash(b.target, (uint32_t)o.assay, bucket) & mask;
-			const uint32_t bit = 1u << (h & 31u);
-			if (atomicOr(a.bits + (h >> 5), bit) & bit) crowd_report(a, b.target, (uint32_t)o.assay);
+			if (atomicOr(occupied + (h >> 5), bit) & bit) atomicOr(twice + (h >> 5), bit);
+			continue;
 		}
-		else {
-			const uint64_t h0 = crowd_hash(b.target, (uint32_t)o.assay, bucket - 1u) & mask;
-			const uint64_t h1 = crowd_hash(b.target, (uint32_t)o.assay, bucket + 1u) & mask;
-			if (((a.bits[h0 >> 5] >> (h0 & 31u)) | (a.bits[h1 >> 5] >> (h1 & 31u))) & 1u) crowd_report(a, b.target, (uint32_t)o.assay);
-		}
+		const uint64_t h0 = crowd_hash(b.target, (uint32_t)o.assay, bucket - 1u) & mask;
+		const uint64_t h1 = crowd_hash(b.target, (uint32_t)o.assay, bucket + 1u) & mask;
+		if (!(((twice[h >> 5] >> (h & 31u)) | (occupied[h0 >> 5] >> (h0 & 31u)) | (occupied[h1 >> 5] >> (h1 & 31u))) & 1u)) continue;
+		const uint32_t slot = atomicAdd(a.out_count, 1u);
+		if (slot < a.out_cap) a.out[slot] = CrowdRec{b.target, (uint32_t)o.assay, b.os, b.loc5, b.loc3, b.t, i, 0u};
 	}
 }
 
@@ -1174,8 +1184,13 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 			tv.trace = trace;
 			tv.Lt = Lt;
 			uint16_t cells[MAX_MAXCELLS];
-			const int ncells = collect_max_cells<ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
-			nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);
+			int cursor = dp.last_raise < 0 ? 0 : dp.last_raise, remaining = dp.nmax;
+			bool fresh = true;
+			do {
+				const int ncells = collect_max_cells<ALIGN_THREADS>(tv, os.len, Lt, cursor, remaining, cells);
+				nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
+				fresh = false;
+			} while (remaining > 0 && !(flags & (F_OOB | F_STACK)));
 		}
 		const uint32_t idx = unit.begin + tid;
 		finish_alignment(a, sh, os, unit.os, target, k, c.t, start, stop, tgt, Lt, best, best_aln, flags,
@@ -1329,6 +1344,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 				ColMajorTraceFull<LQ, ALIGN_THREADS> tv;
 				tv.trace32 = trace32;
 				if (dp.runmax <= 0) handoff = 2; // the reference's ">= -1" rule decides: not recorded here
+				else if (dp.nmax > MAX_MAXCELLS) handoff = 2; // the generic kernel walks any number of tied cells
 				else {
 					const int ncells = collect_max_cells_full<LQ, ALIGN_THREADS>(tv, dp, os.len, Lt, cells, flags);
 					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags);

@@ -91,7 +91,8 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64),
                 ("scan_ms", C.c_double), ("align_ms", C.c_double), ("pair_ms", C.c_double),
                 ("total_ms", C.c_double), ("scan_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("replayed_groups", C.c_uint64), ("nonbinding_dropped", C.c_uint64)]
+                ("replayed_groups", C.c_uint64), ("undefined_dropped", C.c_uint64),
+                ("nonbinding_dropped", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -433,6 +434,14 @@ class Engine:
         kernel launch and one device-to-host copy for all of them)."""
         n, text, offs = self.hit_sequences_raw()
         return [text[offs[i]:offs[i + 1] - 1].decode() for i in range(n)]
+
+    def hit_sequences_bytes(self):
+        """tnt_engine_hit_sequences without materialising anything in Python: (n_hits, text bytes)."""
+        text = C.c_void_p()
+        offs = C.POINTER(C.c_uint64)()
+        n = C.c_size_t()
+        self._check(self.L.tnt_engine_hit_sequences(self.h, C.byref(text), C.byref(offs), C.byref(n)))
+        return n.value, (int(offs[n.value]) if n.value else 0)
 
     def hit_sequences_raw(self):
         """(n_hits, text bytes, offsets) as the C ABI hands them out."""
