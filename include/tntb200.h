@@ -322,6 +322,43 @@ int tnt_engine_oligo_dimer(tnt_engine *e, const char *query, const char *target,
  * the HBM roofline): returns the number of unique candidates and the device time. */
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms);
 
+/* ---- Gathering and finishing hit lists on the host (no GPU needed) ----
+ * What the reference driver does with the lists its search calls return: hits that touch a cut
+ * edge of their fragment are dropped (tntblast_local.cpp:635-648), coordinates become record
+ * coordinates and target_id the record index (:650-654), the lists of one assay id are joined
+ * (:701-706), and per assay id: select_best_match (tntblast_util.cpp:1482-1547) if `best_match`,
+ * uniquify_results (:1555-1755) if any record was cut (`uniquify_mode` < 0: decide from the
+ * fragment tables; 0 / 1: never / always), sort by hybrid_sig::operator< (tntblast_local.cpp:918-930).
+ * Blocks are the hit lists of any number of engines -- the shards of a database spread over several
+ * GPUs -- each with the table of the fragments it holds (by target_id); pass them in shard order. */
+typedef struct {
+	uint32_t record;           /* index of the database record the fragment was cut from */
+	uint32_t start;            /* first base of the piece in the record (local_target_start) */
+	uint32_t stop;             /* nominal inclusive stop (local_target_stop) */
+	uint32_t max_stop;         /* local_target_max_stop */
+	uint32_t len;              /* bases held: piece + right overlap */
+} tnt_fragment;
+
+typedef struct {
+	const tnt_hit *hits;       /* as tnt_engine_get_hits hands them out: ordered by (target_id, assay_index) */
+	size_t n_hits;
+	const char *arena;
+	const tnt_fragment *fragments;
+	size_t n_fragments;
+} tnt_hit_block;
+
+typedef struct {
+	uint32_t block, index;     /* where the hit came from: blocks[block].hits[index] (alignment text: that block's arena) */
+	tnt_hit hit;               /* record coordinates, target_id = record index */
+} tnt_final_hit;
+
+/* `assays`: the array given to tnt_engine_set_assays (ids, oligo lengths).  The result is allocated
+ * by the library: release it with tnt_free.  Error text: tnt_postprocess_error(). */
+int tnt_finalize_hits(const tnt_hit_block *blocks, size_t n_blocks, const tnt_assay *assays, int32_t n_assays,
+	int32_t best_match, int32_t uniquify_mode, tnt_final_hit **out, size_t *n_out);
+void tnt_free(void *p);
+const char *tnt_postprocess_error(void);
+
 /* ---- Host-only diagnostics (no GPU needed; used by the CPU test-suite) ---- */
 
 /* The integer penalty table of NucCruc::update_dp_param (nuc_cruc.cpp:340-487) and the

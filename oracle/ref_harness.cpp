@@ -490,3 +490,47 @@ extern "C" void ref_seq_len_increment(uint32_t len, uint32_t max_len, uint32_t *
 	*delta = r.first;
 	*pieces = r.second;
 }
+
+// ---------------------------------------------------------------------------
+// Post-processing: the reference's select_best_match / uniquify_results / sort on one list
+// ---------------------------------------------------------------------------
+extern "C" long ref_finalize(const ref_post_hit *hits, long n, int best_match, int uniquify, int32_t *order_out)
+{
+	GUARD_BEGIN
+	std::unordered_map<std::string, size_t> str_table;
+	std::list<hybrid_sig> l;
+	for (long i = 0; i < n; ++i) {
+		const ref_post_hit &h = hits[i];
+		hybrid_sig s;
+		s.my_id(h.id);
+		s.my_degen_id(h.degen_id);
+		s.seq_id(h.seq_id);
+		s.name_str_index = str_to_index("assay", str_table);
+		if (h.has_primers) {
+			// only the lengths of the oligo strings matter to uniquify_results (:1601-1602)
+			s.forward_oligo_str_index = str_to_index(std::string((size_t)h.forward_len, 'A'), str_table);
+			s.reverse_oligo_str_index = str_to_index(std::string((size_t)h.reverse_len, 'C'), str_table);
+			s.amplicon_range = std::make_pair(h.amp_first, h.amp_last);
+			s.forward_tm = h.forward_tm;
+			s.reverse_tm = h.reverse_tm;
+			s.forward_align_str_index = str_to_index(deflate_dna_seq(h.forward_align), str_table);
+			s.reverse_align_str_index = str_to_index(deflate_dna_seq(h.reverse_align), str_table);
+		}
+		if (h.has_probe) {
+			s.probe_oligo_str_index = str_to_index(std::string("GGGG"), str_table);
+			s.probe_range = std::make_pair(h.probe_first, h.probe_last);
+			s.probe_tm = h.probe_tm;
+			s.probe_align_str_index = str_to_index(deflate_dna_seq(h.probe_align), str_table);
+		}
+		s.forward_degen = (int)i; // carries the input index through the list operations
+		l.push_back(s);
+	}
+	const std::vector<std::string> index_table = ordered_keys(str_table);
+	if (best_match) select_best_match(l);
+	if (uniquify) uniquify_results(l, index_table);
+	l.sort();
+	long k = 0;
+	for (std::list<hybrid_sig>::const_iterator i = l.begin(); i != l.end(); ++i) order_out[k++] = i->forward_degen;
+	return k;
+	GUARD_END
+}

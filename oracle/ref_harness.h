@@ -103,6 +103,20 @@ long ref_fasta_read(long index, uint32_t start, uint32_t stop, int whole, uint8_
 void ref_fasta_close(void);
 void ref_seq_len_increment(uint32_t len, uint32_t max_len, uint32_t *delta, uint32_t *pieces);
 
+/* Post-processing of a result list by the reference's own select_best_match / uniquify_results
+ * (tntblast_util.cpp:1482-1755) and hybrid_sig::operator< sort (tntblast_local.cpp:918-930).  `hits`
+ * is ONE list in the order the driver would hold it (all records of one assay id); the indices of
+ * the surviving records come back in output order.  Returns their number, -1 on a throw. */
+typedef struct {
+	int32_t id, degen_id, seq_id;
+	int32_t has_primers, has_probe;
+	int32_t amp_first, amp_last, probe_first, probe_last;
+	float forward_tm, reverse_tm, probe_tm;
+	int32_t forward_len, reverse_len;            /* lengths of the oligos in the forward / reverse slot */
+	const char *forward_align, *reverse_align, *probe_align;
+} ref_post_hit;
+long ref_finalize(const ref_post_hit *hits, long n, int best_match, int uniquify, int32_t *order_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,16 @@ def revcomp(s: str) -> str:
     return s.translate(_COMP)[::-1]
 
 
+class PostHit(C.Structure):
+    """ref_post_hit (oracle/ref_harness.h)."""
+    _fields_ = [("id", C.c_int32), ("degen_id", C.c_int32), ("seq_id", C.c_int32),
+                ("has_primers", C.c_int32), ("has_probe", C.c_int32),
+                ("amp_first", C.c_int32), ("amp_last", C.c_int32), ("probe_first", C.c_int32), ("probe_last", C.c_int32),
+                ("forward_tm", C.c_float), ("reverse_tm", C.c_float), ("probe_tm", C.c_float),
+                ("forward_len", C.c_int32), ("reverse_len", C.c_int32),
+                ("forward_align", C.c_char_p), ("reverse_align", C.c_char_p), ("probe_align", C.c_char_p)]
+
+
 class _Lib:
     """Common binding: the reference harness and the C restatement export the same symbols
     with a different prefix (``ref_`` / ``orc_``)."""
@@ -268,6 +278,18 @@ class _Lib:
         got = self._get_hits(arr, n)
         return [arr[i] for i in range(got)]
 
+
+    def finalize(self, hits: Sequence[PostHit], best_match: bool, uniquify: bool) -> List[int]:
+        """One result list through the reference's select_best_match / uniquify_results / sort (only the
+        compiled reference exports it): indices of the surviving records in output order."""
+        f = getattr(self.lib, self.prefix + "finalize")
+        f.restype = C.c_long
+        f.argtypes = [C.POINTER(PostHit), C.c_long, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+        n = len(hits)
+        arr = (PostHit * max(n, 1))(*hits)
+        out = (C.c_int32 * max(n, 1))()
+        k = self._check(f(arr, n, int(best_match), int(uniquify), out))
+        return [out[i] for i in range(k)]
 
     def dimer(self, query: str, target: Optional[str] = None, T=310.15, na=0.05, conc_a=9.0e-7, conc_b=9.0e-7) -> AlignOut:
         """Homodimer (target None) or heterodimer Tm of oligos, as tntblast_local.cpp:657-686 computes them."""

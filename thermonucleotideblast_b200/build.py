@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtntb200.so")
 
-SOURCES = ["engine.cu", "assemble.cpp", "thermo.cpp"]
+SOURCES = ["engine.cu", "assemble.cpp", "thermo.cpp", "postprocess.cpp"]
 HEADERS = ["kernels.cuh", "fasta.cuh", "align_core.cuh", "tnt_types.h", "thermo.h", "assemble.h",
            "santalucia_tables.inc", os.path.join("..", "..", "include", "tntb200.h")]
 

@@ -138,6 +138,22 @@ class FastaFragment(C.Structure):
                 ("len", C.c_uint32), ("target_id", C.c_uint32)]
 
 
+class Fragment(C.Structure):
+    """tnt_fragment (include/tntb200.h): one piece of a database record as the driver cut it."""
+    _fields_ = [("record", C.c_uint32), ("start", C.c_uint32), ("stop", C.c_uint32), ("max_stop", C.c_uint32), ("len", C.c_uint32)]
+
+
+class HitBlock(C.Structure):
+    """tnt_hit_block (include/tntb200.h)."""
+    _fields_ = [("hits", C.POINTER(CHit)), ("n_hits", C.c_size_t), ("arena", C.c_char_p),
+                ("fragments", C.POINTER(Fragment)), ("n_fragments", C.c_size_t)]
+
+
+class FinalHit(C.Structure):
+    """tnt_final_hit (include/tntb200.h)."""
+    _fields_ = [("block", C.c_uint32), ("index", C.c_uint32), ("hit", CHit)]
+
+
 @dataclass
 class Assay:
     id: int
@@ -201,6 +217,11 @@ def load_library() -> C.CDLL:
     L.tnt_engine_hit_sequence.argtypes = [vp, C.POINTER(CHit), C.c_char_p, C.c_size_t]
     L.tnt_engine_hit_sequence.restype = C.c_long
     L.tnt_engine_hit_sequences.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_size_t)]
+    L.tnt_finalize_hits.argtypes = [C.POINTER(HitBlock), C.c_size_t, C.POINTER(CAssay), C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.POINTER(FinalHit)), C.POINTER(C.c_size_t)]
+    L.tnt_free.argtypes = [C.c_void_p]
+    L.tnt_free.restype = None
+    L.tnt_postprocess_error.restype = C.c_char_p
     L.tnt_engine_seeds.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, u32p, u32p, C.c_long]
     L.tnt_engine_seeds.restype = C.c_long
     L.tnt_engine_align.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, C.c_float, u32p, u32p,
@@ -213,6 +234,48 @@ def load_library() -> C.CDLL:
 
 class EngineError(RuntimeError):
     pass
+
+
+def c_assays(assays: Sequence["Assay"]):
+    """(array of tnt_assay, keep-alive list) for a list of Assay."""
+    arr = (CAssay * max(len(assays), 1))()
+    keep = []
+    for i, a in enumerate(assays):
+        f = a.forward.encode() if a.forward else None
+        r = a.reverse.encode() if a.reverse else None
+        p = a.probe.encode() if a.probe else None
+        keep.extend([f, r, p])
+        arr[i] = CAssay(a.id, f, r, p, a.forward_degen, a.reverse_degen, a.probe_degen)
+    return arr, keep
+
+
+def finalize_hits(blocks, assays: Sequence["Assay"], best_match: bool = False, uniquify: Optional[bool] = None):
+    """tnt_finalize_hits: the reference driver's post-processing (truncation filter, record coordinates,
+    select_best_match, uniquify_results, sort) over the hit lists of one or several engines.
+
+    `blocks`: list of (hits_bytes, n_hits, arena_bytes, fragments) per engine, where hits_bytes / arena_bytes
+    are what Engine.hit_records() returns and `fragments` a list of (record, start, stop, max_stop, len)
+    by target id.  Returns a list of (block, index, CHit) in output order.  Runs on the host; no GPU."""
+    L = load_library()
+    nb = len(blocks)
+    cb = (HitBlock * max(nb, 1))()
+    keep = []
+    for i, (hit_bytes, n_hits, arena, frags) in enumerate(blocks):
+        hbuf = C.create_string_buffer(hit_bytes, max(len(hit_bytes), 1))
+        abuf = C.create_string_buffer(arena, max(len(arena), 1) + 1)
+        fr = (Fragment * max(len(frags), 1))(*[Fragment(*f) for f in frags])
+        keep.extend([hbuf, abuf, fr])
+        cb[i] = HitBlock(C.cast(hbuf, C.POINTER(CHit)), n_hits, C.cast(abuf, C.c_char_p), fr, len(frags))
+    arr, keep2 = c_assays(assays)
+    out = C.POINTER(FinalHit)()
+    n = C.c_size_t()
+    mode = -1 if uniquify is None else int(bool(uniquify))
+    rc = L.tnt_finalize_hits(cb, nb, arr, len(assays), int(best_match), mode, C.byref(out), C.byref(n))
+    if rc < 0:
+        raise EngineError(L.tnt_postprocess_error().decode())
+    res = [(out[i].block, out[i].index, CHit.from_buffer_copy(out[i].hit)) for i in range(n.value)]
+    L.tnt_free(out)
+    return res
 
 
 class FragmentList:
@@ -353,14 +416,7 @@ class Engine:
 
     # -- assays ----------------------------------------------------------------------------
     def set_assays(self, assays: Sequence[Assay]):
-        arr = (CAssay * max(len(assays), 1))()
-        keep = []
-        for i, a in enumerate(assays):
-            f = a.forward.encode() if a.forward else None
-            r = a.reverse.encode() if a.reverse else None
-            p = a.probe.encode() if a.probe else None
-            keep.extend([f, r, p])
-            arr[i] = CAssay(a.id, f, r, p, a.forward_degen, a.reverse_degen, a.probe_degen)
+        arr, keep = c_assays(assays)
         self._check(self.L.tnt_engine_set_assays(self.h, arr, len(assays)))
 
     # -- search ----------------------------------------------------------------------------
