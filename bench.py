@@ -462,8 +462,188 @@ def packed_leg(eng, frag_list, opts, units, want_hits, max_over_ranks, barrier, 
             "what": "tnt_engine_import_packed (2 bit/base + mask + non-ACGT list + fragment table, page-locked host memory) + search + hit read-back"}
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[4]: ONE database partitioned over the ranks (strong scaling)
+# ---------------------------------------------------------------------------------------------
+def run_config5(args, rank, local_rank, world):
+    """1000 PCR assays against one database of args.mbp Mbp in all, cut into the reference's fragments
+    and dealt out in contiguous shards (sharding.shard_targets); every rank searches its shard on
+    its GPU, the tnt_hit records travel to rank 0 over the host (gloo: no NCCL in the data path) and
+    are finished there with tnt_finalize_hits (truncation filter at the cuts, record coordinates,
+    uniquify_results in the overlaps)."""
+    import pickle
+    import torch
+    import torch.distributed as dist
+    from thermonucleotideblast_b200 import Assay, Engine, FragmentList, search_options
+    from thermonucleotideblast_b200.engine import finalize_hits
+    from thermonucleotideblast_b200.sharding import fragment_record, shard_targets
+
+    torch.cuda.set_device(local_rank)
+    host_group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")
+
+    n_records = max(1, args.mbp * 1_000_000 // RECORD_BP)
+    assays = gen.config5_assays(args.assays)
+    # global fragment table (record, start, stop, max_stop, len) in database order
+    table = []
+    for r in range(n_records):
+        for (a, b) in fragment_record(RECORD_BP, FRAGMENT_BP):
+            table.append((r, a, b, RECORD_BP - 1, min(RECORD_BP, b + 1 + OVERLAP) - a))
+    lo, hi = shard_targets([t[4] for t in table], world)[rank]
+    mine = table[lo:hi]
+    own_records = sorted({t[0] for t in mine})
+    store = torch.empty(len(own_records) * RECORD_BP, dtype=torch.uint8, pin_memory=True).numpy()
+    rec_view = {}
+    for k, r in enumerate(own_records):
+        rec_view[r] = store[k * RECORD_BP:(k + 1) * RECORD_BP]
+        gen.config5_record(r, assays, rec_view[r])
+    fragments = [rec_view[r][a:a + n] for (r, a, b, ms, n) in mine]
+    frag_list = FragmentList(fragments)
+    shard_bases = int(sum(len(f) for f in fragments))
+    db_bases = n_records * RECORD_BP
+
+    opts = search_options(min_primer_tm=MIN_PRIMER_TM, max_len=MAX_LEN)
+    eng = Engine(device=local_rank)
+    alist = [Assay(i, a[0], a[1], None) for i, a in enumerate(assays)]
+    eng.set_assays(alist)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # ---- resident ---------------------------------------------------------------------------
+    eng.add_targets(frag_list)
+    for _ in range(args.warmup):
+        eng.search_raw(opts)
+    sampler = ClockSampler(local_rank, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = scan_ms = align_ms = 0.0
+    launches = 0
+    for step in range(args.steps):
+        sampler.start_step(step, 0.010)
+        nhits = eng.search_raw(opts)
+        sampler.end_step()
+        st = eng.stats()
+        dev_ms += st.total_ms
+        scan_ms += st.scan_ms
+        align_ms += st.align_ms
+        launches += st.kernel_launches
+    barrier()
+    dt = reduce((time.perf_counter() - t0) / args.steps, dist.ReduceOp.MAX if world > 1 else None)
+    sampler.extra_step(lambda: eng.search_raw(opts), 0.010, n=1)
+    clocks = sampler.result()
+    units = db_bases * len(assays) / 1e9
+
+    # ---- end to end: host fragments -> per-rank hits -> gathered, finished hit list on rank 0 ------
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    t0 = time.perf_counter()
+    gather_s = finalize_s = 0.0
+    final = None
+    for _ in range(e2e_steps):
+        eng.clear_targets()
+        eng.add_targets(frag_list)
+        eng.search_raw(opts)
+        n, raw, text = eng.hit_records()
+        eng.hit_sequences_bytes()
+        d2h = int(eng.stats().d2h_bytes)
+        tg = time.perf_counter()
+        block = (raw, n, text, [tuple(t) for t in mine])
+        if world > 1:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(block, gathered, dst=0, group=host_group)
+        else:
+            gathered = [block]
+        gather_s += time.perf_counter() - tg
+        if rank == 0:
+            tf = time.perf_counter()
+            final = finalize_hits(gathered, alist)
+            finalize_s += time.perf_counter() - tf
+    barrier()
+    e2e_dt = reduce((time.perf_counter() - t0) / e2e_steps, dist.ReduceOp.MAX if world > 1 else None)
+
+    aligns = reduce(float(st.alignments), dist.ReduceOp.SUM if world > 1 else None)
+    cells = reduce(float(st.dp_cells), dist.ReduceOp.SUM if world > 1 else None)
+    raw_hits = reduce(float(nhits), dist.ReduceOp.SUM if world > 1 else None)
+    align_s = reduce(align_ms / args.steps / 1e3, dist.ReduceOp.MAX if world > 1 else None)
+    scan_s = reduce(scan_ms / args.steps / 1e3, dist.ReduceOp.MAX if world > 1 else None)
+    sm_max = clocks.get("sm_max_mhz") or 1965.0
+    alu_peak = world * SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12
+    alu_achieved = ALU_OPS_PER_CELL * cells / align_s / 1e12 if align_s > 0 else 0.0
+
+    # optional check (small sizes): the gathered, finished list equals what ONE engine holding the whole database gives
+    verify = None
+    if args.verify_shards and rank == 0:
+        whole = np.empty(n_records * RECORD_BP, dtype=np.uint8)
+        for r in range(n_records):
+            gen.config5_record(r, assays, whole[r * RECORD_BP:(r + 1) * RECORD_BP])
+        e1 = Engine(device=local_rank)
+        e1.set_assays(alist)
+        e1.add_targets([whole[r * RECORD_BP + a: r * RECORD_BP + a + n] for (r, a, b, ms, n) in table])
+        e1.search_raw(opts)
+        n1, raw1, text1 = e1.hit_records()
+        single = finalize_hits([(raw1, n1, text1, [tuple(t) for t in table])], alist)
+        e1.close()
+        key = lambda c: (c.assay_index, c.target_id, c.amp_first, c.amp_last, c.primer_strand, c.forward.tm, c.reverse.tm,
+                         c.forward.num_mm, c.reverse.num_mm)
+        verify = {"single_engine_hits": len(single), "sharded_hits": len(final),
+                  "identical": [key(c) for (_, _, c) in single] == [key(c) for (_, _, c) in final]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": units / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 (DP) + f32 (dH/dS/Tm)", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: %d PCR assays (-e %g) vs ONE synthetic database of %.3g Gbp (%d records of 5 Mbp, "
+                                   "<=%d kbp fragments + %d bp overlap) partitioned over %d GPU(s) in contiguous shards"
+                                   % (len(assays), MIN_PRIMER_TM, db_bases / 1e9, n_records, FRAGMENT_BP // 1000, OVERLAP, world),
+                       "db_bases_total": db_bases, "fragments_total": len(table), "fragments_rank0": len(mine),
+                       "fragment_bases_rank0": shard_bases, "assays": len(assays),
+                       "l2": "inputs larger than L2 (packed shard %.0f MB + candidate buffers)" % (shard_bases * 0.375 / 1e6)},
+            "alignments_per_s": aligns / dt, "alignments_per_step": aligns, "dp_cells_per_step": cells,
+            "hits_per_step_all_ranks_before_gather": int(raw_hits), "hits_after_finalize": len(final) if final is not None else None,
+            "device_ms_per_step": dev_ms / args.steps,
+            "kernel_ms_per_step": {"seed_scan": scan_s * 1e3, "nuccruc_align": align_s * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": units / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": shard_bases, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
+                    "result": "tnt_hit records + alignment strings + amplicon text of every rank, gathered on rank 0 over the host "
+                              "(gloo) and finished with tnt_finalize_hits (truncation filter, record coordinates, uniquify_results)",
+                    "gather_ms_per_step": gather_s / e2e_steps * 1e3, "finalize_ms_per_step": finalize_s / e2e_steps * 1e3},
+            "roofline": {"bound": "alu-int32", "achieved": alu_achieved, "peak": alu_peak, "unit": "TOP/s",
+                         "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": None,
+                         "kernel": "k_align_fast (NucCruc DP + traceback + evaluation)",
+                         "note": "27 int32 ALU ops per DP cell (SURVEY 8d) x cells of all ranks / max-over-ranks kernel time; "
+                                 "peak = n_gpus x 148 SM x 128 lanes x %.0f MHz (nominal)" % sm_max},
+            "cpu_baseline": {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "measured by the default (configs[1]) run"},
+        }
+        if verify is not None:
+            line["sharded_equals_single_engine"] = verify
+        _emit(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="2: BASELINE configs[1], weak scaling (default, the metric's configuration); "
+                         "5: configs[4], one database partitioned over the GPUs (strong scaling; --mbp = total size)")
+    ap.add_argument("--verify-shards", action="store_true", help="--config 5: also search everything with one engine and compare")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
@@ -524,6 +704,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    if args.config == 5:
+        if args.assays == 100:
+            args.assays = 1000
+        return run_config5(args, rank, local_rank, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -209,3 +209,29 @@ def write_assays(path: str, assays) -> None:
             if P:
                 cols.append(P)
             f.write("\t".join(cols) + "\n")
+
+
+# -- BASELINE configs[4]: a database every rank can generate piecewise ----------------------------
+def config5_assays(n_assays: int):
+    arng = np.random.default_rng(55)
+    return [(rand_oligo(int(arng.integers(18, 23)), arng), rand_oligo(int(arng.integers(19, 24)), arng), None)
+            for _ in range(n_assays)]
+
+
+def config5_record(r: int, assays, out: np.ndarray):
+    """Record r of the synthetic GenBank-scale database: 5 Mbp of uniform bases, seeded by the record
+    index so that every rank can make exactly the records it owns, with amplicons of a few assays
+    planted (an exact copy and mutated ones; some straddle the 500 kbp cuts)."""
+    rng = np.random.default_rng([5, r])
+    out[:] = random_codes(len(out), rng)
+    for k in range(4):
+        F, R, _ = assays[int(rng.integers(0, len(assays)))]
+        for v in range(3):
+            nm = 0 if v == 0 else int(rng.integers(1, 4))
+            text = mutate(F, nm, rng) + rand_oligo(int(rng.integers(80, 400)), rng) + mutate(revcomp(R), nm, rng)
+            if rng.integers(0, 2):
+                text = revcomp(text)
+            pos = int(rng.integers(0, len(out) - len(text) - 1))
+            if v == 2:   # on a cut of the record (reference fragment rule), so overlaps and truncations occur
+                pos = max(0, min(len(out) - len(text) - 1, int(rng.integers(1, 10)) * 500_000 + int(rng.integers(-len(text), 600))))
+            plant(out, pos, text)
