@@ -372,6 +372,10 @@ int tnt_debug_words(const char *oligo, int32_t word_size, int32_t complement, ui
  * alignment of `oligo` needs to reach a melting temperature of min_tm at the given conditions
  * (shorter alignments are rejected without evaluating them).  Negative on error. */
 int tnt_debug_min_columns(float T, float na, const char *oligo, float strand_concentration, float min_tm);
+/* The replay of amplicon()'s staged bind / cull sequence (see TNT_ENGINE_KEEP_CULLED_SITES) in its
+ * array form against its literal std::list form on `cases` random match lists: returns the number of
+ * cases whose hit lists differ (0 expected), the hits compared in *hits. */
+long tnt_debug_replay_selftest(uint32_t seed, int32_t cases, long *hits);
 
 #ifdef __cplusplus
 }

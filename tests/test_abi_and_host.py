@@ -132,3 +132,15 @@ def test_min_columns_bound_against_the_oracle(engine_lib, oracle):
                     assert (not a.valid) or a.tm < min_tm, (ol, n, x, a.tm, b)
                     checked += 1
     assert checked > 1000
+
+
+def test_replay_array_form_equals_list_form(engine_lib):
+    """The replay of the reference's staged PCR search (assemble.cpp) exists twice: literally with
+    std::list, and on arrays with the cheap route wherever the list's comparator is a strict weak
+    ordering.  Random match lists with overlapping bound sites through both: identical hit lists."""
+    engine_lib.tnt_debug_replay_selftest.argtypes = [C.c_uint32, C.c_int32, C.POINTER(C.c_long)]
+    engine_lib.tnt_debug_replay_selftest.restype = C.c_long
+    hits = C.c_long()
+    for seed in (1, 2, 3):
+        assert engine_lib.tnt_debug_replay_selftest(seed, 20000, C.byref(hits)) == 0
+        assert hits.value > 100000

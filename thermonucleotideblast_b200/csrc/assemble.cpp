@@ -7,6 +7,7 @@
 #include <cstring>
 #include <list>
 #include <map>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -419,10 +420,230 @@ bool less_bound_match(const El &a, const El &b) // sort_by_bound_match, bind_oli
 	return a.tm > b.tm;
 }
 
+// std::list::sort of libstdc++ (bits/list.tcc: bottom-up merge, 64 bins, merges in place with
+// "take from the second run only if strictly less") on an array.  sort_by_oligo_loc is no strict
+// weak ordering once bound and unbound elements mix, so the outcome depends on this exact merge
+// sequence; the reference was built with this very library.
+typedef bool (*ElLess)(const El &, const El &);
+
+void merge_runs(std::vector<El> &a, std::vector<El> &b, ElLess less) // a.merge(b): result in a, b emptied
+{
+	std::vector<El> r;
+	r.reserve(a.size() + b.size());
+	size_t i = 0, j = 0;
+	while (i < a.size() && j < b.size()) {
+		if (less(b[j], a[i])) r.push_back(b[j++]);
+		else r.push_back(a[i++]);
+	}
+	for (; i < a.size(); ++i) r.push_back(a[i]);
+	for (; j < b.size(); ++j) r.push_back(b[j]);
+	a.swap(r);
+	b.clear();
+}
+
+void list_sort(std::vector<El> &l, ElLess less)
+{
+	if (l.size() < 2) return;
+	std::vector<El> carry, bins[64];
+	int fill = 0;
+	for (const El &e : l) {
+		carry.assign(1, e);
+		int counter;
+		for (counter = 0; counter != fill && !bins[counter].empty(); ++counter) {
+			merge_runs(bins[counter], carry, less);
+			carry.swap(bins[counter]);
+		}
+		carry.swap(bins[counter]);
+		if (counter == fill) ++fill;
+	}
+	for (int counter = 1; counter != fill; ++counter) merge_runs(bins[counter], bins[counter - 1], less);
+	l.swap(bins[fill - 1]);
+}
+
+bool is_bound(const El &e) { return (e.loc5 + e.loc3) != 0; }
+
+// The list the culls sort, as an array.  `tail` = first element of the run appended by the last bind
+// step (sorted by loc_5 / loc_3); everything in front of it is still in the order of the last sort.
+struct MatchList {
+	std::vector<El> v;
+	size_t tail = 0;
+	bool canonical = false;   // the head run is sorted under a comparator that was a strict weak ordering
+
+	// Is sort_by_oligo_loc a strict weak ordering on the present elements?  It compares bound pairs by
+	// (loc_5, loc_3) and everything else by seed position: it is one iff the bound elements are ordered
+	// strictly alike by both keys.
+	bool ordering_is_consistent() const
+	{
+		std::vector<const El *> b;
+		for (const El &e : v) if (is_bound(e)) b.push_back(&e);
+		for (size_t i = 0; i < b.size(); ++i)
+			for (size_t j = i + 1; j < b.size(); ++j) {
+				const bool loc_ij = less_oligo_loc(*b[i], *b[j]), loc_ji = less_oligo_loc(*b[j], *b[i]);
+				const bool t_ij = b[i]->t < b[j]->t, t_ji = b[j]->t < b[i]->t;
+				if (loc_ij != t_ij || loc_ji != t_ji) return false;
+			}
+		return true;
+	}
+
+	void sort()
+	{
+		if (ordering_is_consistent()) {
+			// a stable sort has one possible outcome: take the cheap route to it
+			if (canonical && tail <= v.size()) std::inplace_merge(v.begin(), v.begin() + (ptrdiff_t)tail, v.end(), less_oligo_loc);
+			else std::stable_sort(v.begin(), v.end(), less_oligo_loc);
+			canonical = true;
+		}
+		else {
+			list_sort(v, less_oligo_loc);
+			canonical = false;
+		}
+		tail = v.size();
+	}
+};
+
 // cull_oligo_match (amplicon_search.cpp:679-765), unsigned wrap of the seed distance included.  The
 // strand counts are taken from the element *after* each kept one, as the reference does (:748-753;
 // its read of end() counts as neither strand).
-void cull(std::list<El> &l, unsigned max_amplicon_len, bool has_probe, bool single_primer_pcr, unsigned *n_minus, unsigned *n_plus)
+void cull(MatchList &ml, unsigned max_amplicon_len, bool has_probe, bool single_primer_pcr, unsigned *n_minus, unsigned *n_plus)
+{
+	const unsigned threshold = max_amplicon_len + 50;
+	ml.sort();
+	std::vector<El> &l = ml.v;
+	for (El &e : l) e.mask &= (uint8_t)~M_VALID;
+	const size_t n = l.size();
+	for (size_t f = 0; f < n; ++f) {
+		if (l[f].mask & (M_PLUS | M_P)) continue;
+		for (size_t r = f + 1; r < n; ++r) {
+			if ((unsigned)(l[r].t - l[f].t) > threshold) break;
+			if (l[r].mask & (M_MINUS | M_P)) continue;
+			if (!single_primer_pcr && ((l[f].mask & (M_R | M_F)) == (l[r].mask & (M_R | M_F)))) continue;
+			if (has_probe) {
+				for (size_t p = f + 1; p < r; ++p)
+					if (l[p].mask & M_P) { l[p].mask |= M_VALID; l[f].mask |= M_VALID; l[r].mask |= M_VALID; }
+			}
+			else { l[f].mask |= M_VALID; l[r].mask |= M_VALID; }
+		}
+	}
+	unsigned cm = 0, cp = 0;
+	size_t m = 0;
+	for (size_t i = 0; i < n; ++i) {
+		if (!(l[i].mask & M_VALID)) continue;
+		const uint8_t next = i + 1 < n ? l[i + 1].mask : (uint8_t)0;
+		cm += (next & M_MINUS) ? 1u : 0u;
+		cp += (next & M_PLUS) ? 1u : 0u;
+		if (m != i) l[m] = l[i];
+		++m;
+	}
+	l.resize(m);
+	ml.tail = m;
+	if (n_minus) *n_minus = cm;
+	if (n_plus) *n_plus = cp;
+}
+
+// bind_oligo_to_{minus,plus}_strand, mask variant (bind_oligo.cpp:456-827, :1159-1530): the elements
+// of one (oligo, strand) leave the list; those whose window passes every filter come back as bound
+// sites, one per (loc_5, loc_3), behind everything else.
+void bind_masked(MatchList &ml, uint8_t want, const std::vector<BoundSite> &sites)
+{
+	std::vector<El> &l = ml.v;
+	std::vector<El> cur;
+	size_t m = 0, head = 0; // head: survivors of the sorted run in front of `tail`
+	const bool pending_run = ml.tail < l.size(); // a run appended by an earlier bind step is not sorted in yet
+	for (size_t i = 0; i < l.size(); ++i) {
+		if ((l[i].mask & want) != want) { if (m != i) l[m] = l[i]; ++m; if (i < ml.tail) ++head; continue; }
+		El e = l[i];
+		if (e.site < 0) continue;
+		const BoundSite &b = sites[(size_t)e.site];
+		e.loc5 = b.loc5; e.loc3 = b.loc3;
+		e.tm = b.tm;
+		e.num_mm = b.num_mm;
+		e.align_len = b.align_len;
+		cur.push_back(e);
+	}
+	// two bind steps in a row (the probe strands) leave two runs behind the sorted head: the next sort
+	// then starts from scratch
+	if (pending_run) ml.canonical = false;
+	l.resize(m);
+	ml.tail = ml.canonical ? head : m;
+	if (cur.empty()) return;
+	std::reverse(cur.begin(), cur.end());            // curr_oligo was filled with push_front
+	std::stable_sort(cur.begin(), cur.end(), less_bound_match); // a strict weak ordering: any stable sort
+	for (size_t k = 0; k < cur.size(); ++k)
+		if (k == 0 || l.back().loc5 != cur[k].loc5 || l.back().loc3 != cur[k].loc3) l.push_back(cur[k]);
+}
+
+} // namespace
+
+void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
+	bool has_probe, int assay_index, int assay_id, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
+{
+	// match_oligo_to_*_strand (bind_oligo.cpp:84-122): per (oligo, strand) one seed per diagonal,
+	// ordered by q - t; the merge of all-unbound lists is an append
+	std::stable_sort(seeds.begin(), seeds.end(), [](const ReplaySeed &a, const ReplaySeed &b) {
+		if (a.cat != b.cat) return a.cat < b.cat;
+		return ((int)a.q - (int)a.t) < ((int)b.q - (int)b.t);
+	});
+	static const uint8_t kMask[6] = {M_F | M_MINUS, M_R | M_MINUS, M_F | M_PLUS, M_R | M_PLUS, M_P | M_MINUS, M_P | M_PLUS};
+	MatchList ml;
+	ml.v.reserve(seeds.size());
+	size_t k = 0;
+	auto append = [&](int cat) {
+		for (; k < seeds.size() && seeds[k].cat == cat; ++k) {
+			El e;
+			e.q = seeds[k].q; e.t = seeds[k].t;
+			e.mask = kMask[cat];
+			e.site = seeds[k].site;
+			ml.v.push_back(e);
+		}
+	};
+	append(0); append(1);
+	const size_t n_minus = ml.v.size();
+	if (n_minus == 0) return;                       // amplicon_search.cpp:103-105
+	append(2); append(3);
+	const size_t n_plus = ml.v.size();
+	if (n_plus == n_minus) return;                  // :113-115
+	if (has_probe) {
+		append(4); append(5);
+		if (ml.v.size() == n_plus) return;          // :123-125
+	}
+
+	unsigned cm = 0, cp = 0;
+	cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, &cm, &cp);
+	const bool first_plus = !(cm < cp);             // :131 vs :218
+	for (int stage = 0; stage < 4; ++stage) {
+		const bool plus = (stage < 2) ? first_plus : !first_plus;
+		const bool is_r = stage & 1;
+		bind_masked(ml, (uint8_t)((is_r ? M_R : M_F) | (plus ? M_PLUS : M_MINUS)), sites);
+		if (stage < 3) {
+			cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
+			// early exits at :153, :177, :240, :264, :288 -- none after the third bind of the minus-first path (:199)
+			if (ml.v.empty() && !(stage == 2 && !first_plus)) return;
+		}
+	}
+	if (has_probe) {
+		cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
+		if (ml.v.empty()) return;
+		bind_masked(ml, (uint8_t)(M_P | M_MINUS), sites);
+		bind_masked(ml, (uint8_t)(M_P | M_PLUS), sites);
+	}
+	ml.sort();                                      // :353
+	std::vector<const BoundSite *> all;
+	all.reserve(ml.v.size());
+	for (const El &e : ml.v) if (e.site >= 0) all.push_back(&sites[(size_t)e.site]);
+	join_pcr_sorted(all, assay_index, assay_id, has_probe, opt, sites.data(), hits, refs);
+}
+
+// ------------------------------------------------------------------------------------------
+// The same replay written with std::list, operation by operation as the reference has it
+// (list::sort, erase while iterating, push_front / sort / push_back in the bind step).  Slower;
+// kept as the yardstick the array version above is checked against (tnt_debug_replay_selftest).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// cull_oligo_match (amplicon_search.cpp:679-765), unsigned wrap of the seed distance included.  The
+// strand counts are taken from the element *after* each kept one, as the reference does (:748-753;
+// its read of end() counts as neither strand).
+void cull_list(std::list<El> &l, unsigned max_amplicon_len, bool has_probe, bool single_primer_pcr, unsigned *n_minus, unsigned *n_plus)
 {
 	const unsigned threshold = max_amplicon_len + 50;
 	l.sort(less_oligo_loc);
@@ -460,7 +681,7 @@ void cull(std::list<El> &l, unsigned max_amplicon_len, bool has_probe, bool sing
 // bind_oligo_to_{minus,plus}_strand, mask variant (bind_oligo.cpp:456-827, :1159-1530): the elements
 // of one (oligo, strand) leave the list; those whose window passes every filter come back as bound
 // sites, one per (loc_5, loc_3), behind everything else.
-void bind_masked(std::list<El> &l, uint8_t want, const std::vector<BoundSite> &sites)
+void bind_masked_list(std::list<El> &l, uint8_t want, const std::vector<BoundSite> &sites)
 {
 	std::list<El> cur;
 	for (auto it = l.begin(); it != l.end();) {
@@ -487,7 +708,7 @@ void bind_masked(std::list<El> &l, uint8_t want, const std::vector<BoundSite> &s
 
 } // namespace
 
-void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
+void replay_pcr_group_list(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
 	bool has_probe, int assay_index, int assay_id, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
 {
 	// match_oligo_to_*_strand (bind_oligo.cpp:84-122): per (oligo, strand) one seed per diagonal,
@@ -520,23 +741,23 @@ void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite
 	}
 
 	unsigned cm = 0, cp = 0;
-	cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, &cm, &cp);
+	cull_list(ml, opt.max_len, has_probe, opt.single_primer_pcr, &cm, &cp);
 	const bool first_plus = !(cm < cp);             // :131 vs :218
 	for (int stage = 0; stage < 4; ++stage) {
 		const bool plus = (stage < 2) ? first_plus : !first_plus;
 		const bool is_r = stage & 1;
-		bind_masked(ml, (uint8_t)((is_r ? M_R : M_F) | (plus ? M_PLUS : M_MINUS)), sites);
+		bind_masked_list(ml, (uint8_t)((is_r ? M_R : M_F) | (plus ? M_PLUS : M_MINUS)), sites);
 		if (stage < 3) {
-			cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
+			cull_list(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
 			// early exits at :153, :177, :240, :264, :288 -- none after the third bind of the minus-first path (:199)
 			if (ml.empty() && !(stage == 2 && !first_plus)) return;
 		}
 	}
 	if (has_probe) {
-		cull(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
+		cull_list(ml, opt.max_len, has_probe, opt.single_primer_pcr, nullptr, nullptr);
 		if (ml.empty()) return;
-		bind_masked(ml, (uint8_t)(M_P | M_MINUS), sites);
-		bind_masked(ml, (uint8_t)(M_P | M_PLUS), sites);
+		bind_masked_list(ml, (uint8_t)(M_P | M_MINUS), sites);
+		bind_masked_list(ml, (uint8_t)(M_P | M_PLUS), sites);
 	}
 	ml.sort(less_oligo_loc);                        // :353
 	std::vector<const BoundSite *> all;
@@ -599,6 +820,61 @@ std::string render_hit_sequence(int start, int stop, SeqMode mode, int seq_len, 
 		}
 	}
 	return s;
+}
+
+// Random match lists through both replays; returns the number of cases whose hit lists differ.
+long replay_selftest(uint32_t seed, int cases, long *hits_out)
+{
+	std::mt19937 rng(seed);
+	long ndiff = 0, nhits = 0;
+	for (int it = 0; it < cases; ++it) {
+		const bool has_probe = it & 1;
+		const int ncat = has_probe ? 6 : 4;
+		const int L = 20, span = 300 + (int)(rng() % 3000);
+		std::vector<ReplaySeed> seeds;
+		std::vector<BoundSite> sites;
+		const int nseed = 4 + (int)(rng() % 60);
+		for (int s = 0; s < nseed; ++s) {
+			ReplaySeed r;
+			r.cat = (int)(rng() % ncat);
+			r.q = rng() % 14;
+			// clusters, so that bound sites overlap and their two orders disagree
+			const int base = (rng() % 4) ? (int)(rng() % span) : 100 + (int)(rng() % 40);
+			r.t = (uint32_t)(base + 50);
+			r.site = -1;
+			if (rng() % 3) {
+				BoundSite b{};
+				b.role = r.cat >= 4 ? 2 : (r.cat & 1);
+				b.plus = r.cat >= 4 ? (r.cat & 1) : (r.cat >= 2);
+				b.os_index = (uint32_t)r.cat;
+				b.index = (uint32_t)sites.size();
+				const int shift = (int)(rng() % 5) - 2;
+				b.loc5 = (int)r.t - (int)r.q + shift - ((rng() % 7) == 0 ? (int)(rng() % 15) : 0);
+				b.loc3 = b.loc5 + L - 1 + (int)(rng() % 3);
+				b.tm = 40.0f + (float)(rng() % 200)/10.0f;
+				b.dH = -100.0f; b.dS = -0.3f;
+				b.anchor5 = 3; b.anchor3 = (int)(rng() % 10);
+				b.num_mm = (int)(rng() % 5);
+				b.query_loc = r.q; b.target_loc = r.t;
+				b.align_len = 60 + 3*(uint32_t)(rng() % 4);
+				r.site = (int)sites.size();
+				sites.push_back(b);
+			}
+			seeds.push_back(r);
+		}
+		AssembleOptions o{0, (uint32_t)(200 + rng() % 1800), (bool)(rng() & 1), (rng() % 3) ? -1 : 2};
+		std::vector<tnt_hit> h1, h2;
+		std::vector<HitSites> r1, r2;
+		replay_pcr_group_list(seeds, sites, o, has_probe, 0, 7, h1, r1);
+		replay_pcr_group(seeds, sites, o, has_probe, 0, 7, h2, r2);
+		bool same = r1.size() == r2.size();
+		for (size_t k = 0; same && k < r1.size(); ++k)
+			same = r1[k].forward == r2[k].forward && r1[k].reverse == r2[k].reverse && r1[k].probe == r2[k].probe;
+		nhits += (long)r1.size();
+		if (!same) ++ndiff;
+	}
+	if (hits_out) *hits_out = nhits;
+	return ndiff;
 }
 
 } // namespace tnt

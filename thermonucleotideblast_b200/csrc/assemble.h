@@ -64,6 +64,9 @@ struct ReplaySeed {
 void replay_pcr_group(std::vector<ReplaySeed> seeds, const std::vector<BoundSite> &sites, const AssembleOptions &opt,
 	bool has_probe, int assay_index, int assay_id, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
 
+// the replay above against its literal std::list form on random match lists (CPU self-test)
+long replay_selftest(uint32_t seed, int cases, long *hits_out);
+
 enum class SeqMode { PcrPlus, PcrMinus, ProbePlus, ProbeMinus, PadlockMinusStrand, PadlockPlusStrand };
 
 void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop, SeqMode &mode);

@@ -1687,54 +1687,50 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	}
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 
-	// (group, oligo strand, position, word) -> site
-	struct Key { uint32_t target, os, t, k; int idx; };
+	// bound sites of this pass -> `sites`, and per group a (oligo strand, position, word) -> site table
+	struct Key { uint32_t os, t, k; int idx; };
 	auto key_less = [](const Key &a, const Key &b) {
-		if (a.target != b.target) return a.target < b.target;
 		if (a.os != b.os) return a.os < b.os;
 		if (a.t != b.t) return a.t < b.t;
 		return a.k < b.k;
 	};
+	// groups of one assay, by fragment: a seed finds its group through its oligo strand's assay
+	std::vector<std::vector<std::pair<uint32_t, uint32_t>>> groups_of_assay(n_assays); // (target, group index), ascending
+	for (size_t g = 0; g < groups.size(); ++g) groups_of_assay[(size_t)groups[g].assay].push_back(std::make_pair(groups[g].target, (uint32_t)g));
+	auto group_index = [&](int assay, uint32_t target) -> long {
+		const auto &v = groups_of_assay[(size_t)assay];
+		const auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(target, 0u));
+		return (it != v.end() && it->first == target) ? (long)it->second : -1;
+	};
 	const size_t site_base = sites.size();
-	std::vector<Key> site_keys(heads.size());
+	std::vector<std::vector<Key>> group_sites(groups.size());
 	for (size_t i = 0; i < heads.size(); ++i) {
 		const BoundHead &b = heads[i];
-		if (b.flags & F_TRUNC)
-			throw std::runtime_error("more than 64 co-optimal DP cells or an alignment longer than the record (unsupported)");
-		if (b.flags & (F_OOB | F_STACK))
-			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked ring-buffer memory here, SURVEY 8a/B4); unsupported parameters");
+		if (b.flags & (F_OOB | F_STACK | F_TRUNC)) throw std::runtime_error("internal: a window without a defined answer reached the host");
 		sites.push_back(make_site(b, rec_before + (uint32_t)i, set.os[b.os]));
-		site_keys[i] = Key{b.target, b.os, b.t, b.k, (int)(site_base + i)};
+		const long g = group_index(set.os[b.os].assay, b.target);
+		if (g >= 0) group_sites[(size_t)g].push_back(Key{b.os, b.t, b.k, (int)(site_base + i)});
 	}
-	std::sort(site_keys.begin(), site_keys.end(), key_less);
+	for (std::vector<Key> &v : group_sites) std::sort(v.begin(), v.end(), key_less);
 
-	// seeds per group: ordered by (fragment, assay) through (target, os)
-	std::vector<Key> seed_keys(nseeds);
-	for (size_t i = 0; i < nseeds; ++i)
-		seed_keys[i] = Key{seeds[i].target_k & 0xffffffu, seeds[i].os, seeds[i].t, seeds[i].target_k >> 24, 0};
-	std::sort(seed_keys.begin(), seed_keys.end(), [&](const Key &a, const Key &b) {
-		if (a.target != b.target) return a.target < b.target;
-		const int aa = set.os[a.os].assay, ab = set.os[b.os].assay;
-		if (aa != ab) return aa < ab;
-		return key_less(a, b);
-	});
-	size_t at = 0;
+	// seeds per group (the spans are per oligo strand, hence per assay)
 	std::vector<std::vector<ReplaySeed>> group_seeds(groups.size());
-	for (size_t gidx = 0; gidx < groups.size(); ++gidx) {
-		const GroupKey &g = groups[gidx];
-		std::vector<ReplaySeed> &gs = group_seeds[gidx];
-		while (at < seed_keys.size() && (seed_keys[at].target < g.target ||
-			(seed_keys[at].target == g.target && set.os[seed_keys[at].os].assay < g.assay))) ++at;
-		for (; at < seed_keys.size() && seed_keys[at].target == g.target && set.os[seed_keys[at].os].assay == g.assay; ++at) {
-			const Key &k = seed_keys[at];
-			const OligoStrand &os = set.os[k.os];
+	for (const CandSpan &sp : spans) {
+		const OligoStrand &os = set.os[sp.os];
+		const int cat = os.role == TNT_OLIGO_P ? (os.plus ? 5 : 4) : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0);
+		for (uint64_t i = sp.out_off; i < sp.out_off + sp.count; ++i) {
+			const ReplaySeedRec &sd = seeds[i];
+			const long g = group_index(os.assay, sd.target_k & 0xffffffu);
+			if (g < 0) continue;
 			ReplaySeed r;
-			r.cat = (os.role == TNT_OLIGO_P ? 4 : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0)) + (os.role == TNT_OLIGO_P && os.plus ? 1 : 0);
-			r.q = k.k;
-			r.t = k.t;
-			const auto it = std::lower_bound(site_keys.begin(), site_keys.end(), k, key_less);
-			r.site = (it != site_keys.end() && !key_less(k, *it)) ? it->idx : -1;
-			gs.push_back(r);
+			r.cat = cat;
+			r.q = sd.target_k >> 24;
+			r.t = sd.t;
+			const std::vector<Key> &sk = group_sites[(size_t)g];
+			const Key k{sp.os, sd.t, sd.target_k >> 24, 0};
+			const auto it = std::lower_bound(sk.begin(), sk.end(), k, key_less);
+			r.site = (it != sk.end() && !key_less(k, *it)) ? it->idx : -1;
+			group_seeds[(size_t)g].push_back(r);
 		}
 	}
 	// the groups are independent: a few host threads when there are many, results in group order
@@ -2876,6 +2872,12 @@ int tnt_debug_min_columns(float T, float na, const char *oligo, float strand_con
 		os.r_log_ct = r_log_ct(strand_concentration);
 		return lean_min_columns(th, os, min_tm);
 	}
+	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
+}
+
+long tnt_debug_replay_selftest(uint32_t seed, int32_t cases, long *hits)
+{
+	try { return replay_selftest(seed, cases, hits); }
 	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
 }
 
