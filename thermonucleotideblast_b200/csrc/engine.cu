@@ -257,6 +257,10 @@ struct tnt_engine {
 	size_t fa_ev_used = 0;
 	tnt_ingest_stats fa_stats{};
 
+	// CUDA-event pairs around the alignment launches of a pass (read after the pass's own synchronisation)
+	std::vector<cudaEvent_t> tev;
+	size_t tev_used = 0;
+
 	// scratch of the search
 	DevBuf<Candidate> d_cand;
 	DevBuf<uint32_t> d_cand_count;
@@ -334,6 +338,7 @@ struct tnt_engine {
 		}
 		if (fa_scanned) cudaEventDestroy(fa_scanned);
 		for (cudaEvent_t ev : fa_ev) cudaEventDestroy(ev);
+		for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
 		if (h_fa_carry) cudaFreeHost(h_fa_carry);
 		for (cudaEvent_t ev : import_ev_pool) cudaEventDestroy(ev);
 		if (emit_done) cudaEventDestroy(emit_done);
@@ -1123,7 +1128,12 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 	// d_trace counts 16-bit units; the lean tier needs none (shared memory)
 	if (lq == 0 || full) e->d_trace.reserve((size_t)grid*a.trace_cells*ALIGN_THREADS*(lq == 0 ? 1 : 2) + 64, 0, e->stream);
 	a.trace = e->d_trace.p;
-	CUDA_OK(cudaEventRecord(e->ev[2], e->stream));
+	// timed with an event pair of its own; nobody waits for the launch here (collect_align_ms)
+	while (e->tev.size() < e->tev_used + 2) {
+		e->tev.emplace_back();
+		CUDA_OK(cudaEventCreate(&e->tev.back()));
+	}
+	CUDA_OK(cudaEventRecord(e->tev[e->tev_used], e->stream));
 	switch (lq) {
 	case 0: k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a); break;
 #define TNT_CLASS_CASE(L) case L: launch_fast<L>(a, grid, full, e->stream); break;
@@ -1132,13 +1142,24 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 	default: throw std::runtime_error("internal: unknown oligo length class");
 	}
 	CUDA_OK(cudaGetLastError());
-	CUDA_OK(cudaEventRecord(e->ev[3], e->stream));
+	CUDA_OK(cudaEventRecord(e->tev[e->tev_used + 1], e->stream));
+	e->tev_used += 2;
 	e->stats.kernel_launches++;
-	CUDA_OK(cudaStreamSynchronize(e->stream));
-	float ms = 0;
-	CUDA_OK(cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]));
 	(void)set;
-	return ms;
+	return 0.0f;
+}
+
+// Device time of the alignment launches since the last call; the stream must have been synchronised.
+float collect_align_ms(tnt_engine *e)
+{
+	float total = 0;
+	for (size_t i = 0; i + 1 < e->tev_used; i += 2) {
+		float ms = 0;
+		CUDA_OK(cudaEventElapsedTime(&ms, e->tev[i], e->tev[i + 1]));
+		total += ms;
+	}
+	e->tev_used = 0;
+	return total;
 }
 
 // Align every candidate currently in the buckets of `set`; append the survivors to `out`.
@@ -1260,6 +1281,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 		CUDA_OK(cudaMemcpy2DAsync(retry_fill.data(), sizeof(uint32_t), e->d_retry_ctl.p + 2*nos, COUNT_STRIDE*sizeof(uint32_t),
 			sizeof(uint32_t), nos, cudaMemcpyDeviceToHost, e->stream));
 		CUDA_OK(cudaStreamSynchronize(e->stream));
+		ms += collect_align_ms(e);
 		if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1]*5/4; continue; }
 		{
 			bool overflow = false;
@@ -1324,6 +1346,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 				if (!retry_units[c].empty()) ms += run_align_kernel(e, set, g, retry_units[c], kFastClasses[c], set.max_len, true);
 			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, 2*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
+			ms += collect_align_ms(e);
 			if (cnt[1] > slow_cap) { slow_cap = (size_t)cnt[1]*5/4; continue; }
 		}
 		t_phase.reset(new HostTimer("    generic tier"));
@@ -1338,6 +1361,7 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 			ms += run_align_kernel(e, set, g, units, 0, set.max_len);
 			CUDA_OK(cudaMemcpyAsync(cnt, e->d_out_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
 			CUDA_OK(cudaStreamSynchronize(e->stream));
+			ms += collect_align_ms(e);
 		}
 		t_phase.reset();
 		e->stats.align_ms += ms;
@@ -1633,6 +1657,7 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	e->d_regions.upload(regions, e->stream);
 
 	const uint32_t rec_before = e->n_bound;
+	std::unique_ptr<HostTimer> t_part(new HostTimer("  replay: scan + align"));
 	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
 	const double expect = (double)worst*(double)set.max_words/(double)set.nkeys;
 	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
@@ -1662,6 +1687,7 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	}
 
 	// seeds -> host
+	t_part.reset(new HostTimer("  replay: seeds and sites to the host"));
 	std::vector<CandSpan> spans;
 	uint64_t nseeds = 0;
 	for (size_t s = 0; s < nos; ++s)
@@ -1688,6 +1714,7 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 
 	// bound sites of this pass -> `sites`, and per group a (oligo strand, position, word) -> site table
+	t_part.reset(new HostTimer("  replay: grouping"));
 	struct Key { uint32_t os, t, k; int idx; };
 	auto key_less = [](const Key &a, const Key &b) {
 		if (a.os != b.os) return a.os < b.os;
@@ -1713,27 +1740,49 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	}
 	for (std::vector<Key> &v : group_sites) std::sort(v.begin(), v.end(), key_less);
 
-	// seeds per group (the spans are per oligo strand, hence per assay)
+	// seeds per group (the spans are per oligo strand, hence per assay: spans of different assays fill
+	// different groups, so the spans are dealt out to a few host threads by assay)
 	std::vector<std::vector<ReplaySeed>> group_seeds(groups.size());
-	for (const CandSpan &sp : spans) {
-		const OligoStrand &os = set.os[sp.os];
-		const int cat = os.role == TNT_OLIGO_P ? (os.plus ? 5 : 4) : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0);
-		for (uint64_t i = sp.out_off; i < sp.out_off + sp.count; ++i) {
-			const ReplaySeedRec &sd = seeds[i];
-			const long g = group_index(os.assay, sd.target_k & 0xffffffu);
-			if (g < 0) continue;
-			ReplaySeed r;
-			r.cat = cat;
-			r.q = sd.target_k >> 24;
-			r.t = sd.t;
-			const std::vector<Key> &sk = group_sites[(size_t)g];
-			const Key k{sp.os, sd.t, sd.target_k >> 24, 0};
-			const auto it = std::lower_bound(sk.begin(), sk.end(), k, key_less);
-			r.site = (it != sk.end() && !key_less(k, *it)) ? it->idx : -1;
-			group_seeds[(size_t)g].push_back(r);
+	{
+		const unsigned nt = nseeds < 200000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		auto fill = [&](unsigned t) {
+			for (const CandSpan &sp : spans) {
+				const OligoStrand &os = set.os[sp.os];
+				if ((unsigned)os.assay % nt != t) continue;
+				const int cat = os.role == TNT_OLIGO_P ? (os.plus ? 5 : 4) : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0);
+				long last_g = -1;
+				uint32_t last_target = 0xffffffffu;
+				for (uint64_t i = sp.out_off; i < sp.out_off + sp.count; ++i) {
+					const ReplaySeedRec &sd = seeds[i];
+					const uint32_t target = sd.target_k & 0xffffffu;
+					if (target != last_target) { last_g = group_index(os.assay, target); last_target = target; }
+					if (last_g < 0) continue;
+					ReplaySeed r;
+					r.cat = cat;
+					r.q = sd.target_k >> 24;
+					r.t = sd.t;
+					const std::vector<Key> &sk = group_sites[(size_t)last_g];
+					r.site = -1;
+					if (!sk.empty()) {
+						const Key k{sp.os, sd.t, sd.target_k >> 24, 0};
+						const auto it = std::lower_bound(sk.begin(), sk.end(), k, key_less);
+						if (it != sk.end() && !key_less(k, *it)) r.site = it->idx;
+					}
+					std::vector<ReplaySeed> &dst = group_seeds[(size_t)last_g];
+					if (dst.capacity() == 0) dst.reserve(2048);
+					dst.push_back(r);
+				}
+			}
+		};
+		if (nt == 1) fill(0);
+		else {
+			std::vector<std::thread> pool;
+			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(fill, t);
+			for (std::thread &t : pool) t.join();
 		}
 	}
 	// the groups are independent: a few host threads when there are many, results in group order
+	t_part.reset(new HostTimer("  replay: list operations"));
 	const unsigned nthreads = groups.size() < 16 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
 	std::vector<std::vector<tnt_hit>> part_hits(nthreads);
 	std::vector<std::vector<HitSites>> part_refs(nthreads);
