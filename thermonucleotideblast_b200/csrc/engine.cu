@@ -80,7 +80,19 @@ struct DevBuf {
 		if (n <= cap) return;
 		size_t ncap = std::max(n, cap + cap/2);
 		T *np = nullptr;
-		CUDA_OK(cudaMalloc(&np, ncap*sizeof(T)));
+		if (cudaMalloc(&np, ncap*sizeof(T)) != cudaSuccess) {
+			cudaGetLastError();
+			ncap = n; // no headroom left: exactly what is needed
+			const cudaError_t err = cudaMalloc(&np, ncap*sizeof(T));
+			if (err != cudaSuccess) {
+				size_t free_b = 0, total_b = 0;
+				cudaMemGetInfo(&free_b, &total_b);
+				char msg[256];
+				snprintf(msg, sizeof(msg), "out of device memory: %.1f MB requested (%zu elements of %zu bytes), %.1f MB free of %.1f MB",
+					(double)ncap*sizeof(T)/1e6, ncap, sizeof(T), (double)free_b/1e6, (double)total_b/1e6);
+				throw CudaError(msg);
+			}
+		}
 		if (keep && p) CUDA_OK(cudaMemcpyAsync(np, p, keep*sizeof(T), cudaMemcpyDeviceToDevice, st));
 		if (p) { CUDA_OK(cudaStreamSynchronize(st)); CUDA_OK(cudaFree(p)); }
 		p = np;
@@ -1492,24 +1504,30 @@ void scan_and_align(tnt_engine *e, OsSet &set, uint32_t os_base)
 	if (!gates.empty() && e->next_emit == e->batches.size()) { e->upload_settled = true; e->import_chunks.clear(); } // everything waited for
 }
 
-// Stage-2: scan regions with the given set
-// (regions in e->d_regions; `worst` = most region positions of any one assay)
-void region_scan_and_align(tnt_engine *e, OsSet &set, uint32_t nregions, uint64_t worst, uint32_t os_base)
+// Stage-2: scan regions [r0, r1) of e->d_regions with the given set and align what they hold
+// (`worst` = most region positions of any one assay, an estimate for the bucket size).  Regions
+// of one promiscuous oligo can hold far more seeds than any estimate; when the buckets of a
+// pass would not fit the budget the region list is halved.
+constexpr size_t REGION_CAND_BUDGET = (size_t)24 << 30;   // HBM is plentiful (180 GB); a 100 Gbp shard packs into 37.5 GB
+
+void region_scan_and_align(tnt_engine *e, OsSet &set, uint32_t r0, uint32_t r1, uint64_t worst, uint32_t os_base)
 {
-	if (set.os.empty() || nregions == 0) return;
+	if (set.os.empty() || r1 <= r0) return;
 	const size_t nos = set.os.size();
+	const uint32_t nregions = r1 - r0;
 	e->d_cand_count.reserve(nos*COUNT_STRIDE, 0, e->stream);
 	// Size the buckets for the busiest assay: expected seeds = positions x words / 4^W; start with
 	// generous slack and use the exact counts after an overflow (repeat-rich fragments can exceed
 	// any estimate).
 	const double expect = (double)worst*(double)set.max_words/(double)set.nkeys;
-	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)(1u << 28));
+	uint32_t cap = (uint32_t)std::min<double>(4.0*expect + 4096.0, (double)REGION_CAND_BUDGET/(double)(nos*sizeof(Candidate)));
+	cap = std::max<uint32_t>(cap, 4096u);
 	for (;;) {
 		e->d_cand.reserve(nos*(size_t)cap, 0, e->stream);
 		CUDA_OK(cudaMemsetAsync(e->d_cand_count.p, 0, nos*COUNT_STRIDE*sizeof(uint32_t), e->stream));
 		RegionScanArgs ra{};
 		ra.s = scan_args(e, set, cap);
-		ra.regions = e->d_regions.p;
+		ra.regions = e->d_regions.p + r0;
 		ra.nregions = nregions;
 		// Regions are dealt out by a static stride, so the grid is made several times larger than the
 		// resident set and the block scheduler evens out the tail (scan + region scan per step: 8.4 ms
@@ -1529,7 +1547,15 @@ void region_scan_and_align(tnt_engine *e, OsSet &set, uint32_t nregions, uint64_
 		if (ok) return;
 		uint32_t need = 0;
 		for (uint32_t c : counts) need = std::max(need, c);
-		cap = need + need/16 + 64; // exact sizes are known after the overflow
+		need += need/16 + 64; // exact sizes are known after the overflow
+		if (HostTimer::enabled()) fprintf(stderr, "[tnt]   region buckets overflowed: %u regions, capacity %u, needed %u\n", nregions, cap, need);
+		if ((size_t)need*nos*sizeof(Candidate) > REGION_CAND_BUDGET && nregions > 1) {
+			const uint32_t mid = r0 + nregions/2;
+			region_scan_and_align(e, set, r0, mid, worst/2, os_base);
+			region_scan_and_align(e, set, mid, r1, worst/2, os_base);
+			return;
+		}
+		cap = need;
 	}
 }
 
@@ -1631,7 +1657,6 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	std::vector<BoundSite> &sites, std::vector<tnt_hit> &out_hits, std::vector<HitSites> &out_refs)
 {
 	if (groups.empty()) return;
-	HostTimer t_all("replay of culled groups");
 	OsSet &stage1 = *e->set1, &stage2 = *e->set2;
 	if (!e->set_all) {
 		e->set_all.reset(new OsSet);
@@ -1654,6 +1679,13 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	}
 	uint64_t worst = 0;
 	for (uint64_t v : per_assay) worst = std::max(worst, v);
+	// many groups of one assay: the seeds of a pass have to fit the candidate budget
+	if (groups.size() > 1 && (double)worst*(double)set.max_words/(double)set.nkeys*4.0*(double)nos*sizeof(Candidate) > (double)REGION_CAND_BUDGET) {
+		const size_t mid = groups.size()/2;
+		replay_groups(e, o, ao, std::vector<GroupKey>(groups.begin(), groups.begin() + (ptrdiff_t)mid), sites, out_hits, out_refs);
+		replay_groups(e, o, ao, std::vector<GroupKey>(groups.begin() + (ptrdiff_t)mid, groups.end()), sites, out_hits, out_refs);
+		return;
+	}
 	e->d_regions.upload(regions, e->stream);
 
 	const uint32_t rec_before = e->n_bound;
@@ -1683,7 +1715,15 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 		if (ok) break;
 		uint32_t need = 0;
 		for (uint32_t c : counts) need = std::max(need, c);
-		cap = need + need/16 + 64;
+		need += need/16 + 64;
+		if ((size_t)need*nos*sizeof(Candidate) > REGION_CAND_BUDGET && groups.size() > 1) {
+			t_part.reset();
+			const size_t mid = groups.size()/2;
+			replay_groups(e, o, ao, std::vector<GroupKey>(groups.begin(), groups.begin() + (ptrdiff_t)mid), sites, out_hits, out_refs);
+			replay_groups(e, o, ao, std::vector<GroupKey>(groups.begin() + (ptrdiff_t)mid, groups.end()), sites, out_hits, out_refs);
+			return;
+		}
+		cap = need;
 	}
 
 	// seeds -> host
@@ -1949,7 +1989,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		CUDA_OK(cudaStreamSynchronize(e->stream));
 		uint64_t worst = 0;
 		for (unsigned long long v : per_assay) worst = std::max<uint64_t>(worst, v);
-		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, n1, worst, nos1); }
+		{ HostTimer t("region_scan_and_align"); region_scan_and_align(e, stage2, 0, n1, worst, nos1); }
 	}
 	const uint32_t n2 = e->n_bound;
 
@@ -2125,6 +2165,7 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		if (!groups.empty()) {
 			std::vector<tnt_hit> rhits;
 			std::vector<HitSites> rrefs;
+			HostTimer t_all("replay of culled groups");
 			replay_groups(e, o, ao, groups, sites, rhits, rrefs);
 			// merge: replayed groups take their hits from the replay, in (fragment, assay) order
 			std::vector<tnt_hit> merged;
