@@ -312,11 +312,34 @@ int tnt_engine_align(tnt_engine *e, uint32_t target_id, const char *oligo, int32
  * approximate_tm_heterodimer with `target` as the second strand, 5'->3' (:2397-2455), as called
  * for primer_dimer_tm (query = forward primer, target = reverse primer).  The strand
  * concentration follows NucCruc::strand(c_a, c_b) (nuc_cruc.h:893-910).  Runs the generic
- * NucCruc kernel on the device with the second oligo as an explicit target (<= 64 bases).  The
- * hairpin temperatures (approximate_tm_hairpin) are not built yet. */
+ * NucCruc kernel on the device with the second oligo as an explicit target (<= 64 bases). */
 int tnt_engine_oligo_dimer(tnt_engine *e, const char *query, const char *target, float conc_a, float conc_b,
 	tnt_align_result *out);
 
+
+/* approximate_tm_hairpin of one oligo (nuc_cruc.cpp:2542-2618: align_hairpin :771-971, the same
+ * recurrence for the oligo against itself over the triangle the steric limit leaves;
+ * enumerate_hairpin_alignments :1172-1407; evaluate_hairpin_alignment :2301-2394 with the loop
+ * entropy, the special tri- / tetra-loop bonuses and the terminal mismatch; Tm = dH/dS). */
+int tnt_engine_oligo_hairpin(tnt_engine *e, const char *query, tnt_align_result *out);
+
+/* Every secondary-structure temperature the driver attaches to the hits of an assay
+ * (tntblast_local.cpp:657-686), for all registered assays with one kernel launch.  They depend on
+ * the oligos and the strand concentrations only; -1 where the assay has no such oligo
+ * (hybrid_sig::init, hybrid_sig.h:71-79).  Index 0 / 1 / 2 = forward primer / reverse primer / probe:
+ *   hairpin_tm[k]      -> forward_hairpin_tm, reverse_hairpin_tm, probe_hairpin_tm
+ *   homodimer_tm[k]    -> forward_dimer_tm, reverse_dimer_tm, probe_dimer_tm      (strand(c, c))
+ *   heterodimer_tm[0]  -> primer_dimer_tm of a hit made by F and R                  (strand(c_f, c_r))
+ *   heterodimer_tm[1], [2] -> primer_dimer_tm of a single-primer hit (F with F, R with R: the driver
+ *                         runs approximate_tm_heterodimer on the oligos in the hit's two primer slots)
+ * A hit whose forward slot holds the reverse primer (single-primer amplicon) takes the values of
+ * that oligo, exactly as the driver looks them up by the hit's oligo strings. */
+typedef struct {
+	float hairpin_tm[3];
+	float homodimer_tm[3];
+	float heterodimer_tm[3];
+} tnt_assay_structures;
+int tnt_engine_assay_structures(tnt_engine *e, const tnt_search_options *opt, tnt_assay_structures *out /* one per assay */);
 
 /* Seed-scan-only pass over every registered fragment with the registered assays (timing aid for
  * the HBM roofline): returns the number of unique candidates and the device time. */

@@ -534,3 +534,58 @@ extern "C" long ref_finalize(const ref_post_hit *hits, long n, int best_match, i
 	return k;
 	GUARD_END
 }
+
+// ---------------------------------------------------------------------------
+// Hairpins: the reference's approximate_tm_hairpin and its parameter tables
+// ---------------------------------------------------------------------------
+extern "C" int ref_hairpin(const char *query, float T, float na, ref_align_out *out)
+{
+	GUARD_BEGIN
+	NucCruc *melt = get_melt(T, na);
+	melt->dangle(false, false);
+	melt->set_duplex(query); // tntblast_local.cpp:659
+	const float tm = melt->approximate_tm_hairpin();
+	memset(out, 0, sizeof(*out));
+	out->tm = tm;
+	out->valid = melt->curr_align.valid ? 1 : 0;
+	out->dH = melt->curr_align.dH;
+	out->dS = melt->curr_align.dS;
+	out->dG = melt->curr_align.dH - T*melt->curr_align.dS;
+	out->dp_dg = melt->curr_align.dp_dg;
+	if (melt->curr_align.valid) {
+		out->q_first = melt->curr_align.first_match.first;
+		out->t_first = melt->curr_align.first_match.second;
+		out->q_last = melt->curr_align.last_match.first;
+		out->t_last = melt->curr_align.last_match.second;
+		out->num_gap = (int)melt->curr_align.query_align.size(); // columns of the stem (incl. an attached end column)
+	}
+	return 0;
+	GUARD_END
+}
+
+extern "C" int ref_hairpin_tables(float *hairpin_S, char (*loops)[8], float *special_H, float *special_S, int cap)
+{
+	GUARD_BEGIN
+	NucCruc *melt = get_melt(310.15f, 0.05f);
+	for (int i = 0; i <= REF_MAX_HAIRPIN; ++i) hairpin_S[i] = melt->param_hairpin_S[i];
+	int n = 0;
+	const char letters[] = "ACGT";
+	for (int len = 5; len <= 6; ++len) {
+		const int total = 1 << (2*len);
+		for (int code = 0; code < total; ++code) {
+			char text[8] = {0};
+			for (int k = 0; k < len; ++k) text[k] = letters[(code >> (2*(len - 1 - k))) & 3];
+			CircleBuffer<BASE::nucleic_acid, MAX_SEQUENCE_LENGTH> q;
+			for (int k = 0; k < len; ++k) q.push_back(BASE::char_to_nucleic_acid(text[k]));
+			const int idx = melt->find_loop_index(q, 0, (unsigned int)len);
+			if (idx < 0) continue;
+			if (n == cap) THROW("ref_hairpin_tables: more special loops than expected");
+			strcpy(loops[n], text);
+			special_H[n] = melt->param_hairpin_special_H[idx];
+			special_S[n] = melt->param_hairpin_special_S[idx];
+			++n;
+		}
+	}
+	return n;
+	GUARD_END
+}

@@ -103,6 +103,14 @@ long ref_fasta_read(long index, uint32_t start, uint32_t stop, int whole, uint8_
 void ref_fasta_close(void);
 void ref_seq_len_increment(uint32_t len, uint32_t max_len, uint32_t *delta, uint32_t *pieces);
 
+/* approximate_tm_hairpin of one oligo (nuc_cruc.cpp:2542-2618), as tntblast_local.cpp:657-686 calls it */
+int ref_hairpin(const char *query, float T, float na, ref_align_out *out);
+/* hairpin parameter tables of the reference (data): loop entropies by loop length, and the special
+ * tri- / tetra-loops -- 5 or 6 letters each (found by probing find_loop_index with every 5- and
+ * 6-mer), with their dH / dS bonuses.  Returns the number of special loops (<= cap). */
+#define REF_MAX_HAIRPIN 512
+int ref_hairpin_tables(float *hairpin_S /* [REF_MAX_HAIRPIN + 1] */, char (*loops)[8], float *special_H, float *special_S, int cap);
+
 /* Post-processing of a result list by the reference's own select_best_match / uniquify_results
  * (tntblast_util.cpp:1482-1755) and hybrid_sig::operator< sort (tntblast_local.cpp:918-930).  `hits`
  * is ONE list in the order the driver would hold it (all records of one assay id); the indices of

@@ -283,6 +283,9 @@ typedef struct {
 	aln_t best;
 	int oob; /* an unchecked out-of-range read of the reference would have happened */
 	int homo; /* HOMO_DIMER mode: the symmetry entropy joins the initiation term (nuc_cruc.cpp:1632) */
+	int tri;  /* > 0: align_hairpin (nuc_cruc.cpp:771-971): the same recurrence over the triangle
+	           * i + j <= tri + 1 (tri = max_stem_len) of the query against itself */
+	int hairpin; /* HAIRPIN mode of evaluate_alignment: no initiation term (the caller preloads dH / dS), Tm = dH/dS */
 } nc_t;
 
 /* align_dimer (nuc_cruc.cpp:492-696).  Rows follow the *reversed* query, columns the target. */
@@ -301,10 +304,12 @@ static int32_t align_dimer(nc_t *nc)
 	int32_t max_score = -1;
 
 #define POS(v) ((v) > 0 ? (v) : 0)
-	for (int i = 1; i <= Lq; ++i) {
+	const int rows = nc->tri > 0 ? nc->tri : (nc->tri < 0 ? 0 : Lq);
+	for (int i = 1; i <= rows; ++i) {
 		const int qb = nc->q[Lq - i];
 		const int pq = (i == 1) ? bGAP : nc->q[Lq - (i - 1)];
-		for (int j = 1; j <= Lt; ++j) {
+		const int cols = nc->tri > 0 ? nc->tri - (i - 1) : Lt;
+		for (int j = 1; j <= cols; ++j) {
 			const int tb = nc->t[j - 1];
 			const int pt = (j == 1) ? bGAP : nc->t[j - 2];
 			cell_t *X = &nc->dp[i*st + j];
@@ -505,6 +510,7 @@ static int evaluate_alignment(const nc_t *nc, aln_t *a)
 
 	int terminal = P_NONE, last_last = P_NONE, last = P_NONE, cur;
 	float dH = SL_INIT_H, dS = SL_INIT_S + (nc->homo ? SL_SYMMETRY_S : 0.0f);
+	if (nc->hairpin) { dH = a->dH; dS = a->dS; } /* :1627-1633: hairpins do not pay the initiation cost */
 	unsigned nqgap = 0, ntgap = 0, nmm = 0, num_base = 0;
 	int terminal_5 = 0;
 
@@ -633,7 +639,8 @@ static int evaluate_alignment(const nc_t *nc, aln_t *a)
 
 	dS += SL_SALT*(0.5f*num_base - 1)*nc->th->log_na;
 	a->dS = dS;
-	const float tm = dH/(NC_R*logf(nc->strand*1.0f) + dS) - NC_ZERO_C;
+	const float tm = nc->hairpin ? dH/dS - NC_ZERO_C /* :2286-2289: no strand concentration */
+		: dH/(NC_R*logf(nc->strand*1.0f) + dS) - NC_ZERO_C;
 	a->tm = tm > 0.0f ? tm : 0.0f;
 	return 1;
 }
@@ -904,6 +911,159 @@ int orc_dimer(const char *query, const char *target, float T, float na, float co
 	nc->homo = 0;
 	if (rc < 0) return -1;
 	fill_out(nc, dp_dg, out);
+	return nc->oob ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Hairpins (tntblast_local.cpp:657-686 attaches approximate_tm_hairpin of every oligo to a hit)
+ * ---------------------------------------------------------------------------------------- */
+/* find_loop_index (nuc_cruc.cpp:2620-2860): the loop with its closing pair, 5 or 6 letters, in the
+ * table of special tri- / tetra-loops; letters come from "ACGTE"[base] (anything else never matches) */
+static int find_loop_index(const nc_t *nc, int start, int len)
+{
+	char text[8] = {0};
+	for (int k = 0; k < len; ++k) {
+		const int b = (start + k >= 0 && start + k < nc->Lq) ? nc->q[start + k] : bGAP;
+		text[k] = b <= bT ? "ACGT"[b] : (b <= bE ? 'E' : '?');
+	}
+	for (int i = 0; i < SL_NUM_HAIRPIN_LOOP; ++i)
+		if (strcmp(SL_HAIRPIN_LOOP[i], text) == 0) return i;
+	return -1;
+}
+
+/* evaluate_hairpin_alignment (nuc_cruc.cpp:2301-2394) */
+static int evaluate_hairpin_alignment(nc_t *nc, aln_t *a)
+{
+	const int last_3 = a->fm_q, last_5 = a->fm_t;
+	const unsigned loop_len = (unsigned)(last_3 - last_5 - 1);
+	a->dH = 0.0f;
+	a->dS = 0.0f;
+	if (loop_len > 512) { nc->oob = 1; return 0; }
+	a->dS += SL_HAIRPIN_S[loop_len];
+	const int last_pair = BBP[q_at(nc, last_5)][q_at(nc, last_3)];
+	int idx;
+	switch (loop_len) {
+	case 3:
+		idx = find_loop_index(nc, last_5, 5);
+		if (idx >= 0) { a->dH += SL_HAIRPIN_SPECIAL_H[idx]; a->dS += SL_HAIRPIN_SPECIAL_S[idx]; }
+		if (last_pair == P_AT || last_pair == P_TA) a->dS += SL_BULGE_AT_CLOSING_S;
+		break;
+	case 4:
+		idx = find_loop_index(nc, last_5, 6);
+		if (idx >= 0) { a->dH += SL_HAIRPIN_SPECIAL_H[idx]; a->dS += SL_HAIRPIN_SPECIAL_S[idx]; }
+		/* falls through to the terminal mismatch */
+	default: {
+		const int cur = BBP[q_at(nc, last_5 + 1)][q_at(nc, last_3 - 1)];
+		/* param_hairpin_terminal_* are copies of the stacking tables (nuc_cruc_santa_lucia.cpp:594-595) */
+		a->dH += SL_PARAM_H[SIDX(last_pair, cur)];
+		a->dS += SL_PARAM_S[SIDX(last_pair, cur)];
+		break;
+	}
+	}
+	nc->hairpin = 1;
+	const int ok = evaluate_alignment(nc, a);
+	nc->hairpin = 0;
+	return ok;
+}
+
+static void hairpin_keep_if_better(nc_t *nc, const aln_t *a, float *best_dg)
+{
+	const float local_dg = a->dH - nc->th->T*a->dS;
+	if (!nc->best.valid || local_dg < *best_dg) {
+		nc->best = *a;
+		nc->best.valid = 1;
+		*best_dg = local_dg;
+	}
+}
+
+/* enumerate_hairpin_alignments (nuc_cruc.cpp:1172-1407) for one maximal cell */
+static int enumerate_hairpin(nc_t *nc, int max_cell)
+{
+	const int Lq = nc->Lq;
+	int first_time = 1, nstack = 0, zero_count = -1;
+	unsigned trace_count = 0;
+	float best_dg = nc->best.dH - nc->th->T*nc->best.dS;
+	branch_t *stack = (branch_t *)malloc(sizeof(branch_t)*(size_t)(6*Lq + 8));
+	aln_t *a = (aln_t *)malloc(sizeof(aln_t));
+	for (;;) {
+		if (!first_time && nstack == 0 && zero_count <= 0) break;
+		if (MAX_DP_PATH_ENUM != 0 && MAX_DP_PATH_ENUM < trace_count) break;
+		++trace_count;
+		first_time = 0;
+		aln_clear(a);
+		if (trace_back(nc, max_cell, stack, &nstack, &zero_count, a) < 0) { free(stack); free(a); return -1; }
+		while (ALN_N(a) > 0 && !WC[BBP[a->q[a->e - 1]][a->t[a->e - 1]]]) {
+			if (!IS_VIRTUAL(a->q[a->e - 1])) --a->lm_q;
+			if (!IS_VIRTUAL(a->t[a->e - 1])) ++a->lm_t;
+			--a->e;
+		}
+		while (ALN_N(a) > 0 && !WC[BBP[a->q[a->b]][a->t[a->b]]]) {
+			if (!IS_VIRTUAL(a->q[a->b])) ++a->fm_q;
+			if (!IS_VIRTUAL(a->t[a->b])) --a->fm_t;
+			++a->b;
+		}
+		if (zero_count == 0 && nstack > 0) {
+			while (nstack > 0 && !branch_next(&stack[nstack - 1])) --nstack;
+			zero_count = -1;
+		}
+		/* the stem as it is (:1265-1286) */
+		if (ALN_N(a) >= 3 && evaluate_hairpin_alignment(nc, a)) hairpin_keep_if_better(nc, a, &best_dg);
+		/* one more column at the open end: the next bases, or a dangling-end virtual base (:1307-1326) */
+		if (a->lm_t != 0 || a->lm_q != Lq - 1) {
+			int tb, qb;
+			if (a->lm_t == 0) tb = bE;
+			else { --a->lm_t; tb = q_at(nc, a->lm_t); }
+			if (a->lm_q == Lq - 1) qb = bE;
+			else { ++a->lm_q; qb = q_at(nc, a->lm_q); }
+			aln_push_back(a, qb, tb);
+		}
+		const int align_size = ALN_N(a);
+		if (align_size < 3) continue;
+		if (evaluate_hairpin_alignment(nc, a)) hairpin_keep_if_better(nc, a, &best_dg);
+		/* without the closing pair, unless it is G-C / C-G (:1360-1406) */
+		if (align_size <= 3) continue;
+		const int last_pair = BBP[q_at(nc, a->fm_t)][q_at(nc, a->fm_q)];
+		if (last_pair == bG*7 + bC || last_pair == bC*7 + bG) continue;
+		++a->fm_q;
+		--a->fm_t;
+		++a->b;
+		if (evaluate_hairpin_alignment(nc, a)) hairpin_keep_if_better(nc, a, &best_dg);
+	}
+	free(stack);
+	free(a);
+	return 0;
+}
+
+/* approximate_tm_hairpin without Dinkelbach (nuc_cruc.cpp:2590-2610) */
+int orc_hairpin(const char *query, float T, float na, ref_align_out *out)
+{
+	nc_t *nc = get_nc(T, na);
+	if (set_query(nc, query) < 0) return -1;
+	memcpy(nc->t, nc->q, (size_t)nc->Lq);
+	nc->Lt = nc->Lq;
+	nc->dangle5 = nc->dangle3 = 0;
+	nc->homo = 0;
+	const int max_stem_len = nc->Lq - 4; /* steric limit: 3 loop bases + 1 anchor (:781-790) */
+	nc->tri = max_stem_len > 0 ? max_stem_len : -1;
+	aln_clear(&nc->best);
+	nc->oob = 0;
+	const int32_t max_score = align_dimer(nc);
+	nc->tri = 0;
+	for (int k = 0; k < nc->n_max; ++k)
+		if (enumerate_hairpin(nc, nc->max_cells[k]) < 0) return -1;
+	memset(out, 0, sizeof(*out));
+	const aln_t *a = &nc->best;
+	out->tm = a->tm;
+	out->valid = a->valid;
+	out->dH = a->dH;
+	out->dS = a->dS;
+	out->dG = a->dH - T*a->dS;
+	out->dp_dg = -((float)max_score/10000.0f);
+	if (a->valid) {
+		out->q_first = a->fm_q; out->t_first = a->fm_t;
+		out->q_last = a->lm_q; out->t_last = a->lm_t;
+		out->num_gap = ALN_N(a);
+	}
 	return nc->oob ? 1 : 0;
 }
 

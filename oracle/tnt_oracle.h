@@ -32,6 +32,7 @@ int orc_get_hits(ref_hit *out, long cap);
  * executed by the last orc_search call -- the unit of the "alignments/s" metric */
 long orc_last_alignment_count(void);
 int orc_dimer(const char *query, const char *target, float T, float na, float conc_a, float conc_b, ref_align_out *out);
+int orc_hairpin(const char *query, float T, float na, ref_align_out *out);
 
 /* FASTA reader + fragment rule (tnt_oracle_fasta.c) */
 long orc_fasta_index(const char *text, uint64_t n, uint64_t *pos, long cap);

@@ -279,6 +279,16 @@ class _Lib:
         return [arr[i] for i in range(got)]
 
 
+    def hairpin(self, query: str, T=310.15, na=0.05) -> AlignOut:
+        """approximate_tm_hairpin of an oligo (tntblast_local.cpp:661); q/t_first = bases closing the loop,
+        num_gap = columns of the stem."""
+        f = getattr(self.lib, self.prefix + "hairpin")
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_float, C.c_float, C.POINTER(AlignOut)]
+        out = AlignOut()
+        self._check(f(query.encode(), T, na, C.byref(out)))
+        return out
+
     def finalize(self, hits: Sequence[PostHit], best_match: bool, uniquify: bool) -> List[int]:
         """One result list through the reference's select_best_match / uniquify_results / sort (only the
         compiled reference exports it): indices of the surviving records in output order."""

@@ -803,3 +803,75 @@ def test_oligo_dimers_on_the_device(eng, oracle):
     eng.oligo_dimer(P)
     assert [hit_key(eng, h, (F, R, P)) for h in eng.search(to_opts(o))] == before and before
     eng.clear_targets()
+
+
+def test_hairpins_on_the_device(eng, oracle):
+    """tnt_engine_oligo_hairpin (k_oligo_jobs: the triangular fill of align_hairpin, the three evaluations
+    per traceback of enumerate_hairpin_alignments, loop entropy / special loops / terminal mismatch)
+    against the oracle and the committed vectors of the compiled reference: floats bit for bit."""
+    import json
+    import os
+    rng = np.random.default_rng(616)
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hairpins.json")))
+    f32 = lambda x: float(np.float32(x)).hex()
+    nvalid = 0
+    for r in gold:
+        if (r["T"], r["na"]) != (310.15, 0.05):
+            continue
+        g = eng.oligo_hairpin(r["q"])
+        w = r["out"]
+        assert g.valid == w["valid"], r["q"]
+        assert (f32(g.tm), f32(g.dH), f32(g.dS)) == (w["tm"], w["dH"], w["dS"]), r["q"]
+        if g.valid:
+            assert [g.q_first, g.t_first] == w["loop"] and [g.q_last, g.t_last] == w["open_end"] and g.num_gap == w["columns"], r["q"]
+            nvalid += 1
+    for it in range(300):
+        L = int(rng.integers(5, 57))
+        q = gen.rand_oligo(L, rng)
+        if it % 2 and L >= 16:
+            stem = gen.rand_oligo(int(rng.integers(3, 10)), rng)
+            q = (gen.rand_oligo(int(rng.integers(0, 3)), rng) + stem + gen.rand_oligo(int(rng.integers(3, 9)), rng) +
+                 gen.mutate(gen.revcomp(stem), int(rng.integers(0, 2)), rng))[:56]
+        w = oracle.hairpin(q)
+        g = eng.oligo_hairpin(q)
+        assert g.valid == w.valid, q
+        assert abs(g.tm - w.tm) <= TM_TOL
+        assert (g.tm, g.dH, g.dS) == (w.tm, w.dH, w.dS), q
+        if w.valid:
+            assert (g.q_first, g.t_first, g.q_last, g.t_last, g.num_gap) == (w.q_first, w.t_first, w.q_last, w.t_last, w.num_gap), q
+            nvalid += 1
+    assert nvalid > 200
+
+
+def test_assay_structures_in_one_call(eng, oracle):
+    """tnt_engine_assay_structures: the seven temperatures tntblast_local.cpp:657-686 attaches to every hit
+    (plus the two single-primer heterodimers), for all assays with one launch, against the oracle."""
+    from thermonucleotideblast_b200 import Assay, search_options
+    rng = np.random.default_rng(717)
+    assays = []
+    for i in range(40):
+        F, R, P = gen.rand_oligo(int(rng.integers(16, 31)), rng), gen.rand_oligo(int(rng.integers(16, 31)), rng), gen.rand_oligo(int(rng.integers(18, 36)), rng)
+        if i % 5 == 0:
+            h = gen.rand_oligo(9, rng)
+            F = h + "GAAA" + gen.revcomp(h)       # a hairpin with a special tetra-loop, and a strong homodimer
+        if i % 7 == 0:
+            R = gen.revcomp(F)[:len(F) - 2]        # primer dimer
+        assays.append(Assay(i, F, R, P) if i % 3 else (Assay(i, F, R, None) if i % 2 else Assay(i, None, None, P)))
+    eng.set_assays(assays)
+    o = search_options(min_primer_tm=45.0, min_probe_tm=50.0, forward_primer_strand=1.8e-6)   # asymmetric PCR: c_f != c_r
+    got = eng.assay_structures(o, len(assays))
+    fps, rps, ps = o.forward_primer_strand, o.reverse_primer_strand, o.probe_strand
+    ne = 0
+    for a, g in zip(assays, got):
+        want_h = [oracle.hairpin(x).tm if x else -1.0 for x in (a.forward, a.reverse, a.probe)]
+        want_d = [oracle.dimer(x, None, conc_a=c, conc_b=c).tm if x else -1.0 for x, c in ((a.forward, fps), (a.reverse, rps), (a.probe, ps))]
+        if a.forward:
+            want_x = [oracle.dimer(a.forward, a.reverse, conc_a=fps, conc_b=rps).tm, oracle.dimer(a.forward, a.forward, conc_a=fps, conc_b=rps).tm,
+                      oracle.dimer(a.reverse, a.reverse, conc_a=fps, conc_b=rps).tm]
+        else:
+            want_x = [-1.0, -1.0, -1.0]
+        assert list(g.hairpin_tm) == [np.float32(x) for x in want_h], a
+        assert list(g.homodimer_tm) == [np.float32(x) for x in want_d], a
+        assert list(g.heterodimer_tm) == [np.float32(x) for x in want_x], a
+        ne += sum(1 for x in want_h + want_d + want_x if x > 0)
+    assert ne > 60

@@ -203,3 +203,34 @@ def test_cull_anomaly_cases(oracle):
                 "forward_align": h.forward_align.decode(), "reverse_align": h.reverse_align.decode()} for h in hits]
         assert got == c["reference_hits"]
         assert tuple(c["lost_amplicon"]) not in [(h.amp_first, h.amp_last) for h in hits]
+
+
+def test_hairpins(oracle):
+    """approximate_tm_hairpin (tntblast_local.cpp:661,667,682): the oracle against vectors made from the
+    compiled reference (tests/golden/make_hairpins.py), floats bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_hairpins", os.path.join(GOLD, "make_hairpins.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    recs = load("hairpins.json")
+    assert len(recs) > 200 and sum(r["out"]["valid"] for r in recs) > 100
+    for r in recs:
+        assert mk.rec(oracle.hairpin(r["q"], r["T"], r["na"])) == r["out"], r["q"]
+
+
+def test_hairpins_against_the_compiled_reference(oracle, ref):
+    rng = np.random.default_rng(31)
+    n = 0
+    for it in range(1500):
+        L = int(rng.integers(5, 57))
+        q = gen.rand_oligo(L, rng)
+        if it % 2 and L >= 16:
+            stem = gen.rand_oligo(int(rng.integers(3, 9)), rng)
+            q = (stem + gen.rand_oligo(int(rng.integers(3, 9)), rng) + gen.revcomp(stem) + gen.rand_oligo(3, rng))[:56]
+        T, na = [(310.15, 0.05), (285.0, 0.5), (340.0, 0.02)][it % 3]
+        a, b = ref.hairpin(q, T, na), oracle.hairpin(q, T, na)
+        assert (a.valid, a.tm, a.dH, a.dS, a.dp_dg) == (b.valid, b.tm, b.dH, b.dS, b.dp_dg), q
+        if a.valid:
+            assert (a.q_first, a.t_first, a.q_last, a.t_last, a.num_gap) == (b.q_first, b.t_first, b.q_last, b.t_last, b.num_gap), q
+            n += 1
+    assert n > 800

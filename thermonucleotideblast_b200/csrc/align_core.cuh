@@ -92,9 +92,13 @@ struct DpResult {
 // Stage 1: fill.  Rows follow the reversed oligo, columns the target 5'->3'
 // (align_dimer, nuc_cruc.cpp:508-693).  NT = threads per block (row/trace stride).
 // ------------------------------------------------------------------------------------------
+// `tri` > 0: align_hairpin (nuc_cruc.cpp:771-971) -- the same recurrence for the oligo against itself
+// over the triangle i + j <= tri + 1 only (tri = the longest stem the steric limit allows); cells
+// inside the triangle depend on cells inside it alone.  The caller clears the trace beforehand
+// (cells outside the triangle are never written).
 template <int NT>
 __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *tgt, int Lt,
-	int32_t *rowM, int32_t *rowIq, int32_t *rowIt, uint16_t *trace)
+	int32_t *rowM, int32_t *rowIq, int32_t *rowIt, uint16_t *trace, int tri = 0)
 {
 	const int32_t *__restrict__ dg = sh.dg;
 	const uint8_t *__restrict__ bbp = sh.bbp;
@@ -107,8 +111,10 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 	res.last_raise = -1;
 	res.nmax = 0;
 
-	int cell = 0;
-	for (int i = 1; i <= Lq; ++i) {
+	const int rows = tri > 0 ? tri : Lq;
+	for (int i = 1; i <= rows; ++i) {
+		int cell = (i - 1)*Lt;
+		const int cols = tri > 0 ? tri - (i - 1) : Lt;
 		const int qb = sh.q[Lq - i];
 		const int pq = (i == 1) ? (int)bGAP : (int)sh.q[Lq - i + 1];
 		const int gap_pq = bbp[bGAP*NB + pq]*NPAIR;   // previous pair (GAP, pq)
@@ -122,7 +128,7 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 		int pt_gap = bbp[bGAP*NB + bGAP];
 
 #pragma unroll 2
-		for (int j = 1; j <= Lt; ++j, ++cell) {
+		for (int j = 1; j <= cols; ++j, ++cell) {
 			const int tb = tgt[j - 1];
 			const int cur = bbp[tb*NB + qb];
 			const int tb_pq = bbp[tb*NB + pq];
@@ -313,7 +319,9 @@ __device__ __forceinline__ bool has_at_initiation(const DpShared &sh, const uint
 	return bp == P_AT || bp == P_TA;
 }
 
-__device__ bool nc_evaluate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct, AlnState &a)
+// `hairpin`: HAIRPIN mode of evaluate_alignment (nuc_cruc.cpp:1627-1633, :2286-2289) -- no initiation
+// term (the caller preloaded a.dH / a.dS with the loop terms), Tm = dH/dS without a strand concentration.
+__device__ bool nc_evaluate(const DpShared &sh, const Thermo *__restrict__ th, float r_log_ct, AlnState &a, bool hairpin = false)
 {
 	const uint8_t *q = a.q + a.b, *t = a.t + a.b;
 	const int n = a.e - a.b;
@@ -328,6 +336,7 @@ __device__ bool nc_evaluate(const DpShared &sh, const Thermo *__restrict__ th, f
 
 	int terminal = P_NONE, last_last = P_NONE, last = P_NONE;
 	float dH = th->init_H, dS = TNT_ADD(th->init_S, 0.0f);
+	if (hairpin) { dH = a.dH; dS = a.dS; }
 	unsigned nqgap = 0, ntgap = 0, nmm = 0, num_base = 0;
 	bool terminal_5 = false;
 
@@ -445,7 +454,7 @@ __device__ bool nc_evaluate(const DpShared &sh, const Thermo *__restrict__ th, f
 	// dS += SALT*(0.5f*num_base - 1)*log[Na+]
 	dS = TNT_ADD(dS, TNT_MUL(TNT_MUL(th->salt, TNT_SUB(TNT_MUL(0.5f, (float)num_base), 1.0f)), th->log_na));
 	a.dS = dS;
-	const float tm = TNT_SUB(__fdiv_rn(dH, TNT_ADD(r_log_ct, dS)), 273.15f);
+	const float tm = hairpin ? TNT_SUB(__fdiv_rn(dH, dS), 273.15f) : TNT_SUB(__fdiv_rn(dH, TNT_ADD(r_log_ct, dS)), 273.15f);
 	a.tm = fmaxf(0.0f, tm);
 	return true;
 #undef ADD_HS
@@ -576,6 +585,136 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 					for (int c = a.b; c < a.e; ++c) { best_aln.q[c] = a.q[c]; best_aln.t[c] = a.t[c]; }
 				}
 			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Hairpins (approximate_tm_hairpin, nuc_cruc.cpp:2542-2618): the oligo against itself
+// ------------------------------------------------------------------------------------------
+// find_loop_index (nuc_cruc.cpp:2620-2860): the loop with its closing pair in the table of special loops
+__device__ inline int nc_find_loop(const DpShared &sh, const Thermo *__restrict__ th, int start, int len)
+{
+	char text[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (int k = 0; k < len; ++k) {
+		const int b = (start + k >= 0 && start + k < sh.Lq) ? sh.q[start + k] : (int)bGAP;
+		text[k] = b <= bT ? "ACGT"[b] : (b <= bE ? 'E' : '?');
+	}
+	for (int i = 0; i < NUM_HAIRPIN_LOOP; ++i) {
+		bool same = true;
+		for (int k = 0; k < 7 && same; ++k) same = th->hairpin_loop[i][k] == text[k];
+		if (same) return i;
+	}
+	return -1;
+}
+
+// evaluate_hairpin_alignment (nuc_cruc.cpp:2301-2394)
+__device__ inline bool nc_evaluate_hairpin(const DpShared &sh, const Thermo *__restrict__ th, AlnState &a, unsigned &flags)
+{
+	const int last_3 = a.fm_q, last_5 = a.fm_t;
+	const int loop_len = last_3 - last_5 - 1;
+	if (loop_len < 0 || loop_len > MAX_LOOP || last_5 < 0 || last_3 >= sh.Lq) { flags |= F_OOB; return false; }
+	a.dH = 0.0f;
+	a.dS = TNT_ADD(0.0f, th->hairpin_S[loop_len]);
+	const int last_pair = sh.bbp[sh.q[last_5]*NB + sh.q[last_3]];
+	if (loop_len == 3) {
+		const int idx = nc_find_loop(sh, th, last_5, 5);
+		if (idx >= 0) { a.dH = TNT_ADD(a.dH, th->hairpin_special_H[idx]); a.dS = TNT_ADD(a.dS, th->hairpin_special_S[idx]); }
+		if (last_pair == P_AT || last_pair == P_TA) a.dS = TNT_ADD(a.dS, th->bulge_at_S);
+	}
+	else {
+		if (loop_len == 4) {
+			const int idx = nc_find_loop(sh, th, last_5, 6);
+			if (idx >= 0) { a.dH = TNT_ADD(a.dH, th->hairpin_special_H[idx]); a.dS = TNT_ADD(a.dS, th->hairpin_special_S[idx]); }
+		}
+		if (last_5 + 1 >= sh.Lq || last_3 - 1 < 0) { flags |= F_OOB; return false; }
+		const int cur = sh.bbp[sh.q[last_5 + 1]*NB + sh.q[last_3 - 1]];
+		// param_hairpin_terminal_* are copies of the stacking tables (nuc_cruc_santa_lucia.cpp:594-595)
+		a.dH = TNT_ADD(a.dH, __ldg(th->H + last_pair*NPAIR + cur));
+		a.dS = TNT_ADD(a.dS, __ldg(th->S + last_pair*NPAIR + cur));
+	}
+	return nc_evaluate(sh, th, 0.0f, a, true);
+}
+
+__device__ __forceinline__ void nc_hairpin_keep(const Thermo *__restrict__ th, const AlnState &a, AlnState &best_aln, Best &best, float &best_dg)
+{
+	const float local_dg = TNT_SUB(a.dH, TNT_MUL(th->T, a.dS));
+	if (!best.valid || local_dg < best_dg) {
+		best.valid = true;
+		best.dH = a.dH; best.dS = a.dS; best.tm = a.tm;
+		best_dg = local_dg;
+		best_aln.b = a.b; best_aln.e = a.e;
+		best_aln.fm_q = a.fm_q; best_aln.fm_t = a.fm_t;
+		best_aln.lm_q = a.lm_q; best_aln.lm_t = a.lm_t;
+	}
+}
+
+// enumerate_hairpin_alignments (nuc_cruc.cpp:1172-1407) over the maximal cells of a chunk
+template <class TV>
+__device__ void nc_enumerate_hairpin(const DpShared &sh, const Thermo *__restrict__ th, const uint8_t *tgt, int Lt, const TV &tv,
+	const uint16_t *cells, int ncells, AlnState &work, AlnState &best_aln, Best &best, unsigned &flags, bool fresh)
+{
+	const int Lq = sh.Lq;
+	if (fresh) {
+		best.valid = false;
+		best.dH = best.dS = best.tm = 0.0f;
+	}
+	Branch stack[MAX_BRANCH];
+	for (int ci = 0; ci < ncells; ++ci) {
+		const int cell = cells[ci];
+		bool first_time = true;
+		int nstack = 0, zero_count = -1;
+		unsigned trace_count = 0;
+		float best_dg = TNT_SUB(best.dH, TNT_MUL(th->T, best.dS));
+		for (;;) {
+			if (!first_time && nstack == 0 && zero_count <= 0) break;
+			if (16u < trace_count) break;
+			++trace_count;
+			first_time = false;
+			AlnState &a = work;
+			a.b = a.e = 2;
+			a.fm_q = a.fm_t = a.lm_q = a.lm_t = 0;
+			a.dH = a.dS = a.tm = 0.0f;
+			nc_trace_back(sh, tgt, Lt, tv, cell, stack, nstack, zero_count, a, flags);
+			if (flags & (F_OOB | F_STACK)) return;
+			nc_trim_frayed_ends(sh, a);
+			if (zero_count == 0 && nstack > 0) {
+				while (nstack > 0) {
+					Branch &br = stack[nstack - 1];
+					bool more = false;
+					while ((br.cur = (uint8_t)(br.cur << 1)) < T_INVALID) if (br.cur & br.mask) { more = true; break; }
+					if (more) break;
+					--nstack;
+				}
+				zero_count = -1;
+			}
+			// the stem as it is (:1265-1286)
+			if (a.e - a.b >= 3 && nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(th, a, best_aln, best, best_dg);
+			if (flags & F_OOB) return;
+			// one more column at the open end: the next bases or a dangling-end virtual base (:1307-1326)
+			if (a.lm_t != 0 || a.lm_q != Lq - 1) {
+				int tb, qb;
+				if (a.lm_t == 0) tb = bE;
+				else { --a.lm_t; if (a.lm_t < 0 || a.lm_t >= Lq) { flags |= F_OOB; return; } tb = sh.q[a.lm_t]; }
+				if (a.lm_q == Lq - 1) qb = bE;
+				else { ++a.lm_q; if (a.lm_q < 0 || a.lm_q >= Lq) { flags |= F_OOB; return; } qb = sh.q[a.lm_q]; }
+				if (a.e < MAX_COLS) { a.q[a.e] = (uint8_t)qb; a.t[a.e] = (uint8_t)tb; ++a.e; }
+				else flags |= F_TRUNC;
+			}
+			const int align_size = a.e - a.b;
+			if (align_size < 3) continue;
+			if (nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(th, a, best_aln, best, best_dg);
+			if (flags & F_OOB) return;
+			// without the closing pair, unless it is G-C / C-G (:1360-1406)
+			if (align_size <= 3) continue;
+			if (a.fm_t < 0 || a.fm_q >= Lq) { flags |= F_OOB; return; }
+			const int last_pair = sh.bbp[sh.q[a.fm_t]*NB + sh.q[a.fm_q]];
+			if (last_pair == bG*7 + bC || last_pair == bC*7 + bG) continue;
+			++a.fm_q;
+			--a.fm_t;
+			++a.b;
+			if (nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(th, a, best_aln, best, best_dg);
+			if (flags & F_OOB) return;
 		}
 	}
 }

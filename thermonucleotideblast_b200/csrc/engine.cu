@@ -183,6 +183,9 @@ struct tnt_engine {
 	// tables with the symmetry entropy folded into the initiation term for homodimers
 	DevBuf<Thermo> d_thermo_homo;
 	DevBuf<uint8_t> d_explicit;
+	DevBuf<OligoJob> d_jobs;
+	DevBuf<OligoJobResult> d_job_results;
+	DevBuf<uint16_t> d_job_trace;
 	const Thermo *thermo_override = nullptr;
 	const uint8_t *explicit_tgt = nullptr;
 	int explicit_len = 0;
@@ -2281,6 +2284,68 @@ long hit_sequence(tnt_engine *e, const tnt_hit *h, char *out, size_t cap)
 	return (long)s.size();
 }
 
+// ------------------------------------------------------------------------------------------
+// Oligo-only structures on the device (k_oligo_jobs)
+// ------------------------------------------------------------------------------------------
+void ensure_homo_thermo(tnt_engine *e)
+{
+	if (e->d_thermo_homo.p) return;
+	// local_align.dS = param_init_S + param_symmetry_S (nuc_cruc.cpp:1632): one float addition,
+	// done here exactly as the reference does it per evaluation
+	std::unique_ptr<Thermo> th(new Thermo(e->h_thermo));
+	th->init_S = th->init_S + symmetry_S();
+	e->d_thermo_homo.reserve(1, 0, e->stream);
+	CUDA_OK(cudaMemcpyAsync(e->d_thermo_homo.p, th.get(), sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+}
+
+OligoJob make_job(int kind, const std::string &query, const std::string &target, float ct)
+{
+	OligoJob j{};
+	if (query.empty() || query.size() > (size_t)MAX_OLIGO) throw std::runtime_error("oligo longer than TNT_MAX_OLIGO_LEN (56) bases");
+	const std::string &t = kind == JOB_HETERODIMER ? target : query;
+	if (t.size() > (size_t)MAX_WINDOW) throw std::runtime_error("second oligo longer than 64 bases");
+	j.kind = kind;
+	j.qlen = (int)query.size();
+	j.tlen = (int)t.size();
+	for (size_t i = 0; i < query.size(); ++i) {
+		const int b = base_from_ascii(query[i]);
+		if (b < 0) throw std::runtime_error(":char_to_nucleic_acid: Illegal base");
+		j.q[i] = (uint8_t)b;
+	}
+	for (size_t i = 0; i < t.size(); ++i) {
+		const int b = base_from_ascii(t[i]);
+		if (b < 0) throw std::runtime_error(":char_to_nucleic_acid: Illegal base");
+		j.t[i] = (uint8_t)b;
+	}
+	if (kind != JOB_HAIRPIN) {
+		if (!(ct > 0.0f)) throw std::runtime_error(":NucCruc::tm_dimer: Invalid strand_concentration");
+		j.r_log_ct = r_log_ct(ct);
+	}
+	return j;
+}
+
+// strand(c_a, c_b), nuc_cruc.h:890-910
+float duplex_ct(float a, float b) { return a > b ? a - 0.5f*b : b - 0.5f*a; }
+
+std::vector<OligoJobResult> run_oligo_jobs(tnt_engine *e, const std::vector<OligoJob> &jobs)
+{
+	std::vector<OligoJobResult> res(jobs.size());
+	if (jobs.empty()) return res;
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	ensure_homo_thermo(e);
+	e->d_jobs.upload(jobs, e->stream);
+	e->d_job_results.reserve(jobs.size(), 0, e->stream);
+	e->d_job_trace.reserve(jobs.size()*(size_t)JOB_TRACE_CELLS, 0, e->stream);
+	k_oligo_jobs<<<(unsigned)((jobs.size() + 31)/32), 32, 0, e->stream>>>(e->d_jobs.p, (uint32_t)jobs.size(), e->d_thermo.p,
+		e->d_thermo_homo.p, e->d_job_trace.p, e->d_job_results.p);
+	CUDA_OK(cudaGetLastError());
+	e->stats.kernel_launches++;
+	CUDA_OK(cudaMemcpyAsync(res.data(), e->d_job_results.p, res.size()*sizeof(OligoJobResult), cudaMemcpyDeviceToHost, e->stream));
+	CUDA_OK(cudaStreamSynchronize(e->stream));
+	return res;
+}
+
 // Text of all hits of the last search: the fragment ranges are read back from the packed database
 // with one kernel and one device-to-host copy, the strings are built on a few host threads.
 void hit_sequences(tnt_engine *e)
@@ -2963,6 +3028,62 @@ int tnt_debug_min_columns(float T, float na, const char *oligo, float strand_con
 		return lean_min_columns(th, os, min_tm);
 	}
 	catch (const std::exception &ex) { g_error = ex.what(); return -1; }
+}
+
+int tnt_engine_oligo_hairpin(tnt_engine *e, const char *query, tnt_align_result *out)
+{
+	API_BEGIN
+	if (!e || !query || !out) throw std::runtime_error("null argument");
+	const std::vector<OligoJobResult> r = run_oligo_jobs(e, std::vector<OligoJob>(1, make_job(JOB_HAIRPIN, query, "", 0.0f)));
+	std::memset(out, 0, sizeof(*out));
+	out->tm = r[0].tm; out->dH = r[0].dH; out->dS = r[0].dS;
+	out->dG = r[0].dH - e->prm.target_T*r[0].dS;
+	out->valid = (r[0].flags & (F_OOB | F_STACK | F_TRUNC)) ? -1 : r[0].valid;
+	if (r[0].valid) {
+		out->q_first = r[0].fm_q; out->t_first = r[0].fm_t;
+		out->q_last = r[0].lm_q; out->t_last = r[0].lm_t;
+		out->num_gap = r[0].ncols; // columns of the stem
+	}
+	API_END
+}
+
+int tnt_engine_assay_structures(tnt_engine *e, const tnt_search_options *opt, tnt_assay_structures *out)
+{
+	API_BEGIN
+	if (!e || !opt || (!out && !e->assays.empty())) throw std::runtime_error("null argument");
+	const float fps = opt->forward_primer_strand, rps = opt->reverse_primer_strand, ps = opt->probe_strand;
+	std::vector<OligoJob> jobs;
+	struct Slot { size_t assay; int field; };
+	std::vector<Slot> slots;
+	auto add = [&](size_t a, int field, const OligoJob &j) { jobs.push_back(j); slots.push_back(Slot{a, field}); };
+	for (size_t a = 0; a < e->assays.size(); ++a) {
+		const AssayHost &as = e->assays[a];
+		tnt_assay_structures &o = out[a];
+		for (int k = 0; k < 3; ++k) o.hairpin_tm[k] = o.homodimer_tm[k] = o.heterodimer_tm[k] = -1.0f; // hybrid_sig::init()
+		if (!as.F.empty() && !as.R.empty()) {
+			// tntblast_local.cpp:659-683: strand(c, c) for the oligo against itself, strand(c_f, c_r) for the pair
+			add(a, 0, make_job(JOB_HAIRPIN, as.F, "", 0.0f));
+			add(a, 1, make_job(JOB_HAIRPIN, as.R, "", 0.0f));
+			add(a, 3, make_job(JOB_HOMODIMER, as.F, "", duplex_ct(fps, fps)));
+			add(a, 4, make_job(JOB_HOMODIMER, as.R, "", duplex_ct(rps, rps)));
+			add(a, 6, make_job(JOB_HETERODIMER, as.F, as.R, duplex_ct(fps, rps)));
+			add(a, 7, make_job(JOB_HETERODIMER, as.F, as.F, duplex_ct(fps, rps)));
+			add(a, 8, make_job(JOB_HETERODIMER, as.R, as.R, duplex_ct(fps, rps)));
+		}
+		if (!as.P.empty()) {
+			add(a, 2, make_job(JOB_HAIRPIN, as.P, "", 0.0f));
+			add(a, 5, make_job(JOB_HOMODIMER, as.P, "", duplex_ct(ps, ps)));
+		}
+	}
+	const std::vector<OligoJobResult> r = run_oligo_jobs(e, jobs);
+	for (size_t i = 0; i < r.size(); ++i) {
+		if (r[i].flags & (F_OOB | F_STACK | F_TRUNC))
+			throw std::runtime_error("NucCruc traceback left the DP matrix (the reference reads unchecked memory here); unsupported parameters");
+		tnt_assay_structures &o = out[slots[i].assay];
+		const int f = slots[i].field;
+		(f < 3 ? o.hairpin_tm[f] : (f < 6 ? o.homodimer_tm[f - 3] : o.heterodimer_tm[f - 6])) = r[i].tm;
+	}
+	API_END
 }
 
 long tnt_debug_replay_selftest(uint32_t seed, int32_t cases, long *hits)

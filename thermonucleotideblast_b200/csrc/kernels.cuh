@@ -1202,6 +1202,73 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 	if ((tid & 31) == 0 && my_cells) atomicAdd(a.cells, my_cells);
 }
 
+// ------------------------------------------------------------------------------------------
+// Oligo-only structures (tntblast_local.cpp:657-686): hairpin of one oligo, homodimer of one oligo,
+// heterodimer of two oligos.  A handful of jobs per assay, one thread each; the DP rows live in
+// local memory, the trace in a global scratch slab (cleared by the thread: the hairpin fill only
+// writes a triangle).
+// ------------------------------------------------------------------------------------------
+enum { JOB_HETERODIMER = 0, JOB_HOMODIMER = 1, JOB_HAIRPIN = 2 };
+
+struct OligoJob {
+	int32_t kind, qlen, tlen;
+	float r_log_ct;                // NC_R*log(Ct) of the duplex (unused for hairpins)
+	uint8_t q[MAX_OLIGO];          // NucCruc codes, 5'->3'
+	uint8_t t[MAX_WINDOW];         // second strand, 5'->3' (the query itself for homodimers / hairpins)
+};
+
+struct OligoJobResult { float tm, dH, dS; int32_t valid, flags; int16_t fm_q, fm_t, lm_q, lm_t; int32_t ncols; };
+
+constexpr int JOB_TRACE_CELLS = MAX_OLIGO*MAX_WINDOW;
+
+__global__ void __launch_bounds__(32) k_oligo_jobs(const OligoJob *__restrict__ jobs, uint32_t njobs, const Thermo *__restrict__ thermo,
+	const Thermo *__restrict__ thermo_homo, uint16_t *__restrict__ trace_all, OligoJobResult *__restrict__ out)
+{
+	const uint32_t j = blockIdx.x*blockDim.x + threadIdx.x;
+	if (j >= njobs) return;
+	const OligoJob &job = jobs[j];
+	// homodimers carry the symmetry entropy in the initiation term (nuc_cruc.cpp:1632): own table copy
+	const Thermo *th = job.kind == JOB_HOMODIMER ? thermo_homo : thermo;
+	DpShared sh;
+	sh.dg = th->dg; sh.bbp = th->bbp; sh.wc = th->wc; sh.q = job.q; sh.Lq = job.qlen;
+	const int Lt = job.tlen;
+	uint16_t *trace = trace_all + (size_t)j*JOB_TRACE_CELLS;
+	int32_t rowM[MAX_WINDOW + 1], rowIq[MAX_WINDOW + 1], rowIt[MAX_WINDOW + 1];
+	unsigned flags = 0;
+	AlnState work, best_aln;
+	Best best;
+	best.valid = false;
+	best.dH = best.dS = best.tm = 0.0f;
+	best_aln.b = best_aln.e = 2;
+	best_aln.fm_q = best_aln.fm_t = best_aln.lm_q = best_aln.lm_t = 0;
+	const bool hairpin = job.kind == JOB_HAIRPIN;
+	const int tri = hairpin ? job.qlen - 4 : 0; // steric limit: three loop bases + one anchor (nuc_cruc.cpp:781-790)
+	if (Lt > 0 && job.qlen > 0 && !(hairpin && tri <= 0)) {
+		for (int c = 0; c < job.qlen*Lt; ++c) trace[c] = 0;
+		const DpResult dp = nc_fill<1>(sh, job.t, Lt, rowM, rowIq, rowIt, trace, tri);
+		RowMajorTrace<1> tv;
+		tv.trace = trace;
+		tv.Lt = Lt;
+		uint16_t cells[MAX_MAXCELLS];
+		int cursor = dp.last_raise < 0 ? 0 : dp.last_raise, remaining = dp.nmax;
+		bool fresh = true;
+		do {
+			const int ncells = collect_max_cells<1>(tv, job.qlen, Lt, cursor, remaining, cells);
+			if (hairpin) nc_enumerate_hairpin(sh, th, job.t, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
+			else nc_enumerate(sh, th, job.r_log_ct, job.t, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
+			fresh = false;
+		} while (remaining > 0 && !(flags & (F_OOB | F_STACK)));
+	}
+	OligoJobResult r;
+	r.tm = best.tm; r.dH = best.dH; r.dS = best.dS;
+	r.valid = best.valid ? 1 : 0;
+	r.flags = (int32_t)flags;
+	r.fm_q = (int16_t)best_aln.fm_q; r.fm_t = (int16_t)best_aln.fm_t;
+	r.lm_q = (int16_t)best_aln.lm_q; r.lm_t = (int16_t)best_aln.lm_t;
+	r.ncols = best.valid ? best_aln.e - best_aln.b : 0;
+	out[j] = r;
+}
+
 // Fast kernel: windows made of A/C/G/T only (the oligo may hold any code).  All units of one
 // launch belong to oligo strands of at most LQ bases.
 // Resident CTAs per SM the register allocation has to allow (other modes: experiments with

@@ -22,6 +22,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tntb200.h"
@@ -241,13 +242,36 @@ int tnt_finalize_hits(const tnt_hit_block *blocks, size_t n_blocks, const tnt_as
 			}
 		}
 		const bool do_uniquify = uniquify_mode < 0 ? any_cut : uniquify_mode != 0;
+		// the lists of different assay ids are independent: a few host threads when there is much to do
+		{
+			std::vector<std::list<Match> *> lists;
+			size_t total = 0;
+			for (auto &kv : by_id) { lists.push_back(&kv.second); total += kv.second.size(); }
+			const unsigned nthreads = total < 50000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+			std::vector<std::string> errors(nthreads);
+			auto work = [&](unsigned t) {
+				try {
+					for (size_t i = t; i < lists.size(); i += nthreads) {
+						std::list<Match> &l = *lists[i];
+						if (l.empty()) continue;
+						if (best_match) select_best_match(l);
+						if (do_uniquify) uniquify(l);
+						l.sort(less_output);
+					}
+				}
+				catch (const std::exception &ex) { errors[t] = ex.what(); }
+			};
+			if (nthreads == 1) work(0);
+			else {
+				std::vector<std::thread> pool;
+				for (unsigned t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
+				for (std::thread &t : pool) t.join();
+			}
+			for (const std::string &err : errors) if (!err.empty()) throw std::runtime_error(err);
+		}
 		std::vector<tnt_final_hit> result;
 		for (auto &kv : by_id) {
 			std::list<Match> &l = kv.second;
-			if (l.empty()) continue;
-			if (best_match) select_best_match(l);
-			if (do_uniquify) uniquify(l);
-			l.sort(less_output);
 			for (const Match &m : l) {
 				tnt_final_hit f;
 				f.block = m.block;

@@ -119,6 +119,11 @@ void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3)
 	std::memcpy(th.S, SL_PARAM_S, sizeof(th.S));
 	std::memcpy(th.loop_S, SL_LOOP_S, sizeof(th.loop_S));
 	std::memcpy(th.bulge_S, SL_BULGE_S, sizeof(th.bulge_S));
+	static_assert(SL_NUM_HAIRPIN_LOOP == NUM_HAIRPIN_LOOP, "special hairpin loops");
+	std::memcpy(th.hairpin_S, SL_HAIRPIN_S, sizeof(th.hairpin_S));
+	std::memcpy(th.hairpin_loop, SL_HAIRPIN_LOOP, sizeof(th.hairpin_loop));
+	std::memcpy(th.hairpin_special_H, SL_HAIRPIN_SPECIAL_H, sizeof(th.hairpin_special_H));
+	std::memcpy(th.hairpin_special_S, SL_HAIRPIN_SPECIAL_S, sizeof(th.hairpin_special_S));
 
 	for (int x = 0; x < NB; ++x)
 		for (int y = 0; y < NB; ++y)

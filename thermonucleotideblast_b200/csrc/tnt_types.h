@@ -14,6 +14,7 @@ constexpr int NUM_FLANK = 4;             // tntblast.h:76
 constexpr int MAX_WINDOW = MAX_OLIGO + 2*NUM_FLANK;   // 64 target bases at most
 constexpr int MAX_COLS = MAX_OLIGO + MAX_WINDOW + 4;  // alignment columns incl. dangling ends
 constexpr int MAX_LOOP = 512;
+constexpr int NUM_HAIRPIN_LOOP = 131;     // NUM_SPECIAL_HAIRPIN_LOOP, nuc_cruc.h:587
 
 // trace bits (reference nuc_cruc.h:62-65)
 constexpr unsigned T_DIAG = 1, T_UP = 2, T_LEFT = 4, T_INVALID = 8;
@@ -30,6 +31,11 @@ struct Thermo {
 	float T, log_na;
 	float init_H, init_S, at_H, at_S, salt, asym_loop_dS, bulge_at_S;
 	int32_t dangle5, dangle3;
+	// hairpins (nuc_cruc.cpp:2301-2394): loop entropy by loop length, special tri- / tetra-loops
+	float hairpin_S[MAX_LOOP + 1];
+	char hairpin_loop[NUM_HAIRPIN_LOOP][8];
+	float hairpin_special_H[NUM_HAIRPIN_LOOP];
+	float hairpin_special_S[NUM_HAIRPIN_LOOP];
 };
 
 // One (oligo, strand) search unit.  `seq` is the oligo 5'->3' in NucCruc codes (the NucCruc

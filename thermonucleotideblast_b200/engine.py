@@ -138,6 +138,12 @@ class FastaFragment(C.Structure):
                 ("len", C.c_uint32), ("target_id", C.c_uint32)]
 
 
+class AssayStructures(C.Structure):
+    """tnt_assay_structures (include/tntb200.h): index 0 / 1 / 2 = forward primer / reverse primer / probe;
+    heterodimer_tm = F with R, F with F, R with R."""
+    _fields_ = [("hairpin_tm", C.c_float * 3), ("homodimer_tm", C.c_float * 3), ("heterodimer_tm", C.c_float * 3)]
+
+
 class Fragment(C.Structure):
     """tnt_fragment (include/tntb200.h): one piece of a database record as the driver cut it."""
     _fields_ = [("record", C.c_uint32), ("start", C.c_uint32), ("stop", C.c_uint32), ("max_stop", C.c_uint32), ("len", C.c_uint32)]
@@ -227,6 +233,8 @@ def load_library() -> C.CDLL:
     L.tnt_engine_align.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int32, C.c_float, u32p, u32p,
                                    C.c_long, C.POINTER(AlignResult)]
     L.tnt_engine_oligo_dimer.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.POINTER(AlignResult)]
+    L.tnt_engine_oligo_hairpin.argtypes = [vp, C.c_char_p, C.POINTER(AlignResult)]
+    L.tnt_engine_assay_structures.argtypes = [vp, C.POINTER(SearchOptions), C.POINTER(AssayStructures)]
     L.tnt_engine_scan_only.argtypes = [vp, C.POINTER(SearchOptions), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -514,6 +522,18 @@ class Engine:
         out = AlignResult()
         self._check(self.L.tnt_engine_oligo_dimer(self.h, query.encode(), target.encode() if target else None, conc_a, conc_b, C.byref(out)))
         return out
+
+    def oligo_hairpin(self, query: str) -> AlignResult:
+        """Hairpin Tm of an oligo (approximate_tm_hairpin, tntblast_local.cpp:661) on the device."""
+        out = AlignResult()
+        self._check(self.L.tnt_engine_oligo_hairpin(self.h, query.encode(), C.byref(out)))
+        return out
+
+    def assay_structures(self, opts: SearchOptions, n_assays: int):
+        """Hairpin / homodimer / heterodimer temperatures of every registered assay (one launch)."""
+        out = (AssayStructures * max(n_assays, 1))()
+        self._check(self.L.tnt_engine_assay_structures(self.h, C.byref(opts), out))
+        return [out[i] for i in range(n_assays)]
 
     def scan_only(self, opts: SearchOptions):
         """Seed scan of all fragments with the stage-1 oligo strands; returns (candidates, ms)."""
