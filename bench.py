@@ -848,7 +848,14 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    alu_peak = SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12  # int32 lane-ops/s, TOP/s
+    alu_nominal = SM_COUNT * LANES_PER_SM * sm_max * 1e6 / 1e12  # int32 lane-ops/s, TOP/s
+    # measured on this GPU, right now (tnt_engine_alu_peak: independent 32-bit adds / min-max / the DP's
+    # subtract-then-max pairs); MEASURED_PEAKS.json carries no integer figure
+    try:
+        alu_measured = eng.alu_peak()
+    except Exception as ex:
+        alu_measured = {"error": str(ex)}
+    alu_peak = alu_measured.get("iadd") or alu_nominal
     align_s = align_ms / args.steps / 1e3
     scan_s = scan_ms / args.steps / 1e3
     alu_achieved = ALU_OPS_PER_CELL * st.dp_cells / align_s / 1e12 if align_s > 0 else 0.0
@@ -885,8 +892,11 @@ def main():
                      "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": nuccruc_traffic,
                      "traffic_note": "bytes per step over all NucCruc launches (ncu, profiles/dram_r01_v7.csv): ~450 GB/s, 7 % of the HBM peak -- the kernels are ALU-bound, not memory-bound",
                      "kernel": "k_align (NucCruc DP + traceback + evaluation)",
-                     "note": "27 int32 ALU ops per DP cell (SURVEY 8d) x %d cells per step / CUDA-event time of the kernel; "
-                             "peak = 148 SM x 128 lanes x %.0f MHz (nominal issue peak, no measured figure exists)" % (st.dp_cells, sm_max)},
+                     "peak_source": "measured on this GPU in this run: independent 32-bit integer adds (tnt_engine_alu_peak)"
+                                    if "iadd" in alu_measured else "nominal",
+                     "peak_nominal": alu_nominal, "alu_measured_TOPs": alu_measured,
+                     "note": "27 int32 ALU ops per DP cell (SURVEY 8d) x %d cells per step / CUDA-event time of the kernels; "
+                             "nominal issue peak = 148 SM x 128 lanes x %.0f MHz" % (st.dp_cells, sm_max)},
         "roofline_seed_scan": {"bound": "hbm", "achieved": scan_achieved, "peak": hbm_peak, "unit": "GB/s",
                                "frac": scan_achieved / hbm_peak if hbm_peak else None, "traffic": scan_traffic,
                                "kernel": "k_seed_scan", "peak_source": hbm_src,

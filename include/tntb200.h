@@ -341,6 +341,11 @@ typedef struct {
 } tnt_assay_structures;
 int tnt_engine_assay_structures(tnt_engine *e, const tnt_search_options *opt, tnt_assay_structures *out /* one per assay */);
 
+/* Measured 32-bit integer throughput of the device in TOP/s (lane operations), the denominator of
+ * the NucCruc roofline: tops[0] independent adds, tops[1] independent min / max, tops[2] the
+ * subtract-then-max pair of the DP recurrence (two operations per pair).  A few milliseconds. */
+int tnt_engine_alu_peak(tnt_engine *e, double *tops /* [3] */);
+
 /* Seed-scan-only pass over every registered fragment with the registered assays (timing aid for
  * the HBM roofline): returns the number of unique candidates and the device time. */
 int tnt_engine_scan_only(tnt_engine *e, const tnt_search_options *opt, uint64_t *candidates, double *ms);

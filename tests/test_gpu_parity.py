@@ -875,3 +875,44 @@ def test_assay_structures_in_one_call(eng, oracle):
         assert list(g.heterodimer_tm) == [np.float32(x) for x in want_x], a
         ne += sum(1 for x in want_h + want_d + want_x if x > 0)
     assert ne > 60
+
+
+def test_device_pairing_equals_host_join(engine_lib, oracle, monkeypatch):
+    """The F x R (x P) join on the device (k_pair_keys / radix sorts / k_pair_unique / k_pair_join) against
+    the same loops on the host (TNT_HOST_JOIN=1) and against the oracle: ordered hit lists, also with
+    single-primer amplicons forbidden, a min-max clamp, duplicate sites (indel copies), nested
+    amplicons and probe-only assays mixed into the PCR run."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(4711)
+    db = [gen.random_codes(int(rng.integers(30000, 80000)), rng) for _ in range(6)]
+    assays = gen.make_assays(rng, db, 6, "taqman", variants=4) + gen.make_assays(rng, db, 6, "pcr", variants=4) + \
+        gen.make_assays(rng, db, 3, "probe", variants=3)
+    # nested amplicons: a second reverse site behind the first one
+    F, R, _ = assays[6]
+    gen.plant(db[0], 5000, F + gen.rand_oligo(120, rng) + gen.revcomp(R) + gen.rand_oligo(60, rng) + gen.revcomp(R))
+    total = 0
+    for single, mmc, max_len in ((1, -1, 2000), (0, 3, 600)):
+        o = H.default_options(min_primer_tm=38.0, min_probe_tm=38.0, max_len=max_len, single_primer_pcr=single, min_max_primer_clamp=mmc)
+
+        def run():
+            with Engine() as e:
+                e.add_targets(db)
+                e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+                return [(h.target_id, h.assay_index) + hit_key(e, h, assays[h.assay_index]) + hit_floats(h) for h in e.search(to_opts(o))]
+
+        dev = run()
+        monkeypatch.setenv("TNT_HOST_JOIN", "1")
+        host = run()
+        monkeypatch.delenv("TNT_HOST_JOIN")
+        assert dev == host and len(dev) >= 20
+        k = 0
+        for t, codes in enumerate(db):
+            for i, a in enumerate(assays):
+                want = oracle.search(codes, a[0], a[1], a[2], o)
+                mine = [x for x in dev if x[0] == t and x[1] == i]
+                assert len(mine) == len(want)
+                assert [x[2:2 + len(w.exact_key())] for x, w in zip(mine, want)] == [w.exact_key() for w in want]
+                k += len(want)
+        assert k == len(dev)
+        total += k
+    assert total >= 50

@@ -184,28 +184,10 @@ void join_pcr_sorted(const std::vector<const BoundSite *> &all, int assay_index,
 			if ((r.loc3 - f.loc5 + 1) > (int)opt.max_len) continue;
 			if (apply_mmc && (unsigned)std::max(f.anchor3, r.anchor3) <= mmc) continue;
 
-			const bool swap_out = (f.role == TNT_OLIGO_R && r.role == TNT_OLIGO_F);
-			const BoundSite &fo = swap_out ? r : f, &ro = swap_out ? f : r;
-			const int f_oligo = (f.role == TNT_OLIGO_R && r.role == TNT_OLIGO_R) ? TNT_OLIGO_R : TNT_OLIGO_F;
-			const int r_oligo = (f.role == TNT_OLIGO_F && r.role == TNT_OLIGO_F) ? TNT_OLIGO_F : TNT_OLIGO_R;
-
 			auto emit = [&](const BoundSite *p) {
-				tnt_hit h = blank_hit(assay_index, assay_id, f.target);
-				h.primer_strand = (f.role == TNT_OLIGO_F) ? TNT_PLUS : TNT_MINUS;
-				h.amp_first = f.loc5;
-				h.amp_last = r.loc3;
-				h.forward = slot_of(fo, f_oligo);
-				h.reverse = slot_of(ro, r_oligo);
-				HitSites hs{(int)(&fo - base), (int)(&ro - base), -1};
-				h.forward_clamp = (int8_t)fo.anchor3;
-				h.reverse_clamp = (int8_t)ro.anchor3;
-				if (p) {
-					h.probe = slot_of(*p, TNT_OLIGO_P);
-					h.probe_first = p->loc5;
-					h.probe_last = p->loc3;
-					h.probe_strand = p->plus ? TNT_PLUS : TNT_MINUS;
-					hs.probe = (int)(p - base);
-				}
+				tnt_hit h;
+				HitSites hs;
+				make_pcr_hit(f, r, p, assay_index, assay_id, base, h, hs);
 				hits.push_back(h);
 				refs.push_back(hs);
 			};
@@ -222,6 +204,36 @@ void join_pcr_sorted(const std::vector<const BoundSite *> &all, int assay_index,
 		}
 	}
 }
+
+} // namespace
+
+void make_pcr_hit(const BoundSite &f, const BoundSite &r, const BoundSite *p, int assay_index, int assay_id,
+	const BoundSite *base, tnt_hit &h, HitSites &hs)
+{
+	// forward primer first in the record whatever bound upstream (amplicon_search.cpp:478-483)
+	const bool swap_out = (f.role == TNT_OLIGO_R && r.role == TNT_OLIGO_F);
+	const BoundSite &fo = swap_out ? r : f, &ro = swap_out ? f : r;
+	const int f_oligo = (f.role == TNT_OLIGO_R && r.role == TNT_OLIGO_R) ? TNT_OLIGO_R : TNT_OLIGO_F;
+	const int r_oligo = (f.role == TNT_OLIGO_F && r.role == TNT_OLIGO_F) ? TNT_OLIGO_F : TNT_OLIGO_R;
+	h = blank_hit(assay_index, assay_id, f.target);
+	h.primer_strand = (f.role == TNT_OLIGO_F) ? TNT_PLUS : TNT_MINUS;
+	h.amp_first = f.loc5;
+	h.amp_last = r.loc3;
+	h.forward = slot_of(fo, f_oligo);
+	h.reverse = slot_of(ro, r_oligo);
+	hs = HitSites{(int)(&fo - base), (int)(&ro - base), -1};
+	h.forward_clamp = (int8_t)fo.anchor3;
+	h.reverse_clamp = (int8_t)ro.anchor3;
+	if (p) {
+		h.probe = slot_of(*p, TNT_OLIGO_P);
+		h.probe_first = p->loc5;
+		h.probe_last = p->loc3;
+		h.probe_strand = p->plus ? TNT_PLUS : TNT_MINUS;
+		hs.probe = (int)(p - base);
+	}
+}
+
+namespace {
 
 void join_padlock(const std::vector<const BoundSite *> &group, int assay_index, int assay_id,
 	const AssembleOptions &opt, const BoundSite *base, std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
@@ -304,7 +316,7 @@ BoundSite make_site(const BoundHead &h, uint32_t index, const OligoStrand &os)
 
 void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
 	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
-	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs)
+	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs, bool primers_joined_on_device)
 {
 	// (fragment, assay) pairs in ascending order, like the reference's nested loops; ties keep the
 	// input order (one packed 64-bit key per site: group rank, then index)
@@ -352,7 +364,7 @@ void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &o
 			if (assay_has_primers[(size_t)ai]) { // tntblast_local.cpp:559-611
 				if (opt.assay_format == TNT_ASSAY_PADLOCK || opt.assay_format == TNT_ASSAY_MIPS)
 					join_padlock(group, ai, id, opt, base, out_hits, out_refs);
-				else join_pcr(group, ai, id, assay_has_probe[(size_t)ai] != 0, opt, base, out_hits, out_refs);
+				else if (!primers_joined_on_device) join_pcr(group, ai, id, assay_has_probe[(size_t)ai] != 0, opt, base, out_hits, out_refs);
 			}
 			else join_probe(group, ai, id, base, out_hits, out_refs); // :612-625
 		}

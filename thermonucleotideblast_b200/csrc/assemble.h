@@ -42,9 +42,16 @@ struct AssembleOptions {
 // amplicon() join (amplicon_search.cpp:355-674), padlock() joins (padlock_search.cpp:130-358),
 // hybrid() (probe_search.cpp:103-227); `sites` holds everything that passed the per-oligo filters.
 // The alignment-text offsets of the hits are left at 0; `refs` tells the caller which sites to render.
+// `primers_joined_on_device`: the PCR join of assays with primers was done by k_pair_join (the caller turns
+// its index triples into hits with make_pcr_hit); only probe-only assays are assembled here.
 void assemble_hits(const std::vector<BoundSite> &sites, const AssembleOptions &opt, const std::vector<int> &assay_ids,
 	const std::vector<int> &assay_has_primers, const std::vector<int> &assay_has_probe,
-	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs);
+	std::vector<tnt_hit> &hits, std::vector<HitSites> &refs, bool primers_joined_on_device = false);
+
+// One PCR hit from its sites: f = the minus-strand primer site, r = the plus-strand primer site, p = probe
+// site or nullptr (amplicon_search.cpp:447-555, :565-671)
+void make_pcr_hit(const BoundSite &f, const BoundSite &r, const BoundSite *p, int assay_index, int assay_id,
+	const BoundSite *base, tnt_hit &hit, HitSites &ref);
 
 // ---- exact replay of the reference's staged PCR search for one (fragment, assay) group ----------
 // amplicon() binds the four primer categories one after the other and culls its match list in

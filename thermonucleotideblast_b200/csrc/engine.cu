@@ -10,6 +10,7 @@
 // There is no CPU fallback: every stage-A/B result comes from the kernels in kernels.cuh.
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cctype>
@@ -307,6 +308,14 @@ struct tnt_engine {
 	DevBuf<uint32_t> d_group;
 	DevBuf<int32_t> d_p5;
 	DevBuf<uint8_t> d_extract;
+
+	// amplicon pairing on the device (k_pair_*)
+	DevBuf<uint64_t> d_pair_key[4];   // group / location keys, each with its sort double
+	DevBuf<uint32_t> d_pair_order[2];
+	DevBuf<uint8_t> d_pair_alive, d_pair_tmp, d_assay_probe;
+	DevBuf<PairRec> d_pairs;
+	DevBuf<uint32_t> d_pair_count;
+	uint64_t assay_probe_version = ~(uint64_t)0;
 
 	// exact replay of the reference's staged PCR search (groups where its culls can lose a site)
 	DevBuf<uint32_t> d_crowd_bits;
@@ -1854,6 +1863,87 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	(void)o;
 }
 
+// Amplicon pairing of the live sites on the device (kernels.cuh: k_pair_*).  Returns the sorted order
+// (position -> index into the live heads) and the index triples, ordered like the reference emits
+// its hits: by (fragment, assay), then forward site, reverse site, probe site in list order.
+void pair_on_device(tnt_engine *e, const tnt_search_options &o, uint32_t n_live, std::vector<uint32_t> &order, std::vector<PairRec> &pairs)
+{
+	order.clear();
+	pairs.clear();
+	if (n_live == 0) return;
+	HostTimer t("pairing on the device");
+	OsSet &stage1 = *e->set1, &stage2 = *e->set2;
+	const size_t n = n_live;
+	if (e->assay_probe_version != e->assays_version) {
+		std::vector<uint8_t> has_probe(e->assays.size());
+		for (size_t a = 0; a < e->assays.size(); ++a) has_probe[a] = !e->assays[a].P.empty();
+		e->d_assay_probe.upload(has_probe, e->stream);
+		e->assay_probe_version = e->assays_version;
+	}
+	for (int k = 0; k < 4; ++k) e->d_pair_key[k].reserve(n, 0, e->stream);
+	for (int k = 0; k < 2; ++k) e->d_pair_order[k].reserve(n, 0, e->stream);
+	e->d_pair_alive.reserve(n, 0, e->stream);
+	e->d_pair_count.reserve(1, 0, e->stream);
+	PairArgs a{};
+	a.heads = e->d_live_heads.p;
+	a.n = n_live;
+	a.os1 = stage1.d_os.p;
+	a.os2 = stage2.d_os.p;
+	a.nos1 = (uint32_t)stage1.os.size();
+	a.assay_has_probe = e->d_assay_probe.p;
+	a.key_group = e->d_pair_key[0].p;
+	a.key_loc = e->d_pair_key[2].p;
+	a.order = e->d_pair_order[0].p;
+	a.alive = e->d_pair_alive.p;
+	a.pair_count = e->d_pair_count.p;
+	a.max_len = (int32_t)o.max_len;
+	a.single_primer_pcr = o.single_primer_pcr;
+	a.min_max_primer_clamp = o.min_max_primer_clamp;
+	const unsigned grid = (unsigned)std::min<size_t>((n + 255)/256, (size_t)e->sm_count*8);
+	k_pair_keys<<<grid, 256, 0, e->stream>>>(a);
+	// stable LSD order: by location first, then by (fragment, assay)
+	size_t tmp_bytes = 0;
+	CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->d_pair_key[2].p, e->d_pair_key[3].p, e->d_pair_order[0].p, e->d_pair_order[1].p,
+		(int)n, 0, 64, e->stream));
+	e->d_pair_tmp.reserve(tmp_bytes + 16, 0, e->stream);
+	CUDA_OK(cub::DeviceRadixSort::SortPairs(e->d_pair_tmp.p, tmp_bytes, e->d_pair_key[2].p, e->d_pair_key[3].p, e->d_pair_order[0].p, e->d_pair_order[1].p,
+		(int)n, 0, 64, e->stream));
+	k_pair_gather<<<grid, 256, 0, e->stream>>>(e->d_pair_key[0].p, e->d_pair_order[1].p, n_live, e->d_pair_key[1].p);
+	CUDA_OK(cub::DeviceRadixSort::SortPairs(e->d_pair_tmp.p, tmp_bytes, e->d_pair_key[1].p, e->d_pair_key[0].p, e->d_pair_order[1].p, e->d_pair_order[0].p,
+		(int)n, 0, 64, e->stream));
+	a.order = e->d_pair_order[0].p;
+	k_pair_unique<<<grid, 256, 0, e->stream>>>(a);
+	CUDA_OK(cudaGetLastError());
+	e->stats.kernel_launches += 3;
+	uint32_t cap = (uint32_t)std::max<size_t>(e->d_pairs.cap, 1u << 16);
+	for (;;) {
+		e->d_pairs.reserve(cap, 0, e->stream);
+		CUDA_OK(cudaMemsetAsync(e->d_pair_count.p, 0, sizeof(uint32_t), e->stream));
+		a.pairs = e->d_pairs.p;
+		a.pair_cap = cap;
+		k_pair_join<<<grid, 256, 0, e->stream>>>(a);
+		CUDA_OK(cudaGetLastError());
+		e->stats.kernel_launches++;
+		uint32_t cnt = 0;
+		CUDA_OK(cudaMemcpyAsync(&cnt, e->d_pair_count.p, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		if (cnt > cap) { cap = cnt + cnt/8; continue; }
+		order.resize(n);
+		pairs.resize(cnt);
+		CUDA_OK(cudaMemcpyAsync(order.data(), e->d_pair_order[0].p, n*sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+		if (cnt) CUDA_OK(cudaMemcpyAsync(pairs.data(), e->d_pairs.p, (size_t)cnt*sizeof(PairRec), cudaMemcpyDeviceToHost, e->stream));
+		CUDA_OK(cudaStreamSynchronize(e->stream));
+		e->stats.d2h_bytes += n*sizeof(uint32_t) + (uint64_t)cnt*sizeof(PairRec);
+		break;
+	}
+	// the reference's order: groups ascending, inside a group the loops' order
+	std::sort(pairs.begin(), pairs.end(), [](const PairRec &x, const PairRec &y) {
+		if (x.f != y.f) return x.f < y.f;
+		if (x.r != y.r) return x.r < y.r;
+		return x.p < y.p;
+	});
+}
+
 // Which groups with a hit does the reference possibly treat differently from a join over all bound
 // sites?  Two ways the culls of amplicon() can lose a site (assemble.h):
 //  (1) two bound sites of the group whose order by (loc_5, loc_3) is not strictly their order by
@@ -2051,6 +2141,9 @@ void search(tnt_engine *e, const tnt_search_options &o)
 	const bool prefilter = ((o.assay_format == TNT_ASSAY_PCR && !stage2.os.empty()) || padlock_format) && key_space <= ((uint64_t)1 << 31);
 	uint32_t n_live = n2;
 	const uint32_t *site_index = nullptr; // record index of each downloaded head (nullptr: identity)
+	bool paired_on_device = false;
+	std::vector<uint32_t> pair_order;     // sorted position -> live site
+	std::vector<PairRec> pair_recs;
 	if (prefilter && n2 != 0) {
 		uint32_t max_target_len = 1;
 		for (const Target &t : e->targets) max_target_len = std::max(max_target_len, t.len);
@@ -2106,6 +2199,11 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		}
 		site_index = e->h_live_index;
 		e->stats.d2h_bytes += (uint64_t)n_live*(sizeof(BoundHead) + sizeof(uint32_t));
+		// PCR: the F x R (x P) join of the live sites runs on the device as well
+		if (!padlock_format && !std::getenv("TNT_HOST_JOIN")) {
+			pair_on_device(e, o, n_live, pair_order, pair_recs);
+			paired_on_device = true;
+		}
 	}
 	else {
 		fetch_heads(e, 0, n2);
@@ -2150,7 +2248,38 @@ void search(tnt_engine *e, const tnt_search_options &o)
 		assay_has_probe.push_back(!a.P.empty());
 	}
 	std::vector<HitSites> refs;
-	{ HostTimer t("assemble_hits"); assemble_hits(sites, ao, assay_ids, assay_has_primers, assay_has_probe, e->hits, refs); }
+	bool any_probe_only = false;
+	for (size_t a = 0; a < assay_has_primers.size(); ++a) any_probe_only = any_probe_only || !assay_has_primers[a];
+	if (!paired_on_device || any_probe_only) {
+		HostTimer t("assemble_hits");
+		assemble_hits(sites, ao, assay_ids, assay_has_primers, assay_has_probe, e->hits, refs, paired_on_device);
+	}
+	if (paired_on_device) {
+		// index triples of k_pair_join -> hit records; merged with the hits of probe-only assays (assembled
+		// above) in (fragment, assay) order
+		std::vector<tnt_hit> dhits(pair_recs.size());
+		std::vector<HitSites> drefs(pair_recs.size());
+		for (size_t i = 0; i < pair_recs.size(); ++i) {
+			const BoundSite &f = sites[pair_order[(size_t)pair_recs[i].f]], &r = sites[pair_order[(size_t)pair_recs[i].r]];
+			const BoundSite *p = pair_recs[i].p >= 0 ? &sites[pair_order[(size_t)pair_recs[i].p]] : nullptr;
+			make_pcr_hit(f, r, p, f.assay, assay_ids[(size_t)f.assay], sites.data(), dhits[i], drefs[i]);
+		}
+		if (e->hits.empty()) { e->hits.swap(dhits); refs.swap(drefs); }
+		else if (!dhits.empty()) {
+			std::vector<tnt_hit> merged(e->hits.size() + dhits.size());
+			std::vector<HitSites> mrefs(merged.size());
+			auto less_group = [](const tnt_hit &x, const tnt_hit &y) { return x.target_id != y.target_id ? x.target_id < y.target_id : x.assay_index < y.assay_index; };
+			size_t i = 0, j = 0, k = 0;
+			while (i < e->hits.size() || j < dhits.size()) {
+				const bool take_dev = j < dhits.size() && (i >= e->hits.size() || less_group(dhits[j], e->hits[i]));
+				if (take_dev) { merged[k] = dhits[j]; mrefs[k] = drefs[j]; ++j; }
+				else { merged[k] = e->hits[i]; mrefs[k] = refs[i]; ++i; }
+				++k;
+			}
+			e->hits.swap(merged);
+			refs.swap(mrefs);
+		}
+	}
 
 	// PCR: the join above runs over every bound site.  The reference culls its match list between
 	// the binding steps and can lose a site when bound sites of one assay overlap
@@ -3082,6 +3211,35 @@ int tnt_engine_assay_structures(tnt_engine *e, const tnt_search_options *opt, tn
 		tnt_assay_structures &o = out[slots[i].assay];
 		const int f = slots[i].field;
 		(f < 3 ? o.hairpin_tm[f] : (f < 6 ? o.homodimer_tm[f - 3] : o.heterodimer_tm[f - 6])) = r[i].tm;
+	}
+	API_END
+}
+
+int tnt_engine_alu_peak(tnt_engine *e, double *tops)
+{
+	API_BEGIN
+	if (!e || !tops) throw std::runtime_error("null argument");
+	CUDA_OK(cudaSetDevice(e->prm.device));
+	DevBuf<int> sink;
+	sink.reserve(4, 0, e->stream);
+	const int iters = 4096, grid = e->sm_count*16, seed = (int)(e->total_bases & 1023u) + 3;
+	for (int mode = 0; mode < 3; ++mode) {
+		double best = 0.0;
+		for (int rep = 0; rep < 4; ++rep) {
+			CUDA_OK(cudaEventRecord(e->ev[6], e->stream));
+			if (mode == 0) k_alu_peak<0><<<grid, 256, 0, e->stream>>>(iters, seed, sink.p);
+			else if (mode == 1) k_alu_peak<1><<<grid, 256, 0, e->stream>>>(iters, seed, sink.p);
+			else k_alu_peak<2><<<grid, 256, 0, e->stream>>>(iters, seed, sink.p);
+			CUDA_OK(cudaGetLastError());
+			CUDA_OK(cudaEventRecord(e->ev[7], e->stream));
+			CUDA_OK(cudaStreamSynchronize(e->stream));
+			float ms = 0;
+			CUDA_OK(cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]));
+			// instructions: mode 0 / 1 one per chain step; mode 2 counts the add and the max as two operations
+			const double ops = (double)grid*256.0*(double)iters*16.0*8.0*(mode == 2 ? 2.0 : 1.0);
+			if (rep > 0) best = std::max(best, ops/(ms*1e-3)/1e12);
+		}
+		tops[mode] = best;
 	}
 	API_END
 }

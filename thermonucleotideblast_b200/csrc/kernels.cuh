@@ -980,9 +980,13 @@ __global__ void k_live_compact(LiveArgs a, uint32_t from, uint32_t to, int pass)
 		bool keep;
 		if (pass == 1) {
 			if (b.flags & (F_OOB | F_STACK | F_TRUNC)) atomicOr(a.err_flags, (uint32_t)b.flags);
-			const uint64_t key = live_key(a, b.target, a.os1[b.os].assay, b.loc5);
-			keep = live_test(a.live_r, key) || live_test(a.live_r, key + 1); // bucket nbucket-1 is never marked
-			if (keep) atomicOr(a.live_f + (key >> 5), 1u << (key & 31u));
+			const OligoStrand &o1 = a.os1[b.os];
+			if (o1.role == 2) keep = true; // site of a probe-only assay in a PCR run (tntblast_local.cpp:612-625): a hit by itself
+			else {
+				const uint64_t key = live_key(a, b.target, o1.assay, b.loc5);
+				keep = live_test(a.live_r, key) || live_test(a.live_r, key + 1); // bucket nbucket-1 is never marked
+				if (keep) atomicOr(a.live_f + (key >> 5), 1u << (key & 31u));
+			}
 		}
 		else {
 			const uint64_t key = live_key(a, b.target, a.os2[b.os - a.nos1].assay, b.loc5);
@@ -1102,6 +1106,129 @@ __global__ void k_compact_cands(const Candidate *__restrict__ cand, uint32_t cap
 			r.target_k = c.target_k;
 			r.t = c.t;
 			out[sp.out_off + i] = r;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Amplicon pairing on the device (the final loops of amplicon(), amplicon_search.cpp:355-441)
+//
+// The bound sites that can be part of an amplicon (k_live_*) are put into the order of the
+// reference's final list -- by (fragment, assay), then (loc_5, loc_3) like sort_by_oligo_loc sorts a
+// list of bound sites (:12-26), sites of equal range in the order of their categories -- by two radix
+// sorts over 64-bit keys (k_pair_keys).  k_pair_unique keeps one site per category and range, the one
+// bind_oligo's own uniqueness step keeps (bind_oligo.cpp:49-82, :810-826: highest Tm, then most
+// mismatches, then the longest alignment text, then the later seed).  k_pair_join runs the F x R (x P)
+// loops of one forward site per thread: orientation, f.loc_3 < r.loc_5, amplicon length <= max_len,
+// the single-primer rule, min-max 3' clamp (:383-397), and for assays with a probe every probe site
+// strictly between the two in the list, inside the amplicon and clear of the primer that binds
+// its own strand (:399-441).  What leaves the device are index triples.
+// ------------------------------------------------------------------------------------------
+struct PairArgs {
+	const BoundHead *heads;        // live sites (compacted by k_live_compact)
+	uint32_t n;
+	const OligoStrand *os1, *os2;
+	uint32_t nos1;
+	const uint8_t *assay_has_probe;
+	uint64_t *key_group, *key_loc; // [n]
+	uint32_t *order;               // [n] site index, becomes the sorted order
+	uint8_t *alive;                // [n] by sorted position
+	PairRec *pairs;
+	uint32_t *pair_count;
+	uint32_t pair_cap;
+	int32_t max_len, single_primer_pcr, min_max_primer_clamp;
+};
+
+__device__ __forceinline__ const OligoStrand &pair_os(const PairArgs &a, uint32_t os) { return os < a.nos1 ? a.os1[os] : a.os2[os - a.nos1]; }
+__device__ __forceinline__ uint32_t pair_category(const OligoStrand &o) { return (uint32_t)(o.plus ? 3 : 0) + (uint32_t)o.role; }
+
+__global__ void k_pair_keys(PairArgs a)
+{
+	for (uint32_t i = blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += gridDim.x*blockDim.x) {
+		const BoundHead b = a.heads[i];
+		const OligoStrand &o = pair_os(a, b.os);
+		a.key_group[i] = ((uint64_t)b.target << 32) | (uint32_t)o.assay;
+		const uint32_t span = (uint32_t)min(max(b.loc3 - b.loc5 + 32768, 0), 0xffffff);
+		a.key_loc[i] = ((uint64_t)((uint32_t)b.loc5 ^ 0x80000000u) << 32) | ((uint64_t)span << 8) | pair_category(o);
+		a.order[i] = i;
+	}
+}
+
+// key_out[j] = key_in[order[j]]
+__global__ void k_pair_gather(const uint64_t *__restrict__ key_in, const uint32_t *__restrict__ order, uint32_t n, uint64_t *__restrict__ key_out)
+{
+	for (uint32_t j = blockIdx.x*blockDim.x + threadIdx.x; j < n; j += gridDim.x*blockDim.x) key_out[j] = key_in[order[j]];
+}
+
+__device__ __forceinline__ bool pair_same_site(const PairArgs &a, const BoundHead &x, const BoundHead &y)
+{
+	if (x.target != y.target || x.loc5 != y.loc5 || x.loc3 != y.loc3) return false;
+	const OligoStrand &ox = pair_os(a, x.os), &oy = pair_os(a, y.os);
+	return ox.assay == oy.assay && pair_category(ox) == pair_category(oy);
+}
+
+// true: x is kept in preference to y (sort_by_bound_match, bind_oligo.cpp:49-82; equal keys: the later seed)
+__device__ __forceinline__ bool pair_better(const BoundHead &x, const BoundHead &y)
+{
+	if (x.tm != y.tm) return x.tm > y.tm;
+	if (x.num_mm != y.num_mm) return x.num_mm > y.num_mm;
+	if (x.align_len != y.align_len) return x.align_len > y.align_len;
+	return x.t > y.t;
+}
+
+__global__ void k_pair_unique(PairArgs a)
+{
+	for (uint32_t j = blockIdx.x*blockDim.x + threadIdx.x; j < a.n; j += gridDim.x*blockDim.x) {
+		const BoundHead me = a.heads[a.order[j]];
+		if (j > 0 && pair_same_site(a, me, a.heads[a.order[j - 1]])) continue; // not the first of its run
+		uint32_t best = j;
+		BoundHead bh = me;
+		uint32_t k = j + 1;
+		for (; k < a.n; ++k) {
+			const BoundHead x = a.heads[a.order[k]];
+			if (!pair_same_site(a, me, x)) break;
+			if (pair_better(x, bh)) { best = k; bh = x; }
+		}
+		for (uint32_t m = j; m < k; ++m) a.alive[m] = m == best ? 1 : 0;
+	}
+}
+
+__global__ void k_pair_join(PairArgs a)
+{
+	const bool apply_mmc = a.min_max_primer_clamp >= 0;
+	for (uint32_t fi = blockIdx.x*blockDim.x + threadIdx.x; fi < a.n; fi += gridDim.x*blockDim.x) {
+		if (!a.alive[fi]) continue;
+		const BoundHead f = a.heads[a.order[fi]];
+		const OligoStrand &of = pair_os(a, f.os);
+		if (of.plus || of.role == 2) continue;
+		const bool has_probe = a.assay_has_probe[of.assay] != 0;
+		for (uint32_t ri = fi + 1; ri < a.n; ++ri) {
+			const BoundHead r = a.heads[a.order[ri]];
+			if (r.target != f.target) break;
+			const OligoStrand &orr = pair_os(a, r.os);
+			if (orr.assay != of.assay) break;
+			if ((int64_t)r.loc5 > (int64_t)f.loc5 + a.max_len) break; // sorted by loc_5: no later site can close an amplicon
+			if (!a.alive[ri] || !orr.plus || orr.role == 2) continue;
+			if (!a.single_primer_pcr && of.role == orr.role) continue;
+			if (f.loc3 >= r.loc5) continue;
+			if (r.loc3 - f.loc5 + 1 > a.max_len) continue;
+			if (apply_mmc && max((int)f.anchor3, (int)r.anchor3) <= a.min_max_primer_clamp) continue;
+			if (!has_probe) {
+				const uint32_t slot = atomicAdd(a.pair_count, 1u);
+				if (slot < a.pair_cap) a.pairs[slot] = PairRec{(int32_t)fi, (int32_t)ri, -1};
+				continue;
+			}
+			for (uint32_t pi = fi + 1; pi < ri; ++pi) {
+				if (!a.alive[pi]) continue;
+				const BoundHead p = a.heads[a.order[pi]];
+				const OligoStrand &op = pair_os(a, p.os);
+				if (op.role != 2) continue;
+				if (!(p.loc5 >= f.loc5 && p.loc3 <= r.loc3)) continue;
+				if (op.plus == of.plus) { if (p.loc5 <= f.loc3) continue; }
+				else if (p.loc3 >= r.loc5) continue;
+				const uint32_t slot = atomicAdd(a.pair_count, 1u);
+				if (slot < a.pair_cap) a.pairs[slot] = PairRec{(int32_t)fi, (int32_t)ri, (int32_t)pi};
+			}
 		}
 	}
 }
@@ -1267,6 +1394,34 @@ __global__ void __launch_bounds__(32) k_oligo_jobs(const OligoJob *__restrict__ 
 	r.lm_q = (int16_t)best_aln.lm_q; r.lm_t = (int16_t)best_aln.lm_t;
 	r.ncols = best.valid ? best_aln.e - best_aln.b : 0;
 	out[j] = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Measured integer-ALU peak (the denominator of the NucCruc roofline): every thread runs eight
+// independent chains of one 32-bit instruction; MODE 0 = add (IADD3), 1 = max (IMNMX), 2 = the
+// add-then-max pair of the DP recurrence (VIADDMNMX where the compiler fuses it).
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_alu_peak(int iters, int seed, int *out)
+{
+	int a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const int b = seed*3 + 1, c = seed - 7;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int u = 0; u < 16; ++u) {
+			// operands come from the neighbouring chain, so that nothing folds into constants
+			if (MODE == 0) { a0 += a1; a1 += a2; a2 += a3; a3 += a4; a4 += a5; a5 += a6; a6 += a7; a7 += a0; }
+			else if (MODE == 1) {
+				a0 = max(a0, a1); a1 = min(a1, a2); a2 = max(a2, a3); a3 = min(a3, a4);
+				a4 = max(a4, a5); a5 = min(a5, a6); a6 = max(a6, a7); a7 = min(a7, a0 ^ u);
+			}
+			else {
+				a0 = max(a0 - b, c); a1 = max(a1 - c, b); a2 = max(a2 - b, c); a3 = max(a3 - c, b);
+				a4 = max(a4 - b, c); a5 = max(a5 - c, b); a6 = max(a6 - b, c); a7 = max(a7 - c, b);
+			}
+		}
+	}
+	if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x7fffffff) out[0] = a0; // keeps the chains alive
 }
 
 // Fast kernel: windows made of A/C/G/T only (the oligo may hold any code).  All units of one

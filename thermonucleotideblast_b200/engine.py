@@ -235,6 +235,7 @@ def load_library() -> C.CDLL:
     L.tnt_engine_oligo_dimer.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.POINTER(AlignResult)]
     L.tnt_engine_oligo_hairpin.argtypes = [vp, C.c_char_p, C.POINTER(AlignResult)]
     L.tnt_engine_assay_structures.argtypes = [vp, C.POINTER(SearchOptions), C.POINTER(AssayStructures)]
+    L.tnt_engine_alu_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.tnt_engine_scan_only.argtypes = [vp, C.POINTER(SearchOptions), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -534,6 +535,12 @@ class Engine:
         out = (AssayStructures * max(n_assays, 1))()
         self._check(self.L.tnt_engine_assay_structures(self.h, C.byref(opts), out))
         return [out[i] for i in range(n_assays)]
+
+    def alu_peak(self):
+        """Measured int32 throughput (TOP/s): independent adds, independent min / max, subtract-then-max pairs."""
+        t = (C.c_double * 3)()
+        self._check(self.L.tnt_engine_alu_peak(self.h, t))
+        return {"iadd": t[0], "imnmx": t[1], "sub_max_pairs": t[2]}
 
     def scan_only(self, opts: SearchOptions):
         """Seed scan of all fragments with the stage-1 oligo strands; returns (candidates, ms)."""
