@@ -109,6 +109,36 @@ def build_workload(rank: int, mbp: int, n_assays: int, pinned: bool = False, kin
     return records, fragments, assays, total
 
 
+def traffic_from_profile():
+    """DRAM bytes of one full-size search, summed per kernel family from the newest committed ncu
+    capture `profiles/dram_r*.csv` (tools/capture_profiles.sh: dram__bytes_read.sum + dram__bytes_write.sum of
+    every launch between cudaProfilerStart/Stop around exactly one warm search of the record workload).
+    Returns (nuccruc_bytes, scan_bytes, file name) or (None, None, None) when no capture is committed."""
+    import csv
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "dram_r*.csv")),
+                   key=lambda f: [int(x) for x in re.findall(r"\d+", os.path.basename(f))])
+    if not files:
+        return None, None, None
+    path = files[-1]
+    nuccruc = scan = 0.0
+    with open(path) as fh:
+        rows = csv.DictReader(line for line in fh if line.startswith('"'))
+        for row in rows:
+            if not row["Metric Name"].startswith("dram__bytes"):
+                continue
+            v = float(row["Metric Value"].replace(",", ""))
+            unit = row["Metric Unit"].lower()
+            v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            name = row["Kernel Name"]
+            if "k_align" in name:
+                nuccruc += v
+            elif "k_seed_scan" in name or "k_region_scan" in name:
+                scan += v
+    return nuccruc or None, scan or None, os.path.basename(path)
+
+
 class ClockSampler:
     """SM clock / throttle reasons during the timed region (B200_PROFILING.md) through NVML.
 
@@ -861,12 +891,12 @@ def main():
     alu_achieved = ALU_OPS_PER_CELL * st.dp_cells / align_s / 1e12 if align_s > 0 else 0.0
     scan_achieved = st.scan_bytes / scan_s / 1e9 if scan_s > 0 else 0.0
 
-    # DRAM traffic of the kernels behind the two rooflines, from one ncu capture of this very workload
-    # (profiles/dram_r01_v7.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the launches
-    # of one search); only quoted when the run is that workload
+    # DRAM traffic of the kernels behind the two rooflines: read from the committed ncu capture of one
+    # search of this very workload (never typed in); only quoted when the run is that workload
     record_cfg = args.kind == "taqman" and args.mbp == 1000 and args.assays == 100
-    nuccruc_traffic = 32.4e9 if record_cfg else None   # lean tier 25.5 GB read (window fetches), full-trace tier 1.4 GB read + 5.1 GB written (trace slabs)
-    scan_traffic = 1.29e9 if record_cfg else None      # 0.255 GB read (the scan needs the 2-bit words only) + 1.03 GB of candidates written
+    nuccruc_traffic = scan_traffic = traffic_file = None
+    if record_cfg:
+        nuccruc_traffic, scan_traffic, traffic_file = traffic_from_profile()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -890,7 +920,9 @@ def main():
                 "hit_text_bytes_per_step": int(seq_bytes)},
         "roofline": {"bound": "alu-int32", "achieved": alu_achieved, "peak": alu_peak, "unit": "TOP/s",
                      "frac": alu_achieved / alu_peak if alu_peak else None, "traffic": nuccruc_traffic,
-                     "traffic_note": "bytes per step over all NucCruc launches (ncu, profiles/dram_r01_v7.csv): ~450 GB/s, 7 % of the HBM peak -- the kernels are ALU-bound, not memory-bound",
+                     "traffic_note": "DRAM bytes of all NucCruc launches of one search, summed from the committed ncu capture profiles/%s "
+                                     "(window fetches are random 32-byte sectors; the kernels are ALU-bound, not memory-bound)" % traffic_file,
+                     "algorithmic_bytes": float(aligns / max(world, 1)) * 24.0,
                      "kernel": "k_align (NucCruc DP + traceback + evaluation)",
                      "peak_source": "measured on this GPU in this run: independent 32-bit integer adds (tnt_engine_alu_peak)"
                                     if "iadd" in alu_measured else "nominal",
@@ -899,6 +931,7 @@ def main():
                              "nominal issue peak = 148 SM x 128 lanes x %.0f MHz" % (st.dp_cells, sm_max)},
         "roofline_seed_scan": {"bound": "hbm", "achieved": scan_achieved, "peak": hbm_peak, "unit": "GB/s",
                                "frac": scan_achieved / hbm_peak if hbm_peak else None, "traffic": scan_traffic,
+                               "traffic_note": "k_seed_scan + k_region_scan launches of one search, profiles/%s" % traffic_file,
                                "kernel": "k_seed_scan", "peak_source": hbm_src,
                                "note": "0.375 B per base per pass + 8 B per emitted candidate (SURVEY 8d); with %d oligo "
                                        "strands the scan is bound by table walks and bucket atomics, not HBM" % (2 * len(assays)),

@@ -49,7 +49,8 @@ typedef struct {
 	float salt;          /* [Na+] M, default 0.05 (tntblast.h:61) */
 	int32_t dangle5;     /* default 0 (tntblast.h:72-73) */
 	int32_t dangle3;
-	int32_t dinkelbach;  /* must be 0: the iterative Tm mode is not implemented */
+	int32_t dinkelbach;  /* default 0; 1: NucCruc::dinkelbach(true), the iterative Tm of nuc_cruc.cpp:2399-2440,
+	                      * :2459-2500, :2548-2588 -- every window then runs through the generic alignment kernel */
 	int32_t word_size;   /* hash word size W, 3..8, default 7 (tntblast.h:68) */
 	int32_t device;      /* CUDA device ordinal */
 	int32_t reserved;    /* flags, TNT_ENGINE_*; 0 = behave exactly like the reference */
@@ -392,6 +393,9 @@ const char *tnt_postprocess_error(void);
 /* The integer penalty table of NucCruc::update_dp_param (nuc_cruc.cpp:340-487) and the
  * best_base_pair table (nuc_cruc.cpp:14-213) as the engine uploads them: dg[49*49], bbp[18*18]. */
 int tnt_debug_thermo(float T, float na, int32_t *dg, uint8_t *bbp);
+
+/* the delta_g table of (T, na) re-derived at T_eval from the rule table the Dinkelbach kernels use */
+int tnt_debug_thermo_at(float T, float na, float T_eval, int32_t *dg);
 
 /* Compacted seed word list of an oligo (DNAHash_iterator::build_word_list, seq_hash.h:287-374);
  * returns the number of words written (at most TNT_MAX_OLIGO_LEN). */

@@ -146,6 +146,9 @@ extern "C" long ref_seeds_unique(const uint8_t *codes, uint32_t len, int word_si
 // ---------------------------------------------------------------------------
 // One NucCruc per thread, rebuilt when (T, [Na+]) changes (the 15 MB dp_matrix makes
 // per-call construction far too slow for million-window differential runs).
+static thread_local bool g_dinkelbach = false;
+extern "C" void ref_set_dinkelbach(int on) { g_dinkelbach = on != 0; }
+
 static NucCruc *get_melt(float T, float na)
 {
 	static thread_local NucCruc *melt = NULL;
@@ -154,9 +157,9 @@ static NucCruc *get_melt(float T, float na)
 	if (!melt) {
 		melt = new NucCruc(NucCruc::SANTA_LUCIA, T);
 		melt->Salt(na);
-		melt->dinkelbach(false);
 		cur_T = T; cur_na = na;
 	}
+	melt->dinkelbach(g_dinkelbach);
 	return melt;
 }
 
@@ -320,7 +323,7 @@ extern "C" long ref_search(const uint8_t *codes, uint32_t len, const char *forwa
 	NucCruc melt(NucCruc::SANTA_LUCIA, o->target_T);
 	melt.Salt(o->salt);
 	melt.dangle(o->dangle5 != 0, o->dangle3 != 0);
-	melt.dinkelbach(false);
+	melt.dinkelbach(g_dinkelbach);
 
 	std::unordered_map<BindCacheKey, BindCacheValue> plus_cache, minus_cache;
 	std::unordered_map<std::string, size_t> str_table;

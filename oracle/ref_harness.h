@@ -78,6 +78,8 @@ typedef struct {
 } ref_hit;
 
 const char *ref_last_error(void);
+/* melt.dinkelbach(on) (nuc_cruc.h:763-766, tntblast_local.cpp:367) for every later call of this thread (default off) */
+void ref_set_dinkelbach(int on);
 int ref_dump_tables(float T, float na, ref_tables *out);
 long ref_seeds_raw(const uint8_t *codes, uint32_t len, int word_size, const char *oligo,
 	int complement, uint32_t *q_out, uint32_t *t_out, long cap);

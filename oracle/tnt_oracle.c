@@ -716,17 +716,49 @@ static int enumerate_alignments(nc_t *nc, int max_cell)
 	return 0;
 }
 
-/* approximate_tm_heterodimer without Dinkelbach (nuc_cruc.cpp:2441-2454) + tm_dimer (:2517-2540) */
+/* NucCruc::dinkelbach(bool) (nuc_cruc.h:763-766): per-thread switch of this library, like the one of the harness */
+static __thread int g_dinkelbach;
+void orc_set_dinkelbach(int on) { g_dinkelbach = on ? 1 : 0; }
+
+/* approximate_tm_heterodimer / _homodimer (nuc_cruc.cpp:2397-2516) + tm_dimer (:2517-2540).
+ * With use_dinkelbach (:2399-2440): align at 0 degC, then at the melting temperature of the previous
+ * pass, while delta_G() of the pass -- dH - target_T*dS at the temperature it was aligned at -- is
+ * negative and still rising; temperature() re-derives the penalty table every time (nuc_cruc.h:1232-1242).
+ * The alignment of the last pass stays; the initial temperature is restored at the end. */
 static int nc_run(nc_t *nc, float *dp_dg)
 {
-	aln_clear(&nc->best);
-	nc->oob = 0;
 	++g_align_count;
-	const int32_t max_score = align_dimer(nc);
-	for (int k = 0; k < nc->n_max; ++k)
-		if (enumerate_alignments(nc, nc->max_cells[k]) < 0) return -1;
+	nc->oob = 0;
+	if (!g_dinkelbach) {
+		aln_clear(&nc->best);
+		const int32_t max_score = align_dimer(nc);
+		for (int k = 0; k < nc->n_max; ++k)
+			if (enumerate_alignments(nc, nc->max_cells[k]) < 0) return -1;
+		if (dp_dg) *dp_dg = -((float)max_score/10000.0f);
+		return 0;
+	}
+	const thermo_t *keep = nc->th;
+	thermo_t *th = (thermo_t *)malloc(sizeof(thermo_t));
+	float q = -999999.9f, last_q, local_tm;
+	int32_t max_score = 0;
+	int rc = 0;
+	thermo_init(th, 273.15f, keep->na);
+	nc->th = th;
+	do {
+		aln_clear(&nc->best);
+		max_score = align_dimer(nc);
+		for (int k = 0; k < nc->n_max && rc == 0; ++k)
+			if (enumerate_alignments(nc, nc->max_cells[k]) < 0) rc = -1;
+		if (rc < 0) break;
+		local_tm = nc->best.tm;
+		last_q = q;
+		q = nc->best.dH - th->T*nc->best.dS;
+		thermo_init(th, 273.15f + local_tm, keep->na);
+	} while (q < 0.0 && q > last_q);
+	nc->th = keep;
+	free(th);
 	if (dp_dg) *dp_dg = -((float)max_score/10000.0f);
-	return 0;
+	return rc;
 }
 
 /* anchor5_query / anchor3_query (nuc_cruc_anchor.cpp:143-192, :249-298) */
@@ -1034,7 +1066,7 @@ static int enumerate_hairpin(nc_t *nc, int max_cell)
 	return 0;
 }
 
-/* approximate_tm_hairpin without Dinkelbach (nuc_cruc.cpp:2590-2610) */
+/* approximate_tm_hairpin (nuc_cruc.cpp:2542-2618) */
 int orc_hairpin(const char *query, float T, float na, ref_align_out *out)
 {
 	nc_t *nc = get_nc(T, na);
@@ -1044,13 +1076,40 @@ int orc_hairpin(const char *query, float T, float na, ref_align_out *out)
 	nc->dangle5 = nc->dangle3 = 0;
 	nc->homo = 0;
 	const int max_stem_len = nc->Lq - 4; /* steric limit: 3 loop bases + 1 anchor (:781-790) */
-	nc->tri = max_stem_len > 0 ? max_stem_len : -1;
-	aln_clear(&nc->best);
 	nc->oob = 0;
-	const int32_t max_score = align_dimer(nc);
-	nc->tri = 0;
-	for (int k = 0; k < nc->n_max; ++k)
-		if (enumerate_hairpin(nc, nc->max_cells[k]) < 0) return -1;
+	int32_t max_score = 0;
+	if (!g_dinkelbach) {
+		nc->tri = max_stem_len > 0 ? max_stem_len : -1;
+		aln_clear(&nc->best);
+		max_score = align_dimer(nc);
+		nc->tri = 0;
+		for (int k = 0; k < nc->n_max; ++k)
+			if (enumerate_hairpin(nc, nc->max_cells[k]) < 0) return -1;
+	}
+	else {
+		/* the Dinkelbach iteration of approximate_tm_hairpin (nuc_cruc.cpp:2548-2588), like nc_run */
+		const thermo_t *keep = nc->th;
+		thermo_t *th = (thermo_t *)malloc(sizeof(thermo_t));
+		float q = -999999.9f, last_q;
+		int rc = 0;
+		thermo_init(th, 273.15f, keep->na);
+		nc->th = th;
+		do {
+			nc->tri = max_stem_len > 0 ? max_stem_len : -1;
+			aln_clear(&nc->best);
+			max_score = align_dimer(nc);
+			nc->tri = 0;
+			for (int k = 0; k < nc->n_max && rc == 0; ++k)
+				if (enumerate_hairpin(nc, nc->max_cells[k]) < 0) rc = -1;
+			if (rc < 0) break;
+			last_q = q;
+			q = nc->best.dH - th->T*nc->best.dS;
+			thermo_init(th, 273.15f + nc->best.tm, keep->na);
+		} while (q < 0.0 && q > last_q);
+		nc->th = keep;
+		free(th);
+		if (rc < 0) return -1;
+	}
 	memset(out, 0, sizeof(*out));
 	const aln_t *a = &nc->best;
 	out->tm = a->tm;

@@ -13,6 +13,8 @@ extern "C" {
 #endif
 
 const char *orc_last_error(void);
+/* NucCruc::dinkelbach(bool) for every later call of this thread (default off) */
+void orc_set_dinkelbach(int on);
 int orc_dump_tables(float T, float na, ref_tables *out);
 long orc_seeds_raw(const uint8_t *codes, uint32_t len, int word_size, const char *oligo,
 	int complement, uint32_t *q_out, uint32_t *t_out, long cap);

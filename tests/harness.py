@@ -204,6 +204,7 @@ class _Lib:
             return f
 
         self._last_error = fn("last_error", C.c_char_p, [])
+        self._set_dinkelbach = fn("set_dinkelbach", None, [C.c_int])
         self._dump_tables = fn("dump_tables", C.c_int, [C.c_float, C.c_float, C.POINTER(Tables)])
         self._seeds_raw = fn("seeds_raw", C.c_long, [u8p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, u32p, u32p, C.c_long])
         self._seeds_unique = fn("seeds_unique", C.c_long, [u8p, C.c_uint32, C.c_int, C.c_char_p, C.c_int, u32p, u32p, C.c_long])
@@ -225,6 +226,10 @@ class _Lib:
             self._fasta_read_file = fn("fasta_read", C.c_long, [C.c_long, C.c_uint32, C.c_uint32, C.c_int, u8p, C.c_long,
                                                               C.c_char_p, C.c_long])
             self._fasta_close = fn("fasta_close", None, [])
+
+    def set_dinkelbach(self, on: bool) -> None:
+        """NucCruc::dinkelbach(on) for every later call of this thread (nuc_cruc.h:763-766)."""
+        self._set_dinkelbach(1 if on else 0)
 
     def _check(self, rc):
         if rc < 0:

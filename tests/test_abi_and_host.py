@@ -59,6 +59,19 @@ def test_host_thermo_table_matches_oracle(engine_lib, oracle):
     assert engine_lib.tnt_debug_thermo(310.15, 2.0, None, None) < 0
 
 
+def test_dinkelbach_rule_table_matches_oracle(engine_lib, oracle):
+    """The Dinkelbach kernels re-derive delta_g entry by entry at the temperature of each iteration
+    (Thermo::dg_class + the T-independent inputs): the rule table of an engine built at T, evaluated at
+    any other temperature, must equal update_dp_param at that temperature."""
+    engine_lib.tnt_debug_thermo_at.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int32)]
+    rng = np.random.default_rng(12)
+    for na in (0.05, 0.2, 1.0):
+        for T_eval in [273.15, 310.15, 355.0] + [float(np.float32(273.15 + x)) for x in rng.uniform(0.0, 95.0, size=12)]:
+            dg = (C.c_int32 * 2401)()
+            assert engine_lib.tnt_debug_thermo_at(310.15, na, T_eval, dg) == 0
+            assert list(dg) == list(oracle.dump_tables(T_eval, na).delta_g), (na, T_eval)
+
+
 def test_host_word_lists_match_oracle_seeds(engine_lib, oracle):
     """The compacted word list (incl. the inosine offset quirk) reproduces the
     oracle's raw seed enumeration on a fragment that contains every word once."""

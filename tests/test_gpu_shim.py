@@ -104,6 +104,19 @@ def test_config1_direct_calls(tmp_path):
     assert info["prefetched"] == 0 and info["direct"] > 0 and a.count(b"name = ") >= 2
 
 
+def test_dinkelbach_flag(tmp_path):
+    """`--dinkelbach T` (options.cpp:222-224 -> melt.dinkelbach, tntblast_local.cpp:367): the shim hands the
+    flag to tnt_engine_create and the iterative Tm of every window comes from the device."""
+    rng = np.random.default_rng(77)
+    records = [gen.random_codes(1_000_000, rng)]
+    assays = gen.make_assays(np.random.default_rng(5), records, 4, "taqman", variants=4)
+    a, b, info, _ = run_pair(tmp_path, records, assays, ["-e", "40", "-E", "45", "--dinkelbach", "T"])
+    check_identical(a, b, info, 4)
+    # and the flag changes the output (it is not silently ignored by either program)
+    c, d, _, _ = run_pair(tmp_path, records, assays, ["-e", "40", "-E", "45"])
+    assert c == d and c != a
+
+
 def test_config2_taqman_slice(tmp_path):
     """BASELINE configs[1]: 100 TaqMan triplets, -e 45 -E 50, leading 50 Mbp of the 1 Gbp database."""
     n = scale(50)

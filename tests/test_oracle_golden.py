@@ -234,3 +234,92 @@ def test_hairpins_against_the_compiled_reference(oracle, ref):
             assert (a.q_first, a.t_first, a.q_last, a.t_last, a.num_gap) == (b.q_first, b.t_first, b.q_last, b.t_last, b.num_gap), q
             n += 1
     assert n > 800
+
+
+@pytest.fixture
+def dinkelbach_oracle(oracle):
+    oracle.set_dinkelbach(True)
+    yield oracle
+    oracle.set_dinkelbach(False)
+
+
+def _load_make_dinkelbach():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_dinkelbach", os.path.join(GOLD, "make_dinkelbach.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    return mk
+
+
+def test_dinkelbach_golden(dinkelbach_oracle):
+    """NucCruc::dinkelbach(true) (nuc_cruc.cpp:2399-2440, :2459-2500, :2548-2588): the iterative Tm of single
+    windows, oligo dimers, hairpins and whole searches against vectors made from the compiled reference
+    (tests/golden/make_dinkelbach.py), floats bit for bit."""
+    oracle = dinkelbach_oracle
+    mk = _load_make_dinkelbach()
+    gold = load("dinkelbach.json")
+    assert len(gold["windows"]) >= 400 and sum(r["out"]["valid"] for r in gold["windows"]) > 300
+    for r in gold["windows"]:
+        tb = np.array([NB[c] for c in r["t"]], dtype=np.uint8)
+        assert mk.align_rec(oracle.align(r["q"], tb, T=r["T"], na=r["na"], ct=r["ct"])) == r["out"], (r["q"], r["t"])
+    for r in gold["dimers"]:
+        assert mk.struct_rec(oracle.dimer(r["q"], r["t"])) == r["out"], (r["q"], r["t"])
+    for r in gold["hairpins"]:
+        assert mk.struct_rec(oracle.hairpin(r["q"])) == r["out"], r["q"]
+    cases = {(kind, t, i): (db[t], assays[i]) for kind, db, assays in mk.search_cases() for t in range(len(db)) for i in range(len(assays))}
+    nhits = 0
+    for s in gold["searches"]:
+        codes, a = cases[(s["kind"], s["target"], s["assay"])]
+        hits = oracle.search(codes, a[0], a[1], a[2], mk.search_options_for(s["kind"]))
+        assert [mk.hit_rec(h) for h in hits] == s["hits"], (s["kind"], s["target"], s["assay"])
+        nhits += len(hits)
+    assert nhits > 20
+
+
+def test_dinkelbach_changes_the_answer(oracle):
+    """The mode is not a no-op: a fifth of partially matching windows change their record."""
+    rng = np.random.default_rng(7)
+    changed = 0
+    for it in range(300):
+        q = gen.rand_oligo(int(rng.integers(16, 30)), rng)
+        t = H.encode(gen.rand_oligo(4, rng) + gen.mutate(gen.revcomp(q), int(rng.integers(0, 5)), rng, indel=False) + gen.rand_oligo(4, rng))
+        oracle.set_dinkelbach(False)
+        a = oracle.align(q, t).key()
+        oracle.set_dinkelbach(True)
+        b = oracle.align(q, t).key()
+        oracle.set_dinkelbach(False)
+        changed += a != b
+    assert 20 < changed < 300
+
+
+def test_dinkelbach_vs_compiled_reference(dinkelbach_oracle, ref):
+    oracle = dinkelbach_oracle
+    ref.set_dinkelbach(True)
+    try:
+        rng = np.random.default_rng(4242)
+        for it in range(4000):
+            L = int(rng.integers(10, 45))
+            q = gen.rand_oligo(L, rng)
+            t = gen.rand_oligo(4, rng) + gen.mutate(gen.revcomp(q), int(rng.integers(0, 6)), rng) + gen.rand_oligo(4, rng)
+            if it % 4 == 0:
+                t = gen.rand_oligo(L + 8, rng)
+            T, na = [(310.15, 0.05), (285.0, 0.5), (340.0, 0.02)][it % 3]
+            tb = H.encode(t)
+            a, b = ref.align(q, tb, T=T, na=na), oracle.align(q, tb, T=T, na=na)
+            assert a.key() == b.key() and (a.valid, a.tm, a.dH, a.dS, a.dG) == (b.valid, b.tm, b.dH, b.dS, b.dG), (q, t)
+            if it % 8 == 0:
+                for x, y in ((ref.hairpin(q, T, na), oracle.hairpin(q, T, na)), (ref.dimer(q, None, T, na), oracle.dimer(q, None, T, na))):
+                    assert (x.valid, x.tm, x.dH, x.dS) == (y.valid, y.tm, y.dH, y.dS), q
+        for kind in ("pcr", "taqman", "probe", "padlock"):
+            db = [gen.random_codes(15000, rng) for _ in range(2)]
+            assays = gen.make_assays(rng, db, 3, kind, variants=3)
+            o = _load_make_dinkelbach().search_options_for(kind)
+            n = 0
+            for codes in db:
+                for a in assays:
+                    x, y = ref.search(codes, a[0], a[1], a[2], o), oracle.search(codes, a[0], a[1], a[2], o)
+                    assert [(h.exact_key(), h.floats()) for h in x] == [(h.exact_key(), h.floats()) for h in y], kind
+                    n += len(x)
+            assert n >= 3, kind
+    finally:
+        ref.set_dinkelbach(False)

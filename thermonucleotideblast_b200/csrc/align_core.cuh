@@ -80,6 +80,47 @@ struct DpShared {
 	const uint8_t *wc;   // [NPAIR]
 	const uint8_t *q;    // oligo, 5'->3'
 	int Lq;
+	float T;             // target_T: ranks co-optimal alignments by dH - T*dS (the engine's temperature, or the
+	                     // temperature of the current Dinkelbach iteration)
+};
+
+// delta_g table as the fill reads it: a resident table ...
+struct DgTable {
+	const int32_t *__restrict__ p;
+	__device__ __forceinline__ int operator[](int i) const { return p[i]; }
+};
+
+// ... or update_dp_param (nuc_cruc.cpp:340-487) evaluated entry by entry at a temperature of the
+// thread's own: the Dinkelbach iteration (nuc_cruc.cpp:2399-2440) re-derives the table at the Tm of
+// the previous pass.  Same binary32 operations as the host (thermo.cpp; no FMA contraction).
+struct DgAtT {
+	const float *__restrict__ H;
+	const float *__restrict__ S;
+	const uint8_t *__restrict__ cls;
+	float T, sc;
+	int32_t pen[7];
+	static __device__ __forceinline__ int32_t scaled(float x) { return __float2int_rz(__fmul_rn(x, 10000.0f)); }
+	__device__ void set(const Thermo *__restrict__ th, float temperature)
+	{
+		H = th->H; S = th->S; cls = th->dg_class;
+		T = temperature;
+		sc = th->salt_correction;
+		pen[0] = 0;
+#define TNT_PEN(k, h, s, c) do { const int32_t v = scaled(__fsub_rn(th->supp[h], __fmul_rn(T, __fadd_rn(th->supp[s], th->supp_sc[c])))); pen[k] = v > 0 ? v : 0; } while (0)
+		TNT_PEN(DG_LOOP, 0, 1, 0);
+		TNT_PEN(DG_BULGE, 2, 3, 1);
+		TNT_PEN(DG_TERM_AT, 4, 5, 2);
+		TNT_PEN(DG_TERM_GC, 6, 7, 2);
+		TNT_PEN(DG_TERM_INO, 8, 9, 2);
+		TNT_PEN(DG_TERM_MM, 10, 11, 3);
+#undef TNT_PEN
+	}
+	__device__ __forceinline__ int operator[](int i) const
+	{
+		const unsigned c = __ldg(cls + i);
+		if (c) return pen[c];
+		return scaled(__fsub_rn(__ldg(H + i), __fmul_rn(T, __fadd_rn(__ldg(S + i), sc))));
+	}
 };
 
 struct DpResult {
@@ -96,11 +137,10 @@ struct DpResult {
 // over the triangle i + j <= tri + 1 only (tri = the longest stem the steric limit allows); cells
 // inside the triangle depend on cells inside it alone.  The caller clears the trace beforehand
 // (cells outside the triangle are never written).
-template <int NT>
-__device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *tgt, int Lt,
+template <int NT, class DG>
+__device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const DG &dg, const uint8_t *tgt, int Lt,
 	int32_t *rowM, int32_t *rowIq, int32_t *rowIt, uint16_t *trace, int tri = 0)
 {
-	const int32_t *__restrict__ dg = sh.dg;
 	const uint8_t *__restrict__ bbp = sh.bbp;
 	const int Lq = sh.Lq;
 
@@ -189,6 +229,13 @@ __device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *t
 		}
 	}
 	return res;
+}
+
+template <int NT>
+__device__ __forceinline__ DpResult nc_fill(const DpShared &sh, const uint8_t *tgt, int Lt,
+	int32_t *rowM, int32_t *rowIq, int32_t *rowIt, uint16_t *trace, int tri = 0)
+{
+	return nc_fill<NT, DgTable>(sh, DgTable{sh.dg}, tgt, Lt, rowM, rowIq, rowIt, trace, tri);
 }
 
 // Read access to the stored trace of one alignment.  get(i, j) returns the trace word of DP cell
@@ -523,7 +570,7 @@ __device__ void nc_enumerate(const DpShared &sh, const Thermo *__restrict__ th, 
 	const TG &tgt, int Lt, const TV &tv, const uint16_t *cells, int ncells,
 	AlnState &work, AlnState &best_aln, Best &best, unsigned &flags, bool fresh = true)
 {
-	const float T = th->T;
+	const float T = sh.T;
 	if (fresh) {
 		best.valid = false;
 		best.dH = best.dS = best.tm = 0.0f;
@@ -636,9 +683,9 @@ __device__ inline bool nc_evaluate_hairpin(const DpShared &sh, const Thermo *__r
 	return nc_evaluate(sh, th, 0.0f, a, true);
 }
 
-__device__ __forceinline__ void nc_hairpin_keep(const Thermo *__restrict__ th, const AlnState &a, AlnState &best_aln, Best &best, float &best_dg)
+__device__ __forceinline__ void nc_hairpin_keep(const DpShared &sh, const AlnState &a, AlnState &best_aln, Best &best, float &best_dg)
 {
-	const float local_dg = TNT_SUB(a.dH, TNT_MUL(th->T, a.dS));
+	const float local_dg = TNT_SUB(a.dH, TNT_MUL(sh.T, a.dS));
 	if (!best.valid || local_dg < best_dg) {
 		best.valid = true;
 		best.dH = a.dH; best.dS = a.dS; best.tm = a.tm;
@@ -665,7 +712,7 @@ __device__ void nc_enumerate_hairpin(const DpShared &sh, const Thermo *__restric
 		bool first_time = true;
 		int nstack = 0, zero_count = -1;
 		unsigned trace_count = 0;
-		float best_dg = TNT_SUB(best.dH, TNT_MUL(th->T, best.dS));
+		float best_dg = TNT_SUB(best.dH, TNT_MUL(sh.T, best.dS));
 		for (;;) {
 			if (!first_time && nstack == 0 && zero_count <= 0) break;
 			if (16u < trace_count) break;
@@ -689,7 +736,7 @@ __device__ void nc_enumerate_hairpin(const DpShared &sh, const Thermo *__restric
 				zero_count = -1;
 			}
 			// the stem as it is (:1265-1286)
-			if (a.e - a.b >= 3 && nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(th, a, best_aln, best, best_dg);
+			if (a.e - a.b >= 3 && nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(sh, a, best_aln, best, best_dg);
 			if (flags & F_OOB) return;
 			// one more column at the open end: the next bases or a dangling-end virtual base (:1307-1326)
 			if (a.lm_t != 0 || a.lm_q != Lq - 1) {
@@ -703,7 +750,7 @@ __device__ void nc_enumerate_hairpin(const DpShared &sh, const Thermo *__restric
 			}
 			const int align_size = a.e - a.b;
 			if (align_size < 3) continue;
-			if (nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(th, a, best_aln, best, best_dg);
+			if (nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(sh, a, best_aln, best, best_dg);
 			if (flags & F_OOB) return;
 			// without the closing pair, unless it is G-C / C-G (:1360-1406)
 			if (align_size <= 3) continue;
@@ -713,7 +760,7 @@ __device__ void nc_enumerate_hairpin(const DpShared &sh, const Thermo *__restric
 			++a.fm_q;
 			--a.fm_t;
 			++a.b;
-			if (nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(th, a, best_aln, best, best_dg);
+			if (nc_evaluate_hairpin(sh, th, a, flags)) nc_hairpin_keep(sh, a, best_aln, best, best_dg);
 			if (flags & F_OOB) return;
 		}
 	}

@@ -927,6 +927,8 @@ void finish_set(tnt_engine *e, OsSet &set)
 			bound += best;
 		}
 		if (bound >= (1 << 20)) set.fast_ok[s] = 0;
+		// Dinkelbach mode: every window iterates at temperatures of its own -> generic kernel only
+		if (e->h_thermo.dinkelbach) set.fast_ok[s] = 0;
 	}
 	set.d_row_tab.upload(set.row_tab, e->stream);
 	set.d_lean_tab.upload(set.lean_tab, e->stream);
@@ -2566,7 +2568,6 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 {
 	API_BEGIN
 	if (!p || !out) throw std::runtime_error("null argument");
-	if (p->dinkelbach) throw std::runtime_error("the Dinkelbach Tm mode is not implemented in the B200 engine");
 	if (p->word_size < 3 || p->word_size > 8) throw std::runtime_error(":DNAHash: Unsupported word length");
 	int ndev = 0;
 	cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -2601,6 +2602,7 @@ int tnt_engine_create(const tnt_engine_params *p, tnt_engine **out)
 	CUDA_OK(cudaMallocHost(&e->h_total, MAX_SLOTS*sizeof(uint64_t)));
 	CUDA_OK(cudaMalloc(&e->d_total, MAX_SLOTS*sizeof(uint64_t)));
 	build_thermo(e->h_thermo, p->target_T, p->salt, p->dangle5 != 0, p->dangle3 != 0);
+	e->h_thermo.dinkelbach = p->dinkelbach ? 1 : 0;
 	e->d_thermo.reserve(1, 0, e->stream);
 	CUDA_OK(cudaMemcpyAsync(e->d_thermo.p, &e->h_thermo, sizeof(Thermo), cudaMemcpyHostToDevice, e->stream));
 	e->d_out_count.reserve(16, 0, e->stream);
@@ -3128,6 +3130,16 @@ int tnt_debug_thermo(float T, float na, int32_t *dg, uint8_t *bbp)
 	build_thermo(*th, T, na, false, false);
 	if (dg) std::memcpy(dg, th->dg, sizeof(th->dg));
 	if (bbp) std::memcpy(bbp, th->bbp, sizeof(th->bbp));
+	API_END
+}
+
+int tnt_debug_thermo_at(float T, float na, float T_eval, int32_t *dg)
+{
+	API_BEGIN
+	if (!dg) throw std::runtime_error("null argument");
+	std::unique_ptr<Thermo> th(new Thermo);
+	build_thermo(*th, T, na, false, false);
+	dg_at_temperature(*th, T_eval, dg);
 	API_END
 }
 

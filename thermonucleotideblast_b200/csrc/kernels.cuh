@@ -1244,6 +1244,8 @@ __global__ void k_gather_recs(const BoundRec *__restrict__ src, const uint32_t *
 	}
 }
 
+constexpr int DINKELBACH_MAX_ITER = 256; // the reference loop has no bound; q rises strictly, a handful of passes in practice
+
 // Generic kernel: any IUPAC / inosine content, DP rows in shared memory.
 __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 {
@@ -1275,7 +1277,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 		if ((uint32_t)tid >= unit.count) continue;
 
 		DpShared sh;
-		sh.dg = s_dg; sh.bbp = s_bbp; sh.wc = s_wc; sh.q = s_q; sh.Lq = os.len;
+		sh.dg = s_dg; sh.bbp = s_bbp; sh.wc = s_wc; sh.q = s_q; sh.Lq = os.len; sh.T = a.thermo->T;
 
 		const Candidate c = a.cand[(size_t)unit.os*a.cap + unit.begin + tid];
 		const uint32_t target = c.target_k & 0xffffffu, k = c.target_k >> 24;
@@ -1305,7 +1307,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 		best_aln.b = best_aln.e = 2;
 		best_aln.fm_q = best_aln.fm_t = best_aln.lm_q = best_aln.lm_t = 0;
 
-		if (Lt > 0) {
+		if (Lt > 0 && !a.thermo->dinkelbach) {
 			const DpResult dp = nc_fill<ALIGN_THREADS>(sh, tgt, Lt, rowM, rowIq, rowIt, trace);
 			RowMajorTrace<ALIGN_THREADS> tv;
 			tv.trace = trace;
@@ -1318,6 +1320,38 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 				nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
 				fresh = false;
 			} while (remaining > 0 && !(flags & (F_OOB | F_STACK)));
+		}
+		else if (Lt > 0) {
+			// approximate_tm_heterodimer with use_dinkelbach (nuc_cruc.cpp:2399-2440): align at 0 degC, then
+			// again and again at the melting temperature of the previous pass while dH - T*dS of the
+			// pass (taken at the temperature it was aligned at) is negative and still rising.  The
+			// record keeps the alignment of the last pass; dG is taken at the engine's temperature.
+			DgAtT dgt;
+			float T = 273.15f, q = -999999.9f, last_q;
+			int iter = 0;
+			do {
+				dgt.set(a.thermo, T);
+				sh.T = T;
+				const DpResult dp = nc_fill<ALIGN_THREADS, DgAtT>(sh, dgt, tgt, Lt, rowM, rowIq, rowIt, trace);
+				RowMajorTrace<ALIGN_THREADS> tv;
+				tv.trace = trace;
+				tv.Lt = Lt;
+				uint16_t cells[MAX_MAXCELLS];
+				int cursor = dp.last_raise < 0 ? 0 : dp.last_raise, remaining = dp.nmax;
+				bool fresh = true;
+				do {
+					const int ncells = collect_max_cells<ALIGN_THREADS>(tv, os.len, Lt, cursor, remaining, cells);
+					nc_enumerate(sh, a.thermo, os.r_log_ct, tgt, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
+					fresh = false;
+				} while (remaining > 0 && !(flags & (F_OOB | F_STACK)));
+				if (flags & (F_OOB | F_STACK)) break;
+				if (fresh) { best.valid = false; best.dH = best.dS = best.tm = 0.0f; }
+				last_q = q;
+				q = __fsub_rn(best.dH, __fmul_rn(T, best.dS));
+				T = __fadd_rn(273.15f, best.tm);
+				if (++iter >= DINKELBACH_MAX_ITER) { flags |= F_STACK; break; } // q rises strictly: never expected
+			} while (q < 0.0f && q > last_q);
+			sh.T = a.thermo->T;
 		}
 		const uint32_t idx = unit.begin + tid;
 		finish_alignment(a, sh, os, unit.os, target, k, c.t, start, stop, tgt, Lt, best, best_aln, flags,
@@ -1357,7 +1391,7 @@ __global__ void __launch_bounds__(32) k_oligo_jobs(const OligoJob *__restrict__ 
 	// homodimers carry the symmetry entropy in the initiation term (nuc_cruc.cpp:1632): own table copy
 	const Thermo *th = job.kind == JOB_HOMODIMER ? thermo_homo : thermo;
 	DpShared sh;
-	sh.dg = th->dg; sh.bbp = th->bbp; sh.wc = th->wc; sh.q = job.q; sh.Lq = job.qlen;
+	sh.dg = th->dg; sh.bbp = th->bbp; sh.wc = th->wc; sh.q = job.q; sh.Lq = job.qlen; sh.T = th->T;
 	const int Lt = job.tlen;
 	uint16_t *trace = trace_all + (size_t)j*JOB_TRACE_CELLS;
 	int32_t rowM[MAX_WINDOW + 1], rowIq[MAX_WINDOW + 1], rowIt[MAX_WINDOW + 1];
@@ -1371,20 +1405,40 @@ __global__ void __launch_bounds__(32) k_oligo_jobs(const OligoJob *__restrict__ 
 	const bool hairpin = job.kind == JOB_HAIRPIN;
 	const int tri = hairpin ? job.qlen - 4 : 0; // steric limit: three loop bases + one anchor (nuc_cruc.cpp:781-790)
 	if (Lt > 0 && job.qlen > 0 && !(hairpin && tri <= 0)) {
-		for (int c = 0; c < job.qlen*Lt; ++c) trace[c] = 0;
-		const DpResult dp = nc_fill<1>(sh, job.t, Lt, rowM, rowIq, rowIt, trace, tri);
-		RowMajorTrace<1> tv;
-		tv.trace = trace;
-		tv.Lt = Lt;
-		uint16_t cells[MAX_MAXCELLS];
-		int cursor = dp.last_raise < 0 ? 0 : dp.last_raise, remaining = dp.nmax;
-		bool fresh = true;
+		// with use_dinkelbach the three structure temperatures iterate like the heterodimer of a window
+		// (nuc_cruc.cpp:2399-2440, :2459-2500, :2548-2588)
+		const bool dink = th->dinkelbach != 0;
+		DgAtT dgt;
+		float T = dink ? 273.15f : th->T, q = -999999.9f, last_q;
+		int iter = 0;
 		do {
-			const int ncells = collect_max_cells<1>(tv, job.qlen, Lt, cursor, remaining, cells);
-			if (hairpin) nc_enumerate_hairpin(sh, th, job.t, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
-			else nc_enumerate(sh, th, job.r_log_ct, job.t, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
-			fresh = false;
-		} while (remaining > 0 && !(flags & (F_OOB | F_STACK)));
+			for (int c = 0; c < job.qlen*Lt; ++c) trace[c] = 0;
+			DpResult dp;
+			if (dink) {
+				dgt.set(th, T);
+				sh.T = T;
+				dp = nc_fill<1, DgAtT>(sh, dgt, job.t, Lt, rowM, rowIq, rowIt, trace, tri);
+			}
+			else dp = nc_fill<1>(sh, job.t, Lt, rowM, rowIq, rowIt, trace, tri);
+			RowMajorTrace<1> tv;
+			tv.trace = trace;
+			tv.Lt = Lt;
+			uint16_t cells[MAX_MAXCELLS];
+			int cursor = dp.last_raise < 0 ? 0 : dp.last_raise, remaining = dp.nmax;
+			bool fresh = true;
+			do {
+				const int ncells = collect_max_cells<1>(tv, job.qlen, Lt, cursor, remaining, cells);
+				if (hairpin) nc_enumerate_hairpin(sh, th, job.t, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
+				else nc_enumerate(sh, th, job.r_log_ct, job.t, Lt, tv, cells, ncells, work, best_aln, best, flags, fresh);
+				fresh = false;
+			} while (remaining > 0 && !(flags & (F_OOB | F_STACK)));
+			if (!dink || (flags & (F_OOB | F_STACK))) break;
+			if (fresh) { best.valid = false; best.dH = best.dS = best.tm = 0.0f; }
+			last_q = q;
+			q = __fsub_rn(best.dH, __fmul_rn(T, best.dS));
+			T = __fadd_rn(273.15f, best.tm);
+			if (++iter >= DINKELBACH_MAX_ITER) { flags |= F_STACK; break; }
+		} while (q < 0.0f && q > last_q);
 	}
 	OligoJobResult r;
 	r.tm = best.tm; r.dH = best.dH; r.dS = best.dS;
@@ -1489,7 +1543,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 		if ((uint32_t)tid >= unit.count) continue;
 
 		DpShared sh;
-		sh.dg = nullptr; sh.bbp = s_bbp; sh.wc = s_wc; sh.q = s_q; sh.Lq = os.len;
+		sh.dg = nullptr; sh.bbp = s_bbp; sh.wc = s_wc; sh.q = s_q; sh.Lq = os.len; sh.T = a.thermo->T;
 
 		const uint32_t idx = unit.begin + tid;
 		const Candidate c = a.cand[(size_t)unit.os*a.cap + idx];

@@ -136,6 +136,9 @@ void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3)
 
 	const float salt_correction = SL_SALT*th.log_na;
 	for (int i = 0; i < TABLE; ++i) th.dg[i] = scaled(SL_PARAM_H[i] - T*(SL_PARAM_S[i] + salt_correction));
+	th.salt_correction = salt_correction;
+	std::memcpy(th.supp, SL_SUPP, sizeof(th.supp));
+	for (int k = 0; k < 4; ++k) th.supp_sc[k] = salt_correction*SL_SUPP_SALT[k];
 
 	// Supplementary terms (nuc_cruc.cpp:271-300, :379-486): pairs next to a gap, double
 	// mismatches and gap extension; never favourable.
@@ -154,26 +157,50 @@ void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3)
 		for (int y = bA; y <= bI; ++y) {
 			const int cur = pair_of(x, y);
 			int32_t next_to_gap = pen_mm;
+			uint8_t cls = DG_TERM_MM;
 			if (th.wc[cur]) {
 				const bool at = (cur == pair_of(bA, bT)) || (cur == pair_of(bT, bA));
 				const bool gc = (cur == pair_of(bG, bC)) || (cur == pair_of(bC, bG));
 				next_to_gap = at ? pen_at : (gc ? pen_gc : pen_ino);
+				cls = at ? DG_TERM_AT : (gc ? DG_TERM_GC : DG_TERM_INO);
 			}
 			for (int k = bA; k <= bI; ++k) {
 				const int g1 = pair_of(k, bGAP), g2 = pair_of(bGAP, k);
 				th.dg[sidx(cur, g1)] = th.dg[sidx(g1, cur)] = next_to_gap;
 				th.dg[sidx(cur, g2)] = th.dg[sidx(g2, cur)] = next_to_gap;
+				th.dg_class[sidx(cur, g1)] = th.dg_class[sidx(g1, cur)] = cls;
+				th.dg_class[sidx(cur, g2)] = th.dg_class[sidx(g2, cur)] = cls;
 			}
 			if (!th.wc[cur])
 				for (int k = bA; k <= bI; ++k)
 					for (int l = bA; l <= bI; ++l)
-						if (!th.wc[pair_of(k, l)]) th.dg[sidx(cur, pair_of(k, l))] = pen_loop;
+						if (!th.wc[pair_of(k, l)]) {
+							th.dg[sidx(cur, pair_of(k, l))] = pen_loop;
+							th.dg_class[sidx(cur, pair_of(k, l))] = DG_LOOP;
+						}
 		}
 	for (int x = bA; x <= bI; ++x)
 		for (int y = bA; y <= bI; ++y) {
 			th.dg[sidx(pair_of(x, bGAP), pair_of(y, bGAP))] = pen_bulge;
 			th.dg[sidx(pair_of(bGAP, x), pair_of(bGAP, y))] = pen_bulge;
+			th.dg_class[sidx(pair_of(x, bGAP), pair_of(y, bGAP))] = DG_BULGE;
+			th.dg_class[sidx(pair_of(bGAP, x), pair_of(bGAP, y))] = DG_BULGE;
 		}
+}
+
+// update_dp_param at another temperature from the rule table (what the kernels do entry by entry in
+// the Dinkelbach mode); used by the host-side self check only
+void dg_at_temperature(const Thermo &th, float T, int32_t *out)
+{
+	const int32_t pen[7] = {0,
+		unfavourable(th.supp[0] - T*(th.supp[1] + th.supp_sc[0])),
+		unfavourable(th.supp[2] - T*(th.supp[3] + th.supp_sc[1])),
+		unfavourable(th.supp[4] - T*(th.supp[5] + th.supp_sc[2])),
+		unfavourable(th.supp[6] - T*(th.supp[7] + th.supp_sc[2])),
+		unfavourable(th.supp[8] - T*(th.supp[9] + th.supp_sc[2])),
+		unfavourable(th.supp[10] - T*(th.supp[11] + th.supp_sc[3]))};
+	for (int i = 0; i < TABLE; ++i)
+		out[i] = th.dg_class[i] ? pen[th.dg_class[i]] : scaled(th.H[i] - T*(th.S[i] + th.salt_correction));
 }
 
 // Per-row penalty tables of the fast alignment kernel.  Row i (1-based) of the DP matrix pairs

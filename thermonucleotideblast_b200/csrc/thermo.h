@@ -6,6 +6,9 @@ namespace tnt {
 // update_dp_param + pair tables for one (T, [Na+]) -- reference nuc_cruc.cpp:226-487
 void build_thermo(Thermo &th, float T, float na, bool dangle5, bool dangle3);
 
+// the same table at another temperature, entry by entry from Thermo::dg_class (Dinkelbach mode)
+void dg_at_temperature(const Thermo &th, float T, int32_t *out);
+
 // penalty tables of the fast alignment kernel: out[len][72] and out[20]
 void build_row_tables(const Thermo &th, const OligoStrand &os, int32_t *out);
 void build_p5_table(const Thermo &th, int32_t *out);

@@ -36,7 +36,19 @@ struct Thermo {
 	char hairpin_loop[NUM_HAIRPIN_LOOP][8];
 	float hairpin_special_H[NUM_HAIRPIN_LOOP];
 	float hairpin_special_S[NUM_HAIRPIN_LOOP];
+	// --dinkelbach (nuc_cruc.cpp:2399-2440): the penalty table is re-derived at a temperature of the
+	// window's own (the Tm of the previous iteration), so the kernels evaluate update_dp_param entry by
+	// entry: dg_class says which rule fills an entry (0: H - T*(S + salt correction); 1..6: the
+	// supplementary terms below, clamped at zero), the rest are the T-independent inputs of the rules.
+	uint8_t dg_class[TABLE + 3];
+	float supp[12];           // param_supp (nuc_cruc.h:640)
+	float supp_sc[4];         // salt correction * param_supp_salt[k]
+	float salt_correction;    // param_SALT * log [Na+]
+	int32_t dinkelbach;
 };
+
+// dg_class values
+enum : int { DG_NN = 0, DG_LOOP = 1, DG_BULGE = 2, DG_TERM_AT = 3, DG_TERM_GC = 4, DG_TERM_INO = 5, DG_TERM_MM = 6 };
 
 // One (oligo, strand) search unit.  `seq` is the oligo 5'->3' in NucCruc codes (the NucCruc
 // "query"); the seed words are those of the oligo (minus strand) or of its reverse complement

@@ -303,10 +303,11 @@ class Engine:
     reference (tntblast_local.cpp:345-372)."""
 
     def __init__(self, target_T: float = 310.15, salt: float = 50.0e-3, dangle5: bool = False,
-                 dangle3: bool = False, word_size: int = 7, device: int = 0, keep_culled_sites: bool = False):
+                 dangle3: bool = False, word_size: int = 7, device: int = 0, keep_culled_sites: bool = False,
+                 dinkelbach: bool = False):
         self.L = load_library()
         prm = EngineParams(target_T=target_T, salt=salt, dangle5=int(dangle5), dangle3=int(dangle3),
-                           dinkelbach=0, word_size=word_size, device=device,
+                           dinkelbach=int(dinkelbach), word_size=word_size, device=device,
                            reserved=1 if keep_culled_sites else 0)   # TNT_ENGINE_KEEP_CULLED_SITES
         self.h = C.c_void_p()
         self._check(self.L.tnt_engine_create(C.byref(prm), C.byref(self.h)))
