@@ -547,10 +547,14 @@ def test_full_size_properties(eng, oracle):
         assert a == b
 
 
-@pytest.mark.parametrize("mode", ["dense", "sparse"])
+@pytest.mark.parametrize("mode", ["dense", "dense_global", "sparse"])
 def test_seeds_both_scan_kernels(eng, oracle, monkeypatch, mode):
-    """k_seed_scan (dense tables) and k_seed_scan_sparse (grouped pre-filter) give the same seeds."""
-    monkeypatch.setenv("TNT_SCAN_MODE", mode)
+    """k_seed_scan_smem (dense tables; tile, table and packed oligos in shared memory), k_seed_scan (dense
+    tables too large for shared memory: table in L2) and k_seed_scan_sparse (grouped pre-filter) give the
+    same seeds."""
+    monkeypatch.setenv("TNT_SCAN_MODE", mode.split("_")[0])
+    if mode == "dense_global":
+        monkeypatch.setenv("TNT_SCAN_GLOBAL_TABLE", "1")
     rng = np.random.default_rng(808)
     eng.clear_targets()
     frags = [gen.random_codes(n, rng) for n in (300000, 131072, 131073, 131072 + 70, 64, 7, 200001)]
@@ -573,10 +577,12 @@ def test_seeds_both_scan_kernels(eng, oracle, monkeypatch, mode):
     assert total > 300
 
 
-@pytest.mark.parametrize("mode", ["dense", "sparse"])
+@pytest.mark.parametrize("mode", ["dense", "dense_global", "sparse"])
 def test_search_both_scan_kernels(engine_lib, oracle, monkeypatch, mode):
     from thermonucleotideblast_b200 import Assay, Engine
-    monkeypatch.setenv("TNT_SCAN_MODE", mode)
+    monkeypatch.setenv("TNT_SCAN_MODE", mode.split("_")[0])
+    if mode == "dense_global":
+        monkeypatch.setenv("TNT_SCAN_GLOBAL_TABLE", "1")
     rng = np.random.default_rng(909)
     db = [gen.random_codes(int(rng.integers(100000, 300000)), rng) for _ in range(3)]
     assays = gen.make_assays(rng, db, 4, "pcr", variants=3)

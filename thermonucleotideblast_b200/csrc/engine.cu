@@ -146,6 +146,10 @@ struct OsSet {
 	DevBuf<uint32_t> d_assay_present;
 	DevBuf<uint64_t> d_packed;
 	DevBuf<uint32_t> d_present, d_offset, d_entry;
+	DevBuf<uint16_t> d_prefix, d_doff;  // rank-compressed table (k_seed_scan_smem)
+	bool smem_table = false;
+	uint32_t distinct = 0;
+	size_t smem_table_bytes = 0;
 	std::vector<int32_t> row_tab;       // fast-kernel penalty rows, [sum of len][ROW_WORDS]
 	std::vector<int32_t> lean_tab;      // lean-tier rows, [sum of len][LEAN_WORDS]
 	std::vector<uint32_t> row_tab_off;  // first row of each oligo strand
@@ -382,6 +386,7 @@ struct tnt_engine {
 		DbView v;
 		v.db2 = db2.p; v.nmask = nmask.p; v.exc_pos = exc_pos.p; v.exc_code = exc_code.p; v.targets = d_targets.p;
 		v.nexc = nexc;
+		v.nwords = db2.cap;
 		return v;
 	}
 
@@ -964,6 +969,29 @@ void finish_set(tnt_engine *e, OsSet &set)
 	set.d_present.upload(set.present, e->stream);
 	set.d_offset.upload(set.offset, e->stream);
 	set.d_entry.upload(set.entry, e->stream);
+	// rank-compressed form of the table for k_seed_scan_smem: set bits in front of each bitmap word, and
+	// offsets of the keys that occur only
+	set.smem_table = false;
+	if (set.nkeys >= 32 && set.total_words < 65536) {
+		const size_t bm_words = set.nkeys/32;
+		std::vector<uint16_t> prefix(bm_words), doff;
+		uint32_t rank = 0;
+		for (size_t w = 0; w < bm_words; ++w) {
+			prefix[w] = (uint16_t)rank;
+			rank += (uint32_t)__builtin_popcount(set.present[w]);
+		}
+		doff.reserve(rank + 1);
+		for (uint32_t k = 0; k < set.nkeys; ++k)
+			if (set.offset[k + 1] > set.offset[k]) doff.push_back((uint16_t)set.offset[k]);
+		doff.push_back((uint16_t)set.total_words);
+		set.distinct = rank;
+		set.smem_table_bytes = 16*nos + 4*std::max<size_t>(set.total_words, 1) + 4*bm_words + 2*bm_words + 2*(rank + 2) + 16;
+		if (rank < 65536 && doff.size() == (size_t)rank + 1 && set.smem_table_bytes <= SCAN_SMEM_TABLE_MAX) {
+			set.d_prefix.upload(prefix, e->stream);
+			set.d_doff.upload(doff, e->stream);
+			set.smem_table = std::getenv("TNT_SCAN_GLOBAL_TABLE") == nullptr; // test hook: the kernel with the table in L2
+		}
+	}
 
 	// Few words in the table -> most positions miss -> grouped pre-filter scan (k_seed_scan_sparse)
 	{
@@ -1057,6 +1085,30 @@ void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1
 		e->d_tile_counter.reserve(1, 0, e->stream);
 		CUDA_OK(cudaMemsetAsync(e->d_tile_counter.p, 0, sizeof(uint32_t), e->stream));
 		a.tile_counter = e->d_tile_counter.p;
+		if (set.smem_table) {
+			// tile, k-mer table and packed oligos in shared memory: the hit path stays on the SM
+			SmemScanArgs sa{};
+			sa.s = a;
+			sa.prefix = set.d_prefix.p;
+			sa.doff = set.d_doff.p;
+			sa.distinct = set.distinct;
+			sa.nentries = (uint32_t)std::max<size_t>(set.total_words, 1);
+			sa.nos = (uint32_t)set.os.size();
+			const size_t smem2 = set.smem_table_bytes;
+			static size_t smem_attr = 0;
+			if (smem2 > smem_attr) { CUDA_OK(cudaFuncSetAttribute(k_seed_scan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); smem_attr = smem2; }
+			static int ctas2 = 0;
+			static size_t ctas2_smem = ~(size_t)0;
+			if (ctas2_smem != smem2) {
+				CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas2, k_seed_scan_smem, SCAN_THREADS, smem2));
+				ctas2 = std::max(ctas2, 1);
+				ctas2_smem = smem2;
+			}
+			const uint32_t grid2 = std::min<uint32_t>(ntiles, (uint32_t)(e->sm_count*ctas2));
+			k_seed_scan_smem<<<grid2, SCAN_THREADS, smem2, e->stream>>>(sa);
+			CUDA_OK(cudaGetLastError());
+			return;
+		}
 		const uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)(e->sm_count*scan_ctas_per_sm));
 		k_seed_scan<<<grid, SCAN_THREADS, smem, e->stream>>>(a);
 	}

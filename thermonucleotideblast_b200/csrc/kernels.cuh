@@ -23,6 +23,7 @@ struct DbView {
 	const uint8_t *exc_code;
 	const Target *targets;
 	uint64_t nexc;
+	uint64_t nwords;   // allocated 2-bit words (read-ahead of whole tiles stays below this)
 };
 
 constexpr int PACK_THREADS = 256;
@@ -162,6 +163,28 @@ __device__ __forceinline__ uint32_t kmer_at(const uint64_t *__restrict__ db2, ui
 	return (uint32_t)x & kmask;
 }
 
+// Where the 2-bit words of the database come from: HBM / L2 ...
+struct GlobalWords {
+	const uint64_t *__restrict__ db2;
+	__device__ __forceinline__ uint64_t operator()(uint64_t wi) const { return __ldg(db2 + wi); }
+};
+// ... or the copy of the current tile (with a halo on both sides) a scan CTA keeps in shared memory
+struct TileWords {
+	const uint64_t *s;   // s[0] holds word wi0
+	uint64_t wi0;
+	__device__ __forceinline__ uint64_t operator()(uint64_t wi) const { return s[(uint32_t)(wi - wi0)]; }
+};
+
+template <class WORDS>
+__device__ __forceinline__ uint32_t kmer_from(const WORDS &words, uint64_t g, uint32_t kmask)
+{
+	const uint64_t wi = g >> 5;
+	const unsigned sh = (unsigned)(g & 31u)*2u;
+	uint64_t x = words(wi) >> sh;
+	if (sh > 48u) x |= words(wi + 1) << (64u - sh);
+	return (uint32_t)x & kmask;
+}
+
 __device__ inline int exception_code(const DbView &db, const Target &tg, uint64_t g)
 {
 	(void)tg;
@@ -251,22 +274,33 @@ struct ScanArgs {
 // (k, t) is therefore dropped when an earlier word k' < k of the same list matches the target
 // at t - (k - k') (same q - t).  `lo` bounds how far back that test may look (0 for a whole
 // fragment, the region start in a region scan).
-__device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ db2, uint64_t tbase, uint32_t t,
-	uint32_t k, uint32_t lo, const uint16_t *__restrict__ keys, uint32_t kmask, int W, const uint64_t *__restrict__ packed)
+template <class WORDS>
+__device__ __forceinline__ bool first_on_diagonal_from(const WORDS &words, uint64_t tbase, uint32_t t,
+	uint32_t k, uint32_t lo, const uint16_t *__restrict__ keys, uint32_t kmask, int W, uint64_t plo, uint64_t phi)
 {
 	if (k == 0) return true;
-	const uint64_t phi = __ldg(packed + 1);
 	if ((phi >> 63) && t >= lo + k) {
 		// Oligo without degenerate letters: word kk is oligo[kk, kk+W), so "an earlier word matches
 		// on this diagonal" is a run of W equal bases starting before base k when the oligo is laid
 		// against the target at t - k.  One XOR of the 2-bit strings, runs by shift-and-AND.
+		// Two cheap answers first.  (a) The base in front of the word: if target[t-1] pairs with oligo
+		// base k-1, word k-1 matches at t-1 -- not the first.  (b) Otherwise every earlier word kk >= k-W
+		// contains that mismatching base and cannot match; for k <= W those are all of them.  Only
+		// k > W is left with the words 0 .. k-W-1 (three quarters of the entries never get here).
+		{
+			const uint64_t g1 = tbase + t - 1;
+			const unsigned tb = (unsigned)(words(g1 >> 5) >> ((unsigned)(g1 & 31u)*2u)) & 3u;
+			const unsigned ob = (unsigned)((k - 1 < 32u ? plo >> (2u*(k - 1)) : phi >> (2u*(k - 33u)))) & 3u;
+			if (tb == ob) return false;
+			if (k <= (uint32_t)W) return true;
+		}
 		const uint64_t g0 = tbase + t - k;
 		const uint64_t wi = g0 >> 5;
 		const unsigned sh = (unsigned)(g0 & 31u)*2u;
-		const uint64_t w0 = __ldg(db2 + wi), w1 = __ldg(db2 + wi + 1), w2 = __ldg(db2 + wi + 2);
+		const uint64_t w0 = words(wi), w1 = words(wi + 1), w2 = words(wi + 2);
 		const uint64_t tl = sh ? ((w0 >> sh) | (w1 << (64u - sh))) : w0;
 		const uint64_t th = sh ? ((w1 >> sh) | (w2 << (64u - sh))) : w1;
-		const uint64_t xl = tl ^ __ldg(packed), xh = th ^ (phi & ~(1ull << 63));
+		const uint64_t xl = tl ^ plo, xh = th ^ (phi & ~(1ull << 63));
 		const uint64_t even = 0x5555555555555555ull;
 		uint64_t rl = ~(xl | (xl >> 1)) & even, rh = ~(xh | (xh >> 1)) & even; // bit 2i: base i equal
 		int len = 1;
@@ -289,9 +323,16 @@ __device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ d
 	for (uint32_t kk = 0; kk < k; ++kk) {
 		const uint32_t back = k - kk;
 		if (t < lo + back) continue;
-		if (kmer_at(db2, tbase + t - back, kmask) == keys[kk]) return false;
+		if (kmer_from(words, tbase + t - back, kmask) == keys[kk]) return false;
 	}
 	return true;
+}
+
+__device__ __forceinline__ bool first_on_diagonal(const uint64_t *__restrict__ db2, uint64_t tbase, uint32_t t,
+	uint32_t k, uint32_t lo, const uint16_t *__restrict__ keys, uint32_t kmask, int W, const uint64_t *__restrict__ packed)
+{
+	if (k == 0) return true;
+	return first_on_diagonal_from(GlobalWords{db2}, tbase, t, k, lo, keys, kmask, W, __ldg(packed), __ldg(packed + 1));
 }
 
 // Append to the bucket of `os`.  Lanes of the warp that append to the same bucket in the same step
@@ -465,6 +506,249 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan(ScanArgs a)
 			}
 			warp_process_hits(a, tg, tl.target, q < total, p, key, kmask, cbuf, cn);
 		}
+		tile = s_next;
+		__syncthreads();
+	}
+	staged_flush(a, cbuf, cn);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense scan with the whole hit path in shared memory (k_seed_scan_smem).
+//
+// ncu on k_seed_scan (profiles/ncu_k_seed_scan_r02_v7_raw.csv): LSU wavefronts 66 %, issue 47 %.  The hit
+// path issued about ten scattered global loads per table hit (two CSR offsets, the entry, two words
+// of the packed oligo, three database words for the diagonal test, the k-mer of the queued position),
+// and a warp-wide load of 32 unrelated addresses costs up to 32 wavefronts where a shared-memory
+// load with random banks costs three or four.  Here a CTA keeps
+//   - the 2-bit words of its tile plus a halo (the diagonal test looks back at most MAX_OLIGO bases
+//     and forward 64),
+//   - the k-mer table in a rank-compressed form: the presence bitmap, the number of set bits in
+//     front of each bitmap word, and offsets only for the keys that occur (rank = prefix + popcount),
+//   - the entries and the packed oligos
+// in shared memory, so that only the candidate append leaves the SM.  Chosen by the host when the
+// table fits (SCAN_SMEM_TABLE_MAX bytes; ~25 KB for 100 TaqMan assays); larger tables (thousands of
+// oligo strands) keep k_seed_scan.
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_HALO_BEFORE = 2;   // 64 bases >= MAX_OLIGO
+constexpr int SCAN_HALO_AFTER = 4;
+constexpr size_t SCAN_SMEM_TABLE_MAX = 72u << 10;
+constexpr int SCAN_ITEMS = 128;       // expanded (position, entry) items per warp and round
+
+struct SmemScanArgs {
+	ScanArgs s;
+	const uint16_t *prefix;    // [nkeys/32] set bits of the presence bitmap in front of each word
+	const uint16_t *doff;      // [distinct + 1] entry offsets of the keys that occur, in key order
+	uint32_t distinct;
+	uint32_t nentries;
+	uint32_t nos;
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa)
+{
+	const ScanArgs &a = sa.s;
+	extern __shared__ __align__(16) unsigned char s_dyn_scan[];
+	// layout: packed oligos (8-byte aligned) | entries | bitmap | prefix | offsets
+	uint64_t *s_packed = reinterpret_cast<uint64_t *>(s_dyn_scan);
+	uint32_t *s_entry = reinterpret_cast<uint32_t *>(s_packed + 2*(size_t)sa.nos);
+	uint32_t *s_present = s_entry + sa.nentries;
+	const uint32_t bm_words = (a.wt.nkeys + 31)/32;
+	uint16_t *s_prefix = reinterpret_cast<uint16_t *>(s_present + bm_words);
+	uint16_t *s_doff = s_prefix + bm_words;
+	__shared__ uint64_t s_tile[SCAN_HALO_BEFORE + SCAN_THREADS + SCAN_HALO_AFTER];
+	__shared__ uint16_t s_queue[SCAN_TILE];
+	__shared__ uint32_t s_warp[SCAN_THREADS/32];
+	__shared__ uint32_t s_total;
+	__shared__ uint32_t s_next;
+	__shared__ StagedCand s_cbuf[SCAN_THREADS/32][64];
+	__shared__ uint32_t s_items[SCAN_THREADS/32][SCAN_ITEMS];   // entry index << 16 | position in the tile
+	__shared__ uint32_t s_full[SCAN_THREADS/32][64];
+
+	for (uint32_t i = threadIdx.x; i < 2*sa.nos; i += SCAN_THREADS) s_packed[i] = a.os_packed[i];
+	for (uint32_t i = threadIdx.x; i < sa.nentries; i += SCAN_THREADS) s_entry[i] = a.wt.entry[i];
+	for (uint32_t i = threadIdx.x; i < bm_words; i += SCAN_THREADS) { s_present[i] = a.wt.present[i]; s_prefix[i] = sa.prefix[i]; }
+	for (uint32_t i = threadIdx.x; i <= sa.distinct; i += SCAN_THREADS) s_doff[i] = sa.doff[i];
+	__syncthreads();
+
+	const uint32_t kmask = a.wt.nkeys - 1;
+	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	StagedCand *cbuf = s_cbuf[warp];
+	uint32_t cn = 0;
+
+	uint32_t tile = a.tile_begin + blockIdx.x;
+	while (tile < a.tile_end) {
+		const ScanTile tl = a.tiles[tile];
+		const Target tg = a.db.targets[tl.target];
+		const uint32_t p0 = tl.start + threadIdx.x*32u;
+		if (threadIdx.x == 0) s_next = a.tile_begin + gridDim.x + atomicAdd(a.tile_counter, 1u);
+
+		// the tile's words (one per thread) and the halo; words outside the fragment are never looked
+		// at by the tests below (positions are bounded by tg.len, look-backs by the fragment start),
+		// they only have to be readable: the allocation is padded behind, and nothing lies in front of word 0
+		const uint64_t wi0 = (tg.base + tl.start) >> 5;
+		const uint64_t lo = wi0 + threadIdx.x < a.db.nwords ? __ldg(a.db.db2 + wi0 + threadIdx.x) : 0ull;
+		s_tile[SCAN_HALO_BEFORE + threadIdx.x] = lo;
+		if (threadIdx.x < SCAN_HALO_BEFORE)
+			s_tile[threadIdx.x] = wi0 + threadIdx.x >= (uint64_t)SCAN_HALO_BEFORE ? __ldg(a.db.db2 + wi0 + threadIdx.x - SCAN_HALO_BEFORE) : 0ull;
+		if (threadIdx.x >= SCAN_THREADS - SCAN_HALO_AFTER) {
+			const uint64_t w = wi0 + SCAN_HALO_AFTER + threadIdx.x;
+			s_tile[SCAN_HALO_BEFORE + SCAN_HALO_AFTER + threadIdx.x] = w < a.db.nwords ? __ldg(a.db.db2 + w) : 0ull;
+		}
+		__syncthreads();
+		const TileWords words{s_tile, wi0 - SCAN_HALO_BEFORE};
+
+		// phase 1: 32 positions per thread -> bit mask of positions whose W-mer is in the table
+		uint32_t hitmask = 0;
+		if (p0 < tg.len) {
+			const uint64_t hi = s_tile[SCAN_HALO_BEFORE + threadIdx.x + 1];
+			const uint32_t nvalid = (p0 + (uint32_t)a.W <= tg.len) ? min(32u, tg.len - (uint32_t)a.W + 1u - p0) : 0u;
+#pragma unroll
+			for (uint32_t b = 0; b < 32; ++b) {
+				const uint64_t x = b ? ((lo >> (2*b)) | (hi << (64 - 2*b))) : lo;
+				const uint32_t key = (uint32_t)x & kmask;
+				hitmask |= ((s_present[key >> 5] >> (key & 31u)) & 1u) << b;
+			}
+			if (nvalid < 32) hitmask &= (nvalid ? ((1u << nvalid) - 1u) : 0u);
+		}
+
+		// block-wide exclusive scan of the hit counts
+		const uint32_t cnt = __popc(hitmask);
+		uint32_t incl = cnt;
+		for (int off = 1; off < 32; off <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= (unsigned)off) incl += v;
+		}
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		uint32_t base = 0;
+		for (unsigned w = 0; w < warp; ++w) base += s_warp[w];
+		if (threadIdx.x == SCAN_THREADS - 1) s_total = base + incl;
+		uint32_t slot = base + incl - cnt;
+		uint32_t m = hitmask;
+		while (m) {
+			const uint32_t b = __ffs(m) - 1;
+			m &= m - 1;
+			s_queue[slot++] = (uint16_t)(threadIdx.x*32u + b);
+		}
+		__syncthreads();
+
+		// phase 2, dense at every step (the lock-step walk of k_seed_scan spends 185 warp instructions per
+		// round whatever the number of busy lanes, and runs the full diagonal test for the whole warp
+		// when one lane needs it -- ncu source page of k_seed_scan, profiles/README.md):
+		//  (a) 32 queued positions per warp: key -> rank -> entry range, expanded into (position, entry)
+		//      items in a per-warp buffer (most keys carry one entry, a few carry several);
+		//  (b) one item per lane: the cheap answers of the diagonal test (word 0, the base in front of
+		//      the word, k <= W); items that need the bit-parallel run test go to a second buffer;
+		//  (c) that buffer, one item per lane.
+		// Survivors are staged and appended like before.
+		const uint32_t total = s_total;
+		uint32_t *ibuf = s_items[warp], *fbuf = s_full[warp];
+		uint32_t fn = 0; // queued full tests of this warp (warp-uniform)
+		auto stage_kept = [&](bool keep, uint32_t os, uint32_t k, uint32_t p) {
+			const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+			if (keep) {
+				StagedCand &c = cbuf[cn + (uint32_t)__popc(kept & ((1u << lane) - 1u))];
+				c.os = os;
+				c.target_k = tl.target | (k << 24);
+				c.t = p;
+			}
+			cn += (uint32_t)__popc(kept);
+			if (cn >= 32) {
+				staged_flush(a, cbuf, 32u);
+				cn -= 32;
+				if (lane < cn) cbuf[lane] = cbuf[32 + lane];
+				__syncwarp();
+			}
+		};
+		auto run_full = [&](uint32_t n) {
+			// (c) n <= 32 items from the front of fbuf
+			bool keep = false;
+			uint32_t os = 0, k = 0, p = 0;
+			if (lane < n) {
+				const uint32_t it = fbuf[lane];
+				const uint32_t ent = s_entry[it >> 16];
+				os = ent >> 8;
+				k = ent & 0xffu;
+				p = tl.start + (it & 0xffffu);
+				keep = first_on_diagonal_from(words, tg.base, p, k, 0u, a.os_keys + (size_t)os*MAX_OLIGO, kmask, a.W,
+					s_packed[2*os], s_packed[2*os + 1]);
+			}
+			stage_kept(keep, os, k, p);
+		};
+		auto run_items = [&](uint32_t i0, uint32_t n) {
+			// (b) n <= 32 items from ibuf[i0 ...]
+			bool keep = false, full = false;
+			uint32_t os = 0, k = 0, p = 0, it = 0;
+			if (lane < n) {
+				it = ibuf[i0 + lane];
+				const uint32_t ent = s_entry[it >> 16];
+				os = ent >> 8;
+				k = ent & 0xffu;
+				p = tl.start + (it & 0xffffu);
+				const uint64_t phi = s_packed[2*os + 1];
+				if (k == 0) keep = true;
+				else if (!(phi >> 63) || p < k) full = true;  // degenerate oligo or fragment start: general test
+				else {
+					const uint64_t g1 = tg.base + p - 1;
+					const unsigned tb = (unsigned)(words(g1 >> 5) >> ((unsigned)(g1 & 31u)*2u)) & 3u;
+					const unsigned ob = (unsigned)((k - 1 < 32u ? s_packed[2*os] >> (2u*(k - 1)) : phi >> (2u*(k - 33u)))) & 3u;
+					if (tb != ob) { if (k <= (uint32_t)a.W) keep = true; else full = true; }
+				}
+			}
+			const uint32_t fm = __ballot_sync(0xffffffffu, full);
+			if (full) fbuf[fn + (uint32_t)__popc(fm & ((1u << lane) - 1u))] = it;
+			fn += (uint32_t)__popc(fm);
+			__syncwarp();
+			stage_kept(keep, os, k, p);
+			if (fn >= 32) {
+				run_full(32u);
+				fn -= 32;
+				if (lane < fn) fbuf[lane] = fbuf[32 + lane];
+				__syncwarp();
+			}
+		};
+		uint32_t in = 0; // items waiting in ibuf (warp-uniform, < 32 between rounds)
+		for (uint32_t q0 = warp*32u; q0 < total; q0 += SCAN_THREADS) {
+			const uint32_t q = q0 + lane;
+			uint32_t prel = 0, e0 = 0, e1 = 0;
+			if (q < total) {
+				prel = s_queue[q];
+				const uint32_t key = kmer_from(words, tg.base + tl.start + prel, kmask);
+				const uint32_t w = key >> 5, bit = key & 31u;
+				const uint32_t rank = (uint32_t)s_prefix[w] + (uint32_t)__popc(s_present[w] & ((1u << bit) - 1u));
+				e0 = s_doff[rank];
+				e1 = s_doff[rank + 1];
+			}
+			// (a) exclusive scan of the entry counts; the items join what the previous round left over
+			// (fewer than 32), so that every pass of (b) but the last has 32 busy lanes
+			const uint32_t ne = e1 - e0;
+			uint32_t incl2 = ne;
+			for (int off = 1; off < 32; off <<= 1) {
+				const uint32_t v = __shfl_up_sync(0xffffffffu, incl2, off);
+				if (lane >= (unsigned)off) incl2 += v;
+			}
+			const uint32_t nitems = __shfl_sync(0xffffffffu, incl2, 31);
+			const uint32_t first = incl2 - ne;
+			for (uint32_t cb = 0; cb < nitems; cb += SCAN_ITEMS - 32) {
+				for (uint32_t j = 0; j < ne; ++j) {
+					const uint32_t idx = first + j;
+					if (idx >= cb && idx < cb + (SCAN_ITEMS - 32)) ibuf[in + idx - cb] = ((e0 + j) << 16) | prel;
+				}
+				__syncwarp();
+				in += min((uint32_t)(SCAN_ITEMS - 32), nitems - cb);
+				uint32_t i0 = 0;
+				for (; i0 + 32 <= in; i0 += 32) run_items(i0, 32u);
+				// the remainder moves to the front
+				const uint32_t rest = in - i0;
+				uint32_t carry = 0;
+				if (lane < rest) carry = ibuf[i0 + lane];
+				__syncwarp();
+				if (lane < rest) ibuf[lane] = carry;
+				__syncwarp();
+				in = rest;
+			}
+		}
+		if (in) run_items(0u, in);
+		if (fn) run_full(fn);
 		tile = s_next;
 		__syncthreads();
 	}
