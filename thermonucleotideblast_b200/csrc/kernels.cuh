@@ -653,7 +653,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa
 			}
 			cn += (uint32_t)__popc(kept);
 			if (cn >= 32) {
+#if !defined(TNT_SCAN_EXP) || TNT_SCAN_EXP != 1
 				staged_flush(a, cbuf, 32u);
+#endif
 				cn -= 32;
 				if (lane < cn) cbuf[lane] = cbuf[32 + lane];
 				__syncwarp();
@@ -707,6 +709,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa
 			}
 		};
 		uint32_t in = 0; // items waiting in ibuf (warp-uniform, < 32 between rounds)
+#if defined(TNT_SCAN_EXP) && TNT_SCAN_EXP == 2
+		if (total == 0xffffffffu) // timing experiment: phase 1 only
+#endif
 		for (uint32_t q0 = warp*32u; q0 < total; q0 += SCAN_THREADS) {
 			const uint32_t q = q0 + lane;
 			uint32_t prel = 0, e0 = 0, e1 = 0;
@@ -736,7 +741,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa
 				__syncwarp();
 				in += min((uint32_t)(SCAN_ITEMS - 32), nitems - cb);
 				uint32_t i0 = 0;
+#if defined(TNT_SCAN_EXP) && TNT_SCAN_EXP == 3
+				if (in > 96) { in = 0; } // timing experiment: expansion only
+#else
 				for (; i0 + 32 <= in; i0 += 32) run_items(i0, 32u);
+#endif
 				// the remainder moves to the front
 				const uint32_t rest = in - i0;
 				uint32_t carry = 0;
