@@ -3,7 +3,8 @@
 #   tools/capture_profiles.sh <tag>      e.g. r02_v7
 # 1. launch list of a short bench run (gpu__time_duration.sum)
 # 2. DRAM bytes of every launch of exactly one warm full-size search (tools/one_search.py) -> the `traffic` fields of the bench line
-# 3. `--set full` captures of the lean tier, the dense seed scan and the region scan
+# 3. `--set full` captures of the lean tier (the two largest launches of a warm search), the dense seed scan
+#    (k_seed_scan_smem) and the region scan
 tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
@@ -14,7 +15,7 @@ $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
 	--csv --log-file $out/dram_$tag.csv python tools/one_search.py 1000 100 taqman > $out/dram_$tag.log 2>&1
 $NCU --set full --import-source on -k regex:'k_align_fast' -s 24 -c 2 -f -o $out/ncu_k_align_lean_$tag \
 	python bench.py --mbp 200 --steps 1 --warmup 1 --no-cpu-baseline --no-fasta > $out/ncu_lean_$tag.log 2>&1
-$NCU --set full --import-source on -k k_seed_scan -s 2 -c 1 -f -o $out/ncu_k_seed_scan_$tag \
+$NCU --set full --import-source on -k k_seed_scan_smem -s 2 -c 1 -f -o $out/ncu_k_seed_scan_smem_$tag \
 	python bench.py --mbp 200 --steps 1 --warmup 1 --no-cpu-baseline --no-fasta > $out/ncu_scan_$tag.log 2>&1
 $NCU --set full --import-source on -k k_region_scan -s 3 -c 1 -f -o $out/ncu_k_region_scan_$tag \
 	python bench.py --mbp 200 --steps 1 --warmup 1 --no-cpu-baseline --no-fasta > $out/ncu_region_$tag.log 2>&1
