@@ -348,12 +348,9 @@ __device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t os, u
 	if ((int)lane == leader) base = atomicAdd(a.cand_count + (size_t)os*COUNT_STRIDE, (uint32_t)__popc(peers));
 	base = __shfl_sync(peers, base, leader);
 	const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-	if (slot < a.cap) {
-		Candidate c;
-		c.target_k = target | (k << 24);
-		c.t = t;
-		a.cand[(size_t)os*a.cap + slot] = c;
-	}
+	if (slot < a.cap)
+		__stcs(reinterpret_cast<unsigned long long *>(a.cand + (size_t)os*a.cap + slot),
+			(unsigned long long)(target | (k << 24)) | ((unsigned long long)t << 32));
 }
 
 // Candidates a warp has found but not yet appended to the buckets
@@ -375,12 +372,57 @@ __device__ __forceinline__ void staged_flush(const ScanArgs &a, const StagedCand
 		base = __shfl_sync(peers, base, leader);
 		const uint32_t slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 		if (slot < a.cap) {
-			Candidate out;
-			out.target_k = c.target_k;
-			out.t = c.t;
-			a.cand[(size_t)c.os*a.cap + slot] = out;
+			// one 8-byte streaming store: the candidate is read once, by another kernel, much later
+			__stcs(reinterpret_cast<unsigned long long *>(a.cand + (size_t)c.os*a.cap + slot),
+				(unsigned long long)c.target_k | ((unsigned long long)c.t << 32));
 		}
 	}
+	__syncwarp();
+}
+
+// The same append split in two, so that the round trip of the atomics overlaps the work on the next 32
+// candidates: `begin` takes the first 32 staged entries into registers and issues one atomic per distinct
+// bucket; `end` (called before the next `begin`, and at the end of the kernel) reads the returned bases and
+// stores.  Timing experiments (tools/scan_timing.py) put the atomics at 1 of 3.9 ms per Gbp x 200 strands
+// when the warp waits for them on the spot.
+struct PendingAppend {
+	uint32_t os, target_k, t, base, rank;
+	int leader;
+	bool mine;    // this lane holds an entry
+	bool open;    // warp-uniform: an append is in flight
+};
+
+__device__ __forceinline__ void staged_append_end(const ScanArgs &a, PendingAppend &pa)
+{
+	if (!pa.open) return;
+	const uint32_t base = __shfl_sync(0xffffffffu, pa.base, pa.leader);
+	if (pa.mine) {
+		const uint32_t slot = base + pa.rank;
+		if (slot < a.cap)
+			__stcs(reinterpret_cast<unsigned long long *>(a.cand + (size_t)pa.os*a.cap + slot),
+				(unsigned long long)pa.target_k | ((unsigned long long)pa.t << 32));
+	}
+	pa.open = false;
+}
+
+__device__ __forceinline__ void staged_append_begin(const ScanArgs &a, const StagedCand *cbuf, uint32_t n, PendingAppend &pa)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	__syncwarp();
+	pa.mine = lane < n;
+	pa.leader = 0;
+	pa.base = 0;
+	pa.rank = 0;
+	if (pa.mine) {
+		const StagedCand c = cbuf[lane];
+		pa.os = c.os; pa.target_k = c.target_k; pa.t = c.t;
+		const unsigned active = __activemask();
+		const unsigned peers = __match_any_sync(active, c.os);
+		pa.leader = __ffs(peers) - 1;
+		pa.rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+		if ((int)lane == pa.leader) pa.base = atomicAdd(a.cand_count + (size_t)c.os*COUNT_STRIDE, (uint32_t)__popc(peers));
+	}
+	pa.open = true;
 	__syncwarp();
 }
 
@@ -573,6 +615,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa
 	const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	StagedCand *cbuf = s_cbuf[warp];
 	uint32_t cn = 0;
+	PendingAppend pend;
+	pend.open = false;
+	pend.mine = false;
+	pend.os = pend.target_k = pend.t = pend.base = pend.rank = 0;
+	pend.leader = 0;
 
 	uint32_t tile = a.tile_begin + blockIdx.x;
 	while (tile < a.tile_end) {
@@ -654,7 +701,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa
 			cn += (uint32_t)__popc(kept);
 			if (cn >= 32) {
 #if !defined(TNT_SCAN_EXP) || TNT_SCAN_EXP != 1
-				staged_flush(a, cbuf, 32u);
+				staged_append_end(a, pend);          // the previous append: its atomics have long returned
+				staged_append_begin(a, cbuf, 32u, pend);
 #endif
 				cn -= 32;
 				if (lane < cn) cbuf[lane] = cbuf[32 + lane];
@@ -761,6 +809,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_seed_scan_smem(SmemScanArgs sa
 		tile = s_next;
 		__syncthreads();
 	}
+	staged_append_end(a, pend);
 	staged_flush(a, cbuf, cn);
 }
 

@@ -78,7 +78,7 @@ struct Target {
 };
 
 // Seed candidate: 8 bytes.  target < 2^24 per engine, k < 256.
-struct Candidate {
+struct alignas(8) Candidate {   // 8-byte aligned: one 64-bit load / store per candidate
 	uint32_t target_k;   // target | k << 24
 	uint32_t t;          // seed position in the fragment
 };
