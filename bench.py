@@ -134,6 +134,26 @@ def bind_to_gpu_numa_node(local_rank: int):
         return None
 
 
+def final_records_equal(a: bytes, b: bytes) -> bool:
+    """Two finished hit lists (bytes of tnt_final_hit records, engine.finalize_hits(raw=True)) hold the same hits in
+    the same order: assay, record, coordinates, strand, Tm and mismatch counts of both primers (block / index /
+    text offsets differ between a sharded and a single-engine run by construction)."""
+    from thermonucleotideblast_b200.engine import FinalHit
+    dt = np.dtype(FinalHit)
+    x, y = np.frombuffer(a, dtype=dt), np.frombuffer(b, dtype=dt)
+    if x.size != y.size:
+        return False
+    hx, hy = x["hit"], y["hit"]
+    for f in ("assay_index", "target_id", "amp_first", "amp_last", "primer_strand"):
+        if not np.array_equal(hx[f], hy[f]):
+            return False
+    for side in ("forward", "reverse"):
+        for f in ("tm", "num_mm"):
+            if not np.array_equal(hx[side][f], hy[side][f]):
+                return False
+    return True
+
+
 def traffic_from_profile():
     """DRAM bytes of one full-size search, summed per kernel family from the newest committed ncu
     capture `profiles/dram_r*.csv` (tools/capture_profiles.sh: dram__bytes_read.sum + dram__bytes_write.sum of
@@ -608,7 +628,7 @@ def run_config5(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     gather_s = finalize_s = 0.0
-    final = None
+    final_n, final_raw = None, b""
     for _ in range(e2e_steps):
         eng.clear_targets()
         eng.add_targets(frag_list)
@@ -626,7 +646,7 @@ def run_config5(args, rank, local_rank, world):
         gather_s += time.perf_counter() - tg
         if rank == 0:
             tf = time.perf_counter()
-            final = finalize_hits(gathered, alist)
+            final_n, final_raw = finalize_hits(gathered, alist, raw=True)
             finalize_s += time.perf_counter() - tf
     barrier()
     e2e_dt = reduce((time.perf_counter() - t0) / e2e_steps, dist.ReduceOp.MAX if world > 1 else None)
@@ -651,12 +671,10 @@ def run_config5(args, rank, local_rank, world):
         e1.add_targets([whole[r * RECORD_BP + a: r * RECORD_BP + a + n] for (r, a, b, ms, n) in table])
         e1.search_raw(opts)
         n1, raw1, text1 = e1.hit_records()
-        single = finalize_hits([(raw1, n1, text1, [tuple(t) for t in table])], alist)
         e1.close()
-        key = lambda c: (c.assay_index, c.target_id, c.amp_first, c.amp_last, c.primer_strand, c.forward.tm, c.reverse.tm,
-                         c.forward.num_mm, c.reverse.num_mm)
-        verify = {"single_engine_hits": len(single), "sharded_hits": len(final),
-                  "identical": [key(c) for (_, _, c) in single] == [key(c) for (_, _, c) in final]}
+        single_n, single_raw = finalize_hits([(raw1, n1, text1, [tuple(t) for t in table])], alist, raw=True)
+        verify = {"single_engine_hits": single_n, "sharded_hits": final_n,
+                  "identical": final_records_equal(single_raw, final_raw)}
 
     if rank == 0:
         line = {
@@ -670,7 +688,7 @@ def run_config5(args, rank, local_rank, world):
                        "fragment_bases_rank0": shard_bases, "assays": len(assays),
                        "l2": "inputs larger than L2 (packed shard %.0f MB + candidate buffers)" % (shard_bases * 0.375 / 1e6)},
             "alignments_per_s": aligns / dt, "alignments_per_step": aligns, "dp_cells_per_step": cells,
-            "hits_per_step_all_ranks_before_gather": int(raw_hits), "hits_after_finalize": len(final) if final is not None else None,
+            "hits_per_step_all_ranks_before_gather": int(raw_hits), "hits_after_finalize": final_n,
             "device_ms_per_step": dev_ms / args.steps,
             "kernel_ms_per_step": {"seed_scan": scan_s * 1e3, "nuccruc_align": align_s * 1e3},
             "gpu_launches": int(launches), "clocks": clocks,

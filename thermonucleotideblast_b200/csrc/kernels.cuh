@@ -1609,12 +1609,19 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(AlignArgs a)
 	unsigned long long my_cells = 0;
 
 	uint32_t group_hint = 0xffffffffu;
-	for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+	uint32_t cur_os = 0xffffffffu;
+	// consecutive units per CTA, like the fast kernels: the oligo changes rarely
+	const uint32_t units_per_cta = (a.nunits + gridDim.x - 1)/gridDim.x;
+	const uint32_t u_end = min(a.nunits, (blockIdx.x + 1u)*units_per_cta);
+	for (uint32_t u = blockIdx.x*units_per_cta; u < u_end; ++u) {
 		const AlignUnit unit = unit_of(a.groups, a.ngroups, u, group_hint);
 		const OligoStrand &os = a.os[unit.os];
-		__syncthreads();
-		for (int i = tid; i < os.len; i += ALIGN_THREADS) s_q[i] = os.seq[i];
-		__syncthreads();
+		if (unit.os != cur_os) { // uniform across the block
+			__syncthreads();
+			for (int i = tid; i < os.len; i += ALIGN_THREADS) s_q[i] = os.seq[i];
+			cur_os = unit.os;
+			__syncthreads();
+		}
 
 		if ((uint32_t)tid >= unit.count) continue;
 

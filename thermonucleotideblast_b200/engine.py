@@ -258,13 +258,15 @@ def c_assays(assays: Sequence["Assay"]):
     return arr, keep
 
 
-def finalize_hits(blocks, assays: Sequence["Assay"], best_match: bool = False, uniquify: Optional[bool] = None):
+def finalize_hits(blocks, assays: Sequence["Assay"], best_match: bool = False, uniquify: Optional[bool] = None,
+                  raw: bool = False):
     """tnt_finalize_hits: the reference driver's post-processing (truncation filter, record coordinates,
     select_best_match, uniquify_results, sort) over the hit lists of one or several engines.
 
     `blocks`: list of (hits_bytes, n_hits, arena_bytes, fragments) per engine, where hits_bytes / arena_bytes
     are what Engine.hit_records() returns and `fragments` a list of (record, start, stop, max_stop, len)
-    by target id.  Returns a list of (block, index, CHit) in output order.  Runs on the host; no GPU."""
+    by target id.  Returns a list of (block, index, CHit) in output order, or with raw=True the pair
+    (n, bytes of n tnt_final_hit records).  Runs on the host; no GPU."""
     L = load_library()
     nb = len(blocks)
     cb = (HitBlock * max(nb, 1))()
@@ -282,6 +284,12 @@ def finalize_hits(blocks, assays: Sequence["Assay"], best_match: bool = False, u
     rc = L.tnt_finalize_hits(cb, nb, arr, len(assays), int(best_match), mode, C.byref(out), C.byref(n))
     if rc < 0:
         raise EngineError(L.tnt_postprocess_error().decode())
+    if raw:
+        # the finished records as one byte string (n x tnt_final_hit): what a C++ host would keep; no
+        # per-hit Python objects (3 us each: 7 s for the 2.3 M hits of bench.py --config 5)
+        data = C.string_at(out, n.value * C.sizeof(FinalHit)) if n.value else b""
+        L.tnt_free(out)
+        return n.value, data
     res = [(out[i].block, out[i].index, CHit.from_buffer_copy(out[i].hit)) for i in range(n.value)]
     L.tnt_free(out)
     return res
