@@ -922,3 +922,37 @@ def test_device_pairing_equals_host_join(engine_lib, oracle, monkeypatch):
         assert k == len(dev)
         total += k
     assert total >= 50
+
+
+@pytest.mark.parametrize("W", [4, 5, 6, 8])
+def test_other_word_sizes(engine_lib, oracle, W):
+    """DNAHash word sizes other than the default 7 (`-W`, tntblast.h:68; DNAHash accepts 3..8): seeds bit-exact
+    and searches equal to the oracle through every scan kernel (table sizes 4^W = 256 ... 65536 keys: the
+    rank-compressed shared-memory table, the sparse group bitmap and the region scan all depend on W)."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(1000 + W)
+    n = 12000 if W <= 5 else 60000
+    db = [gen.random_codes(n, rng), gen.random_codes(n // 2 + 37, rng)]
+    gen.sprinkle_degenerate(db[0], rng, frac=1e-3, n_runs_per_50kb=4)
+    assays = gen.make_assays(rng, db, 3, "taqman", variants=3)
+    o = H.default_options(min_primer_tm=42.0, min_probe_tm=42.0, word_size=W)
+    with Engine(word_size=W) as e:
+        ids = [e.add_target(c) for c in db]
+        ol = assays[0][0]
+        total = 0
+        for tid, codes in zip(ids, db):
+            for oligo in (ol, gen.rand_oligo(25, rng), ol[:9] + "N" + ol[10:]):
+                for plus in (False, True):
+                    want = oracle.seeds(codes, oligo, W, plus, unique=True)
+                    assert e.seeds(tid, oligo, plus) == want, (W, tid, oligo, plus)
+                    total += len(want)
+        assert total > 50
+        e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+        got = e.search(to_opts(o))
+        nh = 0
+        for t, codes in enumerate(db):
+            for i, a in enumerate(assays):
+                want = oracle.search(codes, a[0], a[1], a[2], o)
+                assert_hits_equal(e, [h for h in got if h.target_id == t and h.assay_index == i], want, a)
+                nh += len(want)
+        assert nh >= 3
