@@ -956,3 +956,57 @@ def test_other_word_sizes(engine_lib, oracle, W):
                 assert_hits_equal(e, [h for h in got if h.target_id == t and h.assay_index == i], want, a)
                 nh += len(want)
         assert nh >= 3
+
+
+FILTER_CASES = [
+    dict(max_gap=0),
+    dict(max_mismatch=1),
+    dict(max_gap=1, max_mismatch=2, max_poly_degen=0),
+    dict(max_primer_tm=58.0, max_probe_tm=62.0),
+    dict(min_primer_tm=0.0, min_probe_tm=0.0, max_primer_dg=-9.0, max_probe_dg=-10.0),
+    dict(min_primer_dg=-16.0, min_probe_dg=-20.0),
+    dict(min_primer_tm=38.0, max_primer_dg=-7.5, min_primer_dg=-30.0, max_primer_tm=75.0),
+    dict(primer_clamp=4, probe_clamp_5=3, probe_clamp_3=3),
+    dict(min_max_primer_clamp=6),
+    dict(target_strand=1), dict(target_strand=2),
+    dict(single_primer_pcr=0, max_len=300),
+]
+
+
+@pytest.mark.parametrize("case", range(len(FILTER_CASES)))
+def test_search_filter_cascade(engine_lib, oracle, case):
+    """Every per-oligo bound of the reference's filter cascade (bind_oligo.cpp:593-705: Tm window, dG window,
+    clamps, gaps, mismatches, degenerate runs; amplicon_search.cpp:359-441: length, min-max clamp, strands,
+    single-primer products) alone and in combinations, TaqMan and probe-only assays, lists equal to the
+    oracle's; where the compiled reference travels with the repository it is asked as well."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    kw = dict(min_primer_tm=36.0, min_probe_tm=36.0)
+    kw.update(FILTER_CASES[case])
+    rng = np.random.default_rng(5000 + case)
+    db = [gen.random_codes(int(rng.integers(20000, 40000)), rng) for _ in range(3)]
+    gen.sprinkle_degenerate(db[1], rng, frac=2e-3, n_runs_per_50kb=6)
+    taq = gen.make_assays(rng, db, 4, "taqman", variants=5)
+    prb = gen.make_assays(rng, db, 2, "probe", variants=5)
+    ref = H.ref() if H.have_ref() else None
+    nhits = 0
+    for assays, fmt in ((taq, H.ASSAY_PCR), (prb, H.ASSAY_PROBE)):
+        o = H.default_options(assay_format=fmt, **kw)
+        with Engine() as e:
+            for c in db:
+                e.add_target(c)
+            e.set_assays([Assay(i, *a) for i, a in enumerate(assays)])
+            got = e.search(to_opts(o))
+            n = 0
+            for t, codes in enumerate(db):
+                for i, a in enumerate(assays):
+                    want = oracle.search(codes, a[0], a[1], a[2], o)
+                    mine = [h for h in got if h.target_id == t and h.assay_index == i]
+                    assert_hits_equal(e, mine, want, a)
+                    if ref is not None and t == 0:
+                        r = ref.search(codes, a[0], a[1], a[2], o)
+                        assert [(h.exact_key(), h.floats()) for h in r] == [(h.exact_key(), h.floats()) for h in want], (case, fmt, i)
+                    n += len(mine)
+            assert n == len(got)
+            nhits += n
+    # a cascade that rejects everything would make the comparison vacuous
+    assert nhits >= 1 or case in (2,), (case, nhits)
