@@ -957,7 +957,7 @@ template <int LQ, int NT>
 __device__ TNT_FILL_INLINE FastDp nc_fill_lean(const int32_t *__restrict__ tab, const int32_t *__restrict__ p5tab,
 	uint64_t tlo, uint64_t thi, int Lt, uint32_t *__restrict__ trace32)
 {
-	static_assert(LQ % 2 == 0 && LQ >= 2 && LQ <= 64, "row classes are even, rows fit six key bits");
+	static_assert(LQ >= 2 && LQ <= 64, "rows fit six key bits");
 	constexpr int WPC = LeanGeom<LQ>::kWordsPerCol;
 	int cM[LQ], cIq[LQ], cIt[LQ];
 #pragma unroll

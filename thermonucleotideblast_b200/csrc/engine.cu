@@ -1117,8 +1117,13 @@ void launch_scan(tnt_engine *e, OsSet &set, ScanArgs a, uint32_t t0, uint32_t t1
 
 // Oligo length classes of the fast kernels (rows held in registers)
 #define TNT_FAST_CLASSES(X) X(20) X(22) X(24) X(26) X(28) X(32) X(40) X(56)
+// The lean tier also has the odd classes and 18 / 19 below 28: a row of padding is 4-5 % of a 20-row fill, and the
+// lean fill is two thirds of a step.  The full-trace tier (two rows per trace store, 3 % of the windows) keeps the
+// even classes.
+#define TNT_LEAN_CLASSES(X) X(18) X(19) X(20) X(21) X(22) X(23) X(24) X(25) X(26) X(27) X(28) X(30) X(32) X(36) X(40) X(48) X(56)
 #define TNT_CLASS_ENTRY(L) L,
 const int kFastClasses[] = {TNT_FAST_CLASSES(TNT_CLASS_ENTRY)};
+const int kLeanClasses[] = {TNT_LEAN_CLASSES(TNT_CLASS_ENTRY)};
 #undef TNT_CLASS_ENTRY
 
 // 32-bit trace words per thread of the fast tiers
@@ -1135,24 +1140,36 @@ size_t fast_smem(int lq, bool full)
 }
 
 template <int LQ>
-void launch_fast(const AlignArgs &a, uint32_t grid, bool full, cudaStream_t st)
+void launch_full(const AlignArgs &a, uint32_t grid, cudaStream_t st)
 {
-	if (full) k_align_fast<LQ, true><<<grid, ALIGN_THREADS, 0, st>>>(a);
-	else k_align_fast<LQ, false><<<grid, ALIGN_THREADS, fast_smem(LQ, false), st>>>(a);
+	k_align_fast<LQ, true><<<grid, ALIGN_THREADS, 0, st>>>(a);
 }
 
 template <int LQ>
-int fast_occupancy(bool full)
+void launch_lean(const AlignArgs &a, uint32_t grid, cudaStream_t st)
 {
-	static int cached[2] = {0, 0};
-	int &n = cached[full ? 1 : 0];
+	k_align_fast<LQ, false><<<grid, ALIGN_THREADS, fast_smem(LQ, false), st>>>(a);
+}
+
+template <int LQ>
+int full_occupancy()
+{
+	static int n = 0;
 	if (n == 0) {
-		if (full) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, true>, ALIGN_THREADS, 0);
-		else {
-			const size_t smem = fast_smem(LQ, false);
-			CUDA_OK(cudaFuncSetAttribute(k_align_fast<LQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, smem);
-		}
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, true>, ALIGN_THREADS, 0);
+		n = std::max(n, 1);
+	}
+	return n;
+}
+
+template <int LQ>
+int lean_occupancy()
+{
+	static int n = 0;
+	if (n == 0) {
+		const size_t smem = fast_smem(LQ, false);
+		CUDA_OK(cudaFuncSetAttribute(k_align_fast<LQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_align_fast<LQ, false>, ALIGN_THREADS, smem);
 		n = std::max(n, 1);
 	}
 	return n;
@@ -1160,11 +1177,18 @@ int fast_occupancy(bool full)
 
 int fast_blocks_per_sm(int lq, bool full)
 {
-	switch (lq) {
-#define TNT_CLASS_CASE(L) case L: return fast_occupancy<L>(full);
-	TNT_FAST_CLASSES(TNT_CLASS_CASE)
+	if (full)
+		switch (lq) {
+#define TNT_CLASS_CASE(L) case L: return full_occupancy<L>();
+		TNT_FAST_CLASSES(TNT_CLASS_CASE)
 #undef TNT_CLASS_CASE
-	default: throw std::runtime_error("internal: unknown oligo length class");
+		default: throw std::runtime_error("internal: unknown oligo length class (full-trace tier)");
+		}
+	switch (lq) {
+#define TNT_CLASS_CASE(L) case L: return lean_occupancy<L>();
+	TNT_LEAN_CLASSES(TNT_CLASS_CASE)
+#undef TNT_CLASS_CASE
+	default: throw std::runtime_error("internal: unknown oligo length class (lean tier)");
 	}
 }
 
@@ -1212,13 +1236,21 @@ float run_align_kernel(tnt_engine *e, OsSet &set, AlignArgs a, std::vector<Align
 		CUDA_OK(cudaEventCreate(&e->tev.back()));
 	}
 	CUDA_OK(cudaEventRecord(e->tev[e->tev_used], e->stream));
-	switch (lq) {
-	case 0: k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a); break;
-#define TNT_CLASS_CASE(L) case L: launch_fast<L>(a, grid, full, e->stream); break;
-	TNT_FAST_CLASSES(TNT_CLASS_CASE)
+	if (lq == 0) k_align<<<grid, ALIGN_THREADS, smem, e->stream>>>(a);
+	else if (full)
+		switch (lq) {
+#define TNT_CLASS_CASE(L) case L: launch_full<L>(a, grid, e->stream); break;
+		TNT_FAST_CLASSES(TNT_CLASS_CASE)
 #undef TNT_CLASS_CASE
-	default: throw std::runtime_error("internal: unknown oligo length class");
-	}
+		default: throw std::runtime_error("internal: unknown oligo length class (full-trace tier)");
+		}
+	else
+		switch (lq) {
+#define TNT_CLASS_CASE(L) case L: launch_lean<L>(a, grid, e->stream); break;
+		TNT_LEAN_CLASSES(TNT_CLASS_CASE)
+#undef TNT_CLASS_CASE
+		default: throw std::runtime_error("internal: unknown oligo length class (lean tier)");
+		}
 	CUDA_OK(cudaGetLastError());
 	CUDA_OK(cudaEventRecord(e->tev[e->tev_used + 1], e->stream));
 	e->tev_used += 2;
@@ -1262,20 +1294,28 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 
 	HostTimer t_ab("  align_buckets");
 	// units per fast class
-	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));
-	std::vector<std::vector<AlignGroup>> by_class(nclass + 1); // [nclass] = generic kernel
+	const int nclass = (int)(sizeof(kFastClasses)/sizeof(kFastClasses[0]));   // full-trace tier (even classes)
+	const int nlean = (int)(sizeof(kLeanClasses)/sizeof(kLeanClasses[0]));    // lean tier (odd ones too)
+	std::vector<std::vector<AlignGroup>> by_lean(nlean);
+	std::vector<AlignGroup> by_generic;
 	std::vector<std::vector<AlignGroup>> by_class_full(nclass); // oligo strands the lean tier cannot take
-	auto class_of = [&](size_t s) {
+	auto class_of = [&](size_t s) { // class index of the full-trace tier; nclass: generic kernel
 		int c = 0;
 		while (c < nclass - 1 && kFastClasses[c] < set.os[s].len) ++c;
 		return set.fast_ok[s] ? c : nclass;
+	};
+	auto lean_class_of = [&](size_t s) {
+		int c = 0;
+		while (c < nlean - 1 && kLeanClasses[c] < set.os[s].len) ++c;
+		return c;
 	};
 	for (size_t s = 0; s < nos; ++s)
 		if (counts[s]) {
 			const int c = class_of(s);
 			const AlignGroup g{(uint32_t)s, 0u, counts[s], 0u};
-			if (c < nclass && !set.lean_ok[s]) by_class_full[c].push_back(g);
-			else by_class[c].push_back(g);
+			if (c == nclass) by_generic.push_back(g);
+			else if (!set.lean_ok[s]) by_class_full[c].push_back(g);
+			else by_lean[lean_class_of(s)].push_back(g);
 		}
 
 	const uint32_t base_count = e->n_bound;
@@ -1347,11 +1387,11 @@ bool align_buckets(tnt_engine *e, OsSet &set, uint32_t cap, uint32_t os_base, bo
 
 		float ms = 0;
 		std::unique_ptr<HostTimer> t_phase(new HostTimer("    lean / first pass"));
-		for (int c = 0; c < nclass; ++c)
-			if (!by_class[c].empty()) ms += run_align_kernel(e, set, a, by_class[c], kFastClasses[c], set.max_len);
+		for (int c = 0; c < nlean; ++c)
+			if (!by_lean[c].empty()) ms += run_align_kernel(e, set, a, by_lean[c], kLeanClasses[c], set.max_len);
 		for (int c = 0; c < nclass; ++c)
 			if (!by_class_full[c].empty()) ms += run_align_kernel(e, set, a, by_class_full[c], kFastClasses[c], set.max_len, true);
-		if (!by_class[nclass].empty()) ms += run_align_kernel(e, set, a, by_class[nclass], 0, set.max_len);
+		if (!by_generic.empty()) ms += run_align_kernel(e, set, a, by_generic, 0, set.max_len);
 
 		uint32_t cnt[3] = {0, 0, 0};
 		std::vector<uint32_t> retry_fill(nos);

@@ -1970,7 +1970,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, TNT_FAST_MIN_BLOCKS(LQ, FULL)) 
 		int handoff = 0;
 		if (Lt > 0) {
 			uint16_t cells[MAX_MAXCELLS];
-			if (FULL) {
+			if constexpr (FULL) {
 				const FastDpFull dp = nc_fill_fast_full<LQ, ALIGN_THREADS>(s_tab, s_p5, tlo, thi, Lt, trace32);
 				ColMajorTraceFull<LQ, ALIGN_THREADS> tv;
 				tv.trace32 = trace32;
