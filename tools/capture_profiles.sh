@@ -13,7 +13,7 @@ $NCU --metrics gpu__time_duration.sum --csv --log-file $out/launches_$tag.csv \
 	python bench.py --mbp 200 --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_$tag.log 2>&1
 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --profile-from-start off \
 	--csv --log-file $out/dram_$tag.csv python tools/one_search.py 1000 100 taqman > $out/dram_$tag.log 2>&1
-$NCU --set full --import-source on -k regex:'k_align_fast' -s 24 -c 2 -f -o $out/ncu_k_align_lean_$tag \
+$NCU --set full --import-source on -k regex:'k_align_fast' -s 36 -c 2 -f -o $out/ncu_k_align_lean_$tag \
 	python bench.py --mbp 200 --steps 1 --warmup 1 --no-cpu-baseline --no-fasta > $out/ncu_lean_$tag.log 2>&1
 $NCU --set full --import-source on -k k_seed_scan_smem -s 2 -c 1 -f -o $out/ncu_k_seed_scan_smem_$tag \
 	python bench.py --mbp 200 --steps 1 --warmup 1 --no-cpu-baseline --no-fasta > $out/ncu_scan_$tag.log 2>&1
