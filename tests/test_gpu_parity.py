@@ -924,15 +924,21 @@ def test_device_pairing_equals_host_join(engine_lib, oracle, monkeypatch):
     assert total >= 50
 
 
+@pytest.mark.parametrize("mode", ["auto", "sparse", "dense"])
 @pytest.mark.parametrize("W", [4, 5, 6, 8])
-def test_other_word_sizes(engine_lib, oracle, W):
+def test_other_word_sizes(engine_lib, oracle, monkeypatch, W, mode):
     """DNAHash word sizes other than the default 7 (`-W`, tntblast.h:68; DNAHash accepts 3..8): seeds bit-exact
     and searches equal to the oracle through every scan kernel (table sizes 4^W = 256 ... 65536 keys: the
-    rank-compressed shared-memory table, the sparse group bitmap and the region scan all depend on W)."""
+    rank-compressed shared-memory table, the sparse group bitmap and the region scan all depend on W).
+    Short words in the sparse kernel overflow its group queue, i.e. take its position-by-position path, on
+    fragments whose length is no multiple of 32 (found by tools/fuzz_parity.py: that loop must keep the warp
+    together)."""
     from thermonucleotideblast_b200 import Assay, Engine
+    if mode != "auto":
+        monkeypatch.setenv("TNT_SCAN_MODE", mode)
     rng = np.random.default_rng(1000 + W)
     n = 12000 if W <= 5 else 60000
-    db = [gen.random_codes(n, rng), gen.random_codes(n // 2 + 37, rng)]
+    db = [gen.random_codes(n, rng), gen.random_codes(n // 2 + 37, rng), gen.random_codes(6145, rng)]
     gen.sprinkle_degenerate(db[0], rng, frac=1e-3, n_runs_per_50kb=4)
     assays = gen.make_assays(rng, db, 3, "taqman", variants=3)
     o = H.default_options(min_primer_tm=42.0, min_probe_tm=42.0, word_size=W)
@@ -1010,3 +1016,30 @@ def test_search_filter_cascade(engine_lib, oracle, case):
             nhits += n
     # a cascade that rejects everything would make the comparison vacuous
     assert nhits >= 1 or case in (2,), (case, nhits)
+
+
+def test_probe_sites_overhanging_the_fragment_ends(engine_lib, oracle):
+    """A probe site cut by the end (or the start) of a fragment keeps coordinates beyond the fragment, and the
+    reference prints its text from the clamped end for the full length (probe_search.cpp:129-142, :205-219):
+    bases outside [probe_first, probe_last].  Found by tools/fuzz_parity.py (the text fetch threw)."""
+    from thermonucleotideblast_b200 import Assay, Engine
+    rng = np.random.default_rng(31337)
+    P = gen.rand_oligo(38, rng)
+    site = gen.revcomp(P)
+    n_over = 0
+    for strand_text in (site, P):
+        n = 9000
+        codes = gen.random_codes(n, rng)
+        gen.plant(codes, n - 26, strand_text[:26])      # the last 12 bases of the site lie beyond the end
+        gen.plant(codes, 0, strand_text[10:])           # the first 10 in front of the start
+        gen.plant(codes, 4000, strand_text)
+        o = H.default_options(assay_format=H.ASSAY_PROBE, min_probe_tm=30.0)
+        want = oracle.search(codes, None, None, P, o)
+        n_over += sum(1 for h in want if h.probe_first < 0 or h.probe_last >= n)
+        with Engine() as e:
+            e.add_target(codes)
+            e.set_assays([Assay(0, None, None, P)])
+            got = e.search(to_opts(o))
+            assert_hits_equal(e, got, want, (None, None, P))
+            assert e.hit_sequences() == [e.hit_sequence(h) for h in got]
+    assert n_over >= 2

@@ -794,6 +794,46 @@ void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop
 	else mode = h.primer_strand == TNT_PLUS ? SeqMode::PcrPlus : SeqMode::PcrMinus;
 }
 
+// first_i of render_hit_sequence and the reading direction, per mode
+static void hit_sequence_walk(int start, int stop, SeqMode mode, int seq_len, bool &forward, int &first_i)
+{
+	forward = true;
+	first_i = 0;
+	switch (mode) {
+	case SeqMode::PcrPlus: forward = true; first_i = std::max(0, -start); break;                 // amplicon_search.cpp:512-523
+	case SeqMode::PcrMinus: forward = false; first_i = std::max(0, stop - seq_len + 1); break;  // :526-537
+	case SeqMode::ProbePlus: forward = true; first_i = 0; break;                                // probe_search.cpp:205-219
+	case SeqMode::ProbeMinus: forward = false; first_i = 0; break;                              // :129-142
+	case SeqMode::PadlockMinusStrand: forward = true; first_i = std::max(0, 1 - start); break;  // padlock_search.cpp:206-218
+	case SeqMode::PadlockPlusStrand: forward = false; first_i = std::max(0, stop - seq_len - 1); break; // :341-352
+	}
+}
+
+// The fragment positions [lo, hi] render_hit_sequence reads for this hit (hi < lo: none).  Not simply the
+// overlap of [start, stop] with the fragment: a probe site that overhangs the end of a fragment is printed by
+// the reference from the clamped end for the full length (probe_search.cpp:129-142, :205-219), i.e. from
+// bases outside [start, stop] (found by tools/fuzz_parity.py: such a hit made the text fetch throw).
+void hit_sequence_fetch_range(int start, int stop, SeqMode mode, int seq_len, int &lo, int &hi)
+{
+	bool forward;
+	int first_i;
+	hit_sequence_walk(start, stop, mode, seq_len, forward, first_i);
+	const long count = (long)(stop - start + 1) - first_i;
+	lo = 0;
+	hi = -1;
+	if (count <= 0 || seq_len <= 0) return;
+	if (forward) {
+		const long p = std::max(0, start);
+		lo = (int)p;
+		hi = (int)std::min<long>(p + count - 1, (long)seq_len - 1);
+	}
+	else {
+		const long p = std::min(stop, seq_len - 1);
+		hi = (int)p;
+		lo = (int)std::max<long>(p - (count - 1), 0);
+	}
+}
+
 std::string render_hit_sequence(int start, int stop, SeqMode mode, int seq_len, int lo, const std::vector<uint8_t> &codes)
 {
 	static const char fwd[] = "ACGTIMRSVWYHKDBN-";   // hash_base_to_ascii (seq.h:58-101)
@@ -809,14 +849,7 @@ std::string render_hit_sequence(int start, int stop, SeqMode mode, int seq_len, 
 	};
 	bool forward = true;
 	int first_i = 0;
-	switch (mode) {
-	case SeqMode::PcrPlus: forward = true; first_i = std::max(0, -start); break;                 // amplicon_search.cpp:512-523
-	case SeqMode::PcrMinus: forward = false; first_i = std::max(0, stop - seq_len + 1); break;  // :526-537
-	case SeqMode::ProbePlus: forward = true; first_i = 0; break;                                // probe_search.cpp:205-219
-	case SeqMode::ProbeMinus: forward = false; first_i = 0; break;                              // :129-142
-	case SeqMode::PadlockMinusStrand: forward = true; first_i = std::max(0, 1 - start); break;  // padlock_search.cpp:206-218
-	case SeqMode::PadlockPlusStrand: forward = false; first_i = std::max(0, stop - seq_len - 1); break; // :341-352
-	}
+	hit_sequence_walk(start, stop, mode, seq_len, forward, first_i);
 	if (forward) {
 		long p = std::max(0, start);
 		for (int i = first_i; i < n; ++i, ++p) {

@@ -79,6 +79,8 @@ enum class SeqMode { PcrPlus, PcrMinus, ProbePlus, ProbeMinus, PadlockMinusStran
 void hit_sequence_plan(const tnt_hit &h, int assay_format, int &start, int &stop, SeqMode &mode);
 
 // `codes` are the seq.h codes of fragment positions [lo, lo + codes.size())
+// fragment positions [lo, hi] the renderer reads (hi < lo: none)
+void hit_sequence_fetch_range(int start, int stop, SeqMode mode, int seq_len, int &lo, int &hi);
 std::string render_hit_sequence(int start, int stop, SeqMode mode, int seq_len, int lo, const std::vector<uint8_t> &codes);
 
 } // namespace tnt

@@ -2508,8 +2508,9 @@ long hit_sequence(tnt_engine *e, const tnt_hit *h, char *out, size_t cap)
 	hit_sequence_plan(*h, e->last_opt.assay_format, start, stop, mode);
 	const int n = stop - start + 1;
 	if (n <= 0) throw std::runtime_error("hit with start > stop");
-	// fetch the overlapping part of the fragment
-	const int lo = std::max(start, 0), hi = std::min<int64_t>(stop, (int64_t)tg.len - 1);
+	// fetch the part of the fragment the renderer reads
+	int lo, hi;
+	hit_sequence_fetch_range(start, stop, mode, (int)tg.len, lo, hi);
 	std::vector<uint8_t> codes;
 	if (hi >= lo) {
 		const uint32_t m = (uint32_t)(hi - lo + 1);
@@ -2611,7 +2612,8 @@ void hit_sequences(tnt_engine *e)
 		Plan &p = plan[i];
 		hit_sequence_plan(h, e->last_opt.assay_format, p.start, p.stop, p.mode);
 		if (p.stop < p.start) throw std::runtime_error("hit with start > stop");
-		const int lo = std::max(p.start, 0), hi = (int)std::min<int64_t>(p.stop, (int64_t)tg.len - 1);
+		int lo, hi;
+		hit_sequence_fetch_range(p.start, p.stop, p.mode, (int)tg.len, lo, hi);
 		p.lo = lo;
 		p.m = hi >= lo ? (uint32_t)(hi - lo + 1) : 0u;
 		p.off = total;

@@ -948,7 +948,10 @@ __global__ void __launch_bounds__(SPARSE_THREADS) k_seed_scan_sparse(SparseScanA
 		if (overflow) {
 			// more groups passed the pre-filter than the queue holds (dense table / repeats): redo
 			// this tile base by base, one position per lane
-			for (uint32_t p = tl.start + lane; p < min(tl.start + (uint32_t)SCAN_TILE, tg.len); p += 32) {
+			// (the trip count is the same for all lanes: warp_process_hits synchronises the whole warp)
+			const uint32_t p_end = min(tl.start + (uint32_t)SCAN_TILE, tg.len);
+			for (uint32_t p0 = tl.start; p0 < p_end; p0 += 32) {
+				const uint32_t p = p0 + lane;
 				bool hit = false;
 				uint32_t key = 0;
 				if (any_valid && p <= last_valid) {
