@@ -24,6 +24,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <functional>
 #include <vector>
 
 #include "../../include/tntb200.h"
@@ -187,6 +188,11 @@ struct tnt_engine {
 	// oligo-only duplexes (tnt_engine_oligo_dimer): explicit target of the generic kernel, and the
 	// tables with the symmetry entropy folded into the initiation term for homodimers
 	DevBuf<Thermo> d_thermo_homo;
+	// host scratch of replay_groups, kept across searches (180 MB of fresh pages per search cost ~90 ms
+	// in page faults for a hit-dense PCR search)
+	std::vector<ReplaySeedRec> h_replay_seeds;
+	std::vector<int32_t> h_seed_group, h_seed_site;
+	std::vector<ReplaySeed> h_flat_seeds;
 	DevBuf<uint8_t> d_explicit;
 	DevBuf<OligoJob> d_jobs;
 	DevBuf<OligoJobResult> d_job_results;
@@ -1840,7 +1846,8 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	uint64_t nseeds = 0;
 	for (size_t s = 0; s < nos; ++s)
 		if (counts[s]) { spans.push_back(CandSpan{(uint32_t)s, counts[s], nseeds}); nseeds += counts[s]; }
-	std::vector<ReplaySeedRec> seeds(nseeds);
+	std::vector<ReplaySeedRec> &seeds = e->h_replay_seeds;
+	seeds.resize(nseeds);
 	if (nseeds) {
 		e->d_spans.upload(spans, e->stream);
 		e->d_replay_seeds.reserve(nseeds, 0, e->stream);
@@ -1862,7 +1869,7 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	CUDA_OK(cudaStreamSynchronize(e->stream));
 
 	// bound sites of this pass -> `sites`, and per group a (oligo strand, position, word) -> site table
-	t_part.reset(new HostTimer("  replay: grouping"));
+	t_part.reset(new HostTimer("  replay: grouping (sites)"));
 	struct Key { uint32_t os, t, k; int idx; };
 	auto key_less = [](const Key &a, const Key &b) {
 		if (a.os != b.os) return a.os < b.os;
@@ -1888,38 +1895,21 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 	}
 	for (std::vector<Key> &v : group_sites) std::sort(v.begin(), v.end(), key_less);
 
-	// seeds per group (the spans are per oligo strand, hence per assay: spans of different assays fill
-	// different groups, so the spans are dealt out to a few host threads by assay)
-	std::vector<std::vector<ReplaySeed>> group_seeds(groups.size());
+	// Seeds per group, as one array sorted by group (counting sort; the order inside a group stays span by span,
+	// seed by seed, which the replay's stable list sorts depend on).  Labelling (group of a seed, and whether its
+	// window bound: two binary searches) is the expensive part and runs on a few host threads over disjoint,
+	// contiguous index ranges; an earlier form appended to one vector per group from all threads, and the
+	// adjacent vector headers ping-ponged between the cores (270 ms for 5 M seeds of 100 PCR assays x 1 Gbp).
+	t_part.reset(new HostTimer("  replay: grouping (labels)"));
+	std::vector<int32_t> &seed_group = e->h_seed_group, &seed_site = e->h_seed_site;
+	seed_group.assign(nseeds, -1);
+	seed_site.assign(nseeds, -1);
 	{
 		const unsigned nt = nseeds < 200000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
-		// exact sizes first (a fixed reserve per group was 77 MB of fresh pages per 200 Mbp of a hit-dense PCR search)
-		std::vector<uint32_t> group_count(groups.size(), 0);
-		auto count = [&](unsigned t) {
-			for (const CandSpan &sp : spans) {
+		auto label = [&](unsigned t) {
+			for (size_t si = t; si < spans.size(); si += nt) {
+				const CandSpan &sp = spans[si];
 				const OligoStrand &os = set.os[sp.os];
-				if ((unsigned)os.assay % nt != t) continue;
-				long last_g = -1;
-				uint32_t last_target = 0xffffffffu;
-				for (uint64_t i = sp.out_off; i < sp.out_off + sp.count; ++i) {
-					const uint32_t target = seeds[i].target_k & 0xffffffu;
-					if (target != last_target) { last_g = group_index(os.assay, target); last_target = target; }
-					if (last_g >= 0) ++group_count[(size_t)last_g]; // groups of one assay are touched by one thread only
-				}
-			}
-		};
-		if (nt == 1) count(0);
-		else {
-			std::vector<std::thread> pool;
-			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(count, t);
-			for (std::thread &t : pool) t.join();
-		}
-		for (size_t g = 0; g < groups.size(); ++g) group_seeds[g].reserve(group_count[g]);
-		auto fill = [&](unsigned t) {
-			for (const CandSpan &sp : spans) {
-				const OligoStrand &os = set.os[sp.os];
-				if ((unsigned)os.assay % nt != t) continue;
-				const int cat = os.role == TNT_OLIGO_P ? (os.plus ? 5 : 4) : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0);
 				long last_g = -1;
 				uint32_t last_target = 0xffffffffu;
 				for (uint64_t i = sp.out_off; i < sp.out_off + sp.count; ++i) {
@@ -1927,27 +1917,64 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 					const uint32_t target = sd.target_k & 0xffffffu;
 					if (target != last_target) { last_g = group_index(os.assay, target); last_target = target; }
 					if (last_g < 0) continue;
-					ReplaySeed r;
-					r.cat = cat;
-					r.q = sd.target_k >> 24;
-					r.t = sd.t;
+					seed_group[i] = (int32_t)last_g;
 					const std::vector<Key> &sk = group_sites[(size_t)last_g];
-					r.site = -1;
 					if (!sk.empty()) {
 						const Key k{sp.os, sd.t, sd.target_k >> 24, 0};
 						const auto it = std::lower_bound(sk.begin(), sk.end(), k, key_less);
-						if (it != sk.end() && !key_less(k, *it)) r.site = it->idx;
+						if (it != sk.end() && !key_less(k, *it)) seed_site[i] = it->idx;
 					}
-					group_seeds[(size_t)last_g].push_back(r);
 				}
 			}
 		};
-		if (nt == 1) fill(0);
+		if (nt == 1) label(0);
 		else {
 			std::vector<std::thread> pool;
-			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(fill, t);
+			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(label, t);
 			for (std::thread &t : pool) t.join();
 		}
+	}
+	t_part.reset(new HostTimer("  replay: grouping (sort)"));
+	// counting sort by group; every thread owns a range of groups (it reads all labels, which is cheap and
+	// sequential, and writes only inside its own part of the sorted array)
+	std::vector<uint64_t> group_start(groups.size() + 1, 0);
+	std::vector<ReplaySeed> &flat_seeds = e->h_flat_seeds;
+	{
+		const unsigned nt = nseeds < 200000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		auto run = [&](const std::function<void(unsigned)> &f) {
+			if (nt == 1) { f(0); return; }
+			std::vector<std::thread> pool;
+			for (unsigned t = 0; t < nt; ++t) pool.emplace_back(f, t);
+			for (std::thread &t : pool) t.join();
+		};
+		auto g_lo = [&](unsigned t) { return (int32_t)(groups.size()*(size_t)t/nt); };
+		run([&](unsigned t) {
+			const int32_t g0 = g_lo(t), g1 = g_lo(t + 1);
+			for (uint64_t i = 0; i < nseeds; ++i) {
+				const int32_t g = seed_group[i];
+				if (g >= g0 && g < g1) ++group_start[(size_t)g + 1];
+			}
+		});
+		for (size_t g = 0; g < groups.size(); ++g) group_start[g + 1] += group_start[g];
+		flat_seeds.resize(group_start[groups.size()]);
+		run([&](unsigned t) {
+			const int32_t g0 = g_lo(t), g1 = g_lo(t + 1);
+			if (g0 == g1) return;
+			std::vector<uint64_t> fill(group_start.begin() + g0, group_start.begin() + g1);
+			for (const CandSpan &sp : spans) {
+				const OligoStrand &os = set.os[sp.os];
+				const int cat = os.role == TNT_OLIGO_P ? (os.plus ? 5 : 4) : (os.plus ? 2 : 0) + (os.role == TNT_OLIGO_R ? 1 : 0);
+				for (uint64_t i = sp.out_off; i < sp.out_off + sp.count; ++i) {
+					const int32_t g = seed_group[i];
+					if (g < g0 || g >= g1) continue;
+					ReplaySeed &r = flat_seeds[fill[(size_t)(g - g0)]++];
+					r.cat = cat;
+					r.q = seeds[i].target_k >> 24;
+					r.t = seeds[i].t;
+					r.site = seed_site[i];
+				}
+			}
+		});
 	}
 	// the groups are independent: a few host threads when there are many, results in group order
 	t_part.reset(new HostTimer("  replay: list operations"));
@@ -1960,7 +1987,8 @@ void replay_groups(tnt_engine *e, const tnt_search_options &o, const AssembleOpt
 		try {
 			for (size_t gidx = t*per; gidx < std::min(groups.size(), (t + 1)*per); ++gidx) {
 				const AssayHost &as = e->assays[(size_t)groups[gidx].assay];
-				replay_pcr_group(std::move(group_seeds[gidx]), sites, ao, !as.P.empty(), groups[gidx].assay, as.id, part_hits[t], part_refs[t]);
+				replay_pcr_group(std::vector<ReplaySeed>(flat_seeds.begin() + (ptrdiff_t)group_start[gidx], flat_seeds.begin() + (ptrdiff_t)group_start[gidx + 1]),
+					sites, ao, !as.P.empty(), groups[gidx].assay, as.id, part_hits[t], part_refs[t]);
 			}
 		}
 		catch (const std::exception &ex) { errors[t] = ex.what(); }
