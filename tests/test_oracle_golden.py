@@ -323,3 +323,72 @@ def test_dinkelbach_vs_compiled_reference(dinkelbach_oracle, ref):
             assert n >= 3, kind
     finally:
         ref.set_dinkelbach(False)
+
+
+def test_filter_cascade_vs_compiled_reference(oracle, ref):
+    """Every bound of the reference's filter cascade, alone and in combinations (the cases of
+    tests/test_gpu_parity.py::test_search_filter_cascade): the oracle's hit lists equal the compiled
+    reference's, floats bit for bit -- the GPU test compares the engine with the oracle on the same cases."""
+    from test_gpu_parity import FILTER_CASES
+    total = 0
+    for case, extra in enumerate(FILTER_CASES):
+        kw = dict(min_primer_tm=36.0, min_probe_tm=36.0)
+        kw.update(extra)
+        rng = np.random.default_rng(5000 + case)
+        db = [gen.random_codes(int(rng.integers(20000, 40000)), rng) for _ in range(3)]
+        gen.sprinkle_degenerate(db[1], rng, frac=2e-3, n_runs_per_50kb=6)
+        taq = gen.make_assays(rng, db, 4, "taqman", variants=5)
+        prb = gen.make_assays(rng, db, 2, "probe", variants=5)
+        for assays, fmt in ((taq, H.ASSAY_PCR), (prb, H.ASSAY_PROBE)):
+            o = H.default_options(assay_format=fmt, **kw)
+            for codes in db:
+                for a in assays:
+                    x, y = ref.search(codes, a[0], a[1], a[2], o), oracle.search(codes, a[0], a[1], a[2], o)
+                    assert [(h.exact_key(), h.floats()) for h in x] == [(h.exact_key(), h.floats()) for h in y], (case, fmt)
+                    total += len(x)
+    assert total > 200
+
+
+def test_overhanging_probe_sites_vs_compiled_reference(oracle, ref):
+    """Probe sites cut by a fragment end keep coordinates beyond the fragment and their text is read from the
+    clamped end for the full length (probe_search.cpp:129-142, :205-219): the oracle's restatement of that quirk
+    against the compiled reference (the GPU test of the same name compares the engine with the oracle)."""
+    rng = np.random.default_rng(31337)
+    P = gen.rand_oligo(38, rng)
+    site = gen.revcomp(P)
+    n_over = 0
+    for strand_text in (site, P):
+        n = 9000
+        codes = gen.random_codes(n, rng)
+        gen.plant(codes, n - 26, strand_text[:26])
+        gen.plant(codes, 0, strand_text[10:])
+        gen.plant(codes, 4000, strand_text)
+        o = H.default_options(assay_format=H.ASSAY_PROBE, min_probe_tm=30.0)
+        x, y = ref.search(codes, None, None, P, o), oracle.search(codes, None, None, P, o)
+        assert [(h.exact_key(), h.floats()) for h in x] == [(h.exact_key(), h.floats()) for h in y]
+        n_over += sum(1 for h in x if h.probe_first < 0 or h.probe_last >= n)
+    assert n_over >= 2
+
+
+@pytest.mark.parametrize("W", [4, 5, 6, 8])
+def test_word_sizes_vs_compiled_reference(oracle, ref, W):
+    """Hash word sizes other than 7: seeds and searches of the oracle against the compiled reference
+    (W = 3 is equal as well; with 64 keys nearly every position is a seed and the case runs for minutes)."""
+    rng = np.random.default_rng(1000 + W)
+    n = 12000 if W <= 5 else 60000
+    db = [gen.random_codes(n, rng), gen.random_codes(n // 2 + 37, rng), gen.random_codes(6145, rng)]
+    gen.sprinkle_degenerate(db[0], rng, frac=1e-3, n_runs_per_50kb=4)
+    assays = gen.make_assays(rng, db, 3, "taqman", variants=3)
+    o = H.default_options(min_primer_tm=42.0, min_probe_tm=42.0, word_size=W)
+    nseeds = nhits = 0
+    for codes in db:
+        for oligo in (assays[0][0], assays[0][0][:9] + "N" + assays[0][0][10:]):
+            for plus in (False, True):
+                a, b = ref.seeds(codes, oligo, W, plus, unique=True), oracle.seeds(codes, oligo, W, plus, unique=True)
+                assert a == b, (W, oligo, plus)
+                nseeds += len(a)
+        for a in assays:
+            x, y = ref.search(codes, a[0], a[1], a[2], o), oracle.search(codes, a[0], a[1], a[2], o)
+            assert [(h.exact_key(), h.floats()) for h in x] == [(h.exact_key(), h.floats()) for h in y], W
+            nhits += len(x)
+    assert nseeds > 20 and nhits >= 3
