@@ -1,14 +1,14 @@
 """Randomised differential of the device FASTA reader (tnt_engine_add_fasta) against the oracle's restatement of
 the reference reader: random texts (line widths, CR LF, blank lines, lower case, IUPAC, stray blanks, '*', '-',
 '>' inside lines, tabs, no final newline, records of length 0) x random fragment settings.  Run by hand on a GPU
-box: python tools/fuzz_fasta.py [seconds] [seed]"""
+box: python tests/fuzz_fasta.py [seconds] [seed]"""
 import os
 import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import numpy as np  # noqa: E402
 

@@ -1,7 +1,7 @@
 """Randomised differential of the engine against the oracle (tests/harness.py): many small searches with
 random assay formats, word sizes, temperatures, salt, bounds, clamps and strand settings.  Not a test of the
 suite (those use fixed seeds); a wider net run by hand on a GPU box:
-    python tools/fuzz_parity.py [seconds] [seed]
+    python tests/fuzz_parity.py [seconds] [seed]
 Prints one line per mismatch and a summary; exit code 1 when anything differed."""
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import numpy as np  # noqa: E402
 

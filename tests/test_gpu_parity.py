@@ -931,7 +931,7 @@ def test_other_word_sizes(engine_lib, oracle, monkeypatch, W, mode):
     and searches equal to the oracle through every scan kernel (table sizes 4^W = 256 ... 65536 keys: the
     rank-compressed shared-memory table, the sparse group bitmap and the region scan all depend on W).
     Short words in the sparse kernel overflow its group queue, i.e. take its position-by-position path, on
-    fragments whose length is no multiple of 32 (found by tools/fuzz_parity.py: that loop must keep the warp
+    fragments whose length is no multiple of 32 (found by tests/fuzz_parity.py: that loop must keep the warp
     together)."""
     from thermonucleotideblast_b200 import Assay, Engine
     if mode != "auto":
@@ -1021,7 +1021,7 @@ def test_search_filter_cascade(engine_lib, oracle, case):
 def test_probe_sites_overhanging_the_fragment_ends(engine_lib, oracle):
     """A probe site cut by the end (or the start) of a fragment keeps coordinates beyond the fragment, and the
     reference prints its text from the clamped end for the full length (probe_search.cpp:129-142, :205-219):
-    bases outside [probe_first, probe_last].  Found by tools/fuzz_parity.py (the text fetch threw)."""
+    bases outside [probe_first, probe_last].  Found by tests/fuzz_parity.py (the text fetch threw)."""
     from thermonucleotideblast_b200 import Assay, Engine
     rng = np.random.default_rng(31337)
     P = gen.rand_oligo(38, rng)
